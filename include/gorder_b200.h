@@ -1,0 +1,307 @@
+/*
+ * gorder_b200.h — C ABI of the B200-native per-frame order-parameter engine.
+ *
+ * This is the drop-in boundary for gorder's hot path.  The reference has
+ * no FFI today; the seam this ABI replaces is the generic frame loop
+ *
+ *     system.traj_iter_map_reduce::<Reader, SystemTopology, AnalysisError>(
+ *         file, n_threads, analyze_frame, topology, Some("Master"), begin, end, step, ..)
+ *                                                   reference: src/analysis/common.rs:283-339
+ *     fn analyze_frame(frame: &System, data: &mut SystemTopology) -> Result<(), AnalysisError>
+ *                                                   reference: src/analysis/common.rs:201-235
+ *     impl ParallelTrajData for SystemTopology { reduce, initialize }
+ *                                                   reference: src/analysis/topology/mod.rs:256-278
+ *
+ * Host side (Rust, unchanged) classifies molecules once, then
+ *   gorder_gpu_create()   replaces SystemTopology::new + per-thread clone   (topology/mod.rs:70-118)
+ *   gorder_gpu_submit()   replaces analyze_frame() for a batch of frames    (common.rs:201-235)
+ *   gorder_gpu_finish()   replaces ParallelTrajData::reduce + the Add chain (topology/mod.rs:236-272)
+ *   gorder_gpu_destroy()  drops the state
+ * and back-fills AnalysisOrder / Map / AssignedLeaflets / NormalsStorage from GorderResults
+ * before calling the untouched converter (presentation/converter.rs:52).
+ *
+ * Plain C: pointers + sizes only, no torch / CUDA types in the signatures.  All arrays passed
+ * to gorder_gpu_create() are copied; the caller may free them when the call returns.
+ *
+ * Index convention: every atom index in this file is a "slot" = position of the atom inside the
+ * coordinate frame handed to gorder_gpu_submit (the reference's Master group, common.rs:92-103,
+ * renumbered densely by the host, or simply the absolute atom index when whole frames are passed).
+ * Molecules of one molecule type are congruent (topology/molecule.rs:224-244), so an atom of
+ * molecule m is addressed as  mol_base[m] + relative_index  (bond.rs:87-99).
+ */
+#ifndef GORDER_B200_H
+#define GORDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GORDER_ABI_VERSION 1
+
+/* ---- enums (int32 in the structs) ------------------------------------------------------- */
+
+/* AnalysisType, reference: src/input/analysis.rs (AAOrder / CGOrder / UAOrder). AA and CG share
+ * the bond engine (topology/bond.rs); UA uses the virtual-hydrogen engine (uaorder.rs). */
+enum { GORDER_KIND_AA = 0, GORDER_KIND_CG = 1, GORDER_KIND_UA = 2 };
+
+/* Axis, reference: src/input/axis.rs */
+enum { GORDER_AXIS_X = 0, GORDER_AXIS_Y = 1, GORDER_AXIS_Z = 2 };
+
+/* MembraneNormal, reference: src/input/membrane_normal.rs, analysis/normal.rs:31-35 */
+enum { GORDER_NORMAL_STATIC = 0, GORDER_NORMAL_DYNAMIC = 1, GORDER_NORMAL_MANUAL = 2 };
+
+/* LeafletClassification, reference: src/analysis/leaflets.rs:208-217. MANUAL covers FromFile /
+ * FromMap / FromNdx / Clustering / SphericalClustering: the host computes the table. */
+enum {
+    GORDER_LEAFLET_NONE = 0,
+    GORDER_LEAFLET_GLOBAL = 1,
+    GORDER_LEAFLET_LOCAL = 2,
+    GORDER_LEAFLET_INDIVIDUAL = 3,
+    GORDER_LEAFLET_MANUAL = 4
+};
+
+/* Frequency, reference: src/input/frequency.rs; leaflets.rs:435-441 */
+enum { GORDER_FREQ_EVERY = 0, GORDER_FREQ_ONCE = 1 };
+
+/* Geometry, reference: src/analysis/geometry.rs:288,372,456 */
+enum { GORDER_GEOM_NONE = 0, GORDER_GEOM_CUBOID = 1, GORDER_GEOM_CYLINDER = 2, GORDER_GEOM_SPHERE = 3 };
+
+/* GeomReference, reference: src/input/geometry.rs (Point / Selection / Center) */
+enum { GORDER_GEOMREF_POINT = 0, GORDER_GEOMREF_SELECTION = 1, GORDER_GEOMREF_BOX_CENTER = 2 };
+
+/* Plane, reference: src/input/ordermap.rs:44-50. NOTE YZ projects to (z, y). */
+enum { GORDER_PLANE_XY = 0, GORDER_PLANE_XZ = 1, GORDER_PLANE_YZ = 2 };
+
+/* united-atom carbon kinds, reference: src/analysis/uaorder.rs:234-239 */
+enum { GORDER_UA_CH3 = 0, GORDER_UA_CH2 = 1, GORDER_UA_CH1_UNSAT = 2, GORDER_UA_CH1_SAT = 3 };
+
+/* Leaflet value in every table of this ABI: the reference's export convention (lib.rs:416-422). */
+enum { GORDER_LOWER = 0, GORDER_UPPER = 1 };
+
+/* Index of the three accumulators kept per order slot (bond.rs:221-247). */
+enum { GORDER_TOTAL = 0, GORDER_ACC_UPPER = 1, GORDER_ACC_LOWER = 2 };
+
+/* Error codes; 1:1 with AnalysisError (reference: src/errors.rs:121-169) + device errors. */
+enum {
+    GORDER_OK = 0,
+    GORDER_ERR_UNDEFINED_BOX = 1,              /* AnalysisError::UndefinedBox */
+    GORDER_ERR_NOT_ORTHOGONAL_BOX = 2,         /* AnalysisError::NotOrthogonalBox */
+    GORDER_ERR_ZERO_BOX = 3,                   /* AnalysisError::ZeroBox */
+    GORDER_ERR_UNDEFINED_POSITION = 4,         /* AnalysisError::UndefinedPosition(idx): NaN coordinate */
+    GORDER_ERR_INVALID_GLOBAL_CENTER = 5,      /* AnalysisError::InvalidGlobalMembraneCenter */
+    GORDER_ERR_INVALID_LOCAL_CENTER = 6,       /* AnalysisError::InvalidLocalMembraneCenter(head) */
+    GORDER_ERR_MANUAL_LEAFLET_FRAME = 7,       /* ManualLeafletClassificationError::FrameNotFound */
+    GORDER_ERR_DYNAMIC_NORMAL_POINTS = 8,      /* DynamicNormalError::NotEnoughPoints(n) */
+    GORDER_ERR_DYNAMIC_NORMAL_SVD = 9,         /* DynamicNormalError::SVDFailed */
+    GORDER_ERR_MANUAL_NORMAL_FRAME = 10,       /* ManualNormalError::FrameNotFound */
+    GORDER_ERR_LEAFLET_FRAME_UNAVAILABLE = 11, /* shard does not hold the assignment frame (leaflets.rs:1529) */
+    GORDER_ERR_ORDER_OVERFLOW = 12,            /* OrderValue overflowed (order.rs:47-60 panic) */
+    GORDER_ERR_INVALID_ARGUMENT = 20,
+    GORDER_ERR_ORDERMAP_BIN_TOO_LARGE = 21,    /* OrderMapConfigError::BinTooLarge */
+    GORDER_ERR_ORDERMAP_NO_BOX = 22,           /* OrderMapConfigError::InvalidBoxAuto */
+    GORDER_ERR_NO_DEVICE = 30,                 /* no usable CUDA device: there is NO CPU fallback */
+    GORDER_ERR_CUDA = 31,
+    GORDER_ERR_OUT_OF_MEMORY = 32
+};
+
+/* ---- setup ------------------------------------------------------------------------------ */
+
+/* One molecule type (reference: topology/molecule.rs:147-169 MoleculeType<O>). */
+typedef struct GorderMolType {
+    int32_t n_molecules;
+    const int32_t *mol_base;   /* [n_molecules] slot of relative index 0 of every molecule */
+
+    /* AA / CG: bond types in the reference's sorted order (bond.rs:77-81); rel1 < rel2 so that
+     * the vector goes from the lower to the higher absolute index (bond.rs:298-302). */
+    int32_t n_bond_types;
+    const int32_t *bond_rel;   /* [n_bond_types][2] */
+
+    /* UA: carbon types sorted by relative index (topology/uatom.rs:39-41).
+     * ua_rel[i] = {target, helper1, helper2, helper3}; helper3 = -1 unless CH1_SAT.
+     * Roles as in uaorder.rs:911-915 (AtomTriplet) and :1050-1056 (AtomQuadruplet). */
+    int32_t n_ua_atoms;
+    const int32_t *ua_kind;    /* [n_ua_atoms] GORDER_UA_* */
+    const int32_t *ua_rel;     /* [n_ua_atoms][4] */
+
+    /* leaflets: head identifier (leaflets.rs:575,633,740) and methyls (leaflets.rs:743), relative */
+    int32_t head_rel;          /* -1 if unused */
+    int32_t n_methyls;
+    const int32_t *methyl_rel; /* [n_methyls] */
+
+    /* dynamic normals: this molecule's reference head (normal.rs:136), relative; -1 if unused */
+    int32_t normal_head_rel;
+
+    /* GORDER_LEAFLET_MANUAL: [n_manual_leaflet_frames][n_molecules], GORDER_UPPER / GORDER_LOWER,
+     * BEFORE flip (leaflets.rs:816-874). Row = frame_index / real_frequency (0 for Once). */
+    int32_t n_manual_leaflet_frames;
+    const uint8_t *manual_leaflets;
+
+    /* GORDER_NORMAL_MANUAL: [n_manual_normal_frames][n_molecules][3] (normal.rs:259-298).
+     * Row = frame_index / step. */
+    int32_t n_manual_normal_frames;
+    const float *manual_normals;
+} GorderMolType;
+
+typedef struct GorderSetup {
+    int32_t abi_version;       /* GORDER_ABI_VERSION */
+    int32_t kind;              /* GORDER_KIND_* */
+    int32_t n_atoms;           /* slots per frame */
+    int32_t handle_pbc;        /* Analysis::handle_pbc (common.rs:207): 1 = PBC3D, 0 = NoPBC */
+    int32_t step;              /* Analysis::step; frame_index passed to submit is a multiple of it */
+
+    int32_t n_moltypes;
+    const GorderMolType *moltypes;
+
+    /* membrane normal (normal.rs:31-72) */
+    int32_t normal_mode;       /* GORDER_NORMAL_* */
+    int32_t normal_axis;       /* STATIC: GORDER_AXIS_* */
+    float dynamic_radius;      /* DYNAMIC: radius of the head cloud, nm (normal.rs:140) */
+    int32_t n_normal_heads;    /* DYNAMIC: group "NormalHeads" (common.rs:173-183): all atoms of it */
+    const int32_t *normal_heads;
+    int32_t collect_normals;   /* DYNAMIC: keep per-frame normals for export (normal.rs:211-227) */
+
+    /* leaflets (leaflets.rs:208-330) */
+    int32_t leaflet_mode;      /* GORDER_LEAFLET_* */
+    int32_t leaflet_axis;      /* membrane normal used by the classifier (leaflets.rs:241-255) */
+    int32_t leaflet_freq_kind; /* GORDER_FREQ_* */
+    int32_t leaflet_freq;      /* EVERY: real frequency = configured frequency x step (leaflets.rs:261-262) */
+    int32_t leaflet_flip;      /* leaflets.rs:68-73 */
+    float leaflet_radius;      /* LOCAL: cylinder radius, nm */
+    int32_t n_membrane;        /* GLOBAL / LOCAL: group "Membrane" */
+    const int32_t *membrane;
+    int32_t collect_leaflets;  /* keep assignment tables of every assignment frame for export */
+
+    /* geometry selection (geometry.rs) */
+    int32_t geom_kind;         /* GORDER_GEOM_* */
+    int32_t geom_invert;
+    int32_t geom_ref_kind;     /* GORDER_GEOMREF_* */
+    float geom_ref_point[3];   /* POINT */
+    int32_t n_geom_ref;        /* SELECTION: group "GeomReference" */
+    const int32_t *geom_ref;
+    float geom_dims[6];        /* CUBOID: xmin,xmax,ymin,ymax,zmin,zmax (+-INFINITY allowed);
+                                  CYLINDER: radius, span_min, span_max;  SPHERE: radius */
+    int32_t geom_axis;         /* CYLINDER orientation */
+
+    /* order maps (ordermap.rs:40-96). Spans are resolved by the host exactly as Map::new does
+     * (auto span = box of the structure file). */
+    int32_t map_enabled;
+    int32_t map_plane;         /* GORDER_PLANE_* */
+    float map_span_x[2];       /* span of the first projected coordinate */
+    float map_span_y[2];
+    float map_bin[2];
+
+    /* error estimation / convergence: keep per-frame sums (order.rs:83-88, timewise.rs:131-140) */
+    int32_t timewise;
+
+    /* engine knobs (no reference counterpart) */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t max_batch_frames;  /* frames per launch; 0 = default */
+} GorderSetup;
+
+/* ---- results ---------------------------------------------------------------------------- */
+
+/* Order slots: one per bond type (AA/CG) or per virtual C-H bond (UA: CH3 -> 3 slots, CH2 -> 2,
+ * CH1 -> 1; uaorder.rs:253-272), concatenated over molecule types in input order.
+ * All integer sums are the reference's fixed-point OrderValue (order.rs:13-26): round(S * 1e6). */
+typedef struct GorderResults {
+    int64_t n_slots;           /* out: total order slots */
+    int64_t n_frames;          /* out: SystemTopology::total_frames (topology/mod.rs:49) */
+    int64_t n_map_bins;        /* out: nx * ny (0 if maps disabled) */
+    int64_t map_nx, map_ny;    /* out */
+    int64_t n_leaflet_frames;  /* out: number of assignment frames held (collect_leaflets) */
+    int64_t n_molecules_total; /* out: sum of n_molecules over molecule types */
+
+    /* caller-allocated (may be NULL to skip); filled by gorder_gpu_finish / gorder_gpu_results */
+    int64_t *sum;              /* [n_slots][3]   AnalysisOrder::order      (order.rs:73) */
+    uint64_t *count;           /* [n_slots][3]   AnalysisOrder::n_samples  (order.rs:76) */
+    int64_t *tw_sum;           /* [n_frames][n_slots][3]  TimeWiseData::order     (timewise.rs:134) */
+    uint64_t *tw_count;        /* [n_frames][n_slots][3]  TimeWiseData::n_samples (timewise.rs:136) */
+    int64_t *tw_frame_index;   /* [n_frames] frame_index of each row (ascending) */
+    int64_t *map_sum;          /* [n_slots][3][n_map_bins]  Map::values  (ordermap.rs:27), x-major */
+    uint64_t *map_count;       /* [n_slots][3][n_map_bins]  Map::samples (ordermap.rs:30) */
+    uint8_t *leaflets;         /* [n_leaflet_frames][n_molecules_total] GORDER_UPPER/LOWER after flip */
+    int64_t *leaflet_frame_index; /* [n_leaflet_frames] */
+    float *normals;            /* [n_frames][n_molecules_total][3], NaN where not computed (normal.rs:217) */
+} GorderResults;
+
+typedef struct GorderHandle GorderHandle;
+
+/* ---- entry points ----------------------------------------------------------------------- */
+
+/* Build device state from the classified topology. Fails with GORDER_ERR_NO_DEVICE when no CUDA
+ * device is usable: there is no CPU fallback in this library. */
+int gorder_gpu_create(const GorderSetup *setup, GorderHandle **out);
+
+/* Analyse n_frames frames (replaces n_frames calls of analyze_frame, common.rs:201-235).
+ *   xyz         [n_frames][n_atoms][3] f32, nm, host memory (pinned memory makes the copy async);
+ *               NaN marks an undefined position (-> GORDER_ERR_UNDEFINED_POSITION)
+ *   box         [n_frames][3] orthogonal box lengths, nm; ignored if !handle_pbc.
+ *               box validity (check_box, common.rs:186-198) is the host's job; an all-zero box
+ *               is still rejected here with GORDER_ERR_ZERO_BOX.
+ *   frame_index [n_frames] SystemTopology::frame of each frame (topology/mod.rs:41-43), i.e.
+ *               (ordinal of the trajectory frame since `begin`), a multiple of `step`, strictly
+ *               increasing across calls.
+ * Returns when the batch has been queued and the input buffers may be reused. Errors detected on
+ * the device are reported by a later submit or by finish (first error wins, as in the reference). */
+int gorder_gpu_submit(GorderHandle *h, const float *xyz, const float *box,
+                      const int64_t *frame_index, int32_t n_frames);
+
+/* Same, with frames already resident in device memory in the same [n_frames][n_atoms][3] layout. */
+int gorder_gpu_submit_device(GorderHandle *h, const float *d_xyz, const float *d_box,
+                             const int64_t *frame_index, int32_t n_frames);
+
+/* Device-native frame layout ("planes"): frame_floats floats per frame; atom slot s,
+ * component c lives at plane_offset[s] + c * plane_cstride[s]. A host that fills its pinned
+ * buffers through this map (the Rust shim's per-frame copy of the Master group is a gather
+ * anyway) can skip the device-side re-layout pass. */
+int gorder_gpu_native_layout(GorderHandle *h, int64_t *frame_floats,
+                             int32_t *plane_offset /* [n_atoms] or NULL */,
+                             int32_t *plane_cstride /* [n_atoms] or NULL */);
+int gorder_gpu_submit_native(GorderHandle *h, const float *planes_host, const float *box,
+                             const int64_t *frame_index, int32_t n_frames);
+int gorder_gpu_submit_native_device(GorderHandle *h, const float *d_planes, const float *d_box,
+                                    const int64_t *frame_index, int32_t n_frames);
+
+/* Seed the leaflet assignment used until the next assignment frame (Frequency::Once on a shard
+ * that does not own frame 0: SURVEY.md §8e). table: [n_molecules_total] after flip. */
+int gorder_gpu_set_leaflets(GorderHandle *h, const uint8_t *table, int64_t frame_index);
+
+/* Wait for all queued work, report the first deferred error. */
+int gorder_gpu_sync(GorderHandle *h);
+
+/* Sizes needed to allocate GorderResults arrays (fills the scalar "out" fields only). */
+int gorder_gpu_result_sizes(GorderHandle *h, GorderResults *r);
+
+/* Blocks; copies accumulators into the caller's arrays (replaces ParallelTrajData::reduce for the
+ * single-GPU case). May be called more than once. */
+int gorder_gpu_finish(GorderHandle *h, GorderResults *r);
+
+/* Multi-GPU: the integer accumulators of this handle as ONE contiguous device block so that the
+ * host can combine shards with a single NCCL sum-reduce. Layout: int64 words,
+ *   [sum n_slots*3][count n_slots*3][map_sum n_slots*3*n_map_bins][map_count ...]
+ * gorder_gpu_finish() reads the block back, so reduce first, then finish on the root. */
+int gorder_gpu_accumulator_block(GorderHandle *h, void **d_ptr, int64_t *n_words);
+
+/* Counters for benchmarking: kernels launched by this handle and samples accumulated so far. */
+int gorder_gpu_stats(GorderHandle *h, int64_t *kernel_launches, int64_t *frames);
+
+/* CUDA stream all work of this handle is queued on (as void*), for event timing by the caller. */
+void *gorder_gpu_stream(GorderHandle *h);
+
+/* Human-readable detail of the last error of this handle (offending atom index etc.). */
+int gorder_gpu_last_error(GorderHandle *h, char *buf, size_t len);
+
+/* Offending index / count attached to the first deferred device error (e.g. atom slot). */
+int64_t gorder_gpu_error_detail(GorderHandle *h);
+
+void gorder_gpu_destroy(GorderHandle *h);
+
+const char *gorder_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GORDER_B200_H */
