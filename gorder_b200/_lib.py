@@ -1,0 +1,57 @@
+"""Loader of the C-ABI shared library.  Fails loudly: there is no Python / CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import abi
+from .build import SO_PATH
+
+_LIB = None
+
+#: every symbol ``include/gorder_b200.h`` declares
+SYMBOLS = [
+    "gorder_gpu_create", "gorder_gpu_submit", "gorder_gpu_submit_device", "gorder_gpu_native_layout",
+    "gorder_gpu_submit_native", "gorder_gpu_submit_native_device", "gorder_gpu_set_leaflets", "gorder_gpu_sync",
+    "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block", "gorder_gpu_stats",
+    "gorder_gpu_stream", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
+]
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            f"{SO_PATH} is missing: build it with `python -m gorder_b200.build` "
+            "(or __graft_entry__.build()).  gorder_b200 has no CPU fallback.")
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.gorder_gpu_create.argtypes = [C.POINTER(abi.CGorderSetup), C.POINTER(vp)]
+    L.gorder_gpu_submit.argtypes = [vp, vp, vp, vp, i32]
+    L.gorder_gpu_submit_device.argtypes = [vp, vp, vp, vp, i32]
+    L.gorder_gpu_native_layout.argtypes = [vp, C.POINTER(i64), vp, vp]
+    L.gorder_gpu_submit_native.argtypes = [vp, vp, vp, vp, i32]
+    L.gorder_gpu_submit_native_device.argtypes = [vp, vp, vp, vp, i32]
+    L.gorder_gpu_set_leaflets.argtypes = [vp, vp, i64]
+    L.gorder_gpu_sync.argtypes = [vp]
+    L.gorder_gpu_result_sizes.argtypes = [vp, C.POINTER(abi.CGorderResults)]
+    L.gorder_gpu_finish.argtypes = [vp, C.POINTER(abi.CGorderResults)]
+    L.gorder_gpu_accumulator_block.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.gorder_gpu_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.gorder_gpu_stream.argtypes = [vp]
+    L.gorder_gpu_stream.restype = vp
+    L.gorder_gpu_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.gorder_gpu_error_detail.argtypes = [vp]
+    L.gorder_gpu_error_detail.restype = i64
+    L.gorder_gpu_destroy.argtypes = [vp]
+    L.gorder_gpu_destroy.restype = None
+    L.gorder_gpu_version.restype = C.c_char_p
+    for name in ("gorder_gpu_create", "gorder_gpu_submit", "gorder_gpu_submit_device", "gorder_gpu_native_layout",
+                 "gorder_gpu_submit_native", "gorder_gpu_submit_native_device", "gorder_gpu_set_leaflets",
+                 "gorder_gpu_sync", "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block",
+                 "gorder_gpu_stats", "gorder_gpu_last_error"):
+        getattr(L, name).restype = C.c_int
+    _LIB = L
+    return L

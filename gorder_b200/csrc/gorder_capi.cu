@@ -1,0 +1,885 @@
+// gorder_capi.cu — host side of the engine and its C ABI (include/gorder_b200.h).
+//
+// Replaces, behind the reference's frame loop (src/analysis/common.rs:283-339):
+//   SystemTopology::new / clone per worker   -> gorder_gpu_create      (topology/mod.rs:70-118)
+//   analyze_frame                            -> gorder_gpu_submit*     (common.rs:201-235)
+//   ParallelTrajData::reduce + Add chain     -> gorder_gpu_finish      (topology/mod.rs:236-272)
+// There is NO CPU fallback: every entry point fails with GORDER_ERR_NO_DEVICE / GORDER_ERR_CUDA
+// when the device is not usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gorder_kernels.cuh"
+
+using namespace gorder;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            h->set_error(e__ == cudaErrorMemoryAllocation ? GORDER_ERR_OUT_OF_MEMORY : GORDER_ERR_CUDA,   \
+                         std::string(#call) + ": " + cudaGetErrorString(e__));                           \
+            return h->err_code;                                                                          \
+        }                                                                                                \
+    } while (0)
+
+}  // namespace
+
+struct GorderHandle {
+    // ---- configuration (deep copy) ----
+    GorderSetup s{};
+    std::vector<TypeDesc> types;
+    std::vector<std::vector<int32_t>> mol_base;       // per type (for error decoding)
+    std::vector<std::vector<int32_t>> used_rel;       // per type: used relative atoms (sorted)
+    std::vector<std::vector<int32_t>> item_slots;     // per type, per item: the atom slots (rel) involved
+    std::vector<int32_t> slot_off, slot_cs;
+    std::vector<int> molpad_type_h;
+    int n_slots = 0, n_molpad = 0, n_mol_total = 0, n_chunks = 0, mpt = 1;
+    long long frame_floats = 0;
+    int max_batch = 0;
+    bool leaf = false, extra = false, nvec = false, ua = false;
+
+    // ---- device ----
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    DeviceView view{};
+    std::vector<void *> owned;   // freed at destroy
+    int *d_slot_off = nullptr, *d_slot_cs = nullptr, *d_molpad_type = nullptr;
+    int *d_err = nullptr;
+    long long *d_err_detail = nullptr;
+
+    // accumulator block: [tot_sum n*3][tot_cnt n*3][map_sum n*3*bins][map_cnt n*3*bins] (int64 words)
+    long long *d_block = nullptr;
+    long long block_words = 0;
+    long long *d_tot_sum = nullptr;
+    unsigned long long *d_tot_cnt = nullptr;
+    long long *d_map_sum = nullptr;
+    unsigned long long *d_map_cnt = nullptr;
+
+    // per-frame accumulators: ring of max_batch rows, or (timewise) all frames
+    long long *d_bsum = nullptr;
+    unsigned long long *d_bcnt = nullptr;
+    long long tw_cap = 0;
+    std::vector<long long> frame_index_done;   // frame_index of every analysed frame, in order
+
+    // staging (2-deep)
+    float *d_xyz[2] = {nullptr, nullptr};
+    float *d_planes[2] = {nullptr, nullptr};
+    float *d_box[2] = {nullptr, nullptr};
+    FrameAux *h_aux[2] = {nullptr, nullptr};
+    FrameAux *d_aux[2] = {nullptr, nullptr};
+    int *h_list[2] = {nullptr, nullptr};   // [2*max_batch]: assign list, all list
+    int *d_list[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};   // compute done with staging slot
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    int cur = 0;
+
+    // leaflets
+    unsigned char *d_leaf_rows = nullptr;   // [(1 + max_batch)][n_molpad]
+    bool have_leaflets = false;
+    long long cur_leaflet_frame = -1;
+    unsigned char *d_leaf_collect = nullptr;
+    long long leaf_collect_cap = 0, n_leaf_collected = 0;
+    std::vector<long long> leaf_frame_index;
+
+    // normals
+    float *d_normals = nullptr;          // [max_batch][3][n_molpad]
+    int *d_normal_npoints = nullptr;     // [max_batch][n_molpad]
+    unsigned char *d_normal_used = nullptr;   // [max_batch][n_molpad] (only geometry + collect)
+    float *d_normals_collect = nullptr;  // [cap][3][n_molpad]
+    unsigned char *d_used_collect = nullptr;
+    long long normals_collect_cap = 0;
+
+    // centres
+    float *d_est = nullptr, *d_center = nullptr;   // [max_batch*3]
+    double *d_partial = nullptr;                   // [max_batch][kCenterBlocks][6]
+
+    long long n_frames = 0;
+    long long n_launches = 0;
+    long long last_frame_index = -1;
+
+    // error state
+    int err_code = 0;
+    long long err_detail = -1;
+    std::string err_msg;
+    std::mutex mu;
+
+    void set_error(int code, const std::string &msg, long long detail = -1) {
+        if (!err_code) { err_code = code; err_msg = msg; err_detail = detail; }
+    }
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(GorderHandle *h, T **out, size_t count, bool zero = false) {
+    *out = nullptr;
+    if (count == 0) count = 1;
+    void *p = nullptr;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    if (zero) CK(cudaMemset(p, 0, count * sizeof(T)));
+    h->owned.push_back(p);
+    *out = static_cast<T *>(p);
+    return GORDER_OK;
+}
+
+template <typename T>
+int dev_upload(GorderHandle *h, T **out, const std::vector<T> &v) {
+    int rc = dev_alloc(h, out, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CK(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return GORDER_OK;
+}
+
+int ua_hydrogens(int kind) { return kind == GORDER_UA_CH3 ? 3 : (kind == GORDER_UA_CH2 ? 2 : 1); }
+
+int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+bool should_assign(const GorderSetup &s, long long frame) {   // leaflets.rs:435-441
+    if (s.leaflet_mode == GORDER_LEAFLET_NONE) return false;
+    if (s.leaflet_freq_kind == GORDER_FREQ_ONCE) return frame == 0;
+    return frame % (s.leaflet_freq > 0 ? s.leaflet_freq : 1) == 0;
+}
+long long assignment_frame(const GorderSetup &s, long long frame) {   // leaflets.rs:1438-1473
+    if (s.leaflet_freq_kind == GORDER_FREQ_ONCE) return 0;
+    long long n = s.leaflet_freq > 0 ? s.leaflet_freq : 1;
+    return frame / n * n;
+}
+
+int upload_group(GorderHandle *h, GroupRef *g, const int32_t *idx, int n) {
+    std::vector<int> off(n), cs(n), slot(n);
+    for (int i = 0; i < n; i++) { off[i] = h->slot_off[idx[i]]; cs[i] = h->slot_cs[idx[i]]; slot[i] = idx[i]; }
+    int *d_off, *d_cs, *d_slot;
+    int rc;
+    if ((rc = dev_upload(h, &d_off, off))) return rc;
+    if ((rc = dev_upload(h, &d_cs, cs))) return rc;
+    if ((rc = dev_upload(h, &d_slot, slot))) return rc;
+    g->off = d_off; g->cs = d_cs; g->slot = d_slot; g->n = n;
+    return GORDER_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
+template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA>
+void launch_bond(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o) {
+    bond_order_kernel<MPT, PBC, NVEC, LEAF, EXTRA><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, h->d_normals,
+                                                                                       h->d_normal_npoints, o);
+}
+template <int MPT, bool PBC, bool NVEC>
+void launch_bond2(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o) {
+    if (h->leaf) { if (h->extra) launch_bond<MPT, PBC, NVEC, true, true>(h, grid, smem, planes, aux, o); else launch_bond<MPT, PBC, NVEC, true, false>(h, grid, smem, planes, aux, o); }
+    else { if (h->extra) launch_bond<MPT, PBC, NVEC, false, true>(h, grid, smem, planes, aux, o); else launch_bond<MPT, PBC, NVEC, false, false>(h, grid, smem, planes, aux, o); }
+}
+template <int MPT>
+void launch_bond3(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o) {
+    const bool pbc = h->s.handle_pbc != 0;
+    if (pbc) { if (h->nvec) launch_bond2<MPT, true, true>(h, grid, smem, planes, aux, o); else launch_bond2<MPT, true, false>(h, grid, smem, planes, aux, o); }
+    else { if (h->nvec) launch_bond2<MPT, false, true>(h, grid, smem, planes, aux, o); else launch_bond2<MPT, false, false>(h, grid, smem, planes, aux, o); }
+}
+
+template <bool PBC, bool NVEC>
+void launch_ua2(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o) {
+#define UA_L(L, E) ua_order_kernel<PBC, NVEC, L, E><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, h->d_normals, h->d_normal_npoints, o)
+    if (h->leaf) { if (h->extra) UA_L(true, true); else UA_L(true, false); }
+    else { if (h->extra) UA_L(false, true); else UA_L(false, false); }
+#undef UA_L
+}
+void launch_ua(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o) {
+    const bool pbc = h->s.handle_pbc != 0;
+    if (pbc) { if (h->nvec) launch_ua2<true, true>(h, grid, smem, planes, aux, o); else launch_ua2<true, false>(h, grid, smem, planes, aux, o); }
+    else { if (h->nvec) launch_ua2<false, true>(h, grid, smem, planes, aux, o); else launch_ua2<false, false>(h, grid, smem, planes, aux, o); }
+}
+
+size_t accum_smem(const GorderHandle *h) {
+    int max_items = 0, max_orders = 0;
+    for (auto &t : h->types) { max_items = std::max(max_items, t.n_items); max_orders = std::max(max_orders, t.n_orders); }
+    const int na = h->leaf ? (h->extra ? 3 : 2) : (h->extra ? 2 : 1);
+    const size_t items = h->ua ? (size_t)8 * max_items : (size_t)2 * max_items;
+    return (items + (size_t)kWarps * max_orders * na + 2) * sizeof(int);
+}
+
+// group centre of `g` for the frames in d_list[0..n_list) -> h->d_center[3*i]
+int run_group_center(GorderHandle *h, const GroupRef &g, const float *planes, const FrameAux *aux, const int *d_list, int n_list) {
+    const bool pbc = h->s.handle_pbc != 0;
+    dim3 grid(kCenterBlocks, n_list);
+    group_center_partial_kernel<<<grid, 256, 0, h->stream>>>(h->view, g, planes, aux, d_list, h->d_est, h->d_partial, 0);
+    group_center_final_kernel<<<(n_list + 63) / 64, 64, 0, h->stream>>>(h->view, g.n, aux, d_list, n_list, h->d_partial, kCenterBlocks, h->d_est,
+                                                                         h->d_center, 0);
+    h->n_launches += 2;
+    if (pbc) {
+        group_center_partial_kernel<<<grid, 256, 0, h->stream>>>(h->view, g, planes, aux, d_list, h->d_est, h->d_partial, 1);
+        group_center_final_kernel<<<(n_list + 63) / 64, 64, 0, h->stream>>>(h->view, g.n, aux, d_list, n_list, h->d_partial, kCenterBlocks,
+                                                                             h->d_est, h->d_center, 1);
+        h->n_launches += 2;
+    }
+    CK(cudaGetLastError());
+    return GORDER_OK;
+}
+
+int grow_rows(GorderHandle *h, long long need) {
+    if (!h->s.timewise || need <= h->tw_cap) return GORDER_OK;
+    long long cap = std::max<long long>(need, h->tw_cap * 2);
+    cap = std::max<long long>(cap, 1024);
+    const size_t row = (size_t)h->n_slots * 3;
+    long long *ns = nullptr;
+    unsigned long long *nc = nullptr;
+    CK(cudaMalloc((void **)&ns, cap * row * sizeof(long long)));
+    CK(cudaMalloc((void **)&nc, cap * row * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ns, 0, cap * row * sizeof(long long), h->stream));
+    CK(cudaMemsetAsync(nc, 0, cap * row * sizeof(unsigned long long), h->stream));
+    if (h->d_bsum) {
+        CK(cudaMemcpyAsync(ns, h->d_bsum, h->n_frames * row * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(nc, h->d_bcnt, h->n_frames * row * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_bsum); cudaFree(h->d_bcnt);
+    }
+    h->d_bsum = ns; h->d_bcnt = nc; h->tw_cap = cap;
+    return GORDER_OK;
+}
+
+template <typename T>
+int grow_collect(GorderHandle *h, T **buf, long long *cap, long long used_rows, long long need_rows, size_t row_elems) {
+    if (need_rows <= *cap) return GORDER_OK;
+    long long ncap = std::max<long long>(need_rows, *cap * 2);
+    ncap = std::max<long long>(ncap, 64);
+    T *nb = nullptr;
+    CK(cudaMalloc((void **)&nb, ncap * row_elems * sizeof(T)));
+    if (*buf) {
+        CK(cudaMemcpyAsync(nb, *buf, used_rows * row_elems * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(*buf);
+    }
+    *buf = nb; *cap = ncap;
+    return GORDER_OK;
+}
+
+// Analyse one batch whose frames are resident on the device in the native layout.
+int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, const long long *frame_index, int nf, int slot) {
+    const GorderSetup &s = h->s;
+    FrameAux *ha = h->h_aux[slot];
+    int *list_assign = h->h_list[slot], *list_all = h->h_list[slot] + h->max_batch;
+    int n_assign = 0, last_row = 0;
+    const long long row0 = s.timewise ? h->n_frames : 0;
+    for (int f = 0; f < nf; f++) {
+        FrameAux &a = ha[f];
+        memset(&a, 0, sizeof(a));
+        const long long fi = frame_index[f];
+        if (fi <= h->last_frame_index && h->n_frames + f > 0) {
+            h->set_error(GORDER_ERR_INVALID_ARGUMENT, "frame_index must be strictly increasing");
+            return h->err_code;
+        }
+        h->last_frame_index = fi;
+        a.frame_index = fi;
+        a.tw_row = (int)(row0 + f);
+        a.manual_norm_row = (int)(fi / (s.step > 0 ? s.step : 1));
+        a.leaf_row = -1;
+        if (h->leaf) {
+            if (should_assign(s, fi)) { list_assign[n_assign] = f; last_row = 1 + n_assign; n_assign++; }
+            else if (last_row == 0 && (!h->have_leaflets || h->cur_leaflet_frame != assignment_frame(s, fi))) {
+                h->set_error(GORDER_ERR_LEAFLET_FRAME_UNAVAILABLE, "leaflet assignment frame not held by this handle", fi);
+                return h->err_code;
+            }
+            a.leaf_row = last_row;
+        }
+        list_all[f] = f;
+    }
+    FrameAux *da = h->d_aux[slot];
+    int *dl_assign = h->d_list[slot], *dl_all = h->d_list[slot] + h->max_batch;
+    CK(cudaMemcpyAsync(da, ha, sizeof(FrameAux) * nf, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_list[slot], h->h_list[slot], sizeof(int) * 2 * h->max_batch, cudaMemcpyHostToDevice, h->stream));
+
+    frame_setup_kernel<<<(nf + 63) / 64, 64, 0, h->stream>>>(h->view, da, d_box, nf, 0);
+    h->n_launches++;
+    if (s.geom_kind != GORDER_GEOM_NONE) {
+        if (s.geom_ref_kind == GORDER_GEOMREF_SELECTION) {
+            int rc = run_group_center(h, h->view.geom_ref, d_planes, da, dl_all, nf);
+            if (rc) return rc;
+            store_center_kernel<<<(nf + 63) / 64, 64, 0, h->stream>>>(da, dl_all, nf, h->d_center);
+            h->n_launches++;
+        }
+        frame_setup_kernel<<<(nf + 63) / 64, 64, 0, h->stream>>>(h->view, da, d_box, nf, 1);
+        h->n_launches++;
+    }
+    if (h->leaf && n_assign > 0) {
+        if (s.leaflet_mode == GORDER_LEAFLET_GLOBAL) {
+            int rc = run_group_center(h, h->view.membrane, d_planes, da, dl_assign, n_assign);
+            if (rc) return rc;
+        }
+        dim3 grid((h->n_molpad + 255) / 256, n_assign);
+        leaflet_assign_kernel<<<grid, 256, 0, h->stream>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_molpad_type, h->d_leaf_rows);
+        h->n_launches++;
+        if (s.collect_leaflets) {
+            int rc = grow_collect(h, &h->d_leaf_collect, &h->leaf_collect_cap, h->n_leaf_collected, h->n_leaf_collected + n_assign, (size_t)h->n_molpad);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(h->d_leaf_collect + (size_t)h->n_leaf_collected * h->n_molpad, h->d_leaf_rows + h->n_molpad,
+                               (size_t)n_assign * h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
+            for (int a = 0; a < n_assign; a++) h->leaf_frame_index.push_back(frame_index[list_assign[a]]);
+            h->n_leaf_collected += n_assign;
+        }
+    }
+    if (h->nvec) {
+        if (s.normal_mode == GORDER_NORMAL_DYNAMIC) {
+            dim3 grid((h->n_molpad + 127) / 128, nf);
+            dynamic_normal_kernel<<<grid, 128, 0, h->stream>>>(h->view, d_planes, da, h->d_molpad_type, h->d_normals, h->d_normal_npoints);
+        } else {
+            dim3 grid((h->n_molpad + 255) / 256, nf);
+            manual_normal_kernel<<<grid, 256, 0, h->stream>>>(h->view, da, h->d_molpad_type, h->d_normals);
+        }
+        h->n_launches++;
+        if (h->d_normal_used) CK(cudaMemsetAsync(h->d_normal_used, 0, (size_t)nf * h->n_molpad, h->stream));
+    }
+    // per-frame accumulator rows
+    const size_t row = (size_t)h->n_slots * 3;
+    if (s.timewise) {
+        int rc = grow_rows(h, h->n_frames + nf);
+        if (rc) return rc;
+    } else {
+        CK(cudaMemsetAsync(h->d_bsum, 0, (size_t)nf * row * sizeof(long long), h->stream));
+        CK(cudaMemsetAsync(h->d_bcnt, 0, (size_t)nf * row * sizeof(unsigned long long), h->stream));
+    }
+    AccumOut o;
+    o.bsum = h->d_bsum; o.bcnt = h->d_bcnt; o.map_sum = h->d_map_sum; o.map_cnt = h->d_map_cnt; o.normal_used = h->d_normal_used;
+    dim3 grid(h->n_chunks, nf);
+    const size_t smem = accum_smem(h);
+    if (h->ua) launch_ua(h, grid, smem, d_planes, da, o);
+    else if (h->mpt == 4) launch_bond3<4>(h, grid, smem, d_planes, da, o);
+    else if (h->mpt == 2) launch_bond3<2>(h, grid, smem, d_planes, da, o);
+    else launch_bond3<1>(h, grid, smem, d_planes, da, o);
+    h->n_launches++;
+    fold_kernel<<<(h->n_slots + 127) / 128, 128, 0, h->stream>>>(h->n_slots, nf, h->leaf ? 1 : 0, h->d_bsum + row0 * row, h->d_bcnt + row0 * row,
+                                                                  h->d_tot_sum, h->d_tot_cnt);
+    h->n_launches++;
+    CK(cudaGetLastError());
+    if (h->leaf && n_assign > 0) {   // keep the newest table for the frames of the next batch
+        CK(cudaMemcpyAsync(h->d_leaf_rows, h->d_leaf_rows + (size_t)n_assign * h->n_molpad, h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
+        h->have_leaflets = true;
+        h->cur_leaflet_frame = frame_index[list_assign[n_assign - 1]];
+    }
+    if (s.collect_normals && s.normal_mode == GORDER_NORMAL_DYNAMIC) {
+        // normals that were never requested are exported as NaN (normal.rs:211-227)
+        if (h->d_normal_used) {
+            dim3 g2((h->n_molpad + 255) / 256, nf);
+            mask_normals_kernel<<<g2, 256, 0, h->stream>>>(h->n_molpad, h->d_normal_used, h->d_normals);
+            h->n_launches++;
+        }
+        int rc = grow_collect(h, &h->d_normals_collect, &h->normals_collect_cap, h->n_frames, h->n_frames + nf, (size_t)3 * h->n_molpad);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h->d_normals_collect + (size_t)h->n_frames * 3 * h->n_molpad, h->d_normals, (size_t)nf * 3 * h->n_molpad * sizeof(float),
+                           cudaMemcpyDeviceToDevice, h->stream));
+    }
+    for (int f = 0; f < nf; f++) h->frame_index_done.push_back(frame_index[f]);
+    h->n_frames += nf;
+    return GORDER_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *gorder_gpu_version(void) { return "gorder-b200 0.1.0 (sm_100a)"; }
+
+void gorder_gpu_destroy(GorderHandle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    for (void *p : h->owned) cudaFree(p);
+    cudaFree(h->d_bsum); cudaFree(h->d_bcnt);
+    cudaFree(h->d_leaf_collect); cudaFree(h->d_normals_collect); cudaFree(h->d_used_collect);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(h->d_xyz[i]);
+        if (h->h_aux[i]) cudaFreeHost(h->h_aux[i]);
+        if (h->h_list[i]) cudaFreeHost(h->h_list[i]);
+        if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]);
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
+
+static int create_impl(const GorderSetup *s, GorderHandle *h) {
+    h->s = *s;
+    const bool ua = s->kind == GORDER_KIND_UA;
+    h->ua = ua;
+    h->leaf = s->leaflet_mode != GORDER_LEAFLET_NONE;
+    h->extra = s->geom_kind != GORDER_GEOM_NONE || s->map_enabled;
+    h->nvec = s->normal_mode != GORDER_NORMAL_STATIC;
+    if (s->n_atoms <= 0 || s->n_moltypes < 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "bad n_atoms / n_moltypes"); return h->err_code; }
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || s->device < 0 || s->device >= n_dev) {
+        cudaGetLastError();
+        h->set_error(GORDER_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+        return h->err_code;
+    }
+    h->device = s->device;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+
+    // molecules per thread of the bond kernel (tunable: GORDER_MPT)
+    int max_mol = 0;
+    for (int t = 0; t < s->n_moltypes; t++) max_mol = std::max(max_mol, s->moltypes[t].n_molecules);
+    h->mpt = max_mol >= 148 * kBlock * 4 / 2 ? 4 : (max_mol >= 148 * kBlock ? 2 : 1);
+    if (const char *e = getenv("GORDER_MPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->mpt = v; }
+    if (ua) h->mpt = 1;
+
+    // ---- native layout -------------------------------------------------------------------------
+    h->slot_off.assign(s->n_atoms, -1);
+    h->slot_cs.assign(s->n_atoms, 0);
+    std::vector<BondItem> bonds;
+    std::vector<UAItem> uas;
+    std::vector<int> methyl_offs;
+    std::vector<Chunk> chunks;
+    std::vector<unsigned char> manual_leaf;
+    std::vector<float> manual_norm;
+    long long off = 0;
+    int slot = 0, molpad = 0, mol = 0;
+    auto bad_rel = [&](int r) { return r < 0; };
+    for (int t = 0; t < s->n_moltypes; t++) {
+        const GorderMolType &m = s->moltypes[t];
+        if (m.n_molecules <= 0 || !m.mol_base) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "molecule type without molecules"); return h->err_code; }
+        TypeDesc td{};
+        td.n_mol = m.n_molecules;
+        td.mpad = round_up(m.n_molecules, kMolAlign);
+        std::vector<int32_t> used;
+        if (ua) for (int i = 0; i < m.n_ua_atoms; i++) for (int k = 0; k < 4; k++) { int r = m.ua_rel[4 * i + k]; if (r >= 0) used.push_back(r); else if (k < 3) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "negative UA relative index"); return h->err_code; } }
+        else for (int i = 0; i < 2 * m.n_bond_types; i++) { if (bad_rel(m.bond_rel[i])) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "negative bond relative index"); return h->err_code; } used.push_back(m.bond_rel[i]); }
+        if (m.head_rel >= 0) used.push_back(m.head_rel);
+        if (m.normal_head_rel >= 0) used.push_back(m.normal_head_rel);
+        for (int k = 0; k < m.n_methyls; k++) used.push_back(m.methyl_rel[k]);
+        std::sort(used.begin(), used.end());
+        used.erase(std::unique(used.begin(), used.end()), used.end());
+        auto u_of = [&](int rel) { return (int)(std::lower_bound(used.begin(), used.end(), rel) - used.begin()); };
+        td.plane_base = (int)off;
+        for (size_t u = 0; u < used.size(); u++)
+            for (int mm = 0; mm < m.n_molecules; mm++) {
+                long long sl = (long long)m.mol_base[mm] + used[u];
+                if (sl < 0 || sl >= s->n_atoms) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "atom slot out of range", sl); return h->err_code; }
+                if (h->slot_off[sl] >= 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "atom belongs to two molecules", sl); return h->err_code; }
+                h->slot_off[sl] = (int)(off + (long long)u * 3 * td.mpad + mm);
+                h->slot_cs[sl] = td.mpad;
+            }
+        off += (long long)used.size() * 3 * td.mpad;
+        td.slot0 = slot; td.molpad0 = molpad; td.mol0 = mol;
+        td.head_off = m.head_rel >= 0 ? u_of(m.head_rel) * 3 * td.mpad : -1;
+        td.nhead_off = m.normal_head_rel >= 0 ? u_of(m.normal_head_rel) * 3 * td.mpad : -1;
+        td.n_methyls = m.n_methyls; td.methyl_off = (int)methyl_offs.size();
+        for (int k = 0; k < m.n_methyls; k++) methyl_offs.push_back(u_of(m.methyl_rel[k]) * 3 * td.mpad);
+        std::vector<int32_t> islots;
+        if (ua) {
+            td.item_off = (int)uas.size(); td.n_items = m.n_ua_atoms;
+            int k = 0;
+            for (int i = 0; i < m.n_ua_atoms; i++) {
+                UAItem it{};
+                it.kind = m.ua_kind[i];
+                const int32_t *r = m.ua_rel + 4 * i;
+                it.t_off = u_of(r[0]) * 3 * td.mpad; it.h1_off = u_of(r[1]) * 3 * td.mpad; it.h2_off = u_of(r[2]) * 3 * td.mpad;
+                it.h3_off = r[3] >= 0 ? u_of(r[3]) * 3 * td.mpad : 0;
+                if (it.kind == GORDER_UA_CH1_SAT && r[3] < 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "CH1_SAT needs three helpers"); return h->err_code; }
+                it.slot_rel = k; k += ua_hydrogens(it.kind);
+                uas.push_back(it);
+                islots.push_back(r[0]);
+            }
+            td.n_orders = k;
+        } else {
+            td.item_off = (int)bonds.size(); td.n_items = m.n_bond_types; td.n_orders = m.n_bond_types;
+            for (int i = 0; i < m.n_bond_types; i++) {
+                bonds.push_back(BondItem{u_of(m.bond_rel[2 * i]) * 3 * td.mpad, u_of(m.bond_rel[2 * i + 1]) * 3 * td.mpad});
+                islots.push_back(m.bond_rel[2 * i]);
+            }
+        }
+        td.manual_leaf_off = -1; td.n_manual_leaf = 0; td.manual_norm_off = -1; td.n_manual_norm = 0;
+        if (m.manual_leaflets && m.n_manual_leaflet_frames > 0) {
+            td.manual_leaf_off = (int)manual_leaf.size(); td.n_manual_leaf = m.n_manual_leaflet_frames;
+            manual_leaf.insert(manual_leaf.end(), m.manual_leaflets, m.manual_leaflets + (size_t)m.n_manual_leaflet_frames * m.n_molecules);
+        }
+        if (m.manual_normals && m.n_manual_normal_frames > 0) {
+            td.manual_norm_off = (int)manual_norm.size(); td.n_manual_norm = m.n_manual_normal_frames;
+            manual_norm.insert(manual_norm.end(), m.manual_normals, m.manual_normals + (size_t)3 * m.n_manual_normal_frames * m.n_molecules);
+        }
+        const int per_cta = kBlock * (ua ? 1 : h->mpt);
+        for (int first = 0; first < td.n_mol; first += per_cta) chunks.push_back(Chunk{t, first});
+        for (int i = 0; i < td.mpad; i++) h->molpad_type_h.push_back(t);
+        slot += td.n_orders; molpad += td.mpad; mol += td.n_mol;
+        h->types.push_back(td);
+        h->mol_base.emplace_back(m.mol_base, m.mol_base + m.n_molecules);
+        h->used_rel.push_back(used);
+        h->item_slots.push_back(islots);
+    }
+    h->n_slots = slot; h->n_molpad = molpad; h->n_mol_total = mol; h->n_chunks = (int)chunks.size();
+    // extra atoms: members of the groups that are not part of an analysed molecule
+    std::vector<int32_t> extra;
+    auto scan_group = [&](const int32_t *g, int n) -> int {
+        for (int i = 0; i < n; i++) {
+            if (g[i] < 0 || g[i] >= s->n_atoms) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "group atom out of range", g[i]); return h->err_code; }
+            if (h->slot_off[g[i]] < 0) { h->slot_off[g[i]] = -2; extra.push_back(g[i]); }
+        }
+        return GORDER_OK;
+    };
+    if (int rc = scan_group(s->membrane, s->n_membrane)) return rc;
+    if (int rc = scan_group(s->geom_ref, s->n_geom_ref)) return rc;
+    if (int rc = scan_group(s->normal_heads, s->n_normal_heads)) return rc;
+    const int n_extra_pad = round_up((int)extra.size(), kMolAlign);
+    for (size_t e = 0; e < extra.size(); e++) { h->slot_off[extra[e]] = (int)(off + (long long)e); h->slot_cs[extra[e]] = n_extra_pad; }
+    off += 3LL * n_extra_pad;
+    if (off >= (1LL << 31)) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "frame too large for 32-bit plane offsets"); return h->err_code; }
+    h->frame_floats = std::max<long long>(off, kMolAlign);
+
+    // ---- batch size ------------------------------------------------------------------------------
+    const size_t frame_bytes = (size_t)h->frame_floats * sizeof(float);
+    long long mb = s->max_batch_frames > 0 ? s->max_batch_frames : (long long)((512ull << 20) / std::max<size_t>(frame_bytes, 1));
+    mb = std::max<long long>(1, std::min<long long>(mb, 512));
+    h->max_batch = (int)mb;
+
+    // ---- device tables ---------------------------------------------------------------------------
+    int rc;
+    TypeDesc *d_types; Chunk *d_chunks; BondItem *d_bonds; UAItem *d_ua; int *d_methyl; unsigned char *d_mleaf; float *d_mnorm;
+    if ((rc = dev_upload(h, &d_types, h->types))) return rc;
+    if ((rc = dev_upload(h, &d_chunks, chunks))) return rc;
+    if ((rc = dev_upload(h, &d_bonds, bonds))) return rc;
+    if ((rc = dev_upload(h, &d_ua, uas))) return rc;
+    if ((rc = dev_upload(h, &d_methyl, methyl_offs))) return rc;
+    if ((rc = dev_upload(h, &d_mleaf, manual_leaf))) return rc;
+    if ((rc = dev_upload(h, &d_mnorm, manual_norm))) return rc;
+    if ((rc = dev_upload(h, &h->d_slot_off, h->slot_off))) return rc;
+    if ((rc = dev_upload(h, &h->d_slot_cs, h->slot_cs))) return rc;
+    if ((rc = dev_upload(h, &h->d_molpad_type, h->molpad_type_h))) return rc;
+    if ((rc = dev_alloc(h, &h->d_err, 2, true))) return rc;
+    if ((rc = dev_alloc(h, &h->d_err_detail, 1, true))) return rc;
+
+    DeviceView &v = h->view;
+    v.types = d_types; v.chunks = d_chunks; v.bonds = d_bonds; v.ua = d_ua; v.methyl_offs = d_methyl;
+    v.n_types = s->n_moltypes; v.n_chunks = h->n_chunks; v.n_slots = h->n_slots; v.n_molpad = h->n_molpad; v.n_mol_total = h->n_mol_total;
+    v.frame_floats = h->frame_floats;
+    v.kind = s->kind; v.handle_pbc = s->handle_pbc; v.step = s->step;
+    v.normal_mode = s->normal_mode; v.normal_axis = s->normal_axis; v.dynamic_radius = s->dynamic_radius;
+    v.leaflet_mode = s->leaflet_mode; v.leaflet_axis = s->leaflet_axis; v.leaflet_flip = s->leaflet_flip;
+    v.leaflet_freq_kind = s->leaflet_freq_kind; v.leaflet_freq = s->leaflet_freq; v.leaflet_radius = s->leaflet_radius;
+    v.shape.kind = s->geom_kind; v.shape.invert = s->geom_invert; v.shape.axis = s->geom_axis; v.shape.ref_kind = s->geom_ref_kind;
+    for (int k = 0; k < 3; k++) v.shape.ref_point[k] = s->geom_ref_point[k];
+    for (int k = 0; k < 6; k++) v.shape.dims[k] = s->geom_dims[k];
+    v.manual_leaflets = d_mleaf; v.manual_normals = d_mnorm;
+    v.err = h->d_err; v.err_detail = h->d_err_detail;
+    // rotation constants with the host libm (the reference's sin/cos of the same f32 angles)
+    v.tet_s = sinf(1.910633f); v.tet_c = cosf(1.910633f);
+    v.tet_half_s = sinf(0.9553165f); v.tet_half_c = cosf(0.9553165f);
+    v.ch3_s = sinf(2.0943952f); v.ch3_c = cosf(2.0943952f);
+    if ((rc = upload_group(h, &v.membrane, s->membrane, s->n_membrane))) return rc;
+    if ((rc = upload_group(h, &v.geom_ref, s->geom_ref, s->n_geom_ref))) return rc;
+    if ((rc = upload_group(h, &v.normal_heads, s->normal_heads, s->n_normal_heads))) return rc;
+
+    // order maps: Map::new (ordermap.rs:40-96); node count = round(span / bin) + 1
+    v.map.enabled = 0; v.map.n_bins = 0;
+    if (s->map_enabled) {
+        const float sx = s->map_span_x[1] - s->map_span_x[0], sy = s->map_span_y[1] - s->map_span_y[0];
+        if (!(s->map_bin[0] > 0) || !(s->map_bin[1] > 0) || s->map_bin[0] > sx || s->map_bin[1] > sy) {
+            h->set_error(GORDER_ERR_ORDERMAP_BIN_TOO_LARGE, "ordermap bin larger than span");
+            return h->err_code;
+        }
+        v.map.enabled = 1; v.map.plane = s->map_plane;
+        v.map.nx = (int)roundf(sx / s->map_bin[0]) + 1; v.map.ny = (int)roundf(sy / s->map_bin[1]) + 1;
+        v.map.x0 = s->map_span_x[0]; v.map.y0 = s->map_span_y[0]; v.map.binx = s->map_bin[0]; v.map.biny = s->map_bin[1];
+        v.map.n_bins = (long long)v.map.nx * v.map.ny;
+    }
+
+    // ---- accumulators ----------------------------------------------------------------------------
+    const long long na = (long long)h->n_slots * 3;
+    h->block_words = 2 * na + 2 * na * v.map.n_bins;
+    if ((rc = dev_alloc(h, &h->d_block, (size_t)h->block_words, true))) return rc;
+    h->d_tot_sum = h->d_block;
+    h->d_tot_cnt = reinterpret_cast<unsigned long long *>(h->d_block + na);
+    h->d_map_sum = h->d_block + 2 * na;
+    h->d_map_cnt = reinterpret_cast<unsigned long long *>(h->d_block + 2 * na + na * v.map.n_bins);
+    if (!s->timewise) {
+        CK(cudaMalloc((void **)&h->d_bsum, std::max<size_t>(1, (size_t)h->max_batch * na) * sizeof(long long)));
+        CK(cudaMalloc((void **)&h->d_bcnt, std::max<size_t>(1, (size_t)h->max_batch * na) * sizeof(unsigned long long)));
+    }
+
+    // ---- per-batch buffers -------------------------------------------------------------------------
+    const size_t B = (size_t)h->max_batch;
+    for (int i = 0; i < 2; i++) {
+        if ((rc = dev_alloc(h, &h->d_planes[i], B * (size_t)h->frame_floats))) return rc;
+        if ((rc = dev_alloc(h, &h->d_box[i], B * 3))) return rc;
+        if ((rc = dev_alloc(h, &h->d_aux[i], B))) return rc;
+        if ((rc = dev_alloc(h, &h->d_list[i], 2 * B))) return rc;
+        CK(cudaMallocHost((void **)&h->h_aux[i], B * sizeof(FrameAux)));
+        CK(cudaMallocHost((void **)&h->h_list[i], 2 * B * sizeof(int)));
+        CK(cudaEventCreateWithFlags(&h->ev_stage_free[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+    }
+    // planes may contain padding that is never written: keep it finite
+    for (int i = 0; i < 2; i++) CK(cudaMemset(h->d_planes[i], 0, B * (size_t)h->frame_floats * sizeof(float)));
+    if (h->leaf) { if ((rc = dev_alloc(h, &h->d_leaf_rows, (1 + B) * (size_t)h->n_molpad, true))) return rc; }
+    if (h->nvec) {
+        if ((rc = dev_alloc(h, &h->d_normals, B * 3 * (size_t)h->n_molpad))) return rc;
+        if ((rc = dev_alloc(h, &h->d_normal_npoints, B * (size_t)h->n_molpad, true))) return rc;
+        if (s->collect_normals && s->geom_kind != GORDER_GEOM_NONE && !ua) { if ((rc = dev_alloc(h, &h->d_normal_used, B * (size_t)h->n_molpad, true))) return rc; }
+    }
+    if ((rc = dev_alloc(h, &h->d_est, B * 3))) return rc;
+    if ((rc = dev_alloc(h, &h->d_center, B * 3))) return rc;
+    if ((rc = dev_alloc(h, &h->d_partial, B * kCenterBlocks * 6))) return rc;
+
+    // dynamic shared memory of the accumulation kernels (small; no opt-in needed below 48 KB)
+    if (accum_smem(h) > 48 * 1024) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "too many order slots per molecule type for shared memory"); return h->err_code; }
+    CK(cudaDeviceSynchronize());
+    return GORDER_OK;
+}
+
+int gorder_gpu_create(const GorderSetup *setup, GorderHandle **out) {
+    if (!setup || !out || setup->abi_version != GORDER_ABI_VERSION) return GORDER_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    GorderHandle *h = new GorderHandle();
+    int rc = create_impl(setup, h);
+    if (rc) {
+        if (getenv("GORDER_VERBOSE")) fprintf(stderr, "gorder_gpu_create failed: %s\n", h->err_msg.c_str());
+        // pointers inside the copied setup are not owned
+        gorder_gpu_destroy(h);
+        return rc;
+    }
+    // the copied setup must not keep caller pointers
+    h->s.moltypes = nullptr; h->s.normal_heads = nullptr; h->s.membrane = nullptr; h->s.geom_ref = nullptr;
+    *out = h;
+    return GORDER_OK;
+}
+
+// first deferred device error -> host error state
+static int poll_device_error(GorderHandle *h) {
+    int code[2] = {0, 0};
+    long long detail = 0;
+    CK(cudaMemcpyAsync(code, h->d_err, sizeof(code), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&detail, h->d_err_detail, sizeof(detail), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (code[0]) {
+        long long d = detail;
+        if (code[0] == GORDER_ERR_UNDEFINED_POSITION && (detail >> 32) != 0) {   // (type, item, molecule) -> atom slot
+            int t = (int)(detail >> 48), item = (int)((detail >> 32) & 0xffff), m = (int)(detail & 0xffffffff);
+            if (t < (int)h->mol_base.size() && m < (int)h->mol_base[t].size() && item < (int)h->item_slots[t].size())
+                d = (long long)h->mol_base[t][m] + h->item_slots[t][item];
+        }
+        h->set_error(code[0], "deferred device error", d);
+    }
+    return h->err_code;
+}
+
+static int begin_slot(GorderHandle *h, int *slot) {
+    *slot = h->cur;
+    h->cur ^= 1;
+    CK(cudaEventSynchronize(h->ev_stage_free[*slot]));
+    return GORDER_OK;
+}
+
+static int check_args(GorderHandle *h, const void *frames, const void *box, const int64_t *fi, int32_t n) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    if (h->err_code) return h->err_code;
+    if (n < 0 || (n > 0 && (!frames || !fi || (h->s.handle_pbc && !box)))) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "null argument"); return h->err_code; }
+    cudaSetDevice(h->device);
+    return GORDER_OK;
+}
+
+static int launch_relayout(GorderHandle *h, const float *d_xyz, float *d_planes, int nf) {
+    dim3 grid((h->s.n_atoms + 255) / 256, nf);
+    relayout_kernel<<<grid, 256, 0, h->stream>>>(h->view, d_xyz, d_planes, h->d_slot_off, h->d_slot_cs, h->s.n_atoms);
+    h->n_launches++;
+    CK(cudaGetLastError());
+    return GORDER_OK;
+}
+
+int gorder_gpu_submit(GorderHandle *h, const float *xyz, const float *box, const int64_t *frame_index, int32_t n_frames) {
+    if (int rc = check_args(h, xyz, box, frame_index, n_frames)) return rc;
+    std::lock_guard<std::mutex> lock(h->mu);
+    const size_t fstride = (size_t)h->s.n_atoms * 3;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+        const int nf = std::min(h->max_batch, n_frames - f0);
+        int slot;
+        if (int rc = begin_slot(h, &slot)) return rc;
+        if (!h->d_xyz[slot]) CK(cudaMalloc((void **)&h->d_xyz[slot], (size_t)h->max_batch * fstride * sizeof(float)));
+        CK(cudaMemcpyAsync(h->d_xyz[slot], xyz + (size_t)f0 * fstride, (size_t)nf * fstride * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+        if (h->s.handle_pbc) CK(cudaMemcpyAsync(h->d_box[slot], box + 3 * (size_t)f0, (size_t)nf * 3 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
+        if (int rc = launch_relayout(h, h->d_xyz[slot], h->d_planes[slot], nf)) return rc;
+        if (int rc = process_batch(h, h->d_planes[slot], h->d_box[slot], (const long long *)frame_index + f0, nf, slot)) return rc;
+        CK(cudaEventRecord(h->ev_stage_free[slot], h->stream));
+        CK(cudaEventSynchronize(h->ev_h2d[slot]));   // the caller's buffers may be reused from here on
+    }
+    return GORDER_OK;
+}
+
+int gorder_gpu_submit_device(GorderHandle *h, const float *d_xyz, const float *d_box, const int64_t *frame_index, int32_t n_frames) {
+    if (int rc = check_args(h, d_xyz, d_box, frame_index, n_frames)) return rc;
+    std::lock_guard<std::mutex> lock(h->mu);
+    const size_t fstride = (size_t)h->s.n_atoms * 3;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+        const int nf = std::min(h->max_batch, n_frames - f0);
+        int slot;
+        if (int rc = begin_slot(h, &slot)) return rc;
+        if (int rc = launch_relayout(h, d_xyz + (size_t)f0 * fstride, h->d_planes[slot], nf)) return rc;
+        if (int rc = process_batch(h, h->d_planes[slot], d_box ? d_box + 3 * (size_t)f0 : nullptr, (const long long *)frame_index + f0, nf, slot)) return rc;
+        CK(cudaEventRecord(h->ev_stage_free[slot], h->stream));
+    }
+    return GORDER_OK;
+}
+
+int gorder_gpu_native_layout(GorderHandle *h, int64_t *frame_floats, int32_t *plane_offset, int32_t *plane_cstride) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    if (frame_floats) *frame_floats = h->frame_floats;
+    if (plane_offset) for (int i = 0; i < h->s.n_atoms; i++) plane_offset[i] = h->slot_off[i] >= 0 ? h->slot_off[i] : -1;
+    if (plane_cstride) for (int i = 0; i < h->s.n_atoms; i++) plane_cstride[i] = h->slot_cs[i];
+    return GORDER_OK;
+}
+
+int gorder_gpu_submit_native(GorderHandle *h, const float *planes_host, const float *box, const int64_t *frame_index, int32_t n_frames) {
+    if (int rc = check_args(h, planes_host, box, frame_index, n_frames)) return rc;
+    std::lock_guard<std::mutex> lock(h->mu);
+    const size_t fstride = (size_t)h->frame_floats;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+        const int nf = std::min(h->max_batch, n_frames - f0);
+        int slot;
+        if (int rc = begin_slot(h, &slot)) return rc;
+        CK(cudaMemcpyAsync(h->d_planes[slot], planes_host + (size_t)f0 * fstride, (size_t)nf * fstride * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+        if (h->s.handle_pbc) CK(cudaMemcpyAsync(h->d_box[slot], box + 3 * (size_t)f0, (size_t)nf * 3 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
+        if (int rc = process_batch(h, h->d_planes[slot], h->d_box[slot], (const long long *)frame_index + f0, nf, slot)) return rc;
+        CK(cudaEventRecord(h->ev_stage_free[slot], h->stream));
+        CK(cudaEventSynchronize(h->ev_h2d[slot]));
+    }
+    return GORDER_OK;
+}
+
+int gorder_gpu_submit_native_device(GorderHandle *h, const float *d_planes, const float *d_box, const int64_t *frame_index, int32_t n_frames) {
+    if (int rc = check_args(h, d_planes, d_box, frame_index, n_frames)) return rc;
+    std::lock_guard<std::mutex> lock(h->mu);
+    const size_t fstride = (size_t)h->frame_floats;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+        const int nf = std::min(h->max_batch, n_frames - f0);
+        int slot;
+        if (int rc = begin_slot(h, &slot)) return rc;
+        if (int rc = process_batch(h, d_planes + (size_t)f0 * fstride, d_box ? d_box + 3 * (size_t)f0 : nullptr, (const long long *)frame_index + f0, nf, slot)) return rc;
+        CK(cudaEventRecord(h->ev_stage_free[slot], h->stream));
+    }
+    return GORDER_OK;
+}
+
+int gorder_gpu_set_leaflets(GorderHandle *h, const uint8_t *table, int64_t frame_index) {
+    if (!h || !table) return GORDER_ERR_INVALID_ARGUMENT;
+    if (!h->leaf) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "leaflets are not enabled"); return h->err_code; }
+    cudaSetDevice(h->device);
+    std::vector<unsigned char> row(h->n_molpad, GORDER_UPPER);
+    for (auto &td : h->types) for (int m = 0; m < td.n_mol; m++) row[td.molpad0 + m] = table[td.mol0 + m];
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->d_leaf_rows, row.data(), row.size(), cudaMemcpyHostToDevice));
+    h->have_leaflets = true; h->cur_leaflet_frame = frame_index;
+    return GORDER_OK;
+}
+
+int gorder_gpu_sync(GorderHandle *h) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    if (h->err_code) return h->err_code;
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(h->copy_stream));
+    return poll_device_error(h);
+}
+
+int gorder_gpu_result_sizes(GorderHandle *h, GorderResults *r) {
+    if (!h || !r) return GORDER_ERR_INVALID_ARGUMENT;
+    r->n_slots = h->n_slots; r->n_frames = h->n_frames; r->n_map_bins = h->view.map.n_bins;
+    r->map_nx = h->view.map.enabled ? h->view.map.nx : 0; r->map_ny = h->view.map.enabled ? h->view.map.ny : 0;
+    r->n_leaflet_frames = h->n_leaf_collected; r->n_molecules_total = h->n_mol_total;
+    return GORDER_OK;
+}
+
+int gorder_gpu_finish(GorderHandle *h, GorderResults *r) {
+    if (!h || !r) return GORDER_ERR_INVALID_ARGUMENT;
+    if (int rc = gorder_gpu_sync(h)) return rc;
+    gorder_gpu_result_sizes(h, r);
+    const size_t na = (size_t)h->n_slots * 3;
+    if (r->sum) CK(cudaMemcpy(r->sum, h->d_tot_sum, na * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (r->count) CK(cudaMemcpy(r->count, h->d_tot_cnt, na * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (h->s.timewise && h->n_frames > 0) {
+        if (r->tw_sum) CK(cudaMemcpy(r->tw_sum, h->d_bsum, na * h->n_frames * sizeof(long long), cudaMemcpyDeviceToHost));
+        if (r->tw_count) CK(cudaMemcpy(r->tw_count, h->d_bcnt, na * h->n_frames * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (r->tw_frame_index) for (long long i = 0; i < h->n_frames; i++) r->tw_frame_index[i] = h->frame_index_done[i];
+    if (h->view.map.enabled) {
+        const size_t nb = (size_t)h->view.map.n_bins;
+        if (r->map_sum) {
+            CK(cudaMemcpy(r->map_sum, h->d_map_sum, na * nb * sizeof(long long), cudaMemcpyDeviceToHost));
+            if (h->leaf)   // total map = upper + lower (bond.rs:184-215)
+                for (int sl = 0; sl < h->n_slots; sl++)
+                    for (size_t b = 0; b < nb; b++)
+                        r->map_sum[((size_t)sl * 3 + GORDER_TOTAL) * nb + b] = r->map_sum[((size_t)sl * 3 + GORDER_ACC_UPPER) * nb + b] + r->map_sum[((size_t)sl * 3 + GORDER_ACC_LOWER) * nb + b];
+        }
+        if (r->map_count) {
+            CK(cudaMemcpy(r->map_count, h->d_map_cnt, na * nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            if (h->leaf)
+                for (int sl = 0; sl < h->n_slots; sl++)
+                    for (size_t b = 0; b < nb; b++)
+                        r->map_count[((size_t)sl * 3 + GORDER_TOTAL) * nb + b] = r->map_count[((size_t)sl * 3 + GORDER_ACC_UPPER) * nb + b] + r->map_count[((size_t)sl * 3 + GORDER_ACC_LOWER) * nb + b];
+        }
+    }
+    if (r->leaflets && h->n_leaf_collected > 0) {
+        std::vector<unsigned char> rows((size_t)h->n_leaf_collected * h->n_molpad);
+        CK(cudaMemcpy(rows.data(), h->d_leaf_collect, rows.size(), cudaMemcpyDeviceToHost));
+        for (long long a = 0; a < h->n_leaf_collected; a++)
+            for (auto &td : h->types)
+                memcpy(r->leaflets + (size_t)a * h->n_mol_total + td.mol0, rows.data() + (size_t)a * h->n_molpad + td.molpad0, td.n_mol);
+    }
+    if (r->leaflet_frame_index) for (long long a = 0; a < h->n_leaf_collected; a++) r->leaflet_frame_index[a] = h->leaf_frame_index[a];
+    if (r->normals && h->d_normals_collect && h->n_frames > 0) {
+        std::vector<float> buf((size_t)h->n_frames * 3 * h->n_molpad);
+        CK(cudaMemcpy(buf.data(), h->d_normals_collect, buf.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (long long f = 0; f < h->n_frames; f++)
+            for (auto &td : h->types)
+                for (int m = 0; m < td.n_mol; m++)
+                    for (int c = 0; c < 3; c++)
+                        r->normals[((size_t)f * h->n_mol_total + td.mol0 + m) * 3 + c] = buf[((size_t)f * 3 + c) * h->n_molpad + td.molpad0 + m];
+    }
+    return GORDER_OK;
+}
+
+int gorder_gpu_accumulator_block(GorderHandle *h, void **d_ptr, int64_t *n_words) {
+    if (!h || !d_ptr || !n_words) return GORDER_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    *d_ptr = h->d_block; *n_words = h->block_words;
+    return GORDER_OK;
+}
+
+int gorder_gpu_stats(GorderHandle *h, int64_t *kernel_launches, int64_t *frames) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    if (kernel_launches) *kernel_launches = h->n_launches;
+    if (frames) *frames = h->n_frames;
+    return GORDER_OK;
+}
+
+void *gorder_gpu_stream(GorderHandle *h) { return h ? (void *)h->stream : nullptr; }
+
+int gorder_gpu_last_error(GorderHandle *h, char *buf, size_t len) {
+    if (!h || !buf || !len) return GORDER_ERR_INVALID_ARGUMENT;
+    snprintf(buf, len, "%s", h->err_msg.c_str());
+    return h->err_code;
+}
+
+int64_t gorder_gpu_error_detail(GorderHandle *h) { return h ? h->err_detail : -1; }
+
+}  // extern "C"

@@ -1,0 +1,815 @@
+// gorder_kernels.cuh — sm_100a kernels of the per-frame order-parameter engine.
+//
+//   relayout_kernel         host AoS frames -> device planes (+ undefined-position check)
+//   frame_setup_kernel      box, geometry shape of every frame      (geometry.rs:192-210, :328-514)
+//   group_center_*          PBC-aware centre of a group             (pbc.rs:270; groan group_get_center)
+//   leaflet_assign_kernel   Global / Individual / Manual / Local    (leaflets.rs:571-874)
+//   dynamic_normal_kernel   per-lipid PCA normal                    (normal.rs:160-199, :421-458)
+//   bond_order_kernel       K1: AA / CG bond engine                 (topology/bond.rs:396-446, :184-215)
+//   ua_order_kernel         K2: united-atom engine                  (uaorder.rs:375-437, :947-1104)
+//   fold_kernel             per-frame accumulators -> running totals (order.rs:160-188)
+//
+// All of them are HBM/L2-bound integer/f32 streaming kernels: no tensor cores (nothing on this path
+// is a dense contraction).
+#pragma once
+#include <math_constants.h>
+
+#include "gorder_engine.cuh"
+#include "gorder_math.cuh"
+
+namespace gorder {
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void raise_error(const DeviceView &v, int code, long long detail) {
+    if (atomicCAS(v.err, 0, code) == 0) *v.err_detail = detail;
+}
+
+template <int N> struct Vec;
+template <> struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ void load(const float *p) { v[0] = __ldg(p); }
+};
+template <> struct Vec<2> {
+    float v[2];
+    __device__ __forceinline__ void load(const float *p) { float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; }
+};
+template <> struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float *p) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+
+__device__ __forceinline__ Box load_box(const FrameAux &a) {
+    Box b;
+    b.L[0] = a.L[0]; b.L[1] = a.L[1]; b.L[2] = a.L[2];
+    b.half[0] = a.half[0]; b.half[1] = a.half[1]; b.half[2] = a.half[2];
+    return b;
+}
+
+// Shape::inside / inside_naive XOR invert (geometry.rs:181-190; groan Rectangular / Cylinder / Sphere).
+template <bool PBC>
+__device__ __forceinline__ bool shape_inside(const ShapeParams &sp, const FrameAux &a, const Box &bx, const f3 &pt) {
+    bool in = true;
+    const float o[3] = {a.shape_origin[0], a.shape_origin[1], a.shape_origin[2]};
+    const float q[3] = {pt.x, pt.y, pt.z};
+    if (sp.kind == GORDER_GEOM_CUBOID) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (PBC) {
+                float d = __fsub_rn(q[k], o[k]);
+                if (bx.L[k] > 0.0f) d = wrap1(d, bx.L[k]);
+                in = in && (d <= a.shape_len[k]);
+            } else in = in && (q[k] >= o[k]) && (q[k] <= __fadd_rn(o[k], a.shape_len[k]));
+        }
+    } else if (sp.kind == GORDER_GEOM_CYLINDER) {
+        float r2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (k == sp.axis) continue;
+            float d = __fsub_rn(q[k], o[k]);
+            if (PBC && bx.L[k] > 0.0f) d = min_image(d, bx.L[k], bx.half[k]);
+            r2 = __fadd_rn(r2, __fmul_rn(d, d));
+        }
+        in = __fsqrt_rn(r2) < a.shape_radius;
+        float d = __fsub_rn(q[sp.axis], o[sp.axis]);
+        if (PBC) {
+            if (bx.L[sp.axis] > 0.0f) d = wrap1(d, bx.L[sp.axis]);
+            in = in && (d <= a.shape_height);
+        } else in = in && (d >= 0.0f) && (d <= a.shape_height);
+    } else if (sp.kind == GORDER_GEOM_SPHERE) {
+        f3 c = mk3(o[0], o[1], o[2]);
+        f3 d = vector_to<PBC>(c, pt, bx);
+        in = norm_ref(d) < a.shape_radius;
+    }
+    return in != (sp.invert != 0);
+}
+
+// Map::add_order bin lookup (ordermap.rs:100-113): nearest node, -1 if outside.
+__device__ __forceinline__ long long map_bin(const MapParams &mp, const f3 &pos) {
+    float x, y;
+    if (mp.plane == GORDER_PLANE_XY) { x = pos.x; y = pos.y; }
+    else if (mp.plane == GORDER_PLANE_XZ) { x = pos.x; y = pos.z; }
+    else { x = pos.z; y = pos.y; }   // sic: YZ projects to (z, y), input/ordermap.rs:48
+    float fx = floorf(__fadd_rn(__fdiv_rn(__fsub_rn(x, mp.x0), mp.binx), 0.5f));
+    float fy = floorf(__fadd_rn(__fdiv_rn(__fsub_rn(y, mp.y0), mp.biny), 0.5f));
+    if (!(fx >= 0.0f) || !(fy >= 0.0f) || fx >= (float)mp.nx || fy >= (float)mp.ny) return -1;
+    return (long long)fx * mp.ny + (long long)fy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// relayout: [F][n_atoms][3] AoS -> planes.  One thread per (frame, slot).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relayout_kernel(DeviceView v, const float *__restrict__ xyz, float *__restrict__ planes,
+                                                       const int *__restrict__ slot_off, const int *__restrict__ slot_cs, int n_atoms) {
+    const int f = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_atoms) return;
+    const int off = slot_off[s];
+    if (off < 0) return;
+    const int cs = slot_cs[s];
+    const float *src = xyz + ((size_t)f * n_atoms + s) * 3;
+    float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
+    // AnalysisError::UndefinedPosition: a NaN coordinate marks an atom without position
+    if (x != x || y != y || z != z) raise_error(v, GORDER_ERR_UNDEFINED_POSITION, s);
+    float *dst = planes + (size_t)f * v.frame_floats + off;
+    dst[0] = x; dst[cs] = y; dst[2 * (size_t)cs] = z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame setup: box -> FrameAux.L/half, zero-box check (common.rs:186-198), geometry shape.
+// One thread per frame.  `stage` 0: box; 1: shape (after the optional reference-centre reduction).
+// ---------------------------------------------------------------------------------------------
+template <bool PBC>
+__device__ void construct_shape(const DeviceView &v, FrameAux &a) {
+    const ShapeParams &sp = v.shape;
+    if (sp.kind == GORDER_GEOM_NONE) return;
+    Box bx = load_box(a);
+    float p[3];
+    if (sp.ref_kind == GORDER_GEOMREF_POINT) { p[0] = sp.ref_point[0]; p[1] = sp.ref_point[1]; p[2] = sp.ref_point[2]; }
+    else if (sp.ref_kind == GORDER_GEOMREF_BOX_CENTER) { p[0] = a.L[0] / 2.0f; p[1] = a.L[1] / 2.0f; p[2] = a.L[2] / 2.0f; }  // pbc.rs:399-405
+    else { p[0] = a.center[0]; p[1] = a.center[1]; p[2] = a.center[2]; }
+    const float inf_pos = PBC ? 0.0f : -3.40282347e+38f;   // get_infinite_span: pbc.rs:393-396 / :188-191
+    a.shape_len[0] = a.shape_len[1] = a.shape_len[2] = 0.0f;
+    a.shape_radius = 0.0f; a.shape_height = 0.0f;
+    if (sp.kind == GORDER_GEOM_CUBOID) {   // geometry.rs:328-357
+        for (int k = 0; k < 3; k++) {
+            float lo = sp.dims[2 * k], hi = sp.dims[2 * k + 1];
+            if (isinf(lo) && lo < 0 && isinf(hi) && hi > 0) { p[k] = inf_pos; a.shape_len[k] = CUDART_INF_F; }
+            else { p[k] = __fadd_rn(p[k], lo); a.shape_len[k] = __fsub_rn(hi, lo); }
+        }
+    } else if (sp.kind == GORDER_GEOM_CYLINDER) {   // geometry.rs:422-451
+        float lo = sp.dims[1], hi = sp.dims[2];
+        a.shape_radius = sp.dims[0];
+        if (isinf(lo) && lo < 0 && isinf(hi) && hi > 0) { p[sp.axis] = inf_pos; a.shape_height = CUDART_INF_F; }
+        else { p[sp.axis] = __fadd_rn(p[sp.axis], lo); a.shape_height = __fsub_rn(hi, lo); }
+    } else {   // sphere, geometry.rs:507-514
+        a.shape_radius = sp.dims[0];
+    }
+    f3 o = wrap_point<PBC>(mk3(p[0], p[1], p[2]), bx);
+    a.shape_origin[0] = o.x; a.shape_origin[1] = o.y; a.shape_origin[2] = o.z;
+}
+
+__global__ void frame_setup_kernel(DeviceView v, FrameAux *aux, const float *__restrict__ box, int n_frames, int stage) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    FrameAux &a = aux[f];
+    if (stage == 0) {
+        if (v.handle_pbc) {
+            float bx = box[3 * f], by = box[3 * f + 1], bz = box[3 * f + 2];
+            if (bx == 0.0f && by == 0.0f && bz == 0.0f) raise_error(v, GORDER_ERR_ZERO_BOX, a.frame_index);
+            a.L[0] = bx; a.L[1] = by; a.L[2] = bz;
+            a.half[0] = bx / 2.0f; a.half[1] = by / 2.0f; a.half[2] = bz / 2.0f;
+        } else {
+            a.L[0] = a.L[1] = a.L[2] = 0.0f;
+            a.half[0] = a.half[1] = a.half[2] = 0.0f;
+        }
+    } else {
+        if (v.handle_pbc) construct_shape<true>(v, a);
+        else construct_shape<false>(v, a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// group centre (groan group_get_center: refined Bai-Breen; group_get_center_naive: mean).
+// Deterministic two-level reduction: every CTA writes its partial sums, a single warp per frame
+// adds them in a fixed order.  f64 partials (the reference accumulates f32 sequentially; the
+// difference is far below the resolution that matters for a sign test / shape origin).
+//   pass 0: sum cos(theta), sin(theta) per axis      -> estimate
+//   pass 1: sum min_image(p - estimate) per axis     -> centre = wrap(estimate + mean)
+// frame_list[i]: index in the batch of the i-th frame that needs the centre.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCenterBlocks = 64;
+
+__global__ void __launch_bounds__(256) group_center_partial_kernel(DeviceView v, GroupRef g, const float *__restrict__ planes,
+                                                                   const FrameAux *__restrict__ aux, const int *__restrict__ frame_list,
+                                                                   const float *__restrict__ est, double *__restrict__ partial, int pass) {
+    const int fi = blockIdx.y, f = frame_list[fi];
+    const float *fr = planes + (size_t)f * v.frame_floats;
+    const FrameAux &a = aux[f];
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const bool pbc = v.handle_pbc != 0;
+    float e[3] = {0, 0, 0}, scale[3] = {0, 0, 0};
+    if (pbc) {
+        for (int k = 0; k < 3; k++) scale[k] = __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), a.L[k]);
+        if (pass == 1) { e[0] = est[3 * fi]; e[1] = est[3 * fi + 1]; e[2] = est[3 * fi + 2]; }
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
+        const int off = g.off[i], cs = g.cs[i];
+        float p[3] = {fr[off], fr[off + cs], fr[off + 2 * (size_t)cs]};
+        if (!pbc) { acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; }
+        else if (pass == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float s, c;
+                sincosf(__fmul_rn(p[k], scale[k]), &s, &c);
+                acc[k] += c; acc[3 + k] += s;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) acc[k] += (a.L[k] > 0.0f) ? min_image(__fsub_rn(p[k], e[k]), a.L[k], a.half[k]) : __fsub_rn(p[k], e[k]);
+        }
+    }
+    __shared__ double s_red[6][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        double x = acc[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) s_red[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double x = 0;
+        for (int w = 0; w < 8; w++) x += s_red[threadIdx.x][w];
+        partial[((size_t)fi * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = x;
+    }
+}
+
+// final stage; one thread per frame (sequential over kCenterBlocks partials: fixed order).
+__global__ void group_center_final_kernel(DeviceView v, int n_group, const FrameAux *__restrict__ aux, const int *__restrict__ frame_list,
+                                          int n_list, const double *__restrict__ partial, int n_blocks, float *est, float *center, int pass) {
+    int fi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fi >= n_list) return;
+    const FrameAux &a = aux[frame_list[fi]];
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < n_blocks; b++)
+        for (int k = 0; k < 6; k++) acc[k] += partial[((size_t)fi * n_blocks + b) * 6 + k];
+    const float n = (float)n_group;
+    if (!v.handle_pbc) {
+        for (int k = 0; k < 3; k++) center[3 * fi + k] = n_group > 0 ? __fdiv_rn((float)acc[k], n) : CUDART_NAN_F;
+        return;
+    }
+    if (pass == 0) {
+        for (int k = 0; k < 3; k++) {
+            float th = __fadd_rn(atan2f(-(float)acc[3 + k], -(float)acc[k]), CUDART_PI_F);
+            est[3 * fi + k] = n_group > 0 ? __fdiv_rn(__fmul_rn(a.L[k], th), __fmul_rn(2.0f, CUDART_PI_F)) : CUDART_NAN_F;
+        }
+    } else {
+        for (int k = 0; k < 3; k++) {
+            float c = __fadd_rn(est[3 * fi + k], __fdiv_rn((float)acc[k], n));
+            center[3 * fi + k] = (a.L[k] > 0.0f) ? wrap1(c, a.L[k]) : c;
+        }
+    }
+}
+
+// copy centres into FrameAux.center (geometry reference)
+__global__ void store_center_kernel(FrameAux *aux, const int *frame_list, int n_list, const float *center) {
+    int fi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fi >= n_list) return;
+    FrameAux &a = aux[frame_list[fi]];
+    a.center[0] = center[3 * fi]; a.center[1] = center[3 * fi + 1]; a.center[2] = center[3 * fi + 2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// leaflet assignment (AssignedLeaflets::assign_lipids, leaflets.rs:1406-1435).
+// grid (ceil(n_molpad / 256), n_assign): one thread per (padded molecule, assignment frame).
+// Row written: rows[(1 + ai) * n_molpad + molpad]   (row 0 = table carried over from the last batch).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float distance_1d(float a, float b, float L, float half, bool pbc) {
+    float d = __fsub_rn(a, b);
+    return (pbc && L > 0.0f) ? min_image(d, L, half) : d;
+}
+
+__global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                             const int *__restrict__ frame_list, const float *__restrict__ center,
+                                                             const int *__restrict__ molpad_type, unsigned char *__restrict__ rows) {
+    const int ai = blockIdx.y, f = frame_list[ai];
+    const int mp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mp >= v.n_molpad) return;
+    const int t = molpad_type[mp];
+    if (t < 0) return;
+    const TypeDesc &td = v.types[t];
+    const int m = mp - td.molpad0;
+    unsigned char out = GORDER_UPPER;
+    if (m < td.n_mol) {
+        const FrameAux &a = aux[f];
+        const int ax = v.leaflet_axis;
+        const bool pbc = v.handle_pbc != 0;
+        const float L = a.L[ax], half = a.half[ax];
+        const float *fr = planes + (size_t)f * v.frame_floats + td.plane_base + m;
+        bool upper = true;
+        if (v.leaflet_mode == GORDER_LEAFLET_GLOBAL) {   // leaflets.rs:571-624, :711-732
+            float c = center[3 * ai + ax];
+            if (c != c) raise_error(v, GORDER_ERR_INVALID_GLOBAL_CENTER, a.frame_index);
+            float head = fr[td.head_off + ax * td.mpad];
+            upper = distance_1d(head, c, L, half, pbc) >= 0.0f;
+        } else if (v.leaflet_mode == GORDER_LEAFLET_INDIVIDUAL) {   // leaflets.rs:736-811
+            float head = fr[td.head_off + ax * td.mpad];
+            float total = 0.0f;
+            for (int k = 0; k < td.n_methyls; k++) {
+                float me = fr[v.methyl_offs[td.methyl_off + k] + ax * td.mpad];
+                total = __fadd_rn(total, distance_1d(head, me, L, half, pbc));
+            }
+            upper = total >= 0.0f;
+        } else if (v.leaflet_mode == GORDER_LEAFLET_MANUAL) {   // leaflets.rs:816-874
+            long long row = v.leaflet_freq_kind == GORDER_FREQ_ONCE ? 0 : a.frame_index / (v.leaflet_freq > 0 ? v.leaflet_freq : 1);
+            if (row >= td.n_manual_leaf) { raise_error(v, GORDER_ERR_MANUAL_LEAFLET_FRAME, a.frame_index); }
+            else upper = v.manual_leaflets[td.manual_leaf_off + row * td.n_mol + m] == GORDER_UPPER;
+        } else if (v.leaflet_mode == GORDER_LEAFLET_LOCAL) {   // leaflets.rs:630-707, pbc.rs:273-318
+            // centre of the membrane atoms inside an infinite cylinder around the head (brute force)
+            f3 head = mk3(fr[td.head_off], fr[td.head_off + td.mpad], fr[td.head_off + 2 * td.mpad]);
+            const float *frame0 = planes + (size_t)f * v.frame_floats;
+            const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
+            double sc = 0, ss = 0, sn = 0;
+            int cnt = 0;
+            for (int pass = 0; pass < 2; pass++) {
+                float est = 0.0f;
+                if (pass == 1) {
+                    if (!pbc || cnt == 0) break;
+                    float th = __fadd_rn(atan2f(-(float)ss, -(float)sc), CUDART_PI_F);
+                    est = __fdiv_rn(__fmul_rn(L, th), __fmul_rn(2.0f, CUDART_PI_F));
+                    sn = 0;
+                }
+                for (int i = 0; i < v.membrane.n; i++) {
+                    const int off = v.membrane.off[i], cs = v.membrane.cs[i];
+                    float p[3] = {frame0[off], frame0[off + cs], frame0[off + 2 * (size_t)cs]};
+                    float r2 = 0.0f;
+                    for (int k = 0; k < 3; k++) {
+                        if (k == ax) continue;
+                        float d = __fsub_rn(p[k], comp(head, k));
+                        if (pbc && a.L[k] > 0.0f) d = min_image(d, a.L[k], a.half[k]);
+                        r2 = __fadd_rn(r2, __fmul_rn(d, d));
+                    }
+                    if (!(__fsqrt_rn(r2) < v.leaflet_radius)) continue;
+                    if (pass == 0) {
+                        cnt++;
+                        if (pbc) { float s, c; sincosf(__fmul_rn(p[ax], scale), &s, &c); sc += c; ss += s; }
+                        else sn += p[ax];
+                    } else sn += (L > 0.0f) ? min_image(__fsub_rn(p[ax], est), L, half) : __fsub_rn(p[ax], est);
+                }
+                if (pass == 1) { float c = __fadd_rn(est, __fdiv_rn((float)sn, (float)cnt)); sn = (L > 0.0f) ? wrap1(c, L) : c; }
+            }
+            float c = (cnt == 0) ? CUDART_NAN_F : (pbc ? (float)sn : __fdiv_rn((float)sn, (float)cnt));
+            if (c != c) raise_error(v, GORDER_ERR_INVALID_LOCAL_CENTER, ((long long)t << 32) | (unsigned)m);
+            upper = distance_1d(comp(head, ax), c, L, half, pbc) >= 0.0f;
+        }
+        if (v.leaflet_flip) upper = !upper;   // maybe_flip, leaflets.rs:68-73
+        out = upper ? GORDER_UPPER : GORDER_LOWER;
+    }
+    rows[(size_t)(1 + ai) * v.n_molpad + mp] = out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dynamic membrane normals (normal.rs:160-199, pbc.rs:321-351, normal.rs:421-458).
+// One thread per (padded molecule, frame): heads within `radius` of this lipid's head (minimum
+// image, re-imaged next to the reference), centroid, 3x3 scatter matrix, eigenvector of the
+// smallest eigenvalue by cyclic Jacobi, all in registers.  Brute-force neighbour scan (round 1).
+// Output planes normals[(f*3 + c) * n_molpad + molpad]; NaN + n_points when < 3 points.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jacobi_smallest(float a00, float a01, float a02, float a11, float a12, float a22, f3 &out) {
+    float A[3][3] = {{a00, a01, a02}, {a01, a11, a12}, {a02, a12, a22}};
+    float V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; sweep++) {
+        float off = fabsf(A[0][1]) + fabsf(A[0][2]) + fabsf(A[1][2]);
+        if (off < 1e-30f) break;
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int q = p + 1; q < 3; q++) {
+                if (fabsf(A[p][q]) < 1e-37f) continue;
+                float theta = (A[q][q] - A[p][p]) / (2.0f * A[p][q]);
+                float t = copysignf(1.0f, theta) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+                float c = rsqrtf(t * t + 1.0f), s = t * c;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { float x = A[k][p], y = A[k][q]; A[k][p] = c * x - s * y; A[k][q] = s * x + c * y; }
+#pragma unroll
+                for (int k = 0; k < 3; k++) { float x = A[p][k], y = A[q][k]; A[p][k] = c * x - s * y; A[q][k] = s * x + c * y; }
+#pragma unroll
+                for (int k = 0; k < 3; k++) { float x = V[k][p], y = V[k][q]; V[k][p] = c * x - s * y; V[k][q] = s * x + c * y; }
+            }
+    }
+    int k = 0;
+    if (A[1][1] < A[k][k]) k = 1;
+    if (A[2][2] < A[k][k]) k = 2;
+    f3 n = mk3(V[0][k], V[1][k], V[2][k]);
+    out = unit_ref(n);
+}
+
+__global__ void __launch_bounds__(128) dynamic_normal_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                             const int *__restrict__ molpad_type, float *__restrict__ normals,
+                                                             int *__restrict__ normal_npoints) {
+    const int f = blockIdx.y;
+    const int mp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mp >= v.n_molpad) return;
+    const int t = molpad_type[mp];
+    float *nx = normals + ((size_t)f * 3) * v.n_molpad + mp;
+    if (t < 0) { nx[0] = CUDART_NAN_F; nx[v.n_molpad] = CUDART_NAN_F; nx[2 * (size_t)v.n_molpad] = CUDART_NAN_F; return; }
+    const TypeDesc &td = v.types[t];
+    const int m = mp - td.molpad0;
+    if (m >= td.n_mol || td.nhead_off < 0) { nx[0] = CUDART_NAN_F; nx[v.n_molpad] = CUDART_NAN_F; nx[2 * (size_t)v.n_molpad] = CUDART_NAN_F; return; }
+    const FrameAux &a = aux[f];
+    const Box bx = load_box(a);
+    const float *frame0 = planes + (size_t)f * v.frame_floats;
+    const float *fr = frame0 + td.plane_base + m;
+    const f3 ref = mk3(fr[td.nhead_off], fr[td.nhead_off + td.mpad], fr[td.nhead_off + 2 * td.mpad]);
+    const bool pbc = v.handle_pbc != 0;
+    // pass 1: centroid of the cloud (f32 running sum in group order, as the reference's fold)
+    int n = 0;
+    f3 sum = mk3(0, 0, 0);
+    for (int i = 0; i < v.normal_heads.n; i++) {
+        const int off = v.normal_heads.off[i], cs = v.normal_heads.cs[i];
+        f3 p = mk3(frame0[off], frame0[off + cs], frame0[off + 2 * (size_t)cs]);
+        f3 d = pbc ? vector_to<true>(ref, p, bx) : vector_to<false>(ref, p, bx);
+        if (norm_ref(d) < v.dynamic_radius) {
+            f3 q = pbc ? mk3(__fadd_rn(ref.x, d.x), __fadd_rn(ref.y, d.y), __fadd_rn(ref.z, d.z)) : p;
+            sum = mk3(__fadd_rn(sum.x, q.x), __fadd_rn(sum.y, q.y), __fadd_rn(sum.z, q.z));
+            n++;
+        }
+    }
+    normal_npoints[(size_t)f * v.n_molpad + mp] = n;
+    if (n < 3) { nx[0] = CUDART_NAN_F; nx[v.n_molpad] = CUDART_NAN_F; nx[2 * (size_t)v.n_molpad] = CUDART_NAN_F; return; }
+    const float fn = (float)n;
+    const f3 c = mk3(__fdiv_rn(sum.x, fn), __fdiv_rn(sum.y, fn), __fdiv_rn(sum.z, fn));
+    // pass 2: scatter matrix of the demeaned cloud
+    float a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+    for (int i = 0; i < v.normal_heads.n; i++) {
+        const int off = v.normal_heads.off[i], cs = v.normal_heads.cs[i];
+        f3 p = mk3(frame0[off], frame0[off + cs], frame0[off + 2 * (size_t)cs]);
+        f3 d = pbc ? vector_to<true>(ref, p, bx) : vector_to<false>(ref, p, bx);
+        if (norm_ref(d) < v.dynamic_radius) {
+            f3 q = pbc ? mk3(__fadd_rn(ref.x, d.x), __fadd_rn(ref.y, d.y), __fadd_rn(ref.z, d.z)) : p;
+            float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
+            a00 += dx * dx; a01 += dx * dy; a02 += dx * dz; a11 += dy * dy; a12 += dy * dz; a22 += dz * dz;
+        }
+    }
+    f3 nrm;
+    jacobi_smallest(a00, a01, a02, a11, a12, a22, nrm);
+    nx[0] = nrm.x; nx[v.n_molpad] = nrm.y; nx[2 * (size_t)v.n_molpad] = nrm.z;
+}
+
+// manual membrane normals (ManualMembraneNormal::get_normal, normal.rs:266-298): copy the row of
+// this frame into the per-frame normal planes; NaN when the frame is not available (the error is
+// raised by the accumulation kernel when the normal is actually used).
+__global__ void __launch_bounds__(256) manual_normal_kernel(DeviceView v, const FrameAux *__restrict__ aux, const int *__restrict__ molpad_type,
+                                                            float *__restrict__ normals) {
+    const int f = blockIdx.y;
+    const int mp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mp >= v.n_molpad) return;
+    float *nx = normals + ((size_t)f * 3) * v.n_molpad + mp;
+    float x = CUDART_NAN_F, y = CUDART_NAN_F, z = CUDART_NAN_F;
+    const int t = molpad_type[mp];
+    if (t >= 0) {
+        const TypeDesc &td = v.types[t];
+        const int m = mp - td.molpad0, row = aux[f].manual_norm_row;
+        if (m < td.n_mol && td.manual_norm_off >= 0 && row < td.n_manual_norm) {
+            const float *p = v.manual_normals + td.manual_norm_off + 3 * ((size_t)row * td.n_mol + m);
+            x = p[0]; y = p[1]; z = p[2];
+        }
+    }
+    nx[0] = x; nx[v.n_molpad] = y; nx[2 * (size_t)v.n_molpad] = z;
+}
+
+__global__ void __launch_bounds__(256) mask_normals_kernel(int n_molpad, const unsigned char *__restrict__ used, float *__restrict__ normals) {
+    const int f = blockIdx.y;
+    const int mp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mp >= n_molpad) return;
+    if (!used[(size_t)f * n_molpad + mp]) {
+        float *nx = normals + ((size_t)f * 3) * n_molpad + mp;
+        nx[0] = CUDART_NAN_F; nx[n_molpad] = CUDART_NAN_F; nx[2 * (size_t)n_molpad] = CUDART_NAN_F;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// accumulation helpers shared by K1 and K2
+// ---------------------------------------------------------------------------------------------
+struct AccumOut {
+    long long *bsum;                // [rows][n_slots][3]
+    unsigned long long *bcnt;       // [rows][n_slots][3]
+    long long *map_sum;             // [n_slots][3][n_bins]
+    unsigned long long *map_cnt;
+    unsigned char *normal_used;     // [F][n_molpad] or nullptr
+};
+
+// number of int accumulators per order slot in shared memory
+template <bool LEAF, bool EXTRA> struct AccLayout { static constexpr int N = LEAF ? (EXTRA ? 3 : 2) : (EXTRA ? 2 : 1); };
+//  !LEAF: [sum_total, (cnt_total)]      LEAF: [sum_up, sum_lo, (cnt_up | cnt_lo << 16)]
+
+template <bool LEAF, bool EXTRA>
+__device__ __forceinline__ void warp_commit(int *s_acc, int lane, int su, int sl, int cu, int cl) {
+    // fixed-order hardware tree (REDUX) -> deterministic; one plain shared store per value
+    const unsigned full = 0xffffffffu;
+    if (LEAF) {
+        int a = __reduce_add_sync(full, su), b = __reduce_add_sync(full, sl);
+        if (EXTRA) {
+            int c = __reduce_add_sync(full, cu | (cl << 16));
+            if (lane == 0) { s_acc[0] = a; s_acc[1] = b; s_acc[2] = c; }
+        } else if (lane == 0) { s_acc[0] = a; s_acc[1] = b; }
+    } else {
+        int a = __reduce_add_sync(full, su + sl);
+        if (EXTRA) {
+            int c = __reduce_add_sync(full, cu + cl);
+            if (lane == 0) { s_acc[0] = a; s_acc[1] = c; }
+        } else if (lane == 0) s_acc[0] = a;
+    }
+}
+
+// CTA epilogue: add the per-warp partials of every order slot to this frame's accumulators.
+template <bool LEAF, bool EXTRA>
+__device__ __forceinline__ void cta_flush(const DeviceView &v, const AccumOut &o, const int *s_acc, int n_orders, int slot0, int tw_row,
+                                          int cnt_total, int cnt_up) {
+    constexpr int NA = AccLayout<LEAF, EXTRA>::N;
+    for (int i = threadIdx.x; i < n_orders; i += blockDim.x) {
+        long long acc[NA];
+#pragma unroll
+        for (int k = 0; k < NA; k++) acc[k] = 0;
+        int c_up = 0, c_lo = 0;
+        for (int w = 0; w < kWarps; w++) {
+            const int *p = s_acc + ((size_t)w * n_orders + i) * NA;
+            if (LEAF) {
+                acc[0] += p[0]; acc[1] += p[1];
+                if (EXTRA) { c_up += p[2] & 0xffff; c_lo += (p[2] >> 16) & 0xffff; }
+            } else {
+                acc[0] += p[0];
+                if (EXTRA) c_up += p[1];
+            }
+        }
+        const size_t base = ((size_t)tw_row * v.n_slots + slot0 + i) * 3;
+        if (LEAF) {
+            if (!EXTRA) { c_up = cnt_up; c_lo = cnt_total - cnt_up; }
+            if (c_up) { atomicAdd((unsigned long long *)&o.bsum[base + GORDER_ACC_UPPER], (unsigned long long)acc[0]); atomicAdd(&o.bcnt[base + GORDER_ACC_UPPER], (unsigned long long)c_up); }
+            if (c_lo) { atomicAdd((unsigned long long *)&o.bsum[base + GORDER_ACC_LOWER], (unsigned long long)acc[1]); atomicAdd(&o.bcnt[base + GORDER_ACC_LOWER], (unsigned long long)c_lo); }
+        } else {
+            if (!EXTRA) c_up = cnt_total;
+            if (c_up) { atomicAdd((unsigned long long *)&o.bsum[base + GORDER_TOTAL], (unsigned long long)acc[0]); atomicAdd(&o.bcnt[base + GORDER_TOTAL], (unsigned long long)c_up); }
+        }
+    }
+}
+
+template <bool LEAF>
+__device__ __forceinline__ void map_add(const DeviceView &v, const AccumOut &o, int slot, const f3 &pos, int q, bool upper) {
+    long long b = map_bin(v.map, pos);
+    if (b < 0) return;
+    // with leaflets the total map is upper + lower (derived when results are fetched)
+    const int which = LEAF ? (upper ? GORDER_ACC_UPPER : GORDER_ACC_LOWER) : GORDER_TOTAL;
+    const size_t i = ((size_t)slot * 3 + which) * v.map.n_bins + b;
+    atomicAdd((unsigned long long *)&o.map_sum[i], (unsigned long long)(long long)q);
+    atomicAdd(&o.map_cnt[i], 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: bond engine (topology/bond.rs:396-446 + :184-215).
+//   grid (n_chunks, F); a lane owns MPT consecutive molecules of one molecule type and walks the
+//   type's bond table (staged in shared memory); every plane read is a fully-used 128 B * MPT line.
+// template: MPT molecules per thread; PBC; NVEC per-molecule normal vector (dynamic / manual)
+//           instead of a static axis; LEAF per-leaflet accumulation; EXTRA geometry filter / maps.
+// ---------------------------------------------------------------------------------------------
+template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA>
+__global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                            const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
+                                                            const int *__restrict__ normal_npoints, AccumOut o) {
+    constexpr int NA = AccLayout<LEAF, EXTRA>::N;
+    extern __shared__ int smem[];
+    const Chunk ch = v.chunks[blockIdx.x];
+    const TypeDesc td = v.types[ch.type];
+    const int f = blockIdx.y;
+    const FrameAux &ax = aux[f];
+    const int nb = td.n_items;
+    BondItem *s_bonds = reinterpret_cast<BondItem *>(smem);
+    int *s_acc = smem + 2 * nb;                 // [kWarps][nb][NA]
+    int *s_cnt = s_acc + kWarps * nb * NA;      // [2] valid, valid & upper
+    for (int i = threadIdx.x; i < nb; i += kBlock) s_bonds[i] = v.bonds[td.item_off + i];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m0 = ch.first_mol + threadIdx.x * MPT;
+    const bool active = m0 < td.mpad;
+    bool valid[MPT], up[MPT];
+    f3 nrm[MPT];
+    const Box bx = load_box(ax);
+    int nvalid = 0, nup = 0;
+#pragma unroll
+    for (int j = 0; j < MPT; j++) {
+        valid[j] = active && (m0 + j < td.n_mol);
+        up[j] = false;
+        if (LEAF && valid[j]) up[j] = leaf_rows[(size_t)ax.leaf_row * v.n_molpad + td.molpad0 + m0 + j] == GORDER_UPPER;
+        if (NVEC) {
+            nrm[j] = mk3(0.f, 0.f, 1.f);
+            if (valid[j]) {
+                const float *np = normals + ((size_t)f * 3) * v.n_molpad + td.molpad0 + m0 + j;
+                nrm[j] = mk3(np[0], np[v.n_molpad], np[2 * (size_t)v.n_molpad]);
+            }
+        }
+        nvalid += valid[j]; nup += valid[j] && up[j];
+    }
+    if (!EXTRA) {
+        int a = __reduce_add_sync(0xffffffffu, nvalid), b = __reduce_add_sync(0xffffffffu, nup);
+        if (lane == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], b); }
+    }
+    bool any_used[MPT];
+#pragma unroll
+    for (int j = 0; j < MPT; j++) any_used[j] = false;
+
+    const float *base = planes + (size_t)f * v.frame_floats + td.plane_base + m0;
+    const int mpad = td.mpad;
+    for (int b = 0; b < nb; b++) {
+        const BondItem bi = s_bonds[b];
+        Vec<MPT> x1, y1, z1, x2, y2, z2;
+        if (active) {
+            x1.load(base + bi.a_off); y1.load(base + bi.a_off + mpad); z1.load(base + bi.a_off + 2 * mpad);
+            x2.load(base + bi.b_off); y2.load(base + bi.b_off + mpad); z2.load(base + bi.b_off + 2 * mpad);
+        }
+        int su = 0, sl = 0, cu = 0, cl = 0;
+#pragma unroll
+        for (int j = 0; j < MPT; j++) {
+            if (!valid[j]) continue;
+            const f3 p1 = mk3(x1.v[j], y1.v[j], z1.v[j]), p2 = mk3(x2.v[j], y2.v[j], z2.v[j]);
+            const f3 d = vector_to<PBC>(p1, p2, bx);
+            f3 mid;
+            if (EXTRA) {
+                // bond_pos = pos1 + vec / 2 (bond.rs:422)
+                mid = mk3(__fadd_rn(p1.x, d.x * 0.5f), __fadd_rn(p1.y, d.y * 0.5f), __fadd_rn(p1.z, d.z * 0.5f));
+                if (v.shape.kind != GORDER_GEOM_NONE && !shape_inside<PBC>(v.shape, ax, bx, mid)) continue;
+                any_used[j] = true;
+            }
+            float s;
+            if (NVEC) {
+                if (nrm[j].x != nrm[j].x) {   // normal could not be computed (normal.rs:424)
+                    int npts = normal_npoints ? normal_npoints[(size_t)f * v.n_molpad + td.molpad0 + m0 + j] : 0;
+                    raise_error(v, v.normal_mode == GORDER_NORMAL_DYNAMIC ? GORDER_ERR_DYNAMIC_NORMAL_POINTS : GORDER_ERR_MANUAL_NORMAL_FRAME, npts);
+                    continue;
+                }
+                s = calc_sch(d, nrm[j]);
+            } else s = calc_sch_axis(d, comp(d, v.normal_axis));
+            if (s != s) {   // NaN coordinate reached the engine: AnalysisError::UndefinedPosition
+                raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | ((long long)b << 32) | (unsigned)(m0 + j));
+                continue;
+            }
+            const int q = order_value(s);
+            if (LEAF && !up[j]) { sl += q; cl++; } else { su += q; cu++; }
+            if (EXTRA && v.map.enabled) map_add<LEAF>(v, o, td.slot0 + b, mid, q, up[j]);
+        }
+        warp_commit<LEAF, EXTRA>(s_acc + ((size_t)warp * nb + b) * NA, lane, su, sl, cu, cl);
+    }
+    if (EXTRA && o.normal_used) {
+#pragma unroll
+        for (int j = 0; j < MPT; j++)
+            if (valid[j] && any_used[j]) o.normal_used[(size_t)f * v.n_molpad + td.molpad0 + m0 + j] = 1;
+    }
+    __syncthreads();
+    cta_flush<LEAF, EXTRA>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: united-atom engine (uaorder.rs:400-437): rebuild 1-3 hydrogens per carbon from 2-3 helper
+// heavy atoms, then the same S / accumulate tail as K1.  One molecule per lane (the hydrogen
+// construction is register-heavy), carbon-type table in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <bool PBC>
+__device__ __forceinline__ int predict_hydrogens(const DeviceView &v, int kind, const f3 &t, const f3 &h1, const f3 &h2, const f3 &h3,
+                                                 const Box &bx, f3 (&out)[3]) {
+    const float BOND_LENGTH = 0.109f;   // uaorder.rs:39
+    if (kind == GORDER_UA_CH3) {   // predict_hydrogens_ch3, uaorder.rs:947-981
+        f3 th1 = vector_to<PBC>(t, h1, bx), th2 = vector_to<PBC>(t, h2, bx);
+        f3 axis = unit_ref(cross_ref(th2, th1));
+        f3 hv1 = rotate_axis(th1, axis, v.tet_s, v.tet_c);
+        out[0] = wrap_point<PBC>(shift_ref(t, hv1, BOND_LENGTH), bx);
+        f3 nth1 = unit_ref(th1);
+        out[1] = wrap_point<PBC>(shift_ref(t, rotate_axis(hv1, nth1, v.ch3_s, v.ch3_c), BOND_LENGTH), bx);
+        out[2] = wrap_point<PBC>(shift_ref(t, rotate_axis(hv1, nth1, -v.ch3_s, v.ch3_c), BOND_LENGTH), bx);
+        return 3;
+    } else if (kind == GORDER_UA_CH2) {   // predict_hydrogens_ch2, uaorder.rs:985-1020
+        f3 th1 = unit_ref(vector_to<PBC>(t, h1, bx)), th2 = unit_ref(vector_to<PBC>(t, h2, bx));
+        f3 plane_normal = cross_ref(th2, th1);
+        f3 rot_axis = unit_ref(mk3(__fsub_rn(th1.x, th2.x), __fsub_rn(th1.y, th2.y), __fsub_rn(th1.z, th2.z)));
+        f3 rot_vec = cross_ref(plane_normal, rot_axis);
+        f3 ax = unit_ref(rot_axis);
+        out[0] = wrap_point<PBC>(shift_ref(t, rotate_axis(rot_vec, ax, v.tet_half_s, v.tet_half_c), BOND_LENGTH), bx);
+        out[1] = wrap_point<PBC>(shift_ref(t, rotate_axis(rot_vec, ax, -v.tet_half_s, v.tet_half_c), BOND_LENGTH), bx);
+        return 2;
+    } else if (kind == GORDER_UA_CH1_UNSAT) {   // predict_hydrogen_ch1_unsaturated, uaorder.rs:1024-1045
+        f3 th1 = vector_to<PBC>(t, h1, bx), th2 = vector_to<PBC>(t, h2, bx);
+        // gamma = angle(th1, th2); rotation by pi - gamma/2:  sin = cos(gamma/2), cos = -sin(gamma/2)... evaluated
+        // with the half-angle identities from cos(gamma) (no acos on the device)
+        float n1 = norm_ref(th1), n2 = norm_ref(th2);
+        float cg = __fdiv_rn(dot_ref(th1, th2), __fmul_rn(n1, n2));
+        cg = fminf(1.0f, fmaxf(-1.0f, cg));
+        if (n1 == 0.0f || n2 == 0.0f) cg = 1.0f;
+        float ch = sqrtf(fmaxf(0.0f, 0.5f * (1.0f + cg)));   // cos(gamma/2)
+        float sh = sqrtf(fmaxf(0.0f, 0.5f * (1.0f - cg)));   // sin(gamma/2)
+        f3 axis = unit_ref(cross_ref(th1, th2));
+        // sin(pi - g/2) = sin(g/2), cos(pi - g/2) = -cos(g/2)
+        f3 hv = rotate_axis(th2, axis, sh, -ch);
+        out[0] = wrap_point<PBC>(shift_ref(t, hv, BOND_LENGTH), bx);
+        return 1;
+    } else {   // predict_hydrogen_ch1_saturated, uaorder.rs:1087-1104
+        f3 a = unit_ref(vector_to<PBC>(t, h1, bx)), b = unit_ref(vector_to<PBC>(t, h2, bx)), c = unit_ref(vector_to<PBC>(t, h3, bx));
+        f3 s = mk3(__fadd_rn(__fadd_rn(a.x, b.x), c.x), __fadd_rn(__fadd_rn(a.y, b.y), c.y), __fadd_rn(__fadd_rn(a.z, b.z), c.z));
+        out[0] = wrap_point<PBC>(shift_ref(t, mk3(-s.x, -s.y, -s.z), BOND_LENGTH), bx);
+        return 1;
+    }
+}
+
+template <bool PBC, bool NVEC, bool LEAF, bool EXTRA>
+__global__ void __launch_bounds__(kBlock) ua_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                          const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
+                                                          const int *__restrict__ normal_npoints, AccumOut o) {
+    constexpr int NA = AccLayout<LEAF, EXTRA>::N;
+    extern __shared__ int smem[];
+    const Chunk ch = v.chunks[blockIdx.x];
+    const TypeDesc td = v.types[ch.type];
+    const int f = blockIdx.y;
+    const FrameAux &ax = aux[f];
+    const int ni = td.n_items, no = td.n_orders;
+    UAItem *s_items = reinterpret_cast<UAItem *>(smem);
+    int *s_acc = smem + 8 * ni;                 // [kWarps][no][NA]
+    int *s_cnt = s_acc + kWarps * no * NA;
+    for (int i = threadIdx.x; i < ni; i += kBlock) s_items[i] = v.ua[td.item_off + i];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = ch.first_mol + threadIdx.x;
+    const bool valid = m < td.n_mol;
+    const Box bx = load_box(ax);
+    bool up = false;
+    if (LEAF && valid) up = leaf_rows[(size_t)ax.leaf_row * v.n_molpad + td.molpad0 + m] == GORDER_UPPER;
+    f3 nrm = mk3(v.normal_axis == 0 ? 1.f : 0.f, v.normal_axis == 1 ? 1.f : 0.f, v.normal_axis == 2 ? 1.f : 0.f);
+    bool normal_bad = false;
+    if (NVEC && valid) {
+        const float *np = normals + ((size_t)f * 3) * v.n_molpad + td.molpad0 + m;
+        nrm = mk3(np[0], np[v.n_molpad], np[2 * (size_t)v.n_molpad]);
+        // the normal is requested for every molecule, before the geometry test (uaorder.rs:412-413)
+        if (nrm.x != nrm.x) {
+            normal_bad = true;
+            int npts = normal_npoints ? normal_npoints[(size_t)f * v.n_molpad + td.molpad0 + m] : 0;
+            raise_error(v, v.normal_mode == GORDER_NORMAL_DYNAMIC ? GORDER_ERR_DYNAMIC_NORMAL_POINTS : GORDER_ERR_MANUAL_NORMAL_FRAME, npts);
+        }
+    }
+    if (!EXTRA) {
+        int a = __reduce_add_sync(0xffffffffu, (int)valid), b = __reduce_add_sync(0xffffffffu, (int)(valid && up));
+        if (lane == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], b); }
+    }
+    const float *base = planes + (size_t)f * v.frame_floats + td.plane_base + m;
+    const int mpad = td.mpad;
+    for (int i = 0; i < ni; i++) {
+        const UAItem it = s_items[i];
+        const int nh = it.kind == GORDER_UA_CH3 ? 3 : (it.kind == GORDER_UA_CH2 ? 2 : 1);
+        int q[3] = {0, 0, 0};
+        bool in[3] = {false, false, false};
+        if (valid && !normal_bad) {
+            const f3 t = mk3(__ldg(base + it.t_off), __ldg(base + it.t_off + mpad), __ldg(base + it.t_off + 2 * mpad));
+            const f3 h1 = mk3(__ldg(base + it.h1_off), __ldg(base + it.h1_off + mpad), __ldg(base + it.h1_off + 2 * mpad));
+            const f3 h2 = mk3(__ldg(base + it.h2_off), __ldg(base + it.h2_off + mpad), __ldg(base + it.h2_off + 2 * mpad));
+            f3 h3 = mk3(0, 0, 0);
+            if (it.kind == GORDER_UA_CH1_SAT) h3 = mk3(__ldg(base + it.h3_off), __ldg(base + it.h3_off + mpad), __ldg(base + it.h3_off + 2 * mpad));
+            f3 hyd[3];
+            predict_hydrogens<PBC>(v, it.kind, t, h1, h2, h3, bx, hyd);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (k >= nh) break;
+                const f3 d = vector_to<PBC>(t, hyd[k], bx);   // calculate_sch, uaorder.rs:375-397
+                f3 mid;
+                if (EXTRA) {
+                    // sic: bond_pos = hydrogen + vec / 2 (uaorder.rs:385)
+                    mid = mk3(__fadd_rn(hyd[k].x, d.x * 0.5f), __fadd_rn(hyd[k].y, d.y * 0.5f), __fadd_rn(hyd[k].z, d.z * 0.5f));
+                    if (v.shape.kind != GORDER_GEOM_NONE && !shape_inside<PBC>(v.shape, ax, bx, mid)) continue;
+                }
+                const float s = calc_sch(d, nrm);
+                if (s != s) {
+                    raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | ((long long)i << 32) | (unsigned)m);
+                    continue;
+                }
+                q[k] = order_value(s);
+                in[k] = true;
+                if (EXTRA && v.map.enabled) map_add<LEAF>(v, o, td.slot0 + it.slot_rel + k, mid, q[k], up);
+            }
+        }
+        for (int k = 0; k < nh; k++) {   // warp-uniform trip count
+            int su = 0, sl = 0, cu = 0, cl = 0;
+            if (in[k]) { if (LEAF && !up) { sl = q[k]; cl = 1; } else { su = q[k]; cu = 1; } }
+            warp_commit<LEAF, EXTRA>(s_acc + ((size_t)warp * no + it.slot_rel + k) * NA, lane, su, sl, cu, cl);
+        }
+    }
+    __syncthreads();
+    cta_flush<LEAF, EXTRA>(v, o, s_acc, no, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fold: add the per-frame accumulators of a batch into the running totals (order.rs:160-188).
+// One thread per (slot, leaf); frames added in ascending order (fixed order, integer anyway).
+// With leaflets the kernels only fill upper / lower; total = upper + lower is completed here
+// (bond.rs:184-215 adds every sample to total and to exactly one leaflet).
+// ---------------------------------------------------------------------------------------------
+__global__ void fold_kernel(int n_slots, int n_rows, int leaf, long long *__restrict__ bsum, unsigned long long *__restrict__ bcnt,
+                            long long *__restrict__ tot_sum, unsigned long long *__restrict__ tot_cnt) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    long long ts[3] = {0, 0, 0};
+    unsigned long long tc[3] = {0, 0, 0};
+    for (int r = 0; r < n_rows; r++) {
+        size_t b = ((size_t)r * n_slots + s) * 3;
+        if (leaf) {
+            bsum[b + GORDER_TOTAL] = bsum[b + GORDER_ACC_UPPER] + bsum[b + GORDER_ACC_LOWER];
+            bcnt[b + GORDER_TOTAL] = bcnt[b + GORDER_ACC_UPPER] + bcnt[b + GORDER_ACC_LOWER];
+        }
+        for (int k = 0; k < 3; k++) { ts[k] += bsum[b + k]; tc[k] += bcnt[b + k]; }
+    }
+    for (int k = 0; k < 3; k++) { tot_sum[s * 3 + k] += ts[k]; tot_cnt[s * 3 + k] += tc[k]; }
+}
+
+}  // namespace gorder

@@ -1,0 +1,145 @@
+"""Host-side mirror of the reference's per-worker analysis state.
+
+``SystemTopology`` here plays the role of ``gorder``'s ``SystemTopology``
+(``src/analysis/topology/mod.rs:35-65``): it is built once from the classified molecule types
+(``SystemTopology::new``, :70-118), is fed frames (``analyze_frame``, ``src/analysis/common.rs:201-235``)
+and is reduced into raw accumulators (``ParallelTrajData::reduce``, ``topology/mod.rs:256-272``).
+All the work happens in the CUDA library behind the C ABI of ``include/gorder_b200.h``; this class
+only marshals numpy / torch buffers into plain pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import abi
+from ._lib import lib
+
+
+def _ptr(a) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(None)
+
+
+class SystemTopology:
+    """One engine instance on one GPU (the reference clones one ``SystemTopology`` per thread)."""
+
+    def __init__(self, setup: abi.EngineSetup):
+        self.setup = setup
+        self._c = setup.to_c()
+        self._h = C.c_void_p()
+        rc = lib().gorder_gpu_create(C.byref(self._c), C.byref(self._h))
+        if rc != abi.OK:
+            self._h = C.c_void_p()
+            raise abi.GorderError(rc)
+        self._next_frame = 0
+
+    # -- frames ---------------------------------------------------------------------------------
+    def _frame_index(self, n: int, frame_index) -> np.ndarray:
+        if frame_index is None:
+            fi = self._next_frame + np.arange(n, dtype=np.int64) * self.setup.step
+        else:
+            fi = np.ascontiguousarray(frame_index, dtype=np.int64)
+            if fi.size != n:
+                raise ValueError("frame_index must have one entry per frame")
+        if n:
+            self._next_frame = int(fi[-1]) + self.setup.step
+        return fi
+
+    def _check(self, rc: int):
+        if rc != abi.OK:
+            buf = C.create_string_buffer(512)
+            lib().gorder_gpu_last_error(self._h, buf, 512)
+            raise abi.GorderError(rc, buf.value.decode(errors="replace"), int(lib().gorder_gpu_error_detail(self._h)))
+
+    def analyze_frames(self, xyz, box, frame_index=None):
+        """``analyze_frame`` for a batch: ``xyz`` [F][n_atoms][3] f32 host array, ``box`` [F][3]."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, self.setup.n_atoms, 3)
+        n = xyz.shape[0]
+        box = np.ascontiguousarray(box, dtype=np.float32).reshape(n, 3) if box is not None else None
+        fi = self._frame_index(n, frame_index)
+        self._check(lib().gorder_gpu_submit(self._h, _ptr(xyz), _ptr(box), _ptr(fi), n))
+
+    def analyze_frames_native(self, planes, box, frame_index=None):
+        """Frames already in the native plane layout (host memory)."""
+        planes = np.ascontiguousarray(planes, dtype=np.float32).reshape(-1, self.frame_floats)
+        n = planes.shape[0]
+        box = np.ascontiguousarray(box, dtype=np.float32).reshape(n, 3) if box is not None else None
+        fi = self._frame_index(n, frame_index)
+        self._check(lib().gorder_gpu_submit_native(self._h, _ptr(planes), _ptr(box), _ptr(fi), n))
+
+    def analyze_frames_device(self, d_ptr: int, d_box: int, n_frames: int, frame_index=None, native: bool = False):
+        """Frames resident in device memory (raw device pointers, e.g. ``tensor.data_ptr()``)."""
+        fi = self._frame_index(n_frames, frame_index)
+        fn = lib().gorder_gpu_submit_native_device if native else lib().gorder_gpu_submit_device
+        self._check(fn(self._h, C.c_void_p(d_ptr), C.c_void_p(d_box), _ptr(fi), n_frames))
+
+    # -- layout -----------------------------------------------------------------------------------
+    @property
+    def frame_floats(self) -> int:
+        n = C.c_int64(0)
+        lib().gorder_gpu_native_layout(self._h, C.byref(n), None, None)
+        return int(n.value)
+
+    def native_layout(self):
+        """(frame_floats, plane_offset[n_atoms], plane_cstride[n_atoms]); offset -1 = atom not needed."""
+        n = C.c_int64(0)
+        off = np.zeros(self.setup.n_atoms, np.int32)
+        cs = np.zeros(self.setup.n_atoms, np.int32)
+        lib().gorder_gpu_native_layout(self._h, C.byref(n), _ptr(off), _ptr(cs))
+        return int(n.value), off, cs
+
+    def to_native(self, xyz) -> np.ndarray:
+        """Host-side gather of AoS frames into the native layout (what the Rust shim does while it
+        copies the Master group into its pinned batch buffer)."""
+        xyz = np.asarray(xyz, dtype=np.float32).reshape(-1, self.setup.n_atoms, 3)
+        ff, off, cs = self.native_layout()
+        out = np.zeros((xyz.shape[0], ff), np.float32)
+        sel = np.nonzero(off >= 0)[0]
+        for c in range(3):
+            out[:, off[sel] + c * cs[sel]] = xyz[:, sel, c]
+        return out
+
+    # -- leaflets / reduce ---------------------------------------------------------------------------
+    def set_leaflets(self, table, frame_index: int = 0):
+        t = np.ascontiguousarray(table, dtype=np.uint8)
+        self._check(lib().gorder_gpu_set_leaflets(self._h, _ptr(t), int(frame_index)))
+
+    def sync(self):
+        self._check(lib().gorder_gpu_sync(self._h))
+
+    def accumulator_block(self):
+        """(device pointer, n int64 words) of the contiguous accumulator block (for the NCCL reduce)."""
+        p, n = C.c_void_p(), C.c_int64(0)
+        self._check(lib().gorder_gpu_accumulator_block(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def stats(self):
+        k, f = C.c_int64(0), C.c_int64(0)
+        lib().gorder_gpu_stats(self._h, C.byref(k), C.byref(f))
+        return {"kernel_launches": int(k.value), "frames": int(f.value)}
+
+    @property
+    def stream(self) -> int:
+        return int(lib().gorder_gpu_stream(self._h) or 0)
+
+    def finish(self) -> abi.RawResults:
+        """``ParallelTrajData::reduce`` for one GPU: fetch the raw accumulators."""
+        try:
+            return abi.fetch_results(lib(), self._h, "gorder_gpu", self.setup)
+        except abi.GorderError as e:
+            buf = C.create_string_buffer(512)
+            lib().gorder_gpu_last_error(self._h, buf, 512)
+            raise abi.GorderError(e.code, buf.value.decode(errors="replace"), int(lib().gorder_gpu_error_detail(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().gorder_gpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

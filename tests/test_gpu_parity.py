@@ -1,0 +1,160 @@
+"""GPU parity tests proper: CUDA engine (through the C ABI) vs the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+from gorder_b200 import abi, synthetic
+
+from parity import assert_raw_parity, run_both
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(sys_, n, step=1):
+    xyz, box, idx = sys_.frames(0, n, step)
+    return xyz, box, idx
+
+
+@pytest.mark.parametrize("n_lipids,mpt", [(37, 1), (1000, 1), (5000, 2), (5000, 4)])
+def test_cg_basic(n_lipids, mpt, monkeypatch):
+    monkeypatch.setenv("GORDER_MPT", str(mpt))
+    s = synthetic.s_cg(n_lipids, leaflet_mode=abi.LEAFLET_NONE)
+    xyz, box, idx = _frames(s, 5)
+    g, r = run_both(s.setup, xyz, box, idx)
+    assert r.count[:, 0].min() == n_lipids * 5
+    assert_raw_parity(g, r, s.setup, what=f"cg basic {n_lipids}")
+
+
+@pytest.mark.parametrize("mode", [abi.LEAFLET_GLOBAL, abi.LEAFLET_INDIVIDUAL])
+@pytest.mark.parametrize("freq", [("every", 1), ("every", 3), ("once", 1)])
+def test_cg_leaflets(mode, freq):
+    kind, n = freq
+    s = synthetic.s_cg(600, leaflet_mode=mode, leaflet_freq_kind=abi.FREQ_ONCE if kind == "once" else abi.FREQ_EVERY,
+                       leaflet_freq=n, collect_leaflets=True, timewise=True, split_types=3)
+    xyz, box, idx = _frames(s, 8)
+    g, r = run_both(s.setup, xyz, box, idx, batches=3)
+    assert g.leaflets is not None and g.leaflets.shape[1] == 600
+    assert_raw_parity(g, r, s.setup, what=f"cg leaflets {mode} {freq}")
+
+
+def test_cg_leaflets_flip_nopbc():
+    s = synthetic.s_cg(300, leaflet_mode=abi.LEAFLET_GLOBAL, leaflet_flip=True, handle_pbc=False, collect_leaflets=True)
+    xyz, box, idx = _frames(s, 4)
+    g, r = run_both(s.setup, xyz, box, idx)
+    assert_raw_parity(g, r, s.setup, what="flip nopbc")
+
+
+def test_native_layout_matches_aos():
+    s = synthetic.s_cg(700, leaflet_mode=abi.LEAFLET_GLOBAL)
+    xyz, box, idx = _frames(s, 4)
+    g1, r = run_both(s.setup, xyz, box, idx)
+    g2, _ = run_both(s.setup, xyz, box, idx, native=True)
+    np.testing.assert_array_equal(g1.sum, g2.sum)
+    np.testing.assert_array_equal(g1.count, g2.count)
+    assert_raw_parity(g2, r, s.setup, what="native")
+
+
+def test_aa_basic_and_maps():
+    s = synthetic.s_aa(64, n_water=500, leaflet_mode=abi.LEAFLET_GLOBAL, map_enabled=True, map_plane=abi.PLANE_XY,
+                       map_bin=(0.5, 0.5))
+    s.setup.map_span_x = (0.0, float(s.box[0]))
+    s.setup.map_span_y = (0.0, float(s.box[1]))
+    xyz, box, idx = _frames(s, 6)
+    g, r = run_both(s.setup, xyz, box, idx, batches=2)
+    assert_raw_parity(g, r, s.setup, what="aa maps")
+
+
+@pytest.mark.parametrize("geom", ["cuboid", "cylinder", "sphere", "cylinder_sel", "cuboid_inverted"])
+def test_geometry(geom):
+    kw = dict(leaflet_mode=abi.LEAFLET_GLOBAL)
+    if geom.startswith("cuboid"):
+        kw.update(geom_kind=abi.GEOM_CUBOID, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
+                  geom_dims=(-3.0, 2.5, float("-inf"), float("inf"), -1.0, 4.0), geom_invert=geom.endswith("inverted"))
+    elif geom == "cylinder":
+        kw.update(geom_kind=abi.GEOM_CYLINDER, geom_ref_kind=abi.GEOMREF_POINT, geom_ref_point=(1.0, 2.0, 3.0),
+                  geom_dims=(4.0, float("-inf"), float("inf")), geom_axis=abi.AXIS_Z)
+    elif geom == "cylinder_sel":
+        kw.update(geom_kind=abi.GEOM_CYLINDER, geom_ref_kind=abi.GEOMREF_SELECTION, geom_dims=(3.5, -2.0, 5.0),
+                  geom_axis=abi.AXIS_Z)
+    else:
+        kw.update(geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_BOX_CENTER, geom_dims=(4.5,))
+    s = synthetic.s_cg(800, **kw)
+    if geom == "cylinder_sel":
+        s.setup.geom_ref = np.arange(0, 40 * 12, dtype=np.int32)   # first 40 lipids
+    xyz, box, idx = _frames(s, 5)
+    g, r = run_both(s.setup, xyz, box, idx)
+    assert 0 < r.count[:, 0].min() < 800 * 5, "geometry filter should keep some, not all"
+    assert_raw_parity(g, r, s.setup, what=f"geometry {geom}")
+
+
+@pytest.mark.parametrize("with_sat", [False, True])
+def test_ua(with_sat):
+    s = synthetic.s_ua(96, with_ch1_sat=with_sat, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True)
+    xyz, box, idx = _frames(s, 6)
+    g, r = run_both(s.setup, xyz, box, idx, batches=2)
+    assert g.n_slots == (63 if with_sat else 64)
+    assert_raw_parity(g, r, s.setup, what="ua")
+
+
+def test_dynamic_normals():
+    s = synthetic.s_cg(400, leaflet_mode=abi.LEAFLET_GLOBAL, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0,
+                       collect_normals=True)
+    xyz, box, idx = _frames(s, 3)
+    g, r = run_both(s.setup, xyz, box, idx)
+    assert_raw_parity(g, r, s.setup, what="dynamic normals")
+
+
+def test_manual_normals_and_leaflets():
+    s = synthetic.s_cg(200, leaflet_mode=abi.LEAFLET_MANUAL, normal_mode=abi.NORMAL_MANUAL)
+    rng = np.random.default_rng(5)
+    m = s.setup.moltypes[0]
+    m.manual_leaflets = rng.integers(0, 2, (4, 200)).astype(np.uint8)
+    nrm = rng.normal(size=(4, 200, 3)).astype(np.float32)
+    m.manual_normals = nrm
+    xyz, box, idx = _frames(s, 4)
+    g, r = run_both(s.setup, xyz, box, idx)
+    assert_raw_parity(g, r, s.setup, what="manual")
+
+
+def test_local_leaflets():
+    s = synthetic.s_cg(150, leaflet_mode=abi.LEAFLET_LOCAL, leaflet_radius=2.5, collect_leaflets=True)
+    xyz, box, idx = _frames(s, 2)
+    g, r = run_both(s.setup, xyz, box, idx)
+    assert_raw_parity(g, r, s.setup, what="local leaflets")
+
+
+def test_determinism():
+    s = synthetic.s_cg(3000, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True)
+    xyz, box, idx = _frames(s, 6)
+    g1, _ = run_both(s.setup, xyz, box, idx)
+    g2, _ = run_both(s.setup, xyz, box, idx, batches=3)
+    np.testing.assert_array_equal(g1.sum, g2.sum)
+    np.testing.assert_array_equal(g1.tw_sum, g2.tw_sum)
+
+
+def test_errors():
+    from gorder_b200 import SystemTopology
+    s = synthetic.s_cg(100, leaflet_mode=abi.LEAFLET_GLOBAL)
+    xyz, box, idx = _frames(s, 2)
+    bad = xyz.copy()
+    bad[1, 5, 1] = np.nan
+    eng = SystemTopology(s.setup)
+    eng.analyze_frames(bad, box, idx)
+    with pytest.raises(abi.GorderError) as e:
+        eng.finish()
+    assert e.value.code == abi.ERR_UNDEFINED_POSITION and e.value.index == 5
+    eng.close()
+    eng = SystemTopology(s.setup)
+    zb = box.copy()
+    zb[0] = 0
+    eng.analyze_frames(xyz, zb, idx)
+    with pytest.raises(abi.GorderError) as e:
+        eng.finish()
+    assert e.value.code == abi.ERR_ZERO_BOX
+    eng.close()
+    # a shard that does not hold the assignment frame
+    s2 = synthetic.s_cg(100, leaflet_mode=abi.LEAFLET_GLOBAL, leaflet_freq_kind=abi.FREQ_ONCE)
+    eng = SystemTopology(s2.setup)
+    with pytest.raises(abi.GorderError) as e:
+        eng.analyze_frames(xyz, box, np.array([4, 5]))
+    assert e.value.code == abi.ERR_LEAFLET_FRAME_UNAVAILABLE
+    eng.close()
