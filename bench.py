@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the per-frame order-parameter engine on BASELINE.json's workload.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the oracle port on host cores)
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d "S-CG"): CGOrder on a synthetic Martini bilayer of
+83 334 lipids = 1 000 008 beads, 11 bond types (916 674 S evaluations per frame), Global leaflet
+assignment every frame, static z normal, PBC.  A "step" is one pass of the hot path over one batch of
+``--frames`` frames.  Weak scaling: every rank analyses its own frames (contiguous frame ranges, no
+data-path collective); the integer accumulators are combined with ONE NCCL sum-reduce at the end.
+
+value = whole-job S evaluations / s with the frames already resident in HBM in the engine's plane
+        layout (CUDA events on the engine's stream, max over ranks);
+e2e   = the same metric through the C ABI entry point a host calls (gorder_gpu_submit) with pinned
+        HOST buffers in the decoder's [atom][xyz] layout: H2D copy, device re-layout, analysis and a
+        D2H read of the accumulators inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bond-frame samples/sec (S_CH evaluations/s)"
+UNIT = "samples/s"
+N_LIPIDS = 83334
+BYTES_PER_ATOM = 12.0   # algorithmic: every coordinate of the frame is read once
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    REASONS = {0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x8: "hw_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_system(args):
+    from gorder_b200 import abi, synthetic
+    return synthetic.s_cg(args.lipids, leaflet_mode=abi.LEAFLET_GLOBAL, max_batch_frames=args.frames)
+
+
+def config(args, s, extra=None):
+    c = {"workload": "S-CG: CGOrder Martini bilayer (BASELINE configs[1])", "lipids": args.lipids, "atoms_per_frame": s.n_atoms,
+         "bond_types": 11, "samples_per_frame": s.setup.samples_per_frame(), "frames_per_step": args.frames,
+         "leaflets": "Global, every frame", "normal": "static z", "pbc": True,
+         "l2_policy": "inputs larger than L2 (frames_per_step x 12 MB per step)", "parallelism": f"frame-sharded x{args.gpus}"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def cpu_oracle_rate(s, xyz, box, threads, min_seconds):
+    """Time the oracle port (all host threads) on the given frames, repeated until min_seconds."""
+    from oracle import oracle as orc
+    n = xyz.shape[0]
+    done, t_total, res = 0, 0.0, None
+    while t_total < min_seconds:
+        o = orc.Oracle(s.setup, n_threads=threads)
+        t0 = time.perf_counter()
+        o.analyze_frames(xyz, box, np.arange(n, dtype=np.int64))
+        t_total += time.perf_counter() - t0
+        res = o.finish()
+        o.close()
+        done += n
+        if t_total > 30:
+            break
+    return done * s.setup.samples_per_frame() / t_total, done, t_total, res
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    s = make_system(args)
+    threads = os.cpu_count() or 1
+    nf = min(args.frames, args.ref_frames)
+    xyz, box, _ = s.frames(0, nf)
+    from oracle import oracle as orc
+    for _ in range(min(args.warmup, 1)):
+        o = orc.Oracle(s.setup, n_threads=threads)
+        o.analyze_frames(xyz[:1], box[:1], np.arange(1, dtype=np.int64))
+        o.close()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        o = orc.Oracle(s.setup, n_threads=threads)
+        o.analyze_frames(xyz, box, np.arange(nf, dtype=np.int64))
+        o.finish()
+        o.close()
+    dt = time.perf_counter() - t0
+    value = args.steps * nf * s.setup.samples_per_frame() / dt
+    sample = f"{nf} frames of the S-CG workload per step, oracle port (oracle/gorder_oracle.c) with {threads} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config(args, s, {"frames_per_step": nf}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from gorder_b200 import SystemTopology
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gorder_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    s = make_system(args)
+    s.setup.device = local
+    F, K, W = args.frames, args.steps, args.warmup
+    spf = s.setup.samples_per_frame()
+
+    # ---- inputs: every rank generates its own frames (weak scaling) ---------------------------------
+    first = rank * F
+    xyz, box, _ = s.frames(first, F)
+    eng = SystemTopology(s.setup)
+    planes = eng.to_native(xyz)
+    d_planes = torch.from_numpy(planes).cuda()
+    d_box = torch.from_numpy(box).cuda()
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+    frame_bytes = eng.frame_floats * 4
+
+    def step(k):
+        base = (k * world + rank) * F   # disjoint, strictly increasing frame ranges per rank
+        eng.analyze_frames_device(d_planes.data_ptr(), d_box.data_ptr(), F, frame_index=base + np.arange(F, dtype=np.int64), native=True)
+
+    for k in range(W):
+        step(k)
+    eng.sync()
+    block_ptr, n_words = eng.accumulator_block()
+    red = torch.zeros(n_words, dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = eng.stats()["kernel_launches"]
+    eng.profile(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for k in range(W, W + K):
+        step(k)
+    if world > 1:   # the single collective of the job: sum the integer accumulators on rank 0
+        eng.read_block(red.data_ptr())
+        dist.reduce(red, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            torch.cuda.synchronize()
+            eng.write_block(red.data_ptr())
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    ms = ev0.elapsed_time(ev1)
+    hot_ms, hot_n = eng.profile_read()
+    eng.profile(False)
+    launches = eng.stats()["kernel_launches"] - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = K * F * spf * world / (ms * 1e-3)
+    res = eng.finish()
+    total_samples = int(res.count[:, 0].sum())
+
+    # ---- end to end: pinned host AoS frames through gorder_gpu_submit, D2H of the sums every step -------
+    eng2 = SystemTopology(s.setup)
+    pin = torch.from_numpy(xyz).pin_memory()
+    pin_box = torch.from_numpy(box).pin_memory()
+    hx, hb = pin.numpy(), pin_box.numpy()
+
+    def e2e_step(k):
+        base = (k * world + rank) * F
+        eng2.analyze_frames(hx, hb, base + np.arange(F, dtype=np.int64))
+        return eng2.finish()
+
+    for k in range(min(W, 3)):
+        e2e_step(k)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(3, 3 + K):
+        r2 = e2e_step(k)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = K * F * spf * world / float(t.item())
+    h2d = int(xyz.nbytes + box.nbytes)
+    d2h = int(r2.sum.nbytes + r2.count.nbytes)
+    eng2.close()
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        launch_bytes = F * s.n_atoms * BYTES_PER_ATOM
+        achieved = launch_bytes / (hot_ms / max(hot_n, 1) * 1e-3) / 1e9 if hot_n else None
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                tr = json.load(f)
+            traffic = tr["dram_bytes_per_frame"] * F
+        except Exception:
+            pass
+        # ---- CPU baseline (oracle port) on a bounded sample + parity of the GPU sums against it ------
+        threads = os.cpu_count() or 1
+        nb = min(F, args.ref_frames)
+        cpu_rate, cpu_frames, cpu_t, ref = cpu_oracle_rate(s, xyz[:nb], box[:nb], threads, args.cpu_seconds)
+        eng3 = SystemTopology(s.setup)
+        eng3.analyze_frames(xyz[:nb], box[:nb], np.arange(nb, dtype=np.int64))
+        g = eng3.finish()
+        eng3.close()
+        parity = {"counts_equal": bool(np.array_equal(g.count, ref.count)),
+                  "max_abs_dS": float(np.abs(g.sum / np.maximum(g.count, 1).astype(np.float64) - ref.sum / np.maximum(ref.count, 1).astype(np.float64)).max() / 1e6),
+                  "frames": nb}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config(args, s, {"resident_layout": "engine planes (gorder_gpu_native_layout)", "native_frame_bytes": frame_bytes}),
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "entry": "gorder_gpu_submit (pinned host [atom][xyz] frames) + gorder_gpu_finish", "timer": "host wall clock between device syncs"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "kernel": "bond_order_kernel", "launches_timed": hot_n, "avg_launch_ms": hot_ms / max(hot_n, 1),
+                         "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
+                         "step_share": (hot_ms / ms) if ms else None},
+            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{cpu_frames} frames of the same workload ({cpu_t:.1f} s), oracle port with {threads} OpenMP threads"},
+            "parity": parity, "total_samples_accumulated": total_samples,
+        }
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=32, help="frames per step (batch)")
+    ap.add_argument("--lipids", type=int, default=N_LIPIDS)
+    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU arms")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

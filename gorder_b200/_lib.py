@@ -14,6 +14,7 @@ SYMBOLS = [
     "gorder_gpu_create", "gorder_gpu_submit", "gorder_gpu_submit_device", "gorder_gpu_native_layout",
     "gorder_gpu_submit_native", "gorder_gpu_submit_native_device", "gorder_gpu_set_leaflets", "gorder_gpu_sync",
     "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block", "gorder_gpu_stats",
+    "gorder_gpu_read_block", "gorder_gpu_write_block", "gorder_gpu_profile", "gorder_gpu_profile_read",
     "gorder_gpu_stream", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
 ]
 
@@ -39,6 +40,10 @@ def lib() -> C.CDLL:
     L.gorder_gpu_result_sizes.argtypes = [vp, C.POINTER(abi.CGorderResults)]
     L.gorder_gpu_finish.argtypes = [vp, C.POINTER(abi.CGorderResults)]
     L.gorder_gpu_accumulator_block.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.gorder_gpu_read_block.argtypes = [vp, vp]
+    L.gorder_gpu_write_block.argtypes = [vp, vp]
+    L.gorder_gpu_profile.argtypes = [vp, C.c_int]
+    L.gorder_gpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.gorder_gpu_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.gorder_gpu_stream.argtypes = [vp]
     L.gorder_gpu_stream.restype = vp
@@ -51,7 +56,8 @@ def lib() -> C.CDLL:
     for name in ("gorder_gpu_create", "gorder_gpu_submit", "gorder_gpu_submit_device", "gorder_gpu_native_layout",
                  "gorder_gpu_submit_native", "gorder_gpu_submit_native_device", "gorder_gpu_set_leaflets",
                  "gorder_gpu_sync", "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block",
-                 "gorder_gpu_stats", "gorder_gpu_last_error"):
+                 "gorder_gpu_stats", "gorder_gpu_last_error", "gorder_gpu_read_block", "gorder_gpu_write_block",
+                 "gorder_gpu_profile", "gorder_gpu_profile_read"):
         getattr(L, name).restype = C.c_int
     _LIB = L
     return L

@@ -105,7 +105,17 @@ struct GorderHandle {
 
     // centres
     float *d_est = nullptr, *d_center = nullptr;   // [max_batch*3]
-    double *d_partial = nullptr;                   // [max_batch][kCenterBlocks][6]
+    double *d_partial = nullptr;                   // [max_batch][kCenterBlocks][2]
+    unsigned *d_ticket = nullptr;                  // [max_batch]
+    struct SegList { Seg *d = nullptr; int n = 0; };
+    SegList seg_membrane[3], seg_geom[3];          // per axis
+
+    // optional event timing of the accumulation kernel
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    double prof_ms = 0.0;
+    long long prof_n = 0;
 
     long long n_frames = 0;
     long long n_launches = 0;
@@ -212,19 +222,35 @@ size_t accum_smem(const GorderHandle *h) {
     return (items + (size_t)kWarps * max_orders * na + 2) * sizeof(int);
 }
 
-// group centre of `g` for the frames in d_list[0..n_list) -> h->d_center[3*i]
-int run_group_center(GorderHandle *h, const GroupRef &g, const float *planes, const FrameAux *aux, const int *d_list, int n_list) {
+// runs of contiguous native floats of component `axis` of a group, split into pieces of <= 2048
+int build_segs(GorderHandle *h, GorderHandle::SegList *out, const int32_t *idx, int n, int axis) {
+    std::vector<long long> offs(n);
+    for (int i = 0; i < n; i++) offs[i] = (long long)h->slot_off[idx[i]] + (long long)axis * h->slot_cs[idx[i]];
+    std::sort(offs.begin(), offs.end());
+    std::vector<Seg> segs;
+    for (int i = 0; i < n;) {
+        int j = i + 1;
+        while (j < n && offs[j] == offs[j - 1] + 1 && j - i < 2048) j++;
+        segs.push_back(Seg{(int)offs[i], j - i});
+        i = j;
+    }
+    out->n = (int)segs.size();
+    return dev_upload(h, &out->d, segs);
+}
+
+// centre of a group along the axes in `axis_mask` for the frames in d_list[0..n_list) -> h->d_center[3*i + axis]
+int run_group_center(GorderHandle *h, const GorderHandle::SegList *segs, int n_group, int axis_mask, const float *planes, const FrameAux *aux,
+                     const int *d_list, int n_list) {
     const bool pbc = h->s.handle_pbc != 0;
-    dim3 grid(kCenterBlocks, n_list);
-    group_center_partial_kernel<<<grid, 256, 0, h->stream>>>(h->view, g, planes, aux, d_list, h->d_est, h->d_partial, 0);
-    group_center_final_kernel<<<(n_list + 63) / 64, 64, 0, h->stream>>>(h->view, g.n, aux, d_list, n_list, h->d_partial, kCenterBlocks, h->d_est,
-                                                                         h->d_center, 0);
-    h->n_launches += 2;
-    if (pbc) {
-        group_center_partial_kernel<<<grid, 256, 0, h->stream>>>(h->view, g, planes, aux, d_list, h->d_est, h->d_partial, 1);
-        group_center_final_kernel<<<(n_list + 63) / 64, 64, 0, h->stream>>>(h->view, g.n, aux, d_list, n_list, h->d_partial, kCenterBlocks,
-                                                                             h->d_est, h->d_center, 1);
-        h->n_launches += 2;
+    for (int axis = 0; axis < 3; axis++) {
+        if (!(axis_mask & (1 << axis))) continue;
+        const int nblk = std::max(1, std::min(kCenterBlocks, segs[axis].n));
+        dim3 grid(nblk, n_list);
+        for (int pass = 0; pass < (pbc ? 2 : 1); pass++) {
+            center_axis_kernel<<<grid, 256, 0, h->stream>>>(h->view, segs[axis].d, segs[axis].n, n_group, axis, planes, aux, d_list, h->d_est,
+                                                            h->d_center, h->d_partial, h->d_ticket, pass);
+            h->n_launches++;
+        }
     }
     CK(cudaGetLastError());
     return GORDER_OK;
@@ -306,7 +332,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     h->n_launches++;
     if (s.geom_kind != GORDER_GEOM_NONE) {
         if (s.geom_ref_kind == GORDER_GEOMREF_SELECTION) {
-            int rc = run_group_center(h, h->view.geom_ref, d_planes, da, dl_all, nf);
+            int rc = run_group_center(h, h->seg_geom, h->s.n_geom_ref, 7, d_planes, da, dl_all, nf);
             if (rc) return rc;
             store_center_kernel<<<(nf + 63) / 64, 64, 0, h->stream>>>(da, dl_all, nf, h->d_center);
             h->n_launches++;
@@ -316,7 +342,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     }
     if (h->leaf && n_assign > 0) {
         if (s.leaflet_mode == GORDER_LEAFLET_GLOBAL) {
-            int rc = run_group_center(h, h->view.membrane, d_planes, da, dl_assign, n_assign);
+            int rc = run_group_center(h, h->seg_membrane, h->s.n_membrane, 1 << s.leaflet_axis, d_planes, da, dl_assign, n_assign);
             if (rc) return rc;
         }
         dim3 grid((h->n_molpad + 255) / 256, n_assign);
@@ -355,12 +381,24 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     o.bsum = h->d_bsum; o.bcnt = h->d_bcnt; o.map_sum = h->d_map_sum; o.map_cnt = h->d_map_cnt; o.normal_used = h->d_normal_used;
     dim3 grid(h->n_chunks, nf);
     const size_t smem = accum_smem(h);
+    std::pair<cudaEvent_t, cudaEvent_t> *pe = nullptr;
+    if (h->profiling) {
+        if (h->prof_used == h->prof_events.size()) {
+            std::pair<cudaEvent_t, cudaEvent_t> e;
+            CK(cudaEventCreate(&e.first)); CK(cudaEventCreate(&e.second));
+            h->prof_events.push_back(e);
+        }
+        pe = &h->prof_events[h->prof_used++];
+        CK(cudaEventRecord(pe->first, h->stream));
+    }
     if (h->ua) launch_ua(h, grid, smem, d_planes, da, o);
     else if (h->mpt == 4) launch_bond3<4>(h, grid, smem, d_planes, da, o);
     else if (h->mpt == 2) launch_bond3<2>(h, grid, smem, d_planes, da, o);
     else launch_bond3<1>(h, grid, smem, d_planes, da, o);
     h->n_launches++;
-    fold_kernel<<<(h->n_slots + 127) / 128, 128, 0, h->stream>>>(h->n_slots, nf, h->leaf ? 1 : 0, h->d_bsum + row0 * row, h->d_bcnt + row0 * row,
+    if (pe) CK(cudaEventRecord(pe->second, h->stream));
+    if (h->n_slots > 0)
+        fold_kernel<<<h->n_slots, 128, 0, h->stream>>>(h->n_slots, nf, h->leaf ? 1 : 0, h->d_bsum + row0 * row, h->d_bcnt + row0 * row,
                                                                   h->d_tot_sum, h->d_tot_cnt);
     h->n_launches++;
     CK(cudaGetLastError());
@@ -410,6 +448,7 @@ void gorder_gpu_destroy(GorderHandle *h) {
         if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     }
+    for (auto &e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -586,6 +625,12 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     if ((rc = upload_group(h, &v.membrane, s->membrane, s->n_membrane))) return rc;
     if ((rc = upload_group(h, &v.geom_ref, s->geom_ref, s->n_geom_ref))) return rc;
     if ((rc = upload_group(h, &v.normal_heads, s->normal_heads, s->n_normal_heads))) return rc;
+    for (int axis = 0; axis < 3; axis++) {
+        if (s->leaflet_mode == GORDER_LEAFLET_GLOBAL && axis == s->leaflet_axis)
+            if ((rc = build_segs(h, &h->seg_membrane[axis], s->membrane, s->n_membrane, axis))) return rc;
+        if (s->geom_kind != GORDER_GEOM_NONE && s->geom_ref_kind == GORDER_GEOMREF_SELECTION)
+            if ((rc = build_segs(h, &h->seg_geom[axis], s->geom_ref, s->n_geom_ref, axis))) return rc;
+    }
 
     // order maps: Map::new (ordermap.rs:40-96); node count = round(span / bin) + 1
     v.map.enabled = 0; v.map.n_bins = 0;
@@ -636,7 +681,8 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     }
     if ((rc = dev_alloc(h, &h->d_est, B * 3))) return rc;
     if ((rc = dev_alloc(h, &h->d_center, B * 3))) return rc;
-    if ((rc = dev_alloc(h, &h->d_partial, B * kCenterBlocks * 6))) return rc;
+    if ((rc = dev_alloc(h, &h->d_partial, B * kCenterBlocks * 2))) return rc;
+    if ((rc = dev_alloc(h, &h->d_ticket, B, true))) return rc;
 
     // dynamic shared memory of the accumulation kernels (small; no opt-in needed below 48 KB)
     if (accum_smem(h) > 48 * 1024) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "too many order slots per molecule type for shared memory"); return h->err_code; }
@@ -862,6 +908,52 @@ int gorder_gpu_accumulator_block(GorderHandle *h, void **d_ptr, int64_t *n_words
     cudaSetDevice(h->device);
     CK(cudaStreamSynchronize(h->stream));
     *d_ptr = h->d_block; *n_words = h->block_words;
+    return GORDER_OK;
+}
+
+int gorder_gpu_read_block(GorderHandle *h, void *d_dst) {
+    if (!h || !d_dst) return GORDER_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    CK(cudaMemcpyAsync(d_dst, h->d_block, (size_t)h->block_words * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GORDER_OK;
+}
+
+int gorder_gpu_write_block(GorderHandle *h, const void *d_src) {
+    if (!h || !d_src) return GORDER_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    CK(cudaMemcpyAsync(h->d_block, d_src, (size_t)h->block_words * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GORDER_OK;
+}
+
+static int drain_profile(GorderHandle *h) {
+    if (h->prof_used == 0) return GORDER_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < h->prof_used; i++) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second));
+        h->prof_ms += ms; h->prof_n++;
+    }
+    h->prof_used = 0;
+    return GORDER_OK;
+}
+
+int gorder_gpu_profile(GorderHandle *h, int enable) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    if (int rc = drain_profile(h)) return rc;
+    h->profiling = enable != 0;
+    return GORDER_OK;
+}
+
+int gorder_gpu_profile_read(GorderHandle *h, double *hot_kernel_ms, int64_t *hot_kernel_launches) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    if (int rc = drain_profile(h)) return rc;
+    if (hot_kernel_ms) *hot_kernel_ms = h->prof_ms;
+    if (hot_kernel_launches) *hot_kernel_launches = h->prof_n;
+    h->prof_ms = 0.0; h->prof_n = 0;
     return GORDER_OK;
 }
 

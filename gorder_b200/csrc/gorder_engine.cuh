@@ -67,6 +67,9 @@ struct GroupRef {
     int n;
 };
 
+// Run of contiguous floats inside a native frame (one component of a group's atoms).
+struct Seg { int off, len; };
+
 struct MapParams {
     int enabled, plane, nx, ny;
     float x0, y0, binx, biny;

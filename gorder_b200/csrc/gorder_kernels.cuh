@@ -174,85 +174,74 @@ __global__ void frame_setup_kernel(DeviceView v, FrameAux *aux, const float *__r
 }
 
 // ---------------------------------------------------------------------------------------------
-// group centre (groan group_get_center: refined Bai-Breen; group_get_center_naive: mean).
-// Deterministic two-level reduction: every CTA writes its partial sums, a single warp per frame
-// adds them in a fixed order.  f64 partials (the reference accumulates f32 sequentially; the
-// difference is far below the resolution that matters for a sign test / shape origin).
-//   pass 0: sum cos(theta), sin(theta) per axis      -> estimate
-//   pass 1: sum min_image(p - estimate) per axis     -> centre = wrap(estimate + mean)
+// group centre along one axis (groan group_get_center: refined Bai-Breen; _naive: mean).
+//   pass 0: sum cos(theta), sin(theta), theta = 2 pi x / L          -> estimate
+//   pass 1: sum min_image(x - estimate)                              -> centre = wrap(estimate + mean)
+// The group is given as runs of contiguous floats of the native frame (the axis component of its
+// atoms: whole planes for typical selections), so the reads are coalesced and carry no index
+// traffic.  Deterministic: every CTA writes its partial sums, the last CTA of a frame (ticket) adds
+// them in a fixed order and finishes the pass -- no separate launch, no floating-point atomics.
 // frame_list[i]: index in the batch of the i-th frame that needs the centre.
+// out: est[3 * i + axis] (pass 0) / center[3 * i + axis] (pass 1; pass 0 when !pbc).
 // ---------------------------------------------------------------------------------------------
-constexpr int kCenterBlocks = 64;
+constexpr int kCenterBlocks = 32;
 
-__global__ void __launch_bounds__(256) group_center_partial_kernel(DeviceView v, GroupRef g, const float *__restrict__ planes,
-                                                                   const FrameAux *__restrict__ aux, const int *__restrict__ frame_list,
-                                                                   const float *__restrict__ est, double *__restrict__ partial, int pass) {
+__global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Seg *__restrict__ segs, int n_segs, int n_group, int axis,
+                                                          const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                          const int *__restrict__ frame_list, float *__restrict__ est,
+                                                          float *__restrict__ center, double *__restrict__ partial,
+                                                          unsigned *__restrict__ ticket, int pass) {
     const int fi = blockIdx.y, f = frame_list[fi];
     const float *fr = planes + (size_t)f * v.frame_floats;
-    const FrameAux &a = aux[f];
-    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const float L = aux[f].L[axis], half = aux[f].half[axis];
     const bool pbc = v.handle_pbc != 0;
-    float e[3] = {0, 0, 0}, scale[3] = {0, 0, 0};
-    if (pbc) {
-        for (int k = 0; k < 3; k++) scale[k] = __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), a.L[k]);
-        if (pass == 1) { e[0] = est[3 * fi]; e[1] = est[3 * fi + 1]; e[2] = est[3 * fi + 2]; }
-    }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
-        const int off = g.off[i], cs = g.cs[i];
-        float p[3] = {fr[off], fr[off + cs], fr[off + 2 * (size_t)cs]};
-        if (!pbc) { acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; }
-        else if (pass == 0) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                float s, c;
-                sincosf(__fmul_rn(p[k], scale[k]), &s, &c);
-                acc[k] += c; acc[3 + k] += s;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 3; k++) acc[k] += (a.L[k] > 0.0f) ? min_image(__fsub_rn(p[k], e[k]), a.L[k], a.half[k]) : __fsub_rn(p[k], e[k]);
+    float a0 = 0.0f, a1 = 0.0f;
+    const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
+    const float e = (pbc && pass == 1) ? est[3 * fi + axis] : 0.0f;
+    for (int sg = blockIdx.x; sg < n_segs; sg += gridDim.x) {
+        const Seg sgm = segs[sg];
+        for (int i = threadIdx.x; i < sgm.len; i += blockDim.x) {
+            const float p = __ldg(fr + sgm.off + i);
+            if (!pbc) a0 += p;
+            else if (pass == 0) {
+                float sn, cs;
+                __sincosf(p * scale, &sn, &cs);   // the estimate only seeds the refinement pass
+                a0 += cs; a1 += sn;
+            } else a0 += min_image(__fsub_rn(p, e), L, half);
         }
     }
-    __shared__ double s_red[6][8];
+    __shared__ double s_red[2][8];
+    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        double x = acc[k];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) s_red[k][warp] = x;
+    double x0 = a0, x1 = a1;
+    for (int o = 16; o > 0; o >>= 1) { x0 += __shfl_down_sync(0xffffffffu, x0, o); x1 += __shfl_down_sync(0xffffffffu, x1, o); }
+    if (lane == 0) { s_red[0][warp] = x0; s_red[1][warp] = x1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0, t1 = 0;
+        for (int w = 0; w < 8; w++) { t0 += s_red[0][w]; t1 += s_red[1][w]; }
+        double *pp = partial + ((size_t)fi * gridDim.x + blockIdx.x) * 2;
+        pp[0] = t0; pp[1] = t1;
+        __threadfence();
+        s_last = atomicAdd(&ticket[fi], 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (threadIdx.x < 6) {
-        double x = 0;
-        for (int w = 0; w < 8; w++) x += s_red[threadIdx.x][w];
-        partial[((size_t)fi * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = x;
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    double t0 = 0, t1 = 0;
+    for (unsigned b = 0; b < gridDim.x; b++) {   // fixed order
+        const volatile double *pp = partial + ((size_t)fi * gridDim.x + b) * 2;
+        t0 += pp[0]; t1 += pp[1];
     }
-}
-
-// final stage; one thread per frame (sequential over kCenterBlocks partials: fixed order).
-__global__ void group_center_final_kernel(DeviceView v, int n_group, const FrameAux *__restrict__ aux, const int *__restrict__ frame_list,
-                                          int n_list, const double *__restrict__ partial, int n_blocks, float *est, float *center, int pass) {
-    int fi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (fi >= n_list) return;
-    const FrameAux &a = aux[frame_list[fi]];
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int b = 0; b < n_blocks; b++)
-        for (int k = 0; k < 6; k++) acc[k] += partial[((size_t)fi * n_blocks + b) * 6 + k];
+    ticket[fi] = 0;
     const float n = (float)n_group;
-    if (!v.handle_pbc) {
-        for (int k = 0; k < 3; k++) center[3 * fi + k] = n_group > 0 ? __fdiv_rn((float)acc[k], n) : CUDART_NAN_F;
-        return;
-    }
-    if (pass == 0) {
-        for (int k = 0; k < 3; k++) {
-            float th = __fadd_rn(atan2f(-(float)acc[3 + k], -(float)acc[k]), CUDART_PI_F);
-            est[3 * fi + k] = n_group > 0 ? __fdiv_rn(__fmul_rn(a.L[k], th), __fmul_rn(2.0f, CUDART_PI_F)) : CUDART_NAN_F;
-        }
+    if (!pbc) center[3 * fi + axis] = n_group > 0 ? __fdiv_rn((float)t0, n) : CUDART_NAN_F;
+    else if (pass == 0) {
+        float th = __fadd_rn(atan2f(-(float)t1, -(float)t0), CUDART_PI_F);
+        est[3 * fi + axis] = n_group > 0 ? __fdiv_rn(__fmul_rn(L, th), __fmul_rn(2.0f, CUDART_PI_F)) : CUDART_NAN_F;
     } else {
-        for (int k = 0; k < 3; k++) {
-            float c = __fadd_rn(est[3 * fi + k], __fdiv_rn((float)acc[k], n));
-            center[3 * fi + k] = (a.L[k] > 0.0f) ? wrap1(c, a.L[k]) : c;
-        }
+        float c = __fadd_rn(e, __fdiv_rn((float)t0, n));
+        center[3 * fi + axis] = (L > 0.0f) ? wrap1(c, L) : c;
     }
 }
 
@@ -633,13 +622,13 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
                     raise_error(v, v.normal_mode == GORDER_NORMAL_DYNAMIC ? GORDER_ERR_DYNAMIC_NORMAL_POINTS : GORDER_ERR_MANUAL_NORMAL_FRAME, npts);
                     continue;
                 }
-                s = calc_sch(d, nrm[j]);
-            } else s = calc_sch_axis(d, comp(d, v.normal_axis));
+                s = calc_sch_fast(d, nrm[j]);
+            } else s = calc_sch_axis_fast(d, comp(d, v.normal_axis));
             if (s != s) {   // NaN coordinate reached the engine: AnalysisError::UndefinedPosition
                 raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | ((long long)b << 32) | (unsigned)(m0 + j));
                 continue;
             }
-            const int q = order_value(s);
+            const int q = order_value_fast(s);
             if (LEAF && !up[j]) { sl += q; cl++; } else { su += q; cu++; }
             if (EXTRA && v.map.enabled) map_add<LEAF>(v, o, td.slot0 + b, mid, q, up[j]);
         }
@@ -769,12 +758,12 @@ __global__ void __launch_bounds__(kBlock) ua_order_kernel(DeviceView v, const fl
                     mid = mk3(__fadd_rn(hyd[k].x, d.x * 0.5f), __fadd_rn(hyd[k].y, d.y * 0.5f), __fadd_rn(hyd[k].z, d.z * 0.5f));
                     if (v.shape.kind != GORDER_GEOM_NONE && !shape_inside<PBC>(v.shape, ax, bx, mid)) continue;
                 }
-                const float s = calc_sch(d, nrm);
+                const float s = calc_sch_fast(d, nrm);
                 if (s != s) {
                     raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | ((long long)i << 32) | (unsigned)m);
                     continue;
                 }
-                q[k] = order_value(s);
+                q[k] = order_value_fast(s);
                 in[k] = true;
                 if (EXTRA && v.map.enabled) map_add<LEAF>(v, o, td.slot0 + it.slot_rel + k, mid, q[k], up);
             }
@@ -795,21 +784,36 @@ __global__ void __launch_bounds__(kBlock) ua_order_kernel(DeviceView v, const fl
 // With leaflets the kernels only fill upper / lower; total = upper + lower is completed here
 // (bond.rs:184-215 adds every sample to total and to exactly one leaflet).
 // ---------------------------------------------------------------------------------------------
-__global__ void fold_kernel(int n_slots, int n_rows, int leaf, long long *__restrict__ bsum, unsigned long long *__restrict__ bcnt,
-                            long long *__restrict__ tot_sum, unsigned long long *__restrict__ tot_cnt) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_slots) return;
+__global__ void __launch_bounds__(128) fold_kernel(int n_slots, int n_rows, int leaf, long long *__restrict__ bsum,
+                                                   unsigned long long *__restrict__ bcnt, long long *__restrict__ tot_sum,
+                                                   unsigned long long *__restrict__ tot_cnt) {
+    const int s = blockIdx.x;
     long long ts[3] = {0, 0, 0};
     unsigned long long tc[3] = {0, 0, 0};
-    for (int r = 0; r < n_rows; r++) {
-        size_t b = ((size_t)r * n_slots + s) * 3;
+    for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        const size_t b = ((size_t)r * n_slots + s) * 3;
         if (leaf) {
             bsum[b + GORDER_TOTAL] = bsum[b + GORDER_ACC_UPPER] + bsum[b + GORDER_ACC_LOWER];
             bcnt[b + GORDER_TOTAL] = bcnt[b + GORDER_ACC_UPPER] + bcnt[b + GORDER_ACC_LOWER];
         }
+#pragma unroll
         for (int k = 0; k < 3; k++) { ts[k] += bsum[b + k]; tc[k] += bcnt[b + k]; }
     }
-    for (int k = 0; k < 3; k++) { tot_sum[s * 3 + k] += ts[k]; tot_cnt[s * 3 + k] += tc[k]; }
+    __shared__ long long s_s[3][4];
+    __shared__ unsigned long long s_c[3][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        for (int o = 16; o > 0; o >>= 1) { ts[k] += __shfl_down_sync(0xffffffffu, ts[k], o); tc[k] += __shfl_down_sync(0xffffffffu, tc[k], o); }
+        if (lane == 0) { s_s[k][warp] = ts[k]; s_c[k][warp] = tc[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        long long a = 0; unsigned long long c = 0;
+        for (int w = 0; w < 4; w++) { a += s_s[k][w]; c += s_c[k][w]; }
+        tot_sum[s * 3 + k] += a; tot_cnt[s * 3 + k] += c;
+    }
 }
 
 }  // namespace gorder

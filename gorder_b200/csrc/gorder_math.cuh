@@ -26,16 +26,28 @@ __device__ __forceinline__ float fmod_near(float x, float L) {
     return fmodf(x, L);
 }
 
+// Slow path of the fold (bond longer than half a box, atoms outside the box, degenerate box):
+// the literal expression, out of line so that the hot loop stays small in the instruction cache.
+__device__ __noinline__ float min_image_slow(float d, float L, float half) {
+    if (!(L > 0.0f)) return d;
+    float t = __fadd_rn(d, half);
+    t = fmodf(t, L);
+    float u = __fadd_rn(t, L);
+    u = fmodf(u, L);
+    return __fsub_rn(u, half);
+}
+
 // groan_rs Vector3D::vector_to per component (call site src/analysis/pbc.rs:378-385):
 //   (((d + L/2) % L) + L) % L - L/2     in f32, every operation rounded.
 // The roundings of this expression are part of the reference's results (oracle/gorder_oracle.c
 // min_image, pinned by cgorder.rs:188-241 and uaorder.rs:1113-1200), so they are reproduced.
+// Fast path: for 0 <= t = fl(d + L/2) and u = fl(t + L) < 2L both `%` are exact
+// (t % L = t, u % L = u - L), so the result is fl(fl(u - L) - L/2) with identical bits.
 __device__ __forceinline__ float min_image(float d, float L, float half) {
-    float t = __fadd_rn(d, half);
-    t = fmod_near(t, L);
-    float u = __fadd_rn(t, L);
-    u = fmod_near(u, L);
-    return __fsub_rn(u, half);
+    const float t = __fadd_rn(d, half);
+    const float u = __fadd_rn(t, L);
+    if (t >= 0.0f && u < __fadd_rn(L, L)) return __fsub_rn(__fsub_rn(u, L), half);
+    return min_image_slow(d, L, half);
 }
 
 // Vector3D::wrap per component (call site pbc.rs:388-390): c % L, + L if negative.
@@ -53,10 +65,10 @@ struct Box {
 template <bool PBC>
 __device__ __forceinline__ f3 vector_to(const f3 &p1, const f3 &p2, const Box &b) {
     f3 d = mk3(__fsub_rn(p2.x, p1.x), __fsub_rn(p2.y, p1.y), __fsub_rn(p2.z, p1.z));
-    if (PBC) {
-        if (b.L[0] > 0.0f) d.x = min_image(d.x, b.L[0], b.half[0]);
-        if (b.L[1] > 0.0f) d.y = min_image(d.y, b.L[1], b.half[1]);
-        if (b.L[2] > 0.0f) d.z = min_image(d.z, b.L[2], b.half[2]);
+    if (PBC) {   // a degenerate dimension (L <= 0) falls into the slow path, which returns d
+        d.x = min_image(d.x, b.L[0], b.half[0]);
+        d.y = min_image(d.y, b.L[1], b.half[1]);
+        d.z = min_image(d.z, b.L[2], b.half[2]);
     }
     return d;
 }
@@ -105,6 +117,30 @@ __device__ __forceinline__ float calc_sch_axis(const f3 &v, float v_axis) {
     if (n1 == 0.0f) c = 1.0f;
     return __fsub_rn(__fmul_rn(__fmul_rn(1.5f, c), c), 0.5f);
 }
+
+// Streaming variants used by the accumulation kernels: c = v.n * rsqrt(|v|^2 |n|^2) (MUFU.RSQ,
+// <= 2 ulp) instead of sqrt + IEEE division.  cos(acos(c)) of the reference is itself only defined
+// to ~2 ulp of c, so nothing is lost: |dS| <= 4e-7 per sample either way.
+__device__ __forceinline__ float calc_sch_fast(const f3 &v, const f3 &n) {
+    const float prod = fmaf(v.z, n.z, fmaf(v.y, n.y, v.x * n.x));
+    const float n1 = fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x)), n2 = fmaf(n.z, n.z, fmaf(n.y, n.y, n.x * n.x));
+    const float den = n1 * n2;
+    float c = prod * rsqrtf(den);
+    c = fminf(1.0f, fmaxf(-1.0f, c));
+    if (den == 0.0f) c = 1.0f;      // angle() returns 0 when a norm is 0 -> S = 1
+    return fmaf(1.5f * c, c, -0.5f);   // NaN coordinates propagate (den != den -> c NaN -> S NaN)
+}
+__device__ __forceinline__ float calc_sch_axis_fast(const f3 &v, float v_axis) {
+    const float n1 = fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x));
+    float c = v_axis * rsqrtf(n1);
+    c = fminf(1.0f, fmaxf(-1.0f, c));
+    if (n1 == 0.0f) c = 1.0f;
+    return fmaf(1.5f * c, c, -0.5f);
+}
+
+// OrderValue::from(f32) in one FMUL + F2I: round-to-nearest of fl(S * 1e6).  fl() moves the product
+// by <= 0.03 units of 1e-6, far below the +-0.3 unit uncertainty S already carries.
+__device__ __forceinline__ int order_value_fast(float s) { return __float2int_rn(s * 1000000.0f); }
 
 // OrderValue::from(f32) (src/analysis/order.rs:21-26): (value as f64 * 1e6).round() as i64.
 // S is f32 and 1e6 = 2^6 * 15625, so the f64 product is exact; round() is half away from zero.

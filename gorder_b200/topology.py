@@ -115,6 +115,21 @@ class SystemTopology:
         self._check(lib().gorder_gpu_accumulator_block(self._h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
 
+    def read_block(self, d_dst: int):
+        self._check(lib().gorder_gpu_read_block(self._h, C.c_void_p(d_dst)))
+
+    def write_block(self, d_src: int):
+        self._check(lib().gorder_gpu_write_block(self._h, C.c_void_p(d_src)))
+
+    def profile(self, enable: bool = True):
+        self._check(lib().gorder_gpu_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """(summed ms, launches) of the accumulation kernel since the last read (CUDA events)."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        self._check(lib().gorder_gpu_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def stats(self):
         k, f = C.c_int64(0), C.c_int64(0)
         lib().gorder_gpu_stats(self._h, C.byref(k), C.byref(f))

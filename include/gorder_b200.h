@@ -285,7 +285,18 @@ int gorder_gpu_finish(GorderHandle *h, GorderResults *r);
  * gorder_gpu_finish() reads the block back, so reduce first, then finish on the root. */
 int gorder_gpu_accumulator_block(GorderHandle *h, void **d_ptr, int64_t *n_words);
 
-/* Counters for benchmarking: kernels launched by this handle and samples accumulated so far. */
+/* Copy the accumulator block to / from caller-owned DEVICE memory (n_words int64 words): the host
+ * reduces shards with  read -> ncclReduce(sum, int64) -> write on the root -> finish. */
+int gorder_gpu_read_block(GorderHandle *h, void *d_dst);
+int gorder_gpu_write_block(GorderHandle *h, const void *d_src);
+
+/* Optional CUDA-event timing of the accumulation kernel (K1 / K2) on the handle's own stream.
+ * profile_read returns the summed duration (ms) and the number of timed launches since the last
+ * read and resets both. */
+int gorder_gpu_profile(GorderHandle *h, int enable);
+int gorder_gpu_profile_read(GorderHandle *h, double *hot_kernel_ms, int64_t *hot_kernel_launches);
+
+/* Counters for benchmarking: kernels launched by this handle and frames analysed so far. */
 int gorder_gpu_stats(GorderHandle *h, int64_t *kernel_launches, int64_t *frames);
 
 /* CUDA stream all work of this handle is queued on (as void*), for event timing by the caller. */
