@@ -73,6 +73,7 @@ struct GorderHandle {
     long long *d_bsum = nullptr;
     unsigned long long *d_bcnt = nullptr;
     long long tw_cap = 0;
+    bool ring_owned = false;   // d_bcnt lives inside the d_bsum allocation
     std::vector<long long> frame_index_done;   // frame_index of every analysed frame, in order
 
     // staging (2-deep)
@@ -222,7 +223,7 @@ size_t accum_smem(const GorderHandle *h) {
     return (items + (size_t)kWarps * max_orders * na + 2) * sizeof(int);
 }
 
-// runs of contiguous native floats of component `axis` of a group, split into pieces of <= 2048
+// runs of contiguous native floats of component `axis` of a group, split into pieces of <= 1024
 int build_segs(GorderHandle *h, GorderHandle::SegList *out, const int32_t *idx, int n, int axis) {
     std::vector<long long> offs(n);
     for (int i = 0; i < n; i++) offs[i] = (long long)h->slot_off[idx[i]] + (long long)axis * h->slot_cs[idx[i]];
@@ -230,7 +231,7 @@ int build_segs(GorderHandle *h, GorderHandle::SegList *out, const int32_t *idx, 
     std::vector<Seg> segs;
     for (int i = 0; i < n;) {
         int j = i + 1;
-        while (j < n && offs[j] == offs[j - 1] + 1 && j - i < 2048) j++;
+        while (j < n && offs[j] == offs[j - 1] + 1 && j - i < 1024) j++;
         segs.push_back(Seg{(int)offs[i], j - i});
         i = j;
     }
@@ -326,7 +327,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     FrameAux *da = h->d_aux[slot];
     int *dl_assign = h->d_list[slot], *dl_all = h->d_list[slot] + h->max_batch;
     CK(cudaMemcpyAsync(da, ha, sizeof(FrameAux) * nf, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_list[slot], h->h_list[slot], sizeof(int) * 2 * h->max_batch, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_list[slot], h->h_list[slot], sizeof(int) * (h->max_batch + nf), cudaMemcpyHostToDevice, h->stream));
 
     frame_setup_kernel<<<(nf + 63) / 64, 64, 0, h->stream>>>(h->view, da, d_box, nf, 0);
     h->n_launches++;
@@ -374,8 +375,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         int rc = grow_rows(h, h->n_frames + nf);
         if (rc) return rc;
     } else {
-        CK(cudaMemsetAsync(h->d_bsum, 0, (size_t)nf * row * sizeof(long long), h->stream));
-        CK(cudaMemsetAsync(h->d_bcnt, 0, (size_t)nf * row * sizeof(unsigned long long), h->stream));
+        CK(cudaMemsetAsync(h->d_bsum, 0, 2 * (size_t)h->max_batch * row * sizeof(long long), h->stream));
     }
     AccumOut o;
     o.bsum = h->d_bsum; o.bcnt = h->d_bcnt; o.map_sum = h->d_map_sum; o.map_cnt = h->d_map_cnt; o.normal_used = h->d_normal_used;
@@ -439,7 +439,8 @@ void gorder_gpu_destroy(GorderHandle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     for (void *p : h->owned) cudaFree(p);
-    cudaFree(h->d_bsum); cudaFree(h->d_bcnt);
+    cudaFree(h->d_bsum);
+    if (!h->ring_owned) cudaFree(h->d_bcnt);
     cudaFree(h->d_leaf_collect); cudaFree(h->d_normals_collect); cudaFree(h->d_used_collect);
     for (int i = 0; i < 2; i++) {
         cudaFree(h->d_xyz[i]);
@@ -655,8 +656,11 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     h->d_map_sum = h->d_block + 2 * na;
     h->d_map_cnt = reinterpret_cast<unsigned long long *>(h->d_block + 2 * na + na * v.map.n_bins);
     if (!s->timewise) {
-        CK(cudaMalloc((void **)&h->d_bsum, std::max<size_t>(1, (size_t)h->max_batch * na) * sizeof(long long)));
-        CK(cudaMalloc((void **)&h->d_bcnt, std::max<size_t>(1, (size_t)h->max_batch * na) * sizeof(unsigned long long)));
+        // one allocation: [max_batch rows of sums][max_batch rows of counts] -> a single memset per batch
+        const size_t ring = std::max<size_t>(1, (size_t)h->max_batch * na);
+        CK(cudaMalloc((void **)&h->d_bsum, 2 * ring * sizeof(long long)));
+        h->d_bcnt = reinterpret_cast<unsigned long long *>(h->d_bsum + ring);
+        h->ring_owned = true;
     }
 
     // ---- per-batch buffers -------------------------------------------------------------------------

@@ -184,7 +184,7 @@ __global__ void frame_setup_kernel(DeviceView v, FrameAux *aux, const float *__r
 // frame_list[i]: index in the batch of the i-th frame that needs the centre.
 // out: est[3 * i + axis] (pass 0) / center[3 * i + axis] (pass 1; pass 0 when !pbc).
 // ---------------------------------------------------------------------------------------------
-constexpr int kCenterBlocks = 32;
+constexpr int kCenterBlocks = 128;
 
 __global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Seg *__restrict__ segs, int n_segs, int n_group, int axis,
                                                           const float *__restrict__ planes, const FrameAux *__restrict__ aux,
@@ -198,16 +198,26 @@ __global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Se
     float a0 = 0.0f, a1 = 0.0f;
     const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
     const float e = (pbc && pass == 1) ? est[3 * fi + axis] : 0.0f;
+    auto add = [&](float p) {
+        if (!pbc) a0 += p;
+        else if (pass == 0) {
+            float sn, cs;
+            __sincosf(p * scale, &sn, &cs);   // the estimate only seeds the refinement pass
+            a0 += cs; a1 += sn;
+        } else a0 += min_image(__fsub_rn(p, e), L, half);
+    };
     for (int sg = blockIdx.x; sg < n_segs; sg += gridDim.x) {
         const Seg sgm = segs[sg];
-        for (int i = threadIdx.x; i < sgm.len; i += blockDim.x) {
-            const float p = __ldg(fr + sgm.off + i);
-            if (!pbc) a0 += p;
-            else if (pass == 0) {
-                float sn, cs;
-                __sincosf(p * scale, &sn, &cs);   // the estimate only seeds the refinement pass
-                a0 += cs; a1 += sn;
-            } else a0 += min_image(__fsub_rn(p, e), L, half);
+        const float *src = fr + sgm.off;
+        if ((((size_t)src) & 15) == 0) {   // 16-byte aligned run: 128-bit loads
+            const int n4 = sgm.len >> 2;
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(src) + i);
+                add(q.x); add(q.y); add(q.z); add(q.w);
+            }
+            for (int i = (n4 << 2) + threadIdx.x; i < sgm.len; i += blockDim.x) add(__ldg(src + i));
+        } else {
+            for (int i = threadIdx.x; i < sgm.len; i += blockDim.x) add(__ldg(src + i));
         }
     }
     __shared__ double s_red[2][8];
