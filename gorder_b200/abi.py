@@ -259,6 +259,38 @@ class EngineSetup:
             s += n
         return out
 
+    # -- (de)serialisation: golden fixtures store the setup as JSON ---------------------------------
+    _ARRAY_FIELDS = ("normal_heads", "membrane", "geom_ref")
+
+    def to_dict(self) -> dict:
+        d = {}
+        for k, v in self.__dict__.items():
+            if k in ("_keep", "moltypes"):
+                continue
+            if isinstance(v, np.ndarray):
+                v = v.tolist()
+            elif isinstance(v, (tuple, list)):
+                v = [float(x) if isinstance(x, (float, np.floating)) else int(x) for x in v]
+            elif isinstance(v, (np.integer,)):
+                v = int(v)
+            elif isinstance(v, (np.floating,)):
+                v = float(v)
+            d[k] = v
+        d["moltypes"] = []
+        for m in self.moltypes:
+            md = dict(name=m.name, mol_base=[int(x) for x in m.mol_base], bond_rel=[[int(a), int(b)] for a, b in m.bond_rel],
+                      ua_kind=[int(x) for x in m.ua_kind], ua_rel=[[int(x) for x in r] for r in m.ua_rel], head_rel=int(m.head_rel),
+                      methyl_rel=[int(x) for x in m.methyl_rel], normal_head_rel=int(m.normal_head_rel),
+                      bond_names=list(m.bond_names))
+            d["moltypes"].append(md)
+        return d
+
+    @classmethod
+    def from_dict(cls, d: dict) -> "EngineSetup":
+        d = dict(d)
+        mts = [MolType(**m) for m in d.pop("moltypes")]
+        return cls(moltypes=mts, **d)
+
     def samples_per_frame(self) -> int:
         """Upper bound of S evaluations per frame (no geometry filter)."""
         return sum(m.n_orders(self.kind) * m.n_molecules for m in self.moltypes)

@@ -341,3 +341,14 @@ def build_ua_setup(st: Structure, saturated: Sequence[int], unsaturated: Sequenc
     if normal_heads is not None:
         kw.setdefault("normal_heads", sorted(nh))
     return abi.EngineSetup(kind=abi.KIND_UA, n_atoms=st.n_atoms, moltypes=mts, **kw)
+
+
+def compact(st: Structure, keep: Sequence[int]) -> Tuple[Structure, np.ndarray]:
+    """Keep only ``keep`` atoms (the reference's Master group, common.rs:92-103) and renumber.
+    Returns the compacted structure and the kept original indices."""
+    keep = np.array(sorted(set(int(x) for x in keep)), dtype=np.int64)
+    new = -np.ones(st.n_atoms, np.int64)
+    new[keep] = np.arange(keep.size)
+    bonds = [(int(new[i]), int(new[j])) for i, j in st.bonds if new[i] >= 0 and new[j] >= 0]
+    out = Structure(st.resid[keep], [st.resname[i] for i in keep], [st.name[i] for i in keep], st.xyz[keep].copy(), st.box.copy(), bonds)
+    return out, keep

@@ -1,0 +1,188 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the reference checkout.
+
+Run in the build container (needs /root/reference):   python tests/golden/make_golden.py
+
+Every fixture carries (a) inputs dug out of the reference's own test files (coordinates of the
+Master group only, renumbered densely as the reference does, common.rs:92-103), (b) the engine
+setup as JSON, and (c) the EXPECTED values copied from the reference: the hard-coded vectors of its
+unit tests (cgorder.rs:188-241, aaorder.rs:226-350, uaorder.rs:1113-1200) or its YAML / map /
+leaflet / normals fixtures (tests/files/ua_order_*.yaml, ordermaps_ua/*, ua_leaflets_once.yaml,
+ua_normals.yaml).  Nothing in the expected values comes from this repository's own code.
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from gorder_b200 import abi  # noqa: E402
+from oracle import fixtures  # noqa: E402
+
+REF = "/root/reference"
+FILES = os.path.join(REF, "tests", "files")
+LIPIDS = {"POPC", "POPE", "POPG", "POPS"}
+
+
+def rust_vectors(path: str, fn: str):
+    src = open(path).read()
+    body = src[src.index("fn " + fn):]
+    body = body[: body.index("\n    }\n")]
+    return [np.array([float(x) for x in v.replace("\n", " ").split(",") if x.strip()]) for v in re.findall(r"vec!\[(.*?)\]", body, re.S)]
+
+
+def single_frame(name: str, gro: str, bnd: str, tpr: str, kind: int, rust: str, sign: float, head: str):
+    st = fixtures.read_gro(os.path.join(FILES, gro))
+    fixtures.read_bnd(os.path.join(FILES, bnd), st)
+    xyz, box, _ = fixtures.tpr_coordinates(os.path.join(FILES, tpr), st.xyz)
+    st.xyz = xyz
+    mem = st.select(lambda r, n: r in LIPIDS)
+    cst, keep = fixtures.compact(st, mem)
+    allm = np.arange(cst.n_atoms)
+    if kind == abi.KIND_CG:
+        g1 = g2 = allm
+    else:   # "@membrane and element name carbon / hydrogen" (aaorder.rs:170-181)
+        g1 = cst.select(lambda r, n: n.startswith("C"))
+        g2 = cst.select(lambda r, n: n.startswith("H"))
+    heads = cst.select(lambda r, n: n == head)
+    setup = fixtures.build_bond_setup(cst, kind, g1, g2, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL)
+    exp = {k: (sign * np.concatenate(rust_vectors(os.path.join(REF, "src", "analysis", rust), f"expected_{k}_orders"))).tolist()
+           for k in ("total", "upper", "lower")}
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), xyz=cst.xyz.astype(np.float32), box=box.astype(np.float32),
+                        setup=json.dumps(setup.to_dict()), expected=json.dumps(exp))
+    print(name, cst.n_atoms, "atoms,", setup.n_slots, "bond types")
+
+
+def ua_selections(st):
+    sat_excl = {"POPC": {"C15", "C34", "C24", "C25"}, "POPS": {"C6", "C18", "C39", "C27", "C28"}}
+    unsat_sel = {"POPC": {"C24", "C25"}, "POPS": {"C27", "C28"}}
+    sat = st.select(lambda r, n: r in sat_excl and n.startswith("C") and n not in sat_excl[r])
+    unsat = st.select(lambda r, n: r in unsat_sel and n in unsat_sel[r])
+    return sat, unsat
+
+
+def flatten_yaml(doc: dict, keys=("total",)):
+    """Expected numbers of an order YAML in traversal order (system, then per molecule: average,
+    per atom: atom value(s), per bond value(s)); {mean, error} dicts are expanded to two numbers."""
+    out = []
+
+    def push(node):
+        for k in keys:
+            if k in node:
+                v = node[k]
+                if isinstance(v, dict):
+                    out.append(float(v["mean"]) if v["mean"] == v["mean"] else float("nan"))
+                    out.append(float(v["error"]))
+                else:
+                    out.append(float(v))
+
+    push(doc["average order"])
+    for mol, body in doc.items():
+        if mol == "average order":
+            continue
+        push(body["average order"])
+        for _atom, node in body["order parameters"].items():
+            push(node)
+            for b in node.get("bonds", []):
+                push(b)
+    return out
+
+
+def ua_golden():
+    st = fixtures.read_pdb(os.path.join(FILES, "ua_nobox.pdb"))
+    tpr_xyz, sbox, _ = fixtures.tpr_coordinates(os.path.join(FILES, "ua.tpr"), st.xyz)
+    traj = fixtures.read_xtc(os.path.join(FILES, "ua.xtc"))
+    mem = st.select(lambda r, n: r in LIPIDS)
+    cst, keep = fixtures.compact(st, mem)
+    q = np.round(traj.xyz[:, keep, :].astype(np.float64) * 1000.0).astype(np.int32)   # XTC precision 1000: exact
+    assert np.array_equal((q.astype(np.float32) * np.float32(1.0 / 1000.0)), traj.xyz[:, keep, :]), "XTC coordinates are not k/1000"
+    sat, unsat = ua_selections(cst)
+    heads = cst.select(lambda r, n: n.startswith("P"))
+    allm = np.arange(cst.n_atoms)
+    base = fixtures.build_ua_setup(cst, sat, unsat)
+    cases = {}
+
+    def add(name, setup, yaml_file, keys=("total",), frames=None, **extra):
+        doc = yaml.safe_load(open(os.path.join(FILES, yaml_file)))
+        cases[name] = dict(setup=setup.to_dict(), expected=flatten_yaml(doc, keys), keys=list(keys),
+                           frames=frames if frames is not None else list(range(traj.xyz.shape[0])), source=yaml_file, **extra)
+
+    add("basic", base, "ua_order_basic.yaml")
+    leaf = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL)
+    add("leaflets_global", leaf, "ua_order_leaflets.yaml", keys=("total", "upper", "lower"))
+    # Individual / Local give the same fixture (tests_ua.rs:147-211); methyl selection of that test:
+    # "(resname POPC and name CA2 C50) or (resname POPS and name C36 C55)"
+    methyls = cst.select(lambda r, n: (r == "POPC" and n in ("CA2", "C50")) or (r == "POPS" and n in ("C36", "C55")))
+    ind = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL)
+    add("leaflets_individual", ind, "ua_order_leaflets.yaml", keys=("total", "upper", "lower"))
+    loc = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_LOCAL, leaflet_radius=2.5)
+    add("leaflets_local", loc, "ua_order_leaflets.yaml", keys=("total", "upper", "lower"))
+    err = fixtures.build_ua_setup(cst, sat, unsat, timewise=True)
+    add("error", err, "ua_order_error.yaml", n_blocks=5)
+    errl = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True)
+    add("error_leaflets", errl, "ua_order_leaflets_error.yaml", keys=("total", "upper", "lower"), n_blocks=5)
+    # begin 199200 ps, end 199800 ps, step 3 (tests_ua.rs:301-333): 11 frames
+    sel = [i for i, t in enumerate(traj.time) if 199200.0 <= t <= 199800.0][::3]
+    assert len(sel) == 11
+    bes = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL, step=3)
+    add("begin_end_step", bes, "ua_order_begin_end_step.yaml", keys=("total", "upper", "lower"), frames=sel)
+    cyl = fixtures.build_ua_setup(cst, sat, unsat, geom_kind=abi.GEOM_CYLINDER, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
+                                  geom_dims=(2.5, float("-inf"), float("inf")), geom_axis=abi.AXIS_Z)
+    add("cylinder_center", cyl, "ua_order_cylinder_center.yaml")
+    cub = fixtures.build_ua_setup(cst, sat, unsat, geom_kind=abi.GEOM_CUBOID, geom_ref_kind=abi.GEOMREF_POINT, geom_ref_point=(1.5, 2.5, 0.0),
+                                  geom_dims=(-1.0, 2.0, 0.0, 1.0, float("-inf"), float("inf")))
+    add("cuboid_point", cub, "ua_order_cuboid_point.yaml")
+    dyn = fixtures.build_ua_setup(cst, sat, unsat, normal_heads=heads, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0, collect_normals=True)
+    ndoc = yaml.safe_load(open(os.path.join(FILES, "ua_normals.yaml")))
+    add("dynamic_normals", dyn, "ua_order_dynamic_normals.yaml",
+        normals={k: np.array(v, np.float32).tolist() for k, v in ndoc.items()})
+    # leaflet export, Once (bit-exact fixture)
+    once = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL,
+                                   leaflet_freq_kind=abi.FREQ_ONCE, collect_leaflets=True)
+    ldoc = yaml.safe_load(open(os.path.join(FILES, "ua_leaflets_once.yaml")))
+    cases["leaflets_once_export"] = dict(setup=once.to_dict(), frames=list(range(traj.xyz.shape[0])), source="ua_leaflets_once.yaml",
+                                         leaflets={k: np.array(v, np.uint8).tolist() for k, v in ldoc.items()})
+    # order maps (tests_ua.rs:352-415): bin 0.5 x 2.0, min_samples 5, auto span = box of the structure file
+    msat = cst.select(lambda r, n: r == "POPC" and n in ("C50", "C20", "C13"))
+    munsat = cst.select(lambda r, n: r == "POPC" and n == "C24")
+    maps = fixtures.build_ua_setup(cst, msat, munsat, map_enabled=True, map_plane=abi.PLANE_XY, map_bin=(0.5, 2.0),
+                                   map_span_x=(0.0, float(sbox[0])), map_span_y=(0.0, float(sbox[1])))
+    mexp = {}
+    mdir = os.path.join(FILES, "ordermaps_ua")
+    for fn in sorted(os.listdir(mdir)):
+        if not fn.endswith("_full.dat") or "--" not in fn:
+            continue
+        rows = [ln.split() for ln in open(os.path.join(mdir, fn)) if ln[0] not in "#@$"]
+        mexp[fn] = [[float(a), float(b), float(c)] for a, b, c in rows]
+    cases["maps_basic"] = dict(setup=maps.to_dict(), frames=list(range(traj.xyz.shape[0])), source="ordermaps_ua/*_full.dat",
+                               maps=mexp, map_min_samples=5)
+    np.savez_compressed(os.path.join(HERE, "ua_traj.npz"), q=q, box=traj.box.astype(np.float32), time=traj.time,
+                        structure_box=sbox.astype(np.float32), cases=json.dumps(cases))
+    print("ua_traj", q.shape, "cases:", list(cases))
+    # hydrogen goldens (uaorder.rs:1113-1200): atom indices are absolute in ua.tpr
+    hyd = {
+        "ch2": dict(kind=abi.UA_CH2, idx=[39, 38, 40], gold=[[2.3435528, 2.1503785, 2.1272178], [2.35857, 2.3045487, 2.039533]]),
+        "ch3": dict(kind=abi.UA_CH3, idx=[49, 48, 47], gold=[[3.3708375, 2.7527616, 2.257202], [3.254057, 2.8633823, 2.3334126], [3.3182635, 2.8995805, 2.1713943]]),
+        "ch1_unsat": dict(kind=abi.UA_CH1_UNSAT, idx=[23, 22, 24], gold=[[1.0985602, 2.994375, 2.7727659]]),
+        "ch1_sat": dict(kind=abi.UA_CH1_SAT, idx=[12, 11, 31, 13], gold=[[1.5022101, 2.6938448, 1.7839708]]),
+    }
+    for v in hyd.values():
+        v["atoms"] = [[float(np.float32(c)) for c in tpr_xyz[i]] for i in v["idx"]]
+        v["atoms_hex"] = [[np.float32(c).tobytes().hex() for c in tpr_xyz[i]] for i in v["idx"]]
+    json.dump(dict(box=[float(x) for x in sbox], box_hex=[np.float32(x).tobytes().hex() for x in sbox], cases=hyd),
+              open(os.path.join(HERE, "ua_hydrogens.json"), "w"), indent=1)
+    print("ua_hydrogens ok")
+
+
+if __name__ == "__main__":
+    single_frame("cg_single_frame", "cg.gro", "cg.bnd", "cg.tpr", abi.KIND_CG, "cgorder.rs", 1.0, "PO4")
+    single_frame("aa_single_frame", "pcpepg.gro", "pcpepg.bnd", "pcpepg.tpr", abi.KIND_AA, "aaorder.rs", -1.0, "P")
+    ua_golden()

@@ -1,0 +1,74 @@
+"""Loader of the committed golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py
+from the reference's own test files and expected values)."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from gorder_b200 import abi, results
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIXTURE_TOL = 2e-4   # the reference's own comparator (tests/common/mod.rs:139-150); YAML holds 4 decimals
+
+
+def single_frame(name: str):
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    setup = abi.EngineSetup.from_dict(json.loads(str(z["setup"])))
+    exp = {k: np.array(v) for k, v in json.loads(str(z["expected"])).items()}
+    return setup, z["xyz"][None].astype(np.float32), z["box"][None].astype(np.float32), exp
+
+
+_UA = None
+
+
+def ua_traj():
+    global _UA
+    if _UA is None:
+        z = np.load(os.path.join(GOLDEN, "ua_traj.npz"))
+        xyz = z["q"].astype(np.float32) * np.float32(1.0 / 1000.0)   # exactly the XTC decoder's arithmetic
+        _UA = (xyz, z["box"].astype(np.float32), z["time"], z["structure_box"], json.loads(str(z["cases"])))
+    return _UA
+
+
+def ua_case(name: str):
+    xyz, box, _time, _sbox, cases = ua_traj()
+    c = cases[name]
+    setup = abi.EngineSetup.from_dict(c["setup"])
+    fr = np.array(c["frames"], dtype=np.int64)
+    # SystemTopology::frame counts trajectory frames from `begin` (topology/mod.rs:41-43)
+    frame_index = fr - fr[0]
+    return setup, xyz[fr], box[fr], frame_index, c
+
+
+def flatten_results(res: results.AnalysisResults, keys=("total",), with_error=False):
+    """Same traversal as make_golden.flatten_yaml."""
+    out = []
+
+    def push(coll):
+        for k in keys:
+            o = getattr(coll, k)
+            if o is None:
+                continue
+            out.append(o.value)
+            if with_error:
+                out.append(o.error)
+
+    push(res.average)
+    for m in res.molecules.values():
+        push(m.average)
+        for it in m.items:
+            push(it.order)
+            for b in it.bonds:
+                push(b)
+    return np.array(out, dtype=np.float64)
+
+
+def assert_matches_yaml(raw: abi.RawResults, setup: abi.EngineSetup, case: dict, tol: float = FIXTURE_TOL):
+    nb = case.get("n_blocks")
+    res = results.convert(raw, setup, n_blocks=nb)
+    got = flatten_results(res, tuple(case["keys"]), with_error=nb is not None)
+    exp = np.array(case["expected"], dtype=np.float64)
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    np.testing.assert_allclose(got, exp, atol=tol, rtol=0, equal_nan=True, err_msg=f"fixture {case['source']}")

@@ -1,0 +1,96 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, refuses to run without a device (no CPU fallback), and the ctypes mirror matches the header."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gorder_b200 import abi, synthetic
+from gorder_b200._lib import SYMBOLS, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gorder_b200.h")
+
+
+def test_library_exports_every_declared_symbol():
+    decl = set(re.findall(r"\b(gorder_gpu_[a-z_]+)\s*\(", open(HEADER).read()))
+    assert decl == set(SYMBOLS), decl ^ set(SYMBOLS)
+    L = lib()
+    for s in SYMBOLS:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in L.gorder_gpu_version()
+
+
+def test_enum_values_match_header():
+    src = open(HEADER).read()
+    for name, val in re.findall(r"GORDER_([A-Z0-9_]+)\s*=\s*(\d+)", src):
+        py = {"ACC_UPPER": "ACC_UPPER", "ACC_LOWER": "ACC_LOWER"}.get(name, name)
+        if hasattr(abi, py):
+            assert getattr(abi, py) == int(val), name
+    assert abi.ABI_VERSION == int(re.search(r"#define GORDER_ABI_VERSION (\d+)", src).group(1))
+
+
+def test_struct_layout_matches_c(tmp_path):
+    """Compile a tiny C program against the header and compare sizeof / offsetof with ctypes."""
+    import subprocess
+    fields = [("GorderSetup", "n_moltypes"), ("GorderSetup", "geom_ref_point"), ("GorderSetup", "map_bin"), ("GorderSetup", "max_batch_frames"),
+              ("GorderMolType", "manual_normals"), ("GorderResults", "normals")]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "gorder_b200.h"\nint main(){\n'
+    prog += 'printf("%zu %zu %zu\\n", sizeof(GorderSetup), sizeof(GorderMolType), sizeof(GorderResults));\n'
+    for st, f in fields:
+        prog += f'printf("%zu\\n", offsetof({st}, {f}));\n'
+    prog += "return 0;}\n"
+    src = tmp_path / "layout.c"
+    src.write_text(prog)
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    sizes = [int(x) for x in out[:3]]
+    assert sizes == [C.sizeof(abi.CGorderSetup), C.sizeof(abi.CGorderMolType), C.sizeof(abi.CGorderResults)]
+    cls = {"GorderSetup": abi.CGorderSetup, "GorderMolType": abi.CGorderMolType, "GorderResults": abi.CGorderResults}
+    for (st, f), off in zip(fields, out[3:]):
+        assert getattr(cls[st], f).offset == int(off), (st, f)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device gorder_gpu_create must fail with GORDER_ERR_NO_DEVICE, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from gorder_b200 import SystemTopology
+    s = synthetic.s_cg(64)
+    with pytest.raises(abi.GorderError) as e:
+        SystemTopology(s.setup)
+    assert e.value.code == abi.ERR_NO_DEVICE
+
+
+def test_invalid_arguments_are_rejected():
+    L = lib()
+    h = C.c_void_p()
+    assert L.gorder_gpu_create(None, C.byref(h)) == abi.ERR_INVALID_ARGUMENT
+    s = synthetic.s_cg(8).setup.to_c()
+    s.abi_version = 99
+    assert L.gorder_gpu_create(C.byref(s), C.byref(h)) == abi.ERR_INVALID_ARGUMENT
+    assert L.gorder_gpu_sync(None) == abi.ERR_INVALID_ARGUMENT
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under gorder_b200/ or include/ may reference it."""
+    for base in ("gorder_b200", "include"):
+        for dp, _dn, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dp, fn), errors="replace").read()
+                    assert "import oracle" not in txt and "from oracle" not in txt and "gorder_oracle_" not in txt, os.path.join(dp, fn)
+
+
+def test_synthetic_frames_are_reproducible():
+    s = synthetic.s_cg(100)
+    a, ba = s.frame(7)
+    b, bb = s.frame(7)
+    assert np.array_equal(a, b) and np.array_equal(ba, bb)
+    c, _ = s.frame(8)
+    assert not np.array_equal(a, c)
+    assert s.setup.samples_per_frame() == 1100

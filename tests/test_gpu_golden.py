@@ -1,0 +1,54 @@
+"""GPU vs the reference's own goldens (tests/golden, see make_golden.py) and vs the oracle on the
+same real-system inputs, through the C ABI."""
+import numpy as np
+import pytest
+
+from gorder_b200 import abi
+
+import golden_cases as gc
+from parity import assert_raw_parity, run_both
+from test_oracle_pins import UA_YAML_CASES, _mol_ranges, check_maps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,counts", [("cg_single_frame", ([242, 242, 24], [121, 121, 12], [121, 121, 12])),
+                                         ("aa_single_frame", ([131, 128, 15], [65, 64, 8], [66, 64, 7]))])
+def test_single_frame_goldens(name, counts):
+    setup, xyz, box, exp = gc.single_frame(name)
+    g, r = run_both(setup, xyz, box)
+    assert_raw_parity(g, r, setup, what=name)
+    for col, key in enumerate(("total", "upper", "lower")):
+        # reference tolerance 1e-5 on the raw sums + one unit of 1e-6 per sample for cos(acos(c)) -> c
+        tol = np.maximum(1e-5, np.abs(exp[key]) * 1.2e-7) + g.count[:, col] * 1e-6
+        assert np.all(np.abs(g.sum[:, col] / 1e6 - exp[key]) <= tol), key
+        for (s0, n), c in zip(setup.slot_ranges(), counts[col]):
+            assert np.all(g.count[s0:s0 + n, col] == c)
+
+
+@pytest.mark.parametrize("name", UA_YAML_CASES)
+def test_ua_trajectory_fixtures(name):
+    setup, xyz, box, fi, case = gc.ua_case(name)
+    g, r = run_both(setup, xyz, box, fi, batches=2, oracle_threads=8)
+    assert_raw_parity(g, r, setup, what=name)
+    gc.assert_matches_yaml(g, setup, case)
+    if name == "dynamic_normals":
+        for mt, (m0, n) in zip(setup.moltypes, _mol_ranges(setup)):
+            exp = np.array(case["normals"][mt.name], np.float32)
+            dots = np.abs(np.sum(exp * g.normals[:, m0:m0 + n, :], axis=-1))
+            assert np.all(dots > 1 - 2e-5), dots.min()
+
+
+def test_ua_leaflets_once_export_bit_exact():
+    setup, xyz, box, fi, case = gc.ua_case("leaflets_once_export")
+    g, r = run_both(setup, xyz, box, fi, batches=3)
+    assert_raw_parity(g, r, setup, what="once export")
+    for mt, (m0, n) in zip(setup.moltypes, _mol_ranges(setup)):
+        np.testing.assert_array_equal(g.leaflets[0, m0:m0 + n], np.array(case["leaflets"][mt.name][0], np.uint8))
+
+
+def test_ua_ordermaps_fixture():
+    setup, xyz, box, fi, case = gc.ua_case("maps_basic")
+    g, r = run_both(setup, xyz, box, fi)
+    assert_raw_parity(g, r, setup, what="maps")
+    check_maps(g, setup, case)

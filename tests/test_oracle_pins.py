@@ -1,0 +1,223 @@
+"""Pins of the CPU oracle against the reference's own golden vectors, known-answer tests and
+fixtures.  CPU only.  Every expected number below comes from the reference tree:
+
+  calc_sch known answer                      src/analysis/mod.rs:94-105
+  UA hydrogen positions (18 coordinates)     src/analysis/uaorder.rs:1113-1200      (<= 1 ulp)
+  CG single-frame sums + leaflet counts      src/analysis/cgorder.rs:188-302
+  AA single-frame sums + leaflet counts      src/analysis/aaorder.rs:226-415
+  OrderValue rounding / integer division     src/analysis/order.rs:21-41; converter.rs:787-794
+  block error 0.0514468, prefix averages     src/analysis/timewise.rs:595-648
+  cuboid construct_shape / inside            src/analysis/geometry.rs:527-664
+  UA end-to-end YAML / maps / leaflets / normals fixtures   tests/files/ua_order_*.yaml, ordermaps_ua/, ...
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from gorder_b200 import abi, results
+from oracle import oracle
+
+import golden_cases as gc
+
+
+def test_calc_sch_known_answer():
+    v = oracle.vector_to([1.7, 2.1, 9.7], [1.9, 2.4, 0.8], [10, 10, 10])
+    assert abs(oracle.calc_sch(v, [0, 0, 1]) - 0.8544775) < 1e-6
+
+
+def test_ua_hydrogens_bit_exact():
+    d = json.load(open(os.path.join(gc.GOLDEN, "ua_hydrogens.json")))
+    box = np.array([np.frombuffer(bytes.fromhex(h), np.float32)[0] for h in d["box_hex"]], np.float32)
+    for name, c in d["cases"].items():
+        atoms = np.array([[np.frombuffer(bytes.fromhex(h), np.float32)[0] for h in a] for a in c["atoms_hex"]], np.float32)
+        h3 = atoms[3] if len(atoms) > 3 else None
+        got = oracle.predict_hydrogens(c["kind"], atoms[0], atoms[1], atoms[2], h3, box)
+        gold = np.array(c["gold"], np.float32)
+        ulps = np.abs(got.view(np.int32).astype(np.int64) - gold.view(np.int32).astype(np.int64))
+        assert ulps.max() <= 1, (name, ulps)   # the reference asserts relative 1.2e-7 (= 1 ulp); we hit 0
+
+
+def test_min_image_variant_is_pinned():
+    """The alternatives to the frozen fold / wrap do NOT reproduce the hydrogen goldens."""
+    import ctypes as C
+    L = oracle.lib()
+    vm = C.c_int.in_dll(L, "gorder_oracle_variant_minimage")
+    d = json.load(open(os.path.join(gc.GOLDEN, "ua_hydrogens.json")))
+    box = np.array([np.frombuffer(bytes.fromhex(h), np.float32)[0] for h in d["box_hex"]], np.float32)
+
+    def worst():
+        w = 0
+        for c in d["cases"].values():
+            atoms = np.array([[np.frombuffer(bytes.fromhex(h), np.float32)[0] for h in a] for a in c["atoms_hex"]], np.float32)
+            got = oracle.predict_hydrogens(c["kind"], atoms[0], atoms[1], atoms[2], atoms[3] if len(atoms) > 3 else None, box)
+            gold = np.array(c["gold"], np.float32)
+            w = max(w, int(np.abs(got.view(np.int32).astype(np.int64) - gold.view(np.int32).astype(np.int64)).max()))
+        return w
+
+    assert vm.value == 1 and worst() == 0
+    vm.value = 0
+    try:
+        assert worst() > 1
+    finally:
+        vm.value = 1
+
+
+@pytest.mark.parametrize("name,counts", [("cg_single_frame", ([242, 242, 24], [121, 121, 12], [121, 121, 12])),
+                                         ("aa_single_frame", ([131, 128, 15], [65, 64, 8], [66, 64, 7]))])
+def test_single_frame_goldens(name, counts):
+    setup, xyz, box, exp = gc.single_frame(name)
+    o = oracle.Oracle(setup, n_threads=2)
+    o.analyze_frames(xyz, box)
+    r = o.finish()
+    o.close()
+    for col, key in enumerate(("total", "upper", "lower")):
+        got = r.sum[:, col] / 1e6
+        # the goldens are f32 prints: tolerance = the reference's own (epsilon 1e-5, relative f32 eps)
+        tol = np.maximum(1e-5, np.abs(exp[key]) * 1.2e-7)
+        assert np.all(np.abs(got - exp[key]) <= tol), (key, np.abs(got - exp[key]).max())
+        for (s0, n), c in zip(setup.slot_ranges(), counts[col]):
+            assert np.all(r.count[s0:s0 + n, col] == c)
+
+
+def test_order_value_and_integer_division():
+    assert oracle.order_value(0.1234565) == round(float(np.float32(0.1234565)) * 1e6)
+    assert oracle.order_value(-0.5) == -500000 and oracle.order_value(1.0) == 1000000
+    assert oracle.order_value(np.float32(2.5e-7)) == 0 and oracle.order_value(np.float32(5.000001e-7)) == 1
+    # converter.rs:787-794: AnalysisOrder::new(45.32, 56) -> 0.8092857 (UA reports the negative)
+    total = oracle.order_value(45.32)
+    assert total == 45320000
+    assert abs(oracle.calc_order(total, 56) - 0.8092857) < 1e-6
+    assert results.calc_order(total, 56) == pytest.approx(0.8092857, abs=1e-6)
+    # integer division truncates toward zero (order.rs:34-41)
+    assert oracle.calc_order(-7, 2) == pytest.approx(-3e-6, abs=1e-12) and results.calc_order(-7, 2) == pytest.approx(-3e-6, abs=1e-12)
+    assert np.isnan(oracle.calc_order(10, 3, 5))
+
+
+def test_block_error_and_prefix_average_known_answers():
+    # timewise.rs:594-616: estimate_error(5) == 0.0514468 (f32 relative eq)
+    order = [10.0, 15.0, 18.0, 12.0, 14.0, 15.0, 16.0, 20.0, 21.0, 18.0, 9.0, 11.0, 13.0, 14.0, 19.0, 16.0, 17.0]
+    samples = np.array([10, 12, 15, 11, 13, 11, 11, 17, 18, 15, 8, 10, 12, 13, 17, 14, 15], np.uint64)
+    sums = np.array([oracle.order_value(x) for x in order], np.int64)
+    e = oracle.estimate_error(sums, samples, 5)
+    assert e == pytest.approx(0.0514468, abs=1.2e-7)   # assert_relative_eq! default: absolute f32::EPSILON
+    assert results.estimate_error(sums, samples, 5) == pytest.approx(0.0514468, abs=1.2e-7)
+    assert oracle.estimate_error(np.zeros(0, np.int64), np.zeros(0, np.uint64), 5) is None
+    # timewise.rs:624-647: prefix averages
+    order = [10.0, 12.0, 15.0, 10.0, 9.0, 12.0, 98432.0]
+    samples = np.array([13, 15, 20, 12, 11, 14, 98432], np.uint64)
+    sums = np.array([oracle.order_value(x) for x in order], np.int64)
+    expected = [0.769230769, 0.785714286, 0.770833333, 0.783333333, 0.788732394, 0.8, 0.999827441]
+    np.testing.assert_allclose(oracle.prefix_average(sums, samples), expected, atol=1e-5)
+    np.testing.assert_allclose(results.prefix_average(sums, samples), expected, atol=1e-5)
+
+
+def test_cuboid_shape_construction():
+    # geometry.rs:527-604
+    s = abi.EngineSetup(kind=abi.KIND_CG, n_atoms=1, moltypes=[], geom_kind=abi.GEOM_CUBOID,
+                        geom_dims=(2.5, 3.1, -1.5, 3.5, -1.0, 1.0))
+    o = oracle.shape_origin(s, [0, 0, 0], [10, 6, 8])
+    np.testing.assert_allclose(o[:6], [2.5, 4.5, 7.0, 0.6, 5.0, 2.0], rtol=2e-7)
+    o = oracle.shape_origin(s, [8.0, 5.5, 2.0], [10, 6, 8])
+    np.testing.assert_allclose(o[:3], [0.5, 4.0, 1.0], rtol=2e-7)
+    s.geom_dims = (2.5, 3.1, float("-inf"), float("inf"), -1.0, 1.0)
+    o = oracle.shape_origin(s, [15.0, 5.5, 1.0], [10, 6, 8])
+    np.testing.assert_allclose(o[:3], [7.5, 0.0, 0.0], rtol=2e-7)
+    assert np.isinf(o[4])
+    assert oracle.shape_inside(s, [15.0, 5.5, 1.0], [7.8, -124.4, 1.5], [10, 6, 8])
+    assert oracle.shape_inside(s, [15.0, 5.5, 1.0], [7.8, 124.4, 1.5], [10, 6, 8])
+
+
+def test_cuboid_inside_random():
+    # geometry.rs:607-664: PBC-aware predicate equals the naive open-interval one for points in the box
+    rng = np.random.default_rng(1288746347198273 % (2 ** 32))
+    for i in range(40):
+        lo, hi = np.sort(rng.uniform(0, 10, (2, 3)), axis=0)
+        dims = [lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]]
+        if i % 8 == 0:
+            dims[0:2] = [float("-inf"), float("inf")]
+        if i % 6 == 0:
+            dims[4:6] = [float("-inf"), float("inf")]
+        s = abi.EngineSetup(kind=abi.KIND_CG, n_atoms=1, moltypes=[], geom_kind=abi.GEOM_CUBOID, geom_dims=tuple(float(x) for x in dims))
+        for _ in range(100):
+            p = rng.uniform(0, 10, 3).astype(np.float32)
+            naive = all(np.float32(dims[2 * a]) < p[a] < np.float32(dims[2 * a + 1]) for a in range(3))
+            assert oracle.shape_inside(s, [0, 0, 0], p, [10, 10, 10]) == naive
+
+
+UA_YAML_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "error", "error_leaflets", "begin_end_step",
+                 "cylinder_center", "cuboid_point", "dynamic_normals"]
+
+
+@pytest.mark.parametrize("name", UA_YAML_CASES)
+def test_ua_trajectory_fixtures(name):
+    """51-frame Berger POPC/POPS trajectory: the oracle reproduces the reference's YAML outputs."""
+    setup, xyz, box, fi, case = gc.ua_case(name)
+    o = oracle.Oracle(setup, n_threads=8)
+    o.analyze_frames(xyz, box, fi)
+    raw = o.finish()
+    o.close()
+    gc.assert_matches_yaml(raw, setup, case)
+    if name == "dynamic_normals":   # ua_normals.yaml: signed components at 1e-5 (tests/common/mod.rs:55-91); sign is nalgebra's
+        for (mt, (m0, n)) in zip(setup.moltypes, _mol_ranges(setup)):
+            exp = np.array(case["normals"][mt.name], np.float32)
+            got = raw.normals[:, m0:m0 + n, :]
+            assert exp.shape == got.shape
+            dots = np.abs(np.sum(exp * got, axis=-1))
+            assert np.all(dots > 1 - 2e-5), dots.min()
+            same_sign = np.mean(np.sum(exp * got, axis=-1) > 0)
+            print(f"{mt.name}: {same_sign:.3f} of the normals have the reference's sign")
+
+
+def _mol_ranges(setup):
+    out, m = [], 0
+    for mt in setup.moltypes:
+        out.append((m, mt.n_molecules))
+        m += mt.n_molecules
+    return out
+
+
+def test_ua_leaflets_once_export_bit_exact():
+    setup, xyz, box, fi, case = gc.ua_case("leaflets_once_export")
+    o = oracle.Oracle(setup, n_threads=4)
+    o.analyze_frames(xyz, box, fi)
+    raw = o.finish()
+    o.close()
+    assert raw.leaflets.shape[0] == 1
+    for mt, (m0, n) in zip(setup.moltypes, _mol_ranges(setup)):
+        np.testing.assert_array_equal(raw.leaflets[0, m0:m0 + n], np.array(case["leaflets"][mt.name][0], np.uint8))
+
+
+def test_ua_ordermaps_fixture():
+    setup, xyz, box, fi, case = gc.ua_case("maps_basic")
+    o = oracle.Oracle(setup, n_threads=8)
+    o.analyze_frames(xyz, box, fi)
+    raw = o.finish()
+    o.close()
+    check_maps(raw, setup, case)
+
+
+def check_maps(raw, setup, case):
+    """ordermaps_ua/ordermap_<atom>--<H>_full.dat: x y value rows, x-major; NaN below min_samples."""
+    nx, ny = raw.map_shape
+    # slots in order: per carbon (sorted by relative index), per hydrogen
+    labels = []
+    mt = setup.moltypes[0]
+    for i, kind in enumerate(mt.ua_kind):
+        atom = mt.bond_names[i].split()   # "POPC C13 (12)"
+        for h in range(abi.ua_hydrogens(kind)):
+            labels.append(f"ordermap_{atom[0]}-{atom[1]}-{atom[2].strip('()')}--{atom[0]}-H{h + 1}-{atom[2].strip('()')}_full.dat")
+    assert set(labels) == set(case["maps"].keys()), (labels, list(case["maps"].keys()))
+    for s, lab in enumerate(labels):
+        rows = np.array(case["maps"][lab], np.float64)
+        assert rows.shape[0] == nx * ny, (rows.shape, nx, ny)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            val = -(raw.map_sum[s, 0].astype(np.float64) / 1e6) / raw.map_count[s, 0].astype(np.float64)
+        val = np.where(raw.map_count[s, 0] < case["map_min_samples"], np.nan, val).reshape(-1)
+        np.testing.assert_allclose(val, rows[:, 2], atol=gc.FIXTURE_TOL, rtol=0, equal_nan=True, err_msg=lab)
+        # node coordinates: min + i * bin (GridMap is node-centred)
+        xs = np.repeat(np.arange(nx) * setup.map_bin[0], ny)
+        ys = np.tile(np.arange(ny) * setup.map_bin[1], nx)
+        np.testing.assert_allclose(rows[:, 0], xs, atol=1e-3)
+        np.testing.assert_allclose(rows[:, 1], ys, atol=1e-3)
