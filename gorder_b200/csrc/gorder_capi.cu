@@ -118,6 +118,13 @@ struct GorderHandle {
     double prof_ms = 0.0;
     long long prof_n = 0;
 
+    // persistent pipeline (K1p)
+    bool pipe_ok = false;
+    int pipe_grid = 0, pipe_p_items = 0, pipe_segs_per_item = 0, pipe_lag1 = 3, pipe_lag2 = 6;
+    double *d_pipe_partial0 = nullptr, *d_pipe_partial1 = nullptr;
+    unsigned *d_pipe_ctrl = nullptr;   // [4 * max_batch + 1]: done0, done1, ready0, ready1, work
+    float *d_pipe_est = nullptr, *d_pipe_center = nullptr;
+
     long long n_frames = 0;
     long long n_launches = 0;
     long long last_frame_index = -1;
@@ -215,6 +222,8 @@ void launch_ua(GorderHandle *h, dim3 grid, size_t smem, const float *planes, con
     else { if (h->nvec) launch_ua2<false, true>(h, grid, smem, planes, aux, o); else launch_ua2<false, false>(h, grid, smem, planes, aux, o); }
 }
 
+size_t accum_smem(const GorderHandle *h);
+size_t pipe_smem(const GorderHandle *h) { return std::max(accum_smem(h), (size_t)h->pipe_p_items * 2 * sizeof(double)); }
 size_t accum_smem(const GorderHandle *h) {
     int max_items = 0, max_orders = 0;
     for (auto &t : h->types) { max_items = std::max(max_items, t.n_items); max_orders = std::max(max_orders, t.n_orders); }
@@ -341,7 +350,8 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         frame_setup_kernel<<<(nf + 63) / 64, 64, 0, h->stream>>>(h->view, da, d_box, nf, 1);
         h->n_launches++;
     }
-    if (h->leaf && n_assign > 0) {
+    const bool use_pipe = h->pipe_ok && n_assign == nf;
+    if (h->leaf && n_assign > 0 && !use_pipe) {
         if (s.leaflet_mode == GORDER_LEAFLET_GLOBAL) {
             int rc = run_group_center(h, h->seg_membrane, h->s.n_membrane, 1 << s.leaflet_axis, d_planes, da, dl_assign, n_assign);
             if (rc) return rc;
@@ -349,14 +359,6 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         dim3 grid((h->n_molpad + 255) / 256, n_assign);
         leaflet_assign_kernel<<<grid, 256, 0, h->stream>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_molpad_type, h->d_leaf_rows);
         h->n_launches++;
-        if (s.collect_leaflets) {
-            int rc = grow_collect(h, &h->d_leaf_collect, &h->leaf_collect_cap, h->n_leaf_collected, h->n_leaf_collected + n_assign, (size_t)h->n_molpad);
-            if (rc) return rc;
-            CK(cudaMemcpyAsync(h->d_leaf_collect + (size_t)h->n_leaf_collected * h->n_molpad, h->d_leaf_rows + h->n_molpad,
-                               (size_t)n_assign * h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
-            for (int a = 0; a < n_assign; a++) h->leaf_frame_index.push_back(frame_index[list_assign[a]]);
-            h->n_leaf_collected += n_assign;
-        }
     }
     if (h->nvec) {
         if (s.normal_mode == GORDER_NORMAL_DYNAMIC) {
@@ -381,6 +383,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     o.bsum = h->d_bsum; o.bcnt = h->d_bcnt; o.map_sum = h->d_map_sum; o.map_cnt = h->d_map_cnt; o.normal_used = h->d_normal_used;
     dim3 grid(h->n_chunks, nf);
     const size_t smem = accum_smem(h);
+    if (use_pipe) CK(cudaMemsetAsync(h->d_pipe_ctrl, 0, (4 * (size_t)h->max_batch + 1) * sizeof(unsigned), h->stream));
     std::pair<cudaEvent_t, cudaEvent_t> *pe = nullptr;
     if (h->profiling) {
         if (h->prof_used == h->prof_events.size()) {
@@ -391,7 +394,20 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         pe = &h->prof_events[h->prof_used++];
         CK(cudaEventRecord(pe->first, h->stream));
     }
-    if (h->ua) launch_ua(h, grid, smem, d_planes, da, o);
+    if (use_pipe) {
+        PipeParams pp;
+        pp.segs = h->seg_membrane[s.leaflet_axis].d; pp.n_segs = h->seg_membrane[s.leaflet_axis].n;
+        pp.segs_per_item = h->pipe_segs_per_item; pp.n_p_items = h->pipe_p_items; pp.n_h_items = h->n_chunks;
+        pp.n_frames = nf; pp.n_group = s.n_membrane; pp.lag1 = h->pipe_lag1; pp.lag2 = h->pipe_lag2;
+        pp.partial0 = h->d_pipe_partial0; pp.partial1 = h->d_pipe_partial1;
+        pp.done0 = h->d_pipe_ctrl; pp.done1 = h->d_pipe_ctrl + h->max_batch; pp.ready0 = h->d_pipe_ctrl + 2 * h->max_batch;
+        pp.ready1 = h->d_pipe_ctrl + 3 * h->max_batch; pp.work = h->d_pipe_ctrl + 4 * h->max_batch;
+        pp.est = h->d_pipe_est; pp.center = h->d_pipe_center;
+        pp.leaf_out = s.collect_leaflets ? h->d_leaf_rows : nullptr;
+        if (h->mpt == 4) global_leaflet_pipeline_kernel<4><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
+        else if (h->mpt == 2) global_leaflet_pipeline_kernel<2><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
+        else global_leaflet_pipeline_kernel<1><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
+    } else if (h->ua) launch_ua(h, grid, smem, d_planes, da, o);
     else if (h->mpt == 4) launch_bond3<4>(h, grid, smem, d_planes, da, o);
     else if (h->mpt == 2) launch_bond3<2>(h, grid, smem, d_planes, da, o);
     else launch_bond3<1>(h, grid, smem, d_planes, da, o);
@@ -402,7 +418,20 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
                                                                   h->d_tot_sum, h->d_tot_cnt);
     h->n_launches++;
     CK(cudaGetLastError());
-    if (h->leaf && n_assign > 0) {   // keep the newest table for the frames of the next batch
+    if (h->leaf && n_assign > 0 && s.collect_leaflets) {
+        int rc = grow_collect(h, &h->d_leaf_collect, &h->leaf_collect_cap, h->n_leaf_collected, h->n_leaf_collected + n_assign, (size_t)h->n_molpad);
+        if (rc) return rc;
+        if (use_pipe) {   // the pipeline writes row 1 + f for every frame f
+            CK(cudaMemcpyAsync(h->d_leaf_collect + (size_t)h->n_leaf_collected * h->n_molpad, h->d_leaf_rows + h->n_molpad,
+                               (size_t)nf * h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            CK(cudaMemcpyAsync(h->d_leaf_collect + (size_t)h->n_leaf_collected * h->n_molpad, h->d_leaf_rows + h->n_molpad,
+                               (size_t)n_assign * h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        for (int a = 0; a < n_assign; a++) h->leaf_frame_index.push_back(frame_index[list_assign[a]]);
+        h->n_leaf_collected += n_assign;
+    }
+    if (h->leaf && n_assign > 0 && !use_pipe) {   // keep the newest table for the frames of the next batch
         CK(cudaMemcpyAsync(h->d_leaf_rows, h->d_leaf_rows + (size_t)n_assign * h->n_molpad, h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
         h->have_leaflets = true;
         h->cur_leaflet_frame = frame_index[list_assign[n_assign - 1]];
@@ -687,6 +716,37 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     if ((rc = dev_alloc(h, &h->d_center, B * 3))) return rc;
     if ((rc = dev_alloc(h, &h->d_partial, B * kCenterBlocks * 2))) return rc;
     if ((rc = dev_alloc(h, &h->d_ticket, B, true))) return rc;
+
+    // persistent pipeline: AA/CG, static normal, PBC, Global leaflets on every analysed frame, no geometry / maps
+    h->pipe_ok = !ua && !h->nvec && !h->extra && s->handle_pbc && s->leaflet_mode == GORDER_LEAFLET_GLOBAL &&
+                 s->leaflet_freq_kind == GORDER_FREQ_EVERY && s->leaflet_freq <= std::max(1, s->step) && getenv("GORDER_PIPELINE");
+    // (experimental, opt-in: on S-CG it is only ~2% faster than the separate kernels because the step is
+    //  latency / issue bound, not HBM bound; see profiles/README.md)
+    if (h->pipe_ok) {
+        const int nseg = h->seg_membrane[s->leaflet_axis].n;
+        h->pipe_segs_per_item = 16;
+        h->pipe_p_items = std::max(1, (nseg + h->pipe_segs_per_item - 1) / h->pipe_segs_per_item);
+        if ((rc = dev_alloc(h, &h->d_pipe_partial0, B * h->pipe_p_items * 2))) return rc;
+        if ((rc = dev_alloc(h, &h->d_pipe_partial1, B * h->pipe_p_items))) return rc;
+        if ((rc = dev_alloc(h, &h->d_pipe_ctrl, 4 * B + 1, true))) return rc;
+        if ((rc = dev_alloc(h, &h->d_pipe_est, B))) return rc;
+        if ((rc = dev_alloc(h, &h->d_pipe_center, B))) return rc;
+        int per_sm = 0, n_sm = 0;
+        const size_t smem = pipe_smem(h);
+        cudaError_t e1 = h->mpt == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, global_leaflet_pipeline_kernel<4>, kBlock, smem)
+                       : h->mpt == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, global_leaflet_pipeline_kernel<2>, kBlock, smem)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, global_leaflet_pipeline_kernel<1>, kBlock, smem);
+        CK(e1);
+        CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+        if (const char *e = getenv("GORDER_PIPE_CTAS_PER_SM")) { int q = atoi(e); if (q >= 1 && q < per_sm) per_sm = q; }
+        h->pipe_grid = per_sm * n_sm;   // every CTA must be resident (flag waits)
+        // dependencies of an item should have been popped a full wave (pipe_grid items) earlier
+        const int per_slot = 2 * h->pipe_p_items + h->n_chunks;
+        h->pipe_lag1 = std::max(1, (h->pipe_grid + per_slot - 1) / per_slot + 1);
+        h->pipe_lag2 = 2 * h->pipe_lag1;
+        if (const char *e = getenv("GORDER_PIPE_LAG")) { int q = atoi(e); if (q >= 1) { h->pipe_lag1 = q; h->pipe_lag2 = 2 * q; } }
+        if (h->pipe_grid <= 0 || pipe_smem(h) > 48 * 1024) h->pipe_ok = false;
+    }
 
     // dynamic shared memory of the accumulation kernels (small; no opt-in needed below 48 KB)
     if (accum_smem(h) > 48 * 1024) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "too many order slots per molecule type for shared memory"); return h->err_code; }
