@@ -572,7 +572,11 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         } else {
             td.item_off = (int)bonds.size(); td.n_items = m.n_bond_types; td.n_orders = m.n_bond_types;
             for (int i = 0; i < m.n_bond_types; i++) {
-                bonds.push_back(BondItem{u_of(m.bond_rel[2 * i]) * 3 * td.mpad, u_of(m.bond_rel[2 * i + 1]) * 3 * td.mpad});
+                // plane offsets are multiples of 32: the two low bits of a_off carry the register-reuse hint
+                int reuse = 0;
+                if (i > 0 && m.bond_rel[2 * i] == m.bond_rel[2 * (i - 1)]) reuse = 1;            // same first atom as the previous bond
+                else if (i > 0 && m.bond_rel[2 * i] == m.bond_rel[2 * (i - 1) + 1]) reuse = 2;   // previous bond's second atom
+                bonds.push_back(BondItem{u_of(m.bond_rel[2 * i]) * 3 * td.mpad + reuse, u_of(m.bond_rel[2 * i + 1]) * 3 * td.mpad});
                 islots.push_back(m.bond_rel[2 * i]);
             }
         }

@@ -281,10 +281,10 @@ __global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const
     if (mp >= v.n_molpad) return;
     const int t = molpad_type[mp];
     if (t < 0) return;
-    const TypeDesc &td = v.types[t];
-    const int m = mp - td.molpad0;
+    const TypeDesc &td = v.types[t];   // fields are read individually (read-only cache), not copied
+    const int m = mp - __ldg(&td.molpad0);
     unsigned char out = GORDER_UPPER;
-    if (m < td.n_mol) {
+    if (m < __ldg(&td.n_mol)) {
         const FrameAux &a = aux[f];
         const int ax = v.leaflet_axis;
         const bool pbc = v.handle_pbc != 0;
@@ -561,6 +561,9 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
                                                             const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
                                                             const int *__restrict__ normal_npoints, AccumOut o) {
     constexpr int NA = AccLayout<LEAF, EXTRA>::N;
+    // Static normal without geometry / maps: S depends only on (d_axis, |d|^2), so the kernel reads the
+    // components in the order (axis+1, axis+2, axis) and never selects a component at run time.
+    constexpr bool PERMUTE = !NVEC && !EXTRA;
     extern __shared__ int smem[];
     const Chunk ch = v.chunks[blockIdx.x];
     const TypeDesc td = v.types[ch.type];
@@ -577,15 +580,24 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m0 = ch.first_mol + threadIdx.x * MPT;
     const bool active = m0 < td.mpad;
-    bool valid[MPT], up[MPT];
-    f3 nrm[MPT];
+    const int mpad = td.mpad;
+    const int c0 = PERMUTE ? (v.normal_axis + 1) % 3 : 0, c1 = PERMUTE ? (v.normal_axis + 2) % 3 : 1, c2 = PERMUTE ? v.normal_axis : 2;
+    const int o0 = c0 * mpad, o1 = c1 * mpad, o2 = c2 * mpad;
+    // box in the kernel's component order, with the fast-path guard of the fold
+    const float L0 = ax.L[c0], L1 = ax.L[c1], L2 = ax.L[c2];
+    const float h0 = ax.half[c0], h1 = ax.half[c1], h2 = ax.half[c2];
+    const float g0 = 0.99f * h0, g1 = 0.99f * h1, g2 = 0.99f * h2;
     const Box bx = load_box(ax);
+    bool valid[MPT];
+    int upmask[MPT];
+    f3 nrm[MPT];
     int nvalid = 0, nup = 0;
 #pragma unroll
     for (int j = 0; j < MPT; j++) {
         valid[j] = active && (m0 + j < td.n_mol);
-        up[j] = false;
-        if (LEAF && valid[j]) up[j] = leaf_rows[(size_t)ax.leaf_row * v.n_molpad + td.molpad0 + m0 + j] == GORDER_UPPER;
+        bool up = false;
+        if (LEAF && valid[j]) up = leaf_rows[(size_t)ax.leaf_row * v.n_molpad + td.molpad0 + m0 + j] == GORDER_UPPER;
+        upmask[j] = up ? -1 : 0;
         if (NVEC) {
             nrm[j] = mk3(0.f, 0.f, 1.f);
             if (valid[j]) {
@@ -593,7 +605,7 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
                 nrm[j] = mk3(np[0], np[v.n_molpad], np[2 * (size_t)v.n_molpad]);
             }
         }
-        nvalid += valid[j]; nup += valid[j] && up[j];
+        nvalid += valid[j]; nup += valid[j] && up;
     }
     if (!EXTRA) {
         int a = __reduce_add_sync(0xffffffffu, nvalid), b = __reduce_add_sync(0xffffffffu, nup);
@@ -602,48 +614,57 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
     bool any_used[MPT];
 #pragma unroll
     for (int j = 0; j < MPT; j++) any_used[j] = false;
+    float nan_acc = 0.0f;   // NaN coordinates poison this accumulator (checked once after the loop)
 
     const float *base = planes + (size_t)f * v.frame_floats + td.plane_base + m0;
-    const int mpad = td.mpad;
+    Vec<MPT> x1, y1, z1, x2, y2, z2;
+#pragma unroll
+    for (int j = 0; j < MPT; j++) { x1.v[j] = y1.v[j] = z1.v[j] = x2.v[j] = y2.v[j] = z2.v[j] = 0.0f; }
     for (int b = 0; b < nb; b++) {
         const BondItem bi = s_bonds[b];
-        Vec<MPT> x1, y1, z1, x2, y2, z2;
+        // low bits of a_off: 1 = first atom is the previous bond's first atom, 2 = ... second atom
+        const int reuse = bi.a_off & 3, a_off = bi.a_off & ~3;
+        if (reuse == 2) { x1 = x2; y1 = y2; z1 = z2; }
         if (active) {
-            x1.load(base + bi.a_off); y1.load(base + bi.a_off + mpad); z1.load(base + bi.a_off + 2 * mpad);
-            x2.load(base + bi.b_off); y2.load(base + bi.b_off + mpad); z2.load(base + bi.b_off + 2 * mpad);
+            if (reuse == 0) { x1.load(base + a_off + o0); y1.load(base + a_off + o1); z1.load(base + a_off + o2); }
+            x2.load(base + bi.b_off + o0); y2.load(base + bi.b_off + o1); z2.load(base + bi.b_off + o2);
         }
-        int su = 0, sl = 0, cu = 0, cl = 0;
+        int st = 0, su = 0, ct = 0, cu = 0;   // total / upper (lower = total - upper)
 #pragma unroll
         for (int j = 0; j < MPT; j++) {
-            if (!valid[j]) continue;
-            const f3 p1 = mk3(x1.v[j], y1.v[j], z1.v[j]), p2 = mk3(x2.v[j], y2.v[j], z2.v[j]);
-            const f3 d = vector_to<PBC>(p1, p2, bx);
+            f3 d = mk3(__fsub_rn(x2.v[j], x1.v[j]), __fsub_rn(y2.v[j], y1.v[j]), __fsub_rn(z2.v[j], z1.v[j]));
+            if (PBC) { d.x = min_image_g(d.x, L0, h0, g0); d.y = min_image_g(d.y, L1, h1, g1); d.z = min_image_g(d.z, L2, h2, g2); }
+            bool use = valid[j];
             f3 mid;
             if (EXTRA) {
                 // bond_pos = pos1 + vec / 2 (bond.rs:422)
-                mid = mk3(__fadd_rn(p1.x, d.x * 0.5f), __fadd_rn(p1.y, d.y * 0.5f), __fadd_rn(p1.z, d.z * 0.5f));
-                if (v.shape.kind != GORDER_GEOM_NONE && !shape_inside<PBC>(v.shape, ax, bx, mid)) continue;
-                any_used[j] = true;
+                mid = mk3(__fadd_rn(x1.v[j], d.x * 0.5f), __fadd_rn(y1.v[j], d.y * 0.5f), __fadd_rn(z1.v[j], d.z * 0.5f));
+                if (use && v.shape.kind != GORDER_GEOM_NONE) use = shape_inside<PBC>(v.shape, ax, bx, mid);
+                any_used[j] = any_used[j] || use;
             }
             float s;
             if (NVEC) {
-                if (nrm[j].x != nrm[j].x) {   // normal could not be computed (normal.rs:424)
+                if (use && nrm[j].x != nrm[j].x) {   // normal could not be computed (normal.rs:424)
                     int npts = normal_npoints ? normal_npoints[(size_t)f * v.n_molpad + td.molpad0 + m0 + j] : 0;
                     raise_error(v, v.normal_mode == GORDER_NORMAL_DYNAMIC ? GORDER_ERR_DYNAMIC_NORMAL_POINTS : GORDER_ERR_MANUAL_NORMAL_FRAME, npts);
-                    continue;
+                    use = false;
                 }
                 s = calc_sch_fast(d, nrm[j]);
-            } else s = calc_sch_axis_fast(d, comp(d, v.normal_axis));
-            if (s != s) {   // NaN coordinate reached the engine: AnalysisError::UndefinedPosition
-                raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | ((long long)b << 32) | (unsigned)(m0 + j));
-                continue;
-            }
+            } else s = calc_sch_axis_fast(d, PERMUTE ? d.z : comp(d, v.normal_axis));
+            s = use ? s : 0.0f;
+            nan_acc = fmaf(s, 0.0f, nan_acc);
             const int q = order_value_fast(s);
-            if (LEAF && !up[j]) { sl += q; cl++; } else { su += q; cu++; }
-            if (EXTRA && v.map.enabled) map_add<LEAF>(v, o, td.slot0 + b, mid, q, up[j]);
+            st += q; su += q & upmask[j];
+            if (EXTRA) {
+                ct += use; cu += use & (upmask[j] & 1);
+                if (use && v.map.enabled) map_add<LEAF>(v, o, td.slot0 + b, mid, q, upmask[j] != 0);
+            }
         }
-        warp_commit<LEAF, EXTRA>(s_acc + ((size_t)warp * nb + b) * NA, lane, su, sl, cu, cl);
+        if (LEAF) warp_commit<LEAF, EXTRA>(s_acc + ((size_t)warp * nb + b) * NA, lane, su, st - su, cu, ct - cu);
+        else warp_commit<LEAF, EXTRA>(s_acc + ((size_t)warp * nb + b) * NA, lane, st, 0, ct, 0);
     }
+    if (nan_acc != nan_acc)   // AnalysisError::UndefinedPosition: a NaN coordinate reached the engine
+        raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | (unsigned)m0);
     if (EXTRA && o.normal_used) {
 #pragma unroll
         for (int j = 0; j < MPT; j++)
@@ -830,7 +851,8 @@ __global__ void __launch_bounds__(kBlock, 4) global_leaflet_pipeline_kernel(Devi
             const BondItem bi = s_bonds[b];
             Vec<MPT> x1, y1, z1, x2, y2, z2;
             if (active) {
-                x1.load(base + bi.a_off); y1.load(base + bi.a_off + mpad); z1.load(base + bi.a_off + 2 * mpad);
+                const int a_off = bi.a_off & ~3;
+                x1.load(base + a_off); y1.load(base + a_off + mpad); z1.load(base + a_off + 2 * mpad);
                 x2.load(base + bi.b_off); y2.load(base + bi.b_off + mpad); z2.load(base + bi.b_off + 2 * mpad);
             }
             int su = 0, sl = 0;

@@ -50,6 +50,13 @@ __device__ __forceinline__ float min_image(float d, float L, float half) {
     return min_image_slow(d, L, half);
 }
 
+// Same result with ONE compare on the hot path: |d| <= guard (guard = 0.99 L/2, precomputed per
+// frame) implies 0 <= t and u < 2L, i.e. the exact fast path; everything else takes the literal path.
+__device__ __forceinline__ float min_image_g(float d, float L, float half, float guard) {
+    if (fabsf(d) <= guard) return __fsub_rn(__fsub_rn(__fadd_rn(__fadd_rn(d, half), L), L), half);
+    return min_image_slow(d, L, half);
+}
+
 // Vector3D::wrap per component (call site pbc.rs:388-390): c % L, + L if negative.
 __device__ __forceinline__ float wrap1(float c, float L) {
     float w = fmod_near(c, L);
