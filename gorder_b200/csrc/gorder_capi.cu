@@ -105,9 +105,15 @@ struct GorderHandle {
     long long normals_collect_cap = 0;
 
     // centres
-    float *d_est = nullptr, *d_center = nullptr;   // [max_batch*3]
-    double *d_partial = nullptr;                   // [max_batch][kCenterBlocks][2]
-    unsigned *d_ticket = nullptr;                  // [max_batch]
+    // per staging slot, so that the centre passes of batch k+1 (pre stream) overlap the bond kernel of batch k
+    float *d_est2[2] = {nullptr, nullptr}, *d_center2[2] = {nullptr, nullptr};   // [max_batch*3]
+    double *d_partial2[2] = {nullptr, nullptr};    // [max_batch][kCenterBlocks][2]
+    unsigned *d_ticket2[2] = {nullptr, nullptr};   // [max_batch]
+    float *d_est = nullptr, *d_center = nullptr;   // current slot's buffers
+    double *d_partial = nullptr;
+    unsigned *d_ticket = nullptr;
+    cudaStream_t stream_pre = nullptr;             // frame setup + centre reduction of the next batch
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr};
     struct SegList { Seg *d = nullptr; int n = 0; };
     SegList seg_membrane[3], seg_geom[3];          // per axis
 
@@ -232,7 +238,7 @@ size_t accum_smem(const GorderHandle *h) {
     return (items + (size_t)kWarps * max_orders * na + 2) * sizeof(int);
 }
 
-// runs of contiguous native floats of component `axis` of a group, split into pieces of <= 1024
+// runs of contiguous native floats of component `axis` of a group, split into pieces of <= 4096
 int build_segs(GorderHandle *h, GorderHandle::SegList *out, const int32_t *idx, int n, int axis) {
     std::vector<long long> offs(n);
     for (int i = 0; i < n; i++) offs[i] = (long long)h->slot_off[idx[i]] + (long long)axis * h->slot_cs[idx[i]];
@@ -240,7 +246,7 @@ int build_segs(GorderHandle *h, GorderHandle::SegList *out, const int32_t *idx, 
     std::vector<Seg> segs;
     for (int i = 0; i < n;) {
         int j = i + 1;
-        while (j < n && offs[j] == offs[j - 1] + 1 && j - i < 1024) j++;
+        while (j < n && offs[j] == offs[j - 1] + 1 && j - i < 4096) j++;
         segs.push_back(Seg{(int)offs[i], j - i});
         i = j;
     }
@@ -249,17 +255,25 @@ int build_segs(GorderHandle *h, GorderHandle::SegList *out, const int32_t *idx, 
 }
 
 // centre of a group along the axes in `axis_mask` for the frames in d_list[0..n_list) -> h->d_center[3*i + axis]
-int run_group_center(GorderHandle *h, const GorderHandle::SegList *segs, int n_group, int axis_mask, const float *planes, const FrameAux *aux,
-                     const int *d_list, int n_list) {
+int run_group_center(GorderHandle *h, cudaStream_t st, const GorderHandle::SegList *segs, int n_group, int axis_mask, const float *planes,
+                     const FrameAux *aux, const int *d_list, int n_list) {
     const bool pbc = h->s.handle_pbc != 0;
+    // sub-batches whose axis planes fit comfortably in L2 (126 MB): pass 1 re-reads what pass 0 just streamed
+    long long sub = std::max<long long>(1, (48ll << 20) / std::max<long long>(1, (long long)n_group * 4));
+    if (const char *e = getenv("GORDER_CENTER_SUB")) { int q = atoi(e); if (q >= 1) sub = q; }
     for (int axis = 0; axis < 3; axis++) {
         if (!(axis_mask & (1 << axis))) continue;
-        const int nblk = std::max(1, std::min(kCenterBlocks, segs[axis].n));
-        dim3 grid(nblk, n_list);
-        for (int pass = 0; pass < (pbc ? 2 : 1); pass++) {
-            center_axis_kernel<<<grid, 256, 0, h->stream>>>(h->view, segs[axis].d, segs[axis].n, n_group, axis, planes, aux, d_list, h->d_est,
-                                                            h->d_center, h->d_partial, h->d_ticket, pass);
-            h->n_launches++;
+        int want = kCenterBlocks;
+        if (const char *e = getenv("GORDER_CENTER_BLOCKS")) { int q = atoi(e); if (q >= 1 && q <= kCenterBlocks) want = q; }
+        const int nblk = std::max(1, std::min(want, segs[axis].n));
+        for (int l0 = 0; l0 < n_list; l0 += (int)sub) {
+            const int nl = std::min<int>((int)sub, n_list - l0);
+            dim3 grid(nblk, nl);
+            for (int pass = 0; pass < (pbc ? 2 : 1); pass++) {
+                center_axis_kernel<<<grid, 256, 0, st>>>(h->view, segs[axis].d, segs[axis].n, n_group, axis, planes, aux, d_list + l0, h->d_est + 3 * l0,
+                                                         h->d_center + 3 * l0, h->d_partial + (size_t)l0 * kCenterBlocks * 2, h->d_ticket + l0, pass);
+                h->n_launches++;
+            }
         }
     }
     CK(cudaGetLastError());
@@ -304,7 +318,8 @@ int grow_collect(GorderHandle *h, T **buf, long long *cap, long long used_rows, 
 }
 
 // Analyse one batch whose frames are resident on the device in the native layout.
-int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, const long long *frame_index, int nf, int slot) {
+int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, const long long *frame_index, int nf, int slot,
+                  bool planes_on_main) {
     const GorderSetup &s = h->s;
     FrameAux *ha = h->h_aux[slot];
     int *list_assign = h->h_list[slot], *list_all = h->h_list[slot] + h->max_batch;
@@ -335,30 +350,45 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     }
     FrameAux *da = h->d_aux[slot];
     int *dl_assign = h->d_list[slot], *dl_all = h->d_list[slot] + h->max_batch;
-    CK(cudaMemcpyAsync(da, ha, sizeof(FrameAux) * nf, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_list[slot], h->h_list[slot], sizeof(int) * (h->max_batch + nf), cudaMemcpyHostToDevice, h->stream));
+    h->d_est = h->d_est2[slot]; h->d_center = h->d_center2[slot]; h->d_partial = h->d_partial2[slot]; h->d_ticket = h->d_ticket2[slot];
+    const bool use_pipe = h->pipe_ok && n_assign == nf;
+    // Global leaflets on every analysed frame (AA/CG): the bond kernel classifies inline, no table pass
+    const bool inline_leaf = !use_pipe && !h->ua && s.leaflet_mode == GORDER_LEAFLET_GLOBAL && s.leaflet_freq_kind == GORDER_FREQ_EVERY &&
+                             s.leaflet_freq <= std::max(1, s.step) && n_assign == nf && !getenv("GORDER_NO_INLINE_LEAFLETS");
+    // Frames already resident on the device: frame setup and the centre passes of this batch go to the
+    // pre stream and overlap the bond kernel of the previous batch (both are latency-, not HBM-bound).
+    const bool overlap = inline_leaf && !planes_on_main && !h->nvec && !getenv("GORDER_NO_OVERLAP");
+    cudaStream_t sp = overlap ? h->stream_pre : h->stream;
+    CK(cudaMemcpyAsync(da, ha, sizeof(FrameAux) * nf, cudaMemcpyHostToDevice, sp));
+    CK(cudaMemcpyAsync(h->d_list[slot], h->h_list[slot], sizeof(int) * (h->max_batch + nf), cudaMemcpyHostToDevice, sp));
 
-    frame_setup_kernel<<<(nf + 63) / 64, 64, 0, h->stream>>>(h->view, da, d_box, nf, 0);
+    frame_setup_kernel<<<(nf + 63) / 64, 64, 0, sp>>>(h->view, da, d_box, nf, 0);
     h->n_launches++;
     if (s.geom_kind != GORDER_GEOM_NONE) {
         if (s.geom_ref_kind == GORDER_GEOMREF_SELECTION) {
-            int rc = run_group_center(h, h->seg_geom, h->s.n_geom_ref, 7, d_planes, da, dl_all, nf);
+            int rc = run_group_center(h, sp, h->seg_geom, h->s.n_geom_ref, 7, d_planes, da, dl_all, nf);
             if (rc) return rc;
-            store_center_kernel<<<(nf + 63) / 64, 64, 0, h->stream>>>(da, dl_all, nf, h->d_center);
+            store_center_kernel<<<(nf + 63) / 64, 64, 0, sp>>>(da, dl_all, nf, h->d_center);
             h->n_launches++;
         }
-        frame_setup_kernel<<<(nf + 63) / 64, 64, 0, h->stream>>>(h->view, da, d_box, nf, 1);
+        frame_setup_kernel<<<(nf + 63) / 64, 64, 0, sp>>>(h->view, da, d_box, nf, 1);
         h->n_launches++;
     }
-    const bool use_pipe = h->pipe_ok && n_assign == nf;
-    if (h->leaf && n_assign > 0 && !use_pipe) {
+    if (inline_leaf) {
+        int rc = run_group_center(h, sp, h->seg_membrane, h->s.n_membrane, 1 << s.leaflet_axis, d_planes, da, dl_assign, n_assign);
+        if (rc) return rc;
+    } else if (h->leaf && n_assign > 0 && !use_pipe) {
         if (s.leaflet_mode == GORDER_LEAFLET_GLOBAL) {
-            int rc = run_group_center(h, h->seg_membrane, h->s.n_membrane, 1 << s.leaflet_axis, d_planes, da, dl_assign, n_assign);
+            int rc = run_group_center(h, sp, h->seg_membrane, h->s.n_membrane, 1 << s.leaflet_axis, d_planes, da, dl_assign, n_assign);
             if (rc) return rc;
         }
         dim3 grid((h->n_molpad + 255) / 256, n_assign);
-        leaflet_assign_kernel<<<grid, 256, 0, h->stream>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_molpad_type, h->d_leaf_rows);
+        leaflet_assign_kernel<<<grid, 256, 0, sp>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_molpad_type, h->d_leaf_rows);
         h->n_launches++;
+    }
+    if (overlap) {
+        CK(cudaEventRecord(h->ev_pre[slot], sp));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_pre[slot], 0));
     }
     if (h->nvec) {
         if (s.normal_mode == GORDER_NORMAL_DYNAMIC) {
@@ -380,6 +410,8 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         CK(cudaMemsetAsync(h->d_bsum, 0, 2 * (size_t)h->max_batch * row * sizeof(long long), h->stream));
     }
     AccumOut o;
+    o.inline_center = inline_leaf ? h->d_center : nullptr;
+    o.leaf_out = (inline_leaf && s.collect_leaflets) ? h->d_leaf_rows : nullptr;
     o.bsum = h->d_bsum; o.bcnt = h->d_bcnt; o.map_sum = h->d_map_sum; o.map_cnt = h->d_map_cnt; o.normal_used = h->d_normal_used;
     dim3 grid(h->n_chunks, nf);
     const size_t smem = accum_smem(h);
@@ -421,7 +453,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     if (h->leaf && n_assign > 0 && s.collect_leaflets) {
         int rc = grow_collect(h, &h->d_leaf_collect, &h->leaf_collect_cap, h->n_leaf_collected, h->n_leaf_collected + n_assign, (size_t)h->n_molpad);
         if (rc) return rc;
-        if (use_pipe) {   // the pipeline writes row 1 + f for every frame f
+        if (use_pipe || inline_leaf) {   // rows 1 + f were written by the accumulation kernel for every frame f
             CK(cudaMemcpyAsync(h->d_leaf_collect + (size_t)h->n_leaf_collected * h->n_molpad, h->d_leaf_rows + h->n_molpad,
                                (size_t)nf * h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
         } else {
@@ -431,7 +463,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         for (int a = 0; a < n_assign; a++) h->leaf_frame_index.push_back(frame_index[list_assign[a]]);
         h->n_leaf_collected += n_assign;
     }
-    if (h->leaf && n_assign > 0 && !use_pipe) {   // keep the newest table for the frames of the next batch
+    if (h->leaf && n_assign > 0 && !use_pipe && !inline_leaf) {   // keep the newest table for the frames of the next batch
         CK(cudaMemcpyAsync(h->d_leaf_rows, h->d_leaf_rows + (size_t)n_assign * h->n_molpad, h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
         h->have_leaflets = true;
         h->cur_leaflet_frame = frame_index[list_assign[n_assign - 1]];
@@ -481,6 +513,8 @@ void gorder_gpu_destroy(GorderHandle *h) {
     for (auto &e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->stream_pre) { cudaStreamSynchronize(h->stream_pre); cudaStreamDestroy(h->stream_pre); }
+    for (int i = 0; i < 2; i++) if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
     delete h;
 }
 
@@ -716,10 +750,19 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         if ((rc = dev_alloc(h, &h->d_normal_npoints, B * (size_t)h->n_molpad, true))) return rc;
         if (s->collect_normals && s->geom_kind != GORDER_GEOM_NONE && !ua) { if ((rc = dev_alloc(h, &h->d_normal_used, B * (size_t)h->n_molpad, true))) return rc; }
     }
-    if ((rc = dev_alloc(h, &h->d_est, B * 3))) return rc;
-    if ((rc = dev_alloc(h, &h->d_center, B * 3))) return rc;
-    if ((rc = dev_alloc(h, &h->d_partial, B * kCenterBlocks * 2))) return rc;
-    if ((rc = dev_alloc(h, &h->d_ticket, B, true))) return rc;
+    for (int i = 0; i < 2; i++) {
+        if ((rc = dev_alloc(h, &h->d_est2[i], B * 3))) return rc;
+        if ((rc = dev_alloc(h, &h->d_center2[i], B * 3))) return rc;
+        if ((rc = dev_alloc(h, &h->d_partial2[i], B * kCenterBlocks * 2))) return rc;
+        if ((rc = dev_alloc(h, &h->d_ticket2[i], B, true))) return rc;
+        CK(cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
+    }
+    h->d_est = h->d_est2[0]; h->d_center = h->d_center2[0]; h->d_partial = h->d_partial2[0]; h->d_ticket = h->d_ticket2[0];
+    {   // higher priority: the small centre kernels of the next batch must not queue behind the bond kernel's CTAs
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&h->stream_pre, cudaStreamNonBlocking, hi));
+    }
 
     // persistent pipeline: AA/CG, static normal, PBC, Global leaflets on every analysed frame, no geometry / maps
     h->pipe_ok = !ua && !h->nvec && !h->extra && s->handle_pbc && s->leaflet_mode == GORDER_LEAFLET_GLOBAL &&
@@ -728,7 +771,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     //  latency / issue bound, not HBM bound; see profiles/README.md)
     if (h->pipe_ok) {
         const int nseg = h->seg_membrane[s->leaflet_axis].n;
-        h->pipe_segs_per_item = 16;
+        h->pipe_segs_per_item = 4;
         h->pipe_p_items = std::max(1, (nseg + h->pipe_segs_per_item - 1) / h->pipe_segs_per_item);
         if ((rc = dev_alloc(h, &h->d_pipe_partial0, B * h->pipe_p_items * 2))) return rc;
         if ((rc = dev_alloc(h, &h->d_pipe_partial1, B * h->pipe_p_items))) return rc;
@@ -831,7 +874,7 @@ int gorder_gpu_submit(GorderHandle *h, const float *xyz, const float *box, const
         CK(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
         if (int rc = launch_relayout(h, h->d_xyz[slot], h->d_planes[slot], nf)) return rc;
-        if (int rc = process_batch(h, h->d_planes[slot], h->d_box[slot], (const long long *)frame_index + f0, nf, slot)) return rc;
+        if (int rc = process_batch(h, h->d_planes[slot], h->d_box[slot], (const long long *)frame_index + f0, nf, slot, true)) return rc;
         CK(cudaEventRecord(h->ev_stage_free[slot], h->stream));
         CK(cudaEventSynchronize(h->ev_h2d[slot]));   // the caller's buffers may be reused from here on
     }
@@ -847,7 +890,7 @@ int gorder_gpu_submit_device(GorderHandle *h, const float *d_xyz, const float *d
         int slot;
         if (int rc = begin_slot(h, &slot)) return rc;
         if (int rc = launch_relayout(h, d_xyz + (size_t)f0 * fstride, h->d_planes[slot], nf)) return rc;
-        if (int rc = process_batch(h, h->d_planes[slot], d_box ? d_box + 3 * (size_t)f0 : nullptr, (const long long *)frame_index + f0, nf, slot)) return rc;
+        if (int rc = process_batch(h, h->d_planes[slot], d_box ? d_box + 3 * (size_t)f0 : nullptr, (const long long *)frame_index + f0, nf, slot, true)) return rc;
         CK(cudaEventRecord(h->ev_stage_free[slot], h->stream));
     }
     return GORDER_OK;
@@ -873,7 +916,7 @@ int gorder_gpu_submit_native(GorderHandle *h, const float *planes_host, const fl
         if (h->s.handle_pbc) CK(cudaMemcpyAsync(h->d_box[slot], box + 3 * (size_t)f0, (size_t)nf * 3 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
-        if (int rc = process_batch(h, h->d_planes[slot], h->d_box[slot], (const long long *)frame_index + f0, nf, slot)) return rc;
+        if (int rc = process_batch(h, h->d_planes[slot], h->d_box[slot], (const long long *)frame_index + f0, nf, slot, true)) return rc;
         CK(cudaEventRecord(h->ev_stage_free[slot], h->stream));
         CK(cudaEventSynchronize(h->ev_h2d[slot]));
     }
@@ -888,7 +931,7 @@ int gorder_gpu_submit_native_device(GorderHandle *h, const float *d_planes, cons
         const int nf = std::min(h->max_batch, n_frames - f0);
         int slot;
         if (int rc = begin_slot(h, &slot)) return rc;
-        if (int rc = process_batch(h, d_planes + (size_t)f0 * fstride, d_box ? d_box + 3 * (size_t)f0 : nullptr, (const long long *)frame_index + f0, nf, slot)) return rc;
+        if (int rc = process_batch(h, d_planes + (size_t)f0 * fstride, d_box ? d_box + 3 * (size_t)f0 : nullptr, (const long long *)frame_index + f0, nf, slot, false)) return rc;
         CK(cudaEventRecord(h->ev_stage_free[slot], h->stream));
     }
     return GORDER_OK;
@@ -911,6 +954,7 @@ int gorder_gpu_sync(GorderHandle *h) {
     if (h->err_code) return h->err_code;
     cudaSetDevice(h->device);
     CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaStreamSynchronize(h->stream_pre));
     return poll_device_error(h);
 }
 

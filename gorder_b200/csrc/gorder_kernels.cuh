@@ -209,13 +209,17 @@ __global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Se
     for (int sg = blockIdx.x; sg < n_segs; sg += gridDim.x) {
         const Seg sgm = segs[sg];
         const float *src = fr + sgm.off;
-        if ((((size_t)src) & 15) == 0) {   // 16-byte aligned run: 128-bit loads
+        if ((((size_t)src) & 15) == 0) {   // 16-byte aligned run: 128-bit loads, 4 in flight per thread
             const int n4 = sgm.len >> 2;
-            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-                const float4 q = __ldg(reinterpret_cast<const float4 *>(src) + i);
-                add(q.x); add(q.y); add(q.z); add(q.w);
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            int i = threadIdx.x;
+            for (; i + 3 * (int)blockDim.x < n4; i += 4 * blockDim.x) {
+                const float4 q0 = __ldg(s4 + i), q1 = __ldg(s4 + i + blockDim.x), q2 = __ldg(s4 + i + 2 * blockDim.x), q3 = __ldg(s4 + i + 3 * blockDim.x);
+                add(q0.x); add(q0.y); add(q0.z); add(q0.w); add(q1.x); add(q1.y); add(q1.z); add(q1.w);
+                add(q2.x); add(q2.y); add(q2.z); add(q2.w); add(q3.x); add(q3.y); add(q3.z); add(q3.w);
             }
-            for (int i = (n4 << 2) + threadIdx.x; i < sgm.len; i += blockDim.x) add(__ldg(src + i));
+            for (; i < n4; i += blockDim.x) { const float4 q = __ldg(s4 + i); add(q.x); add(q.y); add(q.z); add(q.w); }
+            for (int k = (n4 << 2) + threadIdx.x; k < sgm.len; k += blockDim.x) add(__ldg(src + k));
         } else {
             for (int i = threadIdx.x; i < sgm.len; i += blockDim.x) add(__ldg(src + i));
         }
@@ -476,6 +480,11 @@ __global__ void __launch_bounds__(256) mask_normals_kernel(int n_molpad, const u
 // accumulation helpers shared by K1 and K2
 // ---------------------------------------------------------------------------------------------
 struct AccumOut {
+    // Global leaflets assigned on every frame: the accumulation kernel classifies its own molecules
+    // from the head coordinate and the frame's membrane centre (common_identify_leaflet,
+    // leaflets.rs:711-732) instead of reading a table; it writes the table rows only for export.
+    const float *inline_center;     // [F][3] centre of frame f, or nullptr (table path)
+    unsigned char *leaf_out;        // rows [(1 + f)][n_molpad] when the tables are collected, else nullptr
     long long *bsum;                // [rows][n_slots][3]
     unsigned long long *bcnt;       // [rows][n_slots][3]
     long long *map_sum;             // [n_slots][3][n_bins]
@@ -588,6 +597,7 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
     const float h0 = ax.half[c0], h1 = ax.half[c1], h2 = ax.half[c2];
     const float g0 = 0.99f * h0, g1 = 0.99f * h1, g2 = 0.99f * h2;
     const Box bx = load_box(ax);
+    const float *base_mol = planes + (size_t)f * v.frame_floats + td.plane_base + m0;
     bool valid[MPT];
     int upmask[MPT];
     f3 nrm[MPT];
@@ -596,7 +606,17 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
     for (int j = 0; j < MPT; j++) {
         valid[j] = active && (m0 + j < td.n_mol);
         bool up = false;
-        if (LEAF && valid[j]) up = leaf_rows[(size_t)ax.leaf_row * v.n_molpad + td.molpad0 + m0 + j] == GORDER_UPPER;
+        if (LEAF && valid[j]) {
+            if (o.inline_center) {
+                const int la = v.leaflet_axis;
+                const float c = o.inline_center[3 * f + la];
+                if (c != c) raise_error(v, GORDER_ERR_INVALID_GLOBAL_CENTER, ax.frame_index);
+                const float hd = __ldg(base_mol + td.head_off + la * mpad + j);
+                up = distance_1d(hd, c, ax.L[la], ax.half[la], PBC) >= 0.0f;
+                if (v.leaflet_flip) up = !up;
+                if (o.leaf_out) o.leaf_out[(size_t)(1 + f) * v.n_molpad + td.molpad0 + m0 + j] = up ? GORDER_UPPER : GORDER_LOWER;
+            } else up = leaf_rows[(size_t)ax.leaf_row * v.n_molpad + td.molpad0 + m0 + j] == GORDER_UPPER;
+        }
         upmask[j] = up ? -1 : 0;
         if (NVEC) {
             nrm[j] = mk3(0.f, 0.f, 1.f);
