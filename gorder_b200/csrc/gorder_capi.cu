@@ -104,6 +104,11 @@ struct GorderHandle {
     unsigned char *d_used_collect = nullptr;
     long long normals_collect_cap = 0;
 
+    // cell list of the normal heads (K4)
+    bool use_cells = false;
+    int cells_cap = 0;
+    int *d_head_cell = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_sorted = nullptr;
+
     // centres
     // per staging slot, so that the centre passes of batch k+1 (pre stream) overlap the bond kernel of batch k
     float *d_est2[2] = {nullptr, nullptr}, *d_center2[2] = {nullptr, nullptr};   // [max_batch*3]
@@ -391,7 +396,18 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         CK(cudaStreamWaitEvent(h->stream, h->ev_pre[slot], 0));
     }
     if (h->nvec) {
-        if (s.normal_mode == GORDER_NORMAL_DYNAMIC) {
+        if (s.normal_mode == GORDER_NORMAL_DYNAMIC && h->use_cells) {
+            const int nh = s.n_normal_heads;
+            CK(cudaMemsetAsync(h->d_cell_count, 0, (size_t)nf * h->cells_cap * sizeof(int), h->stream));
+            dim3 gh((nh + 255) / 256, nf);
+            cell_count_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, da, h->d_head_cell, h->d_cell_count, h->cells_cap);
+            cell_scan_kernel<<<nf, 1024, 0, h->stream>>>(h->view, da, h->d_cell_count, h->d_cell_start, h->cells_cap);
+            cell_fill_kernel<<<gh, 256, 0, h->stream>>>(h->view, h->d_head_cell, h->d_cell_count, h->d_cell_start, h->d_cell_sorted, h->cells_cap);
+            dim3 grid((h->n_molpad + 127) / 128, nf);
+            dynamic_normal_cell_kernel<<<grid, 128, 0, h->stream>>>(h->view, d_planes, da, h->d_molpad_type, h->d_cell_start, h->d_cell_sorted,
+                                                                   h->cells_cap, h->d_normals, h->d_normal_npoints);
+            h->n_launches += 3;
+        } else if (s.normal_mode == GORDER_NORMAL_DYNAMIC) {
             dim3 grid((h->n_molpad + 127) / 128, nf);
             dynamic_normal_kernel<<<grid, 128, 0, h->stream>>>(h->view, d_planes, da, h->d_molpad_type, h->d_normals, h->d_normal_npoints);
         } else {
@@ -654,7 +670,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     // ---- batch size ------------------------------------------------------------------------------
     const size_t frame_bytes = (size_t)h->frame_floats * sizeof(float);
     long long mb = s->max_batch_frames > 0 ? s->max_batch_frames : (long long)((512ull << 20) / std::max<size_t>(frame_bytes, 1));
-    mb = std::max<long long>(1, std::min<long long>(mb, 512));
+    mb = std::max<long long>(1, std::min<long long>(mb, s->normal_mode == GORDER_NORMAL_DYNAMIC ? 32 : 512));
     h->max_batch = (int)mb;
 
     // ---- device tables ---------------------------------------------------------------------------
@@ -745,6 +761,19 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     // planes may contain padding that is never written: keep it finite
     for (int i = 0; i < 2; i++) CK(cudaMemset(h->d_planes[i], 0, B * (size_t)h->frame_floats * sizeof(float)));
     if (h->leaf) { if ((rc = dev_alloc(h, &h->d_leaf_rows, (1 + B) * (size_t)h->n_molpad, true))) return rc; }
+    if (s->normal_mode == GORDER_NORMAL_DYNAMIC && s->handle_pbc) {
+        // cell list for the neighbour search unless the head group is small (brute force keeps the oracle's summation order)
+        int min_heads = 2048;
+        if (const char *e = getenv("GORDER_CELL_MIN_HEADS")) min_heads = atoi(e);
+        h->use_cells = s->n_normal_heads >= min_heads;
+        if (h->use_cells) {
+            h->cells_cap = kCellMaxDim * kCellMaxDim * kCellMaxDim;
+            if ((rc = dev_alloc(h, &h->d_head_cell, B * (size_t)s->n_normal_heads))) return rc;
+            if ((rc = dev_alloc(h, &h->d_cell_sorted, B * (size_t)s->n_normal_heads))) return rc;
+            if ((rc = dev_alloc(h, &h->d_cell_count, B * (size_t)h->cells_cap))) return rc;
+            if ((rc = dev_alloc(h, &h->d_cell_start, B * ((size_t)h->cells_cap + 1)))) return rc;
+        }
+    }
     if (h->nvec) {
         if ((rc = dev_alloc(h, &h->d_normals, B * 3 * (size_t)h->n_molpad))) return rc;
         if ((rc = dev_alloc(h, &h->d_normal_npoints, B * (size_t)h->n_molpad, true))) return rc;

@@ -444,6 +444,149 @@ __global__ void __launch_bounds__(128) dynamic_normal_kernel(DeviceView v, const
     nx[0] = nrm.x; nx[v.n_molpad] = nrm.y; nx[2 * (size_t)v.n_molpad] = nrm.z;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K4 with a cell list (PBC): the reference builds a CellGrid over the NormalHeads group with cell
+// edge >= radius and scans the 27 neighbouring cells (pbc.rs:327-339); so does this.  Per frame:
+//   cell_count_kernel  wrap every head into the box, bin it, count                 (1 thread / head)
+//   cell_scan_kernel   exclusive scan of the counts -> cell_start                  (1 CTA / frame)
+//   cell_fill_kernel   scatter head ids into their cell's range
+//   dynamic_normal_cell_kernel  per lipid: gather heads within `radius` from the 3x3x3 block,
+//                      centroid + scatter matrix relative to the reference head (f64 sums: the
+//                      gather order inside a cell is arbitrary, f64 makes the result independent of
+//                      it to ~1e-13, i.e. bit-stable after rounding to f32), Jacobi smallest eigenvector.
+// Grid: n_k = clamp(floor(L_k / radius), 1, kCellMaxDim) cells along k (cell edge L_k / n_k >= radius).
+// ---------------------------------------------------------------------------------------------
+constexpr int kCellMaxDim = 40;
+
+__device__ __forceinline__ void cell_dims(const FrameAux &a, float radius, int (&n)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int q = (int)floorf(a.L[k] / radius);
+        n[k] = min(max(q, 1), kCellMaxDim);
+    }
+}
+__device__ __forceinline__ int cell_coord(float x, float L, int n) {
+    const float w = (L > 0.0f) ? wrap1(x, L) : 0.0f;
+    return min(max((int)(w * (float)n / L), 0), n - 1);
+}
+
+__global__ void __launch_bounds__(256) cell_count_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                         int *__restrict__ head_cell, int *__restrict__ cell_count, int cells_cap) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.normal_heads.n) return;
+    const FrameAux &a = aux[f];
+    int n[3];
+    cell_dims(a, v.dynamic_radius, n);
+    const float *fr = planes + (size_t)f * v.frame_floats;
+    const int off = v.normal_heads.off[i], cs = v.normal_heads.cs[i];
+    const int cx = cell_coord(fr[off], a.L[0], n[0]), cy = cell_coord(fr[off + cs], a.L[1], n[1]), cz = cell_coord(fr[off + 2 * (size_t)cs], a.L[2], n[2]);
+    const int c = (cx * n[1] + cy) * n[2] + cz;
+    head_cell[(size_t)f * v.normal_heads.n + i] = c;
+    atomicAdd(&cell_count[(size_t)f * cells_cap + c], 1);
+}
+
+__global__ void __launch_bounds__(1024) cell_scan_kernel(DeviceView v, const FrameAux *__restrict__ aux, int *__restrict__ cell_count,
+                                                         int *__restrict__ cell_start, int cells_cap) {
+    const int f = blockIdx.x;
+    int n[3];
+    cell_dims(aux[f], v.dynamic_radius, n);
+    const int nc = n[0] * n[1] * n[2];
+    int *cnt = cell_count + (size_t)f * cells_cap, *st = cell_start + (size_t)f * (cells_cap + 1);
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nc; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int x = i < nc ? cnt[i] : 0;
+        int incl = x;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - x;
+        if (i < nc) { st[i] = excl; cnt[i] = 0; }   // the counts become the fill cursors
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st[nc] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) cell_fill_kernel(DeviceView v, const int *__restrict__ head_cell, int *__restrict__ cell_count,
+                                                        const int *__restrict__ cell_start, int *__restrict__ sorted, int cells_cap) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.normal_heads.n) return;
+    const int c = head_cell[(size_t)f * v.normal_heads.n + i];
+    const int pos = cell_start[(size_t)f * (cells_cap + 1) + c] + atomicAdd(&cell_count[(size_t)f * cells_cap + c], 1);
+    sorted[(size_t)f * v.normal_heads.n + pos] = i;
+}
+
+__global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                                  const int *__restrict__ molpad_type, const int *__restrict__ cell_start,
+                                                                  const int *__restrict__ sorted, int cells_cap, float *__restrict__ normals,
+                                                                  int *__restrict__ normal_npoints) {
+    const int f = blockIdx.y;
+    const int mp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mp >= v.n_molpad) return;
+    float *nx = normals + ((size_t)f * 3) * v.n_molpad + mp;
+    const int t = molpad_type[mp];
+    const TypeDesc &td = v.types[t];
+    const int m = mp - td.molpad0;
+    if (m >= td.n_mol || td.nhead_off < 0) { nx[0] = CUDART_NAN_F; nx[v.n_molpad] = CUDART_NAN_F; nx[2 * (size_t)v.n_molpad] = CUDART_NAN_F; return; }
+    const FrameAux &a = aux[f];
+    const Box bx = load_box(a);
+    int n[3];
+    cell_dims(a, v.dynamic_radius, n);
+    const float *frame0 = planes + (size_t)f * v.frame_floats;
+    const float *fr = frame0 + td.plane_base + m;
+    const f3 ref = mk3(fr[td.nhead_off], fr[td.nhead_off + td.mpad], fr[td.nhead_off + 2 * td.mpad]);
+    const int c0[3] = {cell_coord(ref.x, a.L[0], n[0]), cell_coord(ref.y, a.L[1], n[1]), cell_coord(ref.z, a.L[2], n[2])};
+    const int *st = cell_start + (size_t)f * (cells_cap + 1);
+    const int *srt = sorted + (size_t)f * v.normal_heads.n;
+    int cnt = 0;
+    double sx = 0, sy = 0, sz = 0, xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
+    // with fewer than 3 cells along an axis the +-1 neighbours alias: visit every cell of that axis once
+    const int lo0 = n[0] >= 3 ? -1 : 0, hi0 = n[0] >= 3 ? 1 : n[0] - 1;
+    const int lo1 = n[1] >= 3 ? -1 : 0, hi1 = n[1] >= 3 ? 1 : n[1] - 1;
+    const int lo2 = n[2] >= 3 ? -1 : 0, hi2 = n[2] >= 3 ? 1 : n[2] - 1;
+    for (int dx = lo0; dx <= hi0; dx++) {
+        const int cx = n[0] >= 3 ? (c0[0] + dx + n[0]) % n[0] : dx;
+        for (int dy = lo1; dy <= hi1; dy++) {
+            const int cy = n[1] >= 3 ? (c0[1] + dy + n[1]) % n[1] : dy;
+            for (int dz = lo2; dz <= hi2; dz++) {
+                const int cz = n[2] >= 3 ? (c0[2] + dz + n[2]) % n[2] : dz;
+                const int c = (cx * n[1] + cy) * n[2] + cz;
+                for (int k = st[c]; k < st[c + 1]; k++) {
+                    const int i = srt[k];
+                    const int off = v.normal_heads.off[i], cs = v.normal_heads.cs[i];
+                    const f3 p = mk3(frame0[off], frame0[off + cs], frame0[off + 2 * (size_t)cs]);
+                    const f3 d = vector_to<true>(ref, p, bx);
+                    if (norm_ref(d) < v.dynamic_radius) {
+                        cnt++;
+                        sx += d.x; sy += d.y; sz += d.z;
+                        xx += (double)d.x * d.x; xy += (double)d.x * d.y; xz += (double)d.x * d.z;
+                        yy += (double)d.y * d.y; yz += (double)d.y * d.z; zz += (double)d.z * d.z;
+                    }
+                }
+            }
+        }
+    }
+    normal_npoints[(size_t)f * v.n_molpad + mp] = cnt;
+    if (cnt < 3) { nx[0] = CUDART_NAN_F; nx[v.n_molpad] = CUDART_NAN_F; nx[2 * (size_t)v.n_molpad] = CUDART_NAN_F; return; }
+    const double inv = 1.0 / cnt, mx = sx * inv, my = sy * inv, mz = sz * inv;
+    f3 nrm;
+    jacobi_smallest((float)(xx - cnt * mx * mx), (float)(xy - cnt * mx * my), (float)(xz - cnt * mx * mz), (float)(yy - cnt * my * my),
+                    (float)(yz - cnt * my * mz), (float)(zz - cnt * mz * mz), nrm);
+    nx[0] = nrm.x; nx[v.n_molpad] = nrm.y; nx[2 * (size_t)v.n_molpad] = nrm.z;
+}
+
 // manual membrane normals (ManualMembraneNormal::get_normal, normal.rs:266-298): copy the row of
 // this frame into the per-frame normal planes; NaN when the frame is not available (the error is
 // raised by the accumulation kernel when the normal is actually used).

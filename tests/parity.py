@@ -25,8 +25,10 @@ def assert_raw_parity(gpu: abi.RawResults, ref: abi.RawResults, setup: abi.Engin
     # fixed-point sums: every sample is within 1 unit of 1e-6 -> means within tol
     mg, mr = mean_order(gpu.sum, gpu.count), mean_order(ref.sum, ref.count)
     np.testing.assert_allclose(mg, mr, atol=tol, rtol=0, equal_nan=True, err_msg=f"{what}: order parameters differ")
-    # and far tighter in aggregate: |sum difference| <= 1 unit per sample
-    assert np.all(np.abs(gpu.sum - ref.sum) <= ref.count.astype(np.int64)), f"{what}: a sample moved by more than 1e-6"
+    # and far tighter in aggregate: |sum difference| <= 1 unit of 1e-6 per sample (static / manual normals: the
+    # bond vectors are bit-identical); PCA normals carry their own f32 noise (different summation order): 3 units
+    per_sample = 3 if setup.normal_mode == abi.NORMAL_DYNAMIC else 1
+    assert np.all(np.abs(gpu.sum - ref.sum) <= per_sample * ref.count.astype(np.int64)), f"{what}: a sample moved by more than {per_sample}e-6"
     if setup.timewise:
         np.testing.assert_array_equal(gpu.tw_frame_index, ref.tw_frame_index)
         np.testing.assert_array_equal(gpu.tw_count, ref.tw_count, err_msg=f"{what}: per-frame counts differ")

@@ -103,6 +103,19 @@ def test_dynamic_normals():
     assert_raw_parity(g, r, s.setup, what="dynamic normals")
 
 
+@pytest.mark.parametrize("n_lipids", [400, 6000])
+def test_dynamic_normals_cell_list(n_lipids, monkeypatch):
+    """Force the cell-list neighbour search (default only for >= 2048 heads) and compare with the oracle's brute force."""
+    monkeypatch.setenv("GORDER_CELL_MIN_HEADS", "0")
+    s = synthetic.s_cg(n_lipids, leaflet_mode=abi.LEAFLET_GLOBAL, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=1.7,
+                       collect_normals=True, geom_kind=abi.GEOM_CYLINDER, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
+                       geom_dims=(5.0, float("-inf"), float("inf")), geom_axis=abi.AXIS_Z)
+    xyz, box, idx = _frames(s, 3)
+    g, r = run_both(s.setup, xyz, box, idx, oracle_threads=8)
+    assert_raw_parity(g, r, s.setup, what="dynamic normals (cell list)")
+    assert np.isnan(r.normals).any() and not np.isnan(r.normals).all()   # lazily computed: NaN outside the cylinder
+
+
 def test_manual_normals_and_leaflets():
     s = synthetic.s_cg(200, leaflet_mode=abi.LEAFLET_MANUAL, normal_mode=abi.NORMAL_MANUAL)
     rng = np.random.default_rng(5)
