@@ -81,16 +81,44 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+WORKLOADS = {
+    # name: (description, default lipids, default frames per step)
+    "cg": ("S-CG: CGOrder Martini bilayer, Global leaflets every frame (BASELINE configs[1])", N_LIPIDS, 64),
+    "aa": ("S-AA-small: AAOrder POPC-like, 64 C-H bond types, static z (BASELINE configs[0] shape)", 256, 2048),
+    "ua": ("S-UA: UAOrder Berger-like, 64 virtual C-H, error blocks (BASELINE configs[2])", 256, 2048),
+    "aa_maps": ("S-AA-large: AAOrder 4096 lipids, Global leaflets, XY order maps 0.1 nm, cylinder r=8 nm (BASELINE configs[3])", 4096, 128),
+    "cg_dyn": ("S-DYN: CGOrder flat bilayer, dynamic PCA normals r=2 nm, Global leaflets (BASELINE configs[4] kernel mix)", 100000, 8),
+}
+
+
 def make_system(args):
     from gorder_b200 import abi, synthetic
-    return synthetic.s_cg(args.lipids, leaflet_mode=abi.LEAFLET_GLOBAL, max_batch_frames=args.frames)
+    w, n, F = args.workload, args.lipids, args.frames
+    if w == "cg":
+        return synthetic.s_cg(n, leaflet_mode=abi.LEAFLET_GLOBAL, max_batch_frames=F)
+    if w == "aa":
+        return synthetic.s_aa(n, n_water=30000 * n // 256, max_batch_frames=F)
+    if w == "ua":
+        return synthetic.s_ua(n, timewise=True, max_batch_frames=F)
+    if w == "aa_maps":
+        s = synthetic.s_aa(n, n_water=0, leaflet_mode=abi.LEAFLET_GLOBAL, map_enabled=True, map_plane=abi.PLANE_XY, map_bin=(0.1, 0.1),
+                           geom_kind=abi.GEOM_CYLINDER, geom_ref_kind=abi.GEOMREF_BOX_CENTER, geom_dims=(8.0, float("-inf"), float("inf")),
+                           geom_axis=abi.AXIS_Z, max_batch_frames=F)
+        s.setup.map_span_x = (0.0, float(s.box[0]))
+        s.setup.map_span_y = (0.0, float(s.box[1]))
+        return s
+    if w == "cg_dyn":
+        return synthetic.s_cg(n, leaflet_mode=abi.LEAFLET_GLOBAL, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0, max_batch_frames=F)
+    raise SystemExit(f"unknown workload {w}")
 
 
 def config(args, s, extra=None):
-    c = {"workload": "S-CG: CGOrder Martini bilayer (BASELINE configs[1])", "lipids": args.lipids, "atoms_per_frame": s.n_atoms,
-         "bond_types": 11, "samples_per_frame": s.setup.samples_per_frame(), "frames_per_step": args.frames,
-         "leaflets": "Global, every frame", "normal": "static z", "pbc": True,
-         "l2_policy": "inputs larger than L2 (frames_per_step x 12 MB per step)", "parallelism": f"frame-sharded x{args.gpus}"}
+    st = s.setup
+    c = {"workload": WORKLOADS[args.workload][0], "lipids": args.lipids, "atoms_per_frame": s.n_atoms,
+         "order_slots": st.n_slots, "samples_per_frame": st.samples_per_frame(), "frames_per_step": args.frames,
+         "leaflets": {0: "none", 1: "Global, every frame"}.get(st.leaflet_mode, str(st.leaflet_mode)),
+         "normal": {0: "static z", 1: "dynamic PCA", 2: "manual"}[st.normal_mode], "pbc": bool(st.handle_pbc),
+         "l2_policy": "inputs larger than L2 (one step streams frames_per_step frames; 126 MB L2)", "parallelism": f"frame-sharded x{args.gpus}"}
     if extra:
         c.update(extra)
     return c
@@ -135,7 +163,7 @@ def run_reference(args):
         o.close()
     dt = time.perf_counter() - t0
     value = args.steps * nf * s.setup.samples_per_frame() / dt
-    sample = f"{nf} frames of the S-CG workload per step, oracle port (oracle/gorder_oracle.c) with {threads} OpenMP threads"
+    sample = f"{nf} frames of the {args.workload} workload per step, oracle port (oracle/gorder_oracle.c) with {threads} OpenMP threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -158,6 +186,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: gorder_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     s = make_system(args)
     s.setup.device = local
@@ -174,11 +203,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
     frame_bytes = eng.frame_floats * 4
+    needed_atoms = int((eng.native_layout()[1] >= 0).sum())
 
     def step(k):
         base = (k * world + rank) * F   # disjoint, strictly increasing frame ranges per rank
         eng.analyze_frames_device(d_planes.data_ptr(), d_box.data_ptr(), F, frame_index=base + np.arange(F, dtype=np.int64), native=True)
 
+    eng.reserve_frames((W + K + 6) * F)
     for k in range(W):
         step(k)
     eng.sync()
@@ -217,9 +248,21 @@ def run_ours(args):
     value = K * F * spf * world / (ms * 1e-3)
     res = eng.finish()
     total_samples = int(res.count[:, 0].sum())
+    # the same kernel timed WITHOUT the overlapped centre kernels of the next batch (explains the in-step number)
+    iso_ms = iso_n = None
+    if rank == 0 and s.setup.leaflet_mode == 1:
+        os.environ["GORDER_NO_OVERLAP"] = "1"
+        eng.profile(True)
+        for k in range(W + K, W + K + 5):
+            step(k)
+        eng.sync()
+        iso_ms, iso_n = eng.profile_read()
+        eng.profile(False)
+        del os.environ["GORDER_NO_OVERLAP"]
 
     # ---- end to end: pinned host AoS frames through gorder_gpu_submit, D2H of the sums every step -------
     eng2 = SystemTopology(s.setup)
+    eng2.reserve_frames((K + 4) * F)
     pin = torch.from_numpy(xyz).pin_memory()
     pin_box = torch.from_numpy(box).pin_memory()
     hx, hb = pin.numpy(), pin_box.numpy()
@@ -250,7 +293,8 @@ def run_ours(args):
     out = None
     if rank == 0:
         peak, peak_src = peaks()
-        launch_bytes = F * s.n_atoms * BYTES_PER_ATOM
+        # algorithmic bytes: every coordinate the path needs, once (12 B x used atoms; S-CG: all 1 000 008 beads)
+        launch_bytes = K * F * needed_atoms * BYTES_PER_ATOM / max(hot_n, 1)   # a step may be several launches
         achieved = launch_bytes / (hot_ms / max(hot_n, 1) * 1e-3) / 1e9 if hot_n else None
         traffic = None
         try:
@@ -279,9 +323,12 @@ def run_ours(args):
                     "entry": "gorder_gpu_submit (pinned host [atom][xyz] frames) + gorder_gpu_finish", "timer": "host wall clock between device syncs"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "kernel": "bond_order_kernel", "launches_timed": hot_n, "avg_launch_ms": hot_ms / max(hot_n, 1),
+                         "traffic": traffic, "kernel": "ua_order_kernel" if s.setup.kind == 2 else "bond_order_kernel", "launches_timed": hot_n, "avg_launch_ms": hot_ms / max(hot_n, 1),
                          "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
-                         "step_share": (hot_ms / ms) if ms else None},
+                         "step_share": (hot_ms / ms) if ms else None,
+                         "note": "in-step duration; with Global leaflets the centre kernels of the NEXT batch run concurrently on a second stream",
+                         "isolated": ({"avg_launch_ms": iso_ms / iso_n, "achieved": launch_bytes / (iso_ms / iso_n * 1e-3) / 1e9,
+                                       "frac": launch_bytes / (iso_ms / iso_n * 1e-3) / 1e9 / peak} if iso_n else None)},
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{cpu_frames} frames of the same workload ({cpu_t:.1f} s), oracle port with {threads} OpenMP threads"},
             "parity": parity, "total_samples_accumulated": total_samples,
@@ -300,12 +347,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=32, help="frames per step (batch)")
-    ap.add_argument("--lipids", type=int, default=N_LIPIDS)
-    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU arms")
+    ap.add_argument("--workload", default="cg", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per step (batch); 0 = workload default")
+    ap.add_argument("--lipids", type=int, default=0, help="0 = workload default")
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU arms; 0 = one per host thread")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    args.lipids = args.lipids or WORKLOADS[args.workload][1]
+    args.frames = args.frames or WORKLOADS[args.workload][2]
+    args.ref_frames = args.ref_frames or max(8, os.cpu_count() or 8)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -12,7 +12,7 @@ _LIB = None
 #: every symbol ``include/gorder_b200.h`` declares
 SYMBOLS = [
     "gorder_gpu_create", "gorder_gpu_submit", "gorder_gpu_submit_device", "gorder_gpu_native_layout",
-    "gorder_gpu_submit_native", "gorder_gpu_submit_native_device", "gorder_gpu_set_leaflets", "gorder_gpu_sync",
+    "gorder_gpu_submit_native", "gorder_gpu_submit_native_device", "gorder_gpu_reserve_frames", "gorder_gpu_set_leaflets", "gorder_gpu_sync",
     "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block", "gorder_gpu_stats",
     "gorder_gpu_read_block", "gorder_gpu_write_block", "gorder_gpu_profile", "gorder_gpu_profile_read",
     "gorder_gpu_stream", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
@@ -36,6 +36,8 @@ def lib() -> C.CDLL:
     L.gorder_gpu_submit_native.argtypes = [vp, vp, vp, vp, i32]
     L.gorder_gpu_submit_native_device.argtypes = [vp, vp, vp, vp, i32]
     L.gorder_gpu_set_leaflets.argtypes = [vp, vp, i64]
+    L.gorder_gpu_reserve_frames.argtypes = [vp, i64]
+    L.gorder_gpu_reserve_frames.restype = C.c_int
     L.gorder_gpu_sync.argtypes = [vp]
     L.gorder_gpu_result_sizes.argtypes = [vp, C.POINTER(abi.CGorderResults)]
     L.gorder_gpu_finish.argtypes = [vp, C.POINTER(abi.CGorderResults)]

@@ -264,7 +264,7 @@ int run_group_center(GorderHandle *h, cudaStream_t st, const GorderHandle::SegLi
                      const FrameAux *aux, const int *d_list, int n_list) {
     const bool pbc = h->s.handle_pbc != 0;
     // sub-batches whose axis planes fit comfortably in L2 (126 MB): pass 1 re-reads what pass 0 just streamed
-    long long sub = std::max<long long>(1, (48ll << 20) / std::max<long long>(1, (long long)n_group * 4));
+    long long sub = n_list;   // (sub-batching for L2 reuse of the axis planes was measured slower: small kernels, see profiles/README.md)
     if (const char *e = getenv("GORDER_CENTER_SUB")) { int q = atoi(e); if (q >= 1) sub = q; }
     for (int axis = 0; axis < 3; axis++) {
         if (!(axis_mask & (1 << axis))) continue;
@@ -578,7 +578,8 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         if (m.n_molecules <= 0 || !m.mol_base) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "molecule type without molecules"); return h->err_code; }
         TypeDesc td{};
         td.n_mol = m.n_molecules;
-        td.mpad = round_up(m.n_molecules, kMolAlign);
+        td.tile = kBlock * (ua ? 1 : h->mpt);   // one tile = the molecules of one CTA
+        td.mpad = round_up(m.n_molecules, td.tile);
         std::vector<int32_t> used;
         if (ua) for (int i = 0; i < m.n_ua_atoms; i++) for (int k = 0; k < 4; k++) { int r = m.ua_rel[4 * i + k]; if (r >= 0) used.push_back(r); else if (k < 3) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "negative UA relative index"); return h->err_code; } }
         else for (int i = 0; i < 2 * m.n_bond_types; i++) { if (bad_rel(m.bond_rel[i])) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "negative bond relative index"); return h->err_code; } used.push_back(m.bond_rel[i]); }
@@ -589,20 +590,23 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         used.erase(std::unique(used.begin(), used.end()), used.end());
         auto u_of = [&](int rel) { return (int)(std::lower_bound(used.begin(), used.end(), rel) - used.begin()); };
         td.plane_base = (int)off;
+        td.cstride = (int)used.size() * td.tile;
+        const long long tile_stride = 3LL * td.cstride;
         for (size_t u = 0; u < used.size(); u++)
             for (int mm = 0; mm < m.n_molecules; mm++) {
                 long long sl = (long long)m.mol_base[mm] + used[u];
                 if (sl < 0 || sl >= s->n_atoms) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "atom slot out of range", sl); return h->err_code; }
                 if (h->slot_off[sl] >= 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "atom belongs to two molecules", sl); return h->err_code; }
-                h->slot_off[sl] = (int)(off + (long long)u * 3 * td.mpad + mm);
-                h->slot_cs[sl] = td.mpad;
+                h->slot_off[sl] = (int)(off + (long long)(mm / td.tile) * tile_stride + (long long)u * td.tile + (mm % td.tile));
+                h->slot_cs[sl] = td.cstride;
             }
-        off += (long long)used.size() * 3 * td.mpad;
+        td.tile_stride = (int)tile_stride;
+        off += (long long)(td.mpad / td.tile) * tile_stride;
         td.slot0 = slot; td.molpad0 = molpad; td.mol0 = mol;
-        td.head_off = m.head_rel >= 0 ? u_of(m.head_rel) * 3 * td.mpad : -1;
-        td.nhead_off = m.normal_head_rel >= 0 ? u_of(m.normal_head_rel) * 3 * td.mpad : -1;
+        td.head_off = m.head_rel >= 0 ? u_of(m.head_rel) * td.tile : -1;
+        td.nhead_off = m.normal_head_rel >= 0 ? u_of(m.normal_head_rel) * td.tile : -1;
         td.n_methyls = m.n_methyls; td.methyl_off = (int)methyl_offs.size();
-        for (int k = 0; k < m.n_methyls; k++) methyl_offs.push_back(u_of(m.methyl_rel[k]) * 3 * td.mpad);
+        for (int k = 0; k < m.n_methyls; k++) methyl_offs.push_back(u_of(m.methyl_rel[k]) * td.tile);
         std::vector<int32_t> islots;
         if (ua) {
             td.item_off = (int)uas.size(); td.n_items = m.n_ua_atoms;
@@ -611,8 +615,8 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
                 UAItem it{};
                 it.kind = m.ua_kind[i];
                 const int32_t *r = m.ua_rel + 4 * i;
-                it.t_off = u_of(r[0]) * 3 * td.mpad; it.h1_off = u_of(r[1]) * 3 * td.mpad; it.h2_off = u_of(r[2]) * 3 * td.mpad;
-                it.h3_off = r[3] >= 0 ? u_of(r[3]) * 3 * td.mpad : 0;
+                it.t_off = u_of(r[0]) * td.tile; it.h1_off = u_of(r[1]) * td.tile; it.h2_off = u_of(r[2]) * td.tile;
+                it.h3_off = r[3] >= 0 ? u_of(r[3]) * td.tile : 0;
                 if (it.kind == GORDER_UA_CH1_SAT && r[3] < 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "CH1_SAT needs three helpers"); return h->err_code; }
                 it.slot_rel = k; k += ua_hydrogens(it.kind);
                 uas.push_back(it);
@@ -626,7 +630,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
                 int reuse = 0;
                 if (i > 0 && m.bond_rel[2 * i] == m.bond_rel[2 * (i - 1)]) reuse = 1;            // same first atom as the previous bond
                 else if (i > 0 && m.bond_rel[2 * i] == m.bond_rel[2 * (i - 1) + 1]) reuse = 2;   // previous bond's second atom
-                bonds.push_back(BondItem{u_of(m.bond_rel[2 * i]) * 3 * td.mpad + reuse, u_of(m.bond_rel[2 * i + 1]) * 3 * td.mpad});
+                bonds.push_back(BondItem{u_of(m.bond_rel[2 * i]) * td.tile + reuse, u_of(m.bond_rel[2 * i + 1]) * td.tile});
                 islots.push_back(m.bond_rel[2 * i]);
             }
         }
@@ -670,7 +674,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     // ---- batch size ------------------------------------------------------------------------------
     const size_t frame_bytes = (size_t)h->frame_floats * sizeof(float);
     long long mb = s->max_batch_frames > 0 ? s->max_batch_frames : (long long)((512ull << 20) / std::max<size_t>(frame_bytes, 1));
-    mb = std::max<long long>(1, std::min<long long>(mb, s->normal_mode == GORDER_NORMAL_DYNAMIC ? 32 : 512));
+    mb = std::max<long long>(1, std::min<long long>(mb, s->normal_mode == GORDER_NORMAL_DYNAMIC ? 32 : 4096));
     h->max_batch = (int)mb;
 
     // ---- device tables ---------------------------------------------------------------------------
@@ -702,6 +706,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     for (int k = 0; k < 6; k++) v.shape.dims[k] = s->geom_dims[k];
     v.manual_leaflets = d_mleaf; v.manual_normals = d_mnorm;
     v.err = h->d_err; v.err_detail = h->d_err_detail;
+    v.debug_nocompute = getenv("GORDER_DEBUG_NOCOMPUTE") ? 1 : 0;
     // rotation constants with the host libm (the reference's sin/cos of the same f32 angles)
     v.tet_s = sinf(1.910633f); v.tet_c = cosf(1.910633f);
     v.tet_half_s = sinf(0.9553165f); v.tet_half_c = cosf(0.9553165f);
@@ -964,6 +969,14 @@ int gorder_gpu_submit_native_device(GorderHandle *h, const float *d_planes, cons
         CK(cudaEventRecord(h->ev_stage_free[slot], h->stream));
     }
     return GORDER_OK;
+}
+
+int gorder_gpu_reserve_frames(GorderHandle *h, int64_t n_frames) {
+    if (!h || n_frames < 0) return GORDER_ERR_INVALID_ARGUMENT;
+    if (h->err_code) return h->err_code;
+    cudaSetDevice(h->device);
+    std::lock_guard<std::mutex> lock(h->mu);
+    return grow_rows(h, n_frames);
 }
 
 int gorder_gpu_set_leaflets(GorderHandle *h, const uint8_t *table, int64_t frame_index) {

@@ -9,15 +9,23 @@ namespace gorder {
 
 constexpr int kBlock = 256;        // threads per CTA of the accumulation kernels
 constexpr int kWarps = kBlock / 32;
-constexpr int kMolAlign = 32;      // molecules per type are padded to this (128 B planes)
+constexpr int kMolAlign = 32;      // alignment of the extra (non-molecule) planes, in floats
 
-// One molecule type on the device.  Coordinates of a frame live in "planes": for used atom u of
-// the type and component c, the coordinate of molecule m is
-//     frame[plane_base + (u * 3 + c) * mpad + m]
-// so that a warp whose lanes are consecutive molecules reads one fully-used 128 B line per plane.
+// One molecule type on the device.  Coordinates of a frame live in TILED "planes": molecules are
+// grouped in tiles of `tile` consecutive molecules (= the molecules one CTA of the accumulation
+// kernel owns); inside a tile, for used atom u and component c, molecule m sits at
+//     frame[plane_base + (m / tile) * tile_stride + c * cstride + u * tile + (m % tile)],
+//     cstride = n_used * tile,  tile_stride = 3 * cstride
+// (component-major inside the tile: the leaflet-axis planes of a tile form one contiguous run for the
+// centre reduction).
+// A warp whose lanes are consecutive molecules reads fully-used 128 B lines, and ONE CTA streams ONE
+// contiguous region of tile_stride floats (S-CG: 147 KB) -- the DRAM-friendly pattern of a plain copy.
 struct TypeDesc {
     int n_mol;        // molecules of this type
-    int mpad;         // n_mol rounded up to kMolAlign
+    int mpad;         // n_mol rounded up to a whole number of tiles
+    int tile;         // molecules per tile
+    int tile_stride;  // floats per tile
+    int cstride;      // component stride inside a tile (n_used * tile)
     int n_orders;     // order slots (bond types, or virtual C-H bonds for UA)
     int n_items;      // bond types (AA/CG) or carbon types (UA)
     int plane_base;   // float offset of plane (u=0, c=0) inside a frame
@@ -25,7 +33,7 @@ struct TypeDesc {
     int molpad0;      // offset of this type in padded per-molecule arrays (leaflets, normals)
     int mol0;         // offset of this type in compact per-molecule arrays (exports)
     int item_off;     // offset of this type in the item tables
-    int head_off;     // plane offset (u * 3 * mpad) of the leaflet head, -1 if none
+    int head_off;     // in-tile offset (u * tile) of the leaflet head, -1 if none
     int nhead_off;    // plane offset of the dynamic-normal head, -1 if none
     int n_methyls;
     int methyl_off;   // offset into methyl plane-offset table
@@ -35,7 +43,7 @@ struct TypeDesc {
     int n_manual_norm;
 };
 
-// AA/CG bond type: plane offsets (relative to plane_base) of the two atoms' x planes.
+// AA/CG bond type: in-tile offsets (u * tile) of the two atoms' x planes.
 struct BondItem { int a_off, b_off; };
 
 // UA carbon type (uaorder.rs:234-239): plane offsets of target and helpers, kind, first slot.
@@ -104,6 +112,7 @@ struct DeviceView {
     const float *manual_normals;
     // UA rotation constants (sin, cos) computed on the host with the same libm as the reference
     float tet_s, tet_c, tet_half_s, tet_half_c, ch3_s, ch3_c;
+    int debug_nocompute;      // profiling experiment only: load the planes, skip the arithmetic
     // error word
     int *err;                 // [0] code, [1] unused
     long long *err_detail;

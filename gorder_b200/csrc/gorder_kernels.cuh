@@ -43,6 +43,11 @@ template <> struct Vec<4> {
     }
 };
 
+// float offset (inside a frame) of molecule m's slot in the x plane of the atom at in-tile offset 0
+__device__ __forceinline__ size_t mol_offset(const TypeDesc &td, int m) {
+    return (size_t)td.plane_base + (size_t)(m / td.tile) * td.tile_stride + (m % td.tile);
+}
+
 __device__ __forceinline__ Box load_box(const FrameAux &a) {
     Box b;
     b.L[0] = a.L[0]; b.L[1] = a.L[1]; b.L[2] = a.L[2];
@@ -184,7 +189,7 @@ __global__ void frame_setup_kernel(DeviceView v, FrameAux *aux, const float *__r
 // frame_list[i]: index in the batch of the i-th frame that needs the centre.
 // out: est[3 * i + axis] (pass 0) / center[3 * i + axis] (pass 1; pass 0 when !pbc).
 // ---------------------------------------------------------------------------------------------
-constexpr int kCenterBlocks = 128;
+constexpr int kCenterBlocks = 64;
 
 __global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Seg *__restrict__ segs, int n_segs, int n_group, int axis,
                                                           const float *__restrict__ planes, const FrameAux *__restrict__ aux,
@@ -293,18 +298,19 @@ __global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const
         const int ax = v.leaflet_axis;
         const bool pbc = v.handle_pbc != 0;
         const float L = a.L[ax], half = a.half[ax];
-        const float *fr = planes + (size_t)f * v.frame_floats + td.plane_base + m;
+        const float *fr = planes + (size_t)f * v.frame_floats + mol_offset(td, m);
+        const int cst = td.cstride;   // component stride
         bool upper = true;
         if (v.leaflet_mode == GORDER_LEAFLET_GLOBAL) {   // leaflets.rs:571-624, :711-732
             float c = center[3 * ai + ax];
             if (c != c) raise_error(v, GORDER_ERR_INVALID_GLOBAL_CENTER, a.frame_index);
-            float head = fr[td.head_off + ax * td.mpad];
+            float head = fr[td.head_off + ax * cst];
             upper = distance_1d(head, c, L, half, pbc) >= 0.0f;
         } else if (v.leaflet_mode == GORDER_LEAFLET_INDIVIDUAL) {   // leaflets.rs:736-811
-            float head = fr[td.head_off + ax * td.mpad];
+            float head = fr[td.head_off + ax * cst];
             float total = 0.0f;
             for (int k = 0; k < td.n_methyls; k++) {
-                float me = fr[v.methyl_offs[td.methyl_off + k] + ax * td.mpad];
+                float me = fr[v.methyl_offs[td.methyl_off + k] + ax * cst];
                 total = __fadd_rn(total, distance_1d(head, me, L, half, pbc));
             }
             upper = total >= 0.0f;
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const
             else upper = v.manual_leaflets[td.manual_leaf_off + row * td.n_mol + m] == GORDER_UPPER;
         } else if (v.leaflet_mode == GORDER_LEAFLET_LOCAL) {   // leaflets.rs:630-707, pbc.rs:273-318
             // centre of the membrane atoms inside an infinite cylinder around the head (brute force)
-            f3 head = mk3(fr[td.head_off], fr[td.head_off + td.mpad], fr[td.head_off + 2 * td.mpad]);
+            f3 head = mk3(fr[td.head_off], fr[td.head_off + cst], fr[td.head_off + 2 * cst]);
             const float *frame0 = planes + (size_t)f * v.frame_floats;
             const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
             double sc = 0, ss = 0, sn = 0;
@@ -407,8 +413,8 @@ __global__ void __launch_bounds__(128) dynamic_normal_kernel(DeviceView v, const
     const FrameAux &a = aux[f];
     const Box bx = load_box(a);
     const float *frame0 = planes + (size_t)f * v.frame_floats;
-    const float *fr = frame0 + td.plane_base + m;
-    const f3 ref = mk3(fr[td.nhead_off], fr[td.nhead_off + td.mpad], fr[td.nhead_off + 2 * td.mpad]);
+    const float *fr = frame0 + mol_offset(td, m);
+    const f3 ref = mk3(fr[td.nhead_off], fr[td.nhead_off + td.cstride], fr[td.nhead_off + 2 * td.cstride]);
     const bool pbc = v.handle_pbc != 0;
     // pass 1: centroid of the cloud (f32 running sum in group order, as the reference's fold)
     int n = 0;
@@ -545,8 +551,8 @@ __global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, 
     int n[3];
     cell_dims(a, v.dynamic_radius, n);
     const float *frame0 = planes + (size_t)f * v.frame_floats;
-    const float *fr = frame0 + td.plane_base + m;
-    const f3 ref = mk3(fr[td.nhead_off], fr[td.nhead_off + td.mpad], fr[td.nhead_off + 2 * td.mpad]);
+    const float *fr = frame0 + mol_offset(td, m);
+    const f3 ref = mk3(fr[td.nhead_off], fr[td.nhead_off + td.cstride], fr[td.nhead_off + 2 * td.cstride]);
     const int c0[3] = {cell_coord(ref.x, a.L[0], n[0]), cell_coord(ref.y, a.L[1], n[1]), cell_coord(ref.z, a.L[2], n[2])};
     const int *st = cell_start + (size_t)f * (cells_cap + 1);
     const int *srt = sorted + (size_t)f * v.normal_heads.n;
@@ -709,7 +715,7 @@ __device__ __forceinline__ void map_add(const DeviceView &v, const AccumOut &o, 
 //           instead of a static axis; LEAF per-leaflet accumulation; EXTRA geometry filter / maps.
 // ---------------------------------------------------------------------------------------------
 template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA>
-__global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+__global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : (MPT == 4 ? 3 : 4)) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                             const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
                                                             const int *__restrict__ normal_npoints, AccumOut o) {
     constexpr int NA = AccLayout<LEAF, EXTRA>::N;
@@ -732,7 +738,7 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m0 = ch.first_mol + threadIdx.x * MPT;
     const bool active = m0 < td.mpad;
-    const int mpad = td.mpad;
+    const int mpad = td.cstride;   // component stride inside the CTA's tile
     const int c0 = PERMUTE ? (v.normal_axis + 1) % 3 : 0, c1 = PERMUTE ? (v.normal_axis + 2) % 3 : 1, c2 = PERMUTE ? v.normal_axis : 2;
     const int o0 = c0 * mpad, o1 = c1 * mpad, o2 = c2 * mpad;
     // box in the kernel's component order, with the fast-path guard of the fold
@@ -740,7 +746,7 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
     const float h0 = ax.half[c0], h1 = ax.half[c1], h2 = ax.half[c2];
     const float g0 = 0.99f * h0, g1 = 0.99f * h1, g2 = 0.99f * h2;
     const Box bx = load_box(ax);
-    const float *base_mol = planes + (size_t)f * v.frame_floats + td.plane_base + m0;
+    const float *base_mol = planes + (size_t)f * v.frame_floats + mol_offset(td, m0);
     bool valid[MPT];
     int upmask[MPT];
     f3 nrm[MPT];
@@ -779,24 +785,84 @@ __global__ void __launch_bounds__(kBlock) bond_order_kernel(DeviceView v, const 
     for (int j = 0; j < MPT; j++) any_used[j] = false;
     float nan_acc = 0.0f;   // NaN coordinates poison this accumulator (checked once after the loop)
 
-    const float *base = planes + (size_t)f * v.frame_floats + td.plane_base + m0;
-    Vec<MPT> x1, y1, z1, x2, y2, z2;
+    const float *base = base_mol;
+    // Software pipeline (streaming variant): the planes of bond b+1 are requested before bond b is
+    // evaluated, so every warp keeps two iterations of 128-bit loads in flight (the kernel is bound by
+    // memory latency, not by issue slots: profiles/README.md).
+    constexpr bool PREFETCH = !EXTRA && !NVEC;
+    Vec<MPT> x1, y1, z1, x2, y2, z2, nx1, ny1, nz1, nx2, ny2, nz2;
 #pragma unroll
-    for (int j = 0; j < MPT; j++) { x1.v[j] = y1.v[j] = z1.v[j] = x2.v[j] = y2.v[j] = z2.v[j] = 0.0f; }
+    for (int j = 0; j < MPT; j++) {
+        x1.v[j] = y1.v[j] = z1.v[j] = x2.v[j] = y2.v[j] = z2.v[j] = 0.0f;
+        nx1.v[j] = ny1.v[j] = nz1.v[j] = nx2.v[j] = ny2.v[j] = nz2.v[j] = 0.0f;
+    }
+    if (PREFETCH && nb > 0 && active) {
+        const BondItem b0 = s_bonds[0];
+        const int a_off = b0.a_off & ~3;
+        nx1.load(base + a_off + o0); ny1.load(base + a_off + o1); nz1.load(base + a_off + o2);
+        nx2.load(base + b0.b_off + o0); ny2.load(base + b0.b_off + o1); nz2.load(base + b0.b_off + o2);
+    }
     for (int b = 0; b < nb; b++) {
-        const BondItem bi = s_bonds[b];
-        // low bits of a_off: 1 = first atom is the previous bond's first atom, 2 = ... second atom
-        const int reuse = bi.a_off & 3, a_off = bi.a_off & ~3;
-        if (reuse == 2) { x1 = x2; y1 = y2; z1 = z2; }
-        if (active) {
-            if (reuse == 0) { x1.load(base + a_off + o0); y1.load(base + a_off + o1); z1.load(base + a_off + o2); }
-            x2.load(base + bi.b_off + o0); y2.load(base + bi.b_off + o1); z2.load(base + bi.b_off + o2);
+        if (PREFETCH) {
+            // rotate: the prefetched registers become the current bond ...
+            x1 = nx1; y1 = ny1; z1 = nz1; x2 = nx2; y2 = ny2; z2 = nz2;
+            // ... and the next bond's planes are requested now
+            if (b + 1 < nb) {
+                const BondItem bn = s_bonds[b + 1];
+                const int reuse = bn.a_off & 3, a_off = bn.a_off & ~3;
+                if (reuse == 2) { nx1 = x2; ny1 = y2; nz1 = z2; }       // next first atom = this bond's second atom
+                // reuse == 1: next first atom = this bond's first atom (nx1 already holds it)
+                if (active) {
+                    if (reuse == 0) { nx1.load(base + a_off + o0); ny1.load(base + a_off + o1); nz1.load(base + a_off + o2); }
+                    nx2.load(base + bn.b_off + o0); ny2.load(base + bn.b_off + o1); nz2.load(base + bn.b_off + o2);
+                }
+            }
+        } else {
+            const BondItem bi = s_bonds[b];
+            // low bits of a_off: 1 = first atom is the previous bond's first atom, 2 = ... second atom
+            const int reuse = bi.a_off & 3, a_off = bi.a_off & ~3;
+            if (reuse == 2) { x1 = x2; y1 = y2; z1 = z2; }
+            if (active) {
+                if (reuse == 0) { x1.load(base + a_off + o0); y1.load(base + a_off + o1); z1.load(base + a_off + o2); }
+                x2.load(base + bi.b_off + o0); y2.load(base + bi.b_off + o1); z2.load(base + bi.b_off + o2);
+            }
         }
         int st = 0, su = 0, ct = 0, cu = 0;   // total / upper (lower = total - upper)
+        if (v.debug_nocompute) {   // memory-pattern ceiling experiment (profiles/README.md): loads only
+#pragma unroll
+            for (int j = 0; j < MPT; j++)
+                st += __float_as_int(x1.v[j]) ^ __float_as_int(y1.v[j]) ^ __float_as_int(z1.v[j]) ^ __float_as_int(x2.v[j]) ^ __float_as_int(y2.v[j]) ^ __float_as_int(z2.v[j]);
+            warp_commit<LEAF, EXTRA>(s_acc + ((size_t)warp * nb + b) * NA, lane, st, 0, 0, 0);
+            continue;
+        }
+        // bond vectors of the thread's MPT molecules.  The fold's exact fast path
+        //   fl(fl(fl(fl(d + L/2) + L) - L) - L/2)
+        // is evaluated unconditionally; ONE predicate per iteration sends the (rare) warp that holds a bond
+        // outside the guard |d| <= 0.99 L/2 to the literal, out-of-line expression.
+        f3 dv[MPT];
+        bool slow = false;
 #pragma unroll
         for (int j = 0; j < MPT; j++) {
-            f3 d = mk3(__fsub_rn(x2.v[j], x1.v[j]), __fsub_rn(y2.v[j], y1.v[j]), __fsub_rn(z2.v[j], z1.v[j]));
-            if (PBC) { d.x = min_image_g(d.x, L0, h0, g0); d.y = min_image_g(d.y, L1, h1, g1); d.z = min_image_g(d.z, L2, h2, g2); }
+            const float rx = __fsub_rn(x2.v[j], x1.v[j]), ry = __fsub_rn(y2.v[j], y1.v[j]), rz = __fsub_rn(z2.v[j], z1.v[j]);
+            if (PBC) {
+                slow = slow || (valid[j] && (fabsf(rx) > g0 || fabsf(ry) > g1 || fabsf(rz) > g2));
+                dv[j] = mk3(__fsub_rn(__fsub_rn(__fadd_rn(__fadd_rn(rx, h0), L0), L0), h0),
+                            __fsub_rn(__fsub_rn(__fadd_rn(__fadd_rn(ry, h1), L1), L1), h1),
+                            __fsub_rn(__fsub_rn(__fadd_rn(__fadd_rn(rz, h2), L2), L2), h2));
+            } else dv[j] = mk3(rx, ry, rz);
+        }
+        if (PBC && slow) {
+#pragma unroll
+            for (int j = 0; j < MPT; j++) {
+                const float rx = __fsub_rn(x2.v[j], x1.v[j]), ry = __fsub_rn(y2.v[j], y1.v[j]), rz = __fsub_rn(z2.v[j], z1.v[j]);
+                if (fabsf(rx) > g0) dv[j].x = min_image_slow(rx, L0, h0);
+                if (fabsf(ry) > g1) dv[j].y = min_image_slow(ry, L1, h1);
+                if (fabsf(rz) > g2) dv[j].z = min_image_slow(rz, L2, h2);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MPT; j++) {
+            const f3 d = dv[j];
             bool use = valid[j];
             f3 mid;
             if (EXTRA) {
@@ -986,8 +1052,8 @@ __global__ void __launch_bounds__(kBlock, 4) global_leaflet_pipeline_kernel(Devi
         const float center = s_center;
         const int m0 = ch.first_mol + threadIdx.x * MPT;
         const bool active = m0 < td.mpad;
-        const int mpad = td.mpad;
-        const float *base = planes + (size_t)f * v.frame_floats + td.plane_base + m0;
+        const int mpad = td.cstride;
+        const float *base = planes + (size_t)f * v.frame_floats + mol_offset(td, m0);
         const Box bx = load_box(ax);
         bool valid[MPT], up[MPT];
         int nvalid = 0, nup = 0;
@@ -1128,8 +1194,8 @@ __global__ void __launch_bounds__(kBlock) ua_order_kernel(DeviceView v, const fl
         int a = __reduce_add_sync(0xffffffffu, (int)valid), b = __reduce_add_sync(0xffffffffu, (int)(valid && up));
         if (lane == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], b); }
     }
-    const float *base = planes + (size_t)f * v.frame_floats + td.plane_base + m;
-    const int mpad = td.mpad;
+    const float *base = planes + (size_t)f * v.frame_floats + mol_offset(td, valid ? m : 0);
+    const int mpad = td.cstride;
     for (int i = 0; i < ni; i++) {
         const UAItem it = s_items[i];
         const int nh = it.kind == GORDER_UA_CH3 ? 3 : (it.kind == GORDER_UA_CH2 ? 2 : 1);

@@ -102,6 +102,10 @@ class SystemTopology:
         return out
 
     # -- leaflets / reduce ---------------------------------------------------------------------------
+    def reserve_frames(self, n_frames: int):
+        """Pre-allocate the per-frame rows for ``n_frames`` analysed frames (error estimation)."""
+        self._check(lib().gorder_gpu_reserve_frames(self._h, int(n_frames)))
+
     def set_leaflets(self, table, frame_index: int = 0):
         t = np.ascontiguousarray(table, dtype=np.uint8)
         self._check(lib().gorder_gpu_set_leaflets(self._h, _ptr(t), int(frame_index)))

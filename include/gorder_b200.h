@@ -265,6 +265,11 @@ int gorder_gpu_submit_native(GorderHandle *h, const float *planes_host, const fl
 int gorder_gpu_submit_native_device(GorderHandle *h, const float *d_planes, const float *d_box,
                                     const int64_t *frame_index, int32_t n_frames);
 
+/* Optional: announce how many frames will be analysed in total (the reference knows the trajectory
+ * length only at the end; with error estimation the per-frame rows, order.rs:83-88, then grow without
+ * re-allocation). */
+int gorder_gpu_reserve_frames(GorderHandle *h, int64_t n_frames);
+
 /* Seed the leaflet assignment used until the next assignment frame (Frequency::Once on a shard
  * that does not own frame 0: SURVEY.md §8e). table: [n_molecules_total] after flip. */
 int gorder_gpu_set_leaflets(GorderHandle *h, const uint8_t *table, int64_t frame_index);

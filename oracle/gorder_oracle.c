@@ -620,18 +620,80 @@ static void assign_leaflets(const GorderOracle *o, const float *xyz, const float
     free(scratch);
 }
 
+/* Cell grid over the NormalHeads group (groan CellGrid::new(system, "NormalHeads", radius), pbc.rs:327-333):
+ * cell edge >= radius, the 3x3x3 block around the reference is scanned and filtered by the exact
+ * sphere test, so the result equals the brute-force scan except for the order in which the f32
+ * centroid is summed.  Used only for large head groups (the brute force is O(n^2) per frame). */
+#define ORACLE_CELL_MIN_HEADS 4096
+typedef struct { int n[3]; int *start; int *sorted; } CellGridO;
+
+static void cellgrid_build(const GorderOracle *o, const float *xyz, const float *box, CellGridO *g) {
+    const GorderSetup *s = &o->s;
+    int nh = s->n_normal_heads;
+    for (int k = 0; k < 3; k++) { int q = (int)floorf(box[k] / s->dynamic_radius); g->n[k] = q < 1 ? 1 : (q > 64 ? 64 : q); }
+    int nc = g->n[0] * g->n[1] * g->n[2];
+    g->start = (int *)calloc(nc + 1, sizeof(int));
+    g->sorted = (int *)malloc(sizeof(int) * (nh > 0 ? nh : 1));
+    int *cell = (int *)malloc(sizeof(int) * (nh > 0 ? nh : 1));
+    for (int i = 0; i < nh; i++) {
+        vec3 p = atom_pos(xyz, o->normal_heads[i]);
+        int c[3];
+        float q[3] = {p.x, p.y, p.z};
+        for (int k = 0; k < 3; k++) {
+            float w = wrap1(q[k], box[k]);
+            int ci = (int)(w * (float)g->n[k] / box[k]);
+            c[k] = ci < 0 ? 0 : (ci >= g->n[k] ? g->n[k] - 1 : ci);
+            if (isnan(q[k])) c[k] = 0;
+        }
+        cell[i] = (c[0] * g->n[1] + c[1]) * g->n[2] + c[2];
+        g->start[cell[i] + 1]++;
+    }
+    for (int c = 0; c < nc; c++) g->start[c + 1] += g->start[c];
+    int *cur = (int *)malloc(sizeof(int) * (nc > 0 ? nc : 1));
+    memcpy(cur, g->start, sizeof(int) * nc);
+    for (int i = 0; i < nh; i++) g->sorted[cur[cell[i]]++] = i;
+    free(cur); free(cell);
+}
+static void cellgrid_free(CellGridO *g) { free(g->start); free(g->sorted); g->start = NULL; g->sorted = NULL; }
+
 /* PBC3D::get_heads_cloud (pbc.rs:321-351) / NoPBC (:142-161) + membrane_normal_from_cloud. */
-static int dynamic_normal(const GorderOracle *o, const float *xyz, const float *box, int head_idx, vec3 *out, FrameErr *fe, vec3 *cloud) {
+static int dynamic_normal(const GorderOracle *o, const float *xyz, const float *box, int head_idx, vec3 *out, FrameErr *fe, vec3 *cloud,
+                          const CellGridO *g) {
     const GorderSetup *s = &o->s;
     vec3 ref = atom_pos(xyz, head_idx);
     if (pos_undefined(ref)) { FAIL(fe, GORDER_ERR_UNDEFINED_POSITION, head_idx); return 1; }
     int n = 0;
-    for (int i = 0; i < s->n_normal_heads; i++) {
-        vec3 p = atom_pos(xyz, o->normal_heads[i]);
-        vec3 d = vector_to(ref, p, box, s->handle_pbc);
-        if (vnorm(d) < s->dynamic_radius) {
-            if (pos_undefined(p)) { FAIL(fe, GORDER_ERR_UNDEFINED_POSITION, o->normal_heads[i]); return 1; }
-            cloud[n++] = s->handle_pbc ? vadd(ref, d) : p;
+    if (g && g->start) {
+        int c0[3];
+        float q[3] = {ref.x, ref.y, ref.z};
+        for (int k = 0; k < 3; k++) {
+            int ci = (int)(wrap1(q[k], box[k]) * (float)g->n[k] / box[k]);
+            c0[k] = ci < 0 ? 0 : (ci >= g->n[k] ? g->n[k] - 1 : ci);
+        }
+        int lo[3], hi[3];
+        for (int k = 0; k < 3; k++) { lo[k] = g->n[k] >= 3 ? -1 : 0; hi[k] = g->n[k] >= 3 ? 1 : g->n[k] - 1; }
+        for (int dx = lo[0]; dx <= hi[0]; dx++)
+            for (int dy = lo[1]; dy <= hi[1]; dy++)
+                for (int dz = lo[2]; dz <= hi[2]; dz++) {
+                    int cx = g->n[0] >= 3 ? (c0[0] + dx + g->n[0]) % g->n[0] : dx;
+                    int cy = g->n[1] >= 3 ? (c0[1] + dy + g->n[1]) % g->n[1] : dy;
+                    int cz = g->n[2] >= 3 ? (c0[2] + dz + g->n[2]) % g->n[2] : dz;
+                    int c = (cx * g->n[1] + cy) * g->n[2] + cz;
+                    for (int k = g->start[c]; k < g->start[c + 1]; k++) {
+                        int idx = o->normal_heads[g->sorted[k]];
+                        vec3 p = atom_pos(xyz, idx);
+                        vec3 d = vector_to(ref, p, box, 1);
+                        if (vnorm(d) < s->dynamic_radius) cloud[n++] = vadd(ref, d);
+                    }
+                }
+    } else {
+        for (int i = 0; i < s->n_normal_heads; i++) {
+            vec3 p = atom_pos(xyz, o->normal_heads[i]);
+            vec3 d = vector_to(ref, p, box, s->handle_pbc);
+            if (vnorm(d) < s->dynamic_radius) {
+                if (pos_undefined(p)) { FAIL(fe, GORDER_ERR_UNDEFINED_POSITION, o->normal_heads[i]); return 1; }
+                cloud[n++] = s->handle_pbc ? vadd(ref, d) : p;
+            }
         }
     }
     int rc = normal_from_cloud(cloud, n, out);
@@ -698,7 +760,11 @@ static void analyze_one_frame(GorderOracle *o, const float *xyz, const float *bo
     }
     vec3 static_normal = v3(s->normal_axis == 0, s->normal_axis == 1, s->normal_axis == 2);
     vec3 *cloud = NULL;
-    if (s->normal_mode == GORDER_NORMAL_DYNAMIC) cloud = (vec3 *)malloc(sizeof(vec3) * (s->n_normal_heads > 0 ? s->n_normal_heads : 1));
+    CellGridO grid = {{0, 0, 0}, NULL, NULL};
+    if (s->normal_mode == GORDER_NORMAL_DYNAMIC) {
+        cloud = (vec3 *)malloc(sizeof(vec3) * (s->n_normal_heads > 0 ? s->n_normal_heads : 1));
+        if (pbc && s->n_normal_heads >= ORACLE_CELL_MIN_HEADS) cellgrid_build(o, xyz, box, &grid);
+    }
     if (normals_out) for (int i = 0; i < o->n_mol_total * 3; i++) normals_out[i] = nanf("");
 
     for (int t = 0; t < s->n_moltypes && !fe->err; t++) {
@@ -714,7 +780,7 @@ static void analyze_one_frame(GorderOracle *o, const float *xyz, const float *bo
         if (s->normal_mode == GORDER_NORMAL_STATIC) nvar = static_normal;                                           \
         else if (s->normal_mode == GORDER_NORMAL_DYNAMIC) {                                                         \
             if (!nhave[m]) {                                                                                        \
-                if (dynamic_normal(o, xyz, box, q->mol_base[m] + q->normal_head_rel, &ncache[m], fe, cloud)) break; \
+                if (dynamic_normal(o, xyz, box, q->mol_base[m] + q->normal_head_rel, &ncache[m], fe, cloud, &grid)) break; \
                 nhave[m] = 1;                                                                                       \
             }                                                                                                       \
             nvar = ncache[m];                                                                                       \
@@ -784,6 +850,7 @@ static void analyze_one_frame(GorderOracle *o, const float *xyz, const float *bo
 #undef GET_NORMAL
     }
     free(cloud);
+    cellgrid_free(&grid);
 }
 
 /* Analyse a batch of frames; n_threads > 1 mimics the reference's interleaved frame ownership
