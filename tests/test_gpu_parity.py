@@ -171,3 +171,64 @@ def test_errors():
         eng.analyze_frames(xyz, box, np.array([4, 5]))
     assert e.value.code == abi.ERR_LEAFLET_FRAME_UNAVAILABLE
     eng.close()
+
+
+def test_edge_cases_empty_and_ragged():
+    """Empty submissions, a batch larger than max_batch_frames, per-frame rows growing past their first allocation,
+    molecule types of very different sizes (1 molecule .. hundreds)."""
+    from gorder_b200 import SystemTopology
+    from oracle import oracle as orc
+    s = synthetic.s_cg(333, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True, collect_leaflets=True, max_batch_frames=4)
+    # re-cut the molecule types raggedly: 1, 2, 30 and the rest
+    base = list(s.setup.moltypes[0].mol_base)
+    proto = s.setup.moltypes[0]
+    cuts = [(0, 1), (1, 3), (3, 33), (33, 333)]
+    s.setup.moltypes = [abi.MolType(name=f"T{i}", mol_base=base[a:b], bond_rel=proto.bond_rel, head_rel=proto.head_rel,
+                                    methyl_rel=proto.methyl_rel, normal_head_rel=proto.normal_head_rel) for i, (a, b) in enumerate(cuts)]
+    xyz, box, idx = s.frames(0, 11)
+    eng = SystemTopology(s.setup)
+    ref = orc.Oracle(s.setup, n_threads=2)
+    eng.analyze_frames(xyz[:0], box[:0], idx[:0])          # empty
+    eng.analyze_frames(xyz[:9], box[:9], idx[:9])          # 9 frames with max_batch_frames = 4 -> 3 internal batches
+    eng.analyze_frames(xyz[9:], box[9:], idx[9:])
+    ref.analyze_frames(xyz, box, idx)
+    g, r = eng.finish(), ref.finish()
+    assert g.n_frames == 11 and g.n_slots == 44
+    assert_raw_parity(g, r, s.setup, what="ragged")
+    eng.close()
+    ref.close()
+
+
+def test_no_frames_gives_zero_results():
+    from gorder_b200 import SystemTopology
+    s = synthetic.s_cg(50)
+    eng = SystemTopology(s.setup)
+    g = eng.finish()
+    assert g.n_frames == 0 and not g.sum.any() and not g.count.any()
+    eng.close()
+
+
+def test_large_system_properties():
+    """BASELINE-size frame (83 334 lipids): size-independent properties instead of the (slow) oracle:
+    counts are exact, upper + lower == total, S in [-0.5, 1], two shards sum to the whole (linearity)."""
+    from gorder_b200 import SystemTopology
+    s = synthetic.s_cg(83334, leaflet_mode=abi.LEAFLET_GLOBAL)
+    xyz, box, idx = s.frames(0, 4)
+    whole = SystemTopology(s.setup)
+    whole.analyze_frames(xyz, box, idx)
+    w = whole.finish()
+    whole.close()
+    assert np.all(w.count[:, 0] == 83334 * 4)
+    np.testing.assert_array_equal(w.count[:, 1] + w.count[:, 2], w.count[:, 0])
+    np.testing.assert_array_equal(w.sum[:, 1] + w.sum[:, 2], w.sum[:, 0])
+    mean = w.sum[:, 0] / w.count[:, 0] / 1e6
+    assert np.all(mean > -0.5) and np.all(mean < 1.0)
+    assert abs(int(w.count[0, 1]) - int(w.count[0, 2])) <= 4   # 41 667 lipids per leaflet and frame
+    parts = []
+    for lo, hi in ((0, 2), (2, 4)):
+        e = SystemTopology(s.setup)
+        e.analyze_frames(xyz[lo:hi], box[lo:hi], idx[lo:hi])
+        parts.append(e.finish())
+        e.close()
+    np.testing.assert_array_equal(parts[0].sum + parts[1].sum, w.sum)
+    np.testing.assert_array_equal(parts[0].count + parts[1].count, w.count)
