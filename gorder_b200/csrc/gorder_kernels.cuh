@@ -715,7 +715,7 @@ __device__ __forceinline__ void map_add(const DeviceView &v, const AccumOut &o, 
 //           instead of a static axis; LEAF per-leaflet accumulation; EXTRA geometry filter / maps.
 // ---------------------------------------------------------------------------------------------
 template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA>
-__global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : (MPT == 4 ? 3 : 4)) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+__global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                             const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
                                                             const int *__restrict__ normal_npoints, AccumOut o) {
     constexpr int NA = AccLayout<LEAF, EXTRA>::N;
@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : (MPT == 4 ? 3 : 
     // Software pipeline (streaming variant): the planes of bond b+1 are requested before bond b is
     // evaluated, so every warp keeps two iterations of 128-bit loads in flight (the kernel is bound by
     // memory latency, not by issue slots: profiles/README.md).
-    constexpr bool PREFETCH = !EXTRA && !NVEC;
+    constexpr bool PREFETCH = false;   // measured: no gain (the rotation costs 24 MOVs per iteration), kept for experiments
     Vec<MPT> x1, y1, z1, x2, y2, z2, nx1, ny1, nz1, nx2, ny2, nz2;
 #pragma unroll
     for (int j = 0; j < MPT; j++) {
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : (MPT == 4 ? 3 : 
         for (int j = 0; j < MPT; j++) {
             const float rx = __fsub_rn(x2.v[j], x1.v[j]), ry = __fsub_rn(y2.v[j], y1.v[j]), rz = __fsub_rn(z2.v[j], z1.v[j]);
             if (PBC) {
-                slow = slow || (valid[j] && (fabsf(rx) > g0 || fabsf(ry) > g1 || fabsf(rz) > g2));
+                slow = slow | (valid[j] & ((fabsf(rx) > g0) | (fabsf(ry) > g1) | (fabsf(rz) > g2)));
                 dv[j] = mk3(__fsub_rn(__fsub_rn(__fadd_rn(__fadd_rn(rx, h0), L0), L0), h0),
                             __fsub_rn(__fsub_rn(__fadd_rn(__fadd_rn(ry, h1), L1), L1), h1),
                             __fsub_rn(__fsub_rn(__fadd_rn(__fadd_rn(rz, h2), L2), L2), h2));
@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : (MPT == 4 ? 3 : 
                 s = calc_sch_fast(d, nrm[j]);
             } else s = calc_sch_axis_fast(d, PERMUTE ? d.z : comp(d, v.normal_axis));
             s = use ? s : 0.0f;
-            nan_acc = fmaf(s, 0.0f, nan_acc);
+            nan_acc = fmaf(use ? (d.x + d.y + d.z) : 0.0f, 0.0f, nan_acc);   // NaN / Inf coordinates poison the accumulator
             const int q = order_value_fast(s);
             st += q; su += q & upmask[j];
             if (EXTRA) {
@@ -1220,7 +1220,8 @@ __global__ void __launch_bounds__(kBlock) ua_order_kernel(DeviceView v, const fl
                     if (v.shape.kind != GORDER_GEOM_NONE && !shape_inside<PBC>(v.shape, ax, bx, mid)) continue;
                 }
                 const float s = calc_sch_fast(d, nrm);
-                if (s != s) {
+                const float chk = (d.x + d.y + d.z) * 0.0f;   // NaN / Inf coordinates (the clamp in calc_sch would hide them)
+                if (chk != chk) {
                     raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | ((long long)i << 32) | (unsigned)m);
                     continue;
                 }

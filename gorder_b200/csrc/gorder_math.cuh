@@ -137,12 +137,18 @@ __device__ __forceinline__ float calc_sch_fast(const f3 &v, const f3 &n) {
     if (den == 0.0f) c = 1.0f;      // angle() returns 0 when a norm is 0 -> S = 1
     return fmaf(1.5f * c, c, -0.5f);   // NaN coordinates propagate (den != den -> c NaN -> S NaN)
 }
+// one MUFU.RSQ (rsqrtf() would add denormal scaling; |v|^2 of a bond is never denormal, and 0 is handled)
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float calc_sch_axis_fast(const f3 &v, float v_axis) {
     const float n1 = fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x));
-    float c = v_axis * rsqrtf(n1);
-    c = fminf(1.0f, fmaxf(-1.0f, c));
-    if (n1 == 0.0f) c = 1.0f;
-    return fmaf(1.5f * c, c, -0.5f);
+    const float c = v_axis * rsqrt_ftz(n1);
+    float c2 = fminf(c * c, 1.0f);   // clamp(c, -1, 1)^2
+    if (n1 == 0.0f) c2 = 1.0f;       // angle() returns 0 when a norm is 0 -> S = 1
+    return fmaf(1.5f, c2, -0.5f);    // NaN coordinates propagate (fminf would hide them: re-poison below)
 }
 
 // OrderValue::from(f32) in one FMUL + F2I: round-to-nearest of fl(S * 1e6).  fl() moves the product

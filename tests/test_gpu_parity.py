@@ -232,3 +232,21 @@ def test_large_system_properties():
         e.close()
     np.testing.assert_array_equal(parts[0].sum + parts[1].sum, w.sum)
     np.testing.assert_array_equal(parts[0].count + parts[1].count, w.count)
+
+
+def test_nan_in_native_frames_is_reported():
+    """Frames handed over in the plane layout skip the relayout check: the accumulation kernels must still
+    report AnalysisError::UndefinedPosition for a NaN coordinate (bond and UA engines)."""
+    from gorder_b200 import SystemTopology
+    for s in (synthetic.s_cg(300, leaflet_mode=abi.LEAFLET_NONE), synthetic.s_ua(64, leaflet_mode=abi.LEAFLET_NONE, timewise=False)):
+        xyz, box, idx = s.frames(0, 2)
+        eng = SystemTopology(s.setup)
+        planes = eng.to_native(xyz)
+        _, off, cs = eng.native_layout()
+        victim = int(s.setup.moltypes[0].mol_base[7]) + (int(s.setup.moltypes[0].bond_rel[0][0]) if s.setup.kind != abi.KIND_UA else int(s.setup.moltypes[0].ua_rel[0][0]))
+        planes[1, off[victim] + cs[victim]] = np.nan
+        eng.analyze_frames_native(planes, box, idx)
+        with pytest.raises(abi.GorderError) as e:
+            eng.finish()
+        assert e.value.code == abi.ERR_UNDEFINED_POSITION
+        eng.close()
