@@ -26,19 +26,44 @@ __device__ __forceinline__ void raise_error(const DeviceView &v, int code, long 
     if (atomicCAS(v.err, 0, code) == 0) *v.err_detail = detail;
 }
 
+// L2 eviction-priority hints (createpolicy + ld.global.L2::cache_hint): the accumulation kernel
+// streams every plane once (evict_first), the centre passes want the axis planes to survive from
+// pass 0 to pass 1 (evict_last).
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_hint4(const float *p, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
 template <int N> struct Vec;
 template <> struct Vec<1> {
     float v[1];
     __device__ __forceinline__ void load(const float *p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void load_hint(const float *p, unsigned long long) { load(p); }
 };
 template <> struct Vec<2> {
     float v[2];
     __device__ __forceinline__ void load(const float *p) { float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; }
+    __device__ __forceinline__ void load_hint(const float *p, unsigned long long) { load(p); }
 };
 template <> struct Vec<4> {
     float v[4];
     __device__ __forceinline__ void load(const float *p) {
         float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void load_hint(const float *p, unsigned long long pol) {
+        float4 t = ldg_hint4(p, pol);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
 };
@@ -203,6 +228,7 @@ __global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Se
     float a0 = 0.0f, a1 = 0.0f;
     const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
     const float e = (pbc && pass == 1) ? est[3 * fi + axis] : 0.0f;
+    const unsigned long long pol = l2_policy_evict_last();
     auto add = [&](float p) {
         if (!pbc) a0 += p;
         else if (pass == 0) {
@@ -219,7 +245,8 @@ __global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Se
             const float4 *s4 = reinterpret_cast<const float4 *>(src);
             int i = threadIdx.x;
             for (; i + 3 * (int)blockDim.x < n4; i += 4 * blockDim.x) {
-                const float4 q0 = __ldg(s4 + i), q1 = __ldg(s4 + i + blockDim.x), q2 = __ldg(s4 + i + 2 * blockDim.x), q3 = __ldg(s4 + i + 3 * blockDim.x);
+                const float4 q0 = ldg_hint4(src + 4 * (size_t)i, pol), q1 = ldg_hint4(src + 4 * (size_t)(i + blockDim.x), pol),
+                             q2 = ldg_hint4(src + 4 * (size_t)(i + 2 * blockDim.x), pol), q3 = ldg_hint4(src + 4 * (size_t)(i + 3 * blockDim.x), pol);
                 add(q0.x); add(q0.y); add(q0.z); add(q0.w); add(q1.x); add(q1.y); add(q1.z); add(q1.w);
                 add(q2.x); add(q2.y); add(q2.z); add(q2.w); add(q3.x); add(q3.y); add(q3.z); add(q3.w);
             }
@@ -789,6 +816,7 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
     // Software pipeline (streaming variant): the planes of bond b+1 are requested before bond b is
     // evaluated, so every warp keeps two iterations of 128-bit loads in flight (the kernel is bound by
     // memory latency, not by issue slots: profiles/README.md).
+    const unsigned long long pol_first = l2_policy_evict_first();
     constexpr bool PREFETCH = false;   // measured: no gain (the rotation costs 24 MOVs per iteration), kept for experiments
     Vec<MPT> x1, y1, z1, x2, y2, z2, nx1, ny1, nz1, nx2, ny2, nz2;
 #pragma unroll
@@ -823,8 +851,13 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
             const int reuse = bi.a_off & 3, a_off = bi.a_off & ~3;
             if (reuse == 2) { x1 = x2; y1 = y2; z1 = z2; }
             if (active) {
-                if (reuse == 0) { x1.load(base + a_off + o0); y1.load(base + a_off + o1); z1.load(base + a_off + o2); }
-                x2.load(base + bi.b_off + o0); y2.load(base + bi.b_off + o1); z2.load(base + bi.b_off + o2);
+                if (v.l2_hints) {   // stream through L2 without displacing the axis planes the centre passes keep there
+                    if (reuse == 0) { x1.load_hint(base + a_off + o0, pol_first); y1.load_hint(base + a_off + o1, pol_first); z1.load_hint(base + a_off + o2, pol_first); }
+                    x2.load_hint(base + bi.b_off + o0, pol_first); y2.load_hint(base + bi.b_off + o1, pol_first); z2.load_hint(base + bi.b_off + o2, pol_first);
+                } else {
+                    if (reuse == 0) { x1.load(base + a_off + o0); y1.load(base + a_off + o1); z1.load(base + a_off + o2); }
+                    x2.load(base + bi.b_off + o0); y2.load(base + bi.b_off + o1); z2.load(base + bi.b_off + o2);
+                }
             }
         }
         int st = 0, su = 0, ct = 0, cu = 0;   // total / upper (lower = total - upper)
