@@ -67,18 +67,26 @@ class ClockSampler(threading.Thread):
             return
         while not self.stop_flag:
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                t = time.perf_counter()
+                clk = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
                 mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
+                self.samples.append((t, clk, mask))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
-    def summary(self):
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+    def summary(self, t0=None, t1=None):
+        """Samples inside the timed window [t0, t1] (the sampler runs from before the warm-up on)."""
+        win = [x for x in self.samples if t0 is None or (t0 <= x[0] <= t1)]
+        if not win and self.samples:   # window shorter than one NVML query: take the sample closest to it
+            win = [min(self.samples, key=lambda x: abs(x[0] - (t0 + t1) / 2))]
+        reasons = set()
+        for _t, _c, mask in win:
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([x[1] for x in win])) if win else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(win), "window_ms": None if t0 is None else 1e3 * (t1 - t0)}
 
 
 WORKLOADS = {
@@ -210,6 +218,8 @@ def run_ours(args):
         eng.analyze_frames_device(d_planes.data_ptr(), d_box.data_ptr(), F, frame_index=base + np.arange(F, dtype=np.int64), native=True)
 
     eng.reserve_frames((W + K + 6) * F)
+    sampler = ClockSampler(local)
+    sampler.start()
     for k in range(W):
         step(k)
     eng.sync()
@@ -223,9 +233,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     l0 = eng.stats()["kernel_launches"]
     eng.profile(True)
-    sampler = ClockSampler(local)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_win0 = time.perf_counter()
     ev0.record(stream)
     for k in range(W, W + K):
         step(k)
@@ -239,6 +248,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    t_win1 = time.perf_counter()
     sampler.stop_flag = True
     ms = ev0.elapsed_time(ev1)
     hot_ms, hot_n = eng.profile_read()
@@ -321,7 +331,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config(args, s, {"resident_layout": "engine planes (gorder_gpu_native_layout)", "native_frame_bytes": frame_bytes}),
-            "clocks": sampler.summary(),
+            "clocks": sampler.summary(t_win0, t_win1),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "entry": "gorder_gpu_submit (pinned host [atom][xyz] frames) + gorder_gpu_finish", "timer": "host wall clock between device syncs"},
             "gpu_launches": launches,

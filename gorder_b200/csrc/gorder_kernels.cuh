@@ -229,13 +229,14 @@ __global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Se
     const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
     const float e = (pbc && pass == 1) ? est[3 * fi + axis] : 0.0f;
     const unsigned long long pol = l2_policy_evict_last();
+    const float guard = 0.99f * half;
     auto add = [&](float p) {
         if (!pbc) a0 += p;
         else if (pass == 0) {
             float sn, cs;
             __sincosf(p * scale, &sn, &cs);   // the estimate only seeds the refinement pass
             a0 += cs; a1 += sn;
-        } else a0 += min_image(__fsub_rn(p, e), L, half);
+        } else a0 += min_image_g(__fsub_rn(p, e), L, half, guard);
     };
     for (int sg = blockIdx.x; sg < n_segs; sg += gridDim.x) {
         const Seg sgm = segs[sg];
