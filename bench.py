@@ -313,7 +313,8 @@ def run_ours(args):
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
                 tr = json.load(f)
-            traffic = tr["dram_bytes_per_frame"] * F
+            if args.workload == "cg" and args.lipids == N_LIPIDS:   # the capture is of this workload only
+                traffic = tr["dram_bytes_per_frame"] * K * F / max(hot_n, 1)
         except Exception:
             pass
         # ---- CPU baseline (oracle port) on a bounded sample + parity of the GPU sums against it ------
