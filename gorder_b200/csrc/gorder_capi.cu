@@ -107,7 +107,8 @@ struct GorderHandle {
     // cell list of the normal heads (K4)
     bool use_cells = false;
     int cells_cap = 0;
-    int *d_head_cell = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_sorted = nullptr;
+    int *d_head_cell = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr;
+    float4 *d_cell_sorted = nullptr;   // head positions (+ index) in cell order
 
     // centres
     // per staging slot, so that the centre passes of batch k+1 (pre stream) overlap the bond kernel of batch k
@@ -402,7 +403,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
             dim3 gh((nh + 255) / 256, nf);
             cell_count_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, da, h->d_head_cell, h->d_cell_count, h->cells_cap);
             cell_scan_kernel<<<nf, 1024, 0, h->stream>>>(h->view, da, h->d_cell_count, h->d_cell_start, h->cells_cap);
-            cell_fill_kernel<<<gh, 256, 0, h->stream>>>(h->view, h->d_head_cell, h->d_cell_count, h->d_cell_start, h->d_cell_sorted, h->cells_cap);
+            cell_fill_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, h->d_head_cell, h->d_cell_count, h->d_cell_start, h->d_cell_sorted, h->cells_cap);
             dim3 grid((h->n_molpad + 127) / 128, nf);
             dynamic_normal_cell_kernel<<<grid, 128, 0, h->stream>>>(h->view, d_planes, da, h->d_molpad_type, h->d_cell_start, h->d_cell_sorted,
                                                                    h->cells_cap, h->d_normals, h->d_normal_npoints);

@@ -553,18 +553,22 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(DeviceView v, const Fra
     if (threadIdx.x == 0) st[nc] = s_carry;
 }
 
-__global__ void __launch_bounds__(256) cell_fill_kernel(DeviceView v, const int *__restrict__ head_cell, int *__restrict__ cell_count,
-                                                        const int *__restrict__ cell_start, int *__restrict__ sorted, int cells_cap) {
+__global__ void __launch_bounds__(256) cell_fill_kernel(DeviceView v, const float *__restrict__ planes, const int *__restrict__ head_cell,
+                                                        int *__restrict__ cell_count, const int *__restrict__ cell_start,
+                                                        float4 *__restrict__ sorted_pos, int cells_cap) {
     const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.normal_heads.n) return;
     const int c = head_cell[(size_t)f * v.normal_heads.n + i];
     const int pos = cell_start[(size_t)f * (cells_cap + 1) + c] + atomicAdd(&cell_count[(size_t)f * cells_cap + c], 1);
-    sorted[(size_t)f * v.normal_heads.n + pos] = i;
+    // the coordinates travel with the index: the gather loop reads ONE contiguous float4 per candidate
+    const float *fr = planes + (size_t)f * v.frame_floats;
+    const int off = v.normal_heads.off[i], cs = v.normal_heads.cs[i];
+    sorted_pos[(size_t)f * v.normal_heads.n + pos] = make_float4(fr[off], fr[off + cs], fr[off + 2 * (size_t)cs], __int_as_float(i));
 }
 
 __global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                                   const int *__restrict__ molpad_type, const int *__restrict__ cell_start,
-                                                                  const int *__restrict__ sorted, int cells_cap, float *__restrict__ normals,
+                                                                  const float4 *__restrict__ sorted_pos, int cells_cap, float *__restrict__ normals,
                                                                   int *__restrict__ normal_npoints) {
     const int f = blockIdx.y;
     const int mp = blockIdx.x * blockDim.x + threadIdx.x;
@@ -583,7 +587,9 @@ __global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, 
     const f3 ref = mk3(fr[td.nhead_off], fr[td.nhead_off + td.cstride], fr[td.nhead_off + 2 * td.cstride]);
     const int c0[3] = {cell_coord(ref.x, a.L[0], n[0]), cell_coord(ref.y, a.L[1], n[1]), cell_coord(ref.z, a.L[2], n[2])};
     const int *st = cell_start + (size_t)f * (cells_cap + 1);
-    const int *srt = sorted + (size_t)f * v.normal_heads.n;
+    const float4 *srt = sorted_pos + (size_t)f * v.normal_heads.n;
+    const float g0 = 0.99f * a.half[0], g1 = 0.99f * a.half[1], g2 = 0.99f * a.half[2];
+    const float r2max = v.dynamic_radius;
     int cnt = 0;
     double sx = 0, sy = 0, sz = 0, xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
     // with fewer than 3 cells along an axis the +-1 neighbours alias: visit every cell of that axis once
@@ -598,11 +604,12 @@ __global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, 
                 const int cz = n[2] >= 3 ? (c0[2] + dz + n[2]) % n[2] : dz;
                 const int c = (cx * n[1] + cy) * n[2] + cz;
                 for (int k = st[c]; k < st[c + 1]; k++) {
-                    const int i = srt[k];
-                    const int off = v.normal_heads.off[i], cs = v.normal_heads.cs[i];
-                    const f3 p = mk3(frame0[off], frame0[off + cs], frame0[off + 2 * (size_t)cs]);
-                    const f3 d = vector_to<true>(ref, p, bx);
-                    if (norm_ref(d) < v.dynamic_radius) {
+                    const float4 q = __ldg(srt + k);
+                    f3 d;   // Vector3D::vector_to(reference, head): same fold as everywhere (single-compare fast path)
+                    d.x = min_image_g(__fsub_rn(q.x, ref.x), a.L[0], a.half[0], g0);
+                    d.y = min_image_g(__fsub_rn(q.y, ref.y), a.L[1], a.half[1], g1);
+                    d.z = min_image_g(__fsub_rn(q.z, ref.z), a.L[2], a.half[2], g2);
+                    if (norm_ref(d) < r2max) {
                         cnt++;
                         sx += d.x; sy += d.y; sz += d.z;
                         xx += (double)d.x * d.x; xy += (double)d.x * d.y; xz += (double)d.x * d.z;
