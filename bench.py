@@ -244,6 +244,7 @@ def run_ours(args):
         if rank == 0:
             torch.cuda.synchronize()
             eng.write_block(red.data_ptr())
+    eng.fence()   # the tail (repair + fold) of the last batch runs on a helper stream: the closing event waits for it
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -254,6 +255,7 @@ def run_ours(args):
     hot_ms, hot_n = eng.profile_read()
     eng.profile(False)
     launches = eng.stats()["kernel_launches"] - l0
+    spec_stats = eng.speculation_stats()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -340,12 +342,13 @@ def run_ours(args):
                          "traffic": traffic, "kernel": "ua_order_kernel" if s.setup.kind == 2 else "bond_order_kernel", "launches_timed": hot_n, "avg_launch_ms": hot_ms / max(hot_n, 1),
                          "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
                          "step_share": (hot_ms / ms) if ms else None,
-                         "note": "in-step duration; with Global leaflets the centre kernels of the NEXT batch run concurrently on a second stream",
+                         "note": ("in-step duration; speculative Global leaflets: no centre pre-pass, the kernel runs alone" if spec_stats["enabled"] else
+                                  "in-step duration; with Global leaflets the centre kernels of the NEXT batch run concurrently on a second stream"),
                          "isolated": ({"avg_launch_ms": iso_ms / iso_n, "achieved": launch_bytes / (iso_ms / iso_n * 1e-3) / 1e9,
                                        "frac": launch_bytes / (iso_ms / iso_n * 1e-3) / 1e9 / peak} if iso_n else None)},
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{cpu_frames} frames of the same workload ({cpu_t:.1f} s), oracle port with {threads} OpenMP threads"},
-            "parity": parity, "total_samples_accumulated": total_samples,
+            "parity": parity, "total_samples_accumulated": total_samples, "speculative_leaflets": spec_stats,
         }
     eng.close()
     if world > 1:

@@ -15,7 +15,7 @@ SYMBOLS = [
     "gorder_gpu_submit_native", "gorder_gpu_submit_native_device", "gorder_gpu_reserve_frames", "gorder_gpu_set_leaflets", "gorder_gpu_sync",
     "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block", "gorder_gpu_stats",
     "gorder_gpu_read_block", "gorder_gpu_write_block", "gorder_gpu_profile", "gorder_gpu_profile_read",
-    "gorder_gpu_stream", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
+    "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_stream", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
 ]
 
 
@@ -47,6 +47,10 @@ def lib() -> C.CDLL:
     L.gorder_gpu_profile.argtypes = [vp, C.c_int]
     L.gorder_gpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.gorder_gpu_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.gorder_gpu_speculation_stats.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
+    L.gorder_gpu_speculation_stats.restype = C.c_int
+    L.gorder_gpu_fence.argtypes = [vp]
+    L.gorder_gpu_fence.restype = C.c_int
     L.gorder_gpu_stream.argtypes = [vp]
     L.gorder_gpu_stream.restype = vp
     L.gorder_gpu_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]

@@ -70,10 +70,13 @@ struct GorderHandle {
     unsigned long long *d_map_cnt = nullptr;
 
     // per-frame accumulators: ring of max_batch rows, or (timewise) all frames
-    long long *d_bsum = nullptr;
+    long long *d_bsum = nullptr;            // timewise: [tw_cap][n_slots][3] rows of every analysed frame
     unsigned long long *d_bcnt = nullptr;
     long long tw_cap = 0;
-    bool ring_owned = false;   // d_bcnt lives inside the d_bsum allocation
+    // otherwise one ring per staging slot: [max_batch rows of sums][max_batch rows of counts][flagged-frame counter]
+    long long *d_ring[2] = {nullptr, nullptr};
+    size_t ring_words = 0;
+    unsigned *d_nflag_tw = nullptr;         // [2] flagged-frame counters of the timewise mode
     std::vector<long long> frame_index_done;   // frame_index of every analysed frame, in order
 
     // staging (2-deep)
@@ -120,6 +123,12 @@ struct GorderHandle {
     unsigned *d_ticket = nullptr;
     cudaStream_t stream_pre = nullptr;             // frame setup + centre reduction of the next batch
     cudaEvent_t ev_pre[2] = {nullptr, nullptr};
+    // three-stage pipeline of the speculative path: pre (setup of batch k+1) | main (bond kernels back to back) |
+    // post (repair + fold of batch k-1)
+    cudaStream_t stream_post = nullptr;
+    cudaEvent_t ev_bond[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
+    cudaEvent_t ev_post_any = nullptr;             // last batch whose tail ran on the post stream
+    bool post_used = false;
     struct SegList { Seg *d = nullptr; int n = 0; };
     SegList seg_membrane[3], seg_geom[3];          // per axis
 
@@ -129,6 +138,17 @@ struct GorderHandle {
     size_t prof_used = 0;
     double prof_ms = 0.0;
     long long prof_n = 0;
+
+    // speculative Global leaflets (bond_order_kernel<SPEC> + spec_repair_kernel)
+    bool spec_ok = false, spec_disabled = false, spec_ref_valid = false;
+    int spec_cur = 0;
+    float *d_spec_ref = nullptr;            // [4] ring of provisional centres: batch k reads [k % 4], writes [(k + 1) % 4]
+    double *d_spec_sum = nullptr;           // [max_batch][n_chunks][2]
+    float *d_spec_mm = nullptr;             // [max_batch][n_chunks][4]
+    unsigned *d_spec_ticket = nullptr;      // [max_batch]
+    float *d_spec_center = nullptr;         // [max_batch]
+    unsigned char *d_spec_flag = nullptr;   // [max_batch]
+    unsigned *h_spec_counters = nullptr, *d_spec_counters = nullptr;   // mapped pinned: frames speculated, frames repaired
 
     // persistent pipeline (K1p)
     bool pipe_ok = false;
@@ -221,6 +241,16 @@ void launch_bond3(GorderHandle *h, dim3 grid, size_t smem, const float *planes, 
     else { if (h->nvec) launch_bond2<MPT, false, true>(h, grid, smem, planes, aux, o); else launch_bond2<MPT, false, false>(h, grid, smem, planes, aux, o); }
 }
 
+template <int MPT>
+void launch_bond_spec(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o) {
+    bond_order_kernel<MPT, true, false, true, false, true><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, h->d_normals,
+                                                                                             h->d_normal_npoints, o);
+}
+template <int MPT>
+void launch_repair(GorderHandle *h, cudaStream_t st, dim3 grid, const RepairParams &rp, const float *planes, const FrameAux *aux, AccumOut o, int nf) {
+    spec_repair_kernel<MPT><<<grid, kBlock, 0, st>>>(h->view, rp, planes, aux, o, nf);
+}
+
 template <bool PBC, bool NVEC>
 void launch_ua2(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o) {
 #define UA_L(L, E) ua_order_kernel<PBC, NVEC, L, E><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, h->d_normals, h->d_normal_npoints, o)
@@ -298,6 +328,8 @@ int grow_rows(GorderHandle *h, long long need) {
     CK(cudaMemsetAsync(ns, 0, cap * row * sizeof(long long), h->stream));
     CK(cudaMemsetAsync(nc, 0, cap * row * sizeof(unsigned long long), h->stream));
     if (h->d_bsum) {
+        CK(cudaStreamSynchronize(h->stream_post));
+        CK(cudaStreamSynchronize(h->stream_pre));
         CK(cudaMemcpyAsync(ns, h->d_bsum, h->n_frames * row * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
         CK(cudaMemcpyAsync(nc, h->d_bcnt, h->n_frames * row * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -363,8 +395,22 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
                              s.leaflet_freq <= std::max(1, s.step) && n_assign == nf && !getenv("GORDER_NO_INLINE_LEAFLETS");
     // Frames already resident on the device: frame setup and the centre passes of this batch go to the
     // pre stream and overlap the bond kernel of the previous batch (both are latency-, not HBM-bound).
-    const bool overlap = inline_leaf && !planes_on_main && !h->nvec && !getenv("GORDER_NO_OVERLAP");
-    cudaStream_t sp = overlap ? h->stream_pre : h->stream;
+    // ... and without any centre pre-pass when the speculative path applies (AccumOut::spec_*)
+    if (h->spec_ok && !h->spec_disabled) {   // frames that needed the exact centre so far (mapped counters, no sync)
+        const unsigned checked = h->h_spec_counters[0], repaired = h->h_spec_counters[1];
+        if (checked >= 16 && repaired * 8ull > checked) h->spec_disabled = true;   // thick membrane / thin water: pre-pass is cheaper
+    }
+    const bool spec = inline_leaf && h->spec_ok && !h->spec_disabled && !getenv("GORDER_NO_SPEC");
+    const bool overlap = inline_leaf && !spec && !planes_on_main && !h->nvec && !getenv("GORDER_NO_OVERLAP");
+    // speculative path on resident frames: the bond kernels of consecutive batches run back to back on the main stream,
+    // the setup of the next batch and the tail (repair + fold) of the previous one run beside them
+    const bool pipelined = spec && !planes_on_main && !s.collect_leaflets && !getenv("GORDER_NO_OVERLAP");
+    cudaStream_t sp = (overlap || pipelined) ? h->stream_pre : h->stream;
+    cudaStream_t spost = pipelined ? h->stream_post : h->stream;
+    if (!pipelined && h->post_used) CK(cudaStreamWaitEvent(h->stream, h->ev_post_any, 0));   // totals are touched by one stream at a time
+    long long *bsum = s.timewise ? h->d_bsum : h->d_ring[slot];
+    unsigned long long *bcnt = s.timewise ? h->d_bcnt : reinterpret_cast<unsigned long long *>(h->d_ring[slot] + h->ring_words);
+    unsigned *nflag = s.timewise ? h->d_nflag_tw + slot : reinterpret_cast<unsigned *>(h->d_ring[slot] + 2 * h->ring_words);
     CK(cudaMemcpyAsync(da, ha, sizeof(FrameAux) * nf, cudaMemcpyHostToDevice, sp));
     CK(cudaMemcpyAsync(h->d_list[slot], h->h_list[slot], sizeof(int) * (h->max_batch + nf), cudaMemcpyHostToDevice, sp));
 
@@ -380,7 +426,14 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         frame_setup_kernel<<<(nf + 63) / 64, 64, 0, sp>>>(h->view, da, d_box, nf, 1);
         h->n_launches++;
     }
-    if (inline_leaf) {
+    if (spec) {
+        if (!h->spec_ref_valid) {   // first batch: the provisional centre is the exact centre of its first frame
+            int rc = run_group_center(h, sp, h->seg_membrane, h->s.n_membrane, 1 << s.leaflet_axis, d_planes, da, dl_assign, 1);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(h->d_spec_ref + h->spec_cur % 4, h->d_center + s.leaflet_axis, sizeof(float), cudaMemcpyDeviceToDevice, sp));
+            h->spec_ref_valid = true;
+        }
+    } else if (inline_leaf) {
         int rc = run_group_center(h, sp, h->seg_membrane, h->s.n_membrane, 1 << s.leaflet_axis, d_planes, da, dl_assign, n_assign);
         if (rc) return rc;
     } else if (h->leaf && n_assign > 0 && !use_pipe) {
@@ -392,7 +445,17 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         leaflet_assign_kernel<<<grid, 256, 0, sp>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_molpad_type, h->d_leaf_rows);
         h->n_launches++;
     }
-    if (overlap) {
+    // per-frame accumulator rows
+    const size_t row = (size_t)h->n_slots * 3;
+    if (s.timewise) {
+        int rc = grow_rows(h, h->n_frames + nf);
+        if (rc) return rc;
+        bsum = h->d_bsum; bcnt = h->d_bcnt;
+        if (spec) CK(cudaMemsetAsync(nflag, 0, sizeof(unsigned), sp));
+    } else {
+        CK(cudaMemsetAsync(bsum, 0, (2 * h->ring_words + 2) * sizeof(long long), sp));   // includes the flagged-frame counter
+    }
+    if (overlap || pipelined) {
         CK(cudaEventRecord(h->ev_pre[slot], sp));
         CK(cudaStreamWaitEvent(h->stream, h->ev_pre[slot], 0));
     }
@@ -418,18 +481,15 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         h->n_launches++;
         if (h->d_normal_used) CK(cudaMemsetAsync(h->d_normal_used, 0, (size_t)nf * h->n_molpad, h->stream));
     }
-    // per-frame accumulator rows
-    const size_t row = (size_t)h->n_slots * 3;
-    if (s.timewise) {
-        int rc = grow_rows(h, h->n_frames + nf);
-        if (rc) return rc;
-    } else {
-        CK(cudaMemsetAsync(h->d_bsum, 0, 2 * (size_t)h->max_batch * row * sizeof(long long), h->stream));
+    AccumOut o{};
+    o.inline_center = (inline_leaf && !spec) ? h->d_center : nullptr;
+    if (spec) {
+        o.spec_ref = h->d_spec_ref + h->spec_cur % 4; o.spec_ref_next = h->d_spec_ref + (h->spec_cur + 1) % 4;
+        o.spec_sum = h->d_spec_sum; o.spec_mm = h->d_spec_mm; o.spec_ticket = h->d_spec_ticket; o.spec_center = h->d_spec_center + (size_t)slot * h->max_batch;
+        o.spec_flag = h->d_spec_flag + (size_t)slot * h->max_batch; o.spec_nflag = nflag; o.n_membrane = s.n_membrane;
     }
-    AccumOut o;
-    o.inline_center = inline_leaf ? h->d_center : nullptr;
     o.leaf_out = (inline_leaf && s.collect_leaflets) ? h->d_leaf_rows : nullptr;
-    o.bsum = h->d_bsum; o.bcnt = h->d_bcnt; o.map_sum = h->d_map_sum; o.map_cnt = h->d_map_cnt; o.normal_used = h->d_normal_used;
+    o.bsum = bsum; o.bcnt = bcnt; o.map_sum = h->d_map_sum; o.map_cnt = h->d_map_cnt; o.normal_used = h->d_normal_used;
     dim3 grid(h->n_chunks, nf);
     const size_t smem = accum_smem(h);
     if (use_pipe) CK(cudaMemsetAsync(h->d_pipe_ctrl, 0, (4 * (size_t)h->max_batch + 1) * sizeof(unsigned), h->stream));
@@ -456,17 +516,42 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         if (h->mpt == 4) global_leaflet_pipeline_kernel<4><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
         else if (h->mpt == 2) global_leaflet_pipeline_kernel<2><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
         else global_leaflet_pipeline_kernel<1><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
+    } else if (spec) {
+        if (h->mpt == 4) launch_bond_spec<4>(h, grid, smem, d_planes, da, o);
+        else if (h->mpt == 2) launch_bond_spec<2>(h, grid, smem, d_planes, da, o);
+        else launch_bond_spec<1>(h, grid, smem, d_planes, da, o);
     } else if (h->ua) launch_ua(h, grid, smem, d_planes, da, o);
     else if (h->mpt == 4) launch_bond3<4>(h, grid, smem, d_planes, da, o);
     else if (h->mpt == 2) launch_bond3<2>(h, grid, smem, d_planes, da, o);
     else launch_bond3<1>(h, grid, smem, d_planes, da, o);
     h->n_launches++;
     if (pe) CK(cudaEventRecord(pe->second, h->stream));
+    if (pipelined) {
+        CK(cudaEventRecord(h->ev_bond[slot], h->stream));
+        CK(cudaStreamWaitEvent(spost, h->ev_bond[slot], 0));
+    }
+    if (spec) {   // frames whose leaflets are not provably those of the exact centre (normally none: the kernel returns at once)
+        RepairParams rp;
+        rp.segs = h->seg_membrane[s.leaflet_axis].d; rp.n_segs = h->seg_membrane[s.leaflet_axis].n;
+        rp.n_blocks = std::max(1, std::min(kCenterBlocks, rp.n_segs)); rp.n_group = s.n_membrane;
+        rp.ref = o.spec_ref; rp.flag = o.spec_flag; rp.nflag = nflag; rp.center = h->d_spec_center + (size_t)slot * h->max_batch;
+        rp.host_counters = h->d_spec_counters; rp.leaf_out = o.leaf_out;
+        dim3 rg(h->n_chunks, std::min(nf, 4));
+        if (h->mpt == 4) launch_repair<4>(h, spost, rg, rp, d_planes, da, o, nf);
+        else if (h->mpt == 2) launch_repair<2>(h, spost, rg, rp, d_planes, da, o, nf);
+        else launch_repair<1>(h, spost, rg, rp, d_planes, da, o, nf);
+        h->n_launches++;
+        h->spec_cur = (h->spec_cur + 1) % 4;
+    }
     if (h->n_slots > 0)
-        fold_kernel<<<h->n_slots, 128, 0, h->stream>>>(h->n_slots, nf, h->leaf ? 1 : 0, h->d_bsum + row0 * row, h->d_bcnt + row0 * row,
-                                                                  h->d_tot_sum, h->d_tot_cnt);
+        fold_kernel<<<h->n_slots, 128, 0, spost>>>(h->n_slots, nf, h->leaf ? 1 : 0, bsum + row0 * row, bcnt + row0 * row, h->d_tot_sum, h->d_tot_cnt);
     h->n_launches++;
     CK(cudaGetLastError());
+    if (pipelined) {
+        CK(cudaEventRecord(h->ev_post[slot], spost));
+        CK(cudaEventRecord(h->ev_post_any, spost));
+        h->post_used = true;
+    }
     if (h->leaf && n_assign > 0 && s.collect_leaflets) {
         int rc = grow_collect(h, &h->d_leaf_collect, &h->leaf_collect_cap, h->n_leaf_collected, h->n_leaf_collected + n_assign, (size_t)h->n_molpad);
         if (rc) return rc;
@@ -517,8 +602,8 @@ void gorder_gpu_destroy(GorderHandle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     for (void *p : h->owned) cudaFree(p);
-    cudaFree(h->d_bsum);
-    if (!h->ring_owned) cudaFree(h->d_bcnt);
+    if (h->stream_post) cudaStreamSynchronize(h->stream_post);
+    cudaFree(h->d_bsum); cudaFree(h->d_bcnt);
     cudaFree(h->d_leaf_collect); cudaFree(h->d_normals_collect); cudaFree(h->d_used_collect);
     for (int i = 0; i < 2; i++) {
         cudaFree(h->d_xyz[i]);
@@ -527,11 +612,18 @@ void gorder_gpu_destroy(GorderHandle *h) {
         if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     }
+    if (h->h_spec_counters) cudaFreeHost(h->h_spec_counters);
     for (auto &e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream_pre) { cudaStreamSynchronize(h->stream_pre); cudaStreamDestroy(h->stream_pre); }
-    for (int i = 0; i < 2; i++) if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
+    if (h->stream_post) cudaStreamDestroy(h->stream_post);
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
+        if (h->ev_bond[i]) cudaEventDestroy(h->ev_bond[i]);
+        if (h->ev_post[i]) cudaEventDestroy(h->ev_post[i]);
+    }
+    if (h->ev_post_any) cudaEventDestroy(h->ev_post_any);
     delete h;
 }
 
@@ -574,6 +666,16 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     long long off = 0;
     int slot = 0, molpad = 0, mol = 0;
     auto bad_rel = [&](int r) { return r < 0; };
+    // speculative Global leaflets need every membrane atom to pass through the bond kernel's registers exactly
+    // once: the membrane must be a union of whole planes (relative atom u of ALL molecules of a type) that some
+    // bond loads.  The first bond item that loads such a plane carries the "count it" bit.
+    std::vector<char> in_mem(s->n_atoms, 0);
+    bool mem_cover = !ua && s->leaflet_mode == GORDER_LEAFLET_GLOBAL && s->n_membrane > 0 && s->membrane;
+    for (int i = 0; mem_cover && i < s->n_membrane; i++) {
+        const int a = s->membrane[i];
+        if (a < 0 || a >= s->n_atoms || in_mem[a]) mem_cover = false; else in_mem[a] = 1;
+    }
+    long long mem_counted = 0;
     for (int t = 0; t < s->n_moltypes; t++) {
         const GorderMolType &m = s->moltypes[t];
         if (m.n_molecules <= 0 || !m.mol_base) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "molecule type without molecules"); return h->err_code; }
@@ -626,14 +728,24 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
             td.n_orders = k;
         } else {
             td.item_off = (int)bonds.size(); td.n_items = m.n_bond_types; td.n_orders = m.n_bond_types;
+            std::vector<char> plane_mem(used.size(), 0), plane_done(used.size(), 0);
+            for (size_t u = 0; mem_cover && u < used.size(); u++) {
+                int cnt = 0;
+                for (int mm = 0; mm < m.n_molecules; mm++) cnt += in_mem[m.mol_base[mm] + used[u]];
+                if (cnt == m.n_molecules) plane_mem[u] = 1; else if (cnt != 0) mem_cover = false;
+            }
             for (int i = 0; i < m.n_bond_types; i++) {
                 // plane offsets are multiples of 32: the two low bits of a_off carry the register-reuse hint
                 int reuse = 0;
                 if (i > 0 && m.bond_rel[2 * i] == m.bond_rel[2 * (i - 1)]) reuse = 1;            // same first atom as the previous bond
                 else if (i > 0 && m.bond_rel[2 * i] == m.bond_rel[2 * (i - 1) + 1]) reuse = 2;   // previous bond's second atom
-                bonds.push_back(BondItem{u_of(m.bond_rel[2 * i]) * td.tile + reuse, u_of(m.bond_rel[2 * i + 1]) * td.tile});
+                const int ua_ = u_of(m.bond_rel[2 * i]), ub_ = u_of(m.bond_rel[2 * i + 1]);
+                if (plane_mem[ua_] && !plane_done[ua_]) { reuse |= 4; plane_done[ua_] = 1; mem_counted += m.n_molecules; }
+                if (plane_mem[ub_] && !plane_done[ub_]) { reuse |= 8; plane_done[ub_] = 1; mem_counted += m.n_molecules; }
+                bonds.push_back(BondItem{ua_ * td.tile + reuse, ub_ * td.tile});
                 islots.push_back(m.bond_rel[2 * i]);
             }
+            for (size_t u = 0; u < used.size(); u++) if (plane_mem[u] && !plane_done[u]) mem_cover = false;   // a membrane atom no bond loads
         }
         td.manual_leaf_off = -1; td.n_manual_leaf = 0; td.manual_norm_off = -1; td.n_manual_norm = 0;
         if (m.manual_leaflets && m.n_manual_leaflet_frames > 0) {
@@ -747,10 +859,11 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     h->d_map_cnt = reinterpret_cast<unsigned long long *>(h->d_block + 2 * na + na * v.map.n_bins);
     if (!s->timewise) {
         // one allocation: [max_batch rows of sums][max_batch rows of counts] -> a single memset per batch
-        const size_t ring = std::max<size_t>(1, (size_t)h->max_batch * na);
-        CK(cudaMalloc((void **)&h->d_bsum, 2 * ring * sizeof(long long)));
-        h->d_bcnt = reinterpret_cast<unsigned long long *>(h->d_bsum + ring);
-        h->ring_owned = true;
+        h->ring_words = std::max<size_t>(1, (size_t)h->max_batch * na);
+        for (int i = 0; i < 2; i++)
+            if ((rc = dev_alloc(h, &h->d_ring[i], 2 * h->ring_words + 2, true))) return rc;
+    } else {
+        if ((rc = dev_alloc(h, &h->d_nflag_tw, 2, true))) return rc;
     }
 
     // ---- per-batch buffers -------------------------------------------------------------------------
@@ -798,6 +911,29 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&h->stream_pre, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&h->stream_post, cudaStreamNonBlocking, hi));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&h->ev_bond[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_post[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&h->ev_post_any, cudaEventDisableTiming));
+    }
+
+    // speculative Global leaflets: AA/CG, static normal along the leaflet axis, PBC, assignment on every analysed frame,
+    // no geometry / maps, membrane covered by the bond kernel's loads (above)
+    h->spec_ok = mem_cover && mem_counted == s->n_membrane && !ua && !h->nvec && !h->extra && s->handle_pbc &&
+                 s->leaflet_mode == GORDER_LEAFLET_GLOBAL && s->leaflet_freq_kind == GORDER_FREQ_EVERY && s->leaflet_freq <= std::max(1, s->step) &&
+                 s->leaflet_axis == s->normal_axis && h->n_chunks > 0 && !getenv("GORDER_NO_SPEC");
+    if (h->spec_ok) {
+        if ((rc = dev_alloc(h, &h->d_spec_ref, 4, true))) return rc;
+        if ((rc = dev_alloc(h, &h->d_spec_sum, 2 * B * (size_t)h->n_chunks))) return rc;
+        if ((rc = dev_alloc(h, &h->d_spec_mm, B * (size_t)h->n_chunks * 4))) return rc;
+        if ((rc = dev_alloc(h, &h->d_spec_ticket, B, true))) return rc;
+        if ((rc = dev_alloc(h, &h->d_spec_center, 2 * B, true))) return rc;
+        if ((rc = dev_alloc(h, &h->d_spec_flag, 2 * B, true))) return rc;
+        CK(cudaHostAlloc((void **)&h->h_spec_counters, 2 * sizeof(unsigned), cudaHostAllocMapped));
+        h->h_spec_counters[0] = h->h_spec_counters[1] = 0;
+        CK(cudaHostGetDevicePointer((void **)&h->d_spec_counters, h->h_spec_counters, 0));
     }
 
     // persistent pipeline: AA/CG, static normal, PBC, Global leaflets on every analysed frame, no geometry / maps
@@ -854,6 +990,15 @@ int gorder_gpu_create(const GorderSetup *setup, GorderHandle **out) {
     return GORDER_OK;
 }
 
+// everything queued by this handle, on all of its streams (the tail of a batch may run on the post stream)
+static int sync_all(GorderHandle *h) {
+    CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaStreamSynchronize(h->stream_pre));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->stream_post));
+    return GORDER_OK;
+}
+
 // first deferred device error -> host error state
 static int poll_device_error(GorderHandle *h) {
     int code[2] = {0, 0};
@@ -877,6 +1022,7 @@ static int begin_slot(GorderHandle *h, int *slot) {
     *slot = h->cur;
     h->cur ^= 1;
     CK(cudaEventSynchronize(h->ev_stage_free[*slot]));
+    CK(cudaEventSynchronize(h->ev_post[*slot]));   // tail of the batch that used this slot (post stream)
     return GORDER_OK;
 }
 
@@ -997,8 +1143,7 @@ int gorder_gpu_sync(GorderHandle *h) {
     if (!h) return GORDER_ERR_INVALID_ARGUMENT;
     if (h->err_code) return h->err_code;
     cudaSetDevice(h->device);
-    CK(cudaStreamSynchronize(h->copy_stream));
-    CK(cudaStreamSynchronize(h->stream_pre));
+    if (int rc = sync_all(h)) return rc;
     return poll_device_error(h);
 }
 
@@ -1062,7 +1207,7 @@ int gorder_gpu_finish(GorderHandle *h, GorderResults *r) {
 int gorder_gpu_accumulator_block(GorderHandle *h, void **d_ptr, int64_t *n_words) {
     if (!h || !d_ptr || !n_words) return GORDER_ERR_INVALID_ARGUMENT;
     cudaSetDevice(h->device);
-    CK(cudaStreamSynchronize(h->stream));
+    if (int rc = sync_all(h)) return rc;
     *d_ptr = h->d_block; *n_words = h->block_words;
     return GORDER_OK;
 }
@@ -1070,6 +1215,7 @@ int gorder_gpu_accumulator_block(GorderHandle *h, void **d_ptr, int64_t *n_words
 int gorder_gpu_read_block(GorderHandle *h, void *d_dst) {
     if (!h || !d_dst) return GORDER_ERR_INVALID_ARGUMENT;
     cudaSetDevice(h->device);
+    if (int rc = sync_all(h)) return rc;
     CK(cudaMemcpyAsync(d_dst, h->d_block, (size_t)h->block_words * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return GORDER_OK;
@@ -1078,6 +1224,7 @@ int gorder_gpu_read_block(GorderHandle *h, void *d_dst) {
 int gorder_gpu_write_block(GorderHandle *h, const void *d_src) {
     if (!h || !d_src) return GORDER_ERR_INVALID_ARGUMENT;
     cudaSetDevice(h->device);
+    if (int rc = sync_all(h)) return rc;
     CK(cudaMemcpyAsync(h->d_block, d_src, (size_t)h->block_words * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return GORDER_OK;
@@ -1117,6 +1264,23 @@ int gorder_gpu_stats(GorderHandle *h, int64_t *kernel_launches, int64_t *frames)
     if (!h) return GORDER_ERR_INVALID_ARGUMENT;
     if (kernel_launches) *kernel_launches = h->n_launches;
     if (frames) *frames = h->n_frames;
+    return GORDER_OK;
+}
+
+int gorder_gpu_speculation_stats(GorderHandle *h, int32_t *enabled, int64_t *frames_speculated, int64_t *frames_repaired) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    if (int rc = sync_all(h)) return rc;
+    if (enabled) *enabled = (h->spec_ok && !h->spec_disabled) ? 1 : 0;
+    if (frames_speculated) *frames_speculated = h->h_spec_counters ? h->h_spec_counters[0] : 0;
+    if (frames_repaired) *frames_repaired = h->h_spec_counters ? h->h_spec_counters[1] : 0;
+    return GORDER_OK;
+}
+
+int gorder_gpu_fence(GorderHandle *h) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    if (h->post_used) CK(cudaStreamWaitEvent(h->stream, h->ev_post_any, 0));
     return GORDER_OK;
 }
 

@@ -216,32 +216,25 @@ __global__ void frame_setup_kernel(DeviceView v, FrameAux *aux, const float *__r
 // ---------------------------------------------------------------------------------------------
 constexpr int kCenterBlocks = 64;
 
-__global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Seg *__restrict__ segs, int n_segs, int n_group, int axis,
-                                                          const float *__restrict__ planes, const FrameAux *__restrict__ aux,
-                                                          const int *__restrict__ frame_list, float *__restrict__ est,
-                                                          float *__restrict__ center, double *__restrict__ partial,
-                                                          unsigned *__restrict__ ticket, int pass) {
-    const int fi = blockIdx.y, f = frame_list[fi];
-    const float *fr = planes + (size_t)f * v.frame_floats;
-    const float L = aux[f].L[axis], half = aux[f].half[axis];
-    const bool pbc = v.handle_pbc != 0;
+// sums of one virtual block `vb` of center_axis_kernel (256 threads), result in thread 0 after the reduction
+__device__ __forceinline__ void center_block_sums(const Seg *__restrict__ segs, int n_segs, int vb, int n_blocks, const float *__restrict__ fr,
+                                                  bool pbc, int pass, float scale, float e, float L, float half, double (&s_red)[2][8],
+                                                  double &t0, double &t1) {
     float a0 = 0.0f, a1 = 0.0f;
-    const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
-    const float e = (pbc && pass == 1) ? est[3 * fi + axis] : 0.0f;
     const unsigned long long pol = l2_policy_evict_last();
     const float guard = 0.99f * half;
     auto add = [&](float p) {
         if (!pbc) a0 += p;
         else if (pass == 0) {
             float sn, cs;
-            __sincosf(p * scale, &sn, &cs);   // the estimate only seeds the refinement pass
+            __sincosf(p * scale, &sn, &cs);
             a0 += cs; a1 += sn;
         } else a0 += min_image_g(__fsub_rn(p, e), L, half, guard);
     };
-    for (int sg = blockIdx.x; sg < n_segs; sg += gridDim.x) {
+    for (int sg = vb; sg < n_segs; sg += n_blocks) {
         const Seg sgm = segs[sg];
         const float *src = fr + sgm.off;
-        if ((((size_t)src) & 15) == 0) {   // 16-byte aligned run: 128-bit loads, 4 in flight per thread
+        if ((((size_t)src) & 15) == 0) {
             const int n4 = sgm.len >> 2;
             const float4 *s4 = reinterpret_cast<const float4 *>(src);
             int i = threadIdx.x;
@@ -257,18 +250,35 @@ __global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Se
             for (int i = threadIdx.x; i < sgm.len; i += blockDim.x) add(__ldg(src + i));
         }
     }
-    __shared__ double s_red[2][8];
-    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double x0 = a0, x1 = a1;
     for (int o = 16; o > 0; o >>= 1) { x0 += __shfl_down_sync(0xffffffffu, x0, o); x1 += __shfl_down_sync(0xffffffffu, x1, o); }
+    __syncthreads();   // s_red may still be read from the previous call
     if (lane == 0) { s_red[0][warp] = x0; s_red[1][warp] = x1; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double t0 = 0, t1 = 0;
+    t0 = 0; t1 = 0;
+    if (threadIdx.x == 0)
         for (int w = 0; w < 8; w++) { t0 += s_red[0][w]; t1 += s_red[1][w]; }
+}
+
+__global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Seg *__restrict__ segs, int n_segs, int n_group, int axis,
+                                                          const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                          const int *__restrict__ frame_list, float *__restrict__ est,
+                                                          float *__restrict__ center, double *__restrict__ partial,
+                                                          unsigned *__restrict__ ticket, int pass) {
+    const int fi = blockIdx.y, f = frame_list[fi];
+    const float *fr = planes + (size_t)f * v.frame_floats;
+    const float L = aux[f].L[axis], half = aux[f].half[axis];
+    const bool pbc = v.handle_pbc != 0;
+    const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
+    const float e = (pbc && pass == 1) ? est[3 * fi + axis] : 0.0f;
+    __shared__ double s_red[2][8];
+    __shared__ bool s_last;
+    double b0, b1;
+    center_block_sums(segs, n_segs, blockIdx.x, gridDim.x, fr, pbc, pass, scale, e, L, half, s_red, b0, b1);
+    if (threadIdx.x == 0) {
         double *pp = partial + ((size_t)fi * gridDim.x + blockIdx.x) * 2;
-        pp[0] = t0; pp[1] = t1;
+        pp[0] = b0; pp[1] = b1;
         __threadfence();
         s_last = atomicAdd(&ticket[fi], 1u) == gridDim.x - 1;
     }
@@ -674,6 +684,18 @@ struct AccumOut {
     long long *map_sum;             // [n_slots][3][n_bins]
     unsigned long long *map_cnt;
     unsigned char *normal_used;     // [F][n_molpad] or nullptr
+    // speculative Global leaflets (SPEC): classify against the provisional centre *spec_ref while the
+    // kernel sums the membrane's displacements from it; the last CTA of a frame derives the frame's true
+    // centre and flags the frame for spec_repair_kernel when a head could change sides.
+    const float *spec_ref;          // [1] provisional centre along the leaflet axis
+    float *spec_ref_next;           // [1] provisional centre of the next batch (centre of this batch's last frame)
+    double *spec_sum;               // [F][n_chunks][2] sum d, sum d^2 (d = min-image displacement from *spec_ref)
+    float *spec_mm;                 // [F][n_chunks][4] max |d|, min |d_head|, max |d_head|, NaN seen
+    unsigned *spec_ticket;          // [F] CTAs of the frame that have published their partials (self-resetting)
+    float *spec_center;             // [F] centre derived from the partials
+    unsigned char *spec_flag;       // [F] 1 = the frame needs the exact centre (repair)
+    unsigned *spec_nflag;           // [1] flagged frames of this batch
+    int n_membrane;
 };
 
 // number of int accumulators per order slot in shared memory
@@ -749,7 +771,8 @@ __device__ __forceinline__ void map_add(const DeviceView &v, const AccumOut &o, 
 // template: MPT molecules per thread; PBC; NVEC per-molecule normal vector (dynamic / manual)
 //           instead of a static axis; LEAF per-leaflet accumulation; EXTRA geometry filter / maps.
 // ---------------------------------------------------------------------------------------------
-template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA>
+//           SPEC speculative Global leaflets: no centre pre-pass (see AccumOut::spec_*).
+template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA, bool SPEC = false>
 __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                             const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
                                                             const int *__restrict__ normal_npoints, AccumOut o) {
@@ -786,12 +809,25 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
     int upmask[MPT];
     f3 nrm[MPT];
     int nvalid = 0, nup = 0;
+    // SPEC: provisional centre, |head - centre| extremes of this thread's molecules
+    const float sref = SPEC ? __ldg(o.spec_ref) : 0.0f;
+    float hmin = CUDART_INF_F, hmax = 0.0f;
+    bool hnan = false;
 #pragma unroll
     for (int j = 0; j < MPT; j++) {
         valid[j] = active && (m0 + j < td.n_mol);
         bool up = false;
         if (LEAF && valid[j]) {
-            if (o.inline_center) {
+            if (SPEC) {
+                const int la = v.leaflet_axis;
+                const float hd = __ldg(base_mol + td.head_off + la * mpad + j);
+                const float dh = distance_1d(hd, sref, ax.L[la], ax.half[la], PBC);
+                up = dh >= 0.0f;
+                hmin = fminf(hmin, fabsf(dh)); hmax = fmaxf(hmax, fabsf(dh));
+                hnan = hnan || dh != dh;   // NaN head: the frame is flagged and the exact path reports it
+                if (v.leaflet_flip) up = !up;
+                if (o.leaf_out) o.leaf_out[(size_t)(1 + f) * v.n_molpad + td.molpad0 + m0 + j] = up ? GORDER_UPPER : GORDER_LOWER;
+            } else if (o.inline_center) {
                 const int la = v.leaflet_axis;
                 const float c = o.inline_center[3 * f + la];
                 if (c != c) raise_error(v, GORDER_ERR_INVALID_GLOBAL_CENTER, ax.frame_index);
@@ -819,6 +855,30 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
 #pragma unroll
     for (int j = 0; j < MPT; j++) any_used[j] = false;
     float nan_acc = 0.0f;   // NaN coordinates poison this accumulator (checked once after the loop)
+    // SPEC: head extremes of the CTA -> shared (frees the registers for the loop)
+    __shared__ float s_hmm[2][kWarps];
+    __shared__ double s_dsum[2][kWarps];
+    __shared__ float s_dabs[kWarps];
+    if (SPEC) {
+        float a = hnan ? CUDART_NAN_F : hmin, b = hmax;
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            const float a2 = __shfl_xor_sync(0xffffffffu, a, ofs), b2 = __shfl_xor_sync(0xffffffffu, b, ofs);
+            a = (a != a || a2 != a2) ? CUDART_NAN_F : fminf(a, a2); b = fmaxf(b, b2);
+        }
+        if (lane == 0) { s_hmm[0][warp] = a; s_hmm[1][warp] = b; }
+    }
+    // SPEC: displacement of the membrane atoms from the provisional centre, d = t - L rint(t / L)
+    // (any periodic image), summed per thread in f32 (<= 2 MPT n_items terms), across threads in f64.
+    const float sp_invL = (SPEC && L2 > 0.0f) ? __frcp_rn(L2) : 0.0f;
+    float dsum = 0.0f, dsq = 0.0f, dabs = 0.0f;   // sum d, sum d^2, max |d|
+    auto spec_add = [&](float z, bool ok) {
+        const float t = z - sref;
+        const float k = __fadd_rn(fmaf(t, sp_invL, 12582912.0f), -12582912.0f);
+        float d = fmaf(-L2, k, t);
+        d = ok ? d : 0.0f;
+        dsum += d; dsq = fmaf(d, d, dsq); dabs = fmaxf(dabs, fabsf(d));
+    };
 
     const float *base = base_mol;
     // Software pipeline (streaming variant): the planes of bond b+1 are requested before bond b is
@@ -834,7 +894,7 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
     }
     if (PREFETCH && nb > 0 && active) {
         const BondItem b0 = s_bonds[0];
-        const int a_off = b0.a_off & ~3;
+        const int a_off = b0.a_off & ~15;
         nx1.load(base + a_off + o0); ny1.load(base + a_off + o1); nz1.load(base + a_off + o2);
         nx2.load(base + b0.b_off + o0); ny2.load(base + b0.b_off + o1); nz2.load(base + b0.b_off + o2);
     }
@@ -845,7 +905,7 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
             // ... and the next bond's planes are requested now
             if (b + 1 < nb) {
                 const BondItem bn = s_bonds[b + 1];
-                const int reuse = bn.a_off & 3, a_off = bn.a_off & ~3;
+                const int reuse = bn.a_off & 3, a_off = bn.a_off & ~15;
                 if (reuse == 2) { nx1 = x2; ny1 = y2; nz1 = z2; }       // next first atom = this bond's second atom
                 // reuse == 1: next first atom = this bond's first atom (nx1 already holds it)
                 if (active) {
@@ -855,8 +915,9 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
             }
         } else {
             const BondItem bi = s_bonds[b];
-            // low bits of a_off: 1 = first atom is the previous bond's first atom, 2 = ... second atom
-            const int reuse = bi.a_off & 3, a_off = bi.a_off & ~3;
+            // low bits of a_off: 1 = first atom is the previous bond's first atom, 2 = ... second atom;
+            // 4 / 8 = first / second atom is a membrane atom seen here for the first time (speculative centre)
+            const int reuse = bi.a_off & 3, a_off = bi.a_off & ~15;
             if (reuse == 2) { x1 = x2; y1 = y2; z1 = z2; }
             if (active) {
                 if (v.l2_hints) {   // stream through L2 without displacing the axis planes the centre passes keep there
@@ -866,6 +927,17 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
                     if (reuse == 0) { x1.load(base + a_off + o0); y1.load(base + a_off + o1); z1.load(base + a_off + o2); }
                     x2.load(base + bi.b_off + o0); y2.load(base + bi.b_off + o1); z2.load(base + bi.b_off + o2);
                 }
+            }
+        }
+        if (SPEC) {
+            const int cf = PREFETCH ? 0 : s_bonds[b].a_off;
+            if (cf & 4) {
+#pragma unroll
+                for (int j = 0; j < MPT; j++) spec_add(z1.v[j], valid[j]);
+            }
+            if (cf & 8) {
+#pragma unroll
+                for (int j = 0; j < MPT; j++) spec_add(z2.v[j], valid[j]);
             }
         }
         int st = 0, su = 0, ct = 0, cu = 0;   // total / upper (lower = total - upper)
@@ -940,8 +1012,164 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
         for (int j = 0; j < MPT; j++)
             if (valid[j] && any_used[j]) o.normal_used[(size_t)f * v.n_molpad + td.molpad0 + m0 + j] = 1;
     }
+    if (SPEC) {
+        double ds = (double)dsum, dq = (double)dsq;
+        float a = dabs;
+        if (dsum != dsum) a = dsum;   // NaN / Inf coordinate: poison the extent so that the frame is flagged
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            ds += __shfl_xor_sync(0xffffffffu, ds, ofs); dq += __shfl_xor_sync(0xffffffffu, dq, ofs);
+            const float a2 = __shfl_xor_sync(0xffffffffu, a, ofs);
+            a = (a != a || a2 != a2) ? CUDART_NAN_F : fmaxf(a, a2);
+        }
+        if (lane == 0) { s_dsum[0][warp] = ds; s_dsum[1][warp] = dq; s_dabs[warp] = a; }
+    }
     __syncthreads();
     cta_flush<LEAF, EXTRA>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
+    if (SPEC && threadIdx.x == 0) {
+        // publish this CTA's partials; the last CTA of the frame adds them in chunk order (deterministic)
+        double ds = 0.0, dq = 0.0;
+        float p0 = 0.0f, p1 = CUDART_INF_F, p2 = 0.0f;
+        bool bad = false;
+        for (int w = 0; w < kWarps; w++) {
+            ds += s_dsum[0][w]; dq += s_dsum[1][w];
+            bad = bad || s_dabs[w] != s_dabs[w] || s_hmm[0][w] != s_hmm[0][w];
+            p0 = fmaxf(p0, s_dabs[w]); p1 = fminf(p1, s_hmm[0][w]); p2 = fmaxf(p2, s_hmm[1][w]);
+        }
+        const size_t pi = (size_t)f * gridDim.x + blockIdx.x;
+        o.spec_sum[2 * pi] = ds; o.spec_sum[2 * pi + 1] = dq;
+        reinterpret_cast<float4 *>(o.spec_mm)[pi] = make_float4(p0, p1, p2, bad ? 1.0f : 0.0f);
+        __threadfence();
+        if (atomicAdd(&o.spec_ticket[f], 1u) == gridDim.x - 1) {
+            __threadfence();
+            o.spec_ticket[f] = 0;
+            double tot = 0.0, tot2 = 0.0;
+            float dmax = 0.0f, hmn = CUDART_INF_F, hmx = 0.0f;
+            bool nan = false;
+            for (unsigned c = 0; c < gridDim.x; c++) {
+                const size_t qi = (size_t)f * gridDim.x + c;
+                tot += __ldcg(o.spec_sum + 2 * qi); tot2 += __ldcg(o.spec_sum + 2 * qi + 1);
+                const float4 m4 = __ldcg(reinterpret_cast<const float4 *>(o.spec_mm) + qi);
+                nan = nan || m4.w != 0.0f;
+                dmax = fmaxf(dmax, m4.x); hmn = fminf(hmn, m4.y); hmx = fmaxf(hmx, m4.z);
+            }
+            // group_get_center = wrap(est + mean(min_image(z - est))), est = circular mean of the membrane.
+            // With d_i = min_image(z_i - sref) this equals wrap(sref + mean d) (up to f32 rounding) as long as
+            // every atom keeps its periodic image when seen from est instead of sref:
+            //     |est - sref| < L/2 - max|d_i|.
+            // est is not computed; it is bounded from the moments: with t_i = 2 pi d_i / L, T = max|t_i|,
+            //     sum cos t_i >= N - S2/2,  |sum sin t_i| <= |S1| + T S2 / 6     (S1 = sum t_i, S2 = sum t_i^2)
+            // so |est - sref| <= atan2(|S1| + T S2/6, N - S2/2) L / 2 pi whenever N - S2/2 > 0.
+            // The leaflets are those of the exact centre if no head lies within |delta| (+ margin) of sref or
+            // of the far cut sref + L/2.
+            const double n = (double)o.n_membrane;
+            const float delta = (float)(tot / n);
+            const float margin = 1e-4f + 1e-3f * L2;
+            const double ts = 6.283185307179586 / (double)L2;
+            const double s1 = fabs(tot) * ts, s2 = tot2 * ts * ts, x_lo = n - 0.5 * s2, y_hi = s1 + (double)dmax * ts * s2 / 6.0;
+            const float est_bound = x_lo > 0.0 ? (float)(atan2(y_hi, x_lo) / ts) : CUDART_INF_F;
+            const bool ok = !nan && o.n_membrane > 0 && L2 > 0.0f && (delta == delta) && est_bound + margin < h2 - dmax &&
+                            fabsf(delta) + margin < hmn && hmx + fabsf(delta) + margin < h2;
+            const float c = wrap1(__fadd_rn(sref, delta), L2);
+            o.spec_center[f] = ok ? c : CUDART_NAN_F;
+            o.spec_flag[f] = ok ? 0 : 1;
+            if (!ok) atomicAdd(o.spec_nflag, 1u);
+            if (f == (int)gridDim.y - 1) *o.spec_ref_next = ok ? c : sref;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// spec_repair_kernel: frames whose speculative leaflets are not provably those of the exact centre.
+// grid (n_chunks, R); CTA (x, y) visits the flagged frames y, y + R, ...: it recomputes the exact centre
+// with the arithmetic of center_axis_kernel (same partial sums in the same order; every CTA of the column
+// does so redundantly -- this is the rare path), re-classifies the molecules of chunk x and moves the
+// samples of every molecule that changes sides from one leaflet's accumulators to the other's.
+// ---------------------------------------------------------------------------------------------
+struct RepairParams {
+    const Seg *segs;
+    int n_segs, n_blocks, n_group;
+    const float *ref;            // provisional centre the batch was classified with
+    const unsigned char *flag;   // [F]
+    const unsigned *nflag;       // [1]
+    float *center;               // [F] exact centre of repaired frames
+    unsigned *host_counters;     // mapped pinned: [0] frames speculated, [1] frames repaired
+    unsigned char *leaf_out;
+};
+
+template <int MPT>
+__global__ void __launch_bounds__(kBlock) spec_repair_kernel(DeviceView v, RepairParams rp, const float *__restrict__ planes,
+                                                             const FrameAux *__restrict__ aux, AccumOut o, int n_frames) {
+    const unsigned nflag = *rp.nflag;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        volatile unsigned *hc = rp.host_counters;
+        hc[0] = hc[0] + (unsigned)n_frames; hc[1] = hc[1] + nflag;
+        __threadfence_system();
+    }
+    if (nflag == 0) return;
+    __shared__ double s_red[2][8];
+    __shared__ float s_c;
+    const Chunk ch = v.chunks[blockIdx.x];
+    const TypeDesc td = v.types[ch.type];
+    const int axis = v.leaflet_axis;
+    const float sref = *rp.ref;
+    for (int f = blockIdx.y; f < n_frames; f += gridDim.y) {
+        if (!rp.flag[f]) continue;   // block-uniform
+        const FrameAux &ax = aux[f];
+        const float L = ax.L[axis], half = ax.half[axis];
+        const float *fr = planes + (size_t)f * v.frame_floats;
+        // ---- exact centre (center_axis_kernel, both passes, blocks in index order) ----
+        const float scale = __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L);
+        double T0 = 0, T1 = 0, t0, t1;
+        for (int vb = 0; vb < rp.n_blocks; vb++) { center_block_sums(rp.segs, rp.n_segs, vb, rp.n_blocks, fr, true, 0, scale, 0.0f, L, half, s_red, t0, t1); T0 += t0; T1 += t1; }
+        if (threadIdx.x == 0) {
+            const float th = __fadd_rn(atan2f(-(float)T1, -(float)T0), CUDART_PI_F);
+            s_c = rp.n_group > 0 ? __fdiv_rn(__fmul_rn(L, th), __fmul_rn(2.0f, CUDART_PI_F)) : CUDART_NAN_F;
+        }
+        __syncthreads();
+        const float e = s_c;
+        T0 = 0;
+        for (int vb = 0; vb < rp.n_blocks; vb++) { center_block_sums(rp.segs, rp.n_segs, vb, rp.n_blocks, fr, true, 1, scale, e, L, half, s_red, t0, t1); T0 += t0; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float c = __fadd_rn(e, __fdiv_rn((float)T0, (float)rp.n_group));
+            s_c = (L > 0.0f) ? wrap1(c, L) : c;
+        }
+        __syncthreads();
+        const float center = s_c;
+        if (center != center) { if (threadIdx.x == 0) raise_error(v, GORDER_ERR_INVALID_GLOBAL_CENTER, ax.frame_index); continue; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) rp.center[f] = center;
+        // ---- molecules of this chunk that change sides ----
+        const int mpad = td.cstride;
+        // the bond kernel's component order (PERMUTE) so that every sample rounds exactly as it did there
+        const int c0 = (v.normal_axis + 1) % 3, c1 = (v.normal_axis + 2) % 3, c2 = v.normal_axis;
+#pragma unroll 1
+        for (int j = 0; j < MPT; j++) {
+            const int m = ch.first_mol + threadIdx.x * MPT + j;
+            if (m >= td.n_mol) continue;
+            const float *base = fr + mol_offset(td, m);
+            const float hd = __ldg(base + td.head_off + axis * mpad);
+            bool up_spec = distance_1d(hd, sref, L, half, true) >= 0.0f, up = distance_1d(hd, center, L, half, true) >= 0.0f;
+            if (v.leaflet_flip) { up_spec = !up_spec; up = !up; }
+            if (rp.leaf_out) rp.leaf_out[(size_t)(1 + f) * v.n_molpad + td.molpad0 + m] = up ? GORDER_UPPER : GORDER_LOWER;
+            if (up == up_spec) continue;
+            const int to = up ? GORDER_ACC_UPPER : GORDER_ACC_LOWER, from = up ? GORDER_ACC_LOWER : GORDER_ACC_UPPER;
+            for (int b = 0; b < td.n_items; b++) {
+                const BondItem bi = v.bonds[td.item_off + b];
+                const int a_off = bi.a_off & ~15;
+                const float *pa = base + a_off, *pb = base + bi.b_off;
+                const f3 d = mk3(min_image(__fsub_rn(__ldg(pb + c0 * mpad), __ldg(pa + c0 * mpad)), ax.L[c0], ax.half[c0]),
+                                 min_image(__fsub_rn(__ldg(pb + c1 * mpad), __ldg(pa + c1 * mpad)), ax.L[c1], ax.half[c1]),
+                                 min_image(__fsub_rn(__ldg(pb + c2 * mpad), __ldg(pa + c2 * mpad)), ax.L[c2], ax.half[c2]));
+                const long long q = order_value_fast(calc_sch_axis_fast(d, d.z));
+                const size_t rb = ((size_t)ax.tw_row * v.n_slots + td.slot0 + b) * 3;
+                atomicAdd((unsigned long long *)&o.bsum[rb + to], (unsigned long long)q);
+                atomicAdd((unsigned long long *)&o.bsum[rb + from], (unsigned long long)(-q));
+                atomicAdd(&o.bcnt[rb + to], 1ull);
+                atomicAdd(&o.bcnt[rb + from], ~0ull);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1121,7 +1349,7 @@ __global__ void __launch_bounds__(kBlock, 4) global_leaflet_pipeline_kernel(Devi
             const BondItem bi = s_bonds[b];
             Vec<MPT> x1, y1, z1, x2, y2, z2;
             if (active) {
-                const int a_off = bi.a_off & ~3;
+                const int a_off = bi.a_off & ~15;
                 x1.load(base + a_off); y1.load(base + a_off + mpad); z1.load(base + a_off + 2 * mpad);
                 x2.load(base + bi.b_off); y2.load(base + bi.b_off + mpad); z2.load(base + bi.b_off + 2 * mpad);
             }

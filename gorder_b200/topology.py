@@ -139,6 +139,16 @@ class SystemTopology:
         lib().gorder_gpu_stats(self._h, C.byref(k), C.byref(f))
         return {"kernel_launches": int(k.value), "frames": int(f.value)}
 
+    def fence(self):
+        """Main stream waits for the helper streams (asynchronous); record closing timing events after it."""
+        self._check(lib().gorder_gpu_fence(self._h))
+
+    def speculation_stats(self):
+        """Frames classified without a centre pre-pass / frames that needed the exact centre afterwards."""
+        e, a, b = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+        lib().gorder_gpu_speculation_stats(self._h, C.byref(e), C.byref(a), C.byref(b))
+        return {"enabled": bool(e.value), "frames_speculated": int(a.value), "frames_repaired": int(b.value)}
+
     @property
     def stream(self) -> int:
         return int(lib().gorder_gpu_stream(self._h) or 0)

@@ -304,7 +304,19 @@ int gorder_gpu_profile_read(GorderHandle *h, double *hot_kernel_ms, int64_t *hot
 /* Counters for benchmarking: kernels launched by this handle and frames analysed so far. */
 int gorder_gpu_stats(GorderHandle *h, int64_t *kernel_launches, int64_t *frames);
 
-/* CUDA stream all work of this handle is queued on (as void*), for event timing by the caller. */
+/* Speculative Global leaflets (DESIGN.md §4, K1 SPEC): frames classified without a centre pre-pass and, of those,
+ * frames that needed the exact two-pass centre afterwards (spec_repair_kernel).  `enabled` is 0 when the
+ * configuration does not qualify or the engine switched the path off (too many repairs).  Results are identical
+ * either way; the counters only explain throughput.  Blocks until the queued batches are done. */
+int gorder_gpu_speculation_stats(GorderHandle *h, int32_t *enabled, int64_t *frames_speculated, int64_t *frames_repaired);
+
+/* Asynchronous join: the main stream (gorder_gpu_stream) waits for the work this handle queued on its helper
+ * streams (the tail of a batch -- repair + fold -- may run beside the next batch's kernel).  An event recorded on
+ * the main stream after this call covers everything submitted so far.  Does not block the host. */
+int gorder_gpu_fence(GorderHandle *h);
+
+/* CUDA stream the accumulation kernels of this handle are queued on (as void*), for event timing by the caller
+ * (call gorder_gpu_fence before recording the closing event). */
 void *gorder_gpu_stream(GorderHandle *h);
 
 /* Human-readable detail of the last error of this handle (offending atom index etc.). */
