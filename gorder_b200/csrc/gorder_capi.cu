@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "gorder_kernels.cuh"
+#include "gorder_fast.cuh"
 
 using namespace gorder;
 
@@ -139,6 +140,7 @@ struct GorderHandle {
     double prof_ms = 0.0;
     long long prof_n = 0;
 
+    bool fast_ok = false;   // K1f applies (bond_fast_kernel)
     // speculative Global leaflets (bond_order_kernel<SPEC> + spec_repair_kernel)
     bool spec_ok = false, spec_disabled = false, spec_ref_valid = false;
     int spec_cur = 0;
@@ -246,6 +248,14 @@ void launch_bond_spec(GorderHandle *h, dim3 grid, size_t smem, const float *plan
     bond_order_kernel<MPT, true, false, true, false, true><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, h->d_normals,
                                                                                              h->d_normal_npoints, o);
 }
+// K1f (gorder_fast.cuh): PBC, static normal, no geometry / maps, 2 or 4 molecules per lane
+template <int NP>
+void launch_fast(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o, bool spec) {
+    if (!h->leaf) bond_fast_kernel<NP, false, false><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o);
+    else if (spec) bond_fast_kernel<NP, true, true><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o);
+    else bond_fast_kernel<NP, true, false><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o);
+}
+
 template <int MPT>
 void launch_repair(GorderHandle *h, cudaStream_t st, dim3 grid, const RepairParams &rp, const float *planes, const FrameAux *aux, AccumOut o, int nf) {
     spec_repair_kernel<MPT><<<grid, kBlock, 0, st>>>(h->view, rp, planes, aux, o, nf);
@@ -516,6 +526,9 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         if (h->mpt == 4) global_leaflet_pipeline_kernel<4><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
         else if (h->mpt == 2) global_leaflet_pipeline_kernel<2><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
         else global_leaflet_pipeline_kernel<1><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
+    } else if (h->fast_ok && !getenv("GORDER_NO_FAST")) {
+        if (h->mpt == 4) launch_fast<2>(h, grid, smem, d_planes, da, o, spec);
+        else launch_fast<1>(h, grid, smem, d_planes, da, o, spec);
     } else if (spec) {
         if (h->mpt == 4) launch_bond_spec<4>(h, grid, smem, d_planes, da, o);
         else if (h->mpt == 2) launch_bond_spec<2>(h, grid, smem, d_planes, da, o);
@@ -919,6 +932,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         CK(cudaEventCreateWithFlags(&h->ev_post_any, cudaEventDisableTiming));
     }
 
+    h->fast_ok = !ua && !h->nvec && !h->extra && s->handle_pbc && (h->mpt == 2 || h->mpt == 4);
     // speculative Global leaflets: AA/CG, static normal along the leaflet axis, PBC, assignment on every analysed frame,
     // no geometry / maps, membrane covered by the bond kernel's loads (above)
     h->spec_ok = mem_cover && mem_counted == s->n_membrane && !ua && !h->nvec && !h->extra && s->handle_pbc &&

@@ -1,0 +1,284 @@
+// gorder_fast.cuh — K1f: the bond engine of the headline configurations, written for issue slots.
+//
+// Same arithmetic and results as bond_order_kernel<MPT, PBC=1, NVEC=0, LEAF, EXTRA=0, SPEC> (static normal,
+// PBC, no geometry / maps: AAOrder / CGOrder "basic" and "leaflets" runs; topology/bond.rs:396-446,
+// :184-215, analysis/mod.rs:76-82, order.rs:21-26, leaflets.rs:711-732), bit for bit.  The generic kernel
+// spends ~82 thread-instructions per sample and is bound by the issue rate, not by HBM
+// (profiles/README.md); this one needs about a third of that:
+//   * packed f32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE-rn operations per issue slot):
+//     a lane owns 2 NP consecutive molecules, the j-th pair lives in one 64-bit register pair, exactly as
+//     the 128-bit plane loads deliver it;
+//   * no register copies between bonds that share an atom: the two atom buffers swap ROLES (two
+//     specialisations of the loop body, selected by a warp-uniform branch);
+//   * one |r| <= guard test per component and thread (FMNMX3 over the lane's molecules);
+//   * NaN / Inf coordinates are caught by an integer max over the bit patterns of |d|^2;
+//   * warp sums (REDUX) stay in registers (lane b keeps bond b) and reach shared memory once per 32 bonds;
+//   * molecules past the end of a type read the last real vector (no predicated loads), masks only where
+//     they are free.
+// Requirement: plane floats that no atom maps to (tile padding) are finite; the engine's own staging
+// buffers are zero-initialised and gorder_gpu_native_layout documents it for resident frames.
+#pragma once
+#include "gorder_kernels.cuh"
+
+namespace gorder {
+
+__device__ __forceinline__ float2 padd(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 psub(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; "
+        "mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+
+// one atom of the lane's 2 NP molecules: component c of pair p
+template <int NP> struct AtomBuf { float2 c[3][NP]; };
+
+template <int NP>
+__device__ __forceinline__ void load_atom(AtomBuf<NP> &a, const float *p0, const float *p1, const float *p2) {
+    if (NP == 2) {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(p0)), y = __ldg(reinterpret_cast<const float4 *>(p1)),
+                     z = __ldg(reinterpret_cast<const float4 *>(p2));
+        a.c[0][0] = make_float2(x.x, x.y); a.c[0][NP - 1] = make_float2(x.z, x.w);
+        a.c[1][0] = make_float2(y.x, y.y); a.c[1][NP - 1] = make_float2(y.z, y.w);
+        a.c[2][0] = make_float2(z.x, z.y); a.c[2][NP - 1] = make_float2(z.z, z.w);
+    } else {
+        a.c[0][0] = __ldg(reinterpret_cast<const float2 *>(p0));
+        a.c[1][0] = __ldg(reinterpret_cast<const float2 *>(p1));
+        a.c[2][0] = __ldg(reinterpret_cast<const float2 *>(p2));
+    }
+}
+
+// per-thread state of the bond loop
+template <int NP> struct FastState {
+    int su, st;            // this bond: upper / all
+    unsigned imax;         // max bit pattern of |d|^2 seen so far (NaN / Inf detector)
+    float2 dsum, dsq;      // SPEC: sum d, sum d^2 of the membrane atoms (two lanes of partial sums)
+    float dabs;            // SPEC: max |d|
+};
+
+// One bond of the lane's molecules: `first` holds the bond's first atom, `other` receives the second.
+template <int NP, bool LEAF, bool SPEC>
+__device__ __forceinline__ void fast_bond(AtomBuf<NP> &first, AtomBuf<NP> &other, const float *tp, int a_item, int b_off, int o0, int o1, int o2,
+                                          float L0, float L1, float L2, float h0, float h1, float h2, float g0, float g1, float g2, float sref,
+                                          float sp_invL, bool cta_full, int m0, int n_mol, const bool (&up)[2 * NP], FastState<NP> &s) {
+    const int a_off = a_item & ~15;
+    if ((a_item & 3) == 0) load_atom<NP>(first, tp + (a_off + o0), tp + (a_off + o1), tp + (a_off + o2));
+    load_atom<NP>(other, tp + (b_off + o0), tp + (b_off + o1), tp + (b_off + o2));
+
+    if (SPEC && (a_item & 12)) {   // membrane atoms seen for the first time: displacement from the provisional centre
+        auto add = [&](const AtomBuf<NP> &at) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const float2 t = padd(at.c[2][p], bc2(-sref));
+                const float2 k = padd(pfma(t, bc2(sp_invL), bc2(12582912.0f)), bc2(-12582912.0f));   // rint(t / L)
+                float2 d = pfma(k, bc2(-L2), t);
+                if (!cta_full) {   // last tile of a type: molecules past the end contribute nothing
+                    d.x = (m0 + 2 * p < n_mol) ? d.x : 0.0f;
+                    d.y = (m0 + 2 * p + 1 < n_mol) ? d.y : 0.0f;
+                }
+                s.dsum = padd(s.dsum, d); s.dsq = pfma(d, d, s.dsq);
+                s.dabs = fmaxf(s.dabs, fmaxf(fabsf(d.x), fabsf(d.y)));
+            }
+        };
+        if (a_item & 4) add(first);
+        if (a_item & 8) add(other);
+    }
+
+    // bond vectors; the fold's exact fast path  fl(fl(fl(fl(r + L/2) + L) - L) - L/2)  for everybody, the literal
+    // expression (out of line) for the rare lane that holds a component beyond the guard 0.99 L/2
+    float2 d[3][NP];
+    float m0x = 0.0f, m1x = 0.0f, m2x = 0.0f;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        const float2 r0 = psub(other.c[0][p], first.c[0][p]), r1 = psub(other.c[1][p], first.c[1][p]), r2 = psub(other.c[2][p], first.c[2][p]);
+        m0x = fmaxf(m0x, fmaxf(fabsf(r0.x), fabsf(r0.y)));
+        m1x = fmaxf(m1x, fmaxf(fabsf(r1.x), fabsf(r1.y)));
+        m2x = fmaxf(m2x, fmaxf(fabsf(r2.x), fabsf(r2.y)));
+        d[0][p] = padd(padd(padd(padd(r0, bc2(h0)), bc2(L0)), bc2(-L0)), bc2(-h0));
+        d[1][p] = padd(padd(padd(padd(r1, bc2(h1)), bc2(L1)), bc2(-L1)), bc2(-h1));
+        d[2][p] = padd(padd(padd(padd(r2, bc2(h2)), bc2(L2)), bc2(-L2)), bc2(-h2));
+    }
+    if ((m0x > g0) | (m1x > g1) | (m2x > g2)) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const float2 r0 = psub(other.c[0][p], first.c[0][p]), r1 = psub(other.c[1][p], first.c[1][p]), r2 = psub(other.c[2][p], first.c[2][p]);
+            if (fabsf(r0.x) > g0) d[0][p].x = min_image_slow(r0.x, L0, h0);
+            if (fabsf(r0.y) > g0) d[0][p].y = min_image_slow(r0.y, L0, h0);
+            if (fabsf(r1.x) > g1) d[1][p].x = min_image_slow(r1.x, L1, h1);
+            if (fabsf(r1.y) > g1) d[1][p].y = min_image_slow(r1.y, L1, h1);
+            if (fabsf(r2.x) > g2) d[2][p].x = min_image_slow(r2.x, L2, h2);
+            if (fabsf(r2.y) > g2) d[2][p].y = min_image_slow(r2.y, L2, h2);
+        }
+    }
+    // S = 1.5 c^2 - 0.5, c = d_axis rsqrt(|d|^2) (calc_sch_axis_fast); |d| = 0 -> c = 0 * inf = NaN -> min(NaN, 1) = 1 -> S = 1,
+    // which is what Vector3D::angle's zero-norm rule gives.  q = round(S 1e6) (order_value_fast).
+    s.st = 0; s.su = 0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        const float2 n1 = pfma(d[2][p], d[2][p], pfma(d[1][p], d[1][p], pmul(d[0][p], d[0][p])));
+        s.imax = max(s.imax, max(__float_as_uint(n1.x), __float_as_uint(n1.y)));
+        const float2 c = pmul(d[2][p], make_float2(rsqrt_ftz(n1.x), rsqrt_ftz(n1.y)));
+        float2 c2 = pmul(c, c);
+        c2.x = fminf(c2.x, 1.0f); c2.y = fminf(c2.y, 1.0f);
+        const float2 sv = pmul(pfma(bc2(1.5f), c2, bc2(-0.5f)), bc2(1000000.0f));
+        int qa = __float2int_rn(sv.x), qb = __float2int_rn(sv.y);
+        if (!cta_full) {
+            qa = (m0 + 2 * p < n_mol) ? qa : 0;
+            qb = (m0 + 2 * p + 1 < n_mol) ? qb : 0;
+        }
+        s.st += qa + qb;
+        if (LEAF) s.su += (up[2 * p] ? qa : 0) + (up[2 * p + 1] ? qb : 0);
+    }
+}
+
+template <int NP, bool LEAF, bool SPEC>
+__global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                              const unsigned char *__restrict__ leaf_rows, AccumOut o) {
+    constexpr int MPT = 2 * NP;
+    constexpr int NA = LEAF ? 2 : 1;
+    extern __shared__ int smem[];
+    const Chunk ch = v.chunks[blockIdx.x];
+    const TypeDesc td = v.types[ch.type];
+    const int f = blockIdx.y;
+    const FrameAux &ax = aux[f];
+    const int nb = td.n_items;
+    BondItem *s_bonds = reinterpret_cast<BondItem *>(smem);
+    int *s_acc = smem + 2 * nb;                 // [kWarps][nb][NA]
+    int *s_cnt = s_acc + kWarps * nb * NA;      // [2] valid, valid & upper
+    for (int i = threadIdx.x; i < nb; i += kBlock) s_bonds[i] = v.bonds[td.item_off + i];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m0 = ch.first_mol + threadIdx.x * MPT;
+    const bool cta_full = ch.first_mol + kBlock * MPT <= td.n_mol;
+    // lanes past the end of the type read the last real vector (their samples are masked out)
+    const int m0c = min(m0, (td.n_mol - 1) / MPT * MPT);
+    const int mpad = td.cstride;
+    const int c0 = (v.normal_axis + 1) % 3, c1 = (v.normal_axis + 2) % 3, c2 = v.normal_axis;   // the normal axis comes last
+    const int o0 = c0 * mpad, o1 = c1 * mpad, o2 = c2 * mpad;
+    const float L0 = ax.L[c0], L1 = ax.L[c1], L2 = ax.L[c2];
+    const float h0 = ax.half[c0], h1 = ax.half[c1], h2 = ax.half[c2];
+    const float g0 = 0.99f * h0, g1 = 0.99f * h1, g2 = 0.99f * h2;
+    const float *tp = planes + (size_t)f * v.frame_floats + mol_offset(td, m0c);
+
+    // ---- leaflets of the lane's molecules (leaflets.rs:711-732 inline, or the table) ----
+    bool up[MPT];
+    int nvalid = 0, nup = 0;
+    const float sref = SPEC ? __ldg(o.spec_ref) : 0.0f;
+    float hmin = CUDART_INF_F, hmax = 0.0f;
+    bool hnan = false;
+#pragma unroll
+    for (int j = 0; j < MPT; j++) {
+        const bool valid = m0 + j < td.n_mol;
+        up[j] = false;
+        if (LEAF && valid) {
+            const int la = v.leaflet_axis;
+            if (SPEC || o.inline_center) {
+                const float cen = SPEC ? sref : o.inline_center[3 * f + la];
+                if (!SPEC && cen != cen) raise_error(v, GORDER_ERR_INVALID_GLOBAL_CENTER, ax.frame_index);
+                const float hd = __ldg(tp + td.head_off + la * mpad + j);
+                const float dh = distance_1d(hd, cen, ax.L[la], ax.half[la], true);
+                up[j] = dh >= 0.0f;
+                if (SPEC) { hmin = fminf(hmin, fabsf(dh)); hmax = fmaxf(hmax, fabsf(dh)); hnan = hnan || dh != dh; }
+                if (v.leaflet_flip) up[j] = !up[j];
+                if (o.leaf_out) o.leaf_out[(size_t)(1 + f) * v.n_molpad + td.molpad0 + m0 + j] = up[j] ? GORDER_UPPER : GORDER_LOWER;
+            } else up[j] = leaf_rows[(size_t)ax.leaf_row * v.n_molpad + td.molpad0 + m0 + j] == GORDER_UPPER;
+        }
+        nvalid += valid; nup += valid && up[j];
+    }
+    {
+        const int a = __reduce_add_sync(0xffffffffu, nvalid), b = __reduce_add_sync(0xffffffffu, nup);
+        if (lane == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], b); }
+    }
+    __shared__ float s_hmm[2][kWarps];
+    __shared__ double s_dsum[2][kWarps];
+    __shared__ float s_dabs[kWarps];
+    if (SPEC) {
+        float a = hnan ? CUDART_NAN_F : hmin, b = hmax;
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            const float a2 = __shfl_xor_sync(0xffffffffu, a, ofs), b2 = __shfl_xor_sync(0xffffffffu, b, ofs);
+            a = (a != a || a2 != a2) ? CUDART_NAN_F : fminf(a, a2); b = fmaxf(b, b2);
+        }
+        if (lane == 0) { s_hmm[0][warp] = a; s_hmm[1][warp] = b; }
+    }
+
+    // ---- bond loop ----
+    FastState<NP> s;
+    s.su = s.st = 0; s.imax = 0u; s.dsum = s.dsq = make_float2(0.0f, 0.0f); s.dabs = 0.0f;
+    const float sp_invL = (SPEC && L2 > 0.0f) ? __frcp_rn(L2) : 0.0f;
+    AtomBuf<NP> A, B;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int p = 0; p < NP; p++) A.c[c][p] = B.c[c][p] = make_float2(0.0f, 0.0f);
+    int ru = 0, rl = 0;        // lane (b & 31) keeps the warp sums of bond b
+    bool first_in_a = true;    // which buffer holds the current bond's first atom (warp-uniform)
+    for (int b = 0; b < nb; b++) {
+        const BondItem bi = s_bonds[b];
+        if ((bi.a_off & 3) == 2) first_in_a = !first_in_a;   // the first atom is the previous bond's second atom: swap roles
+        if (first_in_a) fast_bond<NP, LEAF, SPEC>(A, B, tp, bi.a_off, bi.b_off, o0, o1, o2, L0, L1, L2, h0, h1, h2, g0, g1, g2, sref, sp_invL, cta_full, m0, td.n_mol, up, s);
+        else fast_bond<NP, LEAF, SPEC>(B, A, tp, bi.a_off, bi.b_off, o0, o1, o2, L0, L1, L2, h0, h1, h2, g0, g1, g2, sref, sp_invL, cta_full, m0, td.n_mol, up, s);
+        // fixed-order hardware tree (REDUX) -> deterministic
+        const int wu = __reduce_add_sync(0xffffffffu, LEAF ? s.su : s.st);
+        const int wl = LEAF ? __reduce_add_sync(0xffffffffu, s.st - s.su) : 0;
+        if ((b & 31) == lane) { ru = wu; rl = wl; }
+        if ((b & 31) == 31 || b == nb - 1) {
+            if (lane <= (b & 31)) {
+                int *p = s_acc + ((size_t)warp * nb + (b & ~31) + lane) * NA;
+                p[0] = ru;
+                if (LEAF) p[1] = rl;
+            }
+        }
+    }
+    if (s.imax >= 0x7f800000u)   // AnalysisError::UndefinedPosition: a NaN / Inf coordinate reached the engine
+        raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | (unsigned)min(m0, td.n_mol - 1));
+    if (SPEC) {
+        const float tsum = s.dsum.x + s.dsum.y;
+        double ds = (double)s.dsum.x + (double)s.dsum.y, dq = (double)s.dsq.x + (double)s.dsq.y;
+        float a = s.dabs;
+        if (tsum != tsum) a = tsum;   // NaN / Inf coordinate: poison the extent so that the frame is flagged
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            ds += __shfl_xor_sync(0xffffffffu, ds, ofs); dq += __shfl_xor_sync(0xffffffffu, dq, ofs);
+            const float a2 = __shfl_xor_sync(0xffffffffu, a, ofs);
+            a = (a != a || a2 != a2) ? CUDART_NAN_F : fmaxf(a, a2);
+        }
+        if (lane == 0) { s_dsum[0][warp] = ds; s_dsum[1][warp] = dq; s_dabs[warp] = a; }
+    }
+    __syncthreads();
+    cta_flush<LEAF, false>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
+    if (SPEC && threadIdx.x == 0) {
+        double ds = 0.0, dq = 0.0;
+        float p0 = 0.0f, p1 = CUDART_INF_F, p2 = 0.0f;
+        bool bad = false;
+        for (int w = 0; w < kWarps; w++) {
+            ds += s_dsum[0][w]; dq += s_dsum[1][w];
+            bad = bad || s_dabs[w] != s_dabs[w] || s_hmm[0][w] != s_hmm[0][w];
+            p0 = fmaxf(p0, s_dabs[w]); p1 = fminf(p1, s_hmm[0][w]); p2 = fmaxf(p2, s_hmm[1][w]);
+        }
+        spec_publish(o, f, sref, L2, h2, ds, dq, p0, p1, p2, bad);
+    }
+}
+
+}  // namespace gorder

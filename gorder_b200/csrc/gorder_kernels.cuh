@@ -765,6 +765,54 @@ __device__ __forceinline__ void map_add(const DeviceView &v, const AccumOut &o, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// SPEC epilogue (thread 0 of a CTA): publish the CTA's partial sums of the membrane's displacements
+// from the provisional centre `sref`; the last CTA of the frame adds them in chunk order
+// (deterministic) and decides whether the speculative leaflets are provably the exact ones.
+//
+// group_get_center = wrap(est + mean(min_image(z - est))), est = circular mean of the membrane.  With
+// d_i = min_image(z_i - sref) this equals wrap(sref + mean d) (up to f32 rounding) as long as every atom
+// keeps its periodic image when seen from est instead of sref:  |est - sref| < L/2 - max|d_i|.
+// est is not computed; it is bounded from the moments: with t_i = 2 pi d_i / L, T = max|t_i|,
+//     sum cos t_i >= N - S2/2,  |sum sin t_i| <= |S1| + T S2 / 6     (S1 = sum t_i, S2 = sum t_i^2)
+// so |est - sref| <= atan2(|S1| + T S2/6, N - S2/2) L / 2 pi whenever N - S2/2 > 0.
+// The leaflets are those of the exact centre if no head lies within |delta| (+ margin) of sref or of the
+// far cut sref + L/2.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void spec_publish(const AccumOut &o, int f, float sref, float L, float half, double ds, double dq, float dabs,
+                                             float hmin, float hmax, bool bad) {
+    const size_t pi = (size_t)f * gridDim.x + blockIdx.x;
+    o.spec_sum[2 * pi] = ds; o.spec_sum[2 * pi + 1] = dq;
+    reinterpret_cast<float4 *>(o.spec_mm)[pi] = make_float4(dabs, hmin, hmax, bad ? 1.0f : 0.0f);
+    __threadfence();
+    if (atomicAdd(&o.spec_ticket[f], 1u) != gridDim.x - 1) return;
+    __threadfence();
+    o.spec_ticket[f] = 0;
+    double tot = 0.0, tot2 = 0.0;
+    float dmax = 0.0f, hmn = CUDART_INF_F, hmx = 0.0f;
+    bool nan = false;
+    for (unsigned c = 0; c < gridDim.x; c++) {
+        const size_t qi = (size_t)f * gridDim.x + c;
+        tot += __ldcg(o.spec_sum + 2 * qi); tot2 += __ldcg(o.spec_sum + 2 * qi + 1);
+        const float4 m4 = __ldcg(reinterpret_cast<const float4 *>(o.spec_mm) + qi);
+        nan = nan || m4.w != 0.0f;
+        dmax = fmaxf(dmax, m4.x); hmn = fminf(hmn, m4.y); hmx = fmaxf(hmx, m4.z);
+    }
+    const double n = (double)o.n_membrane;
+    const float delta = (float)(tot / n);
+    const float margin = 1e-4f + 1e-3f * L;
+    const double ts = 6.283185307179586 / (double)L;
+    const double s1 = fabs(tot) * ts, s2 = tot2 * ts * ts, x_lo = n - 0.5 * s2, y_hi = s1 + (double)dmax * ts * s2 / 6.0;
+    const float est_bound = x_lo > 0.0 ? (float)(atan2(y_hi, x_lo) / ts) : CUDART_INF_F;
+    const bool ok = !nan && o.n_membrane > 0 && L > 0.0f && (delta == delta) && est_bound + margin < half - dmax &&
+                    fabsf(delta) + margin < hmn && hmx + fabsf(delta) + margin < half;
+    const float c = wrap1(__fadd_rn(sref, delta), L);
+    o.spec_center[f] = ok ? c : CUDART_NAN_F;
+    o.spec_flag[f] = ok ? 0 : 1;
+    if (!ok) atomicAdd(o.spec_nflag, 1u);
+    if (f == (int)gridDim.y - 1) *o.spec_ref_next = ok ? c : sref;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1: bond engine (topology/bond.rs:396-446 + :184-215).
 //   grid (n_chunks, F); a lane owns MPT consecutive molecules of one molecule type and walks the
 //   type's bond table (staged in shared memory); every plane read is a fully-used 128 B * MPT line.
@@ -1027,7 +1075,6 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
     __syncthreads();
     cta_flush<LEAF, EXTRA>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
     if (SPEC && threadIdx.x == 0) {
-        // publish this CTA's partials; the last CTA of the frame adds them in chunk order (deterministic)
         double ds = 0.0, dq = 0.0;
         float p0 = 0.0f, p1 = CUDART_INF_F, p2 = 0.0f;
         bool bad = false;
@@ -1036,46 +1083,7 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
             bad = bad || s_dabs[w] != s_dabs[w] || s_hmm[0][w] != s_hmm[0][w];
             p0 = fmaxf(p0, s_dabs[w]); p1 = fminf(p1, s_hmm[0][w]); p2 = fmaxf(p2, s_hmm[1][w]);
         }
-        const size_t pi = (size_t)f * gridDim.x + blockIdx.x;
-        o.spec_sum[2 * pi] = ds; o.spec_sum[2 * pi + 1] = dq;
-        reinterpret_cast<float4 *>(o.spec_mm)[pi] = make_float4(p0, p1, p2, bad ? 1.0f : 0.0f);
-        __threadfence();
-        if (atomicAdd(&o.spec_ticket[f], 1u) == gridDim.x - 1) {
-            __threadfence();
-            o.spec_ticket[f] = 0;
-            double tot = 0.0, tot2 = 0.0;
-            float dmax = 0.0f, hmn = CUDART_INF_F, hmx = 0.0f;
-            bool nan = false;
-            for (unsigned c = 0; c < gridDim.x; c++) {
-                const size_t qi = (size_t)f * gridDim.x + c;
-                tot += __ldcg(o.spec_sum + 2 * qi); tot2 += __ldcg(o.spec_sum + 2 * qi + 1);
-                const float4 m4 = __ldcg(reinterpret_cast<const float4 *>(o.spec_mm) + qi);
-                nan = nan || m4.w != 0.0f;
-                dmax = fmaxf(dmax, m4.x); hmn = fminf(hmn, m4.y); hmx = fmaxf(hmx, m4.z);
-            }
-            // group_get_center = wrap(est + mean(min_image(z - est))), est = circular mean of the membrane.
-            // With d_i = min_image(z_i - sref) this equals wrap(sref + mean d) (up to f32 rounding) as long as
-            // every atom keeps its periodic image when seen from est instead of sref:
-            //     |est - sref| < L/2 - max|d_i|.
-            // est is not computed; it is bounded from the moments: with t_i = 2 pi d_i / L, T = max|t_i|,
-            //     sum cos t_i >= N - S2/2,  |sum sin t_i| <= |S1| + T S2 / 6     (S1 = sum t_i, S2 = sum t_i^2)
-            // so |est - sref| <= atan2(|S1| + T S2/6, N - S2/2) L / 2 pi whenever N - S2/2 > 0.
-            // The leaflets are those of the exact centre if no head lies within |delta| (+ margin) of sref or
-            // of the far cut sref + L/2.
-            const double n = (double)o.n_membrane;
-            const float delta = (float)(tot / n);
-            const float margin = 1e-4f + 1e-3f * L2;
-            const double ts = 6.283185307179586 / (double)L2;
-            const double s1 = fabs(tot) * ts, s2 = tot2 * ts * ts, x_lo = n - 0.5 * s2, y_hi = s1 + (double)dmax * ts * s2 / 6.0;
-            const float est_bound = x_lo > 0.0 ? (float)(atan2(y_hi, x_lo) / ts) : CUDART_INF_F;
-            const bool ok = !nan && o.n_membrane > 0 && L2 > 0.0f && (delta == delta) && est_bound + margin < h2 - dmax &&
-                            fabsf(delta) + margin < hmn && hmx + fabsf(delta) + margin < h2;
-            const float c = wrap1(__fadd_rn(sref, delta), L2);
-            o.spec_center[f] = ok ? c : CUDART_NAN_F;
-            o.spec_flag[f] = ok ? 0 : 1;
-            if (!ok) atomicAdd(o.spec_nflag, 1u);
-            if (f == (int)gridDim.y - 1) *o.spec_ref_next = ok ? c : sref;
-        }
+        spec_publish(o, f, sref, L2, h2, ds, dq, p0, p1, p2, bad);
     }
 }
 
