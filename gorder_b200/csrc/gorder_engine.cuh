@@ -65,6 +65,7 @@ struct FrameAux {
     float shape_len[3];   // cuboid extents (INFINITY allowed)
     float shape_radius, shape_height;
     float center[3];      // scratch: group centre (geometry reference)
+    float guard[3];       // 0.99 L / 2: below it the minimum-image fold takes its exact fast path
 };
 
 // Group of atoms given by native offsets (membrane, geometry reference, normal heads).

@@ -13,10 +13,8 @@
 //   * one |r| <= guard test per component and thread (FMNMX3 over the lane's molecules);
 //   * NaN / Inf coordinates are caught by an integer max over the bit patterns of |d|^2;
 //   * warp sums (REDUX) stay in registers (lane b keeps bond b) and reach shared memory once per 32 bonds;
-//   * molecules past the end of a type read the last real vector (no predicated loads), masks only where
-//     they are free.
-// Requirement: plane floats that no atom maps to (tile padding) are finite; the engine's own staging
-// buffers are zero-initialised and gorder_gpu_native_layout documents it for resident frames.
+//   * every load address is one IMAD.WIDE from an opaque per-lane pointer;
+//   * no validity masks: the (at most one) partial tile of a molecule type runs the generic body instead.
 #pragma once
 #include "gorder_kernels.cuh"
 
@@ -69,32 +67,43 @@ __device__ __forceinline__ void load_atom(AtomBuf<NP> &a, const float *p0, const
 
 // per-thread state of the bond loop
 template <int NP> struct FastState {
-    int su, st;            // this bond: upper / all
     unsigned imax;         // max bit pattern of |d|^2 seen so far (NaN / Inf detector)
     float2 dsum, dsq;      // SPEC: sum d, sum d^2 of the membrane atoms (two lanes of partial sums)
     float dabs;            // SPEC: max |d|
+    int ru, rl;            // lane (b & 31) keeps the warp sums of bond b until they are flushed to shared memory
+};
+
+// everything that is uniform over the bond loop
+struct FastConst {
+    const float *tp;       // plane x of in-tile offset 0, first molecule of the lane
+    int o1, o2;            // component strides (the normal axis comes last)
+    float L0, L1, L2, h0, h1, h2, g0, g1, g2;
+    float sref, inv_l2;    // SPEC: provisional centre, 1 / L along the leaflet axis
+    int nb, lane;
+    int *s_acc_warp;       // this warp's rows of the shared accumulators
 };
 
 // One bond of the lane's molecules: `first` holds the bond's first atom, `other` receives the second.
 template <int NP, bool LEAF, bool SPEC>
-__device__ __forceinline__ void fast_bond(AtomBuf<NP> &first, AtomBuf<NP> &other, const float *tp, int a_item, int b_off, int o0, int o1, int o2,
-                                          float L0, float L1, float L2, float h0, float h1, float h2, float g0, float g1, float g2, float sref,
-                                          float sp_invL, bool cta_full, int m0, int n_mol, const bool (&up)[2 * NP], FastState<NP> &s) {
-    const int a_off = a_item & ~15;
-    if ((a_item & 3) == 0) load_atom<NP>(first, tp + (a_off + o0), tp + (a_off + o1), tp + (a_off + o2));
-    load_atom<NP>(other, tp + (b_off + o0), tp + (b_off + o1), tp + (b_off + o2));
-
+__device__ __forceinline__ void fast_bond(AtomBuf<NP> &first, AtomBuf<NP> &other, const FastConst &k, const BondItem bi, int b,
+                                          const bool (&up)[2 * NP], FastState<NP> &s) {
+    constexpr int NA = LEAF ? 2 : 1;
+    const int a_item = bi.a_off;
+    if ((a_item & 3) == 0) {
+        const float *pa = k.tp + (a_item & ~15);
+        load_atom<NP>(first, pa, pa + k.o1, pa + k.o2);
+    }
+    {
+        const float *pb = k.tp + bi.b_off;
+        load_atom<NP>(other, pb, pb + k.o1, pb + k.o2);
+    }
     if (SPEC && (a_item & 12)) {   // membrane atoms seen for the first time: displacement from the provisional centre
         auto add = [&](const AtomBuf<NP> &at) {
 #pragma unroll
             for (int p = 0; p < NP; p++) {
-                const float2 t = padd(at.c[2][p], bc2(-sref));
-                const float2 k = padd(pfma(t, bc2(sp_invL), bc2(12582912.0f)), bc2(-12582912.0f));   // rint(t / L)
-                float2 d = pfma(k, bc2(-L2), t);
-                if (!cta_full) {   // last tile of a type: molecules past the end contribute nothing
-                    d.x = (m0 + 2 * p < n_mol) ? d.x : 0.0f;
-                    d.y = (m0 + 2 * p + 1 < n_mol) ? d.y : 0.0f;
-                }
+                const float2 t = padd(at.c[2][p], bc2(-k.sref));
+                const float2 q = padd(pfma(t, bc2(k.inv_l2), bc2(12582912.0f)), bc2(-12582912.0f));   // rint(t / L)
+                const float2 d = pfma(q, bc2(-k.L2), t);
                 s.dsum = padd(s.dsum, d); s.dsq = pfma(d, d, s.dsq);
                 s.dabs = fmaxf(s.dabs, fmaxf(fabsf(d.x), fabsf(d.y)));
             }
@@ -113,25 +122,25 @@ __device__ __forceinline__ void fast_bond(AtomBuf<NP> &first, AtomBuf<NP> &other
         m0x = fmaxf(m0x, fmaxf(fabsf(r0.x), fabsf(r0.y)));
         m1x = fmaxf(m1x, fmaxf(fabsf(r1.x), fabsf(r1.y)));
         m2x = fmaxf(m2x, fmaxf(fabsf(r2.x), fabsf(r2.y)));
-        d[0][p] = padd(padd(padd(padd(r0, bc2(h0)), bc2(L0)), bc2(-L0)), bc2(-h0));
-        d[1][p] = padd(padd(padd(padd(r1, bc2(h1)), bc2(L1)), bc2(-L1)), bc2(-h1));
-        d[2][p] = padd(padd(padd(padd(r2, bc2(h2)), bc2(L2)), bc2(-L2)), bc2(-h2));
+        d[0][p] = padd(padd(padd(padd(r0, bc2(k.h0)), bc2(k.L0)), bc2(-k.L0)), bc2(-k.h0));
+        d[1][p] = padd(padd(padd(padd(r1, bc2(k.h1)), bc2(k.L1)), bc2(-k.L1)), bc2(-k.h1));
+        d[2][p] = padd(padd(padd(padd(r2, bc2(k.h2)), bc2(k.L2)), bc2(-k.L2)), bc2(-k.h2));
     }
-    if ((m0x > g0) | (m1x > g1) | (m2x > g2)) {
+    if ((m0x > k.g0) | (m1x > k.g1) | (m2x > k.g2)) {
 #pragma unroll
         for (int p = 0; p < NP; p++) {
             const float2 r0 = psub(other.c[0][p], first.c[0][p]), r1 = psub(other.c[1][p], first.c[1][p]), r2 = psub(other.c[2][p], first.c[2][p]);
-            if (fabsf(r0.x) > g0) d[0][p].x = min_image_slow(r0.x, L0, h0);
-            if (fabsf(r0.y) > g0) d[0][p].y = min_image_slow(r0.y, L0, h0);
-            if (fabsf(r1.x) > g1) d[1][p].x = min_image_slow(r1.x, L1, h1);
-            if (fabsf(r1.y) > g1) d[1][p].y = min_image_slow(r1.y, L1, h1);
-            if (fabsf(r2.x) > g2) d[2][p].x = min_image_slow(r2.x, L2, h2);
-            if (fabsf(r2.y) > g2) d[2][p].y = min_image_slow(r2.y, L2, h2);
+            if (fabsf(r0.x) > k.g0) d[0][p].x = min_image_slow(r0.x, k.L0, k.h0);
+            if (fabsf(r0.y) > k.g0) d[0][p].y = min_image_slow(r0.y, k.L0, k.h0);
+            if (fabsf(r1.x) > k.g1) d[1][p].x = min_image_slow(r1.x, k.L1, k.h1);
+            if (fabsf(r1.y) > k.g1) d[1][p].y = min_image_slow(r1.y, k.L1, k.h1);
+            if (fabsf(r2.x) > k.g2) d[2][p].x = min_image_slow(r2.x, k.L2, k.h2);
+            if (fabsf(r2.y) > k.g2) d[2][p].y = min_image_slow(r2.y, k.L2, k.h2);
         }
     }
     // S = 1.5 c^2 - 0.5, c = d_axis rsqrt(|d|^2) (calc_sch_axis_fast); |d| = 0 -> c = 0 * inf = NaN -> min(NaN, 1) = 1 -> S = 1,
     // which is what Vector3D::angle's zero-norm rule gives.  q = round(S 1e6) (order_value_fast).
-    s.st = 0; s.su = 0;
+    int st = 0, su = 0;
 #pragma unroll
     for (int p = 0; p < NP; p++) {
         const float2 n1 = pfma(d[2][p], d[2][p], pfma(d[1][p], d[1][p], pmul(d[0][p], d[0][p])));
@@ -140,13 +149,20 @@ __device__ __forceinline__ void fast_bond(AtomBuf<NP> &first, AtomBuf<NP> &other
         float2 c2 = pmul(c, c);
         c2.x = fminf(c2.x, 1.0f); c2.y = fminf(c2.y, 1.0f);
         const float2 sv = pmul(pfma(bc2(1.5f), c2, bc2(-0.5f)), bc2(1000000.0f));
-        int qa = __float2int_rn(sv.x), qb = __float2int_rn(sv.y);
-        if (!cta_full) {
-            qa = (m0 + 2 * p < n_mol) ? qa : 0;
-            qb = (m0 + 2 * p + 1 < n_mol) ? qb : 0;
+        const int qa = __float2int_rn(sv.x), qb = __float2int_rn(sv.y);
+        st += qa + qb;
+        if (LEAF) su += (up[2 * p] ? qa : 0) + (up[2 * p + 1] ? qb : 0);
+    }
+    // fixed-order hardware tree (REDUX) -> deterministic
+    const int wu = __reduce_add_sync(0xffffffffu, LEAF ? su : st);
+    const int wl = LEAF ? __reduce_add_sync(0xffffffffu, st - su) : 0;
+    if ((b & 31) == k.lane) { s.ru = wu; s.rl = wl; }
+    if ((b & 31) == 31 || b == k.nb - 1) {
+        if (k.lane <= (b & 31)) {
+            int *p = k.s_acc_warp + ((b & ~31) + k.lane) * NA;
+            p[0] = s.ru;
+            if (LEAF) p[1] = s.rl;
         }
-        s.st += qa + qb;
-        if (LEAF) s.su += (up[2 * p] ? qa : 0) + (up[2 * p + 1] ? qb : 0);
     }
 }
 
@@ -155,6 +171,13 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
                                                               const unsigned char *__restrict__ leaf_rows, AccumOut o) {
     constexpr int MPT = 2 * NP;
     constexpr int NA = LEAF ? 2 : 1;
+    {   // the last tile of a molecule type (molecules past the end) takes the generic, masked code
+        const Chunk ch = v.chunks[blockIdx.x];
+        if (ch.first_mol + kBlock * MPT > v.types[ch.type].n_mol) {
+            bond_order_body<MPT, true, false, LEAF, false, SPEC>(v, planes, aux, leaf_rows, nullptr, nullptr, o);
+            return;
+        }
+    }
     extern __shared__ int smem[];
     const Chunk ch = v.chunks[blockIdx.x];
     const TypeDesc td = v.types[ch.type];
@@ -163,40 +186,35 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
     const int nb = td.n_items;
     BondItem *s_bonds = reinterpret_cast<BondItem *>(smem);
     int *s_acc = smem + 2 * nb;                 // [kWarps][nb][NA]
-    int *s_cnt = s_acc + kWarps * nb * NA;      // [2] valid, valid & upper
     for (int i = threadIdx.x; i < nb; i += kBlock) s_bonds[i] = v.bonds[td.item_off + i];
-    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m0 = ch.first_mol + threadIdx.x * MPT;
-    const bool cta_full = ch.first_mol + kBlock * MPT <= td.n_mol;
-    // lanes past the end of the type read the last real vector (their samples are masked out)
-    const int m0c = min(m0, (td.n_mol - 1) / MPT * MPT);
     const int mpad = td.cstride;
     const int c0 = (v.normal_axis + 1) % 3, c1 = (v.normal_axis + 2) % 3, c2 = v.normal_axis;   // the normal axis comes last
-    const int o0 = c0 * mpad, o1 = c1 * mpad, o2 = c2 * mpad;
-    const float L0 = ax.L[c0], L1 = ax.L[c1], L2 = ax.L[c2];
-    const float h0 = ax.half[c0], h1 = ax.half[c1], h2 = ax.half[c2];
-    const float g0 = 0.99f * h0, g1 = 0.99f * h1, g2 = 0.99f * h2;
-    const float *tp = planes + (size_t)f * v.frame_floats + mol_offset(td, m0c);
+    FastConst k;
+    k.L0 = ax.L[c0]; k.L1 = ax.L[c1]; k.L2 = ax.L[c2];
+    k.h0 = ax.half[c0]; k.h1 = ax.half[c1]; k.h2 = ax.half[c2];
+    k.g0 = ax.guard[c0]; k.g1 = ax.guard[c1]; k.g2 = ax.guard[c2];
+    k.nb = nb; k.lane = lane; k.s_acc_warp = s_acc + (size_t)warp * nb * NA;
+    const float *tp0 = planes + (size_t)f * v.frame_floats + mol_offset(td, m0);
 
     // ---- leaflets of the lane's molecules (leaflets.rs:711-732 inline, or the table) ----
     bool up[MPT];
-    int nvalid = 0, nup = 0;
-    const float sref = SPEC ? __ldg(o.spec_ref) : 0.0f;
+    int nup = 0;
+    k.sref = SPEC ? __ldg(o.spec_ref) : 0.0f;
     float hmin = CUDART_INF_F, hmax = 0.0f;
     bool hnan = false;
 #pragma unroll
     for (int j = 0; j < MPT; j++) {
-        const bool valid = m0 + j < td.n_mol;
         up[j] = false;
-        if (LEAF && valid) {
+        if (LEAF) {
             const int la = v.leaflet_axis;
             if (SPEC || o.inline_center) {
-                const float cen = SPEC ? sref : o.inline_center[3 * f + la];
+                const float cen = SPEC ? k.sref : o.inline_center[3 * f + la];
                 if (!SPEC && cen != cen) raise_error(v, GORDER_ERR_INVALID_GLOBAL_CENTER, ax.frame_index);
-                const float hd = __ldg(tp + td.head_off + la * mpad + j);
+                const float hd = __ldg(tp0 + td.head_off + la * mpad + j);
                 const float dh = distance_1d(hd, cen, ax.L[la], ax.half[la], true);
                 up[j] = dh >= 0.0f;
                 if (SPEC) { hmin = fminf(hmin, fabsf(dh)); hmax = fmaxf(hmax, fabsf(dh)); hnan = hnan || dh != dh; }
@@ -204,15 +222,16 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
                 if (o.leaf_out) o.leaf_out[(size_t)(1 + f) * v.n_molpad + td.molpad0 + m0 + j] = up[j] ? GORDER_UPPER : GORDER_LOWER;
             } else up[j] = leaf_rows[(size_t)ax.leaf_row * v.n_molpad + td.molpad0 + m0 + j] == GORDER_UPPER;
         }
-        nvalid += valid; nup += valid && up[j];
+        nup += up[j];
     }
-    {
-        const int a = __reduce_add_sync(0xffffffffu, nvalid), b = __reduce_add_sync(0xffffffffu, nup);
-        if (lane == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], b); }
-    }
+    __shared__ int s_nup[kWarps];
     __shared__ float s_hmm[2][kWarps];
     __shared__ double s_dsum[2][kWarps];
     __shared__ float s_dabs[kWarps];
+    {
+        const int a = __reduce_add_sync(0xffffffffu, nup);
+        if (lane == 0) s_nup[warp] = a;
+    }
     if (SPEC) {
         float a = hnan ? CUDART_NAN_F : hmin, b = hmax;
 #pragma unroll
@@ -223,36 +242,36 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
         if (lane == 0) { s_hmm[0][warp] = a; s_hmm[1][warp] = b; }
     }
 
-    // ---- bond loop ----
+    // ---- bond loop: the role of the two atom buffers is encoded in the program counter ----
     FastState<NP> s;
-    s.su = s.st = 0; s.imax = 0u; s.dsum = s.dsq = make_float2(0.0f, 0.0f); s.dabs = 0.0f;
-    const float sp_invL = (SPEC && L2 > 0.0f) ? __frcp_rn(L2) : 0.0f;
+    s.imax = 0u; s.dsum = s.dsq = make_float2(0.0f, 0.0f); s.dabs = 0.0f; s.ru = s.rl = 0;
+    k.inv_l2 = (SPEC && k.L2 > 0.0f) ? __frcp_rn(k.L2) : 0.0f;
+    k.o1 = (c1 - c0) * mpad; k.o2 = (c2 - c0) * mpad;
+    const float *tp = tp0 + c0 * mpad;
+    asm volatile("" : "+l"(tp));   // keep it a pointer: every load address is ONE IMAD.WIDE away
+    k.tp = tp;
     AtomBuf<NP> A, B;
 #pragma unroll
     for (int c = 0; c < 3; c++)
 #pragma unroll
         for (int p = 0; p < NP; p++) A.c[c][p] = B.c[c][p] = make_float2(0.0f, 0.0f);
-    int ru = 0, rl = 0;        // lane (b & 31) keeps the warp sums of bond b
-    bool first_in_a = true;    // which buffer holds the current bond's first atom (warp-uniform)
-    for (int b = 0; b < nb; b++) {
-        const BondItem bi = s_bonds[b];
-        if ((bi.a_off & 3) == 2) first_in_a = !first_in_a;   // the first atom is the previous bond's second atom: swap roles
-        if (first_in_a) fast_bond<NP, LEAF, SPEC>(A, B, tp, bi.a_off, bi.b_off, o0, o1, o2, L0, L1, L2, h0, h1, h2, g0, g1, g2, sref, sp_invL, cta_full, m0, td.n_mol, up, s);
-        else fast_bond<NP, LEAF, SPEC>(B, A, tp, bi.a_off, bi.b_off, o0, o1, o2, L0, L1, L2, h0, h1, h2, g0, g1, g2, sref, sp_invL, cta_full, m0, td.n_mol, up, s);
-        // fixed-order hardware tree (REDUX) -> deterministic
-        const int wu = __reduce_add_sync(0xffffffffu, LEAF ? s.su : s.st);
-        const int wl = LEAF ? __reduce_add_sync(0xffffffffu, s.st - s.su) : 0;
-        if ((b & 31) == lane) { ru = wu; rl = wl; }
-        if ((b & 31) == 31 || b == nb - 1) {
-            if (lane <= (b & 31)) {
-                int *p = s_acc + ((size_t)warp * nb + (b & ~31) + lane) * NA;
-                p[0] = ru;
-                if (LEAF) p[1] = rl;
-            }
-        }
+    int b = 0;
+    bool done = nb <= 0;
+    while (!done) {
+        do {   // the bond's first atom lives in A
+            fast_bond<NP, LEAF, SPEC>(A, B, k, s_bonds[b], b, up, s);
+            b++;
+            done = b >= nb;
+        } while (!done && (s_bonds[b].a_off & 3) != 2);
+        if (done) break;
+        do {   // ... in B (the previous bond's second atom became this bond's first)
+            fast_bond<NP, LEAF, SPEC>(B, A, k, s_bonds[b], b, up, s);
+            b++;
+            done = b >= nb;
+        } while (!done && (s_bonds[b].a_off & 3) != 2);
     }
     if (s.imax >= 0x7f800000u)   // AnalysisError::UndefinedPosition: a NaN / Inf coordinate reached the engine
-        raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | (unsigned)min(m0, td.n_mol - 1));
+        raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | (unsigned)m0);
     if (SPEC) {
         const float tsum = s.dsum.x + s.dsum.y;
         double ds = (double)s.dsum.x + (double)s.dsum.y, dq = (double)s.dsq.x + (double)s.dsq.y;
@@ -267,7 +286,9 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
         if (lane == 0) { s_dsum[0][warp] = ds; s_dsum[1][warp] = dq; s_dabs[warp] = a; }
     }
     __syncthreads();
-    cta_flush<LEAF, false>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
+    int cta_up = 0;
+    for (int w = 0; w < kWarps; w++) cta_up += s_nup[w];
+    cta_flush<LEAF, false>(v, o, s_acc, nb, td.slot0, ax.tw_row, kBlock * MPT, cta_up);
     if (SPEC && threadIdx.x == 0) {
         double ds = 0.0, dq = 0.0;
         float p0 = 0.0f, p1 = CUDART_INF_F, p2 = 0.0f;
@@ -277,7 +298,7 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
             bad = bad || s_dabs[w] != s_dabs[w] || s_hmm[0][w] != s_hmm[0][w];
             p0 = fmaxf(p0, s_dabs[w]); p1 = fminf(p1, s_hmm[0][w]); p2 = fmaxf(p2, s_hmm[1][w]);
         }
-        spec_publish(o, f, sref, L2, h2, ds, dq, p0, p1, p2, bad);
+        spec_publish(o, f, k.sref, k.L2, k.h2, ds, dq, p0, p1, p2, bad);
     }
 }
 

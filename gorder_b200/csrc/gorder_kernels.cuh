@@ -197,6 +197,7 @@ __global__ void frame_setup_kernel(DeviceView v, FrameAux *aux, const float *__r
             a.L[0] = a.L[1] = a.L[2] = 0.0f;
             a.half[0] = a.half[1] = a.half[2] = 0.0f;
         }
+        a.guard[0] = 0.99f * a.half[0]; a.guard[1] = 0.99f * a.half[1]; a.guard[2] = 0.99f * a.half[2];
     } else {
         if (v.handle_pbc) construct_shape<true>(v, a);
         else construct_shape<false>(v, a);
@@ -821,9 +822,9 @@ __device__ __forceinline__ void spec_publish(const AccumOut &o, int f, float sre
 // ---------------------------------------------------------------------------------------------
 //           SPEC speculative Global leaflets: no centre pre-pass (see AccumOut::spec_*).
 template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA, bool SPEC = false>
-__global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
-                                                            const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
-                                                            const int *__restrict__ normal_npoints, AccumOut o) {
+__device__ __forceinline__ void bond_order_body(const DeviceView &v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
+                                                const int *__restrict__ normal_npoints, const AccumOut &o) {
     constexpr int NA = AccLayout<LEAF, EXTRA>::N;
     // Static normal without geometry / maps: S depends only on (d_axis, |d|^2), so the kernel reads the
     // components in the order (axis+1, axis+2, axis) and never selects a component at run time.
@@ -1085,6 +1086,13 @@ __global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_ke
         }
         spec_publish(o, f, sref, L2, h2, ds, dq, p0, p1, p2, bad);
     }
+}
+
+template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA, bool SPEC = false>
+__global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                            const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
+                                                            const int *__restrict__ normal_npoints, AccumOut o) {
+    bond_order_body<MPT, PBC, NVEC, LEAF, EXTRA, SPEC>(v, planes, aux, leaf_rows, normals, normal_npoints, o);
 }
 
 // ---------------------------------------------------------------------------------------------
