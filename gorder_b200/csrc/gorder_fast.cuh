@@ -47,6 +47,11 @@ __device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) {
 }
 __device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
 
+// DRAM -> L2 prefetch of a contiguous run (one instruction, one thread): the CTA's slice of a plane
+__device__ __forceinline__ void l2_prefetch_bulk(const float *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // one atom of the lane's 2 NP molecules: component c of pair p
 template <int NP> struct AtomBuf { float2 c[3][NP]; };
 
@@ -255,16 +260,35 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
     for (int c = 0; c < 3; c++)
 #pragma unroll
         for (int p = 0; p < NP; p++) A.c[c][p] = B.c[c][p] = make_float2(0.0f, 0.0f);
+    // The kernel is bound by memory latency (8 warps per scheduler, ~150 issue slots between a warp's loads): one
+    // lane per CTA asks L2 for the CTA's slices (kBlock * MPT floats per component: contiguous) of the planes that the
+    // bonds kPrefetchAhead iterations later will read, so that the plane loads find their lines in L2.
+    constexpr int kPrefetchAhead = 2;
+    const float *tile0 = planes + (size_t)f * v.frame_floats + mol_offset(td, ch.first_mol) + c0 * mpad;
+    auto prefetch_bond = [&](int bb) {
+        if (threadIdx.x != 0 || bb >= nb || v.l2_hints < 0) return;
+        const BondItem it = s_bonds[bb];
+        constexpr unsigned bytes = kBlock * MPT * sizeof(float);
+        if ((it.a_off & 3) == 0) {
+            const float *pa = tile0 + (it.a_off & ~15);
+            l2_prefetch_bulk(pa, bytes); l2_prefetch_bulk(pa + k.o1, bytes); l2_prefetch_bulk(pa + k.o2, bytes);
+        }
+        const float *pb = tile0 + it.b_off;
+        l2_prefetch_bulk(pb, bytes); l2_prefetch_bulk(pb + k.o1, bytes); l2_prefetch_bulk(pb + k.o2, bytes);
+    };
+    for (int bb = 0; bb < kPrefetchAhead; bb++) prefetch_bond(bb);
     int b = 0;
     bool done = nb <= 0;
     while (!done) {
         do {   // the bond's first atom lives in A
+            prefetch_bond(b + kPrefetchAhead);
             fast_bond<NP, LEAF, SPEC>(A, B, k, s_bonds[b], b, up, s);
             b++;
             done = b >= nb;
         } while (!done && (s_bonds[b].a_off & 3) != 2);
         if (done) break;
         do {   // ... in B (the previous bond's second atom became this bond's first)
+            prefetch_bond(b + kPrefetchAhead);
             fast_bond<NP, LEAF, SPEC>(B, A, k, s_bonds[b], b, up, s);
             b++;
             done = b >= nb;
