@@ -91,7 +91,7 @@ class ClockSampler(threading.Thread):
 
 WORKLOADS = {
     # name: (description, default lipids, default frames per step)
-    "cg": ("S-CG: CGOrder Martini bilayer, Global leaflets every frame (BASELINE configs[1])", N_LIPIDS, 128),
+    "cg": ("S-CG: CGOrder Martini bilayer, Global leaflets every frame (BASELINE configs[1])", N_LIPIDS, 256),
     "aa": ("S-AA-small: AAOrder POPC-like, 64 C-H bond types, static z (BASELINE configs[0] shape)", 256, 2048),
     "ua": ("S-UA: UAOrder Berger-like, 64 virtual C-H, error blocks (BASELINE configs[2])", 256, 2048),
     "aa_maps": ("S-AA-large: AAOrder 4096 lipids, Global leaflets, XY order maps 0.1 nm, cylinder r=8 nm (BASELINE configs[3])", 4096, 128),

@@ -37,6 +37,10 @@ struct DevBuf {
         }                                                                                                \
     } while (0)
 
+// slots of c_fast (constant memory, per device): handles that do not get one use their global tables
+std::mutex g_fast_mu;
+bool g_fast_used[64][kFastSlots];
+
 }  // namespace
 
 struct GorderHandle {
@@ -141,6 +145,7 @@ struct GorderHandle {
     long long prof_n = 0;
 
     bool fast_ok = false;   // K1f applies (bond_fast_kernel)
+    int fast_slot = -1;     // slot of this handle's tables in constant memory (c_fast), -1: global tables
     // speculative Global leaflets (bond_order_kernel<SPEC> + spec_repair_kernel)
     bool spec_ok = false, spec_disabled = false, spec_ref_valid = false;
     int spec_cur = 0;
@@ -251,9 +256,9 @@ void launch_bond_spec(GorderHandle *h, dim3 grid, size_t smem, const float *plan
 // K1f (gorder_fast.cuh): PBC, static normal, no geometry / maps, 2 or 4 molecules per lane
 template <int NP>
 void launch_fast(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o, bool spec) {
-    if (!h->leaf) bond_fast_kernel<NP, false, false><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o);
-    else if (spec) bond_fast_kernel<NP, true, true><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o);
-    else bond_fast_kernel<NP, true, false><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o);
+    if (!h->leaf) bond_fast_kernel<NP, false, false><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o, h->fast_slot);
+    else if (spec) bond_fast_kernel<NP, true, true><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o, h->fast_slot);
+    else bond_fast_kernel<NP, true, false><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o, h->fast_slot);
 }
 
 template <int MPT>
@@ -626,6 +631,10 @@ void gorder_gpu_destroy(GorderHandle *h) {
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     }
     if (h->h_spec_counters) cudaFreeHost(h->h_spec_counters);
+    if (h->fast_slot >= 0) {
+        std::lock_guard<std::mutex> lock(g_fast_mu);
+        g_fast_used[h->device][h->fast_slot] = false;
+    }
     for (auto &e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -933,6 +942,22 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     }
 
     h->fast_ok = !ua && !h->nvec && !h->extra && s->handle_pbc && (h->mpt == 2 || h->mpt == 4);
+    if (h->fast_ok && s->n_moltypes <= kFastTypes && (int)bonds.size() <= kFastBonds && h->device < 64 && !getenv("GORDER_NO_CONST_TABLES")) {
+        {
+            std::lock_guard<std::mutex> lock(g_fast_mu);
+            for (int i = 0; i < kFastSlots && h->fast_slot < 0; i++)
+                if (!g_fast_used[h->device][i]) { g_fast_used[h->device][i] = true; h->fast_slot = i; }
+        }
+        if (h->fast_slot >= 0) {
+            FastTables ft{};
+            ft.n_types = s->n_moltypes;
+            int c = 0;
+            for (int t = 0; t < s->n_moltypes; t++) { ft.chunk0[t] = c; c += h->types[t].mpad / h->types[t].tile; ft.types[t] = h->types[t]; }
+            ft.chunk0[s->n_moltypes] = c;
+            for (size_t i = 0; i < bonds.size(); i++) ft.bonds[i] = bonds[i];
+            CK(cudaMemcpyToSymbol(c_fast, &ft, sizeof(ft), (size_t)h->fast_slot * sizeof(FastTables)));
+        }
+    }
     // speculative Global leaflets: AA/CG, static normal along the leaflet axis, PBC, assignment on every analysed frame,
     // no geometry / maps, membrane covered by the bond kernel's loads (above)
     h->spec_ok = mem_cover && mem_counted == s->n_membrane && !ua && !h->nvec && !h->extra && s->handle_pbc &&

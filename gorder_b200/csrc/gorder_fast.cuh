@@ -70,6 +70,17 @@ __device__ __forceinline__ void load_atom(AtomBuf<NP> &a, const float *p0, const
     }
 }
 
+// Frame-invariant tables of a handle in constant memory: a CTA lives for ~15 us, the chain of dependent
+// global loads chunk -> type -> bond table at its start (3 x L2 latency) was a quarter of its stall time.
+constexpr int kFastSlots = 8, kFastTypes = 8, kFastBonds = 128;
+struct FastTables {
+    int n_types;
+    int chunk0[kFastTypes + 1];   // first chunk of every molecule type
+    TypeDesc types[kFastTypes];
+    BondItem bonds[kFastBonds];
+};
+__constant__ FastTables c_fast[kFastSlots];
+
 // per-thread state of the bond loop
 template <int NP> struct FastState {
     unsigned imax;         // max bit pattern of |d|^2 seen so far (NaN / Inf detector)
@@ -173,32 +184,65 @@ __device__ __forceinline__ void fast_bond(AtomBuf<NP> &first, AtomBuf<NP> &other
 
 template <int NP, bool LEAF, bool SPEC>
 __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
-                                                              const unsigned char *__restrict__ leaf_rows, AccumOut o) {
+                                                              const unsigned char *__restrict__ leaf_rows, AccumOut o, int fast_slot) {
     constexpr int MPT = 2 * NP;
     constexpr int NA = LEAF ? 2 : 1;
-    {   // the last tile of a molecule type (molecules past the end) takes the generic, masked code
-        const Chunk ch = v.chunks[blockIdx.x];
-        if (ch.first_mol + kBlock * MPT > v.types[ch.type].n_mol) {
-            bond_order_body<MPT, true, false, LEAF, false, SPEC>(v, planes, aux, leaf_rows, nullptr, nullptr, o);
-            return;
-        }
-    }
     extern __shared__ int smem[];
-    const Chunk ch = v.chunks[blockIdx.x];
-    const TypeDesc td = v.types[ch.type];
+    __shared__ int s_nup[kWarps];
+    __shared__ unsigned s_done;
+    __shared__ float s_hmm[2][kWarps];
+    __shared__ double s_dsum[2][kWarps];
+    __shared__ float s_dabs[kWarps];
+    Chunk ch;
+    TypeDesc td;
+    if (fast_slot >= 0) {   // tables in constant memory: no global load before the first plane load
+        const FastTables &ft = c_fast[fast_slot];
+        int t = 0;
+        while (t + 1 < ft.n_types && (int)blockIdx.x >= ft.chunk0[t + 1]) t++;
+        td = ft.types[t];
+        ch.type = t; ch.first_mol = ((int)blockIdx.x - ft.chunk0[t]) * (kBlock * MPT);
+    } else {
+        ch = v.chunks[blockIdx.x];
+        td = v.types[ch.type];
+    }
+    if (ch.first_mol + kBlock * MPT > td.n_mol) {   // the last tile of a molecule type (molecules past the end) takes the generic, masked code
+        bond_order_body<MPT, true, false, LEAF, false, SPEC>(v, planes, aux, leaf_rows, nullptr, nullptr, o);
+        return;
+    }
     const int f = blockIdx.y;
     const FrameAux &ax = aux[f];
     const int nb = td.n_items;
+    const int mpad = td.cstride;
+    const int c0 = (v.normal_axis + 1) % 3, c1 = (v.normal_axis + 2) % 3, c2 = v.normal_axis;   // the normal axis comes last
     BondItem *s_bonds = reinterpret_cast<BondItem *>(smem);
     int *s_acc = smem + 2 * nb;                 // [kWarps][nb][NA]
-    for (int i = threadIdx.x; i < nb; i += kBlock) s_bonds[i] = v.bonds[td.item_off + i];
+    for (int i = threadIdx.x; i < nb; i += kBlock) s_bonds[i] = fast_slot >= 0 ? c_fast[fast_slot].bonds[td.item_off + i] : v.bonds[td.item_off + i];
+    if (threadIdx.x == 0) s_done = 0u;
+    // The kernel is bound by memory latency (8 warps per scheduler, ~150 issue slots between a warp's loads): one
+    // lane per CTA asks L2 for the CTA's slices (kBlock * MPT floats per component: contiguous) of the planes that the
+    // bonds kPrefetchAhead iterations later will read, so that the plane loads find their lines in L2.
+    constexpr int kPrefetchAhead = 2;   // measured: 1 -> 0.78, 2 -> 0.80, 3 -> 0.78, 6 -> 0.77, 11 -> 0.75 of the HBM peak
+    constexpr unsigned kSliceBytes = kBlock * MPT * sizeof(float);
+    const float *tile0 = planes + (size_t)f * v.frame_floats + mol_offset(td, ch.first_mol);
+    if (threadIdx.x == 0 && v.l2_hints >= 0 && LEAF && (SPEC || o.inline_center)) l2_prefetch_bulk(tile0 + td.head_off + v.leaflet_axis * mpad, kSliceBytes);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m0 = ch.first_mol + threadIdx.x * MPT;
-    const int mpad = td.cstride;
-    const int c0 = (v.normal_axis + 1) % 3, c1 = (v.normal_axis + 2) % 3, c2 = v.normal_axis;   // the normal axis comes last
     FastConst k;
+    k.o1 = (c1 - c0) * mpad; k.o2 = (c2 - c0) * mpad;
+    auto prefetch_bond = [&](int bb) {
+        if (threadIdx.x != 0 || bb >= nb || v.l2_hints < 0) return;
+        const BondItem it = s_bonds[bb];
+        const float *t0 = tile0 + c0 * mpad;
+        if ((it.a_off & 3) == 0) {
+            const float *pa = t0 + (it.a_off & ~15);
+            l2_prefetch_bulk(pa, kSliceBytes); l2_prefetch_bulk(pa + k.o1, kSliceBytes); l2_prefetch_bulk(pa + k.o2, kSliceBytes);
+        }
+        const float *pb = t0 + it.b_off;
+        l2_prefetch_bulk(pb, kSliceBytes); l2_prefetch_bulk(pb + k.o1, kSliceBytes); l2_prefetch_bulk(pb + k.o2, kSliceBytes);
+    };
+    for (int bb = 0; bb < kPrefetchAhead; bb++) prefetch_bond(bb);
     k.L0 = ax.L[c0]; k.L1 = ax.L[c1]; k.L2 = ax.L[c2];
     k.h0 = ax.half[c0]; k.h1 = ax.half[c1]; k.h2 = ax.half[c2];
     k.g0 = ax.guard[c0]; k.g1 = ax.guard[c1]; k.g2 = ax.guard[c2];
@@ -229,10 +273,6 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
         }
         nup += up[j];
     }
-    __shared__ int s_nup[kWarps];
-    __shared__ float s_hmm[2][kWarps];
-    __shared__ double s_dsum[2][kWarps];
-    __shared__ float s_dabs[kWarps];
     {
         const int a = __reduce_add_sync(0xffffffffu, nup);
         if (lane == 0) s_nup[warp] = a;
@@ -251,7 +291,6 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
     FastState<NP> s;
     s.imax = 0u; s.dsum = s.dsq = make_float2(0.0f, 0.0f); s.dabs = 0.0f; s.ru = s.rl = 0;
     k.inv_l2 = (SPEC && k.L2 > 0.0f) ? __frcp_rn(k.L2) : 0.0f;
-    k.o1 = (c1 - c0) * mpad; k.o2 = (c2 - c0) * mpad;
     const float *tp = tp0 + c0 * mpad;
     asm volatile("" : "+l"(tp));   // keep it a pointer: every load address is ONE IMAD.WIDE away
     k.tp = tp;
@@ -260,23 +299,6 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
     for (int c = 0; c < 3; c++)
 #pragma unroll
         for (int p = 0; p < NP; p++) A.c[c][p] = B.c[c][p] = make_float2(0.0f, 0.0f);
-    // The kernel is bound by memory latency (8 warps per scheduler, ~150 issue slots between a warp's loads): one
-    // lane per CTA asks L2 for the CTA's slices (kBlock * MPT floats per component: contiguous) of the planes that the
-    // bonds kPrefetchAhead iterations later will read, so that the plane loads find their lines in L2.
-    constexpr int kPrefetchAhead = 2;
-    const float *tile0 = planes + (size_t)f * v.frame_floats + mol_offset(td, ch.first_mol) + c0 * mpad;
-    auto prefetch_bond = [&](int bb) {
-        if (threadIdx.x != 0 || bb >= nb || v.l2_hints < 0) return;
-        const BondItem it = s_bonds[bb];
-        constexpr unsigned bytes = kBlock * MPT * sizeof(float);
-        if ((it.a_off & 3) == 0) {
-            const float *pa = tile0 + (it.a_off & ~15);
-            l2_prefetch_bulk(pa, bytes); l2_prefetch_bulk(pa + k.o1, bytes); l2_prefetch_bulk(pa + k.o2, bytes);
-        }
-        const float *pb = tile0 + it.b_off;
-        l2_prefetch_bulk(pb, bytes); l2_prefetch_bulk(pb + k.o1, bytes); l2_prefetch_bulk(pb + k.o2, bytes);
-    };
-    for (int bb = 0; bb < kPrefetchAhead; bb++) prefetch_bond(bb);
     int b = 0;
     bool done = nb <= 0;
     while (!done) {
@@ -309,11 +331,35 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
         }
         if (lane == 0) { s_dsum[0][warp] = ds; s_dsum[1][warp] = dq; s_dabs[warp] = a; }
     }
-    __syncthreads();
+    // No barrier at the end: the warp that finishes last adds the CTA's partials (in warp order: deterministic)
+    // to the frame's accumulators; the others retire and free their slots for the next CTA.
+    __syncwarp();
+    __threadfence_block();
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&s_done, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != kWarps - 1) return;
+    __threadfence_block();
     int cta_up = 0;
     for (int w = 0; w < kWarps; w++) cta_up += s_nup[w];
-    cta_flush<LEAF, false>(v, o, s_acc, nb, td.slot0, ax.tw_row, kBlock * MPT, cta_up);
-    if (SPEC && threadIdx.x == 0) {
+    const int cnt_total = kBlock * MPT;
+    for (int i = lane; i < nb; i += 32) {
+        long long acc0 = 0, acc1 = 0;
+        for (int w = 0; w < kWarps; w++) {
+            const int *p = s_acc + ((size_t)w * nb + i) * NA;
+            acc0 += p[0];
+            if (LEAF) acc1 += p[1];
+        }
+        const size_t base = ((size_t)ax.tw_row * v.n_slots + td.slot0 + i) * 3;
+        if (LEAF) {
+            const int c_up = cta_up, c_lo = cnt_total - cta_up;
+            if (c_up) { atomicAdd((unsigned long long *)&o.bsum[base + GORDER_ACC_UPPER], (unsigned long long)acc0); atomicAdd(&o.bcnt[base + GORDER_ACC_UPPER], (unsigned long long)c_up); }
+            if (c_lo) { atomicAdd((unsigned long long *)&o.bsum[base + GORDER_ACC_LOWER], (unsigned long long)acc1); atomicAdd(&o.bcnt[base + GORDER_ACC_LOWER], (unsigned long long)c_lo); }
+        } else {
+            atomicAdd((unsigned long long *)&o.bsum[base + GORDER_TOTAL], (unsigned long long)acc0); atomicAdd(&o.bcnt[base + GORDER_TOTAL], (unsigned long long)cnt_total);
+        }
+    }
+    if (SPEC && lane == 0) {
         double ds = 0.0, dq = 0.0;
         float p0 = 0.0f, p1 = CUDART_INF_F, p2 = 0.0f;
         bool bad = false;
