@@ -132,6 +132,14 @@ def config(args, s, extra=None):
     return c
 
 
+def hot_kernel_name(st, lipids):
+    """Name of the accumulation kernel gorder_gpu_profile brackets for this configuration (gorder_capi.cu dispatch)."""
+    if st.kind == 2:
+        return "ua_order_kernel"
+    plain = st.handle_pbc and st.normal_mode == 0 and not st.map_enabled and st.geom_kind == 0
+    return "bond_fast_kernel" if plain and lipids >= 1024 and not os.environ.get("GORDER_NO_FAST") else "bond_order_kernel"
+
+
 def cpu_oracle_rate(s, xyz, box, threads, min_seconds):
     """Time the oracle port (all host threads) on the given frames, repeated until min_seconds."""
     from oracle import oracle as orc
@@ -182,6 +190,9 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # libraries (NCCL, torchrun) may print to stdout: keep fd 1 for the ONE JSON line, send everything else to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -194,7 +205,6 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: gorder_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     s = make_system(args)
     s.setup.device = local
@@ -224,7 +234,12 @@ def run_ours(args):
         step(k)
     eng.sync()
     block_ptr, n_words = eng.accumulator_block()
-    red = torch.zeros(n_words, dtype=torch.int64, device="cuda")
+
+    class _Block:   # zero-copy view of the engine's contiguous int64 accumulator block (sums, counts, maps)
+        __cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (block_ptr, False), "version": 2}
+
+    block = torch.as_tensor(_Block(), device=torch.device("cuda", local))
+    assert block.data_ptr() == block_ptr and block.dtype == torch.int64
     if world > 1:
         # warm the communicator with the same collective the job ends with (channel setup is not part of a step)
         warm = torch.zeros(n_words, dtype=torch.int64, device="cuda")
@@ -235,17 +250,14 @@ def run_ours(args):
     eng.profile(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_win0 = time.perf_counter()
-    ev0.record(stream)
-    for k in range(W, W + K):
-        step(k)
-    if world > 1:   # the single collective of the job: sum the integer accumulators on rank 0
-        eng.read_block(red.data_ptr())
-        dist.reduce(red, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            torch.cuda.synchronize()
-            eng.write_block(red.data_ptr())
-    eng.fence()   # the tail (repair + fold) of the last batch runs on a helper stream: the closing event waits for it
-    ev1.record(stream)
+    with torch.cuda.stream(stream):   # the engine's main stream is torch's current stream: NCCL orders itself after it
+        ev0.record()
+        for k in range(W, W + K):
+            step(k)
+        eng.fence()   # the tail (repair + fold) of the last batch runs on a helper stream: the main stream waits for it
+        if world > 1:   # the single collective of the job: sum the integer accumulators in place on rank 0 (no host sync)
+            dist.reduce(block, dst=0, op=dist.ReduceOp.SUM)
+        ev1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -339,7 +351,7 @@ def run_ours(args):
                     "entry": "gorder_gpu_submit (pinned host [atom][xyz] frames) + gorder_gpu_finish", "timer": "host wall clock between device syncs"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "kernel": "ua_order_kernel" if s.setup.kind == 2 else "bond_order_kernel", "launches_timed": hot_n, "avg_launch_ms": hot_ms / max(hot_n, 1),
+                         "traffic": traffic, "kernel": hot_kernel_name(s.setup, args.lipids), "launches_timed": hot_n, "avg_launch_ms": hot_ms / max(hot_n, 1),
                          "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
                          "step_share": (hot_ms / ms) if ms else None,
                          "note": ("in-step duration; speculative Global leaflets: no centre pre-pass, the kernel runs alone" if spec_stats["enabled"] else
@@ -355,7 +367,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 def main():

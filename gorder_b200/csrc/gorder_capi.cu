@@ -672,7 +672,10 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     // molecules per thread of the bond kernel (tunable: GORDER_MPT)
     int max_mol = 0;
     for (int t = 0; t < s->n_moltypes; t++) max_mol = std::max(max_mol, s->moltypes[t].n_molecules);
-    h->mpt = max_mol >= 148 * kBlock * 4 / 2 ? 4 : (max_mol >= 148 * kBlock ? 2 : 1);
+    // a batch supplies the parallelism (grid = tiles x frames), so the vector width only has to leave most molecules in
+    // full tiles (kBlock * mpt molecules: the fast kernel's unit; a partial last tile runs the generic body)
+    h->mpt = (max_mol >= 8 * kBlock * 4 || (max_mol >= kBlock * 4 && max_mol % (kBlock * 4) == 0)) ? 4
+           : (max_mol >= 8 * kBlock * 2 || (max_mol >= kBlock * 2 && max_mol % (kBlock * 2) == 0)) ? 2 : 1;
     if (const char *e = getenv("GORDER_MPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->mpt = v; }
     if (ua) h->mpt = 1;
 
