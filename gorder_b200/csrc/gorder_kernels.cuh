@@ -321,9 +321,23 @@ __device__ __forceinline__ float distance_1d(float a, float b, float L, float ha
     return (pbc && L > 0.0f) ? min_image(d, L, half) : d;
 }
 
+// 2-D cell list over the membrane atoms for the Local method (the reference builds a CellGrid with cell edge >= radius
+// and visits the 3 x 3 columns around the head, pbc.rs:280-303): columns along the leaflet axis, cells over the two
+// lateral axes.  lcell_sorted holds (lateral 0, lateral 1, axis coordinate, -) per atom in cell order.
+constexpr int kLCellMaxDim = 256;
+__device__ __forceinline__ void lcell_dims(const FrameAux &a, float radius, int ax, int (&n)[2]) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float L = a.L[(ax + 1 + k) % 3];
+        n[k] = min(max((int)floorf(L / radius), 1), kLCellMaxDim);
+    }
+}
+
 __global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                              const int *__restrict__ frame_list, const float *__restrict__ center,
-                                                             const int *__restrict__ molpad_type, unsigned char *__restrict__ rows) {
+                                                             const int *__restrict__ molpad_type, unsigned char *__restrict__ rows,
+                                                             const int *__restrict__ lcell_start = nullptr, const float4 *__restrict__ lcell_sorted = nullptr,
+                                                             int lcells_cap = 0) {
     const int ai = blockIdx.y, f = frame_list[ai];
     const int mp = blockIdx.x * blockDim.x + threadIdx.x;
     if (mp >= v.n_molpad) return;
@@ -357,6 +371,47 @@ __global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const
             long long row = v.leaflet_freq_kind == GORDER_FREQ_ONCE ? 0 : a.frame_index / (v.leaflet_freq > 0 ? v.leaflet_freq : 1);
             if (row >= td.n_manual_leaf) { raise_error(v, GORDER_ERR_MANUAL_LEAFLET_FRAME, a.frame_index); }
             else upper = v.manual_leaflets[td.manual_leaf_off + row * td.n_mol + m] == GORDER_UPPER;
+        } else if (v.leaflet_mode == GORDER_LEAFLET_LOCAL && lcell_start) {   // leaflets.rs:630-707, pbc.rs:273-318 with the cell list
+            const int a0 = (ax + 1) % 3, a1 = (ax + 2) % 3;
+            const float h0 = fr[td.head_off + a0 * cst], h1 = fr[td.head_off + a1 * cst], hax = fr[td.head_off + ax * cst];
+            int n[2];
+            lcell_dims(a, v.leaflet_radius, ax, n);
+            const float L0 = a.L[a0], L1 = a.L[a1], hf0 = a.half[a0], hf1 = a.half[a1];
+            const int c0 = min(max((int)(wrap1(h0, L0) * (float)n[0] / L0), 0), n[0] - 1), c1 = min(max((int)(wrap1(h1, L1) * (float)n[1] / L1), 0), n[1] - 1);
+            const int *st = lcell_start + (size_t)ai * (lcells_cap + 1);
+            const float4 *srt = lcell_sorted + (size_t)ai * v.membrane.n;
+            const int lo0 = n[0] >= 3 ? -1 : 0, hi0 = n[0] >= 3 ? 1 : n[0] - 1, lo1 = n[1] >= 3 ? -1 : 0, hi1 = n[1] >= 3 ? 1 : n[1] - 1;
+            const float scale = __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L);
+            double sc = 0, ss = 0, sn = 0;
+            int cnt = 0;
+            float est = 0.0f;
+            for (int pass = 0; pass < 2; pass++) {
+                if (pass == 1) {
+                    if (cnt == 0) break;
+                    const float th = __fadd_rn(atan2f(-(float)ss, -(float)sc), CUDART_PI_F);
+                    est = __fdiv_rn(__fmul_rn(L, th), __fmul_rn(2.0f, CUDART_PI_F));
+                }
+                for (int d0 = lo0; d0 <= hi0; d0++) {
+                    const int x0 = n[0] >= 3 ? (c0 + d0 + n[0]) % n[0] : d0;
+                    for (int d1 = lo1; d1 <= hi1; d1++) {
+                        const int x1 = n[1] >= 3 ? (c1 + d1 + n[1]) % n[1] : d1;
+                        const int cell = x0 * n[1] + x1;
+                        for (int k = st[cell]; k < st[cell + 1]; k++) {
+                            const float4 q = __ldg(srt + k);
+                            const float e0 = min_image(__fsub_rn(q.x, h0), L0, hf0), e1 = min_image(__fsub_rn(q.y, h1), L1, hf1);
+                            // r2 in the oracle's component order (ascending axis index)
+                            const float r2 = a0 < a1 ? __fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1)) : __fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e0, e0));
+                            if (!(__fsqrt_rn(r2) < v.leaflet_radius)) continue;
+                            if (pass == 0) { cnt++; float sv, cv; sincosf(__fmul_rn(q.z, scale), &sv, &cv); sc += cv; ss += sv; }
+                            else sn += min_image(__fsub_rn(q.z, est), L, half);
+                        }
+                    }
+                }
+            }
+            float c = CUDART_NAN_F;
+            if (cnt > 0) { c = __fadd_rn(est, __fdiv_rn((float)sn, (float)cnt)); c = wrap1(c, L); }
+            if (c != c) raise_error(v, GORDER_ERR_INVALID_LOCAL_CENTER, ((long long)t << 32) | (unsigned)m);
+            upper = distance_1d(hax, c, L, half, true) >= 0.0f;
         } else if (v.leaflet_mode == GORDER_LEAFLET_LOCAL) {   // leaflets.rs:630-707, pbc.rs:273-318
             // centre of the membrane atoms inside an infinite cylinder around the head (brute force)
             f3 head = mk3(fr[td.head_off], fr[td.head_off + cst], fr[td.head_off + 2 * cst]);
@@ -639,6 +694,75 @@ __global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, 
     nx[0] = nrm.x; nx[v.n_molpad] = nrm.y; nx[2 * (size_t)v.n_molpad] = nrm.z;
 }
 
+// 2-D cell list of the membrane atoms (Local leaflets): count / scan / fill over the assignment frames of a batch.
+__global__ void __launch_bounds__(256) lcell_count_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+                                                          const int *__restrict__ frame_list, int *__restrict__ atom_cell, int *__restrict__ cell_count,
+                                                          int cells_cap) {
+    const int ai = blockIdx.y, f = frame_list[ai], i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.membrane.n) return;
+    const FrameAux &a = aux[f];
+    const int ax = v.leaflet_axis, a0 = (ax + 1) % 3, a1 = (ax + 2) % 3;
+    int n[2];
+    lcell_dims(a, v.leaflet_radius, ax, n);
+    const float *fr = planes + (size_t)f * v.frame_floats;
+    const int off = v.membrane.off[i];
+    const size_t cs = (size_t)v.membrane.cs[i];
+    const float p0 = fr[off + a0 * cs], p1 = fr[off + a1 * cs];
+    const int c0 = min(max((int)(wrap1(p0, a.L[a0]) * (float)n[0] / a.L[a0]), 0), n[0] - 1);
+    const int c1 = min(max((int)(wrap1(p1, a.L[a1]) * (float)n[1] / a.L[a1]), 0), n[1] - 1);
+    const int c = c0 * n[1] + c1;
+    atom_cell[(size_t)ai * v.membrane.n + i] = c;
+    atomicAdd(&cell_count[(size_t)ai * cells_cap + c], 1);
+}
+
+__global__ void __launch_bounds__(1024) lcell_scan_kernel(DeviceView v, const FrameAux *__restrict__ aux, const int *__restrict__ frame_list,
+                                                          int *__restrict__ cell_count, int *__restrict__ cell_start, int cells_cap) {
+    const int ai = blockIdx.x;
+    int n[2];
+    lcell_dims(aux[frame_list[ai]], v.leaflet_radius, v.leaflet_axis, n);
+    const int nc = n[0] * n[1];
+    int *cnt = cell_count + (size_t)ai * cells_cap, *st = cell_start + (size_t)ai * (cells_cap + 1);
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nc; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int x = i < nc ? cnt[i] : 0;
+        int incl = x;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - x;
+        if (i < nc) { st[i] = excl; cnt[i] = 0; }   // the counts become the fill cursors
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st[nc] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) lcell_fill_kernel(DeviceView v, const float *__restrict__ planes, const int *__restrict__ frame_list,
+                                                         const int *__restrict__ atom_cell, int *__restrict__ cell_count,
+                                                         const int *__restrict__ cell_start, float4 *__restrict__ sorted_pos, int cells_cap) {
+    const int ai = blockIdx.y, f = frame_list[ai], i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.membrane.n) return;
+    const int c = atom_cell[(size_t)ai * v.membrane.n + i];
+    const int pos = cell_start[(size_t)ai * (cells_cap + 1) + c] + atomicAdd(&cell_count[(size_t)ai * cells_cap + c], 1);
+    const int ax = v.leaflet_axis, a0 = (ax + 1) % 3, a1 = (ax + 2) % 3;
+    const float *fr = planes + (size_t)f * v.frame_floats;
+    const int off = v.membrane.off[i];
+    const size_t cs = (size_t)v.membrane.cs[i];
+    sorted_pos[(size_t)ai * v.membrane.n + pos] = make_float4(fr[off + a0 * cs], fr[off + a1 * cs], fr[off + ax * cs], 0.0f);
+}
+
 // manual membrane normals (ManualMembraneNormal::get_normal, normal.rs:266-298): copy the row of
 // this frame into the per-frame normal planes; NaN when the frame is not available (the error is
 // raised by the accumulation kernel when the normal is actually used).
@@ -725,9 +849,9 @@ __device__ __forceinline__ void warp_commit(int *s_acc, int lane, int su, int sl
 // CTA epilogue: add the per-warp partials of every order slot to this frame's accumulators.
 template <bool LEAF, bool EXTRA>
 __device__ __forceinline__ void cta_flush(const DeviceView &v, const AccumOut &o, const int *s_acc, int n_orders, int slot0, int tw_row,
-                                          int cnt_total, int cnt_up) {
+                                          int cnt_total, int cnt_up, int i_lo = 0, int i_hi = 0x7fffffff) {
     constexpr int NA = AccLayout<LEAF, EXTRA>::N;
-    for (int i = threadIdx.x; i < n_orders; i += blockDim.x) {
+    for (int i = i_lo + threadIdx.x; i < min(n_orders, i_hi); i += blockDim.x) {
         long long acc[NA];
 #pragma unroll
         for (int k = 0; k < NA; k++) acc[k] = 0;
@@ -947,7 +1071,11 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
         nx1.load(base + a_off + o0); ny1.load(base + a_off + o1); nz1.load(base + a_off + o2);
         nx2.load(base + b0.b_off + o0); ny2.load(base + b0.b_off + o1); nz2.load(base + b0.b_off + o2);
     }
-    for (int b = 0; b < nb; b++) {
+    // gridDim.z > 1 (order maps): CTA z handles the z-th group of bond types, so that the CTAs resident at any time
+    // scatter into the maps of a few bond types only and the atomics stay in L2 (the maps of all types do not fit)
+    const int b_lo = gridDim.z > 1 ? (int)((long long)nb * blockIdx.z / gridDim.z) : 0;
+    const int b_hi = gridDim.z > 1 ? (int)((long long)nb * (blockIdx.z + 1) / gridDim.z) : nb;
+    for (int b = b_lo; b < b_hi; b++) {
         if (PREFETCH) {
             // rotate: the prefetched registers become the current bond ...
             x1 = nx1; y1 = ny1; z1 = nz1; x2 = nx2; y2 = ny2; z2 = nz2;
@@ -966,7 +1094,7 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
             const BondItem bi = s_bonds[b];
             // low bits of a_off: 1 = first atom is the previous bond's first atom, 2 = ... second atom;
             // 4 / 8 = first / second atom is a membrane atom seen here for the first time (speculative centre)
-            const int reuse = bi.a_off & 3, a_off = bi.a_off & ~15;
+            const int reuse = (b == b_lo) ? 0 : (bi.a_off & 3), a_off = bi.a_off & ~15;
             if (reuse == 2) { x1 = x2; y1 = y2; z1 = z2; }
             if (active) {
                 if (v.l2_hints) {   // stream through L2 without displacing the axis planes the centre passes keep there
@@ -1074,7 +1202,7 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
         if (lane == 0) { s_dsum[0][warp] = ds; s_dsum[1][warp] = dq; s_dabs[warp] = a; }
     }
     __syncthreads();
-    cta_flush<LEAF, EXTRA>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
+    cta_flush<LEAF, EXTRA>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1], b_lo, b_hi);
     if (SPEC && threadIdx.x == 0) {
         double ds = 0.0, dq = 0.0;
         float p0 = 0.0f, p1 = CUDART_INF_F, p2 = 0.0f;

@@ -250,3 +250,59 @@ def test_nan_in_native_frames_is_reported():
             eng.finish()
         assert e.value.code == abi.ERR_UNDEFINED_POSITION
         eng.close()
+
+
+@pytest.mark.parametrize("mpt", [2, 4])
+@pytest.mark.parametrize("mode,freq", [(abi.LEAFLET_GLOBAL, ("every", 3)), (abi.LEAFLET_GLOBAL, ("once", 1)),
+                                       (abi.LEAFLET_INDIVIDUAL, ("every", 1)), (abi.LEAFLET_NONE, ("every", 1))])
+def test_fast_kernel_leaflet_tables(mode, freq, mpt, monkeypatch):
+    """bond_fast_kernel (full tiles) + the generic body (partial last tile) with leaflets read from the table
+    (assignment not on every frame / Individual method) and without leaflets; several batches, per-frame rows."""
+    monkeypatch.setenv("GORDER_MPT", str(mpt))
+    kind, n = freq
+    s = synthetic.s_cg(4500, leaflet_mode=mode, leaflet_freq_kind=abi.FREQ_ONCE if kind == "once" else abi.FREQ_EVERY,
+                       leaflet_freq=n, collect_leaflets=mode != abi.LEAFLET_NONE, timewise=True, split_types=2)
+    xyz, box, idx = _frames(s, 7)
+    g, r = run_both(s.setup, xyz, box, idx, batches=3)
+    assert_raw_parity(g, r, s.setup, what=f"fast kernel, leaflet table {mode} {freq} mpt {mpt}")
+    monkeypatch.setenv("GORDER_NO_FAST", "1")
+    g0, _ = run_both(s.setup, xyz, box, idx, batches=2)
+    np.testing.assert_array_equal(g.sum, g0.sum)      # the two kernels agree bit for bit
+    np.testing.assert_array_equal(g.tw_sum, g0.tw_sum)
+    np.testing.assert_array_equal(g.count, g0.count)
+
+
+@pytest.mark.parametrize("axis", [abi.AXIS_X, abi.AXIS_Y])
+@pytest.mark.parametrize("mpt", [1, 4])
+def test_membrane_normal_along_x_or_y(axis, mpt, monkeypatch):
+    """Membrane normal / leaflet axis other than z: the kernels read the components in a permuted order."""
+    monkeypatch.setenv("GORDER_MPT", str(mpt))
+    s = synthetic.s_cg(2100, leaflet_mode=abi.LEAFLET_GLOBAL, collect_leaflets=True)
+    s.setup.normal_axis = axis
+    s.setup.leaflet_axis = axis
+    xyz, box, idx = _frames(s, 4)
+    perm = [0, 1, 2]
+    perm[axis], perm[2] = 2, axis
+    xyz, box = np.ascontiguousarray(xyz[..., perm]), np.ascontiguousarray(box[..., perm])
+    g, r = run_both(s.setup, xyz, box, idx)
+    assert abs(int(r.leaflets[0].astype(int).sum()) - 1050) <= 2
+    assert_raw_parity(g, r, s.setup, what=f"normal axis {axis}")
+
+
+@pytest.mark.parametrize("n_lipids,axis", [(150, abi.AXIS_Z), (2600, abi.AXIS_Z), (900, abi.AXIS_Y)])
+def test_local_leaflets_cell_list(n_lipids, axis, monkeypatch):
+    """Local leaflet method with the 2-D cell list over the membrane atoms (default for >= 4096 membrane atoms), against
+    the oracle's brute-force cylinder search; also with the membrane normal along y."""
+    monkeypatch.setenv("GORDER_LCELL_MIN_ATOMS", "0")
+    s = synthetic.s_cg(n_lipids, leaflet_mode=abi.LEAFLET_LOCAL, leaflet_radius=2.5, collect_leaflets=True, timewise=True)
+    s.setup.normal_axis = axis
+    s.setup.leaflet_axis = axis
+    xyz, box, idx = _frames(s, 3)
+    if axis != abi.AXIS_Z:
+        perm = [0, 1, 2]
+        perm[axis], perm[2] = 2, axis
+        xyz, box = np.ascontiguousarray(xyz[..., perm]), np.ascontiguousarray(box[..., perm])
+    g, r = run_both(s.setup, xyz, box, idx, batches=2, oracle_threads=8)
+    up = r.leaflets.astype(int).sum(axis=1)
+    assert np.all(np.abs(up - (n_lipids + 1) // 2) <= 2), up
+    assert_raw_parity(g, r, s.setup, what=f"local leaflets, cell list, {n_lipids} lipids, axis {axis}")
