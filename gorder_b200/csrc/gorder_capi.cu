@@ -943,7 +943,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         if (const char *e = getenv("GORDER_CELL_MIN_HEADS")) min_heads = atoi(e);
         h->use_cells = s->n_normal_heads >= min_heads;
         if (h->use_cells) {
-            h->cells_cap = kCellMaxDim * kCellMaxDim * kCellMaxDim;
+            h->cells_cap = kCellBudget;
             if ((rc = dev_alloc(h, &h->d_head_cell, B * (size_t)s->n_normal_heads))) return rc;
             if ((rc = dev_alloc(h, &h->d_cell_sorted, B * (size_t)s->n_normal_heads))) return rc;
             if ((rc = dev_alloc(h, &h->d_cell_count, B * (size_t)h->cells_cap))) return rc;

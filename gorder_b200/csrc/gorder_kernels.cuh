@@ -554,15 +554,23 @@ __global__ void __launch_bounds__(128) dynamic_normal_kernel(DeviceView v, const
 //                      centroid + scatter matrix relative to the reference head (f64 sums: the
 //                      gather order inside a cell is arbitrary, f64 makes the result independent of
 //                      it to ~1e-13, i.e. bit-stable after rounding to f32), Jacobi smallest eigenvector.
-// Grid: n_k = clamp(floor(L_k / radius), 1, kCellMaxDim) cells along k (cell edge L_k / n_k >= radius).
+// Grid: n_k = max(floor(L_k / radius), 1) cells along k (cell edge L_k / n_k >= radius), at most kCellBudget cells per frame.
 // ---------------------------------------------------------------------------------------------
-constexpr int kCellMaxDim = 40;
+constexpr int kCellBudget = 1 << 18;   // cells per frame (count + start arrays: 2 MB per frame)
 
 __device__ __forceinline__ void cell_dims(const FrameAux &a, float radius, int (&n)[3]) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        int q = (int)floorf(a.L[k] / radius);
-        n[k] = min(max(q, 1), kCellMaxDim);
+    for (int k = 0; k < 3; k++) n[k] = min(max((int)floorf(a.L[k] / radius), 1), 4096);
+    // a very large box: shrink the grid uniformly (coarser cells are still correct, the exact distance test decides)
+    long long prod = (long long)n[0] * n[1] * n[2];
+    if (prod > kCellBudget) {
+        const float sc = cbrtf((float)kCellBudget / (float)prod);
+#pragma unroll
+        for (int k = 0; k < 3; k++) n[k] = max((int)((float)n[k] * sc), 1);
+        while ((long long)n[0] * n[1] * n[2] > kCellBudget) {
+            const int big = (n[0] >= n[1] && n[0] >= n[2]) ? 0 : (n[1] >= n[2] ? 1 : 2);
+            if (big == 0) n[0]--; else if (big == 1) n[1]--; else n[2]--;
+        }
     }
 }
 __device__ __forceinline__ int cell_coord(float x, float L, int n) {
