@@ -498,7 +498,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
             dim3 gh((nh + 255) / 256, nf);
             cell_count_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, da, h->d_head_cell, h->d_cell_count, h->cells_cap);
             cell_scan_kernel<<<nf, 1024, 0, h->stream>>>(h->view, da, h->d_cell_count, h->d_cell_start, h->cells_cap);
-            cell_fill_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, h->d_head_cell, h->d_cell_count, h->d_cell_start, h->d_cell_sorted, h->cells_cap);
+            cell_fill_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, da, h->d_head_cell, h->d_cell_count, h->d_cell_start, h->d_cell_sorted, h->cells_cap);
             dim3 grid((h->n_molpad + 127) / 128, nf);
             dynamic_normal_cell_kernel<<<grid, 128, 0, h->stream>>>(h->view, d_planes, da, h->d_molpad_type, h->d_cell_start, h->d_cell_sorted,
                                                                    h->cells_cap, h->d_normals, h->d_normal_npoints);

@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(DeviceView v, const Fra
     if (threadIdx.x == 0) st[nc] = s_carry;
 }
 
-__global__ void __launch_bounds__(256) cell_fill_kernel(DeviceView v, const float *__restrict__ planes, const int *__restrict__ head_cell,
+__global__ void __launch_bounds__(256) cell_fill_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux, const int *__restrict__ head_cell,
                                                         int *__restrict__ cell_count, const int *__restrict__ cell_start,
                                                         float4 *__restrict__ sorted_pos, int cells_cap) {
     const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -637,7 +637,12 @@ __global__ void __launch_bounds__(256) cell_fill_kernel(DeviceView v, const floa
     // the coordinates travel with the index: the gather loop reads ONE contiguous float4 per candidate
     const float *fr = planes + (size_t)f * v.frame_floats;
     const int off = v.normal_heads.off[i], cs = v.normal_heads.cs[i];
-    sorted_pos[(size_t)f * v.normal_heads.n + pos] = make_float4(fr[off], fr[off + cs], fr[off + 2 * (size_t)cs], __int_as_float(i));
+    const float x = fr[off], y = fr[off + cs], z = fr[off + 2 * (size_t)cs];
+    // w: the head's index; complemented (negative) when the head lies outside [0, L): the gather loop then skips its
+    // cell-based image shortcut for this candidate
+    const FrameAux &a = aux[f];
+    const bool inside = x >= 0.0f && x < a.L[0] && y >= 0.0f && y < a.L[1] && z >= 0.0f && z < a.L[2];
+    sorted_pos[(size_t)f * v.normal_heads.n + pos] = make_float4(x, y, z, __int_as_float(inside ? i : ~i));
 }
 
 __global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
@@ -664,21 +669,39 @@ __global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, 
     const float4 *srt = sorted_pos + (size_t)f * v.normal_heads.n;
     const float g0 = 0.99f * a.half[0], g1 = 0.99f * a.half[1], g2 = 0.99f * a.half[2];
     const float r2max = v.dynamic_radius;
+    // Cheap rejection: inside a cell of the 3 x 3 x 3 block the periodic image next to the reference is known from the cell
+    // offset alone (cell edge >= radius, >= 3 cells per axis, both atoms inside the box), so most candidates cost
+    // 3 subtractions + |r|^2; everything within radius + slack is decided by the exact fold and the exact `<`.
+    const bool ref_in = ref.x >= 0.0f && ref.x < a.L[0] && ref.y >= 0.0f && ref.y < a.L[1] && ref.z >= 0.0f && ref.z < a.L[2];
+    const bool quick = ref_in && n[0] >= 3 && n[1] >= 3 && n[2] >= 3;
+    // slack: the shifted reference is rounded at the magnitude of the box (ulp(L) ~ 1.2e-7 L)
+    const float r_hi = r2max + 1e-5f * r2max + 6e-7f * fmaxf(a.L[0], fmaxf(a.L[1], a.L[2]));
+    const float r2hi = r_hi * r_hi;
     int cnt = 0;
     double sx = 0, sy = 0, sz = 0, xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
     // with fewer than 3 cells along an axis the +-1 neighbours alias: visit every cell of that axis once
     const int lo0 = n[0] >= 3 ? -1 : 0, hi0 = n[0] >= 3 ? 1 : n[0] - 1;
     const int lo1 = n[1] >= 3 ? -1 : 0, hi1 = n[1] >= 3 ? 1 : n[1] - 1;
     const int lo2 = n[2] >= 3 ? -1 : 0, hi2 = n[2] >= 3 ? 1 : n[2] - 1;
+    // (four-way unrolled candidate loads with merged z columns were measured 2x SLOWER: 85 registers and more
+    //  divergent code; the simple loop below, one candidate at a time, is what the scheduler hides best)
     for (int dx = lo0; dx <= hi0; dx++) {
         const int cx = n[0] >= 3 ? (c0[0] + dx + n[0]) % n[0] : dx;
+        // reference shifted into the candidate cell's image: r = q - refs is the nearest-image vector
+        const float rsx = ref.x + (c0[0] + dx < 0 ? a.L[0] : (c0[0] + dx >= n[0] ? -a.L[0] : 0.0f));
         for (int dy = lo1; dy <= hi1; dy++) {
             const int cy = n[1] >= 3 ? (c0[1] + dy + n[1]) % n[1] : dy;
+            const float rsy = ref.y + (c0[1] + dy < 0 ? a.L[1] : (c0[1] + dy >= n[1] ? -a.L[1] : 0.0f));
             for (int dz = lo2; dz <= hi2; dz++) {
                 const int cz = n[2] >= 3 ? (c0[2] + dz + n[2]) % n[2] : dz;
+                const float rsz = ref.z + (c0[2] + dz < 0 ? a.L[2] : (c0[2] + dz >= n[2] ? -a.L[2] : 0.0f));
                 const int c = (cx * n[1] + cy) * n[2] + cz;
                 for (int k = st[c]; k < st[c + 1]; k++) {
                     const float4 q = __ldg(srt + k);
+                    if (quick && __float_as_int(q.w) >= 0) {
+                        const float ex = q.x - rsx, ey = q.y - rsy, ez = q.z - rsz;
+                        if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > r2hi) continue;
+                    }
                     f3 d;   // Vector3D::vector_to(reference, head): same fold as everywhere (single-compare fast path)
                     d.x = min_image_g(__fsub_rn(q.x, ref.x), a.L[0], a.half[0], g0);
                     d.y = min_image_g(__fsub_rn(q.y, ref.y), a.L[1], a.half[1], g1);
