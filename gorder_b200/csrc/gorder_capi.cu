@@ -864,6 +864,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     v.manual_leaflets = d_mleaf; v.manual_normals = d_mnorm;
     v.err = h->d_err; v.err_detail = h->d_err_detail;
     v.debug_nocompute = getenv("GORDER_DEBUG_NOCOMPUTE") ? 1 : 0;
+    v.ua_exact = getenv("GORDER_UA_EXACT") ? 1 : 0;
     v.l2_hints = getenv("GORDER_L2_HINTS") ? atoi(getenv("GORDER_L2_HINTS")) : 0;
     // rotation constants with the host libm (the reference's sin/cos of the same f32 angles)
     v.tet_s = sinf(1.910633f); v.tet_c = cosf(1.910633f);

@@ -115,6 +115,7 @@ struct DeviceView {
     float tet_s, tet_c, tet_half_s, tet_half_c, ch3_s, ch3_c;
     int l2_hints;             // L2 eviction-priority hints on the plane loads
     int debug_nocompute;      // profiling experiment only: load the planes, skip the arithmetic
+    int ua_exact;             // UA: bit-exact hydrogen construction everywhere (default: only with geometry / maps)
     // error word
     int *err;                 // [0] code, [1] unused
     long long *err_detail;

@@ -1598,6 +1598,67 @@ __device__ __forceinline__ int predict_hydrogens(const DeviceView &v, int kind, 
     }
 }
 
+// Streaming variant of the hydrogen construction (no geometry / maps): the same constructions with every
+// normalisation done as x * rsqrt(|x|^2) (MUFU + one Newton step, <= 1 ulp) instead of IEEE sqrt + three IEEE
+// divisions, rotations of vectors perpendicular to their axis as  v cos + (u x v) sin,  FMA contraction allowed.
+// The directions agree with the exact path to ~2e-7; the hydrogen is still placed as fl(t + fl(0.109 u)) and the bond
+// vector folded with the reference's expression, so that the dominant rounding (positions at box magnitude) is the
+// reference's own.  Per sample |dS| <~ 1e-6 (zero mean); bit-exact hydrogens stay available (GORDER_UA_EXACT=1, and
+// always with geometry selections / order maps, where a sample's position decides a count).
+__device__ __forceinline__ float rsq_newton(float x) {
+    const float r = rsqrt_ftz(x);
+    return r * fmaf(-0.5f * x, r * r, 1.5f);
+}
+__device__ __forceinline__ f3 cross_f(const f3 &a, const f3 &b) {
+    return mk3(fmaf(a.y, b.z, -a.z * b.y), fmaf(a.z, b.x, -a.x * b.z), fmaf(a.x, b.y, -a.y * b.x));
+}
+__device__ __forceinline__ float dot_f(const f3 &a, const f3 &b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ f3 scale_f(const f3 &a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 unit_f(const f3 &a) { return scale_f(a, rsq_newton(dot_f(a, a))); }
+__device__ __forceinline__ f3 lin2(const f3 &a, float ca, const f3 &b, float cb) {
+    return mk3(fmaf(a.x, ca, b.x * cb), fmaf(a.y, ca, b.y * cb), fmaf(a.z, ca, b.z * cb));
+}
+
+template <bool PBC>
+__device__ __forceinline__ int predict_directions_fast(const DeviceView &v, int kind, const f3 &t, const f3 &h1, const f3 &h2, const f3 &h3,
+                                                       const Box &bx, f3 (&u)[3]) {
+    if (kind == GORDER_UA_CH2) {   // uaorder.rs:985-1020
+        const f3 a = unit_f(vector_to<PBC>(t, h1, bx)), b = unit_f(vector_to<PBC>(t, h2, bx));
+        const f3 pn = cross_f(b, a);
+        const f3 ra = unit_f(mk3(a.x - b.x, a.y - b.y, a.z - b.z));
+        const f3 rv = cross_f(pn, ra), w = cross_f(ra, rv);   // rv is perpendicular to ra: R v = v cos + (ra x v) sin
+        const float inv = rsq_newton(dot_f(rv, rv));
+        u[0] = lin2(rv, v.tet_half_c * inv, w, v.tet_half_s * inv);
+        u[1] = lin2(rv, v.tet_half_c * inv, w, -v.tet_half_s * inv);
+        return 2;
+    } else if (kind == GORDER_UA_CH3) {   // uaorder.rs:947-981
+        const f3 th1 = vector_to<PBC>(t, h1, bx), th2 = vector_to<PBC>(t, h2, bx);
+        const f3 ax = unit_f(cross_f(th2, th1));
+        const f3 hv1 = lin2(th1, v.tet_c, cross_f(ax, th1), v.tet_s);
+        u[0] = unit_f(hv1);
+        const f3 n = unit_f(th1), nxu = cross_f(n, u[0]);
+        const float nd = dot_f(n, u[0]) * (1.0f - v.ch3_c);
+        const f3 base = mk3(fmaf(u[0].x, v.ch3_c, n.x * nd), fmaf(u[0].y, v.ch3_c, n.y * nd), fmaf(u[0].z, v.ch3_c, n.z * nd));
+        u[1] = mk3(fmaf(nxu.x, v.ch3_s, base.x), fmaf(nxu.y, v.ch3_s, base.y), fmaf(nxu.z, v.ch3_s, base.z));
+        u[2] = mk3(fmaf(nxu.x, -v.ch3_s, base.x), fmaf(nxu.y, -v.ch3_s, base.y), fmaf(nxu.z, -v.ch3_s, base.z));
+        return 3;
+    } else if (kind == GORDER_UA_CH1_UNSAT) {   // uaorder.rs:1024-1045
+        const f3 th1 = vector_to<PBC>(t, h1, bx), th2 = vector_to<PBC>(t, h2, bx);
+        const float nn = dot_f(th1, th1) * dot_f(th2, th2);
+        float cg = dot_f(th1, th2) * rsq_newton(nn);
+        cg = fminf(1.0f, fmaxf(-1.0f, cg));
+        if (nn == 0.0f) cg = 1.0f;
+        const float ch = sqrtf(fmaxf(0.0f, 0.5f * (1.0f + cg))), sh = sqrtf(fmaxf(0.0f, 0.5f * (1.0f - cg)));
+        const f3 ax = unit_f(cross_f(th1, th2));
+        u[0] = unit_f(lin2(th2, -ch, cross_f(ax, th2), sh));   // rotation by pi - gamma/2 about ax (perpendicular to th2)
+        return 1;
+    } else {   // uaorder.rs:1087-1104
+        const f3 a = unit_f(vector_to<PBC>(t, h1, bx)), b = unit_f(vector_to<PBC>(t, h2, bx)), c = unit_f(vector_to<PBC>(t, h3, bx));
+        u[0] = unit_f(mk3(-(a.x + b.x + c.x), -(a.y + b.y + c.y), -(a.z + b.z + c.z)));
+        return 1;
+    }
+}
+
 template <bool PBC, bool NVEC, bool LEAF, bool EXTRA>
 __global__ void __launch_bounds__(kBlock) ua_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                           const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
@@ -1652,7 +1713,13 @@ __global__ void __launch_bounds__(kBlock) ua_order_kernel(DeviceView v, const fl
             f3 h3 = mk3(0, 0, 0);
             if (it.kind == GORDER_UA_CH1_SAT) h3 = mk3(__ldg(base + it.h3_off), __ldg(base + it.h3_off + mpad), __ldg(base + it.h3_off + 2 * mpad));
             f3 hyd[3];
-            predict_hydrogens<PBC>(v, it.kind, t, h1, h2, h3, bx, hyd);
+            if (!EXTRA && !v.ua_exact) {
+                f3 u[3];
+                predict_directions_fast<PBC>(v, it.kind, t, h1, h2, h3, bx, u);
+#pragma unroll
+                for (int k = 0; k < 3; k++)   // Vector3D::shift: p + u * 0.109 (the wrap into the box is undone by the fold below)
+                    hyd[k] = mk3(__fadd_rn(t.x, __fmul_rn(u[k].x, 0.109f)), __fadd_rn(t.y, __fmul_rn(u[k].y, 0.109f)), __fadd_rn(t.z, __fmul_rn(u[k].z, 0.109f)));
+            } else predict_hydrogens<PBC>(v, it.kind, t, h1, h2, h3, bx, hyd);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 if (k >= nh) break;

@@ -306,3 +306,49 @@ def test_local_leaflets_cell_list(n_lipids, axis, monkeypatch):
     up = r.leaflets.astype(int).sum(axis=1)
     assert np.all(np.abs(up - (n_lipids + 1) // 2) <= 2), up
     assert_raw_parity(g, r, s.setup, what=f"local leaflets, cell list, {n_lipids} lipids, axis {axis}")
+
+
+def test_ua_streaming_hydrogens_vs_exact(monkeypatch):
+    """UA without geometry / maps builds the hydrogens with rsqrt-normalised directions: against the
+    bit-exact construction (GORDER_UA_EXACT=1) the per-frame, per-leaflet means move by << 1e-5, counts not at all."""
+    from gorder_b200 import SystemTopology
+    s = synthetic.s_ua(200, with_ch1_sat=True, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True)
+    xyz, box, idx = _frames(s, 5)
+    res = []
+    for exact in (False, True):
+        if exact:
+            monkeypatch.setenv("GORDER_UA_EXACT", "1")
+        eng = SystemTopology(s.setup)
+        eng.analyze_frames(xyz, box, idx)
+        res.append(eng.finish())
+        eng.close()
+    fast, exact = res
+    np.testing.assert_array_equal(fast.count, exact.count)
+    np.testing.assert_array_equal(fast.tw_count, exact.tw_count)
+    assert not np.array_equal(fast.sum, exact.sum)   # the streaming path is really a different computation
+    dev = np.abs(fast.sum - exact.sum) / np.maximum(exact.count, 1) / 1e6
+    assert dev.max() < 1e-6, dev.max()
+    tw = np.abs(fast.tw_sum - exact.tw_sum) / np.maximum(exact.tw_count, 1) / 1e6
+    assert tw.max() < 3e-6, tw.max()
+
+
+@pytest.mark.parametrize("leaflets", [abi.LEAFLET_NONE, abi.LEAFLET_GLOBAL])
+@pytest.mark.parametrize("bad", [np.nan, np.inf])
+def test_fast_kernel_reports_undefined_positions(leaflets, bad, monkeypatch):
+    """bond_fast_kernel has no per-sample NaN test: an integer max over the bit patterns of |d|^2 must still turn a
+    NaN / Inf coordinate of a resident frame into AnalysisError::UndefinedPosition (with and without the
+    speculative leaflets, whose sums the same coordinate poisons)."""
+    from gorder_b200 import SystemTopology
+    monkeypatch.setenv("GORDER_MPT", "2")
+    s = synthetic.s_cg(1300, leaflet_mode=leaflets)
+    xyz, box, idx = s.frames(0, 3)
+    eng = SystemTopology(s.setup)
+    planes = eng.to_native(xyz)
+    _, off, cs = eng.native_layout()
+    victim = int(s.setup.moltypes[0].mol_base[700]) + 5   # a tail bead of a lipid in a full tile
+    planes[2, off[victim] + 2 * cs[victim]] = bad
+    eng.analyze_frames_native(planes, box, idx)
+    with pytest.raises(abi.GorderError) as e:
+        eng.finish()
+    assert e.value.code == abi.ERR_UNDEFINED_POSITION
+    eng.close()
