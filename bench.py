@@ -317,6 +317,35 @@ def run_ours(args):
     d2h = int(r2.sum.nbytes + r2.count.nbytes)
     eng2.close()
 
+    # ---- end to end from a trajectory FILE: host XTC decode (all host threads) -> pinned plane batches -> engine -----
+    e2e_xtc = None
+    if rank == 0 and args.xtc_frames > 0:
+        import tempfile
+        from gorder_b200.xtc import XtcFile, write_xtc
+        nx = min(args.xtc_frames, F)
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "bench.xtc")
+            write_xtc(path, xyz[:nx], box[:nx])
+            fbytes = os.path.getsize(path)
+            with XtcFile(path) as xf:
+                threads_x = os.cpu_count() or 1
+                eng4 = SystemTopology(s.setup)
+                eng4.run_xtc(xf, last=min(nx, 8), n_threads=threads_x, batch_frames=8)   # warm-up (page cache, pinned buffers)
+                eng4.finish()
+                eng4.close()
+                eng4 = SystemTopology(s.setup)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                dec_s = eng4.run_xtc(xf, n_threads=threads_x, batch_frames=args.xtc_batch)
+                rx = eng4.finish()
+                dt_x = time.perf_counter() - t0
+                eng4.close()
+        e2e_xtc = {"value": nx * spf / dt_x, "unit": UNIT, "frames": nx, "file_bytes": fbytes, "bytes_per_atom": fbytes / nx / s.n_atoms,
+                   "decode_threads": threads_x, "decode_thread_seconds": dec_s, "wall_seconds": dt_x,
+                   "decode_atoms_per_s_per_thread": nx * s.n_atoms / max(dec_s, 1e-9),
+                   "entry": "gorder_gpu_run_xtc (host XTC decode + H2D + analysis + D2H of the sums; rank 0)",
+                   "samples": int(rx.count[:, 0].sum())}
+
     out = None
     if rank == 0:
         peak, peak_src = peaks()
@@ -360,7 +389,7 @@ def run_ours(args):
                                        "frac": launch_bytes / (iso_ms / iso_n * 1e-3) / 1e9 / peak} if iso_n else None)},
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{cpu_frames} frames of the same workload ({cpu_t:.1f} s), oracle port with {threads} OpenMP threads"},
-            "parity": parity, "total_samples_accumulated": total_samples, "speculative_leaflets": spec_stats,
+            "e2e_xtc": e2e_xtc, "parity": parity, "total_samples_accumulated": total_samples, "speculative_leaflets": spec_stats,
         }
     eng.close()
     if world > 1:
@@ -381,6 +410,8 @@ def main():
     ap.add_argument("--lipids", type=int, default=0, help="0 = workload default")
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU arms; 0 = one per host thread")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--xtc-frames", type=int, default=64, help="frames of the XTC end-to-end leg (0 = skip)")
+    ap.add_argument("--xtc-batch", type=int, default=16, help="frames per decoded batch of the XTC leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.lipids = args.lipids or WORKLOADS[args.workload][1]

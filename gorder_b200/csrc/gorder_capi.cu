@@ -1381,3 +1381,5 @@ int gorder_gpu_last_error(GorderHandle *h, char *buf, size_t len) {
 int64_t gorder_gpu_error_detail(GorderHandle *h) { return h ? h->err_detail : -1; }
 
 }  // extern "C"
+
+#include "gorder_xtc.inl"

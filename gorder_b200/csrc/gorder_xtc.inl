@@ -1,0 +1,464 @@
+// gorder_xtc.inl — host-side trajectory feed of the engine: GROMACS XTC frames are decoded
+// by a pool of host threads straight into pinned batches in the engine's plane layout and handed to
+// gorder_gpu_submit_native; the decode of batch k+1 overlaps the H2D copy and the kernels of batch k.
+//
+// Stands in for the reference's reader when the harness (tests, bench.py) needs a real end-to-end number:
+//   read_trajectory -> groan_rs traj_iter_map_reduce::<GroupXtcReader> (src/analysis/common.rs:281-304) -> molly 0.5.0
+// (Cargo.lock:955, not vendored).  The Rust host keeps its own reader; this file only has to produce
+// the same coordinates: integer lattice * (1 / precision) in f32, as xdrfile's xdr3dfcoord and molly do.
+// Format: big-endian XDR header (magic 1995 | 2023, natoms, step, time, box[9], natoms, precision, minint[3],
+// maxint[3], smallidx, byte count) followed by the "xtc3" bit stream: per atom a mixed-radix triple of
+// sizeint[] in `bitsize` bits, a run flag (+ 5 bits), then run/3 triples relative to the previous atom in `smallidx`
+// bits with the first pair swapped (water trick); smallidx walks through magicints[] as the runs ask.
+// Included at the end of gorder_capi.cu (host code only, no kernels).
+#include <atomic>
+#include <chrono>
+#include <climits>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
+
+namespace gxtc {
+
+const int kMagic[] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512,
+                      645, 812, 1024, 1290, 1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007, 32768,
+                      41285, 52015, 65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127, 524287, 660561, 832255,
+                      1048576, 1321122, 1664510, 2097152, 2642245, 3329021, 4194304, 5284491, 6658042, 8388607, 10568983, 13316085,
+                      16777216};
+constexpr int kFirstIdx = 9, kLastIdx = (int)(sizeof(kMagic) / sizeof(kMagic[0])) - 1;
+
+inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+inline float bef32(const uint8_t *p) { uint32_t u = be32(p); float f; memcpy(&f, &u, 4); return f; }
+
+struct Frame {
+    size_t payload;      // offset of the compressed bytes (or of the raw floats when natoms <= 9)
+    size_t nbytes;
+    int natoms, step, smallidx;
+    float time, precision, box[9];
+    int minint[3], maxint[3];
+};
+
+// MSB-first bit reader over [p, end) with a 64-bit window; reads past `end` yield zeros
+struct BitIn {
+    const uint8_t *p, *end;
+    uint64_t acc = 0;
+    int n = 0;
+    inline void fill() {
+        while (n <= 56) { acc = (acc << 8) | (p < end ? *p : 0); p++; n += 8; }
+    }
+    inline uint32_t get(int bits) {   // bits <= 32
+        if (bits == 0) return 0;
+        if (n < bits) fill();
+        n -= bits;
+        return (uint32_t)((acc >> n) & ((bits == 32) ? 0xffffffffull : ((1ull << bits) - 1ull)));
+    }
+    // the mixed-radix number of a triple: its bytes arrive least significant first, the last one may be partial
+    template <typename W> inline W get_le(int bits) {
+        W v = 0;
+        int shift = 0;
+        while (bits > 8) { v |= (W)get(8) << shift; shift += 8; bits -= 8; }
+        if (bits > 0) v |= (W)get(bits) << shift;
+        return v;
+    }
+};
+
+inline int bits_of(unsigned size) { unsigned num = 1; int b = 0; while (size >= num && b < 32) { b++; num <<= 1; } return b; }
+inline int bits_of_triple(const unsigned s[3]) {   // xdrfile's sizeofints: the bit length of s0 * s1 * s2
+    unsigned __int128 t = (unsigned __int128)s[0] * s[1] * s[2];
+    int b = 0;
+    while (t) { b++; t >>= 1; }
+    return b;
+}
+
+template <typename W>
+inline void unpack3(W v, const unsigned s[3], int out[3]) {
+    out[2] = (int)(v % s[2]); v /= s[2];
+    out[1] = (int)(v % s[1]); v /= s[1];
+    out[0] = (int)v;
+}
+
+// Decode one frame; emit(atom, x, y, z) is called for atoms 0 .. stop_after (inclusive) in order.
+template <typename Emit>
+int decode_frame(const uint8_t *base, const Frame &fr, int stop_after, Emit emit) {
+    const int n = fr.natoms;
+    const int last = std::min(stop_after, n - 1);
+    if (n <= 9) {
+        for (int i = 0; i <= last; i++) emit(i, bef32(base + fr.payload + 12 * (size_t)i), bef32(base + fr.payload + 12 * (size_t)i + 4), bef32(base + fr.payload + 12 * (size_t)i + 8));
+        return 0;
+    }
+    unsigned sizeint[3], bitsint[3] = {0, 0, 0};
+    for (int k = 0; k < 3; k++) sizeint[k] = (unsigned)(fr.maxint[k] - fr.minint[k] + 1);
+    int bitsize = 0;
+    if ((sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffffu) { for (int k = 0; k < 3; k++) bitsint[k] = (unsigned)bits_of(sizeint[k]); }
+    else bitsize = bits_of_triple(sizeint);
+    int smallidx = fr.smallidx;
+    if (smallidx < kFirstIdx || smallidx > kLastIdx) return -1;
+    int smaller = kMagic[std::max(kFirstIdx, smallidx - 1)] / 2, smallnum = kMagic[smallidx] / 2;
+    unsigned ssz[3] = {(unsigned)kMagic[smallidx], (unsigned)kMagic[smallidx], (unsigned)kMagic[smallidx]};
+    const float inv = 1.0f / fr.precision;
+    BitIn in{base + fr.payload, base + fr.payload + fr.nbytes};
+    int i = 0, run = 0, cur[3], prev[3];
+    while (i <= last) {
+        if (bitsize == 0) { cur[0] = (int)in.get((int)bitsint[0]); cur[1] = (int)in.get((int)bitsint[1]); cur[2] = (int)in.get((int)bitsint[2]); }
+        else if (bitsize <= 64) unpack3<uint64_t>(in.get_le<uint64_t>(bitsize), sizeint, cur);
+        else unpack3<unsigned __int128>(in.get_le<unsigned __int128>(bitsize), sizeint, cur);
+        cur[0] += fr.minint[0]; cur[1] += fr.minint[1]; cur[2] += fr.minint[2];
+        prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
+        int is_smaller = 0;
+        if (in.get(1)) {
+            run = (int)in.get(5);
+            is_smaller = run % 3;
+            run -= is_smaller;
+            is_smaller--;
+        }
+        if (run > 0) {
+            for (int k = 0; k < run; k += 3) {
+                int d[3];
+                if (smallidx <= 64) unpack3<uint64_t>(in.get_le<uint64_t>(smallidx), ssz, d);
+                else unpack3<unsigned __int128>(in.get_le<unsigned __int128>(smallidx), ssz, d);
+                int t[3] = {d[0] + prev[0] - smallnum, d[1] + prev[1] - smallnum, d[2] + prev[2] - smallnum};
+                if (i + (k == 0 ? 2 : 1) > n) return -1;
+                if (k == 0) {   // the first two atoms of a run are stored in swapped order: this one comes first ...
+                    emit(i, (float)t[0] * inv, (float)t[1] * inv, (float)t[2] * inv); i++;
+                    emit(i, (float)prev[0] * inv, (float)prev[1] * inv, (float)prev[2] * inv); i++;   // ... then the "large" atom
+                } else {
+                    emit(i, (float)t[0] * inv, (float)t[1] * inv, (float)t[2] * inv); i++;
+                }
+                prev[0] = t[0]; prev[1] = t[1]; prev[2] = t[2];   // the run continues relative to the atom just decoded
+            }
+        } else {
+            if (i >= n) return -1;
+            emit(i, (float)cur[0] * inv, (float)cur[1] * inv, (float)cur[2] * inv); i++;
+        }
+        smallidx += is_smaller;
+        if (smallidx < kFirstIdx || smallidx > kLastIdx) return -1;
+        if (is_smaller < 0) { smallnum = smaller; smaller = smallidx > kFirstIdx ? kMagic[smallidx - 1] / 2 : 0; }
+        else if (is_smaller > 0) { smaller = smallnum; smallnum = kMagic[smallidx] / 2; }
+        ssz[0] = ssz[1] = ssz[2] = (unsigned)kMagic[smallidx];
+    }
+    return 0;
+}
+
+// ---- writer (synthetic trajectories for the bench and the tests) -------------------------------------------
+struct BitOut {
+    std::vector<uint8_t> buf;
+    uint64_t acc = 0;
+    int n = 0;
+    inline void put(uint32_t v, int bits) {
+        if (bits == 0) return;
+        acc = (acc << bits) | (v & ((bits == 32) ? 0xffffffffull : ((1ull << bits) - 1ull)));
+        n += bits;
+        while (n >= 8) { n -= 8; buf.push_back((uint8_t)(acc >> n)); }
+    }
+    template <typename W> inline void put_le(W v, int bits) {
+        while (bits > 8) { put((uint32_t)(v & 0xff), 8); v >>= 8; bits -= 8; }
+        if (bits > 0) put((uint32_t)v, bits);
+    }
+    inline void flush() { if (n > 0) { buf.push_back((uint8_t)(acc << (8 - n))); n = 0; } }
+};
+inline void wr32(std::vector<uint8_t> &o, uint32_t v) { o.push_back(v >> 24); o.push_back(v >> 16); o.push_back(v >> 8); o.push_back(v); }
+inline void wrf(std::vector<uint8_t> &o, float f) { uint32_t u; memcpy(&u, &f, 4); wr32(o, u); }
+
+template <typename W> inline W pack3(const unsigned s[3], const int v[3]) { return ((W)(unsigned)v[0] * s[1] + (unsigned)v[1]) * s[2] + (unsigned)v[2]; }
+inline void put_triple(BitOut &out, int bits, const unsigned s[3], const int v[3]) {
+    if (bits <= 64) out.put_le<uint64_t>(pack3<uint64_t>(s, v), bits);
+    else out.put_le<unsigned __int128>(pack3<unsigned __int128>(s, v), bits);
+}
+
+// xdrfile's compression strategy (runs of atoms within magicints[smallidx] / 2 of their predecessor)
+inline void encode_frame(std::vector<uint8_t> &o, const float *xyz, const float *box3, int natoms, int step, float time, float precision) {
+    wr32(o, 1995); wr32(o, (uint32_t)natoms); wr32(o, (uint32_t)step); wrf(o, time);
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) wrf(o, r == c ? box3[r] : 0.0f);
+    wr32(o, (uint32_t)natoms);
+    if (natoms <= 9) { for (int i = 0; i < 3 * natoms; i++) wrf(o, xyz[i]); return; }
+    wrf(o, precision);
+    std::vector<int> L(3 * (size_t)natoms);
+    int mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+    long long mindiff = INT32_MAX;
+    for (int i = 0; i < natoms; i++) {
+        for (int k = 0; k < 3; k++) {
+            const float lf = xyz[3 * (size_t)i + k] * precision;
+            const int li = (int)(lf >= 0.0f ? lf + 0.5f : lf - 0.5f);
+            L[3 * (size_t)i + k] = li;
+            mn[k] = std::min(mn[k], li); mx[k] = std::max(mx[k], li);
+        }
+        if (i > 0) {
+            long long d = 0;
+            for (int k = 0; k < 3; k++) d += std::llabs((long long)L[3 * (size_t)i + k] - L[3 * (size_t)(i - 1) + k]);
+            mindiff = std::min(mindiff, d);
+        }
+    }
+    for (int k = 0; k < 3; k++) wr32(o, (uint32_t)mn[k]);
+    for (int k = 0; k < 3; k++) wr32(o, (uint32_t)mx[k]);
+    unsigned sizeint[3], bitsint[3] = {0, 0, 0};
+    for (int k = 0; k < 3; k++) sizeint[k] = (unsigned)(mx[k] - mn[k] + 1);
+    int bitsize = 0;
+    if ((sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffffu) { for (int k = 0; k < 3; k++) bitsint[k] = (unsigned)bits_of(sizeint[k]); }
+    else bitsize = bits_of_triple(sizeint);
+    int smallidx = kFirstIdx;
+    while (smallidx < kLastIdx && kMagic[smallidx] < mindiff) smallidx++;
+    wr32(o, (uint32_t)smallidx);
+    const int maxidx = std::min(kLastIdx, smallidx + 8), minidx = maxidx - 8;
+    int smaller = kMagic[std::max(kFirstIdx, smallidx - 1)] / 2, smallnum = kMagic[smallidx] / 2;
+    const int larger = kMagic[maxidx] / 2;
+    unsigned ssz[3] = {(unsigned)kMagic[smallidx], (unsigned)kMagic[smallidx], (unsigned)kMagic[smallidx]};
+    BitOut out;
+    out.buf.reserve((size_t)natoms * 5);
+    int prevrun = -1, i = 0, prev[3] = {0, 0, 0};
+    auto near = [&](const int *a, const int *b, int lim) { return std::abs(a[0] - b[0]) < lim && std::abs(a[1] - b[1]) < lim && std::abs(a[2] - b[2]) < lim; };
+    while (i < natoms) {
+        int *cur = &L[3 * (size_t)i];
+        int is_small = 0, is_smaller;
+        if (smallidx < maxidx && i >= 1 && near(cur, prev, larger)) is_smaller = 1;
+        else if (smallidx > minidx) is_smaller = -1;
+        else is_smaller = 0;
+        if (i + 1 < natoms && near(cur, cur + 3, smallnum)) {
+            for (int k = 0; k < 3; k++) std::swap(cur[k], cur[3 + k]);   // store the pair in swapped order (undone by the reader)
+            is_small = 1;
+        }
+        int tmp[3] = {cur[0] - mn[0], cur[1] - mn[1], cur[2] - mn[2]};
+        if (bitsize == 0) { out.put((uint32_t)tmp[0], (int)bitsint[0]); out.put((uint32_t)tmp[1], (int)bitsint[1]); out.put((uint32_t)tmp[2], (int)bitsint[2]); }
+        else put_triple(out, bitsize, sizeint, tmp);
+        prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
+        i++;
+        int run = 0, small[24];
+        if (is_small == 0 && is_smaller == -1) is_smaller = 0;
+        while (is_small && run < 8 * 3) {
+            const int *nx = &L[3 * (size_t)i];
+            if (is_smaller == -1) {
+                const long long dx = nx[0] - prev[0], dy = nx[1] - prev[1], dz = nx[2] - prev[2];
+                if (dx * dx + dy * dy + dz * dz >= (long long)smaller * smaller) is_smaller = 0;
+            }
+            small[run++] = nx[0] - prev[0] + smallnum; small[run++] = nx[1] - prev[1] + smallnum; small[run++] = nx[2] - prev[2] + smallnum;
+            prev[0] = nx[0]; prev[1] = nx[1]; prev[2] = nx[2];
+            i++;
+            is_small = (i < natoms && near(&L[3 * (size_t)i], prev, smallnum)) ? 1 : 0;
+        }
+        if (run != prevrun || is_smaller != 0) { prevrun = run; out.put(1, 1); out.put((uint32_t)(run + is_smaller + 1), 5); }
+        else out.put(0, 1);
+        for (int k = 0; k < run; k += 3) put_triple(out, smallidx, ssz, small + k);
+        if (is_smaller != 0) {
+            smallidx += is_smaller;
+            if (is_smaller < 0) { smallnum = smaller; smaller = kMagic[smallidx - 1] / 2; }
+            else { smaller = smallnum; smallnum = kMagic[smallidx] / 2; }
+            ssz[0] = ssz[1] = ssz[2] = (unsigned)kMagic[smallidx];
+        }
+    }
+    out.flush();
+    wr32(o, (uint32_t)out.buf.size());
+    o.insert(o.end(), out.buf.begin(), out.buf.end());
+    while (o.size() & 3) o.push_back(0);
+}
+
+}  // namespace gxtc
+
+struct GorderXtc {
+    int fd = -1;
+    const uint8_t *data = nullptr;
+    size_t size = 0;
+    std::vector<gxtc::Frame> frames;
+    int natoms = 0;
+};
+
+extern "C" {
+
+void gorder_xtc_close(GorderXtc *x) {
+    if (!x) return;
+    if (x->data) munmap((void *)x->data, x->size);
+    if (x->fd >= 0) close(x->fd);
+    delete x;
+}
+
+int gorder_xtc_open(const char *path, GorderXtc **out) {
+    if (!path || !out) return GORDER_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    GorderXtc *x = new GorderXtc();
+    x->fd = open(path, O_RDONLY);
+    struct stat st;
+    if (x->fd < 0 || fstat(x->fd, &st) != 0 || st.st_size < 60) { gorder_xtc_close(x); return GORDER_ERR_INVALID_ARGUMENT; }
+    x->size = (size_t)st.st_size;
+    void *m = mmap(nullptr, x->size, PROT_READ, MAP_PRIVATE, x->fd, 0);
+    if (m == MAP_FAILED) { x->data = nullptr; gorder_xtc_close(x); return GORDER_ERR_INVALID_ARGUMENT; }
+    x->data = (const uint8_t *)m;
+    size_t p = 0;
+    while (p + 60 <= x->size) {   // index the frames: headers only
+        const uint8_t *d = x->data + p;
+        const uint32_t magic = gxtc::be32(d);
+        if (magic != 1995 && magic != 2023) { gorder_xtc_close(x); return GORDER_ERR_INVALID_ARGUMENT; }
+        gxtc::Frame f{};
+        f.natoms = (int)gxtc::be32(d + 4); f.step = (int)gxtc::be32(d + 8); f.time = gxtc::bef32(d + 12);
+        for (int i = 0; i < 9; i++) f.box[i] = gxtc::bef32(d + 16 + 4 * i);
+        if ((int)gxtc::be32(d + 52) != f.natoms || f.natoms <= 0) { gorder_xtc_close(x); return GORDER_ERR_INVALID_ARGUMENT; }
+        size_t q = p + 56;
+        if (f.natoms <= 9) { f.payload = q; f.nbytes = 12 * (size_t)f.natoms; f.precision = 0.0f; q += f.nbytes; }
+        else {
+            if (q + 36 > x->size) break;
+            f.precision = gxtc::bef32(x->data + q);
+            for (int k = 0; k < 3; k++) { f.minint[k] = (int)gxtc::be32(x->data + q + 4 + 4 * k); f.maxint[k] = (int)gxtc::be32(x->data + q + 16 + 4 * k); }
+            f.smallidx = (int)gxtc::be32(x->data + q + 28);
+            q += 32;
+            if (magic == 2023) { f.nbytes = ((size_t)gxtc::be32(x->data + q) << 32) | gxtc::be32(x->data + q + 4); q += 8; }
+            else { f.nbytes = gxtc::be32(x->data + q); q += 4; }
+            f.payload = q;
+            q += (f.nbytes + 3) & ~(size_t)3;
+        }
+        if (q > x->size) break;   // truncated last frame: ignored, as trajectory readers do
+        if (x->frames.empty()) x->natoms = f.natoms;
+        else if (f.natoms != x->natoms) { gorder_xtc_close(x); return GORDER_ERR_INVALID_ARGUMENT; }
+        x->frames.push_back(f);
+        p = q;
+    }
+    if (x->frames.empty()) { gorder_xtc_close(x); return GORDER_ERR_INVALID_ARGUMENT; }
+    *out = x;
+    return GORDER_OK;
+}
+
+int gorder_xtc_info(GorderXtc *x, int32_t *n_atoms, int64_t *n_frames, float *precision) {
+    if (!x) return GORDER_ERR_INVALID_ARGUMENT;
+    if (n_atoms) *n_atoms = x->natoms;
+    if (n_frames) *n_frames = (int64_t)x->frames.size();
+    if (precision) *precision = x->frames[0].precision;
+    return GORDER_OK;
+}
+
+// Decode frames first, first + stride, ... (count of them) into host arrays: xyz [count][n_atoms][3], box9 [count][9],
+// time [count], step [count] (any of the last three may be NULL).
+int gorder_xtc_read(GorderXtc *x, int64_t first, int64_t count, int64_t stride, int32_t n_threads, float *xyz, float *box9, float *time, int32_t *step) {
+    if (!x || !xyz || first < 0 || count < 0 || stride < 1 || (count > 0 && first + (count - 1) * stride >= (int64_t)x->frames.size())) return GORDER_ERR_INVALID_ARGUMENT;
+    std::atomic<int64_t> next{0};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+        for (;;) {
+            const int64_t j = next.fetch_add(1);
+            if (j >= count) break;
+            const gxtc::Frame &f = x->frames[(size_t)(first + j * stride)];
+            float *dst = xyz + (size_t)j * x->natoms * 3;
+            if (gxtc::decode_frame(x->data, f, x->natoms - 1, [&](int i, float a, float b, float c) { dst[3 * (size_t)i] = a; dst[3 * (size_t)i + 1] = b; dst[3 * (size_t)i + 2] = c; })) bad = 1;
+            if (box9) memcpy(box9 + 9 * j, f.box, sizeof(f.box));
+            if (time) time[j] = f.time;
+            if (step) step[j] = f.step;
+        }
+    };
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, count));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    return bad ? GORDER_ERR_INVALID_ARGUMENT : GORDER_OK;
+}
+
+// Write (append = 0: create) frames with orthogonal boxes: xyz [n_frames][n_atoms][3], box3 [n_frames][3]; frame f gets
+// step = first_step + f and time = step * dt.
+int gorder_xtc_write(const char *path, const float *xyz, const float *box3, int32_t n_atoms, int64_t n_frames, float precision, int32_t append,
+                     int32_t first_step, float dt, int32_t n_threads) {
+    if (!path || !xyz || !box3 || n_atoms <= 0 || n_frames < 0 || !(precision > 0.0f)) return GORDER_ERR_INVALID_ARGUMENT;
+    std::vector<std::vector<uint8_t>> enc((size_t)n_frames);
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const int64_t f = next.fetch_add(1);
+            if (f >= n_frames) break;
+            gxtc::encode_frame(enc[(size_t)f], xyz + (size_t)f * n_atoms * 3, box3 + 3 * f, n_atoms, first_step + (int)f, (first_step + (int)f) * dt, precision);
+        }
+    };
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n_frames));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    FILE *fp = fopen(path, append ? "ab" : "wb");
+    if (!fp) return GORDER_ERR_INVALID_ARGUMENT;
+    for (auto &e : enc) if (fwrite(e.data(), 1, e.size(), fp) != e.size()) { fclose(fp); return GORDER_ERR_INVALID_ARGUMENT; }
+    fclose(fp);
+    return GORDER_OK;
+}
+
+// analyze_frame for the frames first, first + stride, ... < last of an open trajectory: n_threads host threads decode
+// straight into pinned batches in the plane layout (only the atoms the engine needs; the bit stream of a frame is read
+// up to the last of them), gorder_gpu_submit_native runs them.  atom_of_slot[s] = trajectory atom of engine atom s
+// (NULL: identity).  frame_index of the j-th analysed frame is j * stride (topology/mod.rs:141-144).
+// decode_seconds (optional): host time spent decoding, summed over threads.
+int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride, int32_t n_threads,
+                       int32_t batch_frames, double *decode_seconds) {
+    if (!h || !x || first < 0 || stride < 1) return GORDER_ERR_INVALID_ARGUMENT;
+    if (h->err_code) return h->err_code;
+    last = std::min<int64_t>(last, (int64_t)x->frames.size());
+    const int64_t total = last > first ? (last - first + stride - 1) / stride : 0;
+    if (total == 0) return GORDER_OK;
+    cudaSetDevice(h->device);
+    const int na = h->s.n_atoms;
+    // trajectory atom -> (plane offset, component stride); several engine atoms may not share a trajectory atom
+    std::vector<int> off_of_atom((size_t)x->natoms, -1), cs_of_atom((size_t)x->natoms, 0);
+    int stop_after = -1;
+    for (int s = 0; s < na; s++) {
+        const int a = atom_of_slot ? atom_of_slot[s] : s;
+        if (a < 0 || a >= x->natoms) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "atom_of_slot outside the trajectory", a); return h->err_code; }
+        if (h->slot_off[s] < 0) continue;   // not needed by the analysis
+        off_of_atom[a] = h->slot_off[s]; cs_of_atom[a] = h->slot_cs[s];
+        stop_after = std::max(stop_after, a);
+    }
+    const int B = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(batch_frames > 0 ? batch_frames : 32, h->max_batch), total));
+    const size_t ff = (size_t)h->frame_floats;
+    float *pin[2] = {nullptr, nullptr}, *pbox[2] = {nullptr, nullptr};
+    auto release = [&]() { for (int i = 0; i < 2; i++) { if (pin[i]) cudaFreeHost(pin[i]); if (pbox[i]) cudaFreeHost(pbox[i]); } };
+    for (int i = 0; i < 2; i++) {
+        if (cudaMallocHost((void **)&pin[i], (size_t)B * ff * sizeof(float)) != cudaSuccess || cudaMallocHost((void **)&pbox[i], (size_t)B * 3 * sizeof(float)) != cudaSuccess) {
+            release(); h->set_error(GORDER_ERR_OUT_OF_MEMORY, "pinned batch buffers"); return h->err_code;
+        }
+        memset(pin[i], 0, (size_t)B * ff * sizeof(float));   // padding stays finite
+    }
+    std::atomic<int> bad{0};
+    std::atomic<long long> dec_ns{0};
+    auto decode_batch = [&](int64_t j0, int nf, int buf) {
+        std::atomic<int> next{0};
+        auto work = [&]() {
+            const auto t0 = std::chrono::steady_clock::now();
+            for (;;) {
+                const int j = next.fetch_add(1);
+                if (j >= nf) break;
+                const gxtc::Frame &f = x->frames[(size_t)(first + (j0 + j) * stride)];
+                // check_box (common.rs:186-198): orthogonal boxes only
+                if (f.box[1] != 0.0f || f.box[2] != 0.0f || f.box[3] != 0.0f || f.box[5] != 0.0f || f.box[6] != 0.0f || f.box[7] != 0.0f) bad = GORDER_ERR_NOT_ORTHOGONAL_BOX;
+                pbox[buf][3 * j] = f.box[0]; pbox[buf][3 * j + 1] = f.box[4]; pbox[buf][3 * j + 2] = f.box[8];
+                float *dst = pin[buf] + (size_t)j * ff;
+                const int *oo = off_of_atom.data(), *cc = cs_of_atom.data();
+                if (gxtc::decode_frame(x->data, f, stop_after, [&](int i, float a, float b, float c) {
+                        const int o = oo[i];
+                        if (o >= 0) { const size_t cs = (size_t)cc[i]; dst[o] = a; dst[o + cs] = b; dst[o + 2 * cs] = c; }
+                    })) bad = GORDER_ERR_INVALID_ARGUMENT;
+            }
+            dec_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        };
+        const int nt = std::max(1, std::min<int>(n_threads, nf));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; t++) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    };
+    int rc = GORDER_OK;
+    std::vector<int64_t> fi((size_t)B);
+    int64_t j0 = 0;
+    int nf = (int)std::min<int64_t>(B, total);
+    decode_batch(0, nf, 0);
+    for (int buf = 0; j0 < total && !rc; buf ^= 1) {
+        if (bad) { h->set_error(bad, bad == GORDER_ERR_NOT_ORTHOGONAL_BOX ? "simulation box is not orthogonal" : "corrupt XTC frame"); rc = h->err_code; break; }
+        for (int j = 0; j < nf; j++) fi[(size_t)j] = (j0 + j) * stride;
+        // the next batch is decoded by a helper thread (which runs the pool) while this one is copied and analysed
+        const int64_t j1 = j0 + nf;
+        const int nf1 = (int)std::min<int64_t>(B, total - j1);
+        std::thread ahead;
+        if (nf1 > 0) ahead = std::thread([&, j1, nf1, buf]() { decode_batch(j1, nf1, buf ^ 1); });
+        rc = gorder_gpu_submit_native(h, pin[buf], pbox[buf], fi.data(), nf);
+        if (ahead.joinable()) ahead.join();
+        j0 = j1; nf = nf1;
+    }
+    if (!rc) { cudaStreamSynchronize(h->copy_stream); }
+    // the pinned buffers must outlive the asynchronous copies: submit_native waits for its H2D event before it returns
+    release();
+    if (decode_seconds) *decode_seconds = (double)dec_ns.load() * 1e-9;
+    return rc;
+}
+
+}  // extern "C"

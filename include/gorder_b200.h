@@ -319,6 +319,30 @@ int gorder_gpu_fence(GorderHandle *h);
  * (call gorder_gpu_fence before recording the closing event). */
 void *gorder_gpu_stream(GorderHandle *h);
 
+/* ---- host-side trajectory feed ---------------------------------------------------------
+ * Stands in for the reference's reader -- read_trajectory -> groan_rs traj_iter_map_reduce::<GroupXtcReader>
+ * (src/analysis/common.rs:281-304) -> molly 0.5.0 -- when the harness needs a real end-to-end run from an .xtc file.
+ * The Rust host keeps its own reader; these entry points need no GPU except gorder_gpu_run_xtc. */
+typedef struct GorderXtc GorderXtc;
+/* mmap the file and index its frames (headers only). */
+int gorder_xtc_open(const char *path, GorderXtc **out);
+int gorder_xtc_info(GorderXtc *x, int32_t *n_atoms, int64_t *n_frames, float *precision);
+/* Decode frames first, first + stride, ... (count of them) with n_threads host threads into
+ * xyz [count][n_atoms][3]; box9 [count][9], time [count], step [count] may be NULL. */
+int gorder_xtc_read(GorderXtc *x, int64_t first, int64_t count, int64_t stride, int32_t n_threads, float *xyz, float *box9, float *time,
+                    int32_t *step);
+/* Write frames with orthogonal boxes (xdrfile's compression): xyz [n_frames][n_atoms][3], box3 [n_frames][3]. */
+int gorder_xtc_write(const char *path, const float *xyz, const float *box3, int32_t n_atoms, int64_t n_frames, float precision, int32_t append,
+                     int32_t first_step, float dt, int32_t n_threads);
+void gorder_xtc_close(GorderXtc *x);
+/* analyze_frame for frames first, first + stride, ... < last: n_threads host threads decode straight into pinned
+ * batches in the plane layout (only the atoms the analysis needs), the decode of batch k+1 overlaps the copy and the
+ * kernels of batch k.  atom_of_slot[s] = trajectory atom of engine atom s (NULL: identity).  The j-th analysed frame
+ * gets frame_index j * stride (topology/mod.rs:141-144).  A non-orthogonal box fails with GORDER_ERR_NOT_ORTHOGONAL_BOX
+ * (common.rs:186-198).  decode_seconds (optional): host time spent decoding, summed over threads. */
+int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride,
+                       int32_t n_threads, int32_t batch_frames, double *decode_seconds);
+
 /* Human-readable detail of the last error of this handle (offending atom index etc.). */
 int gorder_gpu_last_error(GorderHandle *h, char *buf, size_t len);
 

@@ -1,0 +1,99 @@
+"""Host-side trajectory feed (gorder_xtc_* in the C ABI): XTC writer / reader, no GPU needed.
+
+The product reader is checked against (i) its own writer (round trip on the lattice), (ii) the oracle's independent
+reader (oracle/xtc.c, the restatement of xdrfile's xdr3dfcoord used for the fixtures) on the same files and
+(iii) -- only where /root/reference is mounted -- the reference's own trajectory tests/files/ua.xtc.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from gorder_b200 import synthetic
+from gorder_b200.xtc import XtcFile, write_xtc
+
+
+def _lattice(xyz, precision):
+    lf = xyz.astype(np.float32) * np.float32(precision)
+    li = np.where(lf >= 0, lf + np.float32(0.5), lf - np.float32(0.5)).astype(np.int32)
+    return li.astype(np.float32) * (np.float32(1.0) / np.float32(precision))
+
+
+def _oracle_read(path):
+    from oracle import fixtures
+    return fixtures.read_xtc(path)
+
+
+@pytest.mark.parametrize("kind,precision", [("cg", 1000.0), ("aa", 1000.0), ("cg", 100.0), ("gas", 1000.0), ("tiny", 1000.0)])
+def test_round_trip_and_oracle_reader(tmp_path, kind, precision):
+    rng = np.random.default_rng(7)
+    if kind == "cg":
+        s = synthetic.s_cg(700)
+        xyz, box, _ = s.frames(0, 5)
+    elif kind == "aa":
+        s = synthetic.s_aa(40, n_water=900)     # bonded hydrogens (runs) + scattered water (no runs)
+        xyz, box, _ = s.frames(0, 4)
+    elif kind == "gas":                          # huge box: per-coordinate bit sizes (sizeint > 2^24), negative coordinates
+        xyz = (rng.random((3, 500, 3)) * 40000.0 - 20000.0).astype(np.float32)
+        box = np.full((3, 3), 40000.0, np.float32)
+    else:                                        # <= 9 atoms: stored uncompressed
+        xyz = rng.random((4, 7, 3)).astype(np.float32)
+        box = np.full((4, 3), 3.0, np.float32)
+    path = str(tmp_path / "t.xtc")
+    write_xtc(path, xyz[:2], box[:2], precision=precision, dt=2.0)
+    write_xtc(path, xyz[2:], box[2:], precision=precision, append=True, first_step=2, dt=2.0)
+    with XtcFile(path) as x:
+        assert (x.n_atoms, x.n_frames) == (xyz.shape[1], xyz.shape[0])
+        got, box9, time, step = x.read(n_threads=3)
+        want = xyz if kind == "tiny" else _lattice(xyz, precision)
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(box9[:, [0, 4, 8]], box)
+        assert not box9[:, [1, 2, 3, 5, 6, 7]].any()
+        np.testing.assert_array_equal(step, np.arange(xyz.shape[0]))
+        np.testing.assert_allclose(time, 2.0 * np.arange(xyz.shape[0]))
+        # strided random access, single thread
+        sub, _, _, st2 = x.read(first=1, stride=2, n_threads=1)
+        np.testing.assert_array_equal(sub, want[1::2])
+        np.testing.assert_array_equal(st2, np.arange(xyz.shape[0])[1::2])
+    if kind in ("cg", "aa"):
+        assert os.path.getsize(path) < 0.6 * xyz.nbytes     # it does compress
+    ref = _oracle_read(path)
+    np.testing.assert_array_equal(np.asarray(ref.xyz, np.float32).reshape(got.shape), got)
+
+
+def test_compression_uses_runs(tmp_path):
+    """Bonded beads 0.47 nm apart are stored as small displacements (runs): well under the 6+ bytes / atom of the
+    run-free encoding for this box."""
+    s = synthetic.s_cg(3000)
+    xyz, box, _ = s.frames(0, 2)
+    path = str(tmp_path / "c.xtc")
+    write_xtc(path, xyz, box)
+    assert os.path.getsize(path) / (2 * xyz.shape[1]) < 5.0
+
+
+def test_truncated_and_bad_files(tmp_path):
+    s = synthetic.s_cg(100)
+    xyz, box, _ = s.frames(0, 3)
+    path = str(tmp_path / "t.xtc")
+    write_xtc(path, xyz, box)
+    raw = open(path, "rb").read()
+    cut = str(tmp_path / "cut.xtc")
+    open(cut, "wb").write(raw[: len(raw) - 100])           # last frame incomplete: ignored
+    with XtcFile(cut) as x:
+        assert x.n_frames == 2
+    bad = str(tmp_path / "bad.xtc")
+    open(bad, "wb").write(b"\x00" * 200)
+    with pytest.raises(OSError):
+        XtcFile(bad)
+    with pytest.raises(OSError):
+        XtcFile(str(tmp_path / "missing.xtc"))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/tests/files/ua.xtc"), reason="reference tree not mounted")
+def test_reference_trajectory_matches_oracle_reader():
+    path = "/root/reference/tests/files/ua.xtc"
+    ref = _oracle_read(path)
+    with XtcFile(path) as x:
+        got, box9, time, step = x.read()
+    np.testing.assert_array_equal(got, np.asarray(ref.xyz, np.float32).reshape(got.shape))
+    assert got.shape[0] == 51 and got.shape[1] == 19790
