@@ -378,10 +378,11 @@ int gorder_xtc_write(const char *path, const float *xyz, const float *box3, int3
 // analyze_frame for the frames first, first + stride, ... < last of an open trajectory: n_threads host threads decode
 // straight into pinned batches in the plane layout (only the atoms the engine needs; the bit stream of a frame is read
 // up to the last of them), gorder_gpu_submit_native runs them.  atom_of_slot[s] = trajectory atom of engine atom s
-// (NULL: identity).  frame_index of the j-th analysed frame is j * stride (topology/mod.rs:141-144).
+// (NULL: identity).  frame_index of the j-th analysed frame is frame_index0 + j * stride (topology/mod.rs:141-144;
+// frame_index0 = 0, or the continuation value when several files are concatenated, common.rs:306-339).
 // decode_seconds (optional): host time spent decoding, summed over threads.
-int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride, int32_t n_threads,
-                       int32_t batch_frames, double *decode_seconds) {
+int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride, int64_t frame_index0,
+                       int32_t n_threads, int32_t batch_frames, double *decode_seconds) {
     if (!h || !x || first < 0 || stride < 1) return GORDER_ERR_INVALID_ARGUMENT;
     if (h->err_code) return h->err_code;
     last = std::min<int64_t>(last, (int64_t)x->frames.size());
@@ -401,14 +402,21 @@ int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slo
     }
     const int B = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(batch_frames > 0 ? batch_frames : 32, h->max_batch), total));
     const size_t ff = (size_t)h->frame_floats;
-    float *pin[2] = {nullptr, nullptr}, *pbox[2] = {nullptr, nullptr};
-    auto release = [&]() { for (int i = 0; i < 2; i++) { if (pin[i]) cudaFreeHost(pin[i]); if (pbox[i]) cudaFreeHost(pbox[i]); } };
-    for (int i = 0; i < 2; i++) {
-        if (cudaMallocHost((void **)&pin[i], (size_t)B * ff * sizeof(float)) != cudaSuccess || cudaMallocHost((void **)&pbox[i], (size_t)B * 3 * sizeof(float)) != cudaSuccess) {
-            release(); h->set_error(GORDER_ERR_OUT_OF_MEMORY, "pinned batch buffers"); return h->err_code;
+    // pinned batch buffers live in the handle (pinning hundreds of MB costs more than decoding them)
+    if (h->xtc_pin_frames < B) {
+        for (int i = 0; i < 2; i++) { if (h->xtc_pin[i]) cudaFreeHost(h->xtc_pin[i]); if (h->xtc_pbox[i]) cudaFreeHost(h->xtc_pbox[i]); h->xtc_pin[i] = h->xtc_pbox[i] = nullptr; }
+        h->xtc_pin_frames = 0;
+        for (int i = 0; i < 2; i++) {
+            if (cudaMallocHost((void **)&h->xtc_pin[i], (size_t)B * ff * sizeof(float)) != cudaSuccess ||
+                cudaMallocHost((void **)&h->xtc_pbox[i], (size_t)B * 3 * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                h->set_error(GORDER_ERR_OUT_OF_MEMORY, "pinned batch buffers"); return h->err_code;
+            }
+            memset(h->xtc_pin[i], 0, (size_t)B * ff * sizeof(float));   // padding stays finite
         }
-        memset(pin[i], 0, (size_t)B * ff * sizeof(float));   // padding stays finite
+        h->xtc_pin_frames = B;
     }
+    float *pin[2] = {h->xtc_pin[0], h->xtc_pin[1]}, *pbox[2] = {h->xtc_pbox[0], h->xtc_pbox[1]};
     std::atomic<int> bad{0};
     std::atomic<long long> dec_ns{0};
     auto decode_batch = [&](int64_t j0, int nf, int buf) {
@@ -444,7 +452,7 @@ int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slo
     decode_batch(0, nf, 0);
     for (int buf = 0; j0 < total && !rc; buf ^= 1) {
         if (bad) { h->set_error(bad, bad == GORDER_ERR_NOT_ORTHOGONAL_BOX ? "simulation box is not orthogonal" : "corrupt XTC frame"); rc = h->err_code; break; }
-        for (int j = 0; j < nf; j++) fi[(size_t)j] = (j0 + j) * stride;
+        for (int j = 0; j < nf; j++) fi[(size_t)j] = frame_index0 + (j0 + j) * stride;
         // the next batch is decoded by a helper thread (which runs the pool) while this one is copied and analysed
         const int64_t j1 = j0 + nf;
         const int nf1 = (int)std::min<int64_t>(B, total - j1);
@@ -454,9 +462,6 @@ int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slo
         if (ahead.joinable()) ahead.join();
         j0 = j1; nf = nf1;
     }
-    if (!rc) { cudaStreamSynchronize(h->copy_stream); }
-    // the pinned buffers must outlive the asynchronous copies: submit_native waits for its H2D event before it returns
-    release();
     if (decode_seconds) *decode_seconds = (double)dec_ns.load() * 1e-9;
     return rc;
 }

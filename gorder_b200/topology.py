@@ -76,7 +76,7 @@ class SystemTopology:
         self._check(fn(self._h, C.c_void_p(d_ptr), C.c_void_p(d_box), _ptr(fi), n_frames))
 
     def run_xtc(self, xtc, atom_of_slot=None, first: int = 0, last: int | None = None, stride: int = 1, n_threads: int = 0,
-                batch_frames: int = 0) -> float:
+                batch_frames: int = 0, frame_index0: int = 0) -> float:
         """``read_trajectory`` for an open :class:`gorder_b200.xtc.XtcFile`: host threads decode, the engine analyses.
         Returns the host seconds spent decoding (summed over threads)."""
         import os
@@ -84,7 +84,7 @@ class SystemTopology:
         if m is not None and m.size != self.setup.n_atoms:
             raise ValueError("atom_of_slot must have one entry per engine atom")
         sec = C.c_double(0)
-        self._check(lib().gorder_gpu_run_xtc(self._h, xtc._x, _ptr(m), first, xtc.n_frames if last is None else last, stride,
+        self._check(lib().gorder_gpu_run_xtc(self._h, xtc._x, _ptr(m), first, xtc.n_frames if last is None else last, stride, frame_index0,
                                              n_threads or (os.cpu_count() or 1), batch_frames, C.byref(sec)))
         return float(sec.value)
 

@@ -338,10 +338,11 @@ void gorder_xtc_close(GorderXtc *x);
 /* analyze_frame for frames first, first + stride, ... < last: n_threads host threads decode straight into pinned
  * batches in the plane layout (only the atoms the analysis needs), the decode of batch k+1 overlaps the copy and the
  * kernels of batch k.  atom_of_slot[s] = trajectory atom of engine atom s (NULL: identity).  The j-th analysed frame
- * gets frame_index j * stride (topology/mod.rs:141-144).  A non-orthogonal box fails with GORDER_ERR_NOT_ORTHOGONAL_BOX
+ * gets frame_index frame_index0 + j * stride (topology/mod.rs:141-144; frame_index0 = 0, or the continuation value when
+ * several files are concatenated, common.rs:306-339).  A non-orthogonal box fails with GORDER_ERR_NOT_ORTHOGONAL_BOX
  * (common.rs:186-198).  decode_seconds (optional): host time spent decoding, summed over threads. */
 int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride,
-                       int32_t n_threads, int32_t batch_frames, double *decode_seconds);
+                       int64_t frame_index0, int32_t n_threads, int32_t batch_frames, double *decode_seconds);
 
 /* Human-readable detail of the last error of this handle (offending atom index etc.). */
 int gorder_gpu_last_error(GorderHandle *h, char *buf, size_t len);
