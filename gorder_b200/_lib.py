@@ -16,7 +16,7 @@ SYMBOLS = [
     "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block", "gorder_gpu_stats",
     "gorder_gpu_read_block", "gorder_gpu_write_block", "gorder_gpu_profile", "gorder_gpu_profile_read",
     "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_stream",
-    "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_gpu_run_xtc", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
+    "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
 ]
 
 
@@ -57,7 +57,8 @@ def lib() -> C.CDLL:
     L.gorder_xtc_close.argtypes = [vp]
     L.gorder_xtc_close.restype = None
     L.gorder_gpu_run_xtc.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, C.POINTER(C.c_double)]
-    for name in ("gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_gpu_run_xtc"):
+    L.gorder_gpu_run_xtc_device.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, C.POINTER(i64)]
+    for name in ("gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device"):
         getattr(L, name).restype = C.c_int
     L.gorder_gpu_fence.argtypes = [vp]
     L.gorder_gpu_fence.restype = C.c_int

@@ -43,6 +43,9 @@ bool g_fast_used[64][kFastSlots];
 
 }  // namespace
 
+struct GorderXtcDev;
+void gorder_xtc_dev_free(GorderXtcDev *d);
+
 struct GorderHandle {
     // ---- configuration (deep copy) ----
     GorderSetup s{};
@@ -171,6 +174,7 @@ struct GorderHandle {
     unsigned *d_pipe_ctrl = nullptr;   // [4 * max_batch + 1]: done0, done1, ready0, ready1, work
     float *d_pipe_est = nullptr, *d_pipe_center = nullptr;
 
+    struct GorderXtcDev *xtc_dev = nullptr;   // device-side XTC unpacker (gorder_gpu_run_xtc_device)
     // pinned batches of the trajectory feed (gorder_gpu_run_xtc)
     float *xtc_pin[2] = {nullptr, nullptr}, *xtc_pbox[2] = {nullptr, nullptr};
     int xtc_pin_frames = 0;
@@ -654,6 +658,7 @@ void gorder_gpu_destroy(GorderHandle *h) {
     }
     if (h->h_spec_counters) cudaFreeHost(h->h_spec_counters);
     for (int i = 0; i < 2; i++) { if (h->xtc_pin[i]) cudaFreeHost(h->xtc_pin[i]); if (h->xtc_pbox[i]) cudaFreeHost(h->xtc_pbox[i]); }
+    if (h->xtc_dev) gorder_xtc_dev_free(h->xtc_dev);
     if (h->fast_slot >= 0) {
         std::lock_guard<std::mutex> lock(g_fast_mu);
         g_fast_used[h->device][h->fast_slot] = false;

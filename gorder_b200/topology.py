@@ -88,6 +88,18 @@ class SystemTopology:
                                              n_threads or (os.cpu_count() or 1), batch_frames, C.byref(sec)))
         return float(sec.value)
 
+    def run_xtc_device(self, xtc, atom_of_slot=None, first: int = 0, last: int | None = None, stride: int = 1, n_threads: int = 0,
+                       batch_frames: int = 0, frame_index0: int = 0) -> int:
+        """``run_xtc`` with the XTC decode on the device; returns the bytes that crossed PCIe."""
+        import os
+        m = None if atom_of_slot is None else np.ascontiguousarray(atom_of_slot, dtype=np.int32)
+        if m is not None and m.size != self.setup.n_atoms:
+            raise ValueError("atom_of_slot must have one entry per engine atom")
+        moved = C.c_int64(0)
+        self._check(lib().gorder_gpu_run_xtc_device(self._h, xtc._x, _ptr(m), first, xtc.n_frames if last is None else last, stride, frame_index0,
+                                                    n_threads or (os.cpu_count() or 1), batch_frames, C.byref(moved)))
+        return int(moved.value)
+
     # -- layout -----------------------------------------------------------------------------------
     @property
     def frame_floats(self) -> int:

@@ -77,3 +77,53 @@ def test_run_xtc_atom_map_and_solvent(tmp_path):
         eng.close()
     np.testing.assert_array_equal(got.sum, want.sum)
     np.testing.assert_array_equal(got.count, want.count)
+
+
+@pytest.mark.parametrize("case", ["cg", "aa_map", "wide_lattice", "cg_prec100"])
+def test_device_decode_equals_host_decode(tmp_path, case):
+    """xtc_scan_kernel + xtc_decode_kernel give the engine the same coordinates as the host decoder, bit for bit:
+    identical accumulators for runs of bonded beads, scattered solvent with an atom map, per-coordinate bit sizes
+    (lattice wider than 2^24) and a coarse lattice; several batch sizes, begin / stride."""
+    precision, perm = 1000.0, None
+    if case == "aa_map":
+        s = synthetic.s_aa(64, n_water=3000, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True)
+        xyz, box, idx = s.frames(0, 7)
+        rng = np.random.default_rng(11)
+        perm = rng.permutation(s.n_atoms).astype(np.int32)
+        traj = np.empty_like(xyz)
+        traj[:, perm] = xyz
+    else:
+        s = synthetic.s_cg(2600, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True, collect_leaflets=True)
+        xyz, box, idx = s.frames(0, 9)
+        traj = xyz
+        precision = {"cg": 1000.0, "wide_lattice": 2.0e6, "cg_prec100": 100.0}[case]
+    path = str(tmp_path / "t.xtc")
+    write_xtc(path, traj, box, precision=precision)
+    with XtcFile(path) as x:
+        eng = SystemTopology(s.setup)
+        eng.run_xtc(x, atom_of_slot=perm, batch_frames=4, n_threads=4)
+        want = eng.finish()
+        eng.close()
+        for batch in (2, 64):
+            eng = SystemTopology(s.setup)
+            moved = eng.run_xtc_device(x, atom_of_slot=perm, batch_frames=batch, n_threads=3)
+            got = eng.finish()
+            eng.close()
+            assert 0 < moved < 0.8 * traj.nbytes
+            np.testing.assert_array_equal(got.sum, want.sum)
+            np.testing.assert_array_equal(got.count, want.count)
+            np.testing.assert_array_equal(got.tw_sum, want.tw_sum)
+            if got.leaflets is not None:
+                np.testing.assert_array_equal(got.leaflets, want.leaflets)
+        # begin / stride, two calls continuing the frame count (concatenated reading)
+        a = SystemTopology(s.setup)
+        a.run_xtc(x, atom_of_slot=perm, first=1, stride=2, batch_frames=3)
+        wa = a.finish()
+        a.close()
+        b = SystemTopology(s.setup)
+        b.run_xtc_device(x, atom_of_slot=perm, first=1, last=4, stride=2, batch_frames=3)
+        b.run_xtc_device(x, atom_of_slot=perm, first=5, stride=2, batch_frames=3, frame_index0=4)
+        wb = b.finish()
+        b.close()
+        np.testing.assert_array_equal(wa.sum, wb.sum)
+        np.testing.assert_array_equal(wa.tw_frame_index, wb.tw_frame_index)
