@@ -339,11 +339,26 @@ def run_ours(args):
                 rx = eng4.finish()
                 dt_x = time.perf_counter() - t0
                 eng4.close()
+                # the same file with the decode on the device: host threads only copy compressed bytes
+                eng5 = SystemTopology(s.setup)
+                eng5.reserve_frames(3 * nx + 8)
+                eng5.run_xtc_device(xf, last=min(nx, args.xtc_dev_batch), n_threads=threads_x, batch_frames=args.xtc_dev_batch)   # warm-up: buffers
+                eng5.sync()
+                torch.cuda.synchronize()
+                reps = 3
+                t0 = time.perf_counter()
+                for r_ in range(reps):
+                    moved = eng5.run_xtc_device(xf, n_threads=threads_x, batch_frames=args.xtc_dev_batch, frame_index0=(r_ + 1) * nx)
+                rd = eng5.finish()
+                dt_d = (time.perf_counter() - t0) / reps
+                eng5.close()
         e2e_xtc = {"value": nx * spf / dt_x, "unit": UNIT, "frames": nx, "file_bytes": fbytes, "bytes_per_atom": fbytes / nx / s.n_atoms,
                    "decode_threads": threads_x, "decode_thread_seconds": dec_s, "wall_seconds": dt_x,
                    "decode_atoms_per_s_per_thread": nx * s.n_atoms / max(dec_s, 1e-9),
                    "entry": "gorder_gpu_run_xtc (host XTC decode + H2D + analysis + D2H of the sums; rank 0)",
-                   "samples_accumulated_incl_warmup": int(rx.count[:, 0].sum())}
+                   "samples_accumulated_incl_warmup": int(rx.count[:, 0].sum()),
+                   "device_decode": {"value": nx * spf / dt_d, "unit": UNIT, "wall_seconds": dt_d, "h2d_bytes": moved, "h2d_bytes_per_atom": moved / nx / s.n_atoms,
+                                     "entry": "gorder_gpu_run_xtc_device (host copies + bookmarks the compressed frames; xtc_decode_kernel unpacks them on the GPU)"}}
 
     out = None
     if rank == 0:
@@ -411,6 +426,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--xtc-frames", type=int, default=64, help="frames of the XTC end-to-end leg (0 = skip)")
     ap.add_argument("--xtc-batch", type=int, default=16, help="frames per decoded batch of the XTC leg")
+    ap.add_argument("--xtc-dev-batch", type=int, default=16, help="frames per batch of the device-decode XTC leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.lipids = args.lipids or WORKLOADS[args.workload][1]

@@ -469,45 +469,83 @@ int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slo
 }  // extern "C"
 
 // =====================================================================================================================
-// Device-side XTC unpacking ("later a GPU XTC bit-unpacker"): the host only copies the compressed
-// frames; the GPU decodes them.  From decoded floats the end-to-end path moves 12 B per atom over PCIe, from a file the
-// host decode bounds it (§6.1 of DESIGN.md); the compressed stream is ~4-6 B per atom and the GPU decodes a batch in a
-// few milliseconds.
+// Device-side XTC unpacking ("later a GPU XTC bit-unpacker"): the GPU does the arithmetic of the
+// decode, the host only copies the compressed frames and bookmarks them.  From decoded floats the end-to-end path moves
+// 12 B per atom over PCIe, from a file the host decode bounds it; the compressed stream is 4-6 B per
+// atom.
 //
 // The bit stream of a frame is sequential only in its CONTROL information: where a group (one "large" atom + run / 3
-// "small" atoms) starts depends on the run flags and on smallidx, not on the coordinates.  Two kernels:
-//   xtc_scan_kernel    one lane per frame walks the stream reading ONLY the flag / run bits and records, per group,
-//                      (bit offset, run, smallidx, first atom) -- ~6 bits looked at per group, the rest is skipped;
-//   xtc_decode_kernel  one thread per group extracts the mixed-radix triples (64-bit arithmetic), rebuilds the lattice
-//                      points of its atoms and writes  int * (1 / precision)  in f32 -- the reader's arithmetic -- into
-//                      the [atom][xyz] staging frame of the engine (atoms the analysis does not need are dropped).
-// Frames the device path does not cover (more than 64 bits per triple: boxes beyond 2^21 lattice units per axis with
-// three large axes; <= 9 atoms) take the host decoder.
+// "small" atoms) starts depends on the run flags and on smallidx, not on the coordinates.
+//   host (the threads that copy a frame into the pinned batch): walk the control bits only -- 6 bits looked at per
+//        group, no arithmetic -- and drop a bookmark (bit offset, first atom, run, smallidx) every 32 groups;
+//   xtc_decode_kernel: one thread per group.  Lane j of a warp starts at the warp's bookmark, walks j groups forward
+//        (control bits only), then extracts the mixed-radix triples of ITS group (64-bit arithmetic), rebuilds the
+//        lattice points of its atoms and writes  int * (1 / precision)  in f32 -- the reader's arithmetic -- into the
+//        [atom][xyz] staging frame of the engine (atoms the analysis does not need are dropped).
+// (A first version walked the whole frame on the device, one lane per frame: 133 ms per frame-walk whatever the batch,
+//  i.e. ~1000 frames in flight to keep PCIe busy; the bookmarks cost the host ~1 ms per frame and thread.)
+// Frames the device path does not cover (more than 64 bits per triple, <= 9 atoms) take the host decoder.
 // =====================================================================================================================
 namespace gxtc {
 
+constexpr int kBookmarkEvery = 32;   // groups per bookmark = lanes per warp
+struct Bookmark { unsigned pos, atom0; unsigned short run, sidx; unsigned pad; };
+
 struct DevFrame {
     unsigned long long payload;   // byte offset of the frame's stream in the batch buffer (multiple of 16)
+    unsigned long long bookmarks; // index of the frame's first bookmark
     unsigned nbytes;
-    int natoms, smallidx, bitsize;
+    int natoms, n_groups, bitsize;
     int minint[3];
     unsigned sizeint[3];
     int bitsint[3];
     float inv_precision;
 };
 
+// host: bookmarks of one frame; returns the number of groups, or -1 when the stream is inconsistent / not covered
+inline int bookmark_frame(const uint8_t *base, const Frame &f, int large_bits, std::vector<Bookmark> &out) {
+    const uint8_t *p = base + f.payload;
+    const unsigned long long end = (unsigned long long)f.nbytes * 8ull;
+    unsigned long long pos = 0;
+    int i = 0, g = 0, run = 0, sidx = f.smallidx;
+    while (i < f.natoms) {
+        if (pos + large_bits + 1 > end || sidx < kFirstIdx || sidx > 64) return -1;
+        if ((g % kBookmarkEvery) == 0) out.push_back(Bookmark{(unsigned)pos, (unsigned)i, (unsigned short)run, (unsigned short)sidx, 0u});
+        pos += large_bits;
+        // flag (1 bit) and, when set, the run code (5 bits): two bytes cover them
+        const size_t b = (size_t)(pos >> 3);
+        const unsigned two = ((unsigned)p[b] << 8) | (b + 1 < f.nbytes ? p[b + 1] : 0u);
+        const unsigned six = (two >> (10 - (pos & 7))) & 63u;
+        int is_smaller = 0;
+        if (six & 32u) {
+            const int code = (int)(six & 31u);
+            is_smaller = code % 3;
+            run = code - is_smaller;
+            is_smaller--;
+            pos += 6;
+        } else pos += 1;
+        const int smalls = run / 3;
+        pos += (unsigned long long)smalls * sidx;
+        i += 1 + smalls;
+        sidx += is_smaller;
+        g++;
+    }
+    if (i != f.natoms || pos > end) return -1;
+    return g;
+}
+
 __constant__ int c_magic[73];
 
 // n <= 32 bits starting at bit `pos` of a big-endian bit stream stored in 32-bit words
-__device__ __forceinline__ unsigned dev_bits(const unsigned *__restrict__ w, unsigned long long pos, int n) {
+__device__ __forceinline__ unsigned dev_bits(const unsigned *__restrict__ w, unsigned pos, int n) {
     if (n == 0) return 0u;
-    const unsigned long long i = pos >> 5;
+    const unsigned i = pos >> 5;
     const unsigned w0 = __byte_perm(__ldg(w + i), 0, 0x0123), w1 = __byte_perm(__ldg(w + i + 1), 0, 0x0123);
-    const unsigned v = __funnelshift_l(w1, w0, (unsigned)(pos & 31));
+    const unsigned v = __funnelshift_l(w1, w0, pos & 31u);
     return v >> (32 - n);
 }
 // the mixed-radix number of a triple (n <= 64): bytes least significant first, the last one may be partial
-__device__ __forceinline__ unsigned long long dev_le(const unsigned *__restrict__ w, unsigned long long pos, int n) {
+__device__ __forceinline__ unsigned long long dev_le(const unsigned *__restrict__ w, unsigned pos, int n) {
     unsigned long long v = 0;
     int shift = 0;
     while (n >= 32) {   // four whole bytes: the stream's first byte is the least significant one
@@ -532,25 +570,22 @@ __device__ __forceinline__ void dev_unpack3(unsigned long long v, unsigned s1, u
     }
 }
 
-// one lane per frame (lane 0 of a warp of its own: the walk is a chain of dependent loads, a whole warp would diverge)
-__global__ void __launch_bounds__(32) xtc_scan_kernel(const unsigned char *__restrict__ bytes, const DevFrame *__restrict__ frames, int max_groups,
-                                                      unsigned long long *__restrict__ meta, int *__restrict__ atom0, int *__restrict__ n_groups,
-                                                      int *__restrict__ err) {
-    if (threadIdx.x != 0) return;
-    const int f = blockIdx.x;
-    const DevFrame fr = frames[f];
-    const unsigned *w = reinterpret_cast<const unsigned *>(bytes + fr.payload);
-    const unsigned long long end = (unsigned long long)fr.nbytes * 8ull;
-    const int large_bits = fr.bitsize ? fr.bitsize : fr.bitsint[0] + fr.bitsint[1] + fr.bitsint[2];
-    unsigned long long pos = 0;
-    int i = 0, g = 0, run = 0, sidx = fr.smallidx;
-    unsigned long long *m = meta + (size_t)f * max_groups;
-    int *a0 = atom0 + (size_t)f * max_groups;
-    while (i < fr.natoms) {
-        if (pos + large_bits + 1 > end || sidx < 9 || sidx > 64) { atomicExch(err, 1 + f); break; }
-        const unsigned long long start = pos;
+__global__ void __launch_bounds__(256) xtc_decode_kernel(const unsigned char *__restrict__ bytes, const DevFrame *__restrict__ frames,
+                                                         const Bookmark *__restrict__ bookmarks, const int *__restrict__ slot_of_atom,
+                                                         int n_engine_atoms, float *__restrict__ xyz) {
+    const int f = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const DevFrame &fr = frames[f];
+    if (g >= __ldg(&fr.n_groups)) return;
+    const unsigned *w = reinterpret_cast<const unsigned *>(bytes + __ldg(&fr.payload));
+    const int bitsize = __ldg(&fr.bitsize);
+    const int large_bits = bitsize ? bitsize : __ldg(&fr.bitsint[0]) + __ldg(&fr.bitsint[1]) + __ldg(&fr.bitsint[2]);
+    // ---- from the warp's bookmark to this lane's group: control bits only ----
+    const Bookmark bm = bookmarks[__ldg(&fr.bookmarks) + (unsigned)(g / kBookmarkEvery)];
+    unsigned pos = bm.pos;
+    int i = (int)bm.atom0, run = bm.run, sidx = bm.sidx;
+    for (int step = g % kBookmarkEvery; step > 0; step--) {
         pos += large_bits;
-        // flag (1 bit) and, when set, the run code (5 bits) in one look
         const unsigned six = dev_bits(w, pos, 6);
         int is_smaller = 0;
         if (six & 32u) {
@@ -560,31 +595,12 @@ __global__ void __launch_bounds__(32) xtc_scan_kernel(const unsigned char *__res
             is_smaller--;
             pos += 6;
         } else pos += 1;
-        m[g] = start | ((unsigned long long)run << 40) | ((unsigned long long)sidx << 48);
-        a0[g] = i;
-        g++;
         const int smalls = run / 3;
-        pos += (unsigned long long)smalls * sidx;
+        pos += (unsigned)(smalls * sidx);
         i += 1 + smalls;
         sidx += is_smaller;
     }
-    if (i != fr.natoms || pos > end) atomicExch(err, 1 + f);
-    n_groups[f] = g;
-}
-
-__global__ void __launch_bounds__(256) xtc_decode_kernel(const unsigned char *__restrict__ bytes, const DevFrame *__restrict__ frames, int max_groups,
-                                                         const unsigned long long *__restrict__ meta, const int *__restrict__ atom0,
-                                                         const int *__restrict__ n_groups, const int *__restrict__ slot_of_atom, int n_engine_atoms,
-                                                         float *__restrict__ xyz) {
-    const int f = blockIdx.y;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_groups[f]) return;
-    const DevFrame &fr = frames[f];
-    const unsigned *w = reinterpret_cast<const unsigned *>(bytes + __ldg(&fr.payload));
-    const unsigned long long mt = meta[(size_t)f * max_groups + g];
-    unsigned long long pos = mt & ((1ull << 40) - 1ull);
-    const int run = (int)((mt >> 40) & 0xff), sidx = (int)(mt >> 48);
-    int i = atom0[(size_t)f * max_groups + g];
+    // ---- this group ----
     const float inv = __ldg(&fr.inv_precision);
     float *out = xyz + (size_t)f * n_engine_atoms * 3;
     auto emit = [&](int atom, const int (&c)[3]) {
@@ -592,7 +608,6 @@ __global__ void __launch_bounds__(256) xtc_decode_kernel(const unsigned char *__
         if (s >= 0) { float *o = out + 3 * (size_t)s; o[0] = (float)c[0] * inv; o[1] = (float)c[1] * inv; o[2] = (float)c[2] * inv; }
     };
     int cur[3];
-    const int bitsize = __ldg(&fr.bitsize);
     if (bitsize) {
         dev_unpack3(dev_le(w, pos, bitsize), __ldg(&fr.sizeint[1]), __ldg(&fr.sizeint[2]), cur);
         pos += bitsize;
@@ -601,7 +616,11 @@ __global__ void __launch_bounds__(256) xtc_decode_kernel(const unsigned char *__
         for (int k = 0; k < 3; k++) { const int b = __ldg(&fr.bitsint[k]); cur[k] = (int)dev_bits(w, pos, b); pos += b; }
     }
     cur[0] += __ldg(&fr.minint[0]); cur[1] += __ldg(&fr.minint[1]); cur[2] += __ldg(&fr.minint[2]);
-    pos += (dev_bits(w, pos, 1) ? 6 : 1);
+    {   // this group's own flag / run code
+        const unsigned six = dev_bits(w, pos, 6);
+        if (six & 32u) { const int code = (int)(six & 31u); run = code - code % 3; pos += 6; }
+        else pos += 1;
+    }
     if (run == 0) { emit(i, cur); return; }
     const unsigned ss = (unsigned)c_magic[sidx];
     const int smallnum = c_magic[sidx] / 2;
@@ -622,21 +641,25 @@ __global__ void __launch_bounds__(256) xtc_decode_kernel(const unsigned char *__
 struct GorderXtcDev {   // device / pinned buffers of the unpacker, owned by the handle
     unsigned char *h_bytes[2] = {nullptr, nullptr}, *d_bytes[2] = {nullptr, nullptr};
     gxtc::DevFrame *h_frames[2] = {nullptr, nullptr}, *d_frames[2] = {nullptr, nullptr};
+    gxtc::Bookmark *h_marks[2] = {nullptr, nullptr}, *d_marks[2] = {nullptr, nullptr};
     float *h_box[2] = {nullptr, nullptr}, *d_box[2] = {nullptr, nullptr};
-    size_t bytes_cap = 0;
-    int frames_cap = 0, max_groups = 0, n_traj_atoms = 0;
-    unsigned long long *d_meta = nullptr;
-    int *d_atom0 = nullptr, *d_ngroups = nullptr, *d_slot_of_atom = nullptr, *d_err = nullptr;
+    size_t bytes_cap = 0, marks_per_frame = 0;
+    int frames_cap = 0, n_traj_atoms = 0;
+    int *d_slot_of_atom = nullptr;
     float *d_xyz = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool magic_uploaded = false;
     void free_all() {
         for (int i = 0; i < 2; i++) {
-            if (h_bytes[i]) cudaFreeHost(h_bytes[i]); if (h_frames[i]) cudaFreeHost(h_frames[i]); if (h_box[i]) cudaFreeHost(h_box[i]);
-            cudaFree(d_bytes[i]); cudaFree(d_frames[i]); cudaFree(d_box[i]);
-            if (ev_copied[i]) cudaEventDestroy(ev_copied[i]); if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+            if (h_bytes[i]) cudaFreeHost(h_bytes[i]);
+            if (h_frames[i]) cudaFreeHost(h_frames[i]);
+            if (h_marks[i]) cudaFreeHost(h_marks[i]);
+            if (h_box[i]) cudaFreeHost(h_box[i]);
+            cudaFree(d_bytes[i]); cudaFree(d_frames[i]); cudaFree(d_marks[i]); cudaFree(d_box[i]);
+            if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+            if (ev_done[i]) cudaEventDestroy(ev_done[i]);
         }
-        cudaFree(d_meta); cudaFree(d_atom0); cudaFree(d_ngroups); cudaFree(d_slot_of_atom); cudaFree(d_err); cudaFree(d_xyz);
+        cudaFree(d_slot_of_atom); cudaFree(d_xyz);
     }
 };
 
@@ -645,8 +668,8 @@ void gorder_xtc_dev_free(GorderXtcDev *d) { if (d) { d->free_all(); delete d; } 
 extern "C" {
 
 // gorder_gpu_run_xtc with the decode on the device.  Same arguments and results (the decoded coordinates are bit-identical
-// to the host decoder's); n_threads host threads only copy compressed bytes into the pinned batch.  bytes_h2d (optional):
-// bytes that crossed PCIe.
+// to the host decoder's); n_threads host threads copy the compressed frames into the pinned batch and bookmark them.
+// bytes_h2d (optional): bytes that crossed PCIe.
 int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride,
                               int64_t frame_index0, int32_t n_threads, int32_t batch_frames, int64_t *bytes_h2d) {
     if (!h || !x || first < 0 || stride < 1) return GORDER_ERR_INVALID_ARGUMENT;
@@ -661,7 +684,7 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
         unsigned sz[3];
         for (int k = 0; k < 3; k++) sz[k] = (unsigned)(f.maxint[k] - f.minint[k] + 1);
         const bool separate = (sz[0] | sz[1] | sz[2]) > 0xffffffu;
-        if (f.natoms <= 9 || (!separate && gxtc::bits_of_triple(sz) > 64) || f.nbytes > 0xfffffff0u)
+        if (f.natoms <= 9 || (!separate && gxtc::bits_of_triple(sz) > 64) || f.nbytes > 0x1ffffff0u)
             return gorder_gpu_run_xtc(h, x, atom_of_slot, first, last, stride, frame_index0, n_threads, batch_frames, nullptr);
         max_bytes = std::max(max_bytes, f.nbytes);
     }
@@ -669,28 +692,25 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
     if (!h->xtc_dev) h->xtc_dev = new GorderXtcDev();
     GorderXtcDev &D = *h->xtc_dev;
     const int na = h->s.n_atoms;
-    const int B = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(batch_frames > 0 ? batch_frames : 64, h->max_batch), total));
+    const int B = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(batch_frames > 0 ? batch_frames : 32, h->max_batch), total));
     const size_t frame_cap = ((max_bytes + 15) & ~(size_t)15) + 16;   // 16-byte aligned streams, one spare word for the reader's look-ahead
+    const size_t marks_per_frame = (size_t)x->natoms / gxtc::kBookmarkEvery + 2;
     if (!D.magic_uploaded) { CK(cudaMemcpyToSymbol(gxtc::c_magic, gxtc::kMagic, sizeof(gxtc::kMagic))); D.magic_uploaded = true; }
     if (D.frames_cap < B || D.bytes_cap < (size_t)B * frame_cap || D.n_traj_atoms != x->natoms) {
         CK(cudaStreamSynchronize(h->stream));
         D.free_all();
         D = GorderXtcDev();
         D.magic_uploaded = true;
-        D.frames_cap = B; D.bytes_cap = (size_t)B * frame_cap; D.max_groups = x->natoms; D.n_traj_atoms = x->natoms;
+        D.frames_cap = B; D.bytes_cap = (size_t)B * frame_cap; D.n_traj_atoms = x->natoms; D.marks_per_frame = marks_per_frame;
         for (int i = 0; i < 2; i++) {
             CK(cudaMallocHost((void **)&D.h_bytes[i], D.bytes_cap)); CK(cudaMalloc((void **)&D.d_bytes[i], D.bytes_cap));
             CK(cudaMallocHost((void **)&D.h_frames[i], B * sizeof(gxtc::DevFrame))); CK(cudaMalloc((void **)&D.d_frames[i], B * sizeof(gxtc::DevFrame)));
+            CK(cudaMallocHost((void **)&D.h_marks[i], B * marks_per_frame * sizeof(gxtc::Bookmark)));
+            CK(cudaMalloc((void **)&D.d_marks[i], B * marks_per_frame * sizeof(gxtc::Bookmark)));
             CK(cudaMallocHost((void **)&D.h_box[i], B * 3 * sizeof(float))); CK(cudaMalloc((void **)&D.d_box[i], B * 3 * sizeof(float)));
             CK(cudaEventCreateWithFlags(&D.ev_copied[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&D.ev_done[i], cudaEventDisableTiming));
-            memset(D.h_bytes[i], 0, D.bytes_cap);
         }
-        CK(cudaMalloc((void **)&D.d_meta, (size_t)B * D.max_groups * sizeof(unsigned long long)));
-        CK(cudaMalloc((void **)&D.d_atom0, (size_t)B * D.max_groups * sizeof(int)));
-        CK(cudaMalloc((void **)&D.d_ngroups, B * sizeof(int)));
         CK(cudaMalloc((void **)&D.d_slot_of_atom, (size_t)x->natoms * sizeof(int)));
-        CK(cudaMalloc((void **)&D.d_err, sizeof(int)));
-        CK(cudaMemset(D.d_err, 0, sizeof(int)));
         CK(cudaMalloc((void **)&D.d_xyz, (size_t)B * na * 3 * sizeof(float)));
         CK(cudaMemset(D.d_xyz, 0, (size_t)B * na * 3 * sizeof(float)));
     }
@@ -706,22 +726,30 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
     }
     std::vector<int64_t> fi((size_t)B);
     long long moved = 0;
-    int bad_box = 0;
-    auto stage = [&](int64_t j0, int nf, int buf) {   // compressed frames -> pinned batch (host threads only copy)
+    std::atomic<int> bad{0};
+    std::vector<int> n_groups((size_t)B);
+    auto stage = [&](int64_t j0, int nf, int buf) {   // compressed frames + bookmarks -> pinned batch
         std::atomic<int> next{0};
         auto work = [&]() {
+            std::vector<gxtc::Bookmark> marks;
             for (;;) {
                 const int j = next.fetch_add(1);
                 if (j >= nf) break;
                 const gxtc::Frame &f = x->frames[(size_t)(first + (j0 + j) * stride)];
-                if (f.box[1] != 0.0f || f.box[2] != 0.0f || f.box[3] != 0.0f || f.box[5] != 0.0f || f.box[6] != 0.0f || f.box[7] != 0.0f) bad_box = 1;
+                if (f.box[1] != 0.0f || f.box[2] != 0.0f || f.box[3] != 0.0f || f.box[5] != 0.0f || f.box[6] != 0.0f || f.box[7] != 0.0f) bad = GORDER_ERR_NOT_ORTHOGONAL_BOX;
                 gxtc::DevFrame &d = D.h_frames[buf][j];
-                d.payload = (unsigned long long)j * frame_cap; d.nbytes = (unsigned)f.nbytes; d.natoms = f.natoms; d.smallidx = f.smallidx;
+                d.payload = (unsigned long long)j * frame_cap; d.bookmarks = (unsigned long long)j * marks_per_frame;
+                d.nbytes = (unsigned)f.nbytes; d.natoms = f.natoms;
                 unsigned sz[3];
                 for (int k = 0; k < 3; k++) { d.minint[k] = f.minint[k]; sz[k] = d.sizeint[k] = (unsigned)(f.maxint[k] - f.minint[k] + 1); }
                 if ((sz[0] | sz[1] | sz[2]) > 0xffffffu) { d.bitsize = 0; for (int k = 0; k < 3; k++) d.bitsint[k] = gxtc::bits_of(sz[k]); }
                 else { d.bitsize = gxtc::bits_of_triple(sz); d.bitsint[0] = d.bitsint[1] = d.bitsint[2] = 0; }
                 d.inv_precision = 1.0f / f.precision;
+                marks.clear();
+                const int ng = gxtc::bookmark_frame(x->data, f, d.bitsize ? d.bitsize : d.bitsint[0] + d.bitsint[1] + d.bitsint[2], marks);
+                if (ng < 0 || marks.size() > marks_per_frame) { bad = GORDER_ERR_INVALID_ARGUMENT; d.n_groups = 0; }
+                else { d.n_groups = ng; memcpy(D.h_marks[buf] + d.bookmarks, marks.data(), marks.size() * sizeof(gxtc::Bookmark)); }
+                n_groups[(size_t)j] = d.n_groups;
                 unsigned char *dst = D.h_bytes[buf] + d.payload;
                 memcpy(dst, x->data + f.payload, f.nbytes);
                 memset(dst + f.nbytes, 0, frame_cap - f.nbytes);
@@ -740,19 +768,20 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
     CK(cudaEventSynchronize(D.ev_done[0]));
     stage(0, nf, 0);
     for (int buf = 0; j0 < total && !rc; buf ^= 1) {
-        if (bad_box) { h->set_error(GORDER_ERR_NOT_ORTHOGONAL_BOX, "simulation box is not orthogonal"); rc = h->err_code; break; }
-        const size_t nbytes = (size_t)nf * frame_cap;
+        if (bad) { h->set_error(bad, bad == GORDER_ERR_NOT_ORTHOGONAL_BOX ? "simulation box is not orthogonal" : "corrupt or unsupported XTC frame"); rc = h->err_code; break; }
+        const size_t nbytes = (size_t)nf * frame_cap, mbytes = (size_t)nf * marks_per_frame * sizeof(gxtc::Bookmark);
         CK(cudaMemcpyAsync(D.d_bytes[buf], D.h_bytes[buf], nbytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaMemcpyAsync(D.d_marks[buf], D.h_marks[buf], mbytes, cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaMemcpyAsync(D.d_frames[buf], D.h_frames[buf], nf * sizeof(gxtc::DevFrame), cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaMemcpyAsync(D.d_box[buf], D.h_box[buf], nf * 3 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaEventRecord(D.ev_copied[buf], h->copy_stream));
-        moved += (long long)nbytes;
+        moved += (long long)(nbytes + mbytes);
         CK(cudaStreamWaitEvent(h->stream, D.ev_copied[buf], 0));
-        gxtc::xtc_scan_kernel<<<nf, 32, 0, h->stream>>>(D.d_bytes[buf], D.d_frames[buf], D.max_groups, D.d_meta, D.d_atom0, D.d_ngroups, D.d_err);
-        dim3 grid((x->natoms + 255) / 256, nf);
-        gxtc::xtc_decode_kernel<<<grid, 256, 0, h->stream>>>(D.d_bytes[buf], D.d_frames[buf], D.max_groups, D.d_meta, D.d_atom0, D.d_ngroups,
-                                                             D.d_slot_of_atom, na, D.d_xyz);
-        h->n_launches += 2;
+        int max_groups = 1;
+        for (int j = 0; j < nf; j++) max_groups = std::max(max_groups, n_groups[(size_t)j]);
+        dim3 grid((max_groups + 255) / 256, nf);
+        gxtc::xtc_decode_kernel<<<grid, 256, 0, h->stream>>>(D.d_bytes[buf], D.d_frames[buf], D.d_marks[buf], D.d_slot_of_atom, na, D.d_xyz);
+        h->n_launches++;
         CK(cudaGetLastError());
         for (int j = 0; j < nf; j++) fi[(size_t)j] = frame_index0 + (j0 + j) * stride;
         rc = gorder_gpu_submit_device(h, D.d_xyz, D.d_box[buf], fi.data(), nf);
@@ -765,12 +794,6 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
             stage(j1, nf1, buf ^ 1);
         }
         j0 = j1; nf = nf1;
-    }
-    if (!rc) {
-        int e = 0;
-        CK(cudaMemcpyAsync(&e, D.d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        if (e) { CK(cudaMemset(D.d_err, 0, sizeof(int))); h->set_error(GORDER_ERR_INVALID_ARGUMENT, "corrupt or unsupported XTC frame", e - 1); rc = h->err_code; }
     }
     if (bytes_h2d) *bytes_h2d = moved;
     return rc;

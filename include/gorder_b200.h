@@ -345,8 +345,8 @@ int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slo
                        int64_t frame_index0, int32_t n_threads, int32_t batch_frames, double *decode_seconds);
 
 /* The same with the decode on the DEVICE: host threads only copy the compressed frames into pinned batches
- * (4-6 B per atom cross PCIe instead of 12), xtc_scan_kernel finds the groups of every frame from the control bits,
- * xtc_decode_kernel unpacks them in parallel into the engine's staging frames.  Coordinates are bit-identical to the
+ * and bookmark every 32nd group of the bit stream (control bits only; 4-6 B per atom cross PCIe instead of 12);
+ * xtc_decode_kernel unpacks the groups in parallel into the engine's staging frames.  Coordinates are bit-identical to the
  * host decoder's.  Frames the device path does not cover (> 64 bits per triple, <= 9 atoms) take the host decoder.
  * bytes_h2d (optional): bytes that crossed PCIe. */
 int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride,
