@@ -251,6 +251,8 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_win0 = time.perf_counter()
     with torch.cuda.stream(stream):   # the engine's main stream is torch's current stream: NCCL orders itself after it
+        if world > 1:   # align the DEVICE timelines of the ranks (the host barrier above leaves ~1 ms of launch skew)
+            dist.all_reduce(torch.zeros(1, device="cuda"))
         ev0.record()
         for k in range(W, W + K):
             step(k)
@@ -424,7 +426,7 @@ def main():
     ap.add_argument("--lipids", type=int, default=0, help="0 = workload default")
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU arms; 0 = one per host thread")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--xtc-frames", type=int, default=64, help="frames of the XTC end-to-end leg (0 = skip)")
+    ap.add_argument("--xtc-frames", type=int, default=256, help="frames of the XTC end-to-end leg (0 = skip)")
     ap.add_argument("--xtc-batch", type=int, default=16, help="frames per decoded batch of the XTC leg")
     ap.add_argument("--xtc-dev-batch", type=int, default=16, help="frames per batch of the device-decode XTC leg")
     args = ap.parse_args()

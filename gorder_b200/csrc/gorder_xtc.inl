@@ -502,35 +502,49 @@ struct DevFrame {
     float inv_precision;
 };
 
-// host: bookmarks of one frame; returns the number of groups, or -1 when the stream is inconsistent / not covered
+// host: bookmarks of one frame; returns the number of groups, or -1 when the stream is inconsistent / not covered.
+// Branch-free in the data: the run code is translated by two 32-entry tables (code = run + is_smaller + 1).
+struct RunTables {
+    signed char smalls[32], delta[32];
+    RunTables() { for (int c = 0; c < 32; c++) { const int sm = c % 3; smalls[c] = (signed char)((c - sm) / 3); delta[c] = (signed char)(sm - 1); } }
+};
 inline int bookmark_frame(const uint8_t *base, const Frame &f, int large_bits, std::vector<Bookmark> &out) {
+    static const RunTables T;
     const uint8_t *p = base + f.payload;
     const unsigned long long end = (unsigned long long)f.nbytes * 8ull;
+    if (end < 16) return -1;
+    const unsigned long long last_safe = end - 16;   // the two-byte look stays inside the stream below this offset
     unsigned long long pos = 0;
-    int i = 0, g = 0, run = 0, sidx = f.smallidx;
-    while (i < f.natoms) {
-        if (pos + large_bits + 1 > end || sidx < kFirstIdx || sidx > 64) return -1;
-        if ((g % kBookmarkEvery) == 0) out.push_back(Bookmark{(unsigned)pos, (unsigned)i, (unsigned short)run, (unsigned short)sidx, 0u});
+    int i = 0, g = 0, smalls = 0, sidx = f.smallidx;
+    const int n = f.natoms;
+    while (i < n) {
+        if (sidx < kFirstIdx || sidx > 64) return -1;
+        if ((g % kBookmarkEvery) == 0) out.push_back(Bookmark{(unsigned)pos, (unsigned)i, (unsigned short)(3 * smalls), (unsigned short)sidx, 0u});
         pos += large_bits;
-        // flag (1 bit) and, when set, the run code (5 bits): two bytes cover them
+        if (pos > last_safe) {   // tail of the stream: careful byte access
+            if (pos + 1 > end) return -1;
+            const size_t b = (size_t)(pos >> 3);
+            const unsigned two = ((unsigned)p[b] << 8) | (b + 1 < f.nbytes ? p[b + 1] : 0u);
+            const unsigned six = (two >> (10 - (pos & 7))) & 63u;
+            const unsigned flag = six >> 5, code = six & 31u;
+            if (flag) smalls = T.smalls[code];
+            pos += 1 + 5 * flag + (unsigned long long)smalls * sidx;
+            i += 1 + smalls;
+            sidx += flag ? T.delta[code] : 0;
+            g++;
+            continue;
+        }
         const size_t b = (size_t)(pos >> 3);
-        const unsigned two = ((unsigned)p[b] << 8) | (b + 1 < f.nbytes ? p[b + 1] : 0u);
+        const unsigned two = ((unsigned)p[b] << 8) | p[b + 1];
         const unsigned six = (two >> (10 - (pos & 7))) & 63u;
-        int is_smaller = 0;
-        if (six & 32u) {
-            const int code = (int)(six & 31u);
-            is_smaller = code % 3;
-            run = code - is_smaller;
-            is_smaller--;
-            pos += 6;
-        } else pos += 1;
-        const int smalls = run / 3;
-        pos += (unsigned long long)smalls * sidx;
+        const unsigned flag = six >> 5, code = six & 31u;
+        smalls = flag ? T.smalls[code] : smalls;
+        pos += 1 + 5 * flag + (unsigned long long)(smalls * sidx);
         i += 1 + smalls;
-        sidx += is_smaller;
+        sidx += flag ? T.delta[code] : 0;
         g++;
     }
-    if (i != f.natoms || pos > end) return -1;
+    if (i != n || pos > end) return -1;
     return g;
 }
 
@@ -649,6 +663,7 @@ struct GorderXtcDev {   // device / pinned buffers of the unpacker, owned by the
     float *d_xyz = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool magic_uploaded = false;
+    std::vector<int> slot_cache;   // host copy of d_slot_of_atom
     void free_all() {
         for (int i = 0; i < 2; i++) {
             if (h_bytes[i]) cudaFreeHost(h_bytes[i]);
@@ -721,8 +736,11 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
             if (a < 0 || a >= x->natoms) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "atom_of_slot outside the trajectory", a); return h->err_code; }
             if (h->slot_off[s] >= 0) slot_of_atom[(size_t)a] = s;
         }
-        CK(cudaStreamSynchronize(h->stream));
-        CK(cudaMemcpy(D.d_slot_of_atom, slot_of_atom.data(), slot_of_atom.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (slot_of_atom != D.slot_cache) {   // unchanged between the calls of one run: keep the device copy
+            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaMemcpy(D.d_slot_of_atom, slot_of_atom.data(), slot_of_atom.size() * sizeof(int), cudaMemcpyHostToDevice));
+            D.slot_cache.swap(slot_of_atom);
+        }
     }
     std::vector<int64_t> fi((size_t)B);
     long long moved = 0;
