@@ -176,7 +176,8 @@ inline void encode_frame(std::vector<uint8_t> &o, const float *xyz, const float 
     wrf(o, precision);
     std::vector<int> L(3 * (size_t)natoms);
     int mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
-    long long mindiff = INT32_MAX;
+    std::vector<int> diffs;
+    diffs.reserve((size_t)natoms);
     for (int i = 0; i < natoms; i++) {
         for (int k = 0; k < 3; k++) {
             const float lf = xyz[3 * (size_t)i + k] * precision;
@@ -187,8 +188,17 @@ inline void encode_frame(std::vector<uint8_t> &o, const float *xyz, const float 
         if (i > 0) {
             long long d = 0;
             for (int k = 0; k < 3; k++) d += std::llabs((long long)L[3 * (size_t)i + k] - L[3 * (size_t)(i - 1) + k]);
-            mindiff = std::min(mindiff, d);
+            diffs.push_back((int)std::min<long long>(d, INT32_MAX));
         }
+    }
+    // xdrfile starts smallidx from the MINIMUM displacement between consecutive atoms.  In a real trajectory sterics keep
+    // that minimum at ~0.1 nm; in a synthetic one a single accidental close pair among a million atoms would switch the
+    // runs off for the whole frame, so the 1st percentile is used instead (any starting smallidx is a valid stream).
+    long long mindiff = INT32_MAX;
+    if (!diffs.empty()) {
+        const size_t q = diffs.size() / 100;
+        std::nth_element(diffs.begin(), diffs.begin() + q, diffs.end());
+        mindiff = diffs[q];
     }
     for (int k = 0; k < 3; k++) wr32(o, (uint32_t)mn[k]);
     for (int k = 0; k < 3; k++) wr32(o, (uint32_t)mx[k]);
@@ -502,7 +512,8 @@ struct DevFrame {
     float inv_precision;
 };
 
-// host: bookmarks of one frame; returns the number of groups, or -1 when the stream is inconsistent / not covered.
+// host: bookmarks of one frame; returns the number of groups, -1 when the stream is inconsistent, -2 when it needs
+// more than 64 bits per small triple (not covered by the device path).
 // Branch-free in the data: the run code is translated by two 32-entry tables (code = run + is_smaller + 1).
 struct RunTables {
     signed char smalls[32], delta[32];
@@ -518,7 +529,8 @@ inline int bookmark_frame(const uint8_t *base, const Frame &f, int large_bits, s
     int i = 0, g = 0, smalls = 0, sidx = f.smallidx;
     const int n = f.natoms;
     while (i < n) {
-        if (sidx < kFirstIdx || sidx > 64) return -1;
+        if (sidx > 64) return -2;
+        if (sidx < kFirstIdx) return -1;
         if ((g % kBookmarkEvery) == 0) out.push_back(Bookmark{(unsigned)pos, (unsigned)i, (unsigned short)(3 * smalls), (unsigned short)sidx, 0u});
         pos += large_bits;
         if (pos > last_safe) {   // tail of the stream: careful byte access
@@ -744,7 +756,7 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
     }
     std::vector<int64_t> fi((size_t)B);
     long long moved = 0;
-    std::atomic<int> bad{0};
+    std::atomic<int> bad{0}, unsupported{0};
     std::vector<int> n_groups((size_t)B);
     auto stage = [&](int64_t j0, int nf, int buf) {   // compressed frames + bookmarks -> pinned batch
         std::atomic<int> next{0};
@@ -765,7 +777,8 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
                 d.inv_precision = 1.0f / f.precision;
                 marks.clear();
                 const int ng = gxtc::bookmark_frame(x->data, f, d.bitsize ? d.bitsize : d.bitsint[0] + d.bitsint[1] + d.bitsint[2], marks);
-                if (ng < 0 || marks.size() > marks_per_frame) { bad = GORDER_ERR_INVALID_ARGUMENT; d.n_groups = 0; }
+                if (ng == -2) { unsupported = 1; d.n_groups = 0; }
+                else if (ng < 0 || marks.size() > marks_per_frame) { bad = GORDER_ERR_INVALID_ARGUMENT; d.n_groups = 0; }
                 else { d.n_groups = ng; memcpy(D.h_marks[buf] + d.bookmarks, marks.data(), marks.size() * sizeof(gxtc::Bookmark)); }
                 n_groups[(size_t)j] = d.n_groups;
                 unsigned char *dst = D.h_bytes[buf] + d.payload;
@@ -786,7 +799,11 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
     CK(cudaEventSynchronize(D.ev_done[0]));
     stage(0, nf, 0);
     for (int buf = 0; j0 < total && !rc; buf ^= 1) {
-        if (bad) { h->set_error(bad, bad == GORDER_ERR_NOT_ORTHOGONAL_BOX ? "simulation box is not orthogonal" : "corrupt or unsupported XTC frame"); rc = h->err_code; break; }
+        if (bad) { h->set_error(bad, bad == GORDER_ERR_NOT_ORTHOGONAL_BOX ? "simulation box is not orthogonal" : "corrupt XTC frame"); rc = h->err_code; break; }
+        if (unsupported) {   // a frame of this batch needs > 64 bits per small triple: the host decoder takes over from here
+            rc = gorder_gpu_run_xtc(h, x, atom_of_slot, first + j0 * stride, last, stride, frame_index0 + j0 * stride, n_threads, batch_frames, nullptr);
+            break;
+        }
         const size_t nbytes = (size_t)nf * frame_cap, mbytes = (size_t)nf * marks_per_frame * sizeof(gxtc::Bookmark);
         CK(cudaMemcpyAsync(D.d_bytes[buf], D.h_bytes[buf], nbytes, cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaMemcpyAsync(D.d_marks[buf], D.h_marks[buf], mbytes, cudaMemcpyHostToDevice, h->copy_stream));

@@ -79,6 +79,27 @@ def test_run_xtc_atom_map_and_solvent(tmp_path):
     np.testing.assert_array_equal(got.count, want.count)
 
 
+def test_device_decode_falls_back_to_the_host_decoder(tmp_path):
+    """2e6 lattice points per nm: bonded displacements need more than 64 bits per small triple, which the device path
+    does not cover -- the host decoder takes over transparently (no bytes of compressed data cross PCIe)."""
+    s = synthetic.s_cg(1100, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True)
+    xyz, box, idx = s.frames(0, 5)
+    path = str(tmp_path / "w.xtc")
+    write_xtc(path, xyz, box, precision=2.0e6)
+    with XtcFile(path) as x:
+        a = SystemTopology(s.setup)
+        a.run_xtc(x, batch_frames=2)
+        want = a.finish()
+        a.close()
+        b = SystemTopology(s.setup)
+        moved = b.run_xtc_device(x, batch_frames=2)
+        got = b.finish()
+        b.close()
+    assert moved == 0
+    np.testing.assert_array_equal(got.sum, want.sum)
+    np.testing.assert_array_equal(got.tw_sum, want.tw_sum)
+
+
 @pytest.mark.parametrize("case", ["cg", "aa_map", "wide_lattice", "cg_prec100"])
 def test_device_decode_equals_host_decode(tmp_path, case):
     """xtc_scan_kernel + xtc_decode_kernel give the engine the same coordinates as the host decoder, bit for bit:
@@ -96,7 +117,9 @@ def test_device_decode_equals_host_decode(tmp_path, case):
         s = synthetic.s_cg(2600, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True, collect_leaflets=True)
         xyz, box, idx = s.frames(0, 9)
         traj = xyz
-        precision = {"cg": 1000.0, "wide_lattice": 2.0e6, "cg_prec100": 100.0}[case]
+        # 1e6 lattice points per nm: the box needs > 2^24 points per axis (per-coordinate bit sizes), the bonded
+        # displacements still fit the 64 bits per triple of the device path (2e6 would not: host fallback, tested below)
+        precision = {"cg": 1000.0, "wide_lattice": 1.0e6, "cg_prec100": 100.0}[case]
     path = str(tmp_path / "t.xtc")
     write_xtc(path, traj, box, precision=precision)
     with XtcFile(path) as x:
