@@ -352,3 +352,21 @@ def test_fast_kernel_reports_undefined_positions(leaflets, bad, monkeypatch):
         eng.finish()
     assert e.value.code == abi.ERR_UNDEFINED_POSITION
     eng.close()
+
+
+@pytest.mark.parametrize("leaflets", [abi.LEAFLET_NONE, abi.LEAFLET_GLOBAL])
+def test_fast_kernel_aa_64_bond_types(leaflets, monkeypatch):
+    """AA lipids (64 C-H bond types: the register-resident warp sums are flushed twice per molecule) through
+    bond_fast_kernel; with Global leaflets the membrane group holds head-group atoms no bond loads, so the centre comes
+    from the pre-pass (inline classification, not speculative)."""
+    from gorder_b200 import SystemTopology
+    monkeypatch.setenv("GORDER_MPT", "2")
+    s = synthetic.s_aa(1100, n_water=200, leaflet_mode=leaflets, timewise=True, collect_leaflets=leaflets != abi.LEAFLET_NONE)
+    xyz, box, idx = _frames(s, 3)
+    g, r = run_both(s.setup, xyz, box, idx, batches=2, oracle_threads=8)
+    assert g.n_slots == 64
+    assert_raw_parity(g, r, s.setup, what=f"aa fast kernel, leaflets {leaflets}")
+    monkeypatch.setenv("GORDER_NO_FAST", "1")
+    g0, _ = run_both(s.setup, xyz, box, idx, oracle_threads=8)
+    np.testing.assert_array_equal(g.sum, g0.sum)
+    np.testing.assert_array_equal(g.count, g0.count)
