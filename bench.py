@@ -333,18 +333,18 @@ def run_ours(args):
                 threads_x = os.cpu_count() or 1
                 eng4 = SystemTopology(s.setup)
                 eng4.reserve_frames(2 * nx + 8)
-                eng4.run_xtc(xf, last=min(nx, args.xtc_batch), n_threads=threads_x, batch_frames=args.xtc_batch)   # warm-up: page cache, pinned buffers
+                eng4.run_xtc(xf, n_threads=threads_x, batch_frames=args.xtc_batch)   # warm-up: page mappings of the file, pinned buffers
                 eng4.sync()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                dec_s = eng4.run_xtc(xf, n_threads=threads_x, batch_frames=args.xtc_batch, frame_index0=args.xtc_batch)
+                dec_s = eng4.run_xtc(xf, n_threads=threads_x, batch_frames=args.xtc_batch, frame_index0=nx)
                 rx = eng4.finish()
                 dt_x = time.perf_counter() - t0
                 eng4.close()
                 # the same file with the decode on the device: host threads only copy compressed bytes
                 eng5 = SystemTopology(s.setup)
-                eng5.reserve_frames(3 * nx + 8)
-                eng5.run_xtc_device(xf, last=min(nx, args.xtc_dev_batch), n_threads=threads_x, batch_frames=args.xtc_dev_batch)   # warm-up: buffers
+                eng5.reserve_frames(4 * nx + 8)
+                eng5.run_xtc_device(xf, n_threads=threads_x, batch_frames=args.xtc_dev_batch)   # warm-up: buffers, page mappings of the file
                 eng5.sync()
                 torch.cuda.synchronize()
                 reps = 3
@@ -428,7 +428,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--xtc-frames", type=int, default=256, help="frames of the XTC end-to-end leg (0 = skip)")
     ap.add_argument("--xtc-batch", type=int, default=16, help="frames per decoded batch of the XTC leg")
-    ap.add_argument("--xtc-dev-batch", type=int, default=16, help="frames per batch of the device-decode XTC leg")
+    ap.add_argument("--xtc-dev-batch", type=int, default=32, help="frames per batch of the device-decode XTC leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.lipids = args.lipids or WORKLOADS[args.workload][1]

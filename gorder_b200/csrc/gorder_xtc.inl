@@ -669,7 +669,7 @@ struct GorderXtcDev {   // device / pinned buffers of the unpacker, owned by the
     gxtc::DevFrame *h_frames[2] = {nullptr, nullptr}, *d_frames[2] = {nullptr, nullptr};
     gxtc::Bookmark *h_marks[2] = {nullptr, nullptr}, *d_marks[2] = {nullptr, nullptr};
     float *h_box[2] = {nullptr, nullptr}, *d_box[2] = {nullptr, nullptr};
-    size_t bytes_cap = 0, marks_per_frame = 0;
+    size_t bytes_cap = 0, marks_per_frame = 0, frame_cap = 0;
     int frames_cap = 0, n_traj_atoms = 0;
     int *d_slot_of_atom = nullptr;
     float *d_xyz = nullptr;
@@ -720,7 +720,10 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
     GorderXtcDev &D = *h->xtc_dev;
     const int na = h->s.n_atoms;
     const int B = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(batch_frames > 0 ? batch_frames : 32, h->max_batch), total));
-    const size_t frame_cap = ((max_bytes + 15) & ~(size_t)15) + 16;   // 16-byte aligned streams, one spare word for the reader's look-ahead
+    // 16-byte aligned streams with room for the reader's look-ahead; 1/8 of slack so that later, slightly larger frames of the
+    // same trajectory do not force the pinned buffers to be re-allocated (frames that outgrow it do)
+    size_t frame_cap = (((max_bytes + max_bytes / 8) + 4095) & ~(size_t)4095) + 16;
+    if (h->xtc_dev && h->xtc_dev->frame_cap >= ((max_bytes + 15) & ~(size_t)15) + 16 && h->xtc_dev->n_traj_atoms == x->natoms) frame_cap = h->xtc_dev->frame_cap;
     const size_t marks_per_frame = (size_t)x->natoms / gxtc::kBookmarkEvery + 2;
     if (!D.magic_uploaded) { CK(cudaMemcpyToSymbol(gxtc::c_magic, gxtc::kMagic, sizeof(gxtc::kMagic))); D.magic_uploaded = true; }
     if (D.frames_cap < B || D.bytes_cap < (size_t)B * frame_cap || D.n_traj_atoms != x->natoms) {
@@ -728,7 +731,7 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
         D.free_all();
         D = GorderXtcDev();
         D.magic_uploaded = true;
-        D.frames_cap = B; D.bytes_cap = (size_t)B * frame_cap; D.n_traj_atoms = x->natoms; D.marks_per_frame = marks_per_frame;
+        D.frames_cap = B; D.bytes_cap = (size_t)B * frame_cap; D.frame_cap = frame_cap; D.n_traj_atoms = x->natoms; D.marks_per_frame = marks_per_frame;
         for (int i = 0; i < 2; i++) {
             CK(cudaMallocHost((void **)&D.h_bytes[i], D.bytes_cap)); CK(cudaMalloc((void **)&D.d_bytes[i], D.bytes_cap));
             CK(cudaMallocHost((void **)&D.h_frames[i], B * sizeof(gxtc::DevFrame))); CK(cudaMalloc((void **)&D.d_frames[i], B * sizeof(gxtc::DevFrame)));
