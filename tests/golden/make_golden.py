@@ -91,7 +91,8 @@ def flatten_yaml(doc: dict, keys=("total",)):
         push(body["average order"])
         for _atom, node in body["order parameters"].items():
             push(node)
-            for b in node.get("bonds", []):
+            bonds = node.get("bonds", [])
+            for b in (bonds.values() if isinstance(bonds, dict) else bonds):   # AA: mapping hydrogen -> values; UA: list
                 push(b)
     return out
 
@@ -182,7 +183,33 @@ def ua_golden():
     print("ua_hydrogens ok")
 
 
+def aa_traj_golden():
+    """AA end to end: tests_aa.rs:1019-1040 (test_aa_order_leaflets_yaml_supershort): pcpepg + pcpepg_selected.xtc
+    (4 frames, precision 100), Global leaflets (@membrane, name P) -> tests/files/aa_order_selected.yaml."""
+    st = fixtures.read_gro(os.path.join(FILES, "pcpepg.gro"))
+    fixtures.read_bnd(os.path.join(FILES, "pcpepg.bnd"), st)
+    traj = fixtures.read_xtc(os.path.join(FILES, "pcpepg_selected.xtc"))
+    assert traj.xyz.shape[1] == st.n_atoms
+    mem = st.select(lambda r, n: r in LIPIDS)
+    cst, keep = fixtures.compact(st, mem)
+    prec = 100.0
+    q = np.round(traj.xyz[:, keep, :].astype(np.float64) * prec).astype(np.int32)
+    assert np.array_equal(q.astype(np.float32) * np.float32(1.0 / prec), traj.xyz[:, keep, :]), "XTC coordinates are not k/100"
+    allm = np.arange(cst.n_atoms)
+    g1 = cst.select(lambda r, n: n.startswith("C"))
+    g2 = cst.select(lambda r, n: n.startswith("H"))
+    heads = cst.select(lambda r, n: n == "P")
+    setup = fixtures.build_bond_setup(cst, abi.KIND_AA, g1, g2, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL)
+    doc = yaml.safe_load(open(os.path.join(FILES, "aa_order_selected.yaml")))
+    keys = ("total", "upper", "lower")
+    np.savez_compressed(os.path.join(HERE, "aa_traj.npz"), q=q, precision=np.float32(prec), box=traj.box.astype(np.float32),
+                        setup=json.dumps(setup.to_dict()), expected=json.dumps(flatten_yaml(doc, keys)), keys=json.dumps(list(keys)),
+                        molecules=json.dumps([k for k in doc if k != "average order"]))
+    print("aa_traj", q.shape, setup.n_slots, "bond types,", [m.name for m in setup.moltypes])
+
+
 if __name__ == "__main__":
     single_frame("cg_single_frame", "cg.gro", "cg.bnd", "cg.tpr", abi.KIND_CG, "cgorder.rs", 1.0, "PO4")
     single_frame("aa_single_frame", "pcpepg.gro", "pcpepg.bnd", "pcpepg.tpr", abi.KIND_AA, "aaorder.rs", -1.0, "P")
     ua_golden()
+    aa_traj_golden()

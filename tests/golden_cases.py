@@ -20,6 +20,16 @@ def single_frame(name: str):
     return setup, z["xyz"][None].astype(np.float32), z["box"][None].astype(np.float32), exp
 
 
+def aa_traj():
+    """AA end-to-end fixture (tests_aa.rs:1019-1040 -> tests/files/aa_order_selected.yaml): setup, frames, expected."""
+    z = np.load(os.path.join(GOLDEN, "aa_traj.npz"))
+    setup = abi.EngineSetup.from_dict(json.loads(str(z["setup"])))
+    xyz = z["q"].astype(np.float32) * np.float32(1.0 / float(z["precision"]))   # exactly the XTC decoder's arithmetic
+    case = dict(expected=json.loads(str(z["expected"])), keys=json.loads(str(z["keys"])), source="aa_order_selected.yaml",
+                molecules=json.loads(str(z["molecules"])))
+    return setup, xyz, z["box"].astype(np.float32), case
+
+
 _UA = None
 
 

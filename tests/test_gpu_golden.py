@@ -52,3 +52,11 @@ def test_ua_ordermaps_fixture():
     g, r = run_both(setup, xyz, box, fi)
     assert_raw_parity(g, r, setup, what="maps")
     check_maps(g, setup, case)
+
+
+def test_aa_trajectory_fixture():
+    """AA end to end on the GPU: the reference's aa_order_selected.yaml (tests_aa.rs:1019-1040), and the oracle."""
+    setup, xyz, box, case = gc.aa_traj()
+    g, r = run_both(setup, xyz, box, batches=2, oracle_threads=8)
+    assert_raw_parity(g, r, setup, what="aa trajectory")
+    gc.assert_matches_yaml(g, setup, case)

@@ -221,3 +221,15 @@ def check_maps(raw, setup, case):
         ys = np.tile(np.arange(ny) * setup.map_bin[1], nx)
         np.testing.assert_allclose(rows[:, 0], xs, atol=1e-3)
         np.testing.assert_allclose(rows[:, 1], ys, atol=1e-3)
+
+
+def test_aa_trajectory_fixture():
+    """AA end to end (tests_aa.rs:1019-1040): pcpepg_selected.xtc, 4 frames, 229 C-H bond types in POPE / POPC / POPG,
+    Global leaflets -> aa_order_selected.yaml (total / upper / lower of every atom and bond, reference tolerance)."""
+    setup, xyz, box, case = gc.aa_traj()
+    assert [m.name for m in setup.moltypes] == case["molecules"]
+    o = oracle.Oracle(setup, n_threads=8)
+    o.analyze_frames(xyz, box, np.arange(xyz.shape[0], dtype=np.int64))
+    raw = o.finish()
+    o.close()
+    gc.assert_matches_yaml(raw, setup, case)
