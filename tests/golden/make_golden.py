@@ -208,8 +208,90 @@ def aa_traj_golden():
     print("aa_traj", q.shape, setup.n_slots, "bond types,", [m.name for m in setup.moltypes])
 
 
+def concatenated(base: str, n: int = 5):
+    """The reference ships its AA / CG test trajectories only in pieces (tests/files/split/<base>1..5.xtc: the inputs of
+    the concatenation tests, tests_aa.rs:48-78, tests_cg.rs:45-76); joined with the duplicated boundary frames dropped
+    (what traj_iter_cat_map_reduce does) they are the full pcpepg.xtc / cg.xtc every other fixture was made from."""
+    xs, bs, ts = [], [], []
+    last = None
+    for i in range(1, n + 1):
+        t = fixtures.read_xtc(os.path.join(FILES, "split", f"{base}{i}.xtc"))
+        lo = 1 if last is not None and t.time[0] == last else 0
+        last = t.time[-1]
+        xs.append(t.xyz[lo:]); bs.append(t.box[lo:]); ts.append(np.asarray(t.time, np.float64)[lo:])
+    return np.concatenate(xs), np.concatenate(bs), np.concatenate(ts)
+
+
+def pack_lattice(q: np.ndarray) -> dict:
+    """int16 frame-to-frame differences of the lattice coordinates (they compress 3x better than the coordinates)."""
+    d = np.diff(q.astype(np.int32), axis=0, prepend=np.zeros((1,) + q.shape[1:], np.int32))
+    assert np.abs(d).max() < 32768
+    return dict(dq=d.astype(np.int16))
+
+
+def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: str, methyl_names, n_expected: int):
+    st = fixtures.read_gro(os.path.join(FILES, gro))
+    fixtures.read_bnd(os.path.join(FILES, bnd), st)
+    xyz, box, time = concatenated(base)
+    assert xyz.shape[0] == n_expected and xyz.shape[1] == st.n_atoms, xyz.shape
+    mem = st.select(lambda r, n: r in LIPIDS)
+    cst, keep = fixtures.compact(st, mem)
+    prec = 100.0
+    q = np.round(xyz[:, keep, :].astype(np.float64) * prec).astype(np.int32)
+    assert np.array_equal(q.astype(np.float32) * np.float32(1.0 / prec), xyz[:, keep, :]), "XTC coordinates are not k/100"
+    allm = np.arange(cst.n_atoms)
+    if kind == abi.KIND_CG:
+        g1 = g2 = allm
+    else:
+        g1 = cst.select(lambda r, n: n.startswith("C"))
+        g2 = cst.select(lambda r, n: n.startswith("H"))
+    heads = cst.select(lambda r, n: n == head)
+    methyls = cst.select(lambda r, n: n in methyl_names)
+    cases = {}
+
+    def add(case, yaml_file, keys=("total",), frames=None, **kw):
+        extra = {k: kw.pop(k) for k in ("n_blocks", "min_samples") if k in kw}
+        setup = fixtures.build_bond_setup(cst, kind, g1, g2, **kw)
+        doc = yaml.safe_load(open(os.path.join(FILES, yaml_file)))
+        cases[case] = dict(setup=setup.to_dict(), expected=flatten_yaml(doc, keys), keys=list(keys),
+                           frames=frames if frames is not None else list(range(xyz.shape[0])), source=yaml_file, **extra)
+
+    tul = ("total", "upper", "lower")
+    glob = dict(heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL)
+    pre = "aa" if kind == abi.KIND_AA else "cg"
+    add("basic", f"{pre}_order_basic.yaml")
+    add("leaflets_global", f"{pre}_order_leaflets.yaml", tul, **glob)
+    add("leaflets_individual", f"{pre}_order_leaflets.yaml", tul, heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL)
+    add("leaflets_local", f"{pre}_order_leaflets.yaml", tul, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_LOCAL, leaflet_radius=2.5)
+    add("leaflets_every5", f"{pre}_order_leaflets.yaml", tul, leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=5, **glob)
+    add("leaflets_once", f"{pre}_order_leaflets.yaml", tul, leaflet_freq_kind=abi.FREQ_ONCE, **glob)
+    add("error", f"{pre}_order_error.yaml", n_blocks=5, timewise=True)
+    add("error_leaflets", f"{pre}_order_error_leaflets.yaml", tul, n_blocks=5, timewise=True, **glob)
+    if kind == abi.KIND_AA:
+        # begin 450 200 ps, end 450 400 ps (, step 3): tests_aa.rs:1202-1232, 1398-1423
+        sel = [i for i, t in enumerate(time) if 450200.0 <= t <= 450400.0]
+        add("begin_end", "aa_order_begin_end.yaml", tul, frames=sel, **glob)
+        add("begin_end_step", "aa_order_begin_end_step.yaml", tul, frames=sel[::3], step=3, **glob)
+        add("limit", "aa_order_limit.yaml", min_samples=2000)                                   # tests_aa.rs:1099-1120
+        add("leaflets_limit", "aa_order_leaflets_limit.yaml", tul, min_samples=500, **glob)     # tests_aa.rs:1123-1149
+        add("sphere_center", "aa_order_sphere_center.yaml", geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
+            geom_dims=(2.5,))                                                                   # tests_aa.rs:3239-3260
+    else:
+        # begin 352 000 ps, end 358 000 ps, step 5: tests_cg.rs:746-772
+        sel = [i for i, t in enumerate(time) if 352000.0 <= t <= 358000.0][::5]
+        add("begin_end_step", "cg_order_begin_end_step.yaml", tul, frames=sel, step=5, **glob)
+        # Individual leaflets assigned once + dynamic normals (PO4, 2 nm): tests_cg.rs:3356-3388
+        add("leaflets_dynamic", "cg_order_leaflets_dynamic.yaml", tul, heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL,
+            leaflet_freq_kind=abi.FREQ_ONCE, normal_heads=heads, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), precision=np.float32(prec), box=box.astype(np.float32), time=time.astype(np.float64),
+                        cases=json.dumps(cases), **pack_lattice(q))
+    print(name, q.shape, "cases:", list(cases))
+
+
 if __name__ == "__main__":
     single_frame("cg_single_frame", "cg.gro", "cg.bnd", "cg.tpr", abi.KIND_CG, "cgorder.rs", 1.0, "PO4")
     single_frame("aa_single_frame", "pcpepg.gro", "pcpepg.bnd", "pcpepg.tpr", abi.KIND_AA, "aaorder.rs", -1.0, "P")
     ua_golden()
     aa_traj_golden()
+    full_traj_golden("aa_full", "pcpepg", "pcpepg.gro", "pcpepg.bnd", abi.KIND_AA, "P", ("C218", "C316"), 51)
+    full_traj_golden("cg_full", "cg", "cg.gro", "cg.bnd", abi.KIND_CG, "PO4", ("C4A", "C4B"), 101)

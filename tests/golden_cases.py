@@ -30,6 +30,29 @@ def aa_traj():
     return setup, xyz, z["box"].astype(np.float32), case
 
 
+_FULL = {}
+
+
+def full_case(which: str, name: str):
+    """A case of the full AA (pcpepg, 51 frames) or CG (cg, 101 frames) test trajectory of the reference, re-joined from
+    tests/files/split/* (make_golden.concatenated): setup, frames, boxes, frame indices, case dict."""
+    if which not in _FULL:
+        z = np.load(os.path.join(GOLDEN, f"{which}_full.npz"))
+        q = np.cumsum(z["dq"].astype(np.int32), axis=0)
+        xyz = q.astype(np.float32) * np.float32(1.0 / float(z["precision"]))   # exactly the XTC decoder's arithmetic
+        _FULL[which] = (xyz, z["box"].astype(np.float32), json.loads(str(z["cases"])))
+    xyz, box, cases = _FULL[which]
+    c = cases[name]
+    setup = abi.EngineSetup.from_dict(c["setup"])
+    fr = np.array(c["frames"], dtype=np.int64)
+    return setup, xyz[fr], box[fr], fr - fr[0], c
+
+
+def full_case_names(which: str):
+    z = np.load(os.path.join(GOLDEN, f"{which}_full.npz"))
+    return list(json.loads(str(z["cases"])))
+
+
 _UA = None
 
 
@@ -77,7 +100,7 @@ def flatten_results(res: results.AnalysisResults, keys=("total",), with_error=Fa
 
 def assert_matches_yaml(raw: abi.RawResults, setup: abi.EngineSetup, case: dict, tol: float = FIXTURE_TOL):
     nb = case.get("n_blocks")
-    res = results.convert(raw, setup, n_blocks=nb)
+    res = results.convert(raw, setup, n_blocks=nb, min_samples=case.get("min_samples", 1))
     got = flatten_results(res, tuple(case["keys"]), with_error=nb is not None)
     exp = np.array(case["expected"], dtype=np.float64)
     assert got.shape == exp.shape, (got.shape, exp.shape)

@@ -60,3 +60,24 @@ def test_aa_trajectory_fixture():
     g, r = run_both(setup, xyz, box, batches=2, oracle_threads=8)
     assert_raw_parity(g, r, setup, what="aa trajectory")
     gc.assert_matches_yaml(g, setup, case)
+
+
+from test_oracle_pins import AA_FULL_CASES, CG_FULL_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", AA_FULL_CASES)
+def test_aa_full_trajectory_fixtures(name):
+    """The reference's full AA test trajectory on the GPU: its aa_order_*.yaml fixtures, and the oracle."""
+    setup, xyz, box, fi, case = gc.full_case("aa", name)
+    g, r = run_both(setup, xyz, box, fi, batches=2, oracle_threads=8)
+    assert_raw_parity(g, r, setup, what=f"aa full {name}")
+    gc.assert_matches_yaml(g, setup, case)
+
+
+@pytest.mark.parametrize("name", CG_FULL_CASES)
+def test_cg_full_trajectory_fixtures(name):
+    """The reference's full CG test trajectory on the GPU: its cg_order_*.yaml fixtures, and the oracle."""
+    setup, xyz, box, fi, case = gc.full_case("cg", name)
+    g, r = run_both(setup, xyz, box, fi, batches=3, oracle_threads=8)
+    assert_raw_parity(g, r, setup, what=f"cg full {name}")
+    gc.assert_matches_yaml(g, setup, case)

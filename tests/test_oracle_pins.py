@@ -233,3 +233,34 @@ def test_aa_trajectory_fixture():
     raw = o.finish()
     o.close()
     gc.assert_matches_yaml(raw, setup, case)
+
+
+# ---- the reference's full AA / CG test trajectories (re-joined from tests/files/split/*) against its YAML fixtures ----
+AA_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
+                 "error_leaflets", "begin_end", "begin_end_step", "limit", "leaflets_limit", "sphere_center"]
+CG_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
+                 "error_leaflets", "begin_end_step", "leaflets_dynamic"]
+
+
+def _oracle_full(which, name):
+    setup, xyz, box, fi, case = gc.full_case(which, name)
+    o = oracle.Oracle(setup, n_threads=8)
+    o.analyze_frames(xyz, box, fi)
+    raw = o.finish()
+    o.close()
+    gc.assert_matches_yaml(raw, setup, case)
+
+
+@pytest.mark.parametrize("name", AA_FULL_CASES)
+def test_aa_full_trajectory_fixtures(name):
+    """pcpepg.xtc (51 frames, 35 432 lipid atoms, 229 C-H bond types): tests_aa.rs:25-45, 289-316, 548-582, 1099-1149,
+    1202-1232, 1398-1423, 2170-2247, 3239-3260 -> tests/files/aa_order_*.yaml."""
+    assert set(AA_FULL_CASES) == set(gc.full_case_names("aa"))
+    _oracle_full("aa", name)
+
+
+@pytest.mark.parametrize("name", CG_FULL_CASES)
+def test_cg_full_trajectory_fixtures(name):
+    """cg.xtc (101 frames, 6 096 beads): tests_cg.rs:26-43, 180-213, 746-772, 1367-1435, 3356-3388 -> tests/files/cg_order_*.yaml."""
+    assert set(CG_FULL_CASES) == set(gc.full_case_names("cg"))
+    _oracle_full("cg", name)
