@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums -----------------------------------------------------------------------------------
 KIND_AA, KIND_CG, KIND_UA = 0, 1, 2
@@ -132,6 +132,7 @@ class CGorderSetup(C.Structure):
         ("geom_ref", _i32p),
         ("geom_dims", C.c_float * 6),
         ("geom_axis", C.c_int32),
+        ("structure_box", C.c_float * 3),
         ("map_enabled", C.c_int32),
         ("map_plane", C.c_int32),
         ("map_span_x", C.c_float * 2),
@@ -231,6 +232,7 @@ class EngineSetup:
     geom_ref: Sequence[int] = ()
     geom_dims: Sequence[float] = (0.0,) * 6
     geom_axis: int = AXIS_Z
+    structure_box: Sequence[float] = (0.0, 0.0, 0.0)
     map_enabled: bool = False
     map_plane: int = PLANE_XY
     map_span_x: Sequence[float] = (0.0, 0.0)
@@ -367,6 +369,7 @@ class EngineSetup:
         dims = list(self.geom_dims) + [0.0] * (6 - len(self.geom_dims))
         s.geom_dims = (C.c_float * 6)(*[float(x) for x in dims])
         s.geom_axis = self.geom_axis
+        s.structure_box = (C.c_float * 3)(*[float(x) for x in self.structure_box])
         s.map_enabled = int(bool(self.map_enabled))
         s.map_plane = self.map_plane
         s.map_span_x = (C.c_float * 2)(*[float(x) for x in self.map_span_x])

@@ -869,7 +869,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     v.leaflet_mode = s->leaflet_mode; v.leaflet_axis = s->leaflet_axis; v.leaflet_flip = s->leaflet_flip;
     v.leaflet_freq_kind = s->leaflet_freq_kind; v.leaflet_freq = s->leaflet_freq; v.leaflet_radius = s->leaflet_radius;
     v.shape.kind = s->geom_kind; v.shape.invert = s->geom_invert; v.shape.axis = s->geom_axis; v.shape.ref_kind = s->geom_ref_kind;
-    for (int k = 0; k < 3; k++) v.shape.ref_point[k] = s->geom_ref_point[k];
+    for (int k = 0; k < 3; k++) { v.shape.ref_point[k] = s->geom_ref_point[k]; v.shape.structure_box[k] = s->structure_box[k]; }
     for (int k = 0; k < 6; k++) v.shape.dims[k] = s->geom_dims[k];
     v.manual_leaflets = d_mleaf; v.manual_normals = d_mnorm;
     v.err = h->d_err; v.err_detail = h->d_err_detail;

@@ -89,6 +89,7 @@ struct ShapeParams {
     int kind, invert, axis, ref_kind;
     float ref_point[3];
     float dims[6];
+    float structure_box[3];   // POINT reference: the shape's origin is wrapped with the structure file's box (0: the frame's)
 };
 
 // Everything the kernels need, passed by value.

@@ -124,8 +124,10 @@ __device__ __forceinline__ long long map_bin(const MapParams &mp, const f3 &pos)
     if (mp.plane == GORDER_PLANE_XY) { x = pos.x; y = pos.y; }
     else if (mp.plane == GORDER_PLANE_XZ) { x = pos.x; y = pos.z; }
     else { x = pos.z; y = pos.y; }   // sic: YZ projects to (z, y), input/ordermap.rs:48
-    float fx = floorf(__fadd_rn(__fdiv_rn(__fsub_rn(x, mp.x0), mp.binx), 0.5f));
-    float fy = floorf(__fadd_rn(__fdiv_rn(__fsub_rn(y, mp.y0), mp.biny), 0.5f));
+    // groan GridMap: nearest node = round((x - min) / bin), half away from zero (pinned by the reference's AA map fixtures,
+    // where bond midpoints sit exactly on bin edges; floor(v + 0.5) does not reproduce them)
+    float fx = roundf(__fdiv_rn(__fsub_rn(x, mp.x0), mp.binx));
+    float fy = roundf(__fdiv_rn(__fsub_rn(y, mp.y0), mp.biny));
     if (!(fx >= 0.0f) || !(fy >= 0.0f) || fx >= (float)mp.nx || fy >= (float)mp.ny) return -1;
     return (long long)fx * mp.ny + (long long)fy;
 }
@@ -178,6 +180,11 @@ __device__ void construct_shape(const DeviceView &v, FrameAux &a) {
         else { p[sp.axis] = __fadd_rn(p[sp.axis], lo); a.shape_height = __fsub_rn(hi, lo); }
     } else {   // sphere, geometry.rs:507-514
         a.shape_radius = sp.dims[0];
+    }
+    // a fixed reference point: the reference built the shape once, with the structure file's box (geometry.rs:297-312)
+    if (sp.ref_kind == GORDER_GEOMREF_POINT && (sp.structure_box[0] != 0.0f || sp.structure_box[1] != 0.0f || sp.structure_box[2] != 0.0f)) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { bx.L[k] = sp.structure_box[k]; bx.half[k] = sp.structure_box[k] / 2.0f; }
     }
     f3 o = wrap_point<PBC>(mk3(p[0], p[1], p[2]), bx);
     a.shape_origin[0] = o.x; a.shape_origin[1] = o.y; a.shape_origin[2] = o.z;

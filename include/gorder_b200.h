@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GORDER_ABI_VERSION 1
+#define GORDER_ABI_VERSION 2
 
 /* ---- enums (int32 in the structs) ------------------------------------------------------- */
 
@@ -184,6 +184,11 @@ typedef struct GorderSetup {
     float geom_dims[6];        /* CUBOID: xmin,xmax,ymin,ymax,zmin,zmax (+-INFINITY allowed);
                                   CYLINDER: radius, span_min, span_max;  SPHERE: radius */
     int32_t geom_axis;         /* CYLINDER orientation */
+    float structure_box[3];    /* POINT reference: box of the STRUCTURE file.  The reference builds the shape of a fixed
+                                  reference point ONCE, in GeometrySelection::new (geometry.rs:297-312), with the box of the
+                                  structure file -- init_reference (geometry.rs:192-210) never rebuilds it -- so the wrap of
+                                  the shape's origin uses that box while `inside` uses the frame's.  All zero: the frame's box
+                                  is used (identical whenever reference + lower offsets lies inside the box). */
 
     /* order maps (ordermap.rs:40-96). Spans are resolved by the host exactly as Map::new does
      * (auto span = box of the structure file). */

@@ -289,7 +289,12 @@ static Shape construct_shape(const GorderSetup *s, vec3 ref, const float *box) {
     } else if (s->geom_kind == GORDER_GEOM_SPHERE) { /* geometry.rs:507-514 */
         sh.radius = s->geom_dims[0];
     }
-    sh.origin = wrap_point(v3(p[0], p[1], p[2]), box, pbc);
+    {   /* a fixed reference point: the shape was built once, with the structure file's box (geometry.rs:297-312) */
+        const float *wb = box;
+        if (s->geom_ref_kind == GORDER_GEOMREF_POINT && (s->structure_box[0] != 0.0f || s->structure_box[1] != 0.0f || s->structure_box[2] != 0.0f))
+            wb = s->structure_box;
+        sh.origin = wrap_point(v3(p[0], p[1], p[2]), wb, pbc);
+    }
     return sh;
 }
 
@@ -710,8 +715,11 @@ static inline int64_t map_bin(const GorderOracle *o, vec3 pos) {
     case GORDER_PLANE_XZ: x = pos.x; y = pos.z; break;
     default: x = pos.z; y = pos.y; break;
     }
-    float fx = floorf((x - s->map_span_x[0]) / s->map_bin[0] + 0.5f);
-    float fy = floorf((y - s->map_span_y[0]) / s->map_bin[1] + 0.5f);
+    /* groan GridMap::get_mut_at: nearest node = round((x - min) / bin), half away from zero.  Pinned by the AA map fixtures
+     * (tests/files/ordermaps/, bin 0.1 nm on a 0.01 nm lattice: bond midpoints sit exactly on bin edges); floor(v + 0.5) and
+     * round-half-even do not reproduce them. */
+    float fx = roundf((x - s->map_span_x[0]) / s->map_bin[0]);
+    float fy = roundf((y - s->map_span_y[0]) / s->map_bin[1]);
     if (!(fx >= 0.0f) || !(fy >= 0.0f) || fx >= (float)o->map_nx || fy >= (float)o->map_ny) return -1;
     return (int64_t)fx * o->map_ny + (int64_t)fy; /* x-major (x slow, y fast) */
 }

@@ -139,7 +139,7 @@ def ua_golden():
                                   geom_dims=(2.5, float("-inf"), float("inf")), geom_axis=abi.AXIS_Z)
     add("cylinder_center", cyl, "ua_order_cylinder_center.yaml")
     cub = fixtures.build_ua_setup(cst, sat, unsat, geom_kind=abi.GEOM_CUBOID, geom_ref_kind=abi.GEOMREF_POINT, geom_ref_point=(1.5, 2.5, 0.0),
-                                  geom_dims=(-1.0, 2.0, 0.0, 1.0, float("-inf"), float("inf")))
+                                  geom_dims=(-1.0, 2.0, 0.0, 1.0, float("-inf"), float("inf")), structure_box=tuple(float(x) for x in sbox))
     add("cuboid_point", cub, "ua_order_cuboid_point.yaml")
     dyn = fixtures.build_ua_setup(cst, sat, unsat, normal_heads=heads, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0, collect_normals=True)
     ndoc = yaml.safe_load(open(os.path.join(FILES, "ua_normals.yaml")))
@@ -276,6 +276,27 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         add("leaflets_limit", "aa_order_leaflets_limit.yaml", tul, min_samples=500, **glob)     # tests_aa.rs:1123-1149
         add("sphere_center", "aa_order_sphere_center.yaml", geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
             geom_dims=(2.5,))                                                                   # tests_aa.rs:3239-3260
+        # order maps of three POPC carbons (+ static geometry): tests_aa.rs:1560-1624, 3023-3087, 3090-3153
+        _, sbox, _ = fixtures.tpr_coordinates(os.path.join(FILES, "pcpepg.tpr"), st.xyz)
+        g1 = cst.select(lambda r, n: r == "POPC" and n in ("C22", "C24", "C218"))
+
+        def add_maps(case, yaml_file, mdir, bin_, min_samples, **kw):
+            add(case, yaml_file, map_enabled=True, map_plane=abi.PLANE_XY, map_bin=bin_, map_span_x=(0.0, float(sbox[0])),
+                map_span_y=(0.0, float(sbox[1])), **kw)
+            mexp = {}
+            for fn in sorted(os.listdir(os.path.join(FILES, mdir))):
+                if fn.endswith("_full.dat") and "average" not in fn:
+                    rows = [ln.split() for ln in open(os.path.join(FILES, mdir, fn)) if ln[0] not in "#@$"]
+                    mexp[fn] = [[float(a), float(b), float(c)] for a, b, c in rows]
+            cases[case].update(maps=mexp, map_min_samples=min_samples)
+
+        add_maps("maps_basic", "aa_order_small.yaml", "ordermaps", (0.1, 4.0), 5)
+        add_maps("maps_cuboid_square", "aa_order_cuboid_square.yaml", "ordermaps_cuboid", (0.5, 0.5), 5, geom_kind=abi.GEOM_CUBOID,
+                 geom_ref_kind=abi.GEOMREF_POINT, geom_ref_point=(8.0, 2.0, 0.0), geom_dims=(-2.0, 4.0, -4.0, 1.0, float("-inf"), float("inf")),
+                 structure_box=tuple(float(x) for x in sbox))
+        add_maps("maps_cylinder", "aa_order_cylinder.yaml", "ordermaps_cylinder", (0.5, 0.5), 1, geom_kind=abi.GEOM_CYLINDER,
+                 geom_ref_kind=abi.GEOMREF_POINT, geom_ref_point=(8.0, 2.0, 0.0), geom_dims=(2.5, float("-inf"), float("inf")), geom_axis=abi.AXIS_Z,
+                 structure_box=tuple(float(x) for x in sbox))
     else:
         # begin 352 000 ps, end 358 000 ps, step 5: tests_cg.rs:746-772
         sel = [i for i, t in enumerate(time) if 352000.0 <= t <= 358000.0][::5]

@@ -62,7 +62,7 @@ def test_aa_trajectory_fixture():
     gc.assert_matches_yaml(g, setup, case)
 
 
-from test_oracle_pins import AA_FULL_CASES, CG_FULL_CASES  # noqa: E402
+from test_oracle_pins import AA_FULL_CASES, CG_FULL_CASES, check_maps_aa  # noqa: E402
 
 
 @pytest.mark.parametrize("name", AA_FULL_CASES)
@@ -72,6 +72,8 @@ def test_aa_full_trajectory_fixtures(name):
     g, r = run_both(setup, xyz, box, fi, batches=2, oracle_threads=8)
     assert_raw_parity(g, r, setup, what=f"aa full {name}")
     gc.assert_matches_yaml(g, setup, case)
+    if "maps" in case:
+        check_maps_aa(g, setup, case)
 
 
 @pytest.mark.parametrize("name", CG_FULL_CASES)

@@ -237,9 +237,46 @@ def test_aa_trajectory_fixture():
 
 # ---- the reference's full AA / CG test trajectories (re-joined from tests/files/split/*) against its YAML fixtures ----
 AA_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
-                 "error_leaflets", "begin_end", "begin_end_step", "limit", "leaflets_limit", "sphere_center"]
+                 "error_leaflets", "begin_end", "begin_end_step", "limit", "leaflets_limit", "sphere_center", "maps_basic",
+                 "maps_cuboid_square", "maps_cylinder"]
 CG_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
                  "error_leaflets", "begin_end_step", "leaflets_dynamic"]
+
+
+def check_maps_aa(raw, setup, case):
+    """ordermaps*/ordermap_<res>-<C>-<i>--<res>-<H>-<j>_full.dat (one per C-H bond type) and ordermap_<res>-<C>-<i>_full.dat
+    (the heavy atom: its bonds merged sample by sample): x y value rows, x-major; NaN below min_samples."""
+    nx, ny = raw.map_shape
+    mt = setup.moltypes[0]
+    per_atom = {}
+    seen = set()
+    for b, name in enumerate(mt.bond_names):    # "POPC C22 (32) - POPC H2R (33)"
+        a, h = name.split(" - ")
+        fa, fh = ("-".join(x.replace("(", "").replace(")", "").split()) for x in (a, h))
+        lab = f"ordermap_{fa}--{fh}_full.dat"
+        rows = np.array(case["maps"][lab], np.float64)
+        assert rows.shape[0] == nx * ny, (rows.shape, nx, ny)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            val = -(raw.map_sum[b, 0].astype(np.float64) / 1e6) / raw.map_count[b, 0].astype(np.float64)
+        val = np.where(raw.map_count[b, 0] < case["map_min_samples"], np.nan, val).reshape(-1)
+        np.testing.assert_allclose(val, rows[:, 2], atol=gc.FIXTURE_TOL, rtol=0, equal_nan=True, err_msg=lab)
+        xs = np.repeat(np.arange(nx) * setup.map_bin[0], ny)
+        ys = np.tile(np.arange(ny) * setup.map_bin[1], nx)
+        np.testing.assert_allclose(rows[:, 0], xs, atol=1e-3)
+        np.testing.assert_allclose(rows[:, 1], ys, atol=1e-3)
+        acc = per_atom.setdefault(fa, [np.zeros((nx, ny), np.int64), np.zeros((nx, ny), np.int64)])
+        acc[0] += raw.map_sum[b, 0]
+        acc[1] += raw.map_count[b, 0].astype(np.int64)
+        seen.add(lab)
+    for fa, (sm, cn) in per_atom.items():
+        lab = f"ordermap_{fa}_full.dat"
+        rows = np.array(case["maps"][lab], np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            val = -(sm.astype(np.float64) / 1e6) / cn.astype(np.float64)
+        val = np.where(cn < case["map_min_samples"], np.nan, val).reshape(-1)
+        np.testing.assert_allclose(val, rows[:, 2], atol=gc.FIXTURE_TOL, rtol=0, equal_nan=True, err_msg=lab)
+        seen.add(lab)
+    assert seen == set(case["maps"].keys()), seen ^ set(case["maps"].keys())
 
 
 def _oracle_full(which, name):
@@ -249,6 +286,8 @@ def _oracle_full(which, name):
     raw = o.finish()
     o.close()
     gc.assert_matches_yaml(raw, setup, case)
+    if "maps" in case:
+        check_maps_aa(raw, setup, case)
 
 
 @pytest.mark.parametrize("name", AA_FULL_CASES)
