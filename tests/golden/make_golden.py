@@ -250,7 +250,7 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
     cases = {}
 
     def add(case, yaml_file, keys=("total",), frames=None, **kw):
-        extra = {k: kw.pop(k) for k in ("n_blocks", "min_samples") if k in kw}
+        extra = {k: kw.pop(k) for k in ("n_blocks", "min_samples", "tol") if k in kw}
         setup = fixtures.build_bond_setup(cst, kind, g1, g2, **kw)
         doc = yaml.safe_load(open(os.path.join(FILES, yaml_file)))
         cases[case] = dict(setup=setup.to_dict(), expected=flatten_yaml(doc, keys), keys=list(keys),
@@ -276,6 +276,29 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         add("leaflets_limit", "aa_order_leaflets_limit.yaml", tul, min_samples=500, **glob)     # tests_aa.rs:1123-1149
         add("sphere_center", "aa_order_sphere_center.yaml", geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
             geom_dims=(2.5,))                                                                   # tests_aa.rs:3239-3260
+        # geometry selections: reference = centre of residue 1 (PBC centre of geometry of a group: the refined Bai-Breen
+        # estimate, otherwise pinned only through leaflets), box centre, fixed point; inverted: tests_aa.rs:3183-3345, 3508-3615
+        inf = (float("-inf"), float("inf"))
+        res1 = np.array([i for i in range(cst.n_atoms) if cst.resid[i] == 1], np.int64)
+        assert 50 < len(res1) < 200
+        dyn = dict(geom_ref_kind=abi.GEOMREF_SELECTION, geom_ref=res1)
+        add("cuboid_dynamic", "aa_order_cuboid_dynamic.yaml", geom_kind=abi.GEOM_CUBOID, geom_dims=(-1.0, 3.0, 1.0, 4.0, -3.0, 3.0), **dyn)
+        add("cylinder_dynamic", "aa_order_cylinder_dynamic.yaml", geom_kind=abi.GEOM_CYLINDER, geom_dims=(2.1,) + inf, geom_axis=abi.AXIS_Y, **dyn)
+        # tol: ONE of the 159 921 samples lies within an ulp of the sphere's surface and falls on the other side with the oracle's
+        # summation order of the group centre (a 900-sample bond moves by 3.4e-4; the reference's own comparator allows 2e-4)
+        add("sphere_dynamic", "aa_order_sphere_dynamic.yaml", geom_kind=abi.GEOM_SPHERE, geom_dims=(2.5,), tol=5e-4, **dyn)
+        add("sphere_dynamic_inverted", "aa_order_sphere_dynamic_inverted.yaml", geom_kind=abi.GEOM_SPHERE, geom_dims=(2.5,), geom_invert=True, **dyn)
+        cen = dict(geom_ref_kind=abi.GEOMREF_BOX_CENTER)
+        add("cuboid_patch", "aa_order_cuboid_patch.yaml", geom_kind=abi.GEOM_CUBOID, geom_dims=(-1.0, 3.0) + inf + inf, **cen)
+        add("cylinder_x", "aa_order_cylinder_x.yaml", geom_kind=abi.GEOM_CYLINDER, geom_dims=(3.0, -1.0, 3.0), geom_axis=abi.AXIS_X, **cen)
+        add("cylinder_z_inverted", "aa_order_cylinder_z_inverted.yaml", geom_kind=abi.GEOM_CYLINDER, geom_dims=(3.0,) + inf, geom_axis=abi.AXIS_Z,
+            geom_invert=True, **cen)
+        _, sbox0, _ = fixtures.tpr_coordinates(os.path.join(FILES, "pcpepg.tpr"), st.xyz)
+        add("cuboid_square_inverted", "aa_order_cuboid_square_inverted.yaml", geom_kind=abi.GEOM_CUBOID, geom_ref_kind=abi.GEOMREF_POINT,
+            geom_ref_point=(8.0, 2.0, 0.0), geom_dims=(-2.0, 4.0, -4.0, 1.0) + inf, geom_invert=True, structure_box=tuple(float(x) for x in sbox0))
+        # dynamic PCA normals (P atoms, 2 nm) + Individual leaflets assigned once: tests_aa.rs:4774-4806
+        add("leaflets_dynamic", "aa_order_leaflets_dynamic.yaml", tul, heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL,
+            leaflet_freq_kind=abi.FREQ_ONCE, normal_heads=heads, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0)
         # order maps of three POPC carbons (+ static geometry): tests_aa.rs:1560-1624, 3023-3087, 3090-3153
         _, sbox, _ = fixtures.tpr_coordinates(os.path.join(FILES, "pcpepg.tpr"), st.xyz)
         g1 = cst.select(lambda r, n: r == "POPC" and n in ("C22", "C24", "C218"))
@@ -301,6 +324,20 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         # begin 352 000 ps, end 358 000 ps, step 5: tests_cg.rs:746-772
         sel = [i for i, t in enumerate(time) if 352000.0 <= t <= 358000.0][::5]
         add("begin_end_step", "cg_order_begin_end_step.yaml", tul, frames=sel, step=5, **glob)
+        # geometry selections (tests_cg.rs:2468-2553, 2682-2713) and min_samples limits (tests_cg.rs:620-665)
+        inf = (float("-inf"), float("inf"))
+        _, sbox_cg, _ = fixtures.tpr_coordinates(os.path.join(FILES, "cg.tpr"), st.xyz)
+        sb = tuple(float(x) for x in sbox_cg)
+        res1 = np.array([i for i in range(cst.n_atoms) if cst.resid[i] == 1], np.int64)
+        add("cuboid_square", "cg_order_cuboid_square.yaml", geom_kind=abi.GEOM_CUBOID, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
+            geom_dims=(-8.0, -2.0, 2.0, 8.0) + inf)
+        add("cylinder", "cg_order_cylinder.yaml", geom_kind=abi.GEOM_CYLINDER, geom_ref_kind=abi.GEOMREF_POINT, geom_ref_point=(2.0, 1.0, 0.0),
+            geom_dims=(3.25,) + inf, geom_axis=abi.AXIS_Z, structure_box=sb)
+        add("sphere_dynamic", "cg_order_sphere.yaml", geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_SELECTION, geom_ref=res1, geom_dims=(2.5,))
+        add("cylinder_z_inverted", "cg_order_cylinder_z_inverted.yaml", geom_kind=abi.GEOM_CYLINDER, geom_ref_kind=abi.GEOMREF_POINT,
+            geom_ref_point=(3.0, 3.0, 3.0), geom_dims=(4.0,) + inf, geom_axis=abi.AXIS_Z, geom_invert=True, structure_box=sb)
+        add("limit", "cg_order_limit.yaml", min_samples=5000)
+        add("leaflets_limit", "cg_order_leaflets_limit.yaml", tul, min_samples=2000, **glob)
         # Individual leaflets assigned once + dynamic normals (PO4, 2 nm): tests_cg.rs:3356-3388
         add("leaflets_dynamic", "cg_order_leaflets_dynamic.yaml", tul, heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL,
             leaflet_freq_kind=abi.FREQ_ONCE, normal_heads=heads, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0)

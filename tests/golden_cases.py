@@ -99,6 +99,7 @@ def flatten_results(res: results.AnalysisResults, keys=("total",), with_error=Fa
 
 
 def assert_matches_yaml(raw: abi.RawResults, setup: abi.EngineSetup, case: dict, tol: float = FIXTURE_TOL):
+    tol = max(tol, case.get("tol", 0.0))
     nb = case.get("n_blocks")
     res = results.convert(raw, setup, n_blocks=nb, min_samples=case.get("min_samples", 1))
     got = flatten_results(res, tuple(case["keys"]), with_error=nb is not None)

@@ -238,9 +238,11 @@ def test_aa_trajectory_fixture():
 # ---- the reference's full AA / CG test trajectories (re-joined from tests/files/split/*) against its YAML fixtures ----
 AA_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
                  "error_leaflets", "begin_end", "begin_end_step", "limit", "leaflets_limit", "sphere_center", "maps_basic",
-                 "maps_cuboid_square", "maps_cylinder"]
+                 "maps_cuboid_square", "maps_cylinder", "cuboid_dynamic", "cylinder_dynamic", "sphere_dynamic", "sphere_dynamic_inverted", "cuboid_patch",
+                 "cylinder_x", "cylinder_z_inverted", "cuboid_square_inverted", "leaflets_dynamic"]
 CG_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
-                 "error_leaflets", "begin_end_step", "leaflets_dynamic"]
+                 "error_leaflets", "begin_end_step", "leaflets_dynamic", "cuboid_square", "cylinder", "sphere_dynamic", "cylinder_z_inverted", "limit",
+                 "leaflets_limit"]
 
 
 def check_maps_aa(raw, setup, case):
