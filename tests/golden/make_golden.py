@@ -276,6 +276,17 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         add("leaflets_limit", "aa_order_leaflets_limit.yaml", tul, min_samples=500, **glob)     # tests_aa.rs:1123-1149
         add("sphere_center", "aa_order_sphere_center.yaml", geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
             geom_dims=(2.5,))                                                                   # tests_aa.rs:3239-3260
+        # exported leaflet tables (bit-exact fixtures; every method writes the same file): tests_aa.rs:588-720
+        def add_export(case, yaml_file, **kw):
+            add(case, "aa_order_leaflets.yaml", tul, collect_leaflets=True, **kw)
+            ldoc = yaml.safe_load(open(os.path.join(FILES, yaml_file)))
+            cases[case].update(leaflets={k: np.array(v, np.uint8).tolist() for k, v in ldoc.items()}, leaflet_source=yaml_file)
+
+        add_export("export_once_global", "aa_leaflets_once.yaml", leaflet_freq_kind=abi.FREQ_ONCE, **glob)
+        add_export("export_every5_local", "aa_leaflets_every5.yaml", heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_LOCAL, leaflet_radius=2.5,
+                   leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=5)
+        add_export("export_every1_individual", "aa_leaflets_every1.yaml", heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL)
+        add_export("export_every1_global", "aa_leaflets_every1.yaml", **glob)
         # geometry selections: reference = centre of residue 1 (PBC centre of geometry of a group: the refined Bai-Breen
         # estimate, otherwise pinned only through leaflets), box centre, fixed point; inverted: tests_aa.rs:3183-3345, 3508-3615
         inf = (float("-inf"), float("inf"))

@@ -239,7 +239,8 @@ def test_aa_trajectory_fixture():
 AA_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
                  "error_leaflets", "begin_end", "begin_end_step", "limit", "leaflets_limit", "sphere_center", "maps_basic",
                  "maps_cuboid_square", "maps_cylinder", "cuboid_dynamic", "cylinder_dynamic", "sphere_dynamic", "sphere_dynamic_inverted", "cuboid_patch",
-                 "cylinder_x", "cylinder_z_inverted", "cuboid_square_inverted", "leaflets_dynamic"]
+                 "cylinder_x", "cylinder_z_inverted", "cuboid_square_inverted", "leaflets_dynamic", "export_once_global", "export_every5_local",
+                 "export_every1_individual", "export_every1_global"]
 CG_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
                  "error_leaflets", "begin_end_step", "leaflets_dynamic", "cuboid_square", "cylinder", "sphere_dynamic", "cylinder_z_inverted", "limit",
                  "leaflets_limit"]
@@ -281,6 +282,14 @@ def check_maps_aa(raw, setup, case):
     assert seen == set(case["maps"].keys()), seen ^ set(case["maps"].keys())
 
 
+def check_leaflet_export(raw, setup, case):
+    """aa_leaflets_*.yaml: one row of 0 / 1 per assignment frame and molecule type -- bit exact."""
+    for mt, (m0, n) in zip(setup.moltypes, _mol_ranges(setup)):
+        exp = np.array(case["leaflets"][mt.name], np.uint8)
+        assert raw.leaflets.shape[0] == exp.shape[0], (raw.leaflets.shape, exp.shape)
+        np.testing.assert_array_equal(raw.leaflets[:, m0:m0 + n], exp, err_msg=f"{case['leaflet_source']} {mt.name}")
+
+
 def _oracle_full(which, name):
     setup, xyz, box, fi, case = gc.full_case(which, name)
     o = oracle.Oracle(setup, n_threads=8)
@@ -290,6 +299,8 @@ def _oracle_full(which, name):
     gc.assert_matches_yaml(raw, setup, case)
     if "maps" in case:
         check_maps_aa(raw, setup, case)
+    if "leaflets" in case:
+        check_leaflet_export(raw, setup, case)
 
 
 @pytest.mark.parametrize("name", AA_FULL_CASES)
