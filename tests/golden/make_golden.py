@@ -276,6 +276,17 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         add("leaflets_limit", "aa_order_leaflets_limit.yaml", tul, min_samples=500, **glob)     # tests_aa.rs:1123-1149
         add("sphere_center", "aa_order_sphere_center.yaml", geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
             geom_dims=(2.5,))                                                                   # tests_aa.rs:3239-3260
+        add("error_blocks10", "aa_order_error_blocks10.yaml", n_blocks=10, timewise=True)        # tests_aa.rs:2530-2552
+        # step 5, leaflets assigned on every analysed frame (real frequency = 1 x step): tests_aa.rs:1307-1346
+        add("step5_leaflets", "aa_order_step.yaml", tul, frames=list(range(0, xyz.shape[0], 5)), step=5, leaflet_freq_kind=abi.FREQ_EVERY,
+            leaflet_freq=5, **glob)
+        # convergence of the molecule averages (prefix averages over frames): tests_aa.rs:2580-2660
+        def read_xvg(fn):
+            return [[float(x) for x in ln.split()] for ln in open(os.path.join(FILES, fn)) if ln[0] not in "#@"]
+        add("convergence", "aa_order_error.yaml", n_blocks=5, timewise=True)
+        cases["convergence"].update(convergence=read_xvg("aa_order_convergence.xvg"))
+        add("convergence_leaflets", "aa_order_error_leaflets.yaml", tul, n_blocks=5, timewise=True, **glob)
+        cases["convergence_leaflets"].update(convergence=read_xvg("aa_order_leaflets_convergence.xvg"))
         # exported leaflet tables (bit-exact fixtures; every method writes the same file): tests_aa.rs:588-720
         def add_export(case, yaml_file, **kw):
             add(case, "aa_order_leaflets.yaml", tul, collect_leaflets=True, **kw)
@@ -314,17 +325,19 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         _, sbox, _ = fixtures.tpr_coordinates(os.path.join(FILES, "pcpepg.tpr"), st.xyz)
         g1 = cst.select(lambda r, n: r == "POPC" and n in ("C22", "C24", "C218"))
 
-        def add_maps(case, yaml_file, mdir, bin_, min_samples, **kw):
-            add(case, yaml_file, map_enabled=True, map_plane=abi.PLANE_XY, map_bin=bin_, map_span_x=(0.0, float(sbox[0])),
+        def add_maps(case, yaml_file, mdir, bin_, min_samples, keys=("total",), **kw):
+            add(case, yaml_file, keys, map_enabled=True, map_plane=abi.PLANE_XY, map_bin=bin_, map_span_x=(0.0, float(sbox[0])),
                 map_span_y=(0.0, float(sbox[1])), **kw)
             mexp = {}
+            ends = ("_full.dat",) if len(keys) == 1 else ("_full.dat", "_upper.dat", "_lower.dat")
             for fn in sorted(os.listdir(os.path.join(FILES, mdir))):
-                if fn.endswith("_full.dat") and "average" not in fn:
+                if fn.endswith(ends) and "average" not in fn:
                     rows = [ln.split() for ln in open(os.path.join(FILES, mdir, fn)) if ln[0] not in "#@$"]
                     mexp[fn] = [[float(a), float(b), float(c)] for a, b, c in rows]
             cases[case].update(maps=mexp, map_min_samples=min_samples)
 
         add_maps("maps_basic", "aa_order_small.yaml", "ordermaps", (0.1, 4.0), 5)
+        add_maps("maps_leaflets", "aa_order_leaflets_small.yaml", "ordermaps", (0.1, 4.0), 5, tul, **glob)   # tests_aa.rs:1627-1730
         add_maps("maps_cuboid_square", "aa_order_cuboid_square.yaml", "ordermaps_cuboid", (0.5, 0.5), 5, geom_kind=abi.GEOM_CUBOID,
                  geom_ref_kind=abi.GEOMREF_POINT, geom_ref_point=(8.0, 2.0, 0.0), geom_dims=(-2.0, 4.0, -4.0, 1.0, float("-inf"), float("inf")),
                  structure_box=tuple(float(x) for x in sbox))
@@ -349,6 +362,25 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
             geom_ref_point=(3.0, 3.0, 3.0), geom_dims=(4.0,) + inf, geom_axis=abi.AXIS_Z, geom_invert=True, structure_box=sb)
         add("limit", "cg_order_limit.yaml", min_samples=5000)
         add("leaflets_limit", "cg_order_leaflets_limit.yaml", tul, min_samples=2000, **glob)
+        # order maps of the POPC B-chain bonds, bin 1 x 1 nm, min_samples 10 (tests_cg.rs:1040-1180)
+        sbox = sbox_cg
+        gsave = (g1, g2)
+        g1 = g2 = cst.select(lambda r, n: r == "POPC" and n in ("C1B", "C2B", "C3B", "C4B"))
+
+        def add_maps(case, yaml_file, mdir, bin_, min_samples, keys=("total",), **kw):
+            add(case, yaml_file, keys, map_enabled=True, map_plane=abi.PLANE_XY, map_bin=bin_, map_span_x=(0.0, float(sbox[0])),
+                map_span_y=(0.0, float(sbox[1])), **kw)
+            mexp = {}
+            ends = ("_full.dat",) if len(keys) == 1 else ("_full.dat", "_upper.dat", "_lower.dat")
+            for fn in sorted(os.listdir(os.path.join(FILES, mdir))):
+                if fn.endswith(ends) and "average" not in fn:
+                    rows = [ln.split() for ln in open(os.path.join(FILES, mdir, fn)) if ln[0] not in "#@$"]
+                    mexp[fn] = [[float(a), float(b), float(c)] for a, b, c in rows]
+            cases[case].update(maps=mexp, map_min_samples=min_samples)
+
+        add_maps("maps_basic", "cg_order_small.yaml", "ordermaps_cg", (1.0, 1.0), 10)
+        add_maps("maps_leaflets", "cg_order_leaflets_small.yaml", "ordermaps_cg", (1.0, 1.0), 10, tul, **glob)
+        g1, g2 = gsave
         # Individual leaflets assigned once + dynamic normals (PO4, 2 nm): tests_cg.rs:3356-3388
         add("leaflets_dynamic", "cg_order_leaflets_dynamic.yaml", tul, heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL,
             leaflet_freq_kind=abi.FREQ_ONCE, normal_heads=heads, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0)

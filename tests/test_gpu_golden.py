@@ -62,7 +62,7 @@ def test_aa_trajectory_fixture():
     gc.assert_matches_yaml(g, setup, case)
 
 
-from test_oracle_pins import AA_FULL_CASES, CG_FULL_CASES, check_leaflet_export, check_maps_aa  # noqa: E402
+from test_oracle_pins import AA_FULL_CASES, CG_FULL_CASES, check_convergence, check_leaflet_export, check_maps_aa  # noqa: E402
 from parity import mean_order  # noqa: E402
 
 # geometry selections around the PBC centre of a group: a sample within an ulp of the shape's surface may fall on either side
@@ -85,6 +85,8 @@ def _check_full(which, name, batches):
         check_maps_aa(g, setup, case)
     if "leaflets" in case:
         check_leaflet_export(g, setup, case)
+    if "convergence" in case:
+        check_convergence(g, setup, case)
 
 
 @pytest.mark.parametrize("name", AA_FULL_CASES)

@@ -240,46 +240,61 @@ AA_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_lo
                  "error_leaflets", "begin_end", "begin_end_step", "limit", "leaflets_limit", "sphere_center", "maps_basic",
                  "maps_cuboid_square", "maps_cylinder", "cuboid_dynamic", "cylinder_dynamic", "sphere_dynamic", "sphere_dynamic_inverted", "cuboid_patch",
                  "cylinder_x", "cylinder_z_inverted", "cuboid_square_inverted", "leaflets_dynamic", "export_once_global", "export_every5_local",
-                 "export_every1_individual", "export_every1_global"]
+                 "export_every1_individual", "export_every1_global", "error_blocks10", "step5_leaflets", "convergence", "convergence_leaflets",
+                 "maps_leaflets"]
 CG_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
                  "error_leaflets", "begin_end_step", "leaflets_dynamic", "cuboid_square", "cylinder", "sphere_dynamic", "cylinder_z_inverted", "limit",
-                 "leaflets_limit"]
+                 "leaflets_limit", "maps_basic", "maps_leaflets"]
 
 
 def check_maps_aa(raw, setup, case):
-    """ordermaps*/ordermap_<res>-<C>-<i>--<res>-<H>-<j>_full.dat (one per C-H bond type) and ordermap_<res>-<C>-<i>_full.dat
-    (the heavy atom: its bonds merged sample by sample): x y value rows, x-major; NaN below min_samples."""
+    """ordermaps*/ordermap_<res>-<A>-<i>--<res>-<B>-<j>_{full,upper,lower}.dat (one per bond type) and, for AA,
+    ordermap_<res>-<C>-<i>_*.dat (the heavy atom: its bonds merged sample by sample): x y value rows, x-major; NaN below
+    min_samples.  AA / UA report -S, CG reports S."""
     nx, ny = raw.map_shape
     mt = setup.moltypes[0]
+    sign = 1.0 if setup.kind == abi.KIND_CG else -1.0
+    suffixes = [("full", 0)] + ([("upper", 1), ("lower", 2)] if any(k.endswith("_upper.dat") for k in case["maps"]) else [])
     per_atom = {}
     seen = set()
-    for b, name in enumerate(mt.bond_names):    # "POPC C22 (32) - POPC H2R (33)"
-        a, h = name.split(" - ")
-        fa, fh = ("-".join(x.replace("(", "").replace(")", "").split()) for x in (a, h))
-        lab = f"ordermap_{fa}--{fh}_full.dat"
+
+    def compare(lab, sm, cn):
         rows = np.array(case["maps"][lab], np.float64)
         assert rows.shape[0] == nx * ny, (rows.shape, nx, ny)
         with np.errstate(divide="ignore", invalid="ignore"):
-            val = -(raw.map_sum[b, 0].astype(np.float64) / 1e6) / raw.map_count[b, 0].astype(np.float64)
-        val = np.where(raw.map_count[b, 0] < case["map_min_samples"], np.nan, val).reshape(-1)
+            val = sign * (sm.astype(np.float64) / 1e6) / cn.astype(np.float64)
+        val = np.where(cn < case["map_min_samples"], np.nan, val).reshape(-1)
         np.testing.assert_allclose(val, rows[:, 2], atol=gc.FIXTURE_TOL, rtol=0, equal_nan=True, err_msg=lab)
         xs = np.repeat(np.arange(nx) * setup.map_bin[0], ny)
         ys = np.tile(np.arange(ny) * setup.map_bin[1], nx)
         np.testing.assert_allclose(rows[:, 0], xs, atol=1e-3)
         np.testing.assert_allclose(rows[:, 1], ys, atol=1e-3)
-        acc = per_atom.setdefault(fa, [np.zeros((nx, ny), np.int64), np.zeros((nx, ny), np.int64)])
-        acc[0] += raw.map_sum[b, 0]
-        acc[1] += raw.map_count[b, 0].astype(np.int64)
         seen.add(lab)
-    for fa, (sm, cn) in per_atom.items():
-        lab = f"ordermap_{fa}_full.dat"
-        rows = np.array(case["maps"][lab], np.float64)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            val = -(sm.astype(np.float64) / 1e6) / cn.astype(np.float64)
-        val = np.where(cn < case["map_min_samples"], np.nan, val).reshape(-1)
-        np.testing.assert_allclose(val, rows[:, 2], atol=gc.FIXTURE_TOL, rtol=0, equal_nan=True, err_msg=lab)
-        seen.add(lab)
+
+    for b, name in enumerate(mt.bond_names):    # "POPC C22 (32) - POPC H2R (33)"
+        a, h = name.split(" - ")
+        fa, fh = ("-".join(x.replace("(", "").replace(")", "").split()) for x in (a, h))
+        for suf, k in suffixes:
+            compare(f"ordermap_{fa}--{fh}_{suf}.dat", raw.map_sum[b, k], raw.map_count[b, k].astype(np.int64))
+            acc = per_atom.setdefault((fa, suf), [np.zeros((nx, ny), np.int64), np.zeros((nx, ny), np.int64)])
+            acc[0] += raw.map_sum[b, k]
+            acc[1] += raw.map_count[b, k].astype(np.int64)
+    if setup.kind == abi.KIND_AA:
+        for (fa, suf), (sm, cn) in per_atom.items():
+            compare(f"ordermap_{fa}_{suf}.dat", sm, cn)
     assert seen == set(case["maps"].keys()), seen ^ set(case["maps"].keys())
+
+
+def check_convergence(raw, setup, case):
+    """*_convergence.xvg: frame number, then the prefix average of every molecule type (total [, upper, lower] blocks)."""
+    res = results.convert(raw, setup, n_blocks=case.get("n_blocks"))
+    exp = np.array(case["convergence"], np.float64)
+    keys = case["keys"]
+    cols = [np.asarray(m.convergence[k], np.float64) for m in res.molecules.values() for k in keys]   # molecule-major
+    got = np.stack(cols, axis=1)
+    assert exp.shape == (got.shape[0], 1 + got.shape[1]), (exp.shape, got.shape)
+    np.testing.assert_array_equal(exp[:, 0], np.arange(1, got.shape[0] + 1))
+    np.testing.assert_allclose(got, exp[:, 1:], atol=gc.FIXTURE_TOL, rtol=0)
 
 
 def check_leaflet_export(raw, setup, case):
@@ -301,6 +316,8 @@ def _oracle_full(which, name):
         check_maps_aa(raw, setup, case)
     if "leaflets" in case:
         check_leaflet_export(raw, setup, case)
+    if "convergence" in case:
+        check_convergence(raw, setup, case)
 
 
 @pytest.mark.parametrize("name", AA_FULL_CASES)
