@@ -208,6 +208,28 @@ def aa_traj_golden():
     print("aa_traj", q.shape, setup.n_slots, "bond types,", [m.name for m in setup.moltypes])
 
 
+def ua_nopbc_golden():
+    """UA without periodic boundary conditions (tests_ua.rs:688-714): ua_nobox.pdb + ua_whole_nobox.xtc (whole molecules, no
+    box), Global leaflets, handle_pbc(false) -> ua_order_leaflets_nopbc.yaml."""
+    st = fixtures.read_pdb(os.path.join(FILES, "ua_nobox.pdb"))
+    traj = fixtures.read_xtc(os.path.join(FILES, "ua_whole_nobox.xtc"))
+    assert traj.xyz.shape[1] == st.n_atoms
+    mem = st.select(lambda r, n: r in LIPIDS)
+    cst, keep = fixtures.compact(st, mem)
+    prec = float(traj.precision)
+    q = np.round(traj.xyz[:, keep, :].astype(np.float64) * prec).astype(np.int32)
+    assert np.array_equal(q.astype(np.float32) * np.float32(1.0 / prec), traj.xyz[:, keep, :]), "XTC coordinates are not k/precision"
+    sat, unsat = ua_selections(cst)
+    heads = cst.select(lambda r, n: n.startswith("P"))
+    setup = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=np.arange(cst.n_atoms), leaflet_mode=abi.LEAFLET_GLOBAL, handle_pbc=False)
+    doc = yaml.safe_load(open(os.path.join(FILES, "ua_order_leaflets_nopbc.yaml")))
+    keys = ("total", "upper", "lower")
+    case = dict(setup=setup.to_dict(), expected=flatten_yaml(doc, keys), keys=list(keys), source="ua_order_leaflets_nopbc.yaml")
+    np.savez_compressed(os.path.join(HERE, "ua_nopbc.npz"), precision=np.float32(prec), box=np.zeros((q.shape[0], 3), np.float32),
+                        case=json.dumps(case), **pack_lattice(q))
+    print("ua_nopbc", q.shape, "precision", prec)
+
+
 def concatenated(base: str, n: int = 5):
     """The reference ships its AA / CG test trajectories only in pieces (tests/files/split/<base>1..5.xtc: the inputs of
     the concatenation tests, tests_aa.rs:48-78, tests_cg.rs:45-76); joined with the duplicated boundary frames dropped
@@ -394,5 +416,6 @@ if __name__ == "__main__":
     single_frame("aa_single_frame", "pcpepg.gro", "pcpepg.bnd", "pcpepg.tpr", abi.KIND_AA, "aaorder.rs", -1.0, "P")
     ua_golden()
     aa_traj_golden()
+    ua_nopbc_golden()
     full_traj_golden("aa_full", "pcpepg", "pcpepg.gro", "pcpepg.bnd", abi.KIND_AA, "P", ("C218", "C316"), 51)
     full_traj_golden("cg_full", "cg", "cg.gro", "cg.bnd", abi.KIND_CG, "PO4", ("C4A", "C4B"), 101)

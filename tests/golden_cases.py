@@ -30,6 +30,15 @@ def aa_traj():
     return setup, xyz, z["box"].astype(np.float32), case
 
 
+def ua_nopbc():
+    """UA without PBC (tests_ua.rs:688-714 -> ua_order_leaflets_nopbc.yaml): setup, frames, (unused) boxes, case."""
+    z = np.load(os.path.join(GOLDEN, "ua_nopbc.npz"))
+    q = np.cumsum(z["dq"].astype(np.int32), axis=0)
+    xyz = q.astype(np.float32) * np.float32(1.0 / float(z["precision"]))
+    case = json.loads(str(z["case"]))
+    return abi.EngineSetup.from_dict(case["setup"]), xyz, z["box"].astype(np.float32), case
+
+
 _FULL = {}
 
 

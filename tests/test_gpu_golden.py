@@ -99,3 +99,11 @@ def test_aa_full_trajectory_fixtures(name):
 def test_cg_full_trajectory_fixtures(name):
     """The reference's full CG test trajectory on the GPU: its cg_order_*.yaml fixtures, and the oracle."""
     _check_full("cg", name, 3)
+
+
+def test_ua_no_pbc_fixture():
+    """handle_pbc(false) on the GPU: ua_order_leaflets_nopbc.yaml (tests_ua.rs:688-714), and the oracle."""
+    setup, xyz, box, case = gc.ua_nopbc()
+    g, r = run_both(setup, xyz, box, batches=2, oracle_threads=8)
+    assert_raw_parity(g, r, setup, what="ua nopbc")
+    gc.assert_matches_yaml(g, setup, case)

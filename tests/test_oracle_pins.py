@@ -333,3 +333,14 @@ def test_cg_full_trajectory_fixtures(name):
     """cg.xtc (101 frames, 6 096 beads): tests_cg.rs:26-43, 180-213, 746-772, 1367-1435, 3356-3388 -> tests/files/cg_order_*.yaml."""
     assert set(CG_FULL_CASES) == set(gc.full_case_names("cg"))
     _oracle_full("cg", name)
+
+
+def test_ua_no_pbc_fixture():
+    """handle_pbc(false): naive centre of geometry, no minimum image, no wrap of the rebuilt hydrogens (pbc.rs:163-199)."""
+    setup, xyz, box, case = gc.ua_nopbc()
+    assert not setup.handle_pbc
+    o = oracle.Oracle(setup, n_threads=8)
+    o.analyze_frames(xyz, box, np.arange(xyz.shape[0], dtype=np.int64))
+    raw = o.finish()
+    o.close()
+    gc.assert_matches_yaml(raw, setup, case)
