@@ -145,6 +145,10 @@ struct GorderHandle {
     bool post_used = false;
     struct SegList { Seg *d = nullptr; int n = 0; };
     SegList seg_membrane[3], seg_geom[3];          // per axis
+    SegList seg_left;                              // leaflet-axis runs of the membrane atoms the bond kernel does not count (SPEC)
+    int spec_left_blocks = 0;
+    double *d_spec_left_sum = nullptr;      // [max_batch][spec_left_blocks][2]
+    float *d_spec_left_mm = nullptr;        // [max_batch][spec_left_blocks][2]
 
     // optional event timing of the accumulation kernel
     bool profiling = false;
@@ -527,6 +531,12 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         o.spec_ref = h->d_spec_ref + h->spec_cur % 4; o.spec_ref_next = h->d_spec_ref + (h->spec_cur + 1) % 4;
         o.spec_sum = h->d_spec_sum; o.spec_mm = h->d_spec_mm; o.spec_ticket = h->d_spec_ticket; o.spec_center = h->d_spec_center + (size_t)slot * h->max_batch;
         o.spec_flag = h->d_spec_flag + (size_t)slot * h->max_batch; o.spec_nflag = nflag; o.n_membrane = s.n_membrane;
+        o.spec_left_sum = h->d_spec_left_sum; o.spec_left_mm = h->d_spec_left_mm; o.spec_left_parts = h->spec_left_blocks;
+        if (h->spec_left_blocks) {   // on the main stream: the provisional centre comes from the previous batch's bond kernel
+            spec_leftover_kernel<<<dim3(h->spec_left_blocks, nf), 256, 0, h->stream>>>(h->view, h->seg_left.d, h->seg_left.n, d_planes, da, o.spec_ref,
+                                                                                      h->d_spec_left_sum, h->d_spec_left_mm);
+            h->n_launches++;
+        }
     }
     o.leaf_out = (inline_leaf && s.collect_leaflets) ? h->d_leaf_rows : nullptr;
     o.bsum = bsum; o.bcnt = bcnt; o.map_sum = h->d_map_sum; o.map_cnt = h->d_map_cnt; o.normal_used = h->d_normal_used;
@@ -719,9 +729,10 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     long long off = 0;
     int slot = 0, molpad = 0, mol = 0;
     auto bad_rel = [&](int r) { return r < 0; };
-    // speculative Global leaflets need every membrane atom to pass through the bond kernel's registers exactly
-    // once: the membrane must be a union of whole planes (relative atom u of ALL molecules of a type) that some
-    // bond loads.  The first bond item that loads such a plane carries the "count it" bit.
+    // speculative Global leaflets sum every membrane atom's displacement exactly once: whole planes (relative atom u
+    // of ALL molecules of a type) that some bond loads are counted in the bond kernel's registers -- the first bond
+    // item that loads such a plane carries the "count it" bit -- and the rest goes through spec_leftover_kernel.
+    std::vector<char> mem_done(s->n_atoms, 0);
     std::vector<char> in_mem(s->n_atoms, 0);
     bool mem_cover = !ua && s->leaflet_mode == GORDER_LEAFLET_GLOBAL && s->n_membrane > 0 && s->membrane;
     for (int i = 0; mem_cover && i < s->n_membrane; i++) {
@@ -785,7 +796,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
             for (size_t u = 0; mem_cover && u < used.size(); u++) {
                 int cnt = 0;
                 for (int mm = 0; mm < m.n_molecules; mm++) cnt += in_mem[m.mol_base[mm] + used[u]];
-                if (cnt == m.n_molecules) plane_mem[u] = 1; else if (cnt != 0) mem_cover = false;
+                if (cnt == m.n_molecules) plane_mem[u] = 1;
             }
             for (int i = 0; i < m.n_bond_types; i++) {
                 // plane offsets are multiples of 32: the two low bits of a_off carry the register-reuse hint
@@ -798,7 +809,8 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
                 bonds.push_back(BondItem{ua_ * td.tile + reuse, ub_ * td.tile});
                 islots.push_back(m.bond_rel[2 * i]);
             }
-            for (size_t u = 0; u < used.size(); u++) if (plane_mem[u] && !plane_done[u]) mem_cover = false;   // a membrane atom no bond loads
+            for (size_t u = 0; u < used.size(); u++)
+                if (plane_done[u]) for (int mm = 0; mm < m.n_molecules; mm++) mem_done[m.mol_base[mm] + used[u]] = 1;
         }
         td.manual_leaf_off = -1; td.n_manual_leaf = 0; td.manual_norm_off = -1; td.n_manual_norm = 0;
         if (m.manual_leaflets && m.n_manual_leaflet_frames > 0) {
@@ -888,6 +900,14 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
             if ((rc = build_segs(h, &h->seg_membrane[axis], s->membrane, s->n_membrane, axis))) return rc;
         if (s->geom_kind != GORDER_GEOM_NONE && s->geom_ref_kind == GORDER_GEOMREF_SELECTION)
             if ((rc = build_segs(h, &h->seg_geom[axis], s->geom_ref, s->n_geom_ref, axis))) return rc;
+    }
+    long long mem_left = 0;
+    if (mem_cover) {
+        std::vector<int32_t> left;
+        for (int i = 0; i < s->n_membrane; i++) if (!mem_done[s->membrane[i]]) left.push_back(s->membrane[i]);
+        mem_left = (long long)left.size();
+        if (getenv("GORDER_NO_SPEC_LEFTOVER") && mem_left) mem_cover = false;
+        else if (mem_left && (rc = build_segs(h, &h->seg_left, left.data(), (int)left.size(), s->leaflet_axis))) return rc;
     }
 
     // order maps: Map::new (ordermap.rs:40-96); node count = round(span / bin) + 1
@@ -1017,7 +1037,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     }
     // speculative Global leaflets: AA/CG, static normal along the leaflet axis, PBC, assignment on every analysed frame,
     // no geometry / maps, membrane covered by the bond kernel's loads (above)
-    h->spec_ok = mem_cover && mem_counted == s->n_membrane && !ua && !h->nvec && !h->extra && s->handle_pbc &&
+    h->spec_ok = mem_cover && mem_counted + mem_left == s->n_membrane && !ua && !h->nvec && !h->extra && s->handle_pbc &&
                  s->leaflet_mode == GORDER_LEAFLET_GLOBAL && s->leaflet_freq_kind == GORDER_FREQ_EVERY && s->leaflet_freq <= std::max(1, s->step) &&
                  s->leaflet_axis == s->normal_axis && h->n_chunks > 0 && !getenv("GORDER_NO_SPEC");
     if (h->spec_ok) {
@@ -1025,6 +1045,11 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         if ((rc = dev_alloc(h, &h->d_spec_sum, 2 * B * (size_t)h->n_chunks))) return rc;
         if ((rc = dev_alloc(h, &h->d_spec_mm, B * (size_t)h->n_chunks * 4))) return rc;
         if ((rc = dev_alloc(h, &h->d_spec_ticket, B, true))) return rc;
+        h->spec_left_blocks = std::min(kSpecLeftBlocks, h->seg_left.n);
+        if (h->spec_left_blocks) {
+            if ((rc = dev_alloc(h, &h->d_spec_left_sum, 2 * B * (size_t)h->spec_left_blocks))) return rc;
+            if ((rc = dev_alloc(h, &h->d_spec_left_mm, 2 * B * (size_t)h->spec_left_blocks))) return rc;
+        }
         if ((rc = dev_alloc(h, &h->d_spec_center, 2 * B, true))) return rc;
         if ((rc = dev_alloc(h, &h->d_spec_flag, 2 * B, true))) return rc;
         CK(cudaHostAlloc((void **)&h->h_spec_counters, 2 * sizeof(unsigned), cudaHostAllocMapped));

@@ -855,6 +855,9 @@ struct AccumOut {
     double *spec_sum;               // [F][n_chunks][2] sum d, sum d^2 (d = min-image displacement from *spec_ref)
     float *spec_mm;                 // [F][n_chunks][4] max |d|, min |d_head|, max |d_head|, NaN seen
     unsigned *spec_ticket;          // [F] CTAs of the frame that have published their partials (self-resetting)
+    const double *spec_left_sum;    // [F][spec_left_parts][2] the same sums over the membrane atoms no bond loads
+    const float *spec_left_mm;      // [F][spec_left_parts][2] max |d|, NaN seen            (spec_leftover_kernel)
+    int spec_left_parts;
     float *spec_center;             // [F] centre derived from the partials
     unsigned char *spec_flag;       // [F] 1 = the frame needs the exact centre (repair)
     unsigned *spec_nflag;           // [1] flagged frames of this batch
@@ -960,6 +963,13 @@ __device__ __forceinline__ void spec_publish(const AccumOut &o, int f, float sre
         nan = nan || m4.w != 0.0f;
         dmax = fmaxf(dmax, m4.x); hmn = fminf(hmn, m4.y); hmx = fmaxf(hmx, m4.z);
     }
+    for (int c = 0; c < o.spec_left_parts; c++) {   // written by spec_leftover_kernel, earlier in the stream
+        const size_t qi = (size_t)f * o.spec_left_parts + c;
+        tot += __ldcg(o.spec_left_sum + 2 * qi); tot2 += __ldcg(o.spec_left_sum + 2 * qi + 1);
+        const float2 m2 = __ldcg(reinterpret_cast<const float2 *>(o.spec_left_mm) + qi);
+        nan = nan || m2.y != 0.0f || m2.x != m2.x;
+        dmax = fmaxf(dmax, m2.x);
+    }
     const double n = (double)o.n_membrane;
     const float delta = (float)(tot / n);
     const float margin = 1e-4f + 1e-3f * L;
@@ -973,6 +983,49 @@ __device__ __forceinline__ void spec_publish(const AccumOut &o, int f, float sre
     o.spec_flag[f] = ok ? 0 : 1;
     if (!ok) atomicAdd(o.spec_nflag, 1u);
     if (f == (int)gridDim.y - 1) *o.spec_ref_next = ok ? c : sref;
+}
+
+// SPEC side pass, grid (<= kSpecLeftBlocks, F): the membrane atoms that no bond of the bond kernel loads (AA: the
+// head-group atoms outside the analysed bonds, lipids without analysed bonds).  One read of their leaflet-axis
+// component gives the sums of spec_add over them; spec_publish adds these partials to the bond kernel's.
+constexpr int kSpecLeftBlocks = 32;
+__global__ void __launch_bounds__(256) spec_leftover_kernel(DeviceView v, const Seg *__restrict__ segs, int n_segs, const float *__restrict__ planes,
+                                                            const FrameAux *__restrict__ aux, const float *__restrict__ ref,
+                                                            double *__restrict__ left_sum, float *__restrict__ left_mm) {
+    const int f = blockIdx.y;
+    const float *fr = planes + (size_t)f * v.frame_floats;
+    const float L = aux[f].L[v.leaflet_axis];
+    const float sref = __ldg(ref);
+    const float invL = L > 0.0f ? __frcp_rn(L) : 0.0f;
+    double ds = 0.0, dq = 0.0;
+    float dabs = 0.0f;
+    for (int sg = blockIdx.x; sg < n_segs; sg += gridDim.x) {
+        const Seg sgm = segs[sg];
+        float a = 0.0f, q = 0.0f;   // <= 16 terms per thread and run
+        for (int i = threadIdx.x; i < sgm.len; i += blockDim.x) {
+            const float t = __ldg(fr + sgm.off + i) - sref;
+            const float k = __fadd_rn(fmaf(t, invL, 12582912.0f), -12582912.0f);
+            const float d = fmaf(-L, k, t);
+            a += d; q = fmaf(d, d, q); dabs = fmaxf(dabs, fabsf(d));
+        }
+        ds += (double)a; dq += (double)q;
+    }
+    float bad = (ds != ds) ? 1.0f : 0.0f;   // NaN / Inf coordinate
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, ofs); dq += __shfl_xor_sync(0xffffffffu, dq, ofs);
+        dabs = fmaxf(dabs, __shfl_xor_sync(0xffffffffu, dabs, ofs)); bad = fmaxf(bad, __shfl_xor_sync(0xffffffffu, bad, ofs));
+    }
+    __shared__ double s_d[2][8];
+    __shared__ float s_m[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_d[0][warp] = ds; s_d[1][warp] = dq; s_m[0][warp] = dabs; s_m[1][warp] = bad; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    ds = 0.0; dq = 0.0; dabs = 0.0f; bad = 0.0f;
+    for (int w = 0; w < 8; w++) { ds += s_d[0][w]; dq += s_d[1][w]; dabs = fmaxf(dabs, s_m[0][w]); bad = fmaxf(bad, s_m[1][w]); }
+    const size_t pi = (size_t)f * gridDim.x + blockIdx.x;
+    left_sum[2 * pi] = ds; left_sum[2 * pi + 1] = dq;
+    left_mm[2 * pi] = dabs; left_mm[2 * pi + 1] = bad;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -124,12 +124,52 @@ def test_spec_switches_itself_off(monkeypatch):
     _same(g, e)
 
 
-def test_spec_not_used_when_membrane_is_not_covered():
-    """AA: the membrane group holds atoms no bond loads (head group): the pre-pass path is used, silently."""
-    s = synthetic.s_aa(64, n_water=100, leaflet_mode=abi.LEAFLET_GLOBAL)
-    xyz, box, idx = s.frames(0, 3)
+@pytest.mark.parametrize("n_lipids,batches", [(64, 1), (1100, 3)])
+def test_spec_with_membrane_atoms_no_bond_loads(n_lipids, batches, monkeypatch):
+    """AA: the membrane group holds atoms no bond loads (head group, lipids of a type without bonds): their
+    displacements come from the side pass (spec_leftover_kernel), the result is that of the pre-pass path."""
+    s = synthetic.s_aa(n_lipids, n_water=100, leaflet_mode=abi.LEAFLET_GLOBAL, collect_leaflets=True)
+    xyz, box, idx = s.frames(0, 6)
+    g, st = _run(s.setup, xyz, box, idx, batches=batches)
+    assert st == {"enabled": True, "frames_speculated": 6, "frames_repaired": 0}
+    monkeypatch.setenv("GORDER_NO_SPEC_LEFTOVER", "1")
+    e, st0 = _run(s.setup, xyz, box, idx)
+    assert not st0["enabled"] and st0["frames_speculated"] == 0
+    monkeypatch.delenv("GORDER_NO_SPEC_LEFTOVER")
+    _same(g, e)
+    g2, r = run_both(s.setup, xyz, box, idx)
+    assert_raw_parity(g2, r, s.setup, what="speculative leaflets, side pass")
+
+
+def test_spec_side_pass_sees_what_the_bond_kernel_does_not(monkeypatch):
+    """Atoms of the side pass half a box away from the membrane centre (which image they belong to depends on the
+    exact centre) must flag the frame."""
+    s = synthetic.s_aa(300, n_water=50, leaflet_mode=abi.LEAFLET_GLOBAL, collect_leaflets=True)
+    xyz, box, idx = s.frames(0, 5)
+    mt = s.setup.moltypes[0]
+    rel = set(np.asarray(mt.bond_rel).ravel().tolist()) | {mt.head_rel}
+    left = [a for a in np.asarray(s.setup.membrane) if (a - np.asarray(mt.mol_base)[0]) not in rel and a < np.asarray(mt.mol_base)[1]]
+    assert left, "the synthetic AA lipid has membrane atoms outside its bonds"
+    stride = int(np.asarray(mt.mol_base)[1] - np.asarray(mt.mol_base)[0])
+    far = np.array([left[0] + stride * m for m in (3, 150, 299)])
+    centre = xyz[2, np.asarray(s.setup.membrane), 2].mean()
+    xyz[2, far, 2] = centre + 0.5 * box[2, 2] - np.array([0.02, 0.01, -0.01], np.float32)
     g, st = _run(s.setup, xyz, box, idx)
-    assert not st["enabled"] and st["frames_speculated"] == 0
+    assert st["frames_speculated"] == 5 and st["frames_repaired"] == 1, st
+    monkeypatch.setenv("GORDER_NO_SPEC", "1")
+    e, _ = _run(s.setup, xyz, box, idx)
+    monkeypatch.delenv("GORDER_NO_SPEC")
+    _same(g, e)
+    # ... and an undefined position that only the side pass reads ends as it does on the pre-pass path:
+    # "invalid global membrane center" (leaflets.rs:187 -> AnalysisError::InvalidGlobalMembraneCenter)
+    xyz[3, far[0], 2] = np.nan
+    for no_spec in (False, True):
+        if no_spec:
+            monkeypatch.setenv("GORDER_NO_SPEC", "1")
+        with pytest.raises(abi.GorderError) as err:
+            _run(s.setup, xyz, box, idx, native=True)   # (the AoS upload would already refuse the NaN)
+        assert err.value.code == abi.ERR_INVALID_GLOBAL_CENTER, (no_spec, str(err.value))
+    monkeypatch.delenv("GORDER_NO_SPEC")
 
 
 @pytest.mark.parametrize("timewise", [False, True])
