@@ -16,7 +16,8 @@ SYMBOLS = [
     "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block", "gorder_gpu_stats",
     "gorder_gpu_read_block", "gorder_gpu_write_block", "gorder_gpu_profile", "gorder_gpu_profile_read",
     "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_stream",
-    "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
+    "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device",
+    "gorder_results_order", "gorder_results_convergence", "gorder_results_map", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
 ]
 
 
@@ -59,6 +60,11 @@ def lib() -> C.CDLL:
     L.gorder_gpu_run_xtc.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, C.POINTER(C.c_double)]
     L.gorder_gpu_run_xtc_device.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, C.POINTER(i64)]
     for name in ("gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device"):
+        getattr(L, name).restype = C.c_int
+    L.gorder_results_order.argtypes = [C.POINTER(abi.CGorderRaw), vp, i32, i32, i32, C.c_float, vp, vp]
+    L.gorder_results_convergence.argtypes = [C.POINTER(abi.CGorderRaw), vp, i32, C.c_float, vp]
+    L.gorder_results_map.argtypes = [vp, vp, i64, i32, C.c_float, vp]
+    for name in ("gorder_results_order", "gorder_results_convergence", "gorder_results_map"):
         getattr(L, name).restype = C.c_int
     L.gorder_gpu_fence.argtypes = [vp]
     L.gorder_gpu_fence.restype = C.c_int

@@ -166,6 +166,19 @@ class CGorderResults(C.Structure):
     ]
 
 
+class CGorderRaw(C.Structure):
+    """``GorderRaw`` (include/gorder_b200.h): views of the accumulators for ``gorder_results_*``."""
+
+    _fields_ = [
+        ("n_slots", C.c_int32),
+        ("n_frames", C.c_int64),
+        ("sum", C.c_void_p),
+        ("count", C.c_void_p),
+        ("tw_sum", C.c_void_p),
+        ("tw_count", C.c_void_p),
+    ]
+
+
 # Python-side description ---------------------------------------------------------------------
 
 def _i32(a) -> np.ndarray:

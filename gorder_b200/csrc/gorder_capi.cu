@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1418,3 +1419,4 @@ int64_t gorder_gpu_error_detail(GorderHandle *h) { return h ? h->err_detail : -1
 }  // extern "C"
 
 #include "gorder_xtc.inl"
+#include "gorder_results.inl"

@@ -44,11 +44,18 @@ def estimate_error(tw_sum: np.ndarray, tw_count: np.ndarray, n_blocks: int) -> O
         if c == 0:
             return float("nan")
         vals.append(np.float32(calc_order(s, c)))
-    v = np.array(vals, np.float32)
-    mean = np.float32(np.float32(v.sum(dtype=np.float32)) / np.float32(n_blocks))
-    dev = (v - mean).astype(np.float32)
-    var = np.float32(np.float32((dev * dev).sum(dtype=np.float32)) / np.float32(n_blocks - 1))
-    return float(np.sqrt(var, dtype=np.float32))
+    # sequential f32 folds, as `statistical 1.0.0` does them (mean = fold(+) / n, variance = fold(+ d^2) / (n - 1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        total = np.float32(0)
+        for x in vals:
+            total = np.float32(total + x)
+        mean = np.float32(total / np.float32(n_blocks))
+        dev2 = np.float32(0)
+        for x in vals:
+            d = np.float32(x - mean)
+            dev2 = np.float32(dev2 + np.float32(d * d))
+        var = np.float32(dev2 / np.float32(n_blocks - 1))
+        return float(np.sqrt(var, dtype=np.float32))
 
 
 def prefix_average(tw_sum: np.ndarray, tw_count: np.ndarray) -> np.ndarray:
@@ -95,107 +102,134 @@ class AnalysisResults:
     n_frames: int
 
 
-class _Summer:
-    """``OrderSummer`` (converter.rs:513-559): element-wise sums of accumulators."""
+class _PythonBackend:
+    """``OrderSummer`` (converter.rs:513-559) + the divisions, in numpy."""
 
-    def __init__(self, n_frames: int, timewise: bool):
-        self.sum = np.zeros(3, np.int64)
-        self.cnt = np.zeros(3, np.uint64)
-        self.tw_sum = np.zeros((n_frames, 3), np.int64) if timewise else None
-        self.tw_cnt = np.zeros((n_frames, 3), np.uint64) if timewise else None
+    def __init__(self, raw: abi.RawResults, sign: float, leaflets: bool, n_blocks: Optional[int], min_samples: int, map_min_samples: int):
+        self.raw, self.sign, self.leaflets, self.nb, self.min_samples, self.map_min = raw, sign, leaflets, n_blocks, min_samples, map_min_samples
+        self.tw = raw.tw_sum is not None
 
-    def add_slot(self, raw: abi.RawResults, s: int):
-        self.sum += raw.sum[s]
-        self.cnt += raw.count[s]
-        if self.tw_sum is not None:
-            self.tw_sum += raw.tw_sum[:, s, :]
-            self.tw_cnt += raw.tw_count[:, s, :]
+    def _sums(self, slots):
+        raw, sl = self.raw, np.asarray(slots, np.int64)
+        sm, ct = raw.sum[sl].sum(axis=0, dtype=np.int64), raw.count[sl].sum(axis=0, dtype=np.uint64)
+        if not self.tw:
+            return sm, ct, None, None
+        return sm, ct, raw.tw_sum[:, sl, :].sum(axis=1, dtype=np.int64), raw.tw_count[:, sl, :].sum(axis=1, dtype=np.uint64)
 
-    def add(self, other: "_Summer"):
-        self.sum += other.sum
-        self.cnt += other.cnt
-        if self.tw_sum is not None:
-            self.tw_sum += other.tw_sum
-            self.tw_cnt += other.tw_cnt
+    def collection(self, slots) -> OrderCollection:
+        sm, ct, ts, tc = self._sums(slots)
+        out = []
+        for k in range(3 if self.leaflets else 1):
+            v = calc_order(sm[k], ct[k], self.min_samples)
+            err = None
+            if self.nb is not None and ts is not None:
+                err = estimate_error(ts[:, k], tc[:, k], self.nb)
+                if err is not None and int(ct[k]) < self.min_samples:
+                    err = float("nan")
+            out.append(Order(self.sign * v if v == v else v, err))
+        return OrderCollection(*out)
+
+    def convergence(self, slots):
+        _sm, _ct, ts, tc = self._sums(slots)
+        return {k: np.array([self.sign * x for x in prefix_average(ts[:, j], tc[:, j])], np.float32)
+                for j, k in enumerate(["total", "upper", "lower"][: 3 if self.leaflets else 1])}
+
+    def slot_map(self, s: int):
+        raw = self.raw
+        with np.errstate(divide="ignore", invalid="ignore"):
+            val = (raw.map_sum[s].astype(np.float64) / 1e6).astype(np.float32) / raw.map_count[s].astype(np.float32)
+        return np.where(raw.map_count[s] < self.map_min, np.nan, self.sign * val).astype(np.float32)
 
 
-def _collection(sign: float, sum3, cnt3, tw_sum, tw_cnt, leaflets: bool, n_blocks: Optional[int], min_samples: int) -> OrderCollection:
-    out = []
-    for k in range(3 if leaflets else 1):
-        v = calc_order(sum3[k], cnt3[k], min_samples)
-        err = None
-        if n_blocks is not None and tw_sum is not None:
-            err = estimate_error(tw_sum[:, k], tw_cnt[:, k], n_blocks)
-            if err is not None and int(cnt3[k]) < min_samples:
-                err = float("nan")
-        out.append(Order(sign * v if v == v else v, err))
-    return OrderCollection(*out)
+class _NativeBackend:
+    """The same through the C ABI (``gorder_results_*``, include/gorder_b200.h; csrc/gorder_results.inl)."""
+
+    def __init__(self, raw: abi.RawResults, sign: float, leaflets: bool, n_blocks: Optional[int], min_samples: int, map_min_samples: int):
+        import ctypes as C
+        from . import _lib
+        self.C, self.lib = C, _lib.lib()
+        self.raw, self.sign, self.leaflets, self.nb, self.min_samples, self.map_min = raw, sign, leaflets, n_blocks, min_samples, map_min_samples
+        self.tw = raw.tw_sum is not None
+        self._keep = [np.ascontiguousarray(raw.sum, np.int64), np.ascontiguousarray(raw.count, np.uint64)]
+        r = abi.CGorderRaw()
+        r.n_slots, r.n_frames = raw.n_slots, (raw.n_frames if self.tw else 0)
+        r.sum, r.count = self._keep[0].ctypes.data, self._keep[1].ctypes.data
+        if self.tw:
+            self._keep += [np.ascontiguousarray(raw.tw_sum, np.int64), np.ascontiguousarray(raw.tw_count, np.uint64)]
+            r.tw_sum, r.tw_count = self._keep[2].ctypes.data, self._keep[3].ctypes.data
+        self.r = r
+
+    def _check(self, rc):
+        if rc != abi.OK:
+            raise abi.GorderError(rc)
+
+    def collection(self, slots) -> OrderCollection:
+        C = self.C
+        sl = np.ascontiguousarray(slots, np.int32)
+        val, err = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        want_err = self.nb is not None and self.tw
+        self._check(self.lib.gorder_results_order(C.byref(self.r), sl.ctypes.data, len(sl), self.nb if want_err else 0, self.min_samples,
+                                                  self.sign, val.ctypes.data, err.ctypes.data if want_err else None))
+        n = 3 if self.leaflets else 1
+        no_frames = self.raw.n_frames == 0
+        return OrderCollection(*[Order(float(val[k]), (None if no_frames else float(err[k])) if want_err else None) for k in range(n)])
+
+    def convergence(self, slots):
+        sl = np.ascontiguousarray(slots, np.int32)
+        out = np.zeros((self.raw.n_frames, 3), np.float32)
+        self._check(self.lib.gorder_results_convergence(self.C.byref(self.r), sl.ctypes.data, len(sl), self.sign, out.ctypes.data))
+        return {k: out[:, j].copy() for j, k in enumerate(["total", "upper", "lower"][: 3 if self.leaflets else 1])}
+
+    def slot_map(self, s: int):
+        ms, mc = np.ascontiguousarray(self.raw.map_sum[s], np.int64), np.ascontiguousarray(self.raw.map_count[s], np.uint64)
+        out = np.zeros(ms.shape, np.float32)
+        self._check(self.lib.gorder_results_map(ms.ctypes.data, mc.ctypes.data, ms.size, self.map_min, self.sign, out.ctypes.data))
+        return out
 
 
 def convert(raw: abi.RawResults, setup: abi.EngineSetup, *, n_blocks: Optional[int] = None, min_samples: int = 1,
-            map_min_samples: int = 1) -> AnalysisResults:
-    """``ResultsConverter::convert_topology`` (converter.rs:52-85)."""
+            map_min_samples: int = 1, native: bool = False) -> AnalysisResults:
+    """``ResultsConverter::convert_topology`` (converter.rs:52-85).  ``native``: the divisions, block errors and prefix
+    averages run in the shared library (``gorder_results_*``) instead of numpy; the tree is built here either way."""
     sign = 1.0 if setup.kind == abi.KIND_CG else -1.0   # AA / UA report -S_CH (presentation/mod.rs:618-691)
     leaflets = setup.leaflet_mode != abi.LEAFLET_NONE
     tw = setup.timewise and raw.tw_sum is not None
-    nb = n_blocks if tw else None
-    nf = raw.n_frames
-    system = _Summer(nf, tw)
+    if not tw and raw.tw_sum is not None:
+        raw = abi.RawResults(**{**raw.__dict__, "tw_sum": None, "tw_count": None})
+    be = (_NativeBackend if native else _PythonBackend)(raw, sign, leaflets, n_blocks if tw else None, min_samples, map_min_samples)
     molecules: Dict[str, MoleculeResults] = {}
-
-    def coll(sm: _Summer) -> OrderCollection:
-        return _collection(sign, sm.sum, sm.cnt, sm.tw_sum, sm.tw_cnt, leaflets, nb, min_samples)
-
-    def slot_coll(s: int) -> OrderCollection:
-        return _collection(sign, raw.sum[s], raw.count[s], raw.tw_sum[:, s, :] if tw else None, raw.tw_count[:, s, :] if tw else None,
-                           leaflets, nb, min_samples)
+    system_slots: List[int] = []
 
     def slot_map(s: int):
-        if raw.map_sum is None:
-            return None
-        with np.errstate(divide="ignore", invalid="ignore"):
-            val = (raw.map_sum[s].astype(np.float64) / 1e6).astype(np.float32) / raw.map_count[s].astype(np.float32)
-        val = np.where(raw.map_count[s] < map_min_samples, np.nan, sign * val).astype(np.float32)
-        return val
+        return None if raw.map_sum is None else be.slot_map(s)
 
     for (s0, n), mt in zip(setup.slot_ranges(), setup.moltypes):
-        mol = _Summer(nf, tw)
+        mol_slots: List[int] = []
         items: List[ItemResults] = []
         if setup.kind == abi.KIND_UA:
             s = s0
             for i, kind in enumerate(mt.ua_kind):
-                atom = _Summer(nf, tw)
-                bonds = []
-                for _ in range(abi.ua_hydrogens(kind)):
-                    atom.add_slot(raw, s)
-                    bonds.append(slot_coll(s))
-                    s += 1
-                mol.add(atom)
+                atom_slots = list(range(s, s + abi.ua_hydrogens(kind)))
+                s += len(atom_slots)
+                mol_slots += atom_slots
                 label = mt.bond_names[i] if i < len(mt.bond_names) else f"atom {i}"
-                items.append(ItemResults(label, coll(atom), bonds))
+                items.append(ItemResults(label, be.collection(atom_slots), [be.collection([q]) for q in atom_slots]))
         elif setup.kind == abi.KIND_CG:
             for b in range(n):
-                mol.add_slot(raw, s0 + b)
+                mol_slots.append(s0 + b)
                 label = mt.bond_names[b] if b < len(mt.bond_names) else f"bond {b}"
-                items.append(ItemResults(label, slot_coll(s0 + b), maps=slot_map(s0 + b)))
+                items.append(ItemResults(label, be.collection([s0 + b]), maps=slot_map(s0 + b)))
         else:
             # AA: bonds grouped by their heavy atom (converter.rs:325-352); bonds are sorted by atom1 (bond.rs:77-81)
             by_atom: Dict[int, List[int]] = {}
             for b, (a1, _a2) in enumerate(mt.bond_rel):
                 by_atom.setdefault(int(a1), []).append(b)
             for a1 in sorted(by_atom):
-                atom = _Summer(nf, tw)
-                bonds = []
-                for b in by_atom[a1]:
-                    atom.add_slot(raw, s0 + b)
-                    bonds.append(slot_coll(s0 + b))
-                mol.add(atom)
+                atom_slots = [s0 + b for b in by_atom[a1]]
+                mol_slots += atom_slots
                 label = (mt.bond_names[by_atom[a1][0]].split(" - ")[0] if by_atom[a1][0] < len(mt.bond_names) else f"atom {a1}")
-                items.append(ItemResults(label, coll(atom), bonds))
-        conv = None
-        if tw:
-            conv = {k: np.array([sign * x for x in prefix_average(mol.tw_sum[:, j], mol.tw_cnt[:, j])], np.float32)
-                    for j, k in enumerate(["total", "upper", "lower"][: 3 if leaflets else 1])}
-        molecules[mt.name] = MoleculeResults(mt.name, coll(mol), items, conv)
-        system.add(mol)
-    return AnalysisResults(coll(system), molecules, nf)
+                items.append(ItemResults(label, be.collection(atom_slots), [be.collection([q]) for q in atom_slots]))
+        conv = be.convergence(mol_slots) if tw else None
+        molecules[mt.name] = MoleculeResults(mt.name, be.collection(mol_slots), items, conv)
+        system_slots += mol_slots
+    return AnalysisResults(be.collection(system_slots), molecules, raw.n_frames)

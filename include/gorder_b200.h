@@ -357,6 +357,31 @@ int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slo
 int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride,
                               int64_t frame_index0, int32_t n_threads, int32_t batch_frames, int64_t *bytes_h2d);
 
+/* ---- results conversion, the step after the path -------------------------------------------
+ * Host only: no GPU, no handle.  Stands in for SystemTopology::convert (topology/mod.rs:122 ->
+ * presentation/converter.rs:52-559) when the harness has no Rust converter: the reference's own converter keeps working on
+ * the back-filled SystemTopology.  `slots` selects the accumulator slots that are summed before the division
+ * (OrderSummer, converter.rs:513-559): one slot = one bond, the bonds of a heavy atom = the atom, all slots of a molecule
+ * type = the molecule, all slots = the system.  Outputs are [total, upper, lower]; `sign` is -1 for AA/UA (-S_CH,
+ * presentation/mod.rs:618-691) and +1 for CG. */
+typedef struct GorderRaw {
+    int32_t n_slots;
+    int64_t n_frames;          /* rows of tw_* (0: no per-frame data) */
+    const int64_t *sum;        /* [n_slots][3]   as filled by gorder_gpu_finish */
+    const uint64_t *count;     /* [n_slots][3] */
+    const int64_t *tw_sum;     /* [n_frames][n_slots][3] or NULL */
+    const uint64_t *tw_count;  /* [n_frames][n_slots][3] or NULL */
+} GorderRaw;
+/* AnalysisOrder::calc_order (order.rs:97-107; NaN below min_samples) and, when `error` is not NULL and per-frame data
+ * exist, TimeWiseData::estimate_error (timewise.rs:191-231): sample standard deviation of n_blocks block means (NaN when a
+ * block is empty, when below min_samples or when there is no per-frame data). */
+int gorder_results_order(const GorderRaw *raw, const int32_t *slots, int32_t n_sel, int32_t n_blocks, int32_t min_samples, float sign,
+                         float *value /* [3] */, float *error /* [3] or NULL */);
+/* TimeWiseData::prefix_average (timewise.rs:259-274): out[f][k] = order over frames 0..f (NaN while there are no samples). */
+int gorder_results_convergence(const GorderRaw *raw, const int32_t *slots, int32_t n_sel, float sign, float *out /* [n_frames][3] */);
+/* Order-map bins (ordermap.rs / converter.rs:159-308): out[i] = sign * (sum[i] / 1e6) / count[i], NaN below min_samples. */
+int gorder_results_map(const int64_t *map_sum, const uint64_t *map_count, int64_t n, int32_t min_samples, float sign, float *out);
+
 /* Human-readable detail of the last error of this handle (offending atom index etc.). */
 int gorder_gpu_last_error(GorderHandle *h, char *buf, size_t len);
 

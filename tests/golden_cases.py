@@ -115,3 +115,7 @@ def assert_matches_yaml(raw: abi.RawResults, setup: abi.EngineSetup, case: dict,
     exp = np.array(case["expected"], dtype=np.float64)
     assert got.shape == exp.shape, (got.shape, exp.shape)
     np.testing.assert_allclose(got, exp, atol=tol, rtol=0, equal_nan=True, err_msg=f"fixture {case['source']}")
+    # the converter of the shared library (gorder_results_*) gives the same bits as the numpy one
+    nat = results.convert(raw, setup, n_blocks=nb, min_samples=case.get("min_samples", 1), native=True)
+    got_native = flatten_results(nat, tuple(case["keys"]), with_error=nb is not None)
+    np.testing.assert_array_equal(got_native.astype(np.float32), got.astype(np.float32), err_msg=f"native converter, {case['source']}")

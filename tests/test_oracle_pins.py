@@ -295,6 +295,10 @@ def check_convergence(raw, setup, case):
     assert exp.shape == (got.shape[0], 1 + got.shape[1]), (exp.shape, got.shape)
     np.testing.assert_array_equal(exp[:, 0], np.arange(1, got.shape[0] + 1))
     np.testing.assert_allclose(got, exp[:, 1:], atol=gc.FIXTURE_TOL, rtol=0)
+    nat = results.convert(raw, setup, n_blocks=case.get("n_blocks"), native=True)
+    for name, m in res.molecules.items():
+        for k in keys:
+            np.testing.assert_array_equal(nat.molecules[name].convergence[k], m.convergence[k], err_msg=f"native prefix average {name} {k}")
 
 
 def check_leaflet_export(raw, setup, case):
