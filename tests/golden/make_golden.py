@@ -145,6 +145,13 @@ def ua_golden():
     ndoc = yaml.safe_load(open(os.path.join(FILES, "ua_normals.yaml")))
     add("dynamic_normals", dyn, "ua_order_dynamic_normals.yaml",
         normals={k: np.array(v, np.float32).tolist() for k, v in ndoc.items()})
+    # saturated / unsaturated carbons only (tests_ua.rs:69-118)
+    add("basic_saturated", fixtures.build_ua_setup(cst, sat, ()), "ua_order_basic_saturated.yaml")
+    add("basic_unsaturated", fixtures.build_ua_setup(cst, (), unsat), "ua_order_basic_unsaturated.yaml")
+    # tests_ua.rs:215-251 (spectral clustering of the P atoms names the leaflets the other way round): the Global
+    # assignment with `flip`
+    flip = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL, leaflet_flip=True)
+    add("leaflets_flipped", flip, "ua_order_leaflets_flipped.yaml", keys=("total", "upper", "lower"))
     # leaflet export, Once (bit-exact fixture)
     once = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL,
                                    leaflet_freq_kind=abi.FREQ_ONCE, collect_leaflets=True)
@@ -299,6 +306,8 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         add("sphere_center", "aa_order_sphere_center.yaml", geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
             geom_dims=(2.5,))                                                                   # tests_aa.rs:3239-3260
         add("error_blocks10", "aa_order_error_blocks10.yaml", n_blocks=10, timewise=True)        # tests_aa.rs:2530-2552
+        add("error_limit", "aa_order_error_limit.yaml", n_blocks=5, timewise=True, min_samples=2000)             # tests_aa.rs:2444-2477
+        add("error_leaflets_limit", "aa_order_error_leaflets_limit.yaml", tul, n_blocks=5, timewise=True, min_samples=500, **glob)   # :2480-2527
         # step 5, leaflets assigned on every analysed frame (real frequency = 1 x step): tests_aa.rs:1307-1346
         add("step5_leaflets", "aa_order_step.yaml", tul, frames=list(range(0, xyz.shape[0], 5)), step=5, leaflet_freq_kind=abi.FREQ_EVERY,
             leaflet_freq=5, **glob)
@@ -340,6 +349,9 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         _, sbox0, _ = fixtures.tpr_coordinates(os.path.join(FILES, "pcpepg.tpr"), st.xyz)
         add("cuboid_square_inverted", "aa_order_cuboid_square_inverted.yaml", geom_kind=abi.GEOM_CUBOID, geom_ref_kind=abi.GEOMREF_POINT,
             geom_ref_point=(8.0, 2.0, 0.0), geom_dims=(-2.0, 4.0, -4.0, 1.0) + inf, geom_invert=True, structure_box=tuple(float(x) for x in sbox0))
+        # sphere around a fixed point: tests_aa.rs:3154-3180
+        add("sphere_static", "aa_order_sphere_static.yaml", geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_POINT, geom_ref_point=(8.0, 2.0, 4.5),
+            geom_dims=(2.5,), structure_box=tuple(float(x) for x in sbox0))
         # dynamic PCA normals (P atoms, 2 nm) + Individual leaflets assigned once: tests_aa.rs:4774-4806
         add("leaflets_dynamic", "aa_order_leaflets_dynamic.yaml", tul, heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL,
             leaflet_freq_kind=abi.FREQ_ONCE, normal_heads=heads, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0)
@@ -384,6 +396,19 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
             geom_ref_point=(3.0, 3.0, 3.0), geom_dims=(4.0,) + inf, geom_axis=abi.AXIS_Z, geom_invert=True, structure_box=sb)
         add("limit", "cg_order_limit.yaml", min_samples=5000)
         add("leaflets_limit", "cg_order_leaflets_limit.yaml", tul, min_samples=2000, **glob)
+        add("error_limit", "cg_order_error_limit.yaml", n_blocks=5, timewise=True, min_samples=5000)                     # tests_cg.rs:1612-1641
+        add("error_leaflets_limit", "cg_order_error_leaflets_limit.yaml", tul, n_blocks=5, timewise=True, min_samples=2000, **glob)   # :1644-1690
+        # begin 352 000 ps, end 358 000 ps: 61 frames (tests_cg.rs:893-915)
+        sel61 = [i for i, t in enumerate(time) if 352000.0 <= t <= 358000.0]
+        assert len(sel61) == 61
+        add("begin_end", "cg_order_begin_end.yaml", tul, frames=sel61, **glob)
+        # only the lipids of the upper leaflet are analysed ("resid 1 to 254"), leaflets assigned once: tests_cg.rs:206-236
+        gsave = (g1, g2)
+        g1 = g2 = np.array([i for i in range(cst.n_atoms) if 1 <= cst.resid[i] <= 254], np.int64)
+        add("leaflets_only_upper", "cg_order_leaflets_only_upper.yaml", tul, leaflet_freq_kind=abi.FREQ_ONCE, **glob)
+        add("leaflets_only_upper_individual", "cg_order_leaflets_only_upper.yaml", tul, heads=heads, methyls=methyls,
+            leaflet_mode=abi.LEAFLET_INDIVIDUAL, leaflet_freq_kind=abi.FREQ_ONCE)
+        g1, g2 = gsave
         # order maps of the POPC B-chain bonds, bin 1 x 1 nm, min_samples 10 (tests_cg.rs:1040-1180)
         sbox = sbox_cg
         gsave = (g1, g2)
