@@ -103,3 +103,53 @@ def test_reference_trajectories_match_oracle_reader(name, shape):
     np.testing.assert_array_equal(time, np.asarray(ref.time, np.float32))
     if shape is not None:
         assert got.shape[:2] == shape
+
+
+_FUZZ = r'''
+import os, sys, tempfile
+import numpy as np
+from gorder_b200 import xtc
+rng = np.random.default_rng(int(sys.argv[1]))
+d = tempfile.mkdtemp()
+n = 500
+xyz = (rng.normal(0, 1.5, (6, n, 3)) + 5).astype(np.float32)
+xyz[:, 1::2] = xyz[:, ::2] + rng.normal(0, 0.1, (6, n // 2, 3)).astype(np.float32)   # pairs of close atoms: runs of small triples
+xtc.write_xtc(os.path.join(d, "a.xtc"), xyz, np.full((6, 3), 10, np.float32), precision=1000.0)
+raw = np.fromfile(os.path.join(d, "a.xtc"), np.uint8)
+ok = 0
+for it in range(int(sys.argv[2])):
+    b = raw.copy()
+    if it % 4 == 0:                                   # scattered byte flips
+        for _ in range(rng.integers(1, 8)):
+            b[rng.integers(0, len(b))] = rng.integers(0, 256)
+    elif it % 4 == 1:                                 # truncation anywhere
+        b = b[: rng.integers(0, len(b))]
+    elif it % 4 == 2:                                 # a header word of the first frame
+        w = rng.integers(0, 24)
+        b[4 * w: 4 * w + 4] = rng.integers(0, 256, 4)
+    else:                                             # 64 bytes of noise in the bit stream
+        i = rng.integers(0, len(b) - 64)
+        b[i: i + 64] = rng.integers(0, 256, 64)
+    p = os.path.join(d, "f.xtc")
+    b.tofile(p)
+    try:
+        with xtc.XtcFile(p) as f:
+            if f.n_frames > 0 and f.n_atoms < 10 ** 7:
+                f.read(0, f.n_frames, n_threads=2)
+        ok += 1
+    except (OSError, ValueError, RuntimeError):
+        pass
+print("survived", ok)
+'''
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_reader_survives_corrupt_files(seed):
+    """Flipped bytes, truncation, corrupt headers and noise in the bit stream end in an error code or in garbage
+    coordinates, never in a crash of the host process (the reader runs inside the caller's analysis)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _FUZZ, str(seed), "400"], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    assert "survived" in r.stdout
