@@ -696,6 +696,12 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     h->extra = s->geom_kind != GORDER_GEOM_NONE || s->map_enabled;
     h->nvec = s->normal_mode != GORDER_NORMAL_STATIC;
     if (s->n_atoms <= 0 || s->n_moltypes < 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "bad n_atoms / n_moltypes"); return h->err_code; }
+    if (s->leaflet_mode < GORDER_LEAFLET_NONE || s->leaflet_mode > GORDER_LEAFLET_MANUAL) {
+        h->set_error(GORDER_ERR_INVALID_ARGUMENT, s->leaflet_mode == GORDER_LEAFLET_SPHERICAL
+                     ? "spherical-clustering leaflets are not computed on the device yet: pass the table with GORDER_LEAFLET_MANUAL"
+                     : "unknown leaflet mode");
+        return h->err_code;
+    }
 
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || s->device < 0 || s->device >= n_dev) {

@@ -60,7 +60,11 @@ enum {
     GORDER_LEAFLET_GLOBAL = 1,
     GORDER_LEAFLET_LOCAL = 2,
     GORDER_LEAFLET_INDIVIDUAL = 3,
-    GORDER_LEAFLET_MANUAL = 4
+    GORDER_LEAFLET_MANUAL = 4,
+    /* spherical clustering (spherical_clustering.rs:36-275; `membrane` holds the ClusterHeads group).  Restated in the
+     * oracle; the device kernel is SURVEY.md §8f rank 2 -- until then gorder_gpu_create refuses it and the host passes
+     * the table with GORDER_LEAFLET_MANUAL. */
+    GORDER_LEAFLET_SPHERICAL = 5
 };
 
 /* Frequency, reference: src/input/frequency.rs; leaflets.rs:435-441 */

@@ -566,6 +566,103 @@ static vec3 local_membrane_center(const GorderOracle *o, const float *xyz, const
     return group_center(xyz, scratch, n, box, pbc);
 }
 
+/* ---- spherical clustering: two-component 1-D Gaussian mixture of the head - vesicle-centre distances ----
+ * (spherical_clustering.rs:22-272; sums are the reference's sequential f32 folds, ln / exp are libm's) */
+#define GMM_MAX_ITERATIONS 50
+#define GMM_TOLERANCE 1e-4f
+
+static inline float gmm_log_gaussian(float x, float mean, float variance) {   /* :103-107 */
+    float diff = x - mean;
+    return -0.5f * (logf(2.0f * 3.14159274101257324f) + logf(variance) + diff * diff / variance);
+}
+static inline float gmm_log_sum_exp(float a, float b) {                       /* :110-114 */
+    float m = a > b ? a : b;
+    return m + logf(expf(a - m) + expf(b - m));
+}
+static int cmp_float(const void *a, const void *b) { float x = *(const float *)a, y = *(const float *)b; return (x > y) - (x < y); }
+
+/* fit_gmm_1d_two_components (:138-237) with initialize_params (:116-136).  params: weight_a, mean_a, var_a, mean_b, var_b. */
+static float gmm_fit(const float *data, int n, float *resp_a, float *params) {
+    float n_f = (float)n;
+    const float var_floor = 1e-6f, weight_floor = 1e-4f;
+    float *sorted = (float *)malloc(sizeof(float) * (n > 0 ? n : 1));
+    memcpy(sorted, data, sizeof(float) * n);
+    qsort(sorted, n, sizeof(float), cmp_float);
+    float mean_a = sorted[n / 4], mean_b = sorted[(3 * n) / 4];
+    free(sorted);
+    float gsum = 0.0f;
+    for (int i = 0; i < n; i++) gsum += data[i];
+    float gmean = gsum / n_f, gdev = 0.0f;
+    for (int i = 0; i < n; i++) { float d = data[i] - gmean; gdev += d * d; }
+    float gvar = gdev / (n_f - 1.0f);
+    if (!isfinite(gvar) || gvar <= 0.0f) gvar = 1.0f;
+    float weight_a = 0.5f, var_a = gvar > var_floor ? gvar : var_floor, var_b = var_a;
+    for (int i = 0; i < n; i++) resp_a[i] = 0.5f;
+    float prev_avg_ll = -INFINITY;
+    for (int it = 0; it < GMM_MAX_ITERATIONS; it++) {
+        float loglik_sum = 0.0f;
+        float log_weight_a = logf(weight_a), log_weight_b = logf(1.0f - weight_a);
+        for (int i = 0; i < n; i++) {
+            float x = data[i];
+            float ja = log_weight_a + gmm_log_gaussian(x, mean_a, var_a), jb = log_weight_b + gmm_log_gaussian(x, mean_b, var_b);
+            float log_px = gmm_log_sum_exp(ja, jb);
+            loglik_sum += log_px;
+            resp_a[i] = expf(ja - log_px);
+        }
+        float avg_ll = loglik_sum / n_f;
+        if (fabsf(avg_ll - prev_avg_ll) < GMM_TOLERANCE) { prev_avg_ll = avg_ll; break; }
+        prev_avg_ll = avg_ll;
+        float sum_a = 0.0f;
+        for (int i = 0; i < n; i++) sum_a += resp_a[i];
+        float sum_b = n_f - sum_a;
+        sum_a = sum_a > 1e-6f ? sum_a : 1e-6f;
+        sum_b = sum_b > 1e-6f ? sum_b : 1e-6f;
+        weight_a = sum_a / n_f;
+        if (weight_a < weight_floor) weight_a = weight_floor;
+        if (weight_a > 1.0f - weight_floor) weight_a = 1.0f - weight_floor;
+        float ma = 0.0f, mb = 0.0f;
+        for (int i = 0; i < n; i++) { ma += resp_a[i] * data[i]; mb += (1.0f - resp_a[i]) * data[i]; }
+        mean_a = ma / sum_a; mean_b = mb / sum_b;
+        float va = 0.0f, vb = 0.0f;
+        for (int i = 0; i < n; i++) {
+            float da = data[i] - mean_a, db = data[i] - mean_b;
+            va += resp_a[i] * da * da; vb += (1.0f - resp_a[i]) * db * db;
+        }
+        var_a = va / sum_a; var_b = vb / sum_b;
+        if (var_a < var_floor) var_a = var_floor;
+        if (var_b < var_floor) var_b = var_floor;
+    }
+    if (params) { params[0] = weight_a; params[1] = mean_a; params[2] = var_a; params[3] = mean_b; params[4] = var_b; }
+    return prev_avg_ll;
+}
+
+/* Clusters::from_responsibilities (:239-272): r < 0.5 -> cluster 1; the cluster farther from the centre is the upper (outer) one. */
+static void gmm_clusters(const float *resp_a, const float *dist, int n, uint8_t *upper) {
+    float s1 = 0.0f, s2 = 0.0f;
+    int n1 = 0, n2 = 0;
+    for (int i = 0; i < n; i++) {
+        if (resp_a[i] < 0.5f) { n1++; s1 += dist[i]; } else { n2++; s2 += dist[i]; }
+    }
+    int first_is_upper = (s1 / (float)n1) > (s2 / (float)n2);
+    for (int i = 0; i < n; i++) upper[i] = ((resp_a[i] < 0.5f) == first_is_upper) ? 1 : 0;
+}
+
+float gorder_oracle_gmm_fit(const float *data, int n, float *resp_a, float *params) { return gmm_fit(data, n, resp_a, params); }
+void gorder_oracle_gmm_clusters(const float *resp_a, const float *dist, int n, uint8_t *upper) { gmm_clusters(resp_a, dist, n, upper); }
+
+/* SystemSphericalClusterClassification::cluster (:42-76): distances of the ClusterHeads group (GorderSetup.membrane in this
+ * mode) from its PBC-aware centre, mixture fit, clusters.  upper[i] = 1 for the outer leaflet. */
+static void spherical_cluster(const GorderOracle *o, const float *xyz, const float *box, uint8_t *upper) {
+    const GorderSetup *s = &o->s;
+    int n = s->n_membrane, pbc = s->handle_pbc;
+    vec3 center = group_center(xyz, o->membrane, n, box, pbc);
+    float *dist = (float *)malloc(sizeof(float) * (n > 0 ? n : 1)), *resp = (float *)malloc(sizeof(float) * (n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) dist[i] = vnorm(vector_to(center, atom_pos(xyz, o->membrane[i]), box, pbc));   /* atom - centre */
+    gmm_fit(dist, n, resp, NULL);
+    gmm_clusters(resp, dist, n, upper);
+    free(dist); free(resp);
+}
+
 /* Assign every molecule of every type (AssignedLeaflets::assign_lipids, leaflets.rs:1406-1435;
  * classifiers: Global :571-624 + common_identify_leaflet :711-732, Local :630-707,
  * Individual :736-811, Manual :816-874), then maybe_flip (:68-73).  Output GORDER_UPPER/LOWER. */
@@ -576,6 +673,15 @@ static void assign_leaflets(const GorderOracle *o, const float *xyz, const float
     if (s->leaflet_mode == GORDER_LEAFLET_GLOBAL) { /* SystemLeafletClassification::run, leaflets.rs:171-205 */
         center = group_center(xyz, o->membrane, s->n_membrane, box, pbc);
         if (pos_undefined(center)) { FAIL(fe, GORDER_ERR_INVALID_GLOBAL_CENTER, 0); return; }
+    }
+    uint8_t *cl_upper = NULL;
+    int32_t *cl_pos = NULL;
+    if (s->leaflet_mode == GORDER_LEAFLET_SPHERICAL) {   /* leaflets.rs:201-204, 1351-1367 */
+        cl_upper = (uint8_t *)malloc(s->n_membrane > 0 ? s->n_membrane : 1);
+        cl_pos = (int32_t *)malloc(sizeof(int32_t) * (s->n_atoms > 0 ? s->n_atoms : 1));
+        for (int i = 0; i < s->n_atoms; i++) cl_pos[i] = -1;
+        for (int i = 0; i < s->n_membrane; i++) cl_pos[o->membrane[i]] = i;
+        spherical_cluster(o, xyz, box, cl_upper);
     }
     int32_t *scratch = NULL;
     if (s->leaflet_mode == GORDER_LEAFLET_LOCAL) scratch = (int32_t *)malloc(sizeof(int32_t) * (s->n_membrane > 0 ? s->n_membrane : 1));
@@ -611,6 +717,12 @@ static void assign_leaflets(const GorderOracle *o, const float *xyz, const float
                 upper = total >= 0.0f;
                 break;
             }
+            case GORDER_LEAFLET_SPHERICAL: {
+                int at = cl_pos[q->mol_base[m] + q->head_rel];
+                if (at < 0) { FAIL(fe, GORDER_ERR_INVALID_ARGUMENT, q->mol_base[m] + q->head_rel); break; }   /* the reference panics */
+                upper = cl_upper[at];
+                break;
+            }
             case GORDER_LEAFLET_MANUAL: {
                 int64_t row = s->leaflet_freq_kind == GORDER_FREQ_ONCE ? 0 : frame / (s->leaflet_freq > 0 ? s->leaflet_freq : 1);
                 if (row >= q->n_manual_leaflet_frames) { FAIL(fe, GORDER_ERR_MANUAL_LEAFLET_FRAME, frame); break; }
@@ -622,7 +734,7 @@ static void assign_leaflets(const GorderOracle *o, const float *xyz, const float
             out[q->mol0 + m] = upper ? GORDER_UPPER : GORDER_LOWER;
         }
     }
-    free(scratch);
+    free(scratch); free(cl_upper); free(cl_pos);
 }
 
 /* Cell grid over the NormalHeads group (groan CellGrid::new(system, "NormalHeads", radius), pbc.rs:327-333):

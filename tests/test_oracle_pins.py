@@ -355,3 +355,102 @@ def test_ua_no_pbc_fixture():
     raw = o.finish()
     o.close()
     gc.assert_matches_yaml(raw, setup, case)
+
+
+# ---- spherical clustering: oracle restatement, pinned by the reference's own unit tests ----
+def _gmm(data):
+    import ctypes as C
+    L = oracle.lib()
+    L.gorder_oracle_gmm_fit.restype = C.c_float
+    L.gorder_oracle_gmm_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    data = np.ascontiguousarray(data, np.float32)
+    resp, params = np.zeros(len(data), np.float32), np.zeros(5, np.float32)
+    ll = L.gorder_oracle_gmm_fit(data.ctypes.data, len(data), resp.ctypes.data, params.ctypes.data)
+    return resp, params, ll
+
+
+def test_spherical_clusters_from_responsibilities_known_answer():
+    """spherical_clustering.rs:299-316: r < 0.5 -> one cluster, the one farther from the centre is the upper (outer) leaflet."""
+    import ctypes as C
+    L = oracle.lib()
+    L.gorder_oracle_gmm_clusters.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    resp = np.array([0.9998, 0.1, 0.42, 0.834, 0.932], np.float32)
+    dist = np.array([10.5, 1.3, 2.8, 7.8, 8.4], np.float32)
+    upper = np.zeros(5, np.uint8)
+    L.gorder_oracle_gmm_clusters(resp.ctypes.data, dist.ctypes.data, 5, upper.ctypes.data)
+    assert upper.tolist() == [1, 0, 0, 1, 1]
+    # the other orientation: cluster 1 (r < 0.5) is the outer one
+    L.gorder_oracle_gmm_clusters(resp.ctypes.data, (12 - dist).astype(np.float32).ctypes.data, 5, upper.ctypes.data)
+    assert upper.tolist() == [0, 1, 1, 0, 0]
+
+
+@pytest.mark.parametrize("seed", [424242, 67676767, 12345678, 1111111, 999999])
+def test_spherical_gmm_separates_two_normals(seed):
+    """spherical_clustering.rs:346-361 (test_fit_gmm): 50 points from N(5, 1) / N(20, 2), p = 0.5: component A
+    (initialised from the 25th percentile) takes the points near 5.  Same property, numpy's generator."""
+    rng = np.random.default_rng(seed)
+    pick = rng.random(50) < 0.5
+    data = np.where(pick, rng.normal(5.0, 1.0, 50), rng.normal(20.0, 2.0, 50)).astype(np.float32)
+    resp, params, ll = _gmm(data)
+    assert np.all(resp[pick] > 0.5) and np.all(resp[~pick] < 0.5)   # (the components are > 5 sigma apart)
+    assert params[1] == pytest.approx(5.0, abs=0.6) and params[3] == pytest.approx(20.0, abs=1.2) and np.isfinite(ll)
+    # against an independent float64 EM with the same initialisation and stopping rule
+    x = data.astype(np.float64)
+    srt = np.sort(x)
+    ma, mb, va, vb, w, prev = srt[len(x) // 4], srt[3 * len(x) // 4], x.var(ddof=1), x.var(ddof=1), 0.5, -np.inf
+    for _ in range(50):
+        ja = np.log(w) - 0.5 * (np.log(2 * np.pi) + np.log(va) + (x - ma) ** 2 / va)
+        jb = np.log(1 - w) - 0.5 * (np.log(2 * np.pi) + np.log(vb) + (x - mb) ** 2 / vb)
+        lp = np.logaddexp(ja, jb)
+        r = np.exp(ja - lp)
+        if abs(lp.mean() - prev) < 1e-4:
+            break
+        prev = lp.mean()
+        sa, sb = r.sum(), len(x) - r.sum()
+        w = min(max(sa / len(x), 1e-4), 1 - 1e-4)
+        ma, mb = (r * x).sum() / sa, ((1 - r) * x).sum() / sb
+        va, vb = max((r * (x - ma) ** 2).sum() / sa, 1e-6), max(((1 - r) * (x - mb) ** 2).sum() / sb, 1e-6)
+    np.testing.assert_allclose(resp, r, atol=2e-4)
+    np.testing.assert_allclose(params, [w, ma, va, mb, vb], rtol=2e-4)
+
+
+def test_spherical_leaflets_on_a_vesicle():
+    """Vesicle across the periodic boundary: the outer leaflet is `upper`, whatever the shift; `flip` swaps them."""
+    rng = np.random.default_rng(5)
+    n_out, n_in = 420, 260
+
+    def sphere(n, r):
+        v = rng.normal(size=(n, 3))
+        return (v / np.linalg.norm(v, axis=1)[:, None]) * (r + rng.normal(0, 0.12, (n, 1)))
+
+    heads = np.concatenate([sphere(n_out, 9.0), sphere(n_in, 5.5)])
+    outward = heads / np.linalg.norm(heads, axis=1)[:, None]
+    is_outer = np.arange(n_out + n_in) < n_out
+    tails = heads - outward * np.where(is_outer, 1.0, -1.0)[:, None] * 0.45     # chains point into the bilayer
+    L = 30.0
+    perm = rng.permutation(n_out + n_in)
+    heads, tails, is_outer = heads[perm], tails[perm], is_outer[perm]
+    xyz = np.empty((1, 2 * len(heads), 3), np.float32)
+    shift = np.array([13.0, -4.0, 29.0])
+    xyz[0, 0::2], xyz[0, 1::2] = np.mod(heads + shift, L), np.mod(tails + shift, L)
+    box = np.full((1, 3), L, np.float32)
+    mt = abi.MolType(name="LIP", mol_base=np.arange(0, 2 * len(heads), 2), bond_rel=[(0, 1)], head_rel=0)
+    for flip in (False, True):
+        setup = abi.EngineSetup(kind=abi.KIND_CG, n_atoms=xyz.shape[1], moltypes=[mt], leaflet_mode=abi.LEAFLET_SPHERICAL,
+                                membrane=np.arange(0, 2 * len(heads), 2), leaflet_flip=flip, collect_leaflets=True)
+        o = oracle.Oracle(setup, n_threads=1)
+        o.analyze_frames(xyz, box, np.arange(1))
+        raw = o.finish()
+        o.close()
+        np.testing.assert_array_equal(raw.leaflets[0].astype(bool), is_outer ^ flip)
+        assert raw.count[0].tolist() == [len(heads), int((is_outer ^ flip).sum()), int((~(is_outer ^ flip)).sum())]
+
+
+def test_engine_refuses_spherical_clustering_for_now():
+    """No silent fallback: the device has no spherical-clustering kernel yet (include/gorder_b200.h)."""
+    from gorder_b200 import SystemTopology
+    mt = abi.MolType(name="LIP", mol_base=np.array([0, 2]), bond_rel=[(0, 1)], head_rel=0)
+    setup = abi.EngineSetup(kind=abi.KIND_CG, n_atoms=4, moltypes=[mt], leaflet_mode=abi.LEAFLET_SPHERICAL, membrane=np.array([0, 2]))
+    with pytest.raises(abi.GorderError) as e:
+        SystemTopology(setup)
+    assert e.value.code == abi.ERR_INVALID_ARGUMENT
