@@ -18,6 +18,7 @@
 
 #include "gorder_kernels.cuh"
 #include "gorder_fast.cuh"
+#include "gorder_spherical.cuh"
 
 using namespace gorder;
 
@@ -146,6 +147,11 @@ struct GorderHandle {
     bool post_used = false;
     struct SegList { Seg *d = nullptr; int n = 0; };
     SegList seg_membrane[3], seg_geom[3];          // per axis
+    // spherical-clustering leaflets (experimental, gorder_spherical.cuh)
+    bool spherical = false;
+    float *d_sph_dist = nullptr, *d_sph_resp = nullptr;   // [max_batch][n_membrane]
+    unsigned char *d_sph_upper = nullptr;                 // [max_batch][n_membrane]
+    int *d_sph_index = nullptr;                           // [n_molpad] position of the molecule's head in the ClusterHeads group
     SegList seg_left;                              // leaflet-axis runs of the membrane atoms the bond kernel does not count (SPEC)
     int spec_left_blocks = 0;
     double *d_spec_left_sum = nullptr;      // [max_batch][spec_left_blocks][2]
@@ -486,8 +492,15 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
             h->n_launches += 3;
         }
         dim3 grid((h->n_molpad + 255) / 256, n_assign);
-        leaflet_assign_kernel<<<grid, 256, 0, sp>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_molpad_type, h->d_leaf_rows,
-                                                     h->use_lcells ? h->d_lcell_start : nullptr, h->d_lcell_sorted, h->lcells_cap);
+        if (h->spherical) {   // experimental (gorder_spherical.cuh)
+            int rc = run_group_center(h, sp, h->seg_membrane, h->s.n_membrane, 7, d_planes, da, dl_assign, n_assign);
+            if (rc) return rc;
+            spherical_cluster_kernel<<<n_assign, kSphThreads, 0, sp>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_sph_dist, h->d_sph_resp, h->d_sph_upper);
+            spherical_assign_kernel<<<grid, 256, 0, sp>>>(h->view, h->d_molpad_type, h->d_sph_index, h->d_sph_upper, h->d_leaf_rows);
+            h->n_launches++;
+        } else
+            leaflet_assign_kernel<<<grid, 256, 0, sp>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_molpad_type, h->d_leaf_rows,
+                                                         h->use_lcells ? h->d_lcell_start : nullptr, h->d_lcell_sorted, h->lcells_cap);
         h->n_launches++;
     }
     // per-frame accumulator rows
@@ -696,12 +709,14 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     h->extra = s->geom_kind != GORDER_GEOM_NONE || s->map_enabled;
     h->nvec = s->normal_mode != GORDER_NORMAL_STATIC;
     if (s->n_atoms <= 0 || s->n_moltypes < 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "bad n_atoms / n_moltypes"); return h->err_code; }
-    if (s->leaflet_mode < GORDER_LEAFLET_NONE || s->leaflet_mode > GORDER_LEAFLET_MANUAL) {
+    h->spherical = s->leaflet_mode == GORDER_LEAFLET_SPHERICAL && getenv("GORDER_EXPERIMENTAL_SPHERICAL");
+    if ((s->leaflet_mode < GORDER_LEAFLET_NONE || s->leaflet_mode > GORDER_LEAFLET_MANUAL) && !h->spherical) {
         h->set_error(GORDER_ERR_INVALID_ARGUMENT, s->leaflet_mode == GORDER_LEAFLET_SPHERICAL
                      ? "spherical-clustering leaflets are not computed on the device yet: pass the table with GORDER_LEAFLET_MANUAL"
                      : "unknown leaflet mode");
         return h->err_code;
     }
+    if (h->spherical && (s->n_membrane < 2 || !s->membrane)) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "spherical clustering needs the ClusterHeads group in `membrane`"); return h->err_code; }
 
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || s->device < 0 || s->device >= n_dev) {
@@ -903,7 +918,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     if ((rc = upload_group(h, &v.geom_ref, s->geom_ref, s->n_geom_ref))) return rc;
     if ((rc = upload_group(h, &v.normal_heads, s->normal_heads, s->n_normal_heads))) return rc;
     for (int axis = 0; axis < 3; axis++) {
-        if (s->leaflet_mode == GORDER_LEAFLET_GLOBAL && axis == s->leaflet_axis)
+        if ((s->leaflet_mode == GORDER_LEAFLET_GLOBAL && axis == s->leaflet_axis) || h->spherical)
             if ((rc = build_segs(h, &h->seg_membrane[axis], s->membrane, s->n_membrane, axis))) return rc;
         if (s->geom_kind != GORDER_GEOM_NONE && s->geom_ref_kind == GORDER_GEOMREF_SELECTION)
             if ((rc = build_segs(h, &h->seg_geom[axis], s->geom_ref, s->n_geom_ref, axis))) return rc;
@@ -1062,6 +1077,26 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         CK(cudaHostAlloc((void **)&h->h_spec_counters, 2 * sizeof(unsigned), cudaHostAllocMapped));
         h->h_spec_counters[0] = h->h_spec_counters[1] = 0;
         CK(cudaHostGetDevicePointer((void **)&h->d_spec_counters, h->h_spec_counters, 0));
+    }
+
+    if (h->spherical) {   // experimental: scratch of spherical_cluster_kernel and the head -> ClusterHeads position table
+        std::vector<int> pos_of(s->n_atoms, -1), index((size_t)h->n_molpad, 0);
+        for (int i = 0; i < s->n_membrane; i++) {
+            if (s->membrane[i] < 0 || s->membrane[i] >= s->n_atoms) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "group atom out of range", s->membrane[i]); return h->err_code; }
+            pos_of[s->membrane[i]] = i;
+        }
+        for (int t = 0; t < s->n_moltypes; t++) {
+            const GorderMolType &m = s->moltypes[t];
+            for (int mm = 0; mm < m.n_molecules; mm++) {
+                const int head = m.head_rel >= 0 ? m.mol_base[mm] + m.head_rel : -1;
+                if (head < 0 || pos_of[head] < 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "molecule head is not in the ClusterHeads group", head); return h->err_code; }
+                index[(size_t)h->types[t].molpad0 + mm] = pos_of[head];
+            }
+        }
+        if ((rc = dev_upload(h, &h->d_sph_index, index))) return rc;
+        if ((rc = dev_alloc(h, &h->d_sph_dist, B * (size_t)s->n_membrane))) return rc;
+        if ((rc = dev_alloc(h, &h->d_sph_resp, B * (size_t)s->n_membrane))) return rc;
+        if ((rc = dev_alloc(h, &h->d_sph_upper, B * (size_t)s->n_membrane))) return rc;
     }
 
     // persistent pipeline: AA/CG, static normal, PBC, Global leaflets on every analysed frame, no geometry / maps

@@ -61,9 +61,10 @@ enum {
     GORDER_LEAFLET_LOCAL = 2,
     GORDER_LEAFLET_INDIVIDUAL = 3,
     GORDER_LEAFLET_MANUAL = 4,
-    /* spherical clustering (spherical_clustering.rs:36-275; `membrane` holds the ClusterHeads group).  Restated in the
-     * oracle; the device kernel is SURVEY.md §8f rank 2 -- until then gorder_gpu_create refuses it and the host passes
-     * the table with GORDER_LEAFLET_MANUAL. */
+    /* spherical clustering (spherical_clustering.rs:36-275; `membrane` holds the ClusterHeads group, every analysed
+     * molecule's head must be in it).  Restated in the oracle; the device kernels (csrc/gorder_spherical.cuh, SURVEY.md §8f
+     * rank 2) have not run on a GPU yet: gorder_gpu_create refuses the mode unless GORDER_EXPERIMENTAL_SPHERICAL is set in
+     * the environment; until they are verified the host passes the table with GORDER_LEAFLET_MANUAL. */
     GORDER_LEAFLET_SPHERICAL = 5
 };
 

@@ -446,9 +446,10 @@ def test_spherical_leaflets_on_a_vesicle():
         assert raw.count[0].tolist() == [len(heads), int((is_outer ^ flip).sum()), int((~(is_outer ^ flip)).sum())]
 
 
-def test_engine_refuses_spherical_clustering_for_now():
-    """No silent fallback: the device has no spherical-clustering kernel yet (include/gorder_b200.h)."""
+def test_engine_refuses_spherical_clustering_for_now(monkeypatch):
+    """No silent fallback: the device kernel (gorder_spherical.cuh) is experimental and opt-in (include/gorder_b200.h)."""
     from gorder_b200 import SystemTopology
+    monkeypatch.delenv("GORDER_EXPERIMENTAL_SPHERICAL", raising=False)
     mt = abi.MolType(name="LIP", mol_base=np.array([0, 2]), bond_rel=[(0, 1)], head_rel=0)
     setup = abi.EngineSetup(kind=abi.KIND_CG, n_atoms=4, moltypes=[mt], leaflet_mode=abi.LEAFLET_SPHERICAL, membrane=np.array([0, 2]))
     with pytest.raises(abi.GorderError) as e:
