@@ -669,8 +669,9 @@ void gorder_gpu_destroy(GorderHandle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-    for (void *p : h->owned) cudaFree(p);
+    if (h->stream_pre) cudaStreamSynchronize(h->stream_pre);
     if (h->stream_post) cudaStreamSynchronize(h->stream_post);
+    for (void *p : h->owned) cudaFree(p);
     cudaFree(h->d_bsum); cudaFree(h->d_bcnt);
     cudaFree(h->d_leaf_collect); cudaFree(h->d_normals_collect); cudaFree(h->d_used_collect);
     for (int i = 0; i < 2; i++) {
@@ -690,7 +691,7 @@ void gorder_gpu_destroy(GorderHandle *h) {
     for (auto &e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    if (h->stream_pre) { cudaStreamSynchronize(h->stream_pre); cudaStreamDestroy(h->stream_pre); }
+    if (h->stream_pre) cudaStreamDestroy(h->stream_pre);
     if (h->stream_post) cudaStreamDestroy(h->stream_post);
     for (int i = 0; i < 2; i++) {
         if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
