@@ -149,7 +149,8 @@ struct GorderHandle {
     SegList seg_membrane[3], seg_geom[3];          // per axis
     // spherical-clustering leaflets (experimental, gorder_spherical.cuh)
     bool spherical = false;
-    float *d_sph_dist = nullptr, *d_sph_resp = nullptr;   // [max_batch][n_membrane]
+    float *d_sph_scratch = nullptr;                       // [max_batch][kSphArrays][sph_pad]
+    int sph_pad = 0;                                      // n_membrane rounded up to 4 floats
     unsigned char *d_sph_upper = nullptr;                 // [max_batch][n_membrane]
     int *d_sph_index = nullptr;                           // [n_molpad] position of the molecule's head in the ClusterHeads group
     SegList seg_left;                              // leaflet-axis runs of the membrane atoms the bond kernel does not count (SPEC)
@@ -495,7 +496,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         if (h->spherical) {   // experimental (gorder_spherical.cuh)
             int rc = run_group_center(h, sp, h->seg_membrane, h->s.n_membrane, 7, d_planes, da, dl_assign, n_assign);
             if (rc) return rc;
-            spherical_cluster_kernel<<<n_assign, kSphThreads, 0, sp>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_sph_dist, h->d_sph_resp, h->d_sph_upper);
+            spherical_cluster_kernel<<<n_assign, kSphThreads, 0, sp>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_sph_scratch, h->sph_pad, h->d_sph_upper);
             spherical_assign_kernel<<<grid, 256, 0, sp>>>(h->view, h->d_molpad_type, h->d_sph_index, h->d_sph_upper, h->d_leaf_rows);
             h->n_launches++;
         } else
@@ -877,6 +878,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     long long mb = s->max_batch_frames > 0 ? s->max_batch_frames : (long long)((512ull << 20) / std::max<size_t>(frame_bytes, 1));
     mb = std::max<long long>(1, std::min<long long>(mb, s->normal_mode == GORDER_NORMAL_DYNAMIC ? 32 : 4096));
     if (s->leaflet_mode == GORDER_LEAFLET_LOCAL && s->handle_pbc) mb = std::min<long long>(mb, 32);   // per-frame cell list of the membrane atoms
+    if (h->spherical) mb = std::min<long long>(mb, 256);   // per-frame scratch of the mixture fit
     h->max_batch = (int)mb;
 
     // ---- device tables ---------------------------------------------------------------------------
@@ -1095,8 +1097,8 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
             }
         }
         if ((rc = dev_upload(h, &h->d_sph_index, index))) return rc;
-        if ((rc = dev_alloc(h, &h->d_sph_dist, B * (size_t)s->n_membrane))) return rc;
-        if ((rc = dev_alloc(h, &h->d_sph_resp, B * (size_t)s->n_membrane))) return rc;
+        h->sph_pad = round_up(s->n_membrane, 4);
+        if ((rc = dev_alloc(h, &h->d_sph_scratch, B * (size_t)kSphArrays * (size_t)h->sph_pad))) return rc;
         if ((rc = dev_alloc(h, &h->d_sph_upper, B * (size_t)s->n_membrane))) return rc;
     }
 

@@ -3,15 +3,23 @@
 // EXPERIMENTAL: written after the last GPU session of round 1 and not yet run on a device.  gorder_gpu_create refuses
 // GORDER_LEAFLET_SPHERICAL unless GORDER_EXPERIMENTAL_SPHERICAL is set; tests/test_gpu_spherical.py is skipped without it.
 //
-// Per assignment frame, one CTA of 1024 threads:
+// Per assignment frame, one CTA:
 //   distances of the ClusterHeads group (GorderSetup.membrane) from its PBC-aware centre (run_group_center, 3 axes),
 //   initial means = the 25th / 75th percentile (exact order statistics by a 4-pass radix select on the float bits),
-//   initial variances = the sample variance, then <= 50 EM iterations of a two-component 1-D Gaussian mixture
-//   (E step + log-likelihood, means, variances: three block reductions per iteration), r < 0.5 -> cluster 1,
-//   the cluster farther from the centre is the upper (outer) leaflet.
-// The reference folds its sums sequentially in f32; the block reductions here run in f64.  The responsibilities
-// therefore agree to ~1e-6, not in bits: an assignment can only differ for a head with r within that of 0.5, i.e.
-// one that sits between the two leaflets of the vesicle.
+//   initial variances = the sample variance, then <= 50 EM iterations of a two-component 1-D Gaussian mixture,
+//   r < 0.5 -> cluster 1, the cluster farther from the centre is the upper (outer) leaflet.
+//
+// The reference folds every sum SEQUENTIALLY in f32, and over 1e5 heads such a fold carries a relative error of ~1e-3
+// that decides at which iteration |d avg_ll| < 1e-4 stops the fit: a tree or f64 reduction lands on a different
+// iteration and, for leaflets whose distance distributions overlap (gap < ~5 sigma), on different assignments (measured
+// with a numpy model of both variants against the oracle: up to 98 of 85 027 heads; with sequential folds: none, max
+// |dr| 4e-5 with +-1 ulp of noise on every log / exp).  So the element-wise work of a phase runs on all threads and leaves
+// its terms in scratch arrays, and each fold is done by ONE lane in the reference's order -- two or three folds of a
+// phase on lanes of different warps at once.  A fold is bound by the latency of the dependent FADDs (~0.2 ms for 1e5
+// heads), a CTA therefore keeps its SM almost idle: throughput comes from the frames of a batch running side by side
+// (256 threads per CTA, several CTAs per SM).
+// Arithmetic: the oracle's operation order with explicit _rn intrinsics (no FMA contraction); logf / expf are CUDA's
+// (<= 2 ulp from libm's).
 #pragma once
 #include "gorder_kernels.cuh"
 
@@ -19,29 +27,33 @@ namespace gorder {
 
 constexpr int kGmmMaxIterations = 50;      // spherical_clustering.rs:23
 constexpr float kGmmTolerance = 1e-4f;     // spherical_clustering.rs:26
-constexpr int kSphThreads = 1024;
+constexpr int kSphThreads = 256;
+constexpr int kSphArrays = 5;              // dist, resp, and three term arrays per frame
 
-// sums of up to four doubles over the CTA, result in every thread
-__device__ __forceinline__ void block_sum4(double (&x)[4], double (*s_red)[32]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-        for (int o = 16; o > 0; o >>= 1) x[k] += __shfl_xor_sync(0xffffffffu, x[k], o);
-    __syncthreads();   // s_red may still be read from the previous call
-    if (lane == 0)
-#pragma unroll
-        for (int k = 0; k < 4; k++) s_red[k][warp] = x[k];
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        double t = 0.0;
-        for (int w = 0; w < kSphThreads / 32; w++) t += s_red[k][w];   // fixed order: deterministic
-        x[k] = t;
+// sum of a[0..n) in index order, a 16-byte aligned; the array was written by this CTA (plain loads)
+__device__ __forceinline__ float seq_sum(const float *a, int n) {
+    float s = 0.0f;
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const float4 q = *reinterpret_cast<const float4 *>(a + i);
+        s = __fadd_rn(s, q.x); s = __fadd_rn(s, q.y); s = __fadd_rn(s, q.z); s = __fadd_rn(s, q.w);
     }
+    for (; i < n; i++) s = __fadd_rn(s, a[i]);
+    return s;
+}
+// folds of up to three arrays at once (lane 0 of warps 0..2); every thread returns with s_out[] valid
+__device__ __forceinline__ void seq_sums(const float *a0, const float *a1, const float *a2, int n, float *s_out) {
+    __syncthreads();   // the arrays were written by all threads; s_out may still be read from the previous call
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && warp < 3) {
+        const float *a = warp == 0 ? a0 : (warp == 1 ? a1 : a2);
+        if (a) s_out[warp] = seq_sum(a, n);
+    }
+    __syncthreads();
 }
 
 // k-th smallest (0-based) of n non-negative floats: radix select over the bit patterns, most significant byte first
-__device__ __forceinline__ float block_select(const float *__restrict__ d, int n, int k, unsigned *s_hist, int *s_pick) {
+__device__ __forceinline__ float block_select(const float *d, int n, int k, unsigned *s_hist, int *s_pick) {
     unsigned prefix = 0u, mask = 0u;
     for (int shift = 24; shift >= 0; shift -= 8) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0u;
@@ -66,17 +78,18 @@ __device__ __forceinline__ float block_select(const float *__restrict__ d, int n
     return __uint_as_float(prefix);
 }
 
-__device__ __forceinline__ float gmm_log_gaussian(float x, float mean, float variance) {   // spherical_clustering.rs:103-107
-    const float diff = x - mean;
-    return -0.5f * (logf(2.0f * CUDART_PI_F) + logf(variance) + __fdiv_rn(__fmul_rn(diff, diff), variance));
+// log_gaussian (spherical_clustering.rs:103-107) with ln(2 pi) and ln(variance) hoisted
+__device__ __forceinline__ float gmm_log_gaussian(float x, float mean, float variance, float ln_2pi, float ln_var) {
+    const float diff = __fsub_rn(x, mean);
+    return __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(ln_2pi, ln_var), __fdiv_rn(__fmul_rn(diff, diff), variance)));
 }
 
-// grid (n_assign), block kSphThreads.  dist / resp: [n_assign][n] scratch; cl_upper: [n_assign][n] result (1 = upper).
+// grid (n_assign), block kSphThreads.  scratch: [n_assign][kSphArrays][n_pad] floats (n_pad = n rounded up to 4);
+// cl_upper: [n_assign][n] result (1 = upper).
 __global__ void __launch_bounds__(kSphThreads) spherical_cluster_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                                        const int *__restrict__ frame_list, const float *__restrict__ center,
-                                                                       float *__restrict__ dist_all, float *__restrict__ resp_all,
-                                                                       unsigned char *__restrict__ cl_upper) {
-    __shared__ double s_red[4][32];
+                                                                       float *scratch, int n_pad, unsigned char *__restrict__ cl_upper) {
+    __shared__ float s_sum[3];
     __shared__ unsigned s_hist[256];
     __shared__ int s_pick[2];
     const int ai = blockIdx.x, f = frame_list[ai], n = v.membrane.n;
@@ -85,79 +98,73 @@ __global__ void __launch_bounds__(kSphThreads) spherical_cluster_kernel(DeviceVi
     const float cx = center[3 * ai], cy = center[3 * ai + 1], cz = center[3 * ai + 2];
     if ((cx != cx || cy != cy || cz != cz) && threadIdx.x == 0) raise_error(v, GORDER_ERR_INVALID_GLOBAL_CENTER, a.frame_index);
     const float *fr = planes + (size_t)f * v.frame_floats;
-    float *dist = dist_all + (size_t)ai * n, *resp = resp_all + (size_t)ai * n;
+    float *dist = scratch + (size_t)ai * kSphArrays * n_pad, *resp = dist + n_pad, *t0 = resp + n_pad, *t1 = t0 + n_pad, *t2 = t1 + n_pad;
     const float n_f = (float)n;
 
-    // distances from the centre (PBCHandler::distance, pbc.rs:354; Dimension::XYZ) and their mean
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // distances from the centre (PBCHandler::distance, pbc.rs:354; Dimension::XYZ): atom - centre, minimum image
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int off = v.membrane.off[i];
         const size_t cs = (size_t)v.membrane.cs[i];
         float dx = __fsub_rn(fr[off], cx), dy = __fsub_rn(fr[off + cs], cy), dz = __fsub_rn(fr[off + 2 * cs], cz);
         if (pbc) { dx = min_image(dx, a.L[0], a.half[0]); dy = min_image(dy, a.L[1], a.half[1]); dz = min_image(dz, a.L[2], a.half[2]); }
-        const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-        dist[i] = d;
-        acc[0] += (double)d;
+        dist[i] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     }
-    block_sum4(acc, s_red);   // (also orders the writes of dist before the reads below)
-    const float gmean = (float)acc[0] / n_f;
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float t = dist[i] - gmean; acc[0] += (double)(t * t); }
-    block_sum4(acc, s_red);
-    float gvar = (float)acc[0] / (n_f - 1.0f);
+    // initialize_params (spherical_clustering.rs:116-136): sample mean and variance, quartiles
+    seq_sums(dist, nullptr, nullptr, n, s_sum);
+    const float gmean = __fdiv_rn(s_sum[0], n_f);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float t = __fsub_rn(dist[i], gmean); t0[i] = __fmul_rn(t, t); }
+    seq_sums(t0, nullptr, nullptr, n, s_sum);
+    float gvar = __fdiv_rn(s_sum[0], __fsub_rn(n_f, 1.0f));
     if (!isfinite(gvar) || gvar <= 0.0f) gvar = 1.0f;
-
-    // initialize_params (spherical_clustering.rs:116-136)
     const float var_floor = 1e-6f, weight_floor = 1e-4f;
     float mean_a = block_select(dist, n, n / 4, s_hist, s_pick);
     float mean_b = block_select(dist, n, (3 * n) / 4, s_hist, s_pick);
     float weight_a = 0.5f, var_a = fmaxf(gvar, var_floor), var_b = var_a;
     float prev_avg_ll = -CUDART_INF_F;
     for (int i = threadIdx.x; i < n; i += blockDim.x) resp[i] = 0.5f;
+    const float ln_2pi = logf(__fmul_rn(2.0f, CUDART_PI_F));
 
     // fit_gmm_1d_two_components (spherical_clustering.rs:138-237)
     for (int it = 0; it < kGmmMaxIterations; it++) {
-        const float lwa = logf(weight_a), lwb = logf(1.0f - weight_a);
-        acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+        const float lwa = logf(weight_a), lwb = logf(__fsub_rn(1.0f, weight_a)), lva = logf(var_a), lvb = logf(var_b);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const float x = dist[i];
-            const float ja = lwa + gmm_log_gaussian(x, mean_a, var_a), jb = lwb + gmm_log_gaussian(x, mean_b, var_b);
+            const float ja = __fadd_rn(lwa, gmm_log_gaussian(x, mean_a, var_a, ln_2pi, lva));
+            const float jb = __fadd_rn(lwb, gmm_log_gaussian(x, mean_b, var_b, ln_2pi, lvb));
             const float m = fmaxf(ja, jb);
-            const float log_px = m + logf(expf(ja - m) + expf(jb - m));
-            const float r = expf(ja - log_px);
-            resp[i] = r;
-            acc[0] += (double)log_px; acc[1] += (double)r;
+            const float log_px = __fadd_rn(m, logf(__fadd_rn(expf(__fsub_rn(ja, m)), expf(__fsub_rn(jb, m)))));
+            t0[i] = log_px;
+            resp[i] = expf(__fsub_rn(ja, log_px));
         }
-        block_sum4(acc, s_red);
-        const float avg_ll = (float)acc[0] / n_f;
-        if (fabsf(avg_ll - prev_avg_ll) < kGmmTolerance) break;
+        seq_sums(t0, nullptr, nullptr, n, s_sum);                 // loglik_sum
+        const float avg_ll = __fdiv_rn(s_sum[0], n_f);
+        if (fabsf(__fsub_rn(avg_ll, prev_avg_ll)) < kGmmTolerance) break;   // (same value in every thread)
         prev_avg_ll = avg_ll;
-        float sum_a = (float)acc[1], sum_b = n_f - sum_a;
-        sum_a = fmaxf(sum_a, 1e-6f); sum_b = fmaxf(sum_b, 1e-6f);
-        weight_a = fminf(fmaxf(sum_a / n_f, weight_floor), 1.0f - weight_floor);
-        acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const float x = dist[i], r = resp[i];
-            acc[0] += (double)(r * x); acc[1] += (double)((1.0f - r) * x);
+            t1[i] = __fmul_rn(r, x); t2[i] = __fmul_rn(__fsub_rn(1.0f, r), x);
         }
-        block_sum4(acc, s_red);
-        mean_a = (float)acc[0] / sum_a; mean_b = (float)acc[1] / sum_b;
-        acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+        seq_sums(resp, t1, t2, n, s_sum);                         // sum of the responsibilities, numerators of the means
+        float sum_a = s_sum[0], sum_b = __fsub_rn(n_f, sum_a);
+        sum_a = fmaxf(sum_a, 1e-6f); sum_b = fmaxf(sum_b, 1e-6f);
+        weight_a = fminf(fmaxf(__fdiv_rn(sum_a, n_f), weight_floor), __fsub_rn(1.0f, weight_floor));
+        mean_a = __fdiv_rn(s_sum[1], sum_a); mean_b = __fdiv_rn(s_sum[2], sum_b);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const float x = dist[i], r = resp[i], da = x - mean_a, db = x - mean_b;
-            acc[0] += (double)(r * da * da); acc[1] += (double)((1.0f - r) * db * db);
+            const float x = dist[i], r = resp[i], da = __fsub_rn(x, mean_a), db = __fsub_rn(x, mean_b);
+            t1[i] = __fmul_rn(__fmul_rn(r, da), da); t2[i] = __fmul_rn(__fmul_rn(__fsub_rn(1.0f, r), db), db);
         }
-        block_sum4(acc, s_red);
-        var_a = fmaxf((float)acc[0] / sum_a, var_floor); var_b = fmaxf((float)acc[1] / sum_b, var_floor);
+        seq_sums(t1, t2, nullptr, n, s_sum);
+        var_a = fmaxf(__fdiv_rn(s_sum[0], sum_a), var_floor); var_b = fmaxf(__fdiv_rn(s_sum[1], sum_b), var_floor);
     }
 
-    // Clusters::from_responsibilities (spherical_clustering.rs:239-272)
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+    // Clusters::from_responsibilities (spherical_clustering.rs:239-272): adding 0 leaves a sequential f32 sum unchanged
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        if (resp[i] < 0.5f) { acc[0] += 1.0; acc[1] += (double)dist[i]; } else { acc[2] += 1.0; acc[3] += (double)dist[i]; }
+        const bool first = resp[i] < 0.5f;
+        t0[i] = first ? 1.0f : 0.0f; t1[i] = first ? dist[i] : 0.0f; t2[i] = first ? 0.0f : dist[i];
     }
-    block_sum4(acc, s_red);
-    const bool first_is_upper = ((float)acc[1] / (float)acc[0]) > ((float)acc[3] / (float)acc[2]);   // NaN (empty cluster) compares false
+    seq_sums(t0, t1, t2, n, s_sum);   // (the count is exact in f32 below 2^24 heads)
+    const float n1 = s_sum[0], n2 = __fsub_rn(n_f, n1);
+    const bool first_is_upper = __fdiv_rn(s_sum[1], n1) > __fdiv_rn(s_sum[2], n2);   // NaN (empty cluster) compares false
     for (int i = threadIdx.x; i < n; i += blockDim.x) cl_upper[(size_t)ai * n + i] = ((resp[i] < 0.5f) == first_is_upper) ? 1 : 0;
 }
 
