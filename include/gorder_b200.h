@@ -255,7 +255,11 @@ int gorder_gpu_create(const GorderSetup *setup, GorderHandle **out);
  *               (ordinal of the trajectory frame since `begin`), a multiple of `step`, strictly
  *               increasing across calls.
  * Returns when the batch has been queued and the input buffers may be reused. Errors detected on
- * the device are reported by a later submit or by finish (first error wins, as in the reference). */
+ * the device are reported by a later submit or by finish (first error wins, as in the reference).
+ * Thread safety: every entry point that takes a handle locks it, so several host threads (the reference's decode
+ * threads) may share one handle; because frame_index must increase, they hand their batches over in trajectory order
+ * (or each thread drives its own handle over its own frame range and the handles are combined like GPUs, see
+ * gorder_gpu_accumulator_block). */
 int gorder_gpu_submit(GorderHandle *h, const float *xyz, const float *box,
                       const int64_t *frame_index, int32_t n_frames);
 
