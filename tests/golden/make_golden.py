@@ -408,6 +408,8 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         add("leaflets_only_upper", "cg_order_leaflets_only_upper.yaml", tul, leaflet_freq_kind=abi.FREQ_ONCE, **glob)
         add("leaflets_only_upper_individual", "cg_order_leaflets_only_upper.yaml", tul, heads=heads, methyls=methyls,
             leaflet_mode=abi.LEAFLET_INDIVIDUAL, leaflet_freq_kind=abi.FREQ_ONCE)
+        add("leaflets_only_upper_local", "cg_order_leaflets_only_upper.yaml", tul, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_LOCAL,
+            leaflet_radius=2.5, leaflet_freq_kind=abi.FREQ_ONCE)
         g1, g2 = gsave
         # order maps of the POPC B-chain bonds, bin 1 x 1 nm, min_samples 10 (tests_cg.rs:1040-1180)
         sbox = sbox_cg
@@ -428,6 +430,17 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
         add_maps("maps_basic", "cg_order_small.yaml", "ordermaps_cg", (1.0, 1.0), 10)
         add_maps("maps_leaflets", "cg_order_leaflets_small.yaml", "ordermaps_cg", (1.0, 1.0), 10, tul, **glob)
         g1, g2 = gsave
+        # bonds redefined by a bond file: a few lipids lose / gain a bond and become molecule types of their own, named
+        # POPE1, POPG1, POPG2, POPE2, POPE3 (classify.rs:262-294): tests_cg.rs:382-406
+        st2 = fixtures.read_gro(os.path.join(FILES, gro))
+        fixtures.read_bnd(os.path.join(FILES, "cg_redefined.bnd"), st2)
+        cst2, keep2 = fixtures.compact(st2, mem)
+        assert np.array_equal(keep, keep2)
+        doc = yaml.safe_load(open(os.path.join(FILES, "cg_order_redefined_bonds.yaml")))
+        all2 = np.arange(cst2.n_atoms)
+        setup2 = fixtures.build_bond_setup(cst2, kind, all2, all2)
+        cases["redefined_bonds"] = dict(setup=setup2.to_dict(), expected=flatten_yaml(doc, ("total",)), keys=["total"],
+                                        frames=list(range(xyz.shape[0])), source="cg_order_redefined_bonds.yaml")
         # Individual leaflets assigned once + dynamic normals (PO4, 2 nm): tests_cg.rs:3356-3388
         add("leaflets_dynamic", "cg_order_leaflets_dynamic.yaml", tul, heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL,
             leaflet_freq_kind=abi.FREQ_ONCE, normal_heads=heads, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0)

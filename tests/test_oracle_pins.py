@@ -154,7 +154,8 @@ UA_YAML_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_lo
 # (tests/test_gpu_golden.py) once they have run on the device
 UA_YAML_CASES_NEW = ["basic_saturated", "basic_unsaturated", "leaflets_flipped"]
 AA_FULL_CASES_NEW = ["error_limit", "error_leaflets_limit", "sphere_static"]
-CG_FULL_CASES_NEW = ["error_limit", "error_leaflets_limit", "begin_end", "leaflets_only_upper", "leaflets_only_upper_individual"]
+CG_FULL_CASES_NEW = ["error_limit", "error_leaflets_limit", "begin_end", "leaflets_only_upper", "leaflets_only_upper_individual",
+                     "leaflets_only_upper_local", "redefined_bonds"]
 
 
 @pytest.mark.parametrize("name", UA_YAML_CASES + UA_YAML_CASES_NEW)
