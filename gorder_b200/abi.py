@@ -298,6 +298,10 @@ class EngineSetup:
                       ua_kind=[int(x) for x in m.ua_kind], ua_rel=[[int(x) for x in r] for r in m.ua_rel], head_rel=int(m.head_rel),
                       methyl_rel=[int(x) for x in m.methyl_rel], normal_head_rel=int(m.normal_head_rel),
                       bond_names=list(m.bond_names))
+            if m.manual_leaflets is not None:
+                md["manual_leaflets"] = np.asarray(m.manual_leaflets, np.uint8).reshape(-1, m.n_molecules).tolist()
+            if m.manual_normals is not None:
+                md["manual_normals"] = np.asarray(m.manual_normals, np.float32).reshape(-1, m.n_molecules, 3).tolist()
             d["moltypes"].append(md)
         return d
 

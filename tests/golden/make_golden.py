@@ -152,6 +152,12 @@ def ua_golden():
     # assignment with `flip`
     flip = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL, leaflet_flip=True)
     add("leaflets_flipped", flip, "ua_order_leaflets_flipped.yaml", keys=("total", "upper", "lower"))
+    # the exported normals read back as manual normals (ManualMembraneNormal, normal.rs:259-298; the reference's own
+    # round trip: tests_aa.rs:4964-5022) reproduce the dynamic-normal result to the 6 printed decimals of the file
+    man = fixtures.build_ua_setup(cst, sat, unsat, normal_mode=abi.NORMAL_MANUAL)
+    for mt in man.moltypes:
+        mt.manual_normals = np.array(ndoc[mt.name], np.float32)
+    add("manual_normals", man, "ua_order_dynamic_normals.yaml")
     # leaflet export, Once (bit-exact fixture)
     once = fixtures.build_ua_setup(cst, sat, unsat, heads=heads, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL,
                                    leaflet_freq_kind=abi.FREQ_ONCE, collect_leaflets=True)
@@ -296,6 +302,14 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
     add("leaflets_once", f"{pre}_order_leaflets.yaml", tul, leaflet_freq_kind=abi.FREQ_ONCE, **glob)
     add("error", f"{pre}_order_error.yaml", n_blocks=5, timewise=True)
     add("error_leaflets", f"{pre}_order_error_leaflets.yaml", tul, n_blocks=5, timewise=True, **glob)
+
+    # leaflets read from files (ManualClassification, leaflets.rs:816-874; 1 / Upper = upper leaflet)
+    def add_manual(case, table_file, yaml_file, frames=None, **kw):
+        add(case, yaml_file, tul, frames=frames, leaflet_mode=abi.LEAFLET_MANUAL, **kw)
+        tab = yaml.safe_load(open(os.path.join(FILES, "inputs", "leaflets_files", table_file)))
+        for md in cases[case]["setup"]["moltypes"]:
+            md["manual_leaflets"] = [[1 if x in (1, "Upper", "upper") else 0 for x in row] for row in tab[md["name"]]]
+
     if kind == abi.KIND_AA:
         # begin 450 200 ps, end 450 400 ps (, step 3): tests_aa.rs:1202-1232, 1398-1423
         sel = [i for i, t in enumerate(time) if 450200.0 <= t <= 450400.0]
@@ -329,6 +343,15 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
                    leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=5)
         add_export("export_every1_individual", "aa_leaflets_every1.yaml", heads=heads, methyls=methyls, leaflet_mode=abi.LEAFLET_INDIVIDUAL)
         add_export("export_every1_global", "aa_leaflets_every1.yaml", **glob)
+        # leaflets read from files: tests_aa.rs:3619-3893
+        add_manual("manual_once", "pcpepg_once.yaml", "aa_order_leaflets.yaml", leaflet_freq_kind=abi.FREQ_ONCE)
+        add_manual("manual_every10", "pcpepg_every10.yaml", "aa_order_leaflets.yaml", leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=10)
+        add_manual("manual_every", "pcpepg_every.yaml", "aa_order_leaflets.yaml", leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=1)
+        # every(2) x step 5 = every 10th trajectory frame (leaflets.rs:261-262)
+        add_manual("manual_every10_stepping", "pcpepg_every10.yaml", "aa_order_step.yaml", frames=list(range(0, xyz.shape[0], 5)), step=5,
+                   leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=10)
+        add_manual("manual_begin_end_step", "pcpepg_every_begin_end_step.yaml", "aa_order_begin_end_step.yaml", frames=sel[::3], step=3,
+                   leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=3)
         # geometry selections: reference = centre of residue 1 (PBC centre of geometry of a group: the refined Bai-Breen
         # estimate, otherwise pinned only through leaflets), box centre, fixed point; inverted: tests_aa.rs:3183-3345, 3508-3615
         inf = (float("-inf"), float("inf"))
@@ -396,6 +419,12 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
             geom_ref_point=(3.0, 3.0, 3.0), geom_dims=(4.0,) + inf, geom_axis=abi.AXIS_Z, geom_invert=True, structure_box=sb)
         add("limit", "cg_order_limit.yaml", min_samples=5000)
         add("leaflets_limit", "cg_order_leaflets_limit.yaml", tul, min_samples=2000, **glob)
+        # leaflets read from files: tests_cg.rs:2719-2876; a table with too few rows (every 16 frames, 6 rows): tests_cg.rs:3054-3074
+        add_manual("manual_once", "cg_once.yaml", "cg_order_leaflets.yaml", leaflet_freq_kind=abi.FREQ_ONCE)
+        add_manual("manual_every20", "cg_every20.yaml", "cg_order_leaflets.yaml", leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=20)
+        add_manual("manual_every", "cg_every.yaml", "cg_order_leaflets.yaml", leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=1)
+        add_manual("manual_not_enough_frames", "cg_every20.yaml", "cg_order_leaflets.yaml", leaflet_freq_kind=abi.FREQ_EVERY, leaflet_freq=16)
+        cases["manual_not_enough_frames"].update(expect_error=abi.ERR_MANUAL_LEAFLET_FRAME)
         add("error_limit", "cg_order_error_limit.yaml", n_blocks=5, timewise=True, min_samples=5000)                     # tests_cg.rs:1612-1641
         add("error_leaflets_limit", "cg_order_error_leaflets_limit.yaml", tul, n_blocks=5, timewise=True, min_samples=2000, **glob)   # :1644-1690
         # begin 352 000 ps, end 358 000 ps: 61 frames (tests_cg.rs:893-915)

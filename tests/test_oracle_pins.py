@@ -152,10 +152,11 @@ UA_YAML_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_lo
 
 # cases added after the last GPU session of round 1: pinned with the oracle here, to be added to the GPU lists
 # (tests/test_gpu_golden.py) once they have run on the device
-UA_YAML_CASES_NEW = ["basic_saturated", "basic_unsaturated", "leaflets_flipped"]
-AA_FULL_CASES_NEW = ["error_limit", "error_leaflets_limit", "sphere_static"]
+UA_YAML_CASES_NEW = ["basic_saturated", "basic_unsaturated", "leaflets_flipped", "manual_normals"]
+AA_FULL_CASES_NEW = ["error_limit", "error_leaflets_limit", "sphere_static", "manual_once", "manual_every10", "manual_every",
+                     "manual_every10_stepping", "manual_begin_end_step"]
 CG_FULL_CASES_NEW = ["error_limit", "error_leaflets_limit", "begin_end", "leaflets_only_upper", "leaflets_only_upper_individual",
-                     "leaflets_only_upper_local", "redefined_bonds"]
+                     "leaflets_only_upper_local", "redefined_bonds", "manual_once", "manual_every20", "manual_every", "manual_not_enough_frames"]
 
 
 @pytest.mark.parametrize("name", UA_YAML_CASES + UA_YAML_CASES_NEW)
@@ -320,6 +321,13 @@ def check_leaflet_export(raw, setup, case):
 def _oracle_full(which, name):
     setup, xyz, box, fi, case = gc.full_case(which, name)
     o = oracle.Oracle(setup, n_threads=8)
+    if "expect_error" in case:   # e.g. "could not get leaflet assignment for frame" (leaflets.rs:816-874)
+        with pytest.raises(abi.GorderError) as e:
+            o.analyze_frames(xyz, box, fi)
+            o.finish()
+        o.close()
+        assert e.value.code == case["expect_error"]
+        return
     o.analyze_frames(xyz, box, fi)
     raw = o.finish()
     o.close()
