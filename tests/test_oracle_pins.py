@@ -151,7 +151,7 @@ UA_YAML_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_lo
 
 
 # cases added after the last GPU session of round 1: pinned with the oracle here, to be added to the GPU lists
-# (tests/test_gpu_golden.py) once they have run on the device
+# (tests/test_gpu_golden.py) once they have run on the device: tests/test_gpu_golden_new.py (opt-in) does that
 UA_YAML_CASES_NEW = ["basic_saturated", "basic_unsaturated", "leaflets_flipped", "manual_normals"]
 AA_FULL_CASES_NEW = ["error_limit", "error_leaflets_limit", "sphere_static", "manual_once", "manual_every10", "manual_every",
                      "manual_every10_stepping", "manual_begin_end_step"]
