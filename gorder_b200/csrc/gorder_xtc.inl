@@ -40,22 +40,44 @@ struct Frame {
     int minint[3], maxint[3];
 };
 
-// MSB-first bit reader over [p, end) with a 64-bit window; reads past `end` yield zeros
+// MSB-first bit reader over [p, end): one unaligned big-endian 64-bit load per field while at least 16 bytes remain,
+// byte-wise near the end of the stream; reads past `end` yield zeros
 struct BitIn {
     const uint8_t *p, *end;
-    uint64_t acc = 0;
-    int n = 0;
-    inline void fill() {
-        while (n <= 56) { acc = (acc << 8) | (p < end ? *p : 0); p++; n += 8; }
+    uint64_t pos = 0;   // bit offset from p
+    inline bool roomy() const { return (pos >> 3) + 16 <= (uint64_t)(end - p); }
+    inline uint64_t window() const {   // the >= 57 bits that follow pos, left-aligned
+        uint64_t w;
+        memcpy(&w, p + (pos >> 3), 8);
+        return __builtin_bswap64(w) << (pos & 7);
+    }
+    inline uint32_t get_slow(int bits) {
+        uint64_t v = 0;
+        for (int i = 0; i < bits; i++) {
+            const uint64_t at = pos + (uint64_t)i;
+            const uint8_t *b = p + (at >> 3);
+            v = (v << 1) | (uint64_t)(b < end ? (*b >> (7 - (at & 7))) & 1 : 0);
+        }
+        pos += (uint64_t)bits;
+        return (uint32_t)v;
     }
     inline uint32_t get(int bits) {   // bits <= 32
         if (bits == 0) return 0;
-        if (n < bits) fill();
-        n -= bits;
-        return (uint32_t)((acc >> n) & ((bits == 32) ? 0xffffffffull : ((1ull << bits) - 1ull)));
+        if (!roomy()) return get_slow(bits);
+        const uint32_t v = (uint32_t)(window() >> (64 - bits));
+        pos += (uint64_t)bits;
+        return v;
     }
     // the mixed-radix number of a triple: its bytes arrive least significant first, the last one may be partial
     template <typename W> inline W get_le(int bits) {
+        if (sizeof(W) == 8 && bits <= 56 && bits > 0 && roomy()) {
+            const uint64_t w = window();
+            const int full = bits >> 3, rem = bits & 7;
+            uint64_t v = full ? (__builtin_bswap64(w) & (full == 8 ? ~0ull : ((1ull << (8 * full)) - 1ull))) : 0ull;
+            if (rem) v |= ((w << (8 * full)) >> (64 - rem)) << (8 * full);
+            pos += (uint64_t)bits;
+            return (W)v;
+        }
         W v = 0;
         int shift = 0;
         while (bits > 8) { v |= (W)get(8) << shift; shift += 8; bits -= 8; }
@@ -79,6 +101,33 @@ inline void unpack3(W v, const unsigned s[3], int out[3]) {
     out[0] = (int)v;
 }
 
+// v / d by one 64 x 64 -> 128 bit multiplication with m = ceil(2^64 / d): exact whenever v * d < 2^64
+struct FastDiv {
+    uint64_t m = 0;
+    unsigned d = 1;
+    bool ok = false;
+    inline void set(unsigned div, int value_bits) {   // values are below 2^value_bits
+        d = div ? div : 1;
+        int db = 0;
+        while (db < 32 && (1ull << db) <= d) db++;
+        ok = d > 1 && value_bits + db < 64;
+        m = ok ? (uint64_t)((((unsigned __int128)1 << 64) + d - 1) / d) : 0;
+    }
+    inline uint64_t div(uint64_t v) const { return ok ? (uint64_t)(((unsigned __int128)v * m) >> 64) : v / d; }
+};
+inline void unpack3_fast(uint64_t v, const FastDiv &d1, const FastDiv &d2, int out[3]) {
+    const uint64_t q = d2.div(v);
+    out[2] = (int)(v - q * d2.d);
+    const uint64_t r = d1.div(q);
+    out[1] = (int)(q - r * d1.d);
+    out[0] = (int)r;
+}
+
+struct SmallDivs {   // the divisor of the small triples for every smallidx (the number has smallidx bits)
+    FastDiv d[sizeof(kMagic) / sizeof(kMagic[0])];
+    SmallDivs() { for (int i = 0; i <= kLastIdx; i++) d[i].set((unsigned)kMagic[i], i); }
+};
+
 // Decode one frame; emit(atom, x, y, z) is called for atoms 0 .. stop_after (inclusive) in order.
 template <typename Emit>
 int decode_frame(const uint8_t *base, const Frame &fr, int stop_after, Emit emit) {
@@ -99,16 +148,29 @@ int decode_frame(const uint8_t *base, const Frame &fr, int stop_after, Emit emit
     unsigned ssz[3] = {(unsigned)kMagic[smallidx], (unsigned)kMagic[smallidx], (unsigned)kMagic[smallidx]};
     const float inv = 1.0f / fr.precision;
     BitIn in{base + fr.payload, base + fr.payload + fr.nbytes};
+    static const SmallDivs kSmall;
+    FastDiv big1, big2;   // divisors of the large triple (per frame)
+    big1.set(sizeint[1], bitsize); big2.set(sizeint[2], bitsize);
+    const FastDiv *small = &kSmall.d[smallidx];
     int i = 0, run = 0, cur[3], prev[3];
     while (i <= last) {
         if (bitsize == 0) { cur[0] = (int)in.get((int)bitsint[0]); cur[1] = (int)in.get((int)bitsint[1]); cur[2] = (int)in.get((int)bitsint[2]); }
-        else if (bitsize <= 64) unpack3<uint64_t>(in.get_le<uint64_t>(bitsize), sizeint, cur);
+        else if (bitsize <= 64) unpack3_fast(in.get_le<uint64_t>(bitsize), big1, big2, cur);
         else unpack3<unsigned __int128>(in.get_le<unsigned __int128>(bitsize), sizeint, cur);
         cur[0] += fr.minint[0]; cur[1] += fr.minint[1]; cur[2] += fr.minint[2];
         prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
         int is_smaller = 0;
-        if (in.get(1)) {
-            run = (int)in.get(5);
+        bool flag;
+        if (in.roomy()) {   // flag and run length in one look
+            const uint32_t six = (uint32_t)(in.window() >> 58);
+            flag = (six & 32u) != 0;
+            if (flag) run = (int)(six & 31u);
+            in.pos += flag ? 6 : 1;
+        } else {
+            flag = in.get(1) != 0;
+            if (flag) run = (int)in.get(5);
+        }
+        if (flag) {
             is_smaller = run % 3;
             run -= is_smaller;
             is_smaller--;
@@ -116,7 +178,7 @@ int decode_frame(const uint8_t *base, const Frame &fr, int stop_after, Emit emit
         if (run > 0) {
             for (int k = 0; k < run; k += 3) {
                 int d[3];
-                if (smallidx <= 64) unpack3<uint64_t>(in.get_le<uint64_t>(smallidx), ssz, d);
+                if (smallidx <= 64) unpack3_fast(in.get_le<uint64_t>(smallidx), *small, *small, d);
                 else unpack3<unsigned __int128>(in.get_le<unsigned __int128>(smallidx), ssz, d);
                 int t[3] = {d[0] + prev[0] - smallnum, d[1] + prev[1] - smallnum, d[2] + prev[2] - smallnum};
                 if (i + (k == 0 ? 2 : 1) > n) return -1;
@@ -136,7 +198,7 @@ int decode_frame(const uint8_t *base, const Frame &fr, int stop_after, Emit emit
         if (smallidx < kFirstIdx || smallidx > kLastIdx) return -1;
         if (is_smaller < 0) { smallnum = smaller; smaller = smallidx > kFirstIdx ? kMagic[smallidx - 1] / 2 : 0; }
         else if (is_smaller > 0) { smaller = smallnum; smallnum = kMagic[smallidx] / 2; }
-        ssz[0] = ssz[1] = ssz[2] = (unsigned)kMagic[smallidx];
+        if (is_smaller) { ssz[0] = ssz[1] = ssz[2] = (unsigned)kMagic[smallidx]; small = &kSmall.d[smallidx]; }
     }
     return 0;
 }
