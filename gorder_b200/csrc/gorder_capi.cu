@@ -711,6 +711,23 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     h->extra = s->geom_kind != GORDER_GEOM_NONE || s->map_enabled;
     h->nvec = s->normal_mode != GORDER_NORMAL_STATIC;
     if (s->n_atoms <= 0 || s->n_moltypes < 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "bad n_atoms / n_moltypes"); return h->err_code; }
+    {   // enumerators and counts: a value outside its range would index past a 3-vector or skip every branch on the device
+        auto in = [](int v, int lo, int hi) { return v >= lo && v <= hi; };
+        const char *what = nullptr;
+        if (!in(s->kind, GORDER_KIND_AA, GORDER_KIND_UA)) what = "kind";
+        else if (!in(s->normal_mode, GORDER_NORMAL_STATIC, GORDER_NORMAL_MANUAL)) what = "normal_mode";
+        else if (!in(s->normal_axis, GORDER_AXIS_X, GORDER_AXIS_Z)) what = "normal_axis";
+        else if (!in(s->leaflet_axis, GORDER_AXIS_X, GORDER_AXIS_Z)) what = "leaflet_axis";
+        else if (!in(s->leaflet_freq_kind, GORDER_FREQ_EVERY, GORDER_FREQ_ONCE)) what = "leaflet_freq_kind";
+        else if (!in(s->geom_kind, GORDER_GEOM_NONE, GORDER_GEOM_SPHERE)) what = "geom_kind";
+        else if (!in(s->geom_ref_kind, GORDER_GEOMREF_POINT, GORDER_GEOMREF_BOX_CENTER)) what = "geom_ref_kind";
+        else if (!in(s->geom_axis, GORDER_AXIS_X, GORDER_AXIS_Z)) what = "geom_axis";
+        else if (s->map_enabled && !in(s->map_plane, GORDER_PLANE_XY, GORDER_PLANE_YZ)) what = "map_plane";
+        else if (s->n_membrane < 0 || s->n_geom_ref < 0 || s->n_normal_heads < 0 || (s->n_moltypes > 0 && !s->moltypes)) what = "group sizes / moltypes";
+        else if (s->normal_mode == GORDER_NORMAL_DYNAMIC && !(s->dynamic_radius > 0.0f)) what = "dynamic_radius";
+        else if (s->leaflet_mode == GORDER_LEAFLET_LOCAL && !(s->leaflet_radius > 0.0f)) what = "leaflet_radius";
+        if (what) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, (std::string("value out of range: ") + what).c_str()); return h->err_code; }
+    }
     h->spherical = s->leaflet_mode == GORDER_LEAFLET_SPHERICAL && getenv("GORDER_EXPERIMENTAL_SPHERICAL");
     if ((s->leaflet_mode < GORDER_LEAFLET_NONE || s->leaflet_mode > GORDER_LEAFLET_MANUAL) && !h->spherical) {
         h->set_error(GORDER_ERR_INVALID_ARGUMENT, s->leaflet_mode == GORDER_LEAFLET_SPHERICAL

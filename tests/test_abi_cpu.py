@@ -94,3 +94,20 @@ def test_synthetic_frames_are_reproducible():
     c, _ = s.frame(8)
     assert not np.array_equal(a, c)
     assert s.setup.samples_per_frame() == 1100
+
+
+def test_create_rejects_values_outside_their_range():
+    """Checked before any device is touched (so also on this box): an axis or a mode outside its enumeration must not reach
+    a kernel, where it would index past a 3-vector."""
+    import numpy as np
+    import pytest
+    from gorder_b200 import SystemTopology, abi
+    mt = abi.MolType(name="LIP", mol_base=np.array([0, 2]), bond_rel=[(0, 1)], head_rel=0)
+    bad = [dict(kind=7), dict(normal_axis=3), dict(normal_axis=-1), dict(leaflet_axis=5), dict(normal_mode=9), dict(geom_kind=4), dict(geom_ref_kind=-2),
+           dict(geom_axis=3), dict(leaflet_freq_kind=2), dict(leaflet_mode=17), dict(map_enabled=True, map_plane=3),
+           dict(normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=0.0), dict(leaflet_mode=abi.LEAFLET_LOCAL, leaflet_radius=-1.0)]
+    for kw in bad:
+        setup = abi.EngineSetup(**{**dict(kind=abi.KIND_CG, n_atoms=4, moltypes=[mt]), **kw})
+        with pytest.raises(abi.GorderError) as e:
+            SystemTopology(setup)
+        assert e.value.code == abi.ERR_INVALID_ARGUMENT, kw
