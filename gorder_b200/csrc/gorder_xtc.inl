@@ -18,6 +18,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <thread>
+#include <type_traits>
 #include <unistd.h>
 
 namespace gxtc {
@@ -61,16 +62,17 @@ struct BitIn {
         pos += (uint64_t)bits;
         return (uint32_t)v;
     }
-    inline uint32_t get(int bits) {   // bits <= 32
+    // SURE: the caller has checked that the whole group lies at least 16 bytes before the end of the stream
+    template <bool SURE = false> inline uint32_t get(int bits) {   // bits <= 32
         if (bits == 0) return 0;
-        if (!roomy()) return get_slow(bits);
+        if (!SURE && !roomy()) return get_slow(bits);
         const uint32_t v = (uint32_t)(window() >> (64 - bits));
         pos += (uint64_t)bits;
         return v;
     }
     // the mixed-radix number of a triple: its bytes arrive least significant first, the last one may be partial
-    template <typename W> inline W get_le(int bits) {
-        if (sizeof(W) == 8 && bits <= 56 && bits > 0 && roomy()) {
+    template <typename W, bool SURE = false> inline W get_le(int bits) {
+        if (sizeof(W) == 8 && bits <= 56 && bits > 0 && (SURE || roomy())) {
             const uint64_t w = window();
             const int full = bits >> 3, rem = bits & 7;
             uint64_t v = full ? (__builtin_bswap64(w) & (full == 8 ? ~0ull : ((1ull << (8 * full)) - 1ull))) : 0ull;
@@ -80,8 +82,8 @@ struct BitIn {
         }
         W v = 0;
         int shift = 0;
-        while (bits > 8) { v |= (W)get(8) << shift; shift += 8; bits -= 8; }
-        if (bits > 0) v |= (W)get(bits) << shift;
+        while (bits > 8) { v |= (W)get<SURE>(8) << shift; shift += 8; bits -= 8; }
+        if (bits > 0) v |= (W)get<SURE>(bits) << shift;
         return v;
     }
 };
@@ -153,15 +155,17 @@ int decode_frame(const uint8_t *base, const Frame &fr, int stop_after, Emit emit
     big1.set(sizeint[1], bitsize); big2.set(sizeint[2], bitsize);
     const FastDiv *small = &kSmall.d[smallidx];
     int i = 0, run = 0, cur[3], prev[3];
-    while (i <= last) {
-        if (bitsize == 0) { cur[0] = (int)in.get((int)bitsint[0]); cur[1] = (int)in.get((int)bitsint[1]); cur[2] = (int)in.get((int)bitsint[2]); }
-        else if (bitsize <= 64) unpack3_fast(in.get_le<uint64_t>(bitsize), big1, big2, cur);
-        else unpack3<unsigned __int128>(in.get_le<unsigned __int128>(bitsize), sizeint, cur);
+    // one group (a "large" atom and the run of small ones behind it): at most 128 + 6 + 10 * 72 bits = 107 bytes, even in a corrupt stream
+    auto group = [&](auto sure_tag) -> int {
+        constexpr bool SURE = decltype(sure_tag)::value;
+        if (bitsize == 0) { cur[0] = (int)in.template get<SURE>((int)bitsint[0]); cur[1] = (int)in.template get<SURE>((int)bitsint[1]); cur[2] = (int)in.template get<SURE>((int)bitsint[2]); }
+        else if (bitsize <= 64) unpack3_fast(in.template get_le<uint64_t, SURE>(bitsize), big1, big2, cur);
+        else unpack3<unsigned __int128>(in.template get_le<unsigned __int128, SURE>(bitsize), sizeint, cur);
         cur[0] += fr.minint[0]; cur[1] += fr.minint[1]; cur[2] += fr.minint[2];
         prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
         int is_smaller = 0;
         bool flag;
-        if (in.roomy()) {   // flag and run length in one look
+        if (SURE || in.roomy()) {   // flag and run length in one look
             const uint32_t six = (uint32_t)(in.window() >> 58);
             flag = (six & 32u) != 0;
             if (flag) run = (int)(six & 31u);
@@ -178,8 +182,8 @@ int decode_frame(const uint8_t *base, const Frame &fr, int stop_after, Emit emit
         if (run > 0) {
             for (int k = 0; k < run; k += 3) {
                 int d[3];
-                if (smallidx <= 64) unpack3_fast(in.get_le<uint64_t>(smallidx), *small, *small, d);
-                else unpack3<unsigned __int128>(in.get_le<unsigned __int128>(smallidx), ssz, d);
+                if (smallidx <= 64) unpack3_fast(in.template get_le<uint64_t, SURE>(smallidx), *small, *small, d);
+                else unpack3<unsigned __int128>(in.template get_le<unsigned __int128, SURE>(smallidx), ssz, d);
                 int t[3] = {d[0] + prev[0] - smallnum, d[1] + prev[1] - smallnum, d[2] + prev[2] - smallnum};
                 if (i + (k == 0 ? 2 : 1) > n) return -1;
                 if (k == 0) {   // the first two atoms of a run are stored in swapped order: this one comes first ...
@@ -199,6 +203,11 @@ int decode_frame(const uint8_t *base, const Frame &fr, int stop_after, Emit emit
         if (is_smaller < 0) { smallnum = smaller; smaller = smallidx > kFirstIdx ? kMagic[smallidx - 1] / 2 : 0; }
         else if (is_smaller > 0) { smaller = smallnum; smallnum = kMagic[smallidx] / 2; }
         if (is_smaller) { ssz[0] = ssz[1] = ssz[2] = (unsigned)kMagic[smallidx]; small = &kSmall.d[smallidx]; }
+        return 0;
+    };
+    while (i <= last) {
+        const int rc = (in.pos >> 3) + 128 <= (uint64_t)fr.nbytes ? group(std::true_type{}) : group(std::false_type{});
+        if (rc) return rc;
     }
     return 0;
 }
