@@ -16,7 +16,7 @@ SYMBOLS = [
     "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block", "gorder_gpu_stats",
     "gorder_gpu_read_block", "gorder_gpu_write_block", "gorder_gpu_profile", "gorder_gpu_profile_read",
     "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_stream",
-    "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device",
+    "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_xtc_scan", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device",
     "gorder_results_order", "gorder_results_convergence", "gorder_results_map", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
 ]
 
@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
     L.gorder_xtc_read.argtypes = [vp, i64, i64, i64, i32, vp, vp, vp, vp]
     L.gorder_xtc_write.argtypes = [C.c_char_p, vp, vp, i32, i64, C.c_float, i32, i32, C.c_float, i32]
     L.gorder_xtc_close.argtypes = [vp]
+    L.gorder_xtc_scan.argtypes = [vp, i64, C.POINTER(i32), C.POINTER(i32)]
+    L.gorder_xtc_scan.restype = C.c_int
     L.gorder_xtc_close.restype = None
     L.gorder_gpu_run_xtc.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, C.POINTER(C.c_double)]
     L.gorder_gpu_run_xtc_device.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, C.POINTER(i64)]

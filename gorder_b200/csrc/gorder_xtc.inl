@@ -765,6 +765,27 @@ void gorder_xtc_dev_free(GorderXtcDev *d) { if (d) { d->free_all(); delete d; } 
 
 extern "C" {
 
+// The host stage of the device-decode path for one frame, without a GPU: walk the control bits of the stream (one look per
+// group) and count its groups and the bookmarks the kernel would get.  Cheap integrity check of a frame (the coordinates
+// are not decoded).  GORDER_ERR_INVALID_ARGUMENT: inconsistent stream; *n_groups = -2: consistent, but a small triple needs
+// more than 64 bits (such frames take the host decoder).  Frames of <= 9 atoms are stored uncompressed: 0 groups.
+int gorder_xtc_scan(GorderXtc *x, int64_t frame, int32_t *n_groups, int32_t *n_bookmarks) {
+    if (!x || frame < 0 || frame >= (int64_t)x->frames.size()) return GORDER_ERR_INVALID_ARGUMENT;
+    const gxtc::Frame &f = x->frames[(size_t)frame];
+    if (n_groups) *n_groups = 0;
+    if (n_bookmarks) *n_bookmarks = 0;
+    if (f.natoms <= 9) return GORDER_OK;
+    unsigned sz[3];
+    for (int k = 0; k < 3; k++) sz[k] = (unsigned)(f.maxint[k] - f.minint[k] + 1);
+    const int large_bits = (sz[0] | sz[1] | sz[2]) > 0xffffffu ? gxtc::bits_of(sz[0]) + gxtc::bits_of(sz[1]) + gxtc::bits_of(sz[2]) : gxtc::bits_of_triple(sz);
+    std::vector<gxtc::Bookmark> marks;
+    const int ng = gxtc::bookmark_frame(x->data, f, large_bits, marks);
+    if (ng == -1) return GORDER_ERR_INVALID_ARGUMENT;
+    if (n_groups) *n_groups = ng;
+    if (n_bookmarks) *n_bookmarks = ng < 0 ? 0 : (int32_t)marks.size();
+    return GORDER_OK;
+}
+
 // gorder_gpu_run_xtc with the decode on the device.  Same arguments and results (the decoded coordinates are bit-identical
 // to the host decoder's); n_threads host threads copy the compressed frames into the pinned batch and bookmark them.
 // bytes_h2d (optional): bytes that crossed PCIe.

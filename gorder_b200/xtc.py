@@ -43,6 +43,15 @@ class XtcFile:
             raise OSError(f"gorder_xtc_read failed with code {rc}")
         return xyz, box9, time, step
 
+    def scan(self, frame: int):
+        """(groups, bookmarks) of a frame as the device-decode path's host stage sees them (``gorder_xtc_scan``); groups is -2
+        for a frame that path hands to the host decoder.  Raises OSError for an inconsistent stream."""
+        ng, nb = C.c_int32(0), C.c_int32(0)
+        rc = lib().gorder_xtc_scan(self._x, frame, C.byref(ng), C.byref(nb))
+        if rc:
+            raise OSError(f"gorder_xtc_scan: frame {frame} is corrupt (code {rc})")
+        return int(ng.value), int(nb.value)
+
     def close(self):
         if self._x:
             lib().gorder_xtc_close(self._x)

@@ -136,6 +136,11 @@ for it in range(int(sys.argv[2])):
         with xtc.XtcFile(p) as f:
             if f.n_frames > 0 and f.n_atoms < 10 ** 7:
                 f.read(0, f.n_frames, n_threads=2)
+                for k in range(f.n_frames):          # the host stage of the device-decode path walks the same bits
+                    try:
+                        f.scan(k)
+                    except OSError:
+                        pass
         ok += 1
     except (OSError, ValueError, RuntimeError):
         pass
@@ -153,3 +158,29 @@ def test_reader_survives_corrupt_files(seed):
     r = subprocess.run([sys.executable, "-c", _FUZZ, str(seed), "400"], cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
     assert "survived" in r.stdout
+
+
+def test_scan_counts_the_groups_of_a_frame(tmp_path):
+    """gorder_xtc_scan (the host stage of the device-decode path, without a GPU): every atom is either the large atom of a
+    group or one of the <= 8 small ones behind it; one bookmark per 32 groups; uncompressed frames have no groups."""
+    s = synthetic.s_cg(700)
+    xyz, box, _ = s.frames(0, 3)
+    path = str(tmp_path / "t.xtc")
+    write_xtc(path, xyz, box)
+    with XtcFile(path) as x:
+        for k in range(3):
+            groups, marks = x.scan(k)
+            assert x.n_atoms / 9 <= groups <= x.n_atoms
+            assert marks == (groups + 31) // 32
+        with pytest.raises(OSError):
+            x.scan(3)
+    # a gas: the writer widens the small triples until runs form again, so the same bounds hold
+    rng = np.random.default_rng(2)
+    far = rng.uniform(0, 50, (1, 640, 3)).astype(np.float32)
+    write_xtc(path, far, np.full((1, 3), 50, np.float32))
+    with XtcFile(path) as x:
+        groups, marks = x.scan(0)
+        assert 640 / 9 <= groups <= 640 and marks == (groups + 31) // 32
+    write_xtc(path, far[:, :7], np.full((1, 3), 50, np.float32))
+    with XtcFile(path) as x:
+        assert x.scan(0) == (0, 0)
