@@ -360,7 +360,7 @@ def run_ours(args):
                        "decode_atoms_per_s_per_thread": nx * s.n_atoms / max(dec_s, 1e-9),
                        "entry": "gorder_gpu_run_xtc (host XTC decode + H2D + analysis + D2H of the sums; rank 0)",
                        "samples_accumulated_incl_warmup": int(rx.count[:, 0].sum()),
-                       "device_decode": {"value": nx * spf / dt_d, "unit": UNIT, "wall_seconds": dt_d, "h2d_bytes": moved, "h2d_bytes_per_atom": moved / nx / s.n_atoms,
+                       "device_decode": {"value": nx * spf / dt_d, "unit": UNIT, "wall_seconds": dt_d, "batch_frames": args.xtc_dev_batch, "h2d_bytes": moved, "h2d_bytes_per_atom": moved / nx / s.n_atoms,
                                          "entry": "gorder_gpu_run_xtc_device (host copies + bookmarks the compressed frames; xtc_decode_kernel unpacks them on the GPU)"}}
         except Exception as exc:   # noqa: BLE001
             e2e_xtc = {"error": f"{type(exc).__name__}: {exc}"}
@@ -431,7 +431,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--xtc-frames", type=int, default=256, help="frames of the XTC end-to-end leg (0 = skip)")
     ap.add_argument("--xtc-batch", type=int, default=16, help="frames per decoded batch of the XTC leg")
-    ap.add_argument("--xtc-dev-batch", type=int, default=32, help="frames per batch of the device-decode XTC leg")
+    ap.add_argument("--xtc-dev-batch", type=int, default=64, help="frames per batch of the device-decode XTC leg (>= 4 per staging thread lets a thread walk 4 frames at once)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.lipids = args.lipids or WORKLOADS[args.workload][1]

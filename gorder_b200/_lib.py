@@ -56,7 +56,7 @@ def lib() -> C.CDLL:
     L.gorder_xtc_read.argtypes = [vp, i64, i64, i64, i32, vp, vp, vp, vp]
     L.gorder_xtc_write.argtypes = [C.c_char_p, vp, vp, i32, i64, C.c_float, i32, i32, C.c_float, i32]
     L.gorder_xtc_close.argtypes = [vp]
-    L.gorder_xtc_scan.argtypes = [vp, i64, C.POINTER(i32), C.POINTER(i32)]
+    L.gorder_xtc_scan.argtypes = [vp, i64, i64, vp, vp]
     L.gorder_xtc_scan.restype = C.c_int
     L.gorder_xtc_close.restype = None
     L.gorder_gpu_run_xtc.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, C.POINTER(C.c_double)]

@@ -590,35 +590,35 @@ struct RunTables {
     signed char smalls[32], delta[32];
     RunTables() { for (int c = 0; c < 32; c++) { const int sm = c % 3; smalls[c] = (signed char)((c - sm) / 3); delta[c] = (signed char)(sm - 1); } }
 };
-inline int bookmark_frame(const uint8_t *base, const Frame &f, int large_bits, std::vector<Bookmark> &out) {
-    static const RunTables T;
-    const uint8_t *p = base + f.payload;
-    const unsigned long long end = (unsigned long long)f.nbytes * 8ull;
-    if (end < 16) return -1;
-    const unsigned long long last_safe = end - 16;   // the two-byte look stays inside the stream below this offset
-    unsigned long long pos = 0;
-    int i = 0, g = 0, smalls = 0, sidx = f.smallidx;
-    const int n = f.natoms;
-    while (i < n) {
-        if (sidx > 64) return -2;
-        if (sidx < kFirstIdx) return -1;
-        if ((g % kBookmarkEvery) == 0) out.push_back(Bookmark{(unsigned)pos, (unsigned)i, (unsigned short)(3 * smalls), (unsigned short)sidx, 0u});
-        pos += large_bits;
-        if (pos > last_safe) {   // tail of the stream: careful byte access
-            if (pos + 1 > end) return -1;
-            const size_t b = (size_t)(pos >> 3);
-            const unsigned two = ((unsigned)p[b] << 8) | (b + 1 < f.nbytes ? p[b + 1] : 0u);
-            const unsigned six = (two >> (10 - (pos & 7))) & 63u;
-            const unsigned flag = six >> 5, code = six & 31u;
-            if (flag) smalls = T.smalls[code];
-            pos += 1 + 5 * flag + (unsigned long long)smalls * sidx;
-            i += 1 + smalls;
-            sidx += flag ? T.delta[code] : 0;
-            g++;
-            continue;
-        }
+// The walk over the control bits of one frame, one group per step() so that two frames can be walked in the same loop:
+// a step is a chain of dependent operations (look at 6 bits, two table look-ups, a multiply-add: ~12 ns), two independent
+// chains overlap in the core's out-of-order window.
+struct Walker {
+    const uint8_t *p = nullptr;
+    size_t nbytes = 0;
+    unsigned long long end = 0, last_safe = 0, pos = 0;
+    int i = 0, g = 0, smalls = 0, sidx = 0, n = 0, large_bits = 0;
+    int rc = 0;   // 0: walking, 1: finished, -1: inconsistent stream, -2: > 64 bits per small triple
+    std::vector<Bookmark> *out = nullptr;
+    inline void init(const uint8_t *base, const Frame &f, int large_bits_, std::vector<Bookmark> *out_) {
+        p = base + f.payload; nbytes = f.nbytes; end = (unsigned long long)f.nbytes * 8ull; pos = 0;
+        i = 0; g = 0; smalls = 0; sidx = f.smallidx; n = f.natoms; large_bits = large_bits_; out = out_;
+        rc = 0;
+        if (end < 16) { rc = -1; return; }
+        last_safe = end - 16;   // the two-byte look stays inside the stream below this offset
+        if (n <= 0) rc = 1;
+    }
+    inline void step(const RunTables &T) {   // rc == 0
+        if (sidx > 64) { rc = -2; return; }
+        if (sidx < kFirstIdx) { rc = -1; return; }
+        if ((g % kBookmarkEvery) == 0) out->push_back(Bookmark{(unsigned)pos, (unsigned)i, (unsigned short)(3 * smalls), (unsigned short)sidx, 0u});
+        pos += (unsigned long long)large_bits;
         const size_t b = (size_t)(pos >> 3);
-        const unsigned two = ((unsigned)p[b] << 8) | p[b + 1];
+        unsigned two;
+        if (pos > last_safe) {   // tail of the stream: careful byte access
+            if (pos + 1 > end) { rc = -1; return; }
+            two = ((unsigned)p[b] << 8) | (b + 1 < nbytes ? p[b + 1] : 0u);
+        } else two = ((unsigned)p[b] << 8) | p[b + 1];
         const unsigned six = (two >> (10 - (pos & 7))) & 63u;
         const unsigned flag = six >> 5, code = six & 31u;
         smalls = flag ? T.smalls[code] : smalls;
@@ -626,9 +626,30 @@ inline int bookmark_frame(const uint8_t *base, const Frame &f, int large_bits, s
         i += 1 + smalls;
         sidx += flag ? T.delta[code] : 0;
         g++;
+        if (i >= n) rc = (i != n || pos > end) ? -1 : 1;
     }
-    if (i != n || pos > end) return -1;
-    return g;
+    inline int result() const { return rc == 1 ? g : rc; }
+};
+inline int bookmark_frame(const uint8_t *base, const Frame &f, int large_bits, std::vector<Bookmark> &out) {
+    static const RunTables T;
+    Walker w;
+    w.init(base, f, large_bits, &out);
+    while (w.rc == 0) w.step(T);
+    return w.result();
+}
+// up to kWalkWays frames at once (see Walker): ng[k] = groups of frame k or its error code
+constexpr int kWalkWays = 4;
+inline void bookmark_many(const uint8_t *base, const Frame *const *fr, const int *bits, std::vector<Bookmark> *const *out, int *ng, int count) {
+    static const RunTables T;
+    Walker w[kWalkWays];
+    for (int k = 0; k < count; k++) w[k].init(base, *fr[k], bits[k], out[k]);
+    for (;;) {
+        int active = 0;
+        for (int k = 0; k < count; k++)
+            if (w[k].rc == 0) { w[k].step(T); active++; }
+        if (!active) break;
+    }
+    for (int k = 0; k < count; k++) ng[k] = w[k].result();
 }
 
 __constant__ int c_magic[73];
@@ -765,25 +786,37 @@ void gorder_xtc_dev_free(GorderXtcDev *d) { if (d) { d->free_all(); delete d; } 
 
 extern "C" {
 
-// The host stage of the device-decode path for one frame, without a GPU: walk the control bits of the stream (one look per
-// group) and count its groups and the bookmarks the kernel would get.  Cheap integrity check of a frame (the coordinates
-// are not decoded).  GORDER_ERR_INVALID_ARGUMENT: inconsistent stream; *n_groups = -2: consistent, but a small triple needs
-// more than 64 bits (such frames take the host decoder).  Frames of <= 9 atoms are stored uncompressed: 0 groups.
-int gorder_xtc_scan(GorderXtc *x, int64_t frame, int32_t *n_groups, int32_t *n_bookmarks) {
-    if (!x || frame < 0 || frame >= (int64_t)x->frames.size()) return GORDER_ERR_INVALID_ARGUMENT;
-    const gxtc::Frame &f = x->frames[(size_t)frame];
-    if (n_groups) *n_groups = 0;
-    if (n_bookmarks) *n_bookmarks = 0;
-    if (f.natoms <= 9) return GORDER_OK;
-    unsigned sz[3];
-    for (int k = 0; k < 3; k++) sz[k] = (unsigned)(f.maxint[k] - f.minint[k] + 1);
-    const int large_bits = (sz[0] | sz[1] | sz[2]) > 0xffffffu ? gxtc::bits_of(sz[0]) + gxtc::bits_of(sz[1]) + gxtc::bits_of(sz[2]) : gxtc::bits_of_triple(sz);
-    std::vector<gxtc::Bookmark> marks;
-    const int ng = gxtc::bookmark_frame(x->data, f, large_bits, marks);
-    if (ng == -1) return GORDER_ERR_INVALID_ARGUMENT;
-    if (n_groups) *n_groups = ng;
-    if (n_bookmarks) *n_bookmarks = ng < 0 ? 0 : (int32_t)marks.size();
-    return GORDER_OK;
+// The host stage of the device-decode path without a GPU: walk the control bits of frames first .. first + count - 1 (one
+// look per group, two frames per loop as the staging threads do) and report, per frame, its groups and the bookmarks the
+// kernel would get.  Cheap integrity check (the coordinates are not decoded).  n_groups[k] = -1: inconsistent stream (the call
+// then returns GORDER_ERR_INVALID_ARGUMENT after scanning everything), -2: consistent, but a small triple needs more than 64
+// bits (such frames take the host decoder); frames of <= 9 atoms are stored uncompressed: 0 groups.
+int gorder_xtc_scan(GorderXtc *x, int64_t first, int64_t count, int32_t *n_groups, int32_t *n_bookmarks) {
+    if (!x || first < 0 || count < 0 || first + count > (int64_t)x->frames.size()) return GORDER_ERR_INVALID_ARGUMENT;
+    auto bits_of_frame = [&](const gxtc::Frame &f) {
+        unsigned sz[3];
+        for (int k = 0; k < 3; k++) sz[k] = (unsigned)(f.maxint[k] - f.minint[k] + 1);
+        return (sz[0] | sz[1] | sz[2]) > 0xffffffu ? gxtc::bits_of(sz[0]) + gxtc::bits_of(sz[1]) + gxtc::bits_of(sz[2]) : gxtc::bits_of_triple(sz);
+    };
+    std::vector<gxtc::Bookmark> marks[gxtc::kWalkWays];
+    int bad = 0;
+    for (int64_t k0 = 0; k0 < count; k0 += gxtc::kWalkWays) {
+        const int m = (int)std::min<int64_t>(gxtc::kWalkWays, count - k0);
+        const gxtc::Frame *fr[gxtc::kWalkWays];
+        std::vector<gxtc::Bookmark> *out[gxtc::kWalkWays];
+        int bits[gxtc::kWalkWays], ng[gxtc::kWalkWays];
+        for (int k = 0; k < m; k++) { fr[k] = &x->frames[(size_t)(first + k0 + k)]; bits[k] = bits_of_frame(*fr[k]); marks[k].clear(); out[k] = &marks[k]; }
+        gxtc::bookmark_many(x->data, fr, bits, out, ng, m);
+        for (int k = 0; k < m; k++) {
+            int g = ng[k];
+            size_t nm = marks[k].size();
+            if (fr[k]->natoms <= 9) { g = 0; nm = 0; }
+            if (g == -1) bad = 1;
+            if (n_groups) n_groups[k0 + k] = g;
+            if (n_bookmarks) n_bookmarks[k0 + k] = g < 0 ? 0 : (int32_t)nm;
+        }
+    }
+    return bad ? GORDER_ERR_INVALID_ARGUMENT : GORDER_OK;
 }
 
 // gorder_gpu_run_xtc with the decode on the device.  Same arguments and results (the decoded coordinates are bit-identical
@@ -855,34 +888,50 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
     std::vector<int> n_groups((size_t)B);
     auto stage = [&](int64_t j0, int nf, int buf) {   // compressed frames + bookmarks -> pinned batch
         std::atomic<int> next{0};
+        const int nt = std::max(1, std::min<int>(n_threads, nf));
+        // a thread walks the control bits of up to kWalkWays frames in one loop (gxtc::Walker): the walk is a chain of dependent
+        // steps, several chains overlap in the core (x2 per thread at 4 ways); not more ways than keep every thread busy
+        const int ways = std::max(1, std::min(gxtc::kWalkWays, nf / nt));
         auto work = [&]() {
-            std::vector<gxtc::Bookmark> marks;
+            std::vector<gxtc::Bookmark> marks[gxtc::kWalkWays];
             for (;;) {
-                const int j = next.fetch_add(1);
-                if (j >= nf) break;
-                const gxtc::Frame &f = x->frames[(size_t)(first + (j0 + j) * stride)];
-                if (f.box[1] != 0.0f || f.box[2] != 0.0f || f.box[3] != 0.0f || f.box[5] != 0.0f || f.box[6] != 0.0f || f.box[7] != 0.0f) bad = GORDER_ERR_NOT_ORTHOGONAL_BOX;
-                gxtc::DevFrame &d = D.h_frames[buf][j];
-                d.payload = (unsigned long long)j * frame_cap; d.bookmarks = (unsigned long long)j * marks_per_frame;
-                d.nbytes = (unsigned)f.nbytes; d.natoms = f.natoms;
-                unsigned sz[3];
-                for (int k = 0; k < 3; k++) { d.minint[k] = f.minint[k]; sz[k] = d.sizeint[k] = (unsigned)(f.maxint[k] - f.minint[k] + 1); }
-                if ((sz[0] | sz[1] | sz[2]) > 0xffffffu) { d.bitsize = 0; for (int k = 0; k < 3; k++) d.bitsint[k] = gxtc::bits_of(sz[k]); }
-                else { d.bitsize = gxtc::bits_of_triple(sz); d.bitsint[0] = d.bitsint[1] = d.bitsint[2] = 0; }
-                d.inv_precision = 1.0f / f.precision;
-                marks.clear();
-                const int ng = gxtc::bookmark_frame(x->data, f, d.bitsize ? d.bitsize : d.bitsint[0] + d.bitsint[1] + d.bitsint[2], marks);
-                if (ng == -2) { unsupported = 1; d.n_groups = 0; }
-                else if (ng < 0 || marks.size() > marks_per_frame) { bad = GORDER_ERR_INVALID_ARGUMENT; d.n_groups = 0; }
-                else { d.n_groups = ng; memcpy(D.h_marks[buf] + d.bookmarks, marks.data(), marks.size() * sizeof(gxtc::Bookmark)); }
-                n_groups[(size_t)j] = d.n_groups;
-                unsigned char *dst = D.h_bytes[buf] + d.payload;
-                memcpy(dst, x->data + f.payload, f.nbytes);
-                memset(dst + f.nbytes, 0, frame_cap - f.nbytes);
-                D.h_box[buf][3 * j] = f.box[0]; D.h_box[buf][3 * j + 1] = f.box[4]; D.h_box[buf][3 * j + 2] = f.box[8];
+                const int jb = next.fetch_add(ways);
+                if (jb >= nf) break;
+                const int m = std::min(ways, nf - jb);
+                const gxtc::Frame *fr[gxtc::kWalkWays];
+                std::vector<gxtc::Bookmark> *out[gxtc::kWalkWays];
+                int bits[gxtc::kWalkWays], ngs[gxtc::kWalkWays];
+                for (int k = 0; k < m; k++) {
+                    const int j = jb + k;
+                    const gxtc::Frame &f = x->frames[(size_t)(first + (j0 + j) * stride)];
+                    if (f.box[1] != 0.0f || f.box[2] != 0.0f || f.box[3] != 0.0f || f.box[5] != 0.0f || f.box[6] != 0.0f || f.box[7] != 0.0f) bad = GORDER_ERR_NOT_ORTHOGONAL_BOX;
+                    gxtc::DevFrame &d = D.h_frames[buf][j];
+                    d.payload = (unsigned long long)j * frame_cap; d.bookmarks = (unsigned long long)j * marks_per_frame;
+                    d.nbytes = (unsigned)f.nbytes; d.natoms = f.natoms;
+                    unsigned sz[3];
+                    for (int c = 0; c < 3; c++) { d.minint[c] = f.minint[c]; sz[c] = d.sizeint[c] = (unsigned)(f.maxint[c] - f.minint[c] + 1); }
+                    if ((sz[0] | sz[1] | sz[2]) > 0xffffffu) { d.bitsize = 0; for (int c = 0; c < 3; c++) d.bitsint[c] = gxtc::bits_of(sz[c]); }
+                    else { d.bitsize = gxtc::bits_of_triple(sz); d.bitsint[0] = d.bitsint[1] = d.bitsint[2] = 0; }
+                    d.inv_precision = 1.0f / f.precision;
+                    fr[k] = &f; bits[k] = d.bitsize ? d.bitsize : d.bitsint[0] + d.bitsint[1] + d.bitsint[2];
+                    marks[k].clear(); out[k] = &marks[k];
+                }
+                gxtc::bookmark_many(x->data, fr, bits, out, ngs, m);
+                for (int k = 0; k < m; k++) {
+                    const int j = jb + k, ng = ngs[k];
+                    const gxtc::Frame &f = *fr[k];
+                    gxtc::DevFrame &d = D.h_frames[buf][j];
+                    if (ng == -2) { unsupported = 1; d.n_groups = 0; }
+                    else if (ng < 0 || marks[k].size() > marks_per_frame) { bad = GORDER_ERR_INVALID_ARGUMENT; d.n_groups = 0; }
+                    else { d.n_groups = ng; memcpy(D.h_marks[buf] + d.bookmarks, marks[k].data(), marks[k].size() * sizeof(gxtc::Bookmark)); }
+                    n_groups[(size_t)j] = d.n_groups;
+                    unsigned char *dst = D.h_bytes[buf] + d.payload;
+                    memcpy(dst, x->data + f.payload, f.nbytes);
+                    memset(dst + f.nbytes, 0, frame_cap - f.nbytes);
+                    D.h_box[buf][3 * j] = f.box[0]; D.h_box[buf][3 * j + 1] = f.box[4]; D.h_box[buf][3 * j + 2] = f.box[8];
+                }
             }
         };
-        const int nt = std::max(1, std::min<int>(n_threads, nf));
         std::vector<std::thread> pool;
         for (int t = 1; t < nt; t++) pool.emplace_back(work);
         work();

@@ -43,14 +43,17 @@ class XtcFile:
             raise OSError(f"gorder_xtc_read failed with code {rc}")
         return xyz, box9, time, step
 
-    def scan(self, frame: int):
-        """(groups, bookmarks) of a frame as the device-decode path's host stage sees them (``gorder_xtc_scan``); groups is -2
-        for a frame that path hands to the host decoder.  Raises OSError for an inconsistent stream."""
-        ng, nb = C.c_int32(0), C.c_int32(0)
-        rc = lib().gorder_xtc_scan(self._x, frame, C.byref(ng), C.byref(nb))
+    def scan(self, first: int = 0, count: int | None = None):
+        """(groups [count], bookmarks [count]) of frames first .. first + count - 1 as the device-decode path's host stage sees
+        them (``gorder_xtc_scan``); groups is -2 for a frame that path hands to the host decoder.  Raises OSError when a
+        stream is inconsistent."""
+        if count is None:
+            count = self.n_frames - first
+        ng, nb = np.zeros(max(count, 0), np.int32), np.zeros(max(count, 0), np.int32)
+        rc = lib().gorder_xtc_scan(self._x, first, count, _ptr(ng), _ptr(nb))
         if rc:
-            raise OSError(f"gorder_xtc_scan: frame {frame} is corrupt (code {rc})")
-        return int(ng.value), int(nb.value)
+            raise OSError(f"gorder_xtc_scan: corrupt frame(s) {np.flatnonzero(ng == -1) + first} (code {rc})")
+        return ng, nb
 
     def close(self):
         if self._x:

@@ -391,11 +391,12 @@ int gorder_results_convergence(const GorderRaw *raw, const int32_t *slots, int32
 /* Order-map bins (ordermap.rs / converter.rs:159-308): out[i] = sign * (sum[i] / 1e6) / count[i], NaN below min_samples. */
 int gorder_results_map(const int64_t *map_sum, const uint64_t *map_count, int64_t n, int32_t min_samples, float sign, float *out);
 
-/* The host stage of gorder_gpu_run_xtc_device for one frame, without a GPU: walks the control bits of the frame's stream
- * and reports its groups (one "large" atom + its run of small ones) and the bookmarks the kernel would get.  A cheap
- * integrity check (nothing is decoded): GORDER_ERR_INVALID_ARGUMENT for an inconsistent stream; *n_groups = -2 for a frame
- * the device path hands to the host decoder (> 64 bits per small triple). */
-int gorder_xtc_scan(GorderXtc *x, int64_t frame, int32_t *n_groups, int32_t *n_bookmarks);
+/* The host stage of gorder_gpu_run_xtc_device without a GPU: walks the control bits of frames first .. first + count - 1
+ * and reports per frame its groups (one "large" atom + its run of small ones) and the bookmarks the kernel would get.  A
+ * cheap integrity check (nothing is decoded): n_groups[k] = -1 and GORDER_ERR_INVALID_ARGUMENT for an inconsistent stream;
+ * n_groups[k] = -2 for a frame the device path hands to the host decoder (> 64 bits per small triple).  Either array may
+ * be NULL. */
+int gorder_xtc_scan(GorderXtc *x, int64_t first, int64_t count, int32_t *n_groups /* [count] */, int32_t *n_bookmarks /* [count] */);
 
 /* Human-readable detail of the last error of this handle (offending atom index etc.). */
 int gorder_gpu_last_error(GorderHandle *h, char *buf, size_t len);

@@ -136,11 +136,10 @@ for it in range(int(sys.argv[2])):
         with xtc.XtcFile(p) as f:
             if f.n_frames > 0 and f.n_atoms < 10 ** 7:
                 f.read(0, f.n_frames, n_threads=2)
-                for k in range(f.n_frames):          # the host stage of the device-decode path walks the same bits
-                    try:
-                        f.scan(k)
-                    except OSError:
-                        pass
+                try:                                  # the host stage of the device-decode path walks the same bits
+                    f.scan()
+                except OSError:
+                    pass
         ok += 1
     except (OSError, ValueError, RuntimeError):
         pass
@@ -162,25 +161,65 @@ def test_reader_survives_corrupt_files(seed):
 
 def test_scan_counts_the_groups_of_a_frame(tmp_path):
     """gorder_xtc_scan (the host stage of the device-decode path, without a GPU): every atom is either the large atom of a
-    group or one of the <= 8 small ones behind it; one bookmark per 32 groups; uncompressed frames have no groups."""
+    group or one of the <= 8 small ones behind it; one bookmark per 32 groups; uncompressed frames have no groups; walking two
+    frames in one loop (even counts) gives what walking them one by one (count = 1) gives."""
     s = synthetic.s_cg(700)
-    xyz, box, _ = s.frames(0, 3)
+    xyz, box, _ = s.frames(0, 5)
+    xyz[3] += 0.37                                   # frames of different lengths next to each other
     path = str(tmp_path / "t.xtc")
     write_xtc(path, xyz, box)
     with XtcFile(path) as x:
-        for k in range(3):
-            groups, marks = x.scan(k)
-            assert x.n_atoms / 9 <= groups <= x.n_atoms
-            assert marks == (groups + 31) // 32
+        groups, marks = x.scan()
+        assert groups.shape == (5,) and np.all(groups >= x.n_atoms / 9) and np.all(groups <= x.n_atoms)
+        np.testing.assert_array_equal(marks, (groups + 31) // 32)
+        for k in range(5):
+            g1, m1 = x.scan(k, 1)
+            assert (g1[0], m1[0]) == (groups[k], marks[k])
+        g2, m2 = x.scan(1, 4)
+        np.testing.assert_array_equal(g2, groups[1:])
         with pytest.raises(OSError):
-            x.scan(3)
+            x.scan(3, 3)
+        assert x.scan(5, 0)[0].shape == (0,)
     # a gas: the writer widens the small triples until runs form again, so the same bounds hold
     rng = np.random.default_rng(2)
-    far = rng.uniform(0, 50, (1, 640, 3)).astype(np.float32)
-    write_xtc(path, far, np.full((1, 3), 50, np.float32))
+    far = rng.uniform(0, 50, (2, 640, 3)).astype(np.float32)
+    write_xtc(path, far, np.full((2, 3), 50, np.float32))
     with XtcFile(path) as x:
-        groups, marks = x.scan(0)
-        assert 640 / 9 <= groups <= 640 and marks == (groups + 31) // 32
-    write_xtc(path, far[:, :7], np.full((1, 3), 50, np.float32))
+        groups, marks = x.scan()
+        assert np.all(groups >= 640 / 9) and np.all(groups <= 640)
+        np.testing.assert_array_equal(marks, (groups + 31) // 32)
+    write_xtc(path, far[:, :7], np.full((2, 3), 50, np.float32))
     with XtcFile(path) as x:
-        assert x.scan(0) == (0, 0)
+        groups, marks = x.scan()
+        assert groups.tolist() == [0, 0] and marks.tolist() == [0, 0]
+
+
+def test_scan_of_corrupt_frames_next_to_good_ones(tmp_path):
+    """A corrupt stream walked beside a good one (two frames per loop) is reported for that frame only."""
+    s = synthetic.s_cg(300)
+    xyz, box, _ = s.frames(0, 4)
+    path = str(tmp_path / "t.xtc")
+    write_xtc(path, xyz, box)
+    raw = bytearray(open(path, "rb").read())
+    with XtcFile(path) as x:
+        good, _ = x.scan()
+    per = len(raw) // 4
+    rng = np.random.default_rng(0)
+    hit = 0
+    for trial in range(30):
+        b = bytearray(raw)
+        at = per + 200 + int(rng.integers(0, per - 400))          # somewhere inside the stream of frame 1
+        for k in range(24):
+            b[at + k] = int(rng.integers(0, 256))
+        open(path, "wb").write(b)
+        with XtcFile(path) as x:
+            if x.n_frames != 4:
+                continue
+            L = __import__("gorder_b200._lib", fromlist=["lib"]).lib()
+            ng, nb = np.zeros(4, np.int32), np.zeros(4, np.int32)
+            rc = L.gorder_xtc_scan(x._x, 0, 4, ng.ctypes.data, nb.ctypes.data)
+            assert ng[0] == good[0] and ng[2] == good[2] and ng[3] == good[3]
+            if rc:
+                assert ng[1] == -1
+                hit += 1
+    assert hit > 0
