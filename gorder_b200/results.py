@@ -84,7 +84,8 @@ class ItemResults:
     label: str
     order: OrderCollection
     bonds: List[OrderCollection] = field(default_factory=list)
-    maps: Optional[np.ndarray] = None   # [3][nx][ny] f32 (NaN where samples < min)
+    maps: Optional[np.ndarray] = None   # [3][nx][ny] f32 (NaN where samples < min); AA / UA: the bonds of the atom merged
+    bond_maps: List[np.ndarray] = field(default_factory=list)   # AA / UA: one [3][nx][ny] per bond of the atom
 
 
 @dataclass
@@ -134,11 +135,13 @@ class _PythonBackend:
         return {k: np.array([self.sign * x for x in prefix_average(ts[:, j], tc[:, j])], np.float32)
                 for j, k in enumerate(["total", "upper", "lower"][: 3 if self.leaflets else 1])}
 
-    def slot_map(self, s: int):
-        raw = self.raw
+    def slots_map(self, slots):
+        """Map of the samples of `slots` together (one bond; the bonds of an atom: ordermap.rs:116-138 `Add`)."""
+        raw, sl = self.raw, np.asarray(slots, np.int64)
+        ms, mc = raw.map_sum[sl].sum(axis=0, dtype=np.int64), raw.map_count[sl].sum(axis=0, dtype=np.uint64)
         with np.errstate(divide="ignore", invalid="ignore"):
-            val = (raw.map_sum[s].astype(np.float64) / 1e6).astype(np.float32) / raw.map_count[s].astype(np.float32)
-        return np.where(raw.map_count[s] < self.map_min, np.nan, self.sign * val).astype(np.float32)
+            val = (ms.astype(np.float64) / 1e6).astype(np.float32) / mc.astype(np.float32)
+        return np.where(mc < self.map_min, np.nan, self.sign * val).astype(np.float32)
 
 
 class _NativeBackend:
@@ -180,8 +183,10 @@ class _NativeBackend:
         self._check(self.lib.gorder_results_convergence(self.C.byref(self.r), sl.ctypes.data, len(sl), self.sign, out.ctypes.data))
         return {k: out[:, j].copy() for j, k in enumerate(["total", "upper", "lower"][: 3 if self.leaflets else 1])}
 
-    def slot_map(self, s: int):
-        ms, mc = np.ascontiguousarray(self.raw.map_sum[s], np.int64), np.ascontiguousarray(self.raw.map_count[s], np.uint64)
+    def slots_map(self, slots):
+        sl = np.asarray(slots, np.int64)
+        ms = np.ascontiguousarray(self.raw.map_sum[sl].sum(axis=0, dtype=np.int64))
+        mc = np.ascontiguousarray(self.raw.map_count[sl].sum(axis=0, dtype=np.uint64))
         out = np.zeros(ms.shape, np.float32)
         self._check(self.lib.gorder_results_map(ms.ctypes.data, mc.ctypes.data, ms.size, self.map_min, self.sign, out.ctypes.data))
         return out
@@ -200,8 +205,11 @@ def convert(raw: abi.RawResults, setup: abi.EngineSetup, *, n_blocks: Optional[i
     molecules: Dict[str, MoleculeResults] = {}
     system_slots: List[int] = []
 
-    def slot_map(s: int):
-        return None if raw.map_sum is None else be.slot_map(s)
+    def slots_map(slots):
+        return None if raw.map_sum is None else be.slots_map(slots)
+
+    def bond_maps(slots):
+        return [] if raw.map_sum is None else [be.slots_map([q]) for q in slots]
 
     for (s0, n), mt in zip(setup.slot_ranges(), setup.moltypes):
         mol_slots: List[int] = []
@@ -213,12 +221,13 @@ def convert(raw: abi.RawResults, setup: abi.EngineSetup, *, n_blocks: Optional[i
                 s += len(atom_slots)
                 mol_slots += atom_slots
                 label = mt.bond_names[i] if i < len(mt.bond_names) else f"atom {i}"
-                items.append(ItemResults(label, be.collection(atom_slots), [be.collection([q]) for q in atom_slots]))
+                items.append(ItemResults(label, be.collection(atom_slots), [be.collection([q]) for q in atom_slots],
+                                         maps=slots_map(atom_slots), bond_maps=bond_maps(atom_slots)))
         elif setup.kind == abi.KIND_CG:
             for b in range(n):
                 mol_slots.append(s0 + b)
                 label = mt.bond_names[b] if b < len(mt.bond_names) else f"bond {b}"
-                items.append(ItemResults(label, be.collection([s0 + b]), maps=slot_map(s0 + b)))
+                items.append(ItemResults(label, be.collection([s0 + b]), maps=slots_map([s0 + b])))
         else:
             # AA: bonds grouped by their heavy atom (converter.rs:325-352); bonds are sorted by atom1 (bond.rs:77-81)
             by_atom: Dict[int, List[int]] = {}
@@ -228,7 +237,8 @@ def convert(raw: abi.RawResults, setup: abi.EngineSetup, *, n_blocks: Optional[i
                 atom_slots = [s0 + b for b in by_atom[a1]]
                 mol_slots += atom_slots
                 label = (mt.bond_names[by_atom[a1][0]].split(" - ")[0] if by_atom[a1][0] < len(mt.bond_names) else f"atom {a1}")
-                items.append(ItemResults(label, be.collection(atom_slots), [be.collection([q]) for q in atom_slots]))
+                items.append(ItemResults(label, be.collection(atom_slots), [be.collection([q]) for q in atom_slots],
+                                         maps=slots_map(atom_slots), bond_maps=bond_maps(atom_slots)))
         conv = be.convergence(mol_slots) if tw else None
         molecules[mt.name] = MoleculeResults(mt.name, be.collection(mol_slots), items, conv)
         system_slots += mol_slots

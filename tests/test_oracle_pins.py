@@ -266,6 +266,7 @@ def check_maps_aa(raw, setup, case):
     suffixes = [("full", 0)] + ([("upper", 1), ("lower", 2)] if any(k.endswith("_upper.dat") for k in case["maps"]) else [])
     per_atom = {}
     seen = set()
+    vals = {}
 
     def compare(lab, sm, cn):
         rows = np.array(case["maps"][lab], np.float64)
@@ -279,6 +280,7 @@ def check_maps_aa(raw, setup, case):
         np.testing.assert_allclose(rows[:, 0], xs, atol=1e-3)
         np.testing.assert_allclose(rows[:, 1], ys, atol=1e-3)
         seen.add(lab)
+        vals[lab] = val.reshape(nx, ny)
 
     for b, name in enumerate(mt.bond_names):    # "POPC C22 (32) - POPC H2R (33)"
         a, h = name.split(" - ")
@@ -292,6 +294,22 @@ def check_maps_aa(raw, setup, case):
         for (fa, suf), (sm, cn) in per_atom.items():
             compare(f"ordermap_{fa}_{suf}.dat", sm, cn)
     assert seen == set(case["maps"].keys()), seen ^ set(case["maps"].keys())
+    # the converters (numpy and the shared library's gorder_results_map) produce the same maps: per bond and, for AA, per atom
+    for native in (False, True):
+        res = results.convert(raw, setup, map_min_samples=case["map_min_samples"], native=native)
+        items = next(iter(res.molecules.values())).items
+        b = 0
+        for it in items:
+            per_bond = it.bond_maps if setup.kind != abi.KIND_CG else [it.maps]
+            for bm in per_bond:
+                a, h = mt.bond_names[b].split(" - ")
+                fa, fh = ("-".join(x.replace("(", "").replace(")", "").split()) for x in (a, h))
+                for suf, k in suffixes:
+                    np.testing.assert_allclose(bm[k], vals[f"ordermap_{fa}--{fh}_{suf}.dat"], atol=1e-6, rtol=0, equal_nan=True)
+                    if setup.kind == abi.KIND_AA:
+                        np.testing.assert_allclose(it.maps[k], vals[f"ordermap_{fa}_{suf}.dat"], atol=1e-6, rtol=0, equal_nan=True)
+                b += 1
+        assert b == len(mt.bond_names)
 
 
 def check_convergence(raw, setup, case):

@@ -121,9 +121,10 @@ def test_maps():
         py = results._PythonBackend(raw, -1.0, True, None, 1, min_samples)
         nat = results._NativeBackend(raw, -1.0, True, None, 1, min_samples)
         for s in range(5):
-            a, b = py.slot_map(s), nat.slot_map(s)
+            a, b = py.slots_map([s]), nat.slots_map([s])
             np.testing.assert_array_equal(a, b)
             assert np.array_equal(np.isnan(b), cnt[s] < min_samples)
+        np.testing.assert_array_equal(py.slots_map([1, 2, 4]), nat.slots_map([1, 2, 4]))   # the bonds of one atom, merged
 
 
 @pytest.mark.parametrize("kind", ["cg", "aa", "ua"])
