@@ -24,7 +24,7 @@ KIND_AA, KIND_CG, KIND_UA = 0, 1, 2
 AXIS_X, AXIS_Y, AXIS_Z = 0, 1, 2
 NORMAL_STATIC, NORMAL_DYNAMIC, NORMAL_MANUAL = 0, 1, 2
 LEAFLET_NONE, LEAFLET_GLOBAL, LEAFLET_LOCAL, LEAFLET_INDIVIDUAL, LEAFLET_MANUAL = 0, 1, 2, 3, 4
-LEAFLET_SPHERICAL = 5   # spherical clustering: restated in the oracle only so far (include/gorder_b200.h)
+LEAFLET_SPHERICAL = 5   # spherical clustering (spherical_clustering.rs:36-275; csrc/gorder_spherical.cuh)
 FREQ_EVERY, FREQ_ONCE = 0, 1
 GEOM_NONE, GEOM_CUBOID, GEOM_CYLINDER, GEOM_SPHERE = 0, 1, 2, 3
 GEOMREF_POINT, GEOMREF_SELECTION, GEOMREF_BOX_CENTER = 0, 1, 2

@@ -48,9 +48,37 @@ bool g_fast_used[64][kFastSlots];
 struct GorderXtcDev;
 void gorder_xtc_dev_free(GorderXtcDev *d);
 
+// Debugging / A-B switches: read ONCE from the environment when a handle is created, never per batch.
+struct Switches {
+    int mpt = 0;                 // GORDER_MPT: molecules per lane of the bond kernels (1 | 2 | 4), 0 = size heuristic
+    bool no_fast = false;        // GORDER_NO_FAST: generic bond_order_kernel instead of bond_fast_kernel
+    bool no_const_tables = false;   // GORDER_NO_CONST_TABLES: K1f tables from global instead of constant memory
+    bool no_spec = false, no_spec_leftover = false;   // GORDER_NO_SPEC, GORDER_NO_SPEC_LEFTOVER: centre pre-pass
+    bool no_inline_leaflets = false;   // GORDER_NO_INLINE_LEAFLETS: separate leaflet_assign_kernel for Global-every-frame
+    bool no_overlap = false;     // GORDER_NO_OVERLAP: one stream instead of the pre / main / post pipeline
+    bool ua_exact = false;       // GORDER_UA_EXACT: bit-exact hydrogen construction everywhere
+    bool verbose = false;        // GORDER_VERBOSE
+    int center_blocks = 0, center_sub = 0;   // GORDER_CENTER_BLOCKS, GORDER_CENTER_SUB
+    int cell_min_heads = 2048, lcell_min_atoms = 4096;   // GORDER_CELL_MIN_HEADS, GORDER_LCELL_MIN_ATOMS
+    static Switches from_env() {
+        Switches w;
+        auto flag = [](const char *n) { return getenv(n) != nullptr; };
+        auto num = [](const char *n, int dflt) { const char *e = getenv(n); return e ? atoi(e) : dflt; };
+        w.mpt = num("GORDER_MPT", 0);
+        w.no_fast = flag("GORDER_NO_FAST"); w.no_const_tables = flag("GORDER_NO_CONST_TABLES");
+        w.no_spec = flag("GORDER_NO_SPEC"); w.no_spec_leftover = flag("GORDER_NO_SPEC_LEFTOVER");
+        w.no_inline_leaflets = flag("GORDER_NO_INLINE_LEAFLETS"); w.no_overlap = flag("GORDER_NO_OVERLAP");
+        w.ua_exact = flag("GORDER_UA_EXACT"); w.verbose = flag("GORDER_VERBOSE");
+        w.center_blocks = num("GORDER_CENTER_BLOCKS", 0); w.center_sub = num("GORDER_CENTER_SUB", 0);
+        w.cell_min_heads = num("GORDER_CELL_MIN_HEADS", 2048); w.lcell_min_atoms = num("GORDER_LCELL_MIN_ATOMS", 4096);
+        return w;
+    }
+};
+
 struct GorderHandle {
     // ---- configuration (deep copy) ----
     GorderSetup s{};
+    Switches sw;
     std::vector<TypeDesc> types;
     std::vector<std::vector<int32_t>> mol_base;       // per type (for error decoding)
     std::vector<std::vector<int32_t>> used_rel;       // per type: used relative atoms (sorted)
@@ -147,7 +175,7 @@ struct GorderHandle {
     bool post_used = false;
     struct SegList { Seg *d = nullptr; int n = 0; };
     SegList seg_membrane[3], seg_geom[3];          // per axis
-    // spherical-clustering leaflets (experimental, gorder_spherical.cuh)
+    // spherical-clustering leaflets (gorder_spherical.cuh)
     bool spherical = false;
     float *d_sph_scratch = nullptr;                       // [max_batch][kSphArrays][sph_pad]
     int sph_pad = 0;                                      // n_membrane rounded up to 4 floats
@@ -165,7 +193,6 @@ struct GorderHandle {
     double prof_ms = 0.0;
     long long prof_n = 0;
 
-    int map_groups = 1;     // order maps: bond types are processed in this many groups (gridDim.z) to keep the maps in L2
     bool fast_ok = false;   // K1f applies (bond_fast_kernel)
     int fast_slot = -1;     // slot of this handle's tables in constant memory (c_fast), -1: global tables
     // speculative Global leaflets (bond_order_kernel<SPEC> + spec_repair_kernel)
@@ -178,13 +205,6 @@ struct GorderHandle {
     float *d_spec_center = nullptr;         // [max_batch]
     unsigned char *d_spec_flag = nullptr;   // [max_batch]
     unsigned *h_spec_counters = nullptr, *d_spec_counters = nullptr;   // mapped pinned: frames speculated, frames repaired
-
-    // persistent pipeline (K1p)
-    bool pipe_ok = false;
-    int pipe_grid = 0, pipe_p_items = 0, pipe_segs_per_item = 0, pipe_lag1 = 3, pipe_lag2 = 6;
-    double *d_pipe_partial0 = nullptr, *d_pipe_partial1 = nullptr;
-    unsigned *d_pipe_ctrl = nullptr;   // [4 * max_batch + 1]: done0, done1, ready0, ready1, work
-    float *d_pipe_est = nullptr, *d_pipe_center = nullptr;
 
     struct GorderXtcDev *xtc_dev = nullptr;   // device-side XTC unpacker (gorder_gpu_run_xtc_device)
     // pinned batches of the trajectory feed (gorder_gpu_run_xtc)
@@ -199,7 +219,7 @@ struct GorderHandle {
     int err_code = 0;
     long long err_detail = -1;
     std::string err_msg;
-    std::mutex mu;
+    std::recursive_mutex mu;   // every entry point that takes a handle holds it (finish -> sync, run_xtc -> submit nest)
 
     void set_error(int code, const std::string &msg, long long detail = -1) {
         if (!err_code) { err_code = code; err_msg = msg; err_detail = detail; }
@@ -306,8 +326,6 @@ void launch_ua(GorderHandle *h, dim3 grid, size_t smem, const float *planes, con
     else { if (h->nvec) launch_ua2<false, true>(h, grid, smem, planes, aux, o); else launch_ua2<false, false>(h, grid, smem, planes, aux, o); }
 }
 
-size_t accum_smem(const GorderHandle *h);
-size_t pipe_smem(const GorderHandle *h) { return std::max(accum_smem(h), (size_t)h->pipe_p_items * 2 * sizeof(double)); }
 size_t accum_smem(const GorderHandle *h) {
     int max_items = 0, max_orders = 0;
     for (auto &t : h->types) { max_items = std::max(max_items, t.n_items); max_orders = std::max(max_orders, t.n_orders); }
@@ -338,11 +356,10 @@ int run_group_center(GorderHandle *h, cudaStream_t st, const GorderHandle::SegLi
     const bool pbc = h->s.handle_pbc != 0;
     // sub-batches whose axis planes fit comfortably in L2 (126 MB): pass 1 re-reads what pass 0 just streamed
     long long sub = n_list;   // (sub-batching for L2 reuse of the axis planes was measured slower: small kernels, see profiles/README.md)
-    if (const char *e = getenv("GORDER_CENTER_SUB")) { int q = atoi(e); if (q >= 1) sub = q; }
+    if (h->sw.center_sub >= 1) sub = h->sw.center_sub;
     for (int axis = 0; axis < 3; axis++) {
         if (!(axis_mask & (1 << axis))) continue;
-        int want = kCenterBlocks;
-        if (const char *e = getenv("GORDER_CENTER_BLOCKS")) { int q = atoi(e); if (q >= 1 && q <= kCenterBlocks) want = q; }
+        const int want = (h->sw.center_blocks >= 1 && h->sw.center_blocks <= kCenterBlocks) ? h->sw.center_blocks : kCenterBlocks;
         const int nblk = std::max(1, std::min(want, segs[axis].n));
         for (int l0 = 0; l0 < n_list; l0 += (int)sub) {
             const int nl = std::min<int>((int)sub, n_list - l0);
@@ -366,7 +383,11 @@ int grow_rows(GorderHandle *h, long long need) {
     long long *ns = nullptr;
     unsigned long long *nc = nullptr;
     CK(cudaMalloc((void **)&ns, cap * row * sizeof(long long)));
-    CK(cudaMalloc((void **)&nc, cap * row * sizeof(unsigned long long)));
+    if (cudaError_t e = cudaMalloc((void **)&nc, cap * row * sizeof(unsigned long long))) {
+        cudaFree(ns);
+        h->set_error(e == cudaErrorMemoryAllocation ? GORDER_ERR_OUT_OF_MEMORY : GORDER_ERR_CUDA, std::string("per-frame rows: ") + cudaGetErrorString(e));
+        return h->err_code;
+    }
     CK(cudaMemsetAsync(ns, 0, cap * row * sizeof(long long), h->stream));
     CK(cudaMemsetAsync(nc, 0, cap * row * sizeof(unsigned long long), h->stream));
     if (h->d_bsum) {
@@ -405,15 +426,16 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     int *list_assign = h->h_list[slot], *list_all = h->h_list[slot] + h->max_batch;
     int n_assign = 0, last_row = 0;
     const long long row0 = s.timewise ? h->n_frames : 0;
+    long long last_fi = h->last_frame_index;   // committed with n_frames once the batch is queued
     for (int f = 0; f < nf; f++) {
         FrameAux &a = ha[f];
         memset(&a, 0, sizeof(a));
         const long long fi = frame_index[f];
-        if (fi <= h->last_frame_index && h->n_frames + f > 0) {
+        if (fi <= last_fi && h->n_frames + f > 0) {
             h->set_error(GORDER_ERR_INVALID_ARGUMENT, "frame_index must be strictly increasing");
             return h->err_code;
         }
-        h->last_frame_index = fi;
+        last_fi = fi;
         a.frame_index = fi;
         a.tw_row = (int)(row0 + f);
         a.manual_norm_row = (int)(fi / (s.step > 0 ? s.step : 1));
@@ -431,10 +453,9 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     FrameAux *da = h->d_aux[slot];
     int *dl_assign = h->d_list[slot], *dl_all = h->d_list[slot] + h->max_batch;
     h->d_est = h->d_est2[slot]; h->d_center = h->d_center2[slot]; h->d_partial = h->d_partial2[slot]; h->d_ticket = h->d_ticket2[slot];
-    const bool use_pipe = h->pipe_ok && n_assign == nf;
     // Global leaflets on every analysed frame (AA/CG): the bond kernel classifies inline, no table pass
-    const bool inline_leaf = !use_pipe && !h->ua && s.leaflet_mode == GORDER_LEAFLET_GLOBAL && s.leaflet_freq_kind == GORDER_FREQ_EVERY &&
-                             s.leaflet_freq <= std::max(1, s.step) && n_assign == nf && !getenv("GORDER_NO_INLINE_LEAFLETS");
+    const bool inline_leaf = !h->ua && s.leaflet_mode == GORDER_LEAFLET_GLOBAL && s.leaflet_freq_kind == GORDER_FREQ_EVERY &&
+                             s.leaflet_freq <= std::max(1, s.step) && n_assign == nf && !h->sw.no_inline_leaflets;
     // Frames already resident on the device: frame setup and the centre passes of this batch go to the
     // pre stream and overlap the bond kernel of the previous batch (both are latency-, not HBM-bound).
     // ... and without any centre pre-pass when the speculative path applies (AccumOut::spec_*)
@@ -442,11 +463,11 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         const unsigned checked = h->h_spec_counters[0], repaired = h->h_spec_counters[1];
         if (checked >= 16 && repaired * 8ull > checked) h->spec_disabled = true;   // thick membrane / thin water: pre-pass is cheaper
     }
-    const bool spec = inline_leaf && h->spec_ok && !h->spec_disabled && !getenv("GORDER_NO_SPEC");
-    const bool overlap = inline_leaf && !spec && !planes_on_main && !h->nvec && !getenv("GORDER_NO_OVERLAP");
+    const bool spec = inline_leaf && h->spec_ok && !h->spec_disabled;
+    const bool overlap = inline_leaf && !spec && !planes_on_main && !h->nvec && !h->sw.no_overlap;
     // speculative path on resident frames: the bond kernels of consecutive batches run back to back on the main stream,
     // the setup of the next batch and the tail (repair + fold) of the previous one run beside them
-    const bool pipelined = spec && !planes_on_main && !s.collect_leaflets && !getenv("GORDER_NO_OVERLAP");
+    const bool pipelined = spec && !planes_on_main && !s.collect_leaflets && !h->sw.no_overlap;
     cudaStream_t sp = (overlap || pipelined) ? h->stream_pre : h->stream;
     cudaStream_t spost = pipelined ? h->stream_post : h->stream;
     if (!pipelined && h->post_used) CK(cudaStreamWaitEvent(h->stream, h->ev_post_any, 0));   // totals are touched by one stream at a time
@@ -478,7 +499,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     } else if (inline_leaf) {
         int rc = run_group_center(h, sp, h->seg_membrane, h->s.n_membrane, 1 << s.leaflet_axis, d_planes, da, dl_assign, n_assign);
         if (rc) return rc;
-    } else if (h->leaf && n_assign > 0 && !use_pipe) {
+    } else if (h->leaf && n_assign > 0) {
         if (s.leaflet_mode == GORDER_LEAFLET_GLOBAL) {
             int rc = run_group_center(h, sp, h->seg_membrane, h->s.n_membrane, 1 << s.leaflet_axis, d_planes, da, dl_assign, n_assign);
             if (rc) return rc;
@@ -493,7 +514,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
             h->n_launches += 3;
         }
         dim3 grid((h->n_molpad + 255) / 256, n_assign);
-        if (h->spherical) {   // experimental (gorder_spherical.cuh)
+        if (h->spherical) {   // gorder_spherical.cuh
             int rc = run_group_center(h, sp, h->seg_membrane, h->s.n_membrane, 7, d_planes, da, dl_assign, n_assign);
             if (rc) return rc;
             spherical_cluster_kernel<<<n_assign, kSphThreads, 0, sp>>>(h->view, d_planes, da, dl_assign, h->d_center, h->d_sph_scratch, h->sph_pad, h->d_sph_upper);
@@ -556,9 +577,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     o.leaf_out = (inline_leaf && s.collect_leaflets) ? h->d_leaf_rows : nullptr;
     o.bsum = bsum; o.bcnt = bcnt; o.map_sum = h->d_map_sum; o.map_cnt = h->d_map_cnt; o.normal_used = h->d_normal_used;
     dim3 grid(h->n_chunks, nf);
-    if (h->map_groups > 1) grid.z = h->map_groups;
     const size_t smem = accum_smem(h);
-    if (use_pipe) CK(cudaMemsetAsync(h->d_pipe_ctrl, 0, (4 * (size_t)h->max_batch + 1) * sizeof(unsigned), h->stream));
     std::pair<cudaEvent_t, cudaEvent_t> *pe = nullptr;
     if (h->profiling) {
         if (h->prof_used == h->prof_events.size()) {
@@ -569,20 +588,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         pe = &h->prof_events[h->prof_used++];
         CK(cudaEventRecord(pe->first, h->stream));
     }
-    if (use_pipe) {
-        PipeParams pp;
-        pp.segs = h->seg_membrane[s.leaflet_axis].d; pp.n_segs = h->seg_membrane[s.leaflet_axis].n;
-        pp.segs_per_item = h->pipe_segs_per_item; pp.n_p_items = h->pipe_p_items; pp.n_h_items = h->n_chunks;
-        pp.n_frames = nf; pp.n_group = s.n_membrane; pp.lag1 = h->pipe_lag1; pp.lag2 = h->pipe_lag2;
-        pp.partial0 = h->d_pipe_partial0; pp.partial1 = h->d_pipe_partial1;
-        pp.done0 = h->d_pipe_ctrl; pp.done1 = h->d_pipe_ctrl + h->max_batch; pp.ready0 = h->d_pipe_ctrl + 2 * h->max_batch;
-        pp.ready1 = h->d_pipe_ctrl + 3 * h->max_batch; pp.work = h->d_pipe_ctrl + 4 * h->max_batch;
-        pp.est = h->d_pipe_est; pp.center = h->d_pipe_center;
-        pp.leaf_out = s.collect_leaflets ? h->d_leaf_rows : nullptr;
-        if (h->mpt == 4) global_leaflet_pipeline_kernel<4><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
-        else if (h->mpt == 2) global_leaflet_pipeline_kernel<2><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
-        else global_leaflet_pipeline_kernel<1><<<h->pipe_grid, kBlock, pipe_smem(h), h->stream>>>(h->view, pp, d_planes, da, o);
-    } else if (h->fast_ok && !getenv("GORDER_NO_FAST")) {
+    if (h->fast_ok && !h->sw.no_fast) {
         if (h->mpt == 4) launch_fast<2>(h, grid, smem, d_planes, da, o, spec);
         else launch_fast<1>(h, grid, smem, d_planes, da, o, spec);
     } else if (spec) {
@@ -624,7 +630,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     if (h->leaf && n_assign > 0 && s.collect_leaflets) {
         int rc = grow_collect(h, &h->d_leaf_collect, &h->leaf_collect_cap, h->n_leaf_collected, h->n_leaf_collected + n_assign, (size_t)h->n_molpad);
         if (rc) return rc;
-        if (use_pipe || inline_leaf) {   // rows 1 + f were written by the accumulation kernel for every frame f
+        if (inline_leaf) {   // rows 1 + f were written by the accumulation kernel for every frame f
             CK(cudaMemcpyAsync(h->d_leaf_collect + (size_t)h->n_leaf_collected * h->n_molpad, h->d_leaf_rows + h->n_molpad,
                                (size_t)nf * h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
         } else {
@@ -634,7 +640,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         for (int a = 0; a < n_assign; a++) h->leaf_frame_index.push_back(frame_index[list_assign[a]]);
         h->n_leaf_collected += n_assign;
     }
-    if (h->leaf && n_assign > 0 && !use_pipe && !inline_leaf) {   // keep the newest table for the frames of the next batch
+    if (h->leaf && n_assign > 0 && !inline_leaf) {   // keep the newest table for the frames of the next batch
         CK(cudaMemcpyAsync(h->d_leaf_rows, h->d_leaf_rows + (size_t)n_assign * h->n_molpad, h->n_molpad, cudaMemcpyDeviceToDevice, h->stream));
         h->have_leaflets = true;
         h->cur_leaflet_frame = frame_index[list_assign[n_assign - 1]];
@@ -653,6 +659,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     }
     for (int f = 0; f < nf; f++) h->frame_index_done.push_back(frame_index[f]);
     h->n_frames += nf;
+    h->last_frame_index = last_fi;
     return GORDER_OK;
 }
 
@@ -705,6 +712,7 @@ void gorder_gpu_destroy(GorderHandle *h) {
 
 static int create_impl(const GorderSetup *s, GorderHandle *h) {
     h->s = *s;
+    h->sw = Switches::from_env();
     const bool ua = s->kind == GORDER_KIND_UA;
     h->ua = ua;
     h->leaf = s->leaflet_mode != GORDER_LEAFLET_NONE;
@@ -728,14 +736,20 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         else if (s->leaflet_mode == GORDER_LEAFLET_LOCAL && !(s->leaflet_radius > 0.0f)) what = "leaflet_radius";
         if (what) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, (std::string("value out of range: ") + what).c_str()); return h->err_code; }
     }
-    h->spherical = s->leaflet_mode == GORDER_LEAFLET_SPHERICAL && getenv("GORDER_EXPERIMENTAL_SPHERICAL");
-    if ((s->leaflet_mode < GORDER_LEAFLET_NONE || s->leaflet_mode > GORDER_LEAFLET_MANUAL) && !h->spherical) {
-        h->set_error(GORDER_ERR_INVALID_ARGUMENT, s->leaflet_mode == GORDER_LEAFLET_SPHERICAL
-                     ? "spherical-clustering leaflets are not computed on the device yet: pass the table with GORDER_LEAFLET_MANUAL"
-                     : "unknown leaflet mode");
-        return h->err_code;
-    }
+    h->spherical = s->leaflet_mode == GORDER_LEAFLET_SPHERICAL;
+    if (s->leaflet_mode < GORDER_LEAFLET_NONE || s->leaflet_mode > GORDER_LEAFLET_SPHERICAL) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "unknown leaflet mode"); return h->err_code; }
     if (h->spherical && (s->n_membrane < 2 || !s->membrane)) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "spherical clustering needs the ClusterHeads group in `membrane`"); return h->err_code; }
+
+    for (int t = 0; t < s->n_moltypes; t++) {   // the classifiers read the head (and the methyls) of every molecule: a missing one would index before the type's planes
+        const GorderMolType &m = s->moltypes[t];
+        const int lm = s->leaflet_mode;
+        const bool needs_head = lm == GORDER_LEAFLET_GLOBAL || lm == GORDER_LEAFLET_LOCAL || lm == GORDER_LEAFLET_INDIVIDUAL || lm == GORDER_LEAFLET_SPHERICAL;
+        if (needs_head && m.head_rel < 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "leaflet classification needs head_rel >= 0 for every molecule type", t); return h->err_code; }
+        if (m.n_methyls < 0 || (m.n_methyls > 0 && !m.methyl_rel)) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "bad methyl table", t); return h->err_code; }
+        for (int k = 0; k < m.n_methyls; k++) if (m.methyl_rel[k] < 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "negative methyl relative index", t); return h->err_code; }
+        if (lm == GORDER_LEAFLET_INDIVIDUAL && m.n_methyls == 0) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "individual leaflet classification needs methyls", t); return h->err_code; }
+        if (lm == GORDER_LEAFLET_MANUAL && (!m.manual_leaflets || m.n_manual_leaflet_frames <= 0)) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "manual leaflet classification needs a table", t); return h->err_code; }
+    }
 
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || s->device < 0 || s->device >= n_dev) {
@@ -755,7 +769,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     // full tiles (kBlock * mpt molecules: the fast kernel's unit; a partial last tile runs the generic body)
     h->mpt = (max_mol >= 8 * kBlock * 4 || (max_mol >= kBlock * 4 && max_mol % (kBlock * 4) == 0)) ? 4
            : (max_mol >= 8 * kBlock * 2 || (max_mol >= kBlock * 2 && max_mol % (kBlock * 2) == 0)) ? 2 : 1;
-    if (const char *e = getenv("GORDER_MPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->mpt = v; }
+    if (h->sw.mpt == 1 || h->sw.mpt == 2 || h->sw.mpt == 4) h->mpt = h->sw.mpt;
     if (ua) h->mpt = 1;
 
     // ---- native layout -------------------------------------------------------------------------
@@ -927,9 +941,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     for (int k = 0; k < 6; k++) v.shape.dims[k] = s->geom_dims[k];
     v.manual_leaflets = d_mleaf; v.manual_normals = d_mnorm;
     v.err = h->d_err; v.err_detail = h->d_err_detail;
-    v.debug_nocompute = getenv("GORDER_DEBUG_NOCOMPUTE") ? 1 : 0;
-    v.ua_exact = getenv("GORDER_UA_EXACT") ? 1 : 0;
-    v.l2_hints = getenv("GORDER_L2_HINTS") ? atoi(getenv("GORDER_L2_HINTS")) : 0;
+    v.ua_exact = h->sw.ua_exact ? 1 : 0;
     // rotation constants with the host libm (the reference's sin/cos of the same f32 angles)
     v.tet_s = sinf(1.910633f); v.tet_c = cosf(1.910633f);
     v.tet_half_s = sinf(0.9553165f); v.tet_half_c = cosf(0.9553165f);
@@ -948,7 +960,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         std::vector<int32_t> left;
         for (int i = 0; i < s->n_membrane; i++) if (!mem_done[s->membrane[i]]) left.push_back(s->membrane[i]);
         mem_left = (long long)left.size();
-        if (getenv("GORDER_NO_SPEC_LEFTOVER") && mem_left) mem_cover = false;
+        if (h->sw.no_spec_leftover && mem_left) mem_cover = false;
         else if (mem_left && (rc = build_segs(h, &h->seg_left, left.data(), (int)left.size(), s->leaflet_axis))) return rc;
     }
 
@@ -964,18 +976,6 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         v.map.nx = (int)roundf(sx / s->map_bin[0]) + 1; v.map.ny = (int)roundf(sy / s->map_bin[1]) + 1;
         v.map.x0 = s->map_span_x[0]; v.map.y0 = s->map_span_y[0]; v.map.binx = s->map_bin[0]; v.map.biny = s->map_bin[1];
         v.map.n_bins = (long long)v.map.nx * v.map.ny;
-    }
-
-    // (opt-in: measured on S-AA-large, 64 types x 361 x 361 bins: 1 group 4.69e10, 4 groups 4.78e10, 10 groups 4.56e10,
-    //  32 groups 4.15e10 samples/s -- the scatter is bound by the L2 atomic units, not by map residency)
-    if (v.map.enabled && !ua && getenv("GORDER_MAP_GROUPS")) {
-        // maps of one bond type: 3 leaflets x n_bins x (sum + count); keep the concurrently updated ones within ~48 MB of L2
-        const double per_slot = 3.0 * (double)v.map.n_bins * 16.0;
-        const int fit = std::max(1, (int)(48e6 / per_slot));
-        int max_items = 1;
-        for (auto &t : h->types) max_items = std::max(max_items, t.n_items);
-        h->map_groups = std::min(max_items, (max_items + fit - 1) / fit);
-        if (const char *e = getenv("GORDER_MAP_GROUPS")) { int q = atoi(e); if (q >= 1) h->map_groups = std::min(q, max_items); }
     }
 
     // ---- accumulators ----------------------------------------------------------------------------
@@ -1012,9 +1012,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     if (h->leaf) { if ((rc = dev_alloc(h, &h->d_leaf_rows, (1 + B) * (size_t)h->n_molpad, true))) return rc; }
     if (s->normal_mode == GORDER_NORMAL_DYNAMIC && s->handle_pbc) {
         // cell list for the neighbour search unless the head group is small (brute force keeps the oracle's summation order)
-        int min_heads = 2048;
-        if (const char *e = getenv("GORDER_CELL_MIN_HEADS")) min_heads = atoi(e);
-        h->use_cells = s->n_normal_heads >= min_heads;
+        h->use_cells = s->n_normal_heads >= h->sw.cell_min_heads;
         if (h->use_cells) {
             h->cells_cap = kCellBudget;
             if ((rc = dev_alloc(h, &h->d_head_cell, B * (size_t)s->n_normal_heads))) return rc;
@@ -1024,9 +1022,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         }
     }
     if (s->leaflet_mode == GORDER_LEAFLET_LOCAL && s->handle_pbc) {
-        int min_atoms = 4096;   // below: brute force over the membrane group
-        if (const char *e = getenv("GORDER_LCELL_MIN_ATOMS")) min_atoms = atoi(e);
-        h->use_lcells = s->n_membrane >= min_atoms;
+        h->use_lcells = s->n_membrane >= h->sw.lcell_min_atoms;   // below: brute force over the membrane group
         if (h->use_lcells) {
             h->lcells_cap = kLCellMaxDim * kLCellMaxDim;
             if ((rc = dev_alloc(h, &h->d_matom_cell, B * (size_t)s->n_membrane))) return rc;
@@ -1061,7 +1057,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     }
 
     h->fast_ok = !ua && !h->nvec && !h->extra && s->handle_pbc && (h->mpt == 2 || h->mpt == 4);
-    if (h->fast_ok && s->n_moltypes <= kFastTypes && (int)bonds.size() <= kFastBonds && h->device < 64 && !getenv("GORDER_NO_CONST_TABLES")) {
+    if (h->fast_ok && s->n_moltypes <= kFastTypes && (int)bonds.size() <= kFastBonds && h->device < 64 && !h->sw.no_const_tables) {
         {
             std::lock_guard<std::mutex> lock(g_fast_mu);
             for (int i = 0; i < kFastSlots && h->fast_slot < 0; i++)
@@ -1081,7 +1077,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     // no geometry / maps, membrane covered by the bond kernel's loads (above)
     h->spec_ok = mem_cover && mem_counted + mem_left == s->n_membrane && !ua && !h->nvec && !h->extra && s->handle_pbc &&
                  s->leaflet_mode == GORDER_LEAFLET_GLOBAL && s->leaflet_freq_kind == GORDER_FREQ_EVERY && s->leaflet_freq <= std::max(1, s->step) &&
-                 s->leaflet_axis == s->normal_axis && h->n_chunks > 0 && !getenv("GORDER_NO_SPEC");
+                 s->leaflet_axis == s->normal_axis && h->n_chunks > 0 && !h->sw.no_spec;
     if (h->spec_ok) {
         if ((rc = dev_alloc(h, &h->d_spec_ref, 4, true))) return rc;
         if ((rc = dev_alloc(h, &h->d_spec_sum, 2 * B * (size_t)h->n_chunks))) return rc;
@@ -1099,7 +1095,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         CK(cudaHostGetDevicePointer((void **)&h->d_spec_counters, h->h_spec_counters, 0));
     }
 
-    if (h->spherical) {   // experimental: scratch of spherical_cluster_kernel and the head -> ClusterHeads position table
+    if (h->spherical) {   // scratch of spherical_cluster_kernel and the head -> ClusterHeads position table
         std::vector<int> pos_of(s->n_atoms, -1), index((size_t)h->n_molpad, 0);
         for (int i = 0; i < s->n_membrane; i++) {
             if (s->membrane[i] < 0 || s->membrane[i] >= s->n_atoms) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "group atom out of range", s->membrane[i]); return h->err_code; }
@@ -1119,37 +1115,6 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         if ((rc = dev_alloc(h, &h->d_sph_upper, B * (size_t)s->n_membrane))) return rc;
     }
 
-    // persistent pipeline: AA/CG, static normal, PBC, Global leaflets on every analysed frame, no geometry / maps
-    h->pipe_ok = !ua && !h->nvec && !h->extra && s->handle_pbc && s->leaflet_mode == GORDER_LEAFLET_GLOBAL &&
-                 s->leaflet_freq_kind == GORDER_FREQ_EVERY && s->leaflet_freq <= std::max(1, s->step) && getenv("GORDER_PIPELINE");
-    // (experimental, opt-in: on S-CG it is only ~2% faster than the separate kernels because the step is
-    //  latency / issue bound, not HBM bound; see profiles/README.md)
-    if (h->pipe_ok) {
-        const int nseg = h->seg_membrane[s->leaflet_axis].n;
-        h->pipe_segs_per_item = 4;
-        h->pipe_p_items = std::max(1, (nseg + h->pipe_segs_per_item - 1) / h->pipe_segs_per_item);
-        if ((rc = dev_alloc(h, &h->d_pipe_partial0, B * h->pipe_p_items * 2))) return rc;
-        if ((rc = dev_alloc(h, &h->d_pipe_partial1, B * h->pipe_p_items))) return rc;
-        if ((rc = dev_alloc(h, &h->d_pipe_ctrl, 4 * B + 1, true))) return rc;
-        if ((rc = dev_alloc(h, &h->d_pipe_est, B))) return rc;
-        if ((rc = dev_alloc(h, &h->d_pipe_center, B))) return rc;
-        int per_sm = 0, n_sm = 0;
-        const size_t smem = pipe_smem(h);
-        cudaError_t e1 = h->mpt == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, global_leaflet_pipeline_kernel<4>, kBlock, smem)
-                       : h->mpt == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, global_leaflet_pipeline_kernel<2>, kBlock, smem)
-                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, global_leaflet_pipeline_kernel<1>, kBlock, smem);
-        CK(e1);
-        CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
-        if (const char *e = getenv("GORDER_PIPE_CTAS_PER_SM")) { int q = atoi(e); if (q >= 1 && q < per_sm) per_sm = q; }
-        h->pipe_grid = per_sm * n_sm;   // every CTA must be resident (flag waits)
-        // dependencies of an item should have been popped a full wave (pipe_grid items) earlier
-        const int per_slot = 2 * h->pipe_p_items + h->n_chunks;
-        h->pipe_lag1 = std::max(1, (h->pipe_grid + per_slot - 1) / per_slot + 1);
-        h->pipe_lag2 = 2 * h->pipe_lag1;
-        if (const char *e = getenv("GORDER_PIPE_LAG")) { int q = atoi(e); if (q >= 1) { h->pipe_lag1 = q; h->pipe_lag2 = 2 * q; } }
-        if (h->pipe_grid <= 0 || pipe_smem(h) > 48 * 1024) h->pipe_ok = false;
-    }
-
     // dynamic shared memory of the accumulation kernels (small; no opt-in needed below 48 KB)
     if (accum_smem(h) > 48 * 1024) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "too many order slots per molecule type for shared memory"); return h->err_code; }
     CK(cudaDeviceSynchronize());
@@ -1162,7 +1127,7 @@ int gorder_gpu_create(const GorderSetup *setup, GorderHandle **out) {
     GorderHandle *h = new GorderHandle();
     int rc = create_impl(setup, h);
     if (rc) {
-        if (getenv("GORDER_VERBOSE")) fprintf(stderr, "gorder_gpu_create failed: %s\n", h->err_msg.c_str());
+        if (h->sw.verbose || getenv("GORDER_VERBOSE")) fprintf(stderr, "gorder_gpu_create failed: %s\n", h->err_msg.c_str());
         // pointers inside the copied setup are not owned
         gorder_gpu_destroy(h);
         return rc;
@@ -1226,8 +1191,9 @@ static int launch_relayout(GorderHandle *h, const float *d_xyz, float *d_planes,
 }
 
 int gorder_gpu_submit(GorderHandle *h, const float *xyz, const float *box, const int64_t *frame_index, int32_t n_frames) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (int rc = check_args(h, xyz, box, frame_index, n_frames)) return rc;
-    std::lock_guard<std::mutex> lock(h->mu);
     const size_t fstride = (size_t)h->s.n_atoms * 3;
     for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
         const int nf = std::min(h->max_batch, n_frames - f0);
@@ -1247,8 +1213,9 @@ int gorder_gpu_submit(GorderHandle *h, const float *xyz, const float *box, const
 }
 
 int gorder_gpu_submit_device(GorderHandle *h, const float *d_xyz, const float *d_box, const int64_t *frame_index, int32_t n_frames) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (int rc = check_args(h, d_xyz, d_box, frame_index, n_frames)) return rc;
-    std::lock_guard<std::mutex> lock(h->mu);
     const size_t fstride = (size_t)h->s.n_atoms * 3;
     for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
         const int nf = std::min(h->max_batch, n_frames - f0);
@@ -1270,8 +1237,9 @@ int gorder_gpu_native_layout(GorderHandle *h, int64_t *frame_floats, int32_t *pl
 }
 
 int gorder_gpu_submit_native(GorderHandle *h, const float *planes_host, const float *box, const int64_t *frame_index, int32_t n_frames) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (int rc = check_args(h, planes_host, box, frame_index, n_frames)) return rc;
-    std::lock_guard<std::mutex> lock(h->mu);
     const size_t fstride = (size_t)h->frame_floats;
     for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
         const int nf = std::min(h->max_batch, n_frames - f0);
@@ -1289,8 +1257,9 @@ int gorder_gpu_submit_native(GorderHandle *h, const float *planes_host, const fl
 }
 
 int gorder_gpu_submit_native_device(GorderHandle *h, const float *d_planes, const float *d_box, const int64_t *frame_index, int32_t n_frames) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (int rc = check_args(h, d_planes, d_box, frame_index, n_frames)) return rc;
-    std::lock_guard<std::mutex> lock(h->mu);
     const size_t fstride = (size_t)h->frame_floats;
     for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
         const int nf = std::min(h->max_batch, n_frames - f0);
@@ -1304,19 +1273,21 @@ int gorder_gpu_submit_native_device(GorderHandle *h, const float *d_planes, cons
 
 int gorder_gpu_reserve_frames(GorderHandle *h, int64_t n_frames) {
     if (!h || n_frames < 0) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (h->err_code) return h->err_code;
     cudaSetDevice(h->device);
-    std::lock_guard<std::mutex> lock(h->mu);
     return grow_rows(h, n_frames);
 }
 
 int gorder_gpu_set_leaflets(GorderHandle *h, const uint8_t *table, int64_t frame_index) {
     if (!h || !table) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
+    if (h->err_code) return h->err_code;
     if (!h->leaf) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "leaflets are not enabled"); return h->err_code; }
     cudaSetDevice(h->device);
     std::vector<unsigned char> row(h->n_molpad, GORDER_UPPER);
     for (auto &td : h->types) for (int m = 0; m < td.n_mol; m++) row[td.molpad0 + m] = table[td.mol0 + m];
-    CK(cudaStreamSynchronize(h->stream));
+    if (int rc = sync_all(h)) return rc;   // batches in flight (any stream) may still read row 0
     CK(cudaMemcpy(h->d_leaf_rows, row.data(), row.size(), cudaMemcpyHostToDevice));
     h->have_leaflets = true; h->cur_leaflet_frame = frame_index;
     return GORDER_OK;
@@ -1324,6 +1295,7 @@ int gorder_gpu_set_leaflets(GorderHandle *h, const uint8_t *table, int64_t frame
 
 int gorder_gpu_sync(GorderHandle *h) {
     if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (h->err_code) return h->err_code;
     cudaSetDevice(h->device);
     if (int rc = sync_all(h)) return rc;
@@ -1332,6 +1304,7 @@ int gorder_gpu_sync(GorderHandle *h) {
 
 int gorder_gpu_result_sizes(GorderHandle *h, GorderResults *r) {
     if (!h || !r) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     r->n_slots = h->n_slots; r->n_frames = h->n_frames; r->n_map_bins = h->view.map.n_bins;
     r->map_nx = h->view.map.enabled ? h->view.map.nx : 0; r->map_ny = h->view.map.enabled ? h->view.map.ny : 0;
     r->n_leaflet_frames = h->n_leaf_collected; r->n_molecules_total = h->n_mol_total;
@@ -1340,6 +1313,7 @@ int gorder_gpu_result_sizes(GorderHandle *h, GorderResults *r) {
 
 int gorder_gpu_finish(GorderHandle *h, GorderResults *r) {
     if (!h || !r) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (int rc = gorder_gpu_sync(h)) return rc;
     gorder_gpu_result_sizes(h, r);
     const size_t na = (size_t)h->n_slots * 3;
@@ -1389,6 +1363,7 @@ int gorder_gpu_finish(GorderHandle *h, GorderResults *r) {
 
 int gorder_gpu_accumulator_block(GorderHandle *h, void **d_ptr, int64_t *n_words) {
     if (!h || !d_ptr || !n_words) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     cudaSetDevice(h->device);
     if (int rc = sync_all(h)) return rc;
     *d_ptr = h->d_block; *n_words = h->block_words;
@@ -1397,6 +1372,7 @@ int gorder_gpu_accumulator_block(GorderHandle *h, void **d_ptr, int64_t *n_words
 
 int gorder_gpu_read_block(GorderHandle *h, void *d_dst) {
     if (!h || !d_dst) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     cudaSetDevice(h->device);
     if (int rc = sync_all(h)) return rc;
     CK(cudaMemcpyAsync(d_dst, h->d_block, (size_t)h->block_words * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
@@ -1406,6 +1382,7 @@ int gorder_gpu_read_block(GorderHandle *h, void *d_dst) {
 
 int gorder_gpu_write_block(GorderHandle *h, const void *d_src) {
     if (!h || !d_src) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     cudaSetDevice(h->device);
     if (int rc = sync_all(h)) return rc;
     CK(cudaMemcpyAsync(h->d_block, d_src, (size_t)h->block_words * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
@@ -1427,6 +1404,7 @@ static int drain_profile(GorderHandle *h) {
 
 int gorder_gpu_profile(GorderHandle *h, int enable) {
     if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     cudaSetDevice(h->device);
     if (int rc = drain_profile(h)) return rc;
     h->profiling = enable != 0;
@@ -1435,6 +1413,7 @@ int gorder_gpu_profile(GorderHandle *h, int enable) {
 
 int gorder_gpu_profile_read(GorderHandle *h, double *hot_kernel_ms, int64_t *hot_kernel_launches) {
     if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     cudaSetDevice(h->device);
     if (int rc = drain_profile(h)) return rc;
     if (hot_kernel_ms) *hot_kernel_ms = h->prof_ms;
@@ -1445,6 +1424,7 @@ int gorder_gpu_profile_read(GorderHandle *h, double *hot_kernel_ms, int64_t *hot
 
 int gorder_gpu_stats(GorderHandle *h, int64_t *kernel_launches, int64_t *frames) {
     if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (kernel_launches) *kernel_launches = h->n_launches;
     if (frames) *frames = h->n_frames;
     return GORDER_OK;
@@ -1452,6 +1432,7 @@ int gorder_gpu_stats(GorderHandle *h, int64_t *kernel_launches, int64_t *frames)
 
 int gorder_gpu_speculation_stats(GorderHandle *h, int32_t *enabled, int64_t *frames_speculated, int64_t *frames_repaired) {
     if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     cudaSetDevice(h->device);
     if (int rc = sync_all(h)) return rc;
     if (enabled) *enabled = (h->spec_ok && !h->spec_disabled) ? 1 : 0;
@@ -1462,6 +1443,7 @@ int gorder_gpu_speculation_stats(GorderHandle *h, int32_t *enabled, int64_t *fra
 
 int gorder_gpu_fence(GorderHandle *h) {
     if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     cudaSetDevice(h->device);
     if (h->post_used) CK(cudaStreamWaitEvent(h->stream, h->ev_post_any, 0));
     return GORDER_OK;

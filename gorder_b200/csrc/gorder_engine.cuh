@@ -114,8 +114,6 @@ struct DeviceView {
     const float *manual_normals;
     // UA rotation constants (sin, cos) computed on the host with the same libm as the reference
     float tet_s, tet_c, tet_half_s, tet_half_c, ch3_s, ch3_c;
-    int l2_hints;             // L2 eviction-priority hints on the plane loads
-    int debug_nocompute;      // profiling experiment only: load the planes, skip the arithmetic
     int ua_exact;             // UA: bit-exact hydrogen construction everywhere (default: only with geometry / maps)
     // error word
     int *err;                 // [0] code, [1] unused

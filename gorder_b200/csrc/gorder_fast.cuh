@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
     constexpr int kPrefetchAhead = 2;   // measured: 1 -> 0.78, 2 -> 0.80, 3 -> 0.78, 6 -> 0.77, 11 -> 0.75 of the HBM peak
     constexpr unsigned kSliceBytes = kBlock * MPT * sizeof(float);
     const float *tile0 = planes + (size_t)f * v.frame_floats + mol_offset(td, ch.first_mol);
-    if (threadIdx.x == 0 && v.l2_hints >= 0 && LEAF && (SPEC || o.inline_center)) l2_prefetch_bulk(tile0 + td.head_off + v.leaflet_axis * mpad, kSliceBytes);
+    if (threadIdx.x == 0 && LEAF && (SPEC || o.inline_center)) l2_prefetch_bulk(tile0 + td.head_off + v.leaflet_axis * mpad, kSliceBytes);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
     FastConst k;
     k.o1 = (c1 - c0) * mpad; k.o2 = (c2 - c0) * mpad;
     auto prefetch_bond = [&](int bb) {
-        if (threadIdx.x != 0 || bb >= nb || v.l2_hints < 0) return;
+        if (threadIdx.x != 0 || bb >= nb) return;
         const BondItem it = s_bonds[bb];
         const float *t0 = tile0 + c0 * mpad;
         if ((it.a_off & 3) == 0) {

@@ -26,14 +26,8 @@ __device__ __forceinline__ void raise_error(const DeviceView &v, int code, long 
     if (atomicCAS(v.err, 0, code) == 0) *v.err_detail = detail;
 }
 
-// L2 eviction-priority hints (createpolicy + ld.global.L2::cache_hint): the accumulation kernel
-// streams every plane once (evict_first), the centre passes want the axis planes to survive from
-// pass 0 to pass 1 (evict_last).
-__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
+// L2 eviction-priority hint (createpolicy + ld.global.L2::cache_hint): the centre passes want the axis planes to
+// survive from pass 0 to pass 1 (evict_last).
 __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -49,21 +43,15 @@ template <int N> struct Vec;
 template <> struct Vec<1> {
     float v[1];
     __device__ __forceinline__ void load(const float *p) { v[0] = __ldg(p); }
-    __device__ __forceinline__ void load_hint(const float *p, unsigned long long) { load(p); }
 };
 template <> struct Vec<2> {
     float v[2];
     __device__ __forceinline__ void load(const float *p) { float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; }
-    __device__ __forceinline__ void load_hint(const float *p, unsigned long long) { load(p); }
 };
 template <> struct Vec<4> {
     float v[4];
     __device__ __forceinline__ void load(const float *p) {
         float4 t = __ldg(reinterpret_cast<const float4 *>(p));
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-    __device__ __forceinline__ void load_hint(const float *p, unsigned long long pol) {
-        float4 t = ldg_hint4(p, pol);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
 };
@@ -890,9 +878,9 @@ __device__ __forceinline__ void warp_commit(int *s_acc, int lane, int su, int sl
 // CTA epilogue: add the per-warp partials of every order slot to this frame's accumulators.
 template <bool LEAF, bool EXTRA>
 __device__ __forceinline__ void cta_flush(const DeviceView &v, const AccumOut &o, const int *s_acc, int n_orders, int slot0, int tw_row,
-                                          int cnt_total, int cnt_up, int i_lo = 0, int i_hi = 0x7fffffff) {
+                                          int cnt_total, int cnt_up) {
     constexpr int NA = AccLayout<LEAF, EXTRA>::N;
-    for (int i = i_lo + threadIdx.x; i < min(n_orders, i_hi); i += blockDim.x) {
+    for (int i = threadIdx.x; i < n_orders; i += blockDim.x) {
         long long acc[NA];
 #pragma unroll
         for (int k = 0; k < NA; k++) acc[k] = 0;
@@ -1145,60 +1133,23 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
     };
 
     const float *base = base_mol;
-    // Software pipeline (streaming variant): the planes of bond b+1 are requested before bond b is
-    // evaluated, so every warp keeps two iterations of 128-bit loads in flight (the kernel is bound by
-    // memory latency, not by issue slots: profiles/README.md).
-    const unsigned long long pol_first = l2_policy_evict_first();
-    constexpr bool PREFETCH = false;   // measured: no gain (the rotation costs 24 MOVs per iteration), kept for experiments
-    Vec<MPT> x1, y1, z1, x2, y2, z2, nx1, ny1, nz1, nx2, ny2, nz2;
+    Vec<MPT> x1, y1, z1, x2, y2, z2;
 #pragma unroll
-    for (int j = 0; j < MPT; j++) {
-        x1.v[j] = y1.v[j] = z1.v[j] = x2.v[j] = y2.v[j] = z2.v[j] = 0.0f;
-        nx1.v[j] = ny1.v[j] = nz1.v[j] = nx2.v[j] = ny2.v[j] = nz2.v[j] = 0.0f;
-    }
-    if (PREFETCH && nb > 0 && active) {
-        const BondItem b0 = s_bonds[0];
-        const int a_off = b0.a_off & ~15;
-        nx1.load(base + a_off + o0); ny1.load(base + a_off + o1); nz1.load(base + a_off + o2);
-        nx2.load(base + b0.b_off + o0); ny2.load(base + b0.b_off + o1); nz2.load(base + b0.b_off + o2);
-    }
-    // gridDim.z > 1 (order maps): CTA z handles the z-th group of bond types, so that the CTAs resident at any time
-    // scatter into the maps of a few bond types only and the atomics stay in L2 (the maps of all types do not fit)
-    const int b_lo = gridDim.z > 1 ? (int)((long long)nb * blockIdx.z / gridDim.z) : 0;
-    const int b_hi = gridDim.z > 1 ? (int)((long long)nb * (blockIdx.z + 1) / gridDim.z) : nb;
-    for (int b = b_lo; b < b_hi; b++) {
-        if (PREFETCH) {
-            // rotate: the prefetched registers become the current bond ...
-            x1 = nx1; y1 = ny1; z1 = nz1; x2 = nx2; y2 = ny2; z2 = nz2;
-            // ... and the next bond's planes are requested now
-            if (b + 1 < nb) {
-                const BondItem bn = s_bonds[b + 1];
-                const int reuse = bn.a_off & 3, a_off = bn.a_off & ~15;
-                if (reuse == 2) { nx1 = x2; ny1 = y2; nz1 = z2; }       // next first atom = this bond's second atom
-                // reuse == 1: next first atom = this bond's first atom (nx1 already holds it)
-                if (active) {
-                    if (reuse == 0) { nx1.load(base + a_off + o0); ny1.load(base + a_off + o1); nz1.load(base + a_off + o2); }
-                    nx2.load(base + bn.b_off + o0); ny2.load(base + bn.b_off + o1); nz2.load(base + bn.b_off + o2);
-                }
-            }
-        } else {
+    for (int j = 0; j < MPT; j++) x1.v[j] = y1.v[j] = z1.v[j] = x2.v[j] = y2.v[j] = z2.v[j] = 0.0f;
+    for (int b = 0; b < nb; b++) {
+        {
             const BondItem bi = s_bonds[b];
             // low bits of a_off: 1 = first atom is the previous bond's first atom, 2 = ... second atom;
             // 4 / 8 = first / second atom is a membrane atom seen here for the first time (speculative centre)
-            const int reuse = (b == b_lo) ? 0 : (bi.a_off & 3), a_off = bi.a_off & ~15;
+            const int reuse = bi.a_off & 3, a_off = bi.a_off & ~15;
             if (reuse == 2) { x1 = x2; y1 = y2; z1 = z2; }
             if (active) {
-                if (v.l2_hints) {   // stream through L2 without displacing the axis planes the centre passes keep there
-                    if (reuse == 0) { x1.load_hint(base + a_off + o0, pol_first); y1.load_hint(base + a_off + o1, pol_first); z1.load_hint(base + a_off + o2, pol_first); }
-                    x2.load_hint(base + bi.b_off + o0, pol_first); y2.load_hint(base + bi.b_off + o1, pol_first); z2.load_hint(base + bi.b_off + o2, pol_first);
-                } else {
-                    if (reuse == 0) { x1.load(base + a_off + o0); y1.load(base + a_off + o1); z1.load(base + a_off + o2); }
-                    x2.load(base + bi.b_off + o0); y2.load(base + bi.b_off + o1); z2.load(base + bi.b_off + o2);
-                }
+                if (reuse == 0) { x1.load(base + a_off + o0); y1.load(base + a_off + o1); z1.load(base + a_off + o2); }
+                x2.load(base + bi.b_off + o0); y2.load(base + bi.b_off + o1); z2.load(base + bi.b_off + o2);
             }
         }
         if (SPEC) {
-            const int cf = PREFETCH ? 0 : s_bonds[b].a_off;
+            const int cf = s_bonds[b].a_off;
             if (cf & 4) {
 #pragma unroll
                 for (int j = 0; j < MPT; j++) spec_add(z1.v[j], valid[j]);
@@ -1209,13 +1160,6 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
             }
         }
         int st = 0, su = 0, ct = 0, cu = 0;   // total / upper (lower = total - upper)
-        if (v.debug_nocompute) {   // memory-pattern ceiling experiment (profiles/README.md): loads only
-#pragma unroll
-            for (int j = 0; j < MPT; j++)
-                st += __float_as_int(x1.v[j]) ^ __float_as_int(y1.v[j]) ^ __float_as_int(z1.v[j]) ^ __float_as_int(x2.v[j]) ^ __float_as_int(y2.v[j]) ^ __float_as_int(z2.v[j]);
-            warp_commit<LEAF, EXTRA>(s_acc + ((size_t)warp * nb + b) * NA, lane, st, 0, 0, 0);
-            continue;
-        }
         // bond vectors of the thread's MPT molecules.  The fold's exact fast path
         //   fl(fl(fl(fl(d + L/2) + L) - L) - L/2)
         // is evaluated unconditionally; ONE predicate per iteration sends the (rare) warp that holds a bond
@@ -1293,7 +1237,7 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
         if (lane == 0) { s_dsum[0][warp] = ds; s_dsum[1][warp] = dq; s_dabs[warp] = a; }
     }
     __syncthreads();
-    cta_flush<LEAF, EXTRA>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1], b_lo, b_hi);
+    cta_flush<LEAF, EXTRA>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
     if (SPEC && threadIdx.x == 0) {
         double ds = 0.0, dq = 0.0;
         float p0 = 0.0f, p1 = CUDART_INF_F, p2 = 0.0f;
@@ -1404,207 +1348,6 @@ __global__ void __launch_bounds__(kBlock) spec_repair_kernel(DeviceView v, Repai
                 atomicAdd(&o.bcnt[rb + from], ~0ull);
             }
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1p: persistent pipeline for the headline configuration (AA/CG, static normal, PBC, Global
-// leaflets assigned every analysed frame, no geometry / maps).  One launch per batch; the three
-// dependent phases of a frame
-//     P0(f): partial sums of cos / sin of the leaflet-axis planes      (leaflets.rs:187, pass 0)
-//     P1(f): partial sums of min_image(z - estimate(f))                 (pass 1)
-//     H(f):  centre(f) -> per-lipid leaflet (leaflets.rs:711-732) -> bond engine (bond.rs:396-446)
-// are work items of ONE ordered list  ... P0(s) P1(s-1) H(s-2) ...  that resident CTAs pop with an
-// atomic counter.  An item only waits (flag spin) on items EARLIER in the list, which are already
-// owned by running CTAs, so the kernel cannot deadlock as long as every CTA is resident (the host
-// sizes the grid from the occupancy API).  The axis planes of frame f are read from HBM by P0(f)
-// and found in L2 by P1(f) and H(f) two slots later: HBM traffic stays at the algorithmic 12 B per
-// atom instead of 20 B for the three-kernel version.  Deterministic: partials are written per item
-// and summed in index order by whoever needs them.
-// ---------------------------------------------------------------------------------------------
-struct PipeParams {
-    const Seg *segs;       // runs of the membrane group's leaflet-axis component
-    int n_segs, segs_per_item, n_p_items, n_h_items, n_frames, n_group;
-    int lag1, lag2;        // P1(f) sits in slot f + lag1, H(f) in slot f + lag2 (dependencies one wave behind)
-    double *partial0;      // [F][n_p_items][2]
-    double *partial1;      // [F][n_p_items]
-    unsigned *done0, *done1;   // [F] finished items per frame and pass
-    unsigned *ready0, *ready1; // [F] estimate / centre published
-    float *est, *center;       // [F]
-    unsigned *work;        // [1]
-    unsigned char *leaf_out;   // rows [(1 + f)][n_molpad] when the tables are collected, else nullptr
-};
-
-__device__ __forceinline__ void spin_until(const unsigned *flag, unsigned target) {
-    const volatile unsigned *vf = flag;
-    while (*vf < target) __nanosleep(64);
-    __threadfence();
-}
-
-template <int MPT>
-__global__ void __launch_bounds__(kBlock, 4) global_leaflet_pipeline_kernel(DeviceView v, PipeParams p, const float *__restrict__ planes,
-                                                                          const FrameAux *__restrict__ aux, AccumOut o) {
-    extern __shared__ int smem[];
-    __shared__ double s_red[2][kWarps];
-    __shared__ unsigned s_item;
-    __shared__ bool s_last;
-    __shared__ float s_est, s_center;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per_slot = 2 * p.n_p_items + p.n_h_items;
-    const unsigned total = (unsigned)(p.n_frames + p.lag2) * per_slot;
-    const int axis = v.leaflet_axis;
-
-    for (;;) {
-        __syncthreads();   // protects s_item and the shared accumulators of the previous item
-        if (threadIdx.x == 0) s_item = atomicAdd(p.work, 1u);
-        __syncthreads();
-        const unsigned item = s_item;
-        if (item >= total) break;
-        const int slot = item / per_slot, r = item % per_slot;
-        const int phase = r < p.n_p_items ? 0 : (r < 2 * p.n_p_items ? 1 : 2);
-        const int f = slot - (phase == 0 ? 0 : (phase == 1 ? p.lag1 : p.lag2));
-        if (f < 0 || f >= p.n_frames) continue;
-        const FrameAux &ax = aux[f];
-        const float L = ax.L[axis], half = ax.half[axis];
-
-        if (phase < 2) {
-            // ---- centre partial sums over this item's runs ----
-            const int chunk = phase == 0 ? r : r - p.n_p_items;
-            float e = 0.0f;
-            if (phase == 1) {
-                if (threadIdx.x == 0) { spin_until(p.ready0 + f, 1u); s_est = __ldcg(p.est + f); }
-                __syncthreads();
-                e = s_est;
-            }
-            const float *fr = planes + (size_t)f * v.frame_floats;
-            const float scale = __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L);
-            float a0 = 0.0f, a1 = 0.0f;
-            auto add = [&](float q) {
-                if (phase == 0) { float sn, cs; __sincosf(q * scale, &sn, &cs); a0 += cs; a1 += sn; }
-                else a0 += min_image(__fsub_rn(q, e), L, half);
-            };
-            const int sg1 = min(p.n_segs, (chunk + 1) * p.segs_per_item);
-            for (int sg = chunk * p.segs_per_item; sg < sg1; sg++) {
-                const Seg sgm = p.segs[sg];
-                const float *src = fr + sgm.off;
-                if ((((size_t)src) & 15) == 0) {
-                    const int n4 = sgm.len >> 2;
-                    for (int i = threadIdx.x; i < n4; i += kBlock) {
-                        const float4 q = __ldg(reinterpret_cast<const float4 *>(src) + i);
-                        add(q.x); add(q.y); add(q.z); add(q.w);
-                    }
-                    for (int i = (n4 << 2) + threadIdx.x; i < sgm.len; i += kBlock) add(__ldg(src + i));
-                } else {
-                    for (int i = threadIdx.x; i < sgm.len; i += kBlock) add(__ldg(src + i));
-                }
-            }
-            double x0 = a0, x1 = a1;
-            for (int ofs = 16; ofs > 0; ofs >>= 1) { x0 += __shfl_down_sync(0xffffffffu, x0, ofs); x1 += __shfl_down_sync(0xffffffffu, x1, ofs); }
-            if (lane == 0) { s_red[0][warp] = x0; s_red[1][warp] = x1; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double t0 = 0, t1 = 0;
-                for (int w = 0; w < kWarps; w++) { t0 += s_red[0][w]; t1 += s_red[1][w]; }
-                if (phase == 0) { p.partial0[((size_t)f * p.n_p_items + chunk) * 2] = t0; p.partial0[((size_t)f * p.n_p_items + chunk) * 2 + 1] = t1; }
-                else p.partial1[(size_t)f * p.n_p_items + chunk] = t0;
-                __threadfence();
-                s_last = atomicAdd(phase == 0 ? p.done0 + f : p.done1 + f, 1u) == (unsigned)p.n_p_items - 1u;
-            }
-            __syncthreads();
-            if (!s_last) continue;
-            // the last item of (frame, pass) adds the partials in index order and publishes the result
-            __threadfence();
-            double *s_part = reinterpret_cast<double *>(smem);   // [2][n_p_items] (fits: checked on the host)
-            for (int b = threadIdx.x; b < p.n_p_items; b += kBlock) {
-                if (phase == 0) {
-                    s_part[b] = __ldcg(p.partial0 + ((size_t)f * p.n_p_items + b) * 2);
-                    s_part[p.n_p_items + b] = __ldcg(p.partial0 + ((size_t)f * p.n_p_items + b) * 2 + 1);
-                } else s_part[b] = __ldcg(p.partial1 + (size_t)f * p.n_p_items + b);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double t0 = 0, t1 = 0;
-                for (int b = 0; b < p.n_p_items; b++) { t0 += s_part[b]; if (phase == 0) t1 += s_part[p.n_p_items + b]; }
-                if (phase == 0) {
-                    float th = __fadd_rn(atan2f(-(float)t1, -(float)t0), CUDART_PI_F);
-                    p.est[f] = p.n_group > 0 ? __fdiv_rn(__fmul_rn(L, th), __fmul_rn(2.0f, CUDART_PI_F)) : CUDART_NAN_F;
-                    __threadfence();
-                    atomicExch(p.ready0 + f, 1u);
-                } else {
-                    float c = __fadd_rn(e, __fdiv_rn((float)t0, (float)p.n_group));
-                    c = (L > 0.0f) ? wrap1(c, L) : c;
-                    if (c != c) raise_error(v, GORDER_ERR_INVALID_GLOBAL_CENTER, ax.frame_index);
-                    p.center[f] = c;
-                    __threadfence();
-                    atomicExch(p.ready1 + f, 1u);
-                }
-            }
-            continue;
-        }
-
-        // ---- H(f): centre, leaflets, bond engine for one chunk of molecules ----
-        if (threadIdx.x == 0) { spin_until(p.ready1 + f, 1u); s_center = __ldcg(p.center + f); }
-        const Chunk ch = v.chunks[r - 2 * p.n_p_items];
-        const TypeDesc td = v.types[ch.type];
-        const int nb = td.n_items;
-        BondItem *s_bonds = reinterpret_cast<BondItem *>(smem);
-        int *s_acc = smem + 2 * nb;            // [kWarps][nb][2]
-        int *s_cnt = s_acc + kWarps * nb * 2;  // [2]
-        for (int i = threadIdx.x; i < nb; i += kBlock) s_bonds[i] = v.bonds[td.item_off + i];
-        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        const float center = s_center;
-        const int m0 = ch.first_mol + threadIdx.x * MPT;
-        const bool active = m0 < td.mpad;
-        const int mpad = td.cstride;
-        const float *base = planes + (size_t)f * v.frame_floats + mol_offset(td, m0);
-        const Box bx = load_box(ax);
-        bool valid[MPT], up[MPT];
-        int nvalid = 0, nup = 0;
-        {
-            Vec<MPT> hz;
-            if (active) hz.load(base + td.head_off + axis * mpad);
-#pragma unroll
-            for (int j = 0; j < MPT; j++) {
-                valid[j] = active && (m0 + j < td.n_mol);
-                up[j] = false;
-                if (valid[j]) {
-                    up[j] = min_image(__fsub_rn(hz.v[j], center), L, half) >= 0.0f;   // common_identify_leaflet
-                    if (v.leaflet_flip) up[j] = !up[j];
-                    if (p.leaf_out) p.leaf_out[(size_t)(1 + f) * v.n_molpad + td.molpad0 + m0 + j] = up[j] ? GORDER_UPPER : GORDER_LOWER;
-                }
-                nvalid += valid[j]; nup += valid[j] && up[j];
-            }
-        }
-        {
-            int a = __reduce_add_sync(0xffffffffu, nvalid), b = __reduce_add_sync(0xffffffffu, nup);
-            if (lane == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], b); }
-        }
-        for (int b = 0; b < nb; b++) {
-            const BondItem bi = s_bonds[b];
-            Vec<MPT> x1, y1, z1, x2, y2, z2;
-            if (active) {
-                const int a_off = bi.a_off & ~15;
-                x1.load(base + a_off); y1.load(base + a_off + mpad); z1.load(base + a_off + 2 * mpad);
-                x2.load(base + bi.b_off); y2.load(base + bi.b_off + mpad); z2.load(base + bi.b_off + 2 * mpad);
-            }
-            int su = 0, sl = 0;
-#pragma unroll
-            for (int j = 0; j < MPT; j++) {
-                if (!valid[j]) continue;
-                const f3 d = vector_to<true>(mk3(x1.v[j], y1.v[j], z1.v[j]), mk3(x2.v[j], y2.v[j], z2.v[j]), bx);
-                const float s = calc_sch_axis_fast(d, comp(d, v.normal_axis));
-                if (s != s) {
-                    raise_error(v, GORDER_ERR_UNDEFINED_POSITION, ((long long)ch.type << 48) | ((long long)b << 32) | (unsigned)(m0 + j));
-                    continue;
-                }
-                const int q = order_value_fast(s);
-                if (up[j]) su += q; else sl += q;
-            }
-            warp_commit<true, false>(s_acc + ((size_t)warp * nb + b) * 2, lane, su, sl, 0, 0);
-        }
-        __syncthreads();
-        cta_flush<true, false>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
     }
 }
 

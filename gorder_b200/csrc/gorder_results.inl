@@ -54,6 +54,9 @@ int gorder_results_order(const GorderRaw *raw, const int32_t *slots, int32_t n_s
     if (!error) return GORDER_OK;
     const bool tw = raw->tw_sum && raw->n_frames > 0 && n_blocks > 0;
     if (!tw) { error[0] = error[1] = error[2] = nan; return GORDER_OK; }
+    // the reference refuses fewer than two blocks (timewise.rs:196-199) and divides by block_size = n_frames / n_blocks
+    // (:201-207: a block size of zero is a division by zero there)
+    if (n_blocks < 2 || (long long)n_blocks > raw->n_frames) return GORDER_ERR_INVALID_ARGUMENT;
     const long long block = raw->n_frames / n_blocks;
     const size_t row = 3 * (size_t)raw->n_slots;
     std::vector<float> means(3 * (size_t)n_blocks);

@@ -1,7 +1,5 @@
 // Spherical-clustering leaflets on the device (spherical_clustering.rs:36-275).
-//
-// EXPERIMENTAL: written after the last GPU session of round 1 and not yet run on a device.  gorder_gpu_create refuses
-// GORDER_LEAFLET_SPHERICAL unless GORDER_EXPERIMENTAL_SPHERICAL is set; tests/test_gpu_spherical.py is skipped without it.
+// Parity: tests/test_gpu_spherical.py (device vs the oracle, which is pinned by spherical_clustering.rs:299-361).
 //
 // Per assignment frame, one CTA:
 //   distances of the ClusterHeads group (GorderSetup.membrane) from its PBC-aware centre (run_group_center, 3 axes),

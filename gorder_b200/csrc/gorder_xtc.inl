@@ -383,9 +383,11 @@ int gorder_xtc_open(const char *path, GorderXtc **out) {
             if (magic == 2023) { f.nbytes = ((size_t)gxtc::be32(x->data + q) << 32) | gxtc::be32(x->data + q + 4); q += 8; }
             else { f.nbytes = gxtc::be32(x->data + q); q += 4; }
             f.payload = q;
-            q += (f.nbytes + 3) & ~(size_t)3;
+            // a forged / corrupt length (the 64-bit field of magic 2023 can hold anything) must not wrap the cursor
+            if (f.nbytes > x->size - q) break;   // truncated (or hostile) frame: indexing stops here
+            q += std::min((f.nbytes + 3) & ~(size_t)3, x->size - q);   // the padding of the last frame may be missing
         }
-        if (q > x->size) break;   // truncated last frame: ignored, as trajectory readers do
+        if (q > x->size || q <= p) break;   // truncated last frame: ignored, as trajectory readers do
         if (x->frames.empty()) x->natoms = f.natoms;
         else if (f.natoms != x->natoms) { gorder_xtc_close(x); return GORDER_ERR_INVALID_ARGUMENT; }
         x->frames.push_back(f);
@@ -465,6 +467,7 @@ int gorder_xtc_write(const char *path, const float *xyz, const float *box3, int3
 int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride, int64_t frame_index0,
                        int32_t n_threads, int32_t batch_frames, double *decode_seconds) {
     if (!h || !x || first < 0 || stride < 1) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (h->err_code) return h->err_code;
     last = std::min<int64_t>(last, (int64_t)x->frames.size());
     const int64_t total = last > first ? (last - first + stride - 1) / stride : 0;
@@ -825,6 +828,7 @@ int gorder_xtc_scan(GorderXtc *x, int64_t first, int64_t count, int32_t *n_group
 int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride,
                               int64_t frame_index0, int32_t n_threads, int32_t batch_frames, int64_t *bytes_h2d) {
     if (!h || !x || first < 0 || stride < 1) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     if (h->err_code) return h->err_code;
     last = std::min<int64_t>(last, (int64_t)x->frames.size());
     const int64_t total = last > first ? (last - first + stride - 1) / stride : 0;

@@ -36,6 +36,8 @@ def estimate_error(tw_sum: np.ndarray, tw_count: np.ndarray, n_blocks: int) -> O
     n_frames = len(tw_sum)
     if n_frames == 0:
         return None
+    if n_blocks < 2 or n_blocks > n_frames:   # timewise.rs:196-199 panics below two blocks; block_size 0 divides by zero
+        raise abi.GorderError(abi.ERR_INVALID_ARGUMENT, f"cannot estimate the error from {n_blocks} blocks of {n_frames} frames")
     block = n_frames // n_blocks
     vals = []
     for b in range(n_blocks):

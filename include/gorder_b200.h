@@ -54,17 +54,16 @@ enum { GORDER_AXIS_X = 0, GORDER_AXIS_Y = 1, GORDER_AXIS_Z = 2 };
 enum { GORDER_NORMAL_STATIC = 0, GORDER_NORMAL_DYNAMIC = 1, GORDER_NORMAL_MANUAL = 2 };
 
 /* LeafletClassification, reference: src/analysis/leaflets.rs:208-217. MANUAL covers FromFile /
- * FromMap / FromNdx / Clustering / SphericalClustering: the host computes the table. */
+ * FromMap / FromNdx / Clustering: the host computes the table. */
 enum {
     GORDER_LEAFLET_NONE = 0,
     GORDER_LEAFLET_GLOBAL = 1,
     GORDER_LEAFLET_LOCAL = 2,
     GORDER_LEAFLET_INDIVIDUAL = 3,
     GORDER_LEAFLET_MANUAL = 4,
-    /* spherical clustering (spherical_clustering.rs:36-275; `membrane` holds the ClusterHeads group, every analysed
-     * molecule's head must be in it).  Restated in the oracle; the device kernels (csrc/gorder_spherical.cuh, SURVEY.md §8f
-     * rank 2) have not run on a GPU yet: gorder_gpu_create refuses the mode unless GORDER_EXPERIMENTAL_SPHERICAL is set in
-     * the environment; until they are verified the host passes the table with GORDER_LEAFLET_MANUAL. */
+    /* spherical clustering (spherical_clustering.rs:36-275): 1-D two-component Gaussian mixture over the heads' distances
+     * from the vesicle centre, outer cluster = upper.  `membrane` holds the ClusterHeads group; every analysed molecule's
+     * head must be in it. */
     GORDER_LEAFLET_SPHERICAL = 5
 };
 

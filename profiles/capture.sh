@@ -2,7 +2,7 @@
 # Re-captures the evidence under profiles/ on a B200 box.  Run from the repo root THROUGH gpurun, e.g.
 #   gpurun --timeout 900 -- 'bash profiles/capture.sh r02 all'
 # Writes into gpurun_out/ (scratch); copy what should be judged into profiles/<tag>_*.
-# Parts: tests | newcases | bench | workloads | launches | ncu | xtc | spherical | all
+# Parts: tests | bench | workloads | launches | ncu | xtc | all
 set -u
 TAG=${1:-rXX}; PART=${2:-all}; OUT=gpurun_out; mkdir -p $OUT
 want() { [ "$PART" = all ] || [ "$PART" = "$1" ]; }
@@ -10,12 +10,6 @@ want() { [ "$PART" = all ] || [ "$PART" = "$1" ]; }
 if want tests; then
   python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $OUT/${TAG}_pytest_gpu.txt
   python __graft_entry__.py --smoke 2>&1 | tail -2
-fi
-if want newcases; then    # fixtures pinned on the CPU after the last GPU session (tests/test_gpu_golden_new.py)
-  GORDER_NEW_GPU_CASES=1 timeout 600 python -m pytest tests/test_gpu_golden_new.py -m gpu -q 2>&1 | tail -15 | tee $OUT/${TAG}_pytest_newcases.txt
-fi
-if want spherical; then   # experimental kernels (csrc/gorder_spherical.cuh): first run on a device
-  GORDER_EXPERIMENTAL_SPHERICAL=1 timeout 300 python -m pytest tests/test_gpu_spherical.py -m gpu -x -q 2>&1 | tail -15 | tee $OUT/${TAG}_pytest_spherical.txt
 fi
 if want bench; then       # the headline line (S-CG), then the CPU arm
   python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench_1gpu.json 2> $OUT/${TAG}_bench_1gpu.err; tail -c 600 $OUT/${TAG}_bench_1gpu.json

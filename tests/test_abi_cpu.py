@@ -111,3 +111,24 @@ def test_create_rejects_values_outside_their_range():
         with pytest.raises(abi.GorderError) as e:
             SystemTopology(setup)
         assert e.value.code == abi.ERR_INVALID_ARGUMENT, kw
+
+
+def test_create_rejects_classifiers_without_heads_or_methyls():
+    """A molecule type without a head (or, for the individual method, without methyls) would make the classifiers read one
+    float before the type's planes; the reference cannot reach that state (its classification guarantees a head), the C ABI
+    can.  Checked before any device is touched."""
+    import numpy as np
+    import pytest
+    from gorder_b200 import SystemTopology, abi
+    base = dict(kind=abi.KIND_CG, n_atoms=4, membrane=np.array([0, 2]))
+    no_head = abi.MolType(name="LIP", mol_base=np.array([0, 2]), bond_rel=[(0, 1)], head_rel=-1)
+    head = abi.MolType(name="LIP", mol_base=np.array([0, 2]), bond_rel=[(0, 1)], head_rel=0)
+    neg_methyl = abi.MolType(name="LIP", mol_base=np.array([0, 2]), bond_rel=[(0, 1)], head_rel=0, methyl_rel=[-1])
+    cases = [(no_head, dict(leaflet_mode=abi.LEAFLET_GLOBAL)), (no_head, dict(leaflet_mode=abi.LEAFLET_LOCAL, leaflet_radius=1.0)),
+             (no_head, dict(leaflet_mode=abi.LEAFLET_INDIVIDUAL)), (no_head, dict(leaflet_mode=abi.LEAFLET_SPHERICAL)),
+             (head, dict(leaflet_mode=abi.LEAFLET_INDIVIDUAL)), (neg_methyl, dict(leaflet_mode=abi.LEAFLET_INDIVIDUAL)),
+             (head, dict(leaflet_mode=abi.LEAFLET_MANUAL))]
+    for mt, kw in cases:
+        with pytest.raises(abi.GorderError) as e:
+            SystemTopology(abi.EngineSetup(moltypes=[mt], **base, **kw))
+        assert e.value.code == abi.ERR_INVALID_ARGUMENT, kw

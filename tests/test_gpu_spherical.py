@@ -1,11 +1,5 @@
-"""Spherical-clustering leaflets on the device (gorder_spherical.cuh) against the oracle's restatement.
-
-EXPERIMENTAL: the kernels were written after the last GPU session of round 1 and have not run on a device yet; the engine
-only accepts GORDER_LEAFLET_SPHERICAL with GORDER_EXPERIMENTAL_SPHERICAL=1, and so do these tests:
-    GORDER_EXPERIMENTAL_SPHERICAL=1 python -m pytest tests/test_gpu_spherical.py -m gpu
-"""
-import os
-
+"""Spherical-clustering leaflets on the device (gorder_spherical.cuh; reference spherical_clustering.rs:36-275) against the
+oracle's restatement, which is pinned by the reference's unit tests (spherical_clustering.rs:299-361, tests/test_oracle_pins.py)."""
 import numpy as np
 import pytest
 
@@ -13,8 +7,7 @@ from gorder_b200 import abi
 
 from parity import assert_raw_parity, run_both
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("GORDER_EXPERIMENTAL_SPHERICAL"), reason="experimental kernel: set GORDER_EXPERIMENTAL_SPHERICAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 def vesicle(n_out, n_in, n_frames, seed=5, box=30.0, pbc=True):

@@ -147,19 +147,11 @@ def test_cuboid_inside_random():
 
 
 UA_YAML_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "error", "error_leaflets", "begin_end_step",
-                 "cylinder_center", "cuboid_point", "dynamic_normals"]
+                 "cylinder_center", "cuboid_point", "dynamic_normals", "basic_saturated", "basic_unsaturated", "leaflets_flipped",
+                 "manual_normals"]
 
 
-# cases added after the last GPU session of round 1: pinned with the oracle here, to be added to the GPU lists
-# (tests/test_gpu_golden.py) once they have run on the device: tests/test_gpu_golden_new.py (opt-in) does that
-UA_YAML_CASES_NEW = ["basic_saturated", "basic_unsaturated", "leaflets_flipped", "manual_normals"]
-AA_FULL_CASES_NEW = ["error_limit", "error_leaflets_limit", "sphere_static", "manual_once", "manual_every10", "manual_every",
-                     "manual_every10_stepping", "manual_begin_end_step"]
-CG_FULL_CASES_NEW = ["error_limit", "error_leaflets_limit", "begin_end", "leaflets_only_upper", "leaflets_only_upper_individual",
-                     "leaflets_only_upper_local", "redefined_bonds", "manual_once", "manual_every20", "manual_every", "manual_not_enough_frames"]
-
-
-@pytest.mark.parametrize("name", UA_YAML_CASES + UA_YAML_CASES_NEW)
+@pytest.mark.parametrize("name", UA_YAML_CASES)
 def test_ua_trajectory_fixtures(name):
     """51-frame Berger POPC/POPS trajectory: the oracle reproduces the reference's YAML outputs."""
     setup, xyz, box, fi, case = gc.ua_case(name)
@@ -250,10 +242,13 @@ AA_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_lo
                  "maps_cuboid_square", "maps_cylinder", "cuboid_dynamic", "cylinder_dynamic", "sphere_dynamic", "sphere_dynamic_inverted", "cuboid_patch",
                  "cylinder_x", "cylinder_z_inverted", "cuboid_square_inverted", "leaflets_dynamic", "export_once_global", "export_every5_local",
                  "export_every1_individual", "export_every1_global", "error_blocks10", "step5_leaflets", "convergence", "convergence_leaflets",
-                 "maps_leaflets"]
+                 "maps_leaflets", "error_limit", "error_leaflets_limit", "sphere_static", "manual_once", "manual_every10", "manual_every",
+                 "manual_every10_stepping", "manual_begin_end_step"]
 CG_FULL_CASES = ["basic", "leaflets_global", "leaflets_individual", "leaflets_local", "leaflets_every5", "leaflets_once", "error",
                  "error_leaflets", "begin_end_step", "leaflets_dynamic", "cuboid_square", "cylinder", "sphere_dynamic", "cylinder_z_inverted", "limit",
-                 "leaflets_limit", "maps_basic", "maps_leaflets"]
+                 "leaflets_limit", "maps_basic", "maps_leaflets", "error_limit", "error_leaflets_limit", "begin_end", "leaflets_only_upper",
+                 "leaflets_only_upper_individual", "leaflets_only_upper_local", "redefined_bonds", "manual_once", "manual_every20",
+                 "manual_every", "manual_not_enough_frames"]
 
 
 def check_maps_aa(raw, setup, case):
@@ -358,18 +353,18 @@ def _oracle_full(which, name):
         check_convergence(raw, setup, case)
 
 
-@pytest.mark.parametrize("name", AA_FULL_CASES + AA_FULL_CASES_NEW)
+@pytest.mark.parametrize("name", AA_FULL_CASES)
 def test_aa_full_trajectory_fixtures(name):
     """pcpepg.xtc (51 frames, 35 432 lipid atoms, 229 C-H bond types): tests_aa.rs:25-45, 289-316, 548-582, 1099-1149,
     1202-1232, 1398-1423, 2170-2247, 3239-3260 -> tests/files/aa_order_*.yaml."""
-    assert set(AA_FULL_CASES + AA_FULL_CASES_NEW) == set(gc.full_case_names("aa"))
+    assert set(AA_FULL_CASES) == set(gc.full_case_names("aa"))
     _oracle_full("aa", name)
 
 
-@pytest.mark.parametrize("name", CG_FULL_CASES + CG_FULL_CASES_NEW)
+@pytest.mark.parametrize("name", CG_FULL_CASES)
 def test_cg_full_trajectory_fixtures(name):
     """cg.xtc (101 frames, 6 096 beads): tests_cg.rs:26-43, 180-213, 746-772, 1367-1435, 3356-3388 -> tests/files/cg_order_*.yaml."""
-    assert set(CG_FULL_CASES + CG_FULL_CASES_NEW) == set(gc.full_case_names("cg"))
+    assert set(CG_FULL_CASES) == set(gc.full_case_names("cg"))
     _oracle_full("cg", name)
 
 
@@ -471,17 +466,6 @@ def test_spherical_leaflets_on_a_vesicle():
         o.close()
         np.testing.assert_array_equal(raw.leaflets[0].astype(bool), is_outer ^ flip)
         assert raw.count[0].tolist() == [len(heads), int((is_outer ^ flip).sum()), int((~(is_outer ^ flip)).sum())]
-
-
-def test_engine_refuses_spherical_clustering_for_now(monkeypatch):
-    """No silent fallback: the device kernel (gorder_spherical.cuh) is experimental and opt-in (include/gorder_b200.h)."""
-    from gorder_b200 import SystemTopology
-    monkeypatch.delenv("GORDER_EXPERIMENTAL_SPHERICAL", raising=False)
-    mt = abi.MolType(name="LIP", mol_base=np.array([0, 2]), bond_rel=[(0, 1)], head_rel=0)
-    setup = abi.EngineSetup(kind=abi.KIND_CG, n_atoms=4, moltypes=[mt], leaflet_mode=abi.LEAFLET_SPHERICAL, membrane=np.array([0, 2]))
-    with pytest.raises(abi.GorderError) as e:
-        SystemTopology(setup)
-    assert e.value.code == abi.ERR_INVALID_ARGUMENT
 
 
 def test_spherical_gmm_parallel_model_with_sequential_folds():

@@ -95,8 +95,12 @@ def test_empty_blocks_few_frames_and_min_samples():
     assert not np.any(np.isnan(err))
     rc, val, err = _order(raw, [1], n_blocks=2, min_samples=10**9)
     assert np.all(np.isnan(val)) and np.all(np.isnan(err))
-    rc, val, err = _order(_raw(2, 3, seed=5), [0], n_blocks=5)   # fewer frames than blocks: every block is empty
-    assert rc == abi.OK and np.all(np.isnan(err))
+    # fewer frames than blocks (block size 0 divides by zero in the reference, timewise.rs:201-207) and fewer than two
+    # blocks (timewise.rs:196-199 panics) are refused, by the C converter and by the numpy one
+    for nb in (5, 1):
+        assert _order(_raw(2, 3, seed=5), [0], n_blocks=nb)[0] == abi.ERR_INVALID_ARGUMENT
+        with pytest.raises(abi.GorderError):
+            results.estimate_error(np.ones(3, np.int64), np.ones(3, np.uint64), nb)
     no_tw = abi.RawResults(2, 0, raw.sum[:2], raw.count[:2])
     rc, val, err = _order(no_tw, [0, 1], n_blocks=5)
     assert rc == abi.OK and np.all(np.isnan(err)) and not np.any(np.isnan(val))

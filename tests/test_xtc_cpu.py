@@ -81,6 +81,20 @@ def test_truncated_and_bad_files(tmp_path):
     open(cut, "wb").write(raw[: len(raw) - 100])           # last frame incomplete: ignored
     with XtcFile(cut) as x:
         assert x.n_frames == 2
+    # a forged 64-bit length in a magic-2023 header: 0xFFFFFFFFFFFFFFF0 wraps the cursor, 2^40 points far
+    # outside the mapping; both must stop the index at the frames before, not crash or loop
+    import struct
+    s9 = synthetic.s_cg(100)
+    for forged in (0xFFFFFFFFFFFFFFF0, 1 << 40, len(raw)):
+        n_first = raw.index(struct.pack(">i", 1995), 4)          # start of the second frame
+        head = bytearray(raw[n_first:n_first + 56 + 32])
+        head[0:4] = struct.pack(">i", 2023)
+        evil = str(tmp_path / "evil.xtc")
+        open(evil, "wb").write(raw[:n_first] + bytes(head) + struct.pack(">Q", forged) + raw[n_first + 92:])
+        with XtcFile(evil) as x:
+            assert x.n_frames == 1
+            got, _, _, _ = x.read()
+            assert got.shape[0] == 1
     bad = str(tmp_path / "bad.xtc")
     open(bad, "wb").write(b"\x00" * 200)
     with pytest.raises(OSError):
