@@ -160,10 +160,10 @@ struct GorderHandle {
     // centres
     // per staging slot, so that the centre passes of batch k+1 (pre stream) overlap the bond kernel of batch k
     float *d_est2[2] = {nullptr, nullptr}, *d_center2[2] = {nullptr, nullptr};   // [max_batch*3]
-    double *d_partial2[2] = {nullptr, nullptr};    // [max_batch][kCenterBlocks][2]
+    long long *d_partial2[2] = {nullptr, nullptr};    // [max_batch][kCenterBlocks][2] fixed-point partial sums
     unsigned *d_ticket2[2] = {nullptr, nullptr};   // [max_batch]
     float *d_est = nullptr, *d_center = nullptr;   // current slot's buffers
-    double *d_partial = nullptr;
+    long long *d_partial = nullptr;
     unsigned *d_ticket = nullptr;
     cudaStream_t stream_pre = nullptr;             // frame setup + centre reduction of the next batch
     cudaEvent_t ev_pre[2] = {nullptr, nullptr};

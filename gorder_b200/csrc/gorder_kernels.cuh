@@ -200,13 +200,14 @@ __global__ void frame_setup_kernel(DeviceView v, FrameAux *aux, const float *__r
 }
 
 // ---------------------------------------------------------------------------------------------
-// group centre along one axis (groan group_get_center: refined Bai-Breen; _naive: mean).
-//   pass 0: sum cos(theta), sin(theta), theta = 2 pi x / L          -> estimate
-//   pass 1: sum min_image(x - estimate)                              -> centre = wrap(estimate + mean)
+// group centre along one axis (groan group_get_center: refined Bai-Breen; _naive: mean), in the order-free
+// fixed-point arithmetic of gorder_math.cuh (bit-identical to oracle/gorder_oracle.c group_center):
+//   pass 0: sum q(cos 2 pi x / L), q(sin 2 pi x / L)                 -> estimate
+//   pass 1: sum q(min_image(x - estimate))                           -> centre = wrap(estimate + mean)
 // The group is given as runs of contiguous floats of the native frame (the axis component of its
 // atoms: whole planes for typical selections), so the reads are coalesced and carry no index
-// traffic.  Deterministic: every CTA writes its partial sums, the last CTA of a frame (ticket) adds
-// them in a fixed order and finishes the pass -- no separate launch, no floating-point atomics.
+// traffic.  The sums are integers: every CTA writes its partials, the last CTA of a frame (ticket) adds
+// them and finishes the pass -- no separate launch; the result does not depend on the partition.
 // frame_list[i]: index in the batch of the i-th frame that needs the centre.
 // out: est[3 * i + axis] (pass 0) / center[3 * i + axis] (pass 1; pass 0 when !pbc).
 // ---------------------------------------------------------------------------------------------
@@ -214,18 +215,19 @@ constexpr int kCenterBlocks = 64;
 
 // sums of one virtual block `vb` of center_axis_kernel (256 threads), result in thread 0 after the reduction
 __device__ __forceinline__ void center_block_sums(const Seg *__restrict__ segs, int n_segs, int vb, int n_blocks, const float *__restrict__ fr,
-                                                  bool pbc, int pass, float scale, float e, float L, float half, double (&s_red)[2][8],
-                                                  double &t0, double &t1) {
-    float a0 = 0.0f, a1 = 0.0f;
+                                                  bool pbc, int pass, float inv_l, float e, float L, float half, long long (&s_red)[3][8],
+                                                  long long &t0, long long &t1, bool &tbad) {
+    long long a0 = 0, a1 = 0;
+    bool bad = false;
     const unsigned long long pol = l2_policy_evict_last();
     const float guard = 0.99f * half;
     auto add = [&](float p) {
-        if (!pbc) a0 += p;
+        if (!pbc) a0 += center_q(p, bad);
         else if (pass == 0) {
             float sn, cs;
-            __sincosf(p * scale, &sn, &cs);
-            a0 += cs; a1 += sn;
-        } else a0 += min_image_g(__fsub_rn(p, e), L, half, guard);
+            sincos_turns(__fmul_rn(p, inv_l), sn, cs);
+            a0 += center_q(cs, bad); a1 += center_q(sn, bad);
+        } else a0 += center_q(min_image_g(__fsub_rn(p, e), L, half, guard), bad);
     };
     for (int sg = vb; sg < n_segs; sg += n_blocks) {
         const Seg sgm = segs[sg];
@@ -247,54 +249,55 @@ __device__ __forceinline__ void center_block_sums(const Seg *__restrict__ segs, 
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double x0 = a0, x1 = a1;
+    long long x0 = a0, x1 = a1;
     for (int o = 16; o > 0; o >>= 1) { x0 += __shfl_down_sync(0xffffffffu, x0, o); x1 += __shfl_down_sync(0xffffffffu, x1, o); }
+    const bool wbad = __any_sync(0xffffffffu, bad);
     __syncthreads();   // s_red may still be read from the previous call
-    if (lane == 0) { s_red[0][warp] = x0; s_red[1][warp] = x1; }
+    if (lane == 0) { s_red[0][warp] = x0; s_red[1][warp] = x1; s_red[2][warp] = wbad ? 1 : 0; }
     __syncthreads();
-    t0 = 0; t1 = 0;
+    t0 = 0; t1 = 0; tbad = false;
     if (threadIdx.x == 0)
-        for (int w = 0; w < 8; w++) { t0 += s_red[0][w]; t1 += s_red[1][w]; }
+        for (int w = 0; w < 8; w++) { t0 += s_red[0][w]; t1 += s_red[1][w]; tbad = tbad || s_red[2][w] != 0; }
 }
 
+// ticket word of a (frame, pass): low half = CTAs that have published, high half = CTAs that saw a NaN / Inf term
 __global__ void __launch_bounds__(256) center_axis_kernel(DeviceView v, const Seg *__restrict__ segs, int n_segs, int n_group, int axis,
                                                           const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                           const int *__restrict__ frame_list, float *__restrict__ est,
-                                                          float *__restrict__ center, double *__restrict__ partial,
+                                                          float *__restrict__ center, long long *__restrict__ partial,
                                                           unsigned *__restrict__ ticket, int pass) {
     const int fi = blockIdx.y, f = frame_list[fi];
     const float *fr = planes + (size_t)f * v.frame_floats;
     const float L = aux[f].L[axis], half = aux[f].half[axis];
     const bool pbc = v.handle_pbc != 0;
-    const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
+    const float inv_l = pbc ? __fdiv_rn(1.0f, L) : 0.0f;
     const float e = (pbc && pass == 1) ? est[3 * fi + axis] : 0.0f;
-    __shared__ double s_red[2][8];
-    __shared__ bool s_last;
-    double b0, b1;
-    center_block_sums(segs, n_segs, blockIdx.x, gridDim.x, fr, pbc, pass, scale, e, L, half, s_red, b0, b1);
+    __shared__ long long s_red[3][8];
+    __shared__ unsigned s_ticket;
+    long long b0, b1;
+    bool bbad;
+    center_block_sums(segs, n_segs, blockIdx.x, gridDim.x, fr, pbc, pass, inv_l, e, L, half, s_red, b0, b1, bbad);
     if (threadIdx.x == 0) {
-        double *pp = partial + ((size_t)fi * gridDim.x + blockIdx.x) * 2;
+        long long *pp = partial + ((size_t)fi * gridDim.x + blockIdx.x) * 2;
         pp[0] = b0; pp[1] = b1;
         __threadfence();
-        s_last = atomicAdd(&ticket[fi], 1u) == gridDim.x - 1;
+        s_ticket = atomicAdd(&ticket[fi], 1u | (bbad ? 0x10000u : 0u)) + (bbad ? 0x10000u : 0u);
     }
     __syncthreads();
-    if (!s_last || threadIdx.x != 0) return;
+    if ((s_ticket & 0xffffu) != gridDim.x - 1 || threadIdx.x != 0) return;
     __threadfence();
-    double t0 = 0, t1 = 0;
-    for (unsigned b = 0; b < gridDim.x; b++) {   // fixed order
-        const volatile double *pp = partial + ((size_t)fi * gridDim.x + b) * 2;
+    const bool bad = (s_ticket >> 16) != 0;
+    long long t0 = 0, t1 = 0;
+    for (unsigned b = 0; b < gridDim.x; b++) {
+        const volatile long long *pp = partial + ((size_t)fi * gridDim.x + b) * 2;
         t0 += pp[0]; t1 += pp[1];
     }
     ticket[fi] = 0;
-    const float n = (float)n_group;
-    if (!pbc) center[3 * fi + axis] = n_group > 0 ? __fdiv_rn((float)t0, n) : CUDART_NAN_F;
-    else if (pass == 0) {
-        float th = __fadd_rn(atan2f(-(float)t1, -(float)t0), CUDART_PI_F);
-        est[3 * fi + axis] = n_group > 0 ? __fdiv_rn(__fmul_rn(L, th), __fmul_rn(2.0f, CUDART_PI_F)) : CUDART_NAN_F;
-    } else {
-        float c = __fadd_rn(e, __fdiv_rn((float)t0, n));
-        center[3 * fi + axis] = (L > 0.0f) ? wrap1(c, L) : c;
+    if (!pbc) center[3 * fi + axis] = (n_group > 0 && !bad) ? center_mean(t0, n_group) : CUDART_NAN_F;
+    else if (pass == 0) est[3 * fi + axis] = (n_group > 0 && !bad) ? center_estimate(t0, t1, L) : CUDART_NAN_F;
+    else {
+        const float c = __fadd_rn(e, center_mean(t0, n_group));
+        center[3 * fi + axis] = (n_group > 0 && !bad && e == e) ? ((L > 0.0f) ? wrap1(c, L) : c) : CUDART_NAN_F;
     }
 }
 
@@ -376,15 +379,16 @@ __global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const
             const int *st = lcell_start + (size_t)ai * (lcells_cap + 1);
             const float4 *srt = lcell_sorted + (size_t)ai * v.membrane.n;
             const int lo0 = n[0] >= 3 ? -1 : 0, hi0 = n[0] >= 3 ? 1 : n[0] - 1, lo1 = n[1] >= 3 ? -1 : 0, hi1 = n[1] >= 3 ? 1 : n[1] - 1;
-            const float scale = __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L);
-            double sc = 0, ss = 0, sn = 0;
+            // centre of the atoms inside the cylinder: the order-free sums of center_axis_kernel (gorder_math.cuh)
+            const float inv_l = __fdiv_rn(1.0f, L);
+            long long sc = 0, ss = 0, sn = 0;
+            bool bad = false;
             int cnt = 0;
             float est = 0.0f;
             for (int pass = 0; pass < 2; pass++) {
                 if (pass == 1) {
                     if (cnt == 0) break;
-                    const float th = __fadd_rn(atan2f(-(float)ss, -(float)sc), CUDART_PI_F);
-                    est = __fdiv_rn(__fmul_rn(L, th), __fmul_rn(2.0f, CUDART_PI_F));
+                    est = center_estimate(sc, ss, L);
                 }
                 for (int d0 = lo0; d0 <= hi0; d0++) {
                     const int x0 = n[0] >= 3 ? (c0 + d0 + n[0]) % n[0] : d0;
@@ -397,30 +401,29 @@ __global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const
                             // r2 in the oracle's component order (ascending axis index)
                             const float r2 = a0 < a1 ? __fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1)) : __fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e0, e0));
                             if (!(__fsqrt_rn(r2) < v.leaflet_radius)) continue;
-                            if (pass == 0) { cnt++; float sv, cv; sincosf(__fmul_rn(q.z, scale), &sv, &cv); sc += cv; ss += sv; }
-                            else sn += min_image(__fsub_rn(q.z, est), L, half);
+                            if (pass == 0) { cnt++; float sv, cv; sincos_turns(__fmul_rn(q.z, inv_l), sv, cv); sc += center_q(cv, bad); ss += center_q(sv, bad); }
+                            else sn += center_q(min_image(__fsub_rn(q.z, est), L, half), bad);
                         }
                     }
                 }
             }
             float c = CUDART_NAN_F;
-            if (cnt > 0) { c = __fadd_rn(est, __fdiv_rn((float)sn, (float)cnt)); c = wrap1(c, L); }
+            if (cnt > 0 && !bad && est == est) c = wrap1(__fadd_rn(est, center_mean(sn, cnt)), L);
             if (c != c) raise_error(v, GORDER_ERR_INVALID_LOCAL_CENTER, ((long long)t << 32) | (unsigned)m);
             upper = distance_1d(hax, c, L, half, true) >= 0.0f;
         } else if (v.leaflet_mode == GORDER_LEAFLET_LOCAL) {   // leaflets.rs:630-707, pbc.rs:273-318
             // centre of the membrane atoms inside an infinite cylinder around the head (brute force)
             f3 head = mk3(fr[td.head_off], fr[td.head_off + cst], fr[td.head_off + 2 * cst]);
             const float *frame0 = planes + (size_t)f * v.frame_floats;
-            const float scale = pbc ? __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L) : 0.0f;
-            double sc = 0, ss = 0, sn = 0;
+            const float inv_l = pbc ? __fdiv_rn(1.0f, L) : 0.0f;
+            long long sc = 0, ss = 0, sn = 0;
+            bool bad = false;
             int cnt = 0;
+            float est = 0.0f;
             for (int pass = 0; pass < 2; pass++) {
-                float est = 0.0f;
                 if (pass == 1) {
                     if (!pbc || cnt == 0) break;
-                    float th = __fadd_rn(atan2f(-(float)ss, -(float)sc), CUDART_PI_F);
-                    est = __fdiv_rn(__fmul_rn(L, th), __fmul_rn(2.0f, CUDART_PI_F));
-                    sn = 0;
+                    est = center_estimate(sc, ss, L);
                 }
                 for (int i = 0; i < v.membrane.n; i++) {
                     const int off = v.membrane.off[i], cs = v.membrane.cs[i];
@@ -435,13 +438,13 @@ __global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const
                     if (!(__fsqrt_rn(r2) < v.leaflet_radius)) continue;
                     if (pass == 0) {
                         cnt++;
-                        if (pbc) { float s, c; sincosf(__fmul_rn(p[ax], scale), &s, &c); sc += c; ss += s; }
-                        else sn += p[ax];
-                    } else sn += (L > 0.0f) ? min_image(__fsub_rn(p[ax], est), L, half) : __fsub_rn(p[ax], est);
+                        if (pbc) { float sv, cv; sincos_turns(__fmul_rn(p[ax], inv_l), sv, cv); sc += center_q(cv, bad); ss += center_q(sv, bad); }
+                        else sn += center_q(p[ax], bad);
+                    } else sn += center_q((L > 0.0f) ? min_image(__fsub_rn(p[ax], est), L, half) : __fsub_rn(p[ax], est), bad);
                 }
-                if (pass == 1) { float c = __fadd_rn(est, __fdiv_rn((float)sn, (float)cnt)); sn = (L > 0.0f) ? wrap1(c, L) : c; }
             }
-            float c = (cnt == 0) ? CUDART_NAN_F : (pbc ? (float)sn : __fdiv_rn((float)sn, (float)cnt));
+            float c = CUDART_NAN_F;
+            if (cnt > 0 && !bad && est == est) c = pbc ? ((L > 0.0f) ? wrap1(__fadd_rn(est, center_mean(sn, cnt)), L) : __fadd_rn(est, center_mean(sn, cnt))) : center_mean(sn, cnt);
             if (c != c) raise_error(v, GORDER_ERR_INVALID_LOCAL_CENTER, ((long long)t << 32) | (unsigned)m);
             upper = distance_1d(comp(head, ax), c, L, half, pbc) >= 0.0f;
         }
@@ -1286,7 +1289,7 @@ __global__ void __launch_bounds__(kBlock) spec_repair_kernel(DeviceView v, Repai
         __threadfence_system();
     }
     if (nflag == 0) return;
-    __shared__ double s_red[2][8];
+    __shared__ long long s_red[3][8];
     __shared__ float s_c;
     const Chunk ch = v.chunks[blockIdx.x];
     const TypeDesc td = v.types[ch.type];
@@ -1297,22 +1300,20 @@ __global__ void __launch_bounds__(kBlock) spec_repair_kernel(DeviceView v, Repai
         const FrameAux &ax = aux[f];
         const float L = ax.L[axis], half = ax.half[axis];
         const float *fr = planes + (size_t)f * v.frame_floats;
-        // ---- exact centre (center_axis_kernel, both passes, blocks in index order) ----
-        const float scale = __fdiv_rn(__fmul_rn(2.0f, CUDART_PI_F), L);
-        double T0 = 0, T1 = 0, t0, t1;
-        for (int vb = 0; vb < rp.n_blocks; vb++) { center_block_sums(rp.segs, rp.n_segs, vb, rp.n_blocks, fr, true, 0, scale, 0.0f, L, half, s_red, t0, t1); T0 += t0; T1 += t1; }
-        if (threadIdx.x == 0) {
-            const float th = __fadd_rn(atan2f(-(float)T1, -(float)T0), CUDART_PI_F);
-            s_c = rp.n_group > 0 ? __fdiv_rn(__fmul_rn(L, th), __fmul_rn(2.0f, CUDART_PI_F)) : CUDART_NAN_F;
-        }
+        // ---- exact centre (the sums of center_axis_kernel: integers, any partition gives the same bits) ----
+        const float inv_l = __fdiv_rn(1.0f, L);
+        long long T0 = 0, T1 = 0, t0, t1;
+        bool bad = false, tb;
+        for (int vb = 0; vb < rp.n_blocks; vb++) { center_block_sums(rp.segs, rp.n_segs, vb, rp.n_blocks, fr, true, 0, inv_l, 0.0f, L, half, s_red, t0, t1, tb); T0 += t0; T1 += t1; bad = bad || tb; }
+        if (threadIdx.x == 0) s_c = (rp.n_group > 0 && !bad) ? center_estimate(T0, T1, L) : CUDART_NAN_F;
         __syncthreads();
         const float e = s_c;
         T0 = 0;
-        for (int vb = 0; vb < rp.n_blocks; vb++) { center_block_sums(rp.segs, rp.n_segs, vb, rp.n_blocks, fr, true, 1, scale, e, L, half, s_red, t0, t1); T0 += t0; }
+        for (int vb = 0; vb < rp.n_blocks; vb++) { center_block_sums(rp.segs, rp.n_segs, vb, rp.n_blocks, fr, true, 1, inv_l, e, L, half, s_red, t0, t1, tb); T0 += t0; bad = bad || tb; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const float c = __fadd_rn(e, __fdiv_rn((float)T0, (float)rp.n_group));
-            s_c = (L > 0.0f) ? wrap1(c, L) : c;
+            const float c = __fadd_rn(e, center_mean(T0, rp.n_group));
+            s_c = (rp.n_group > 0 && !bad && e == e) ? ((L > 0.0f) ? wrap1(c, L) : c) : CUDART_NAN_F;
         }
         __syncthreads();
         const float center = s_c;

@@ -87,6 +87,57 @@ __device__ __forceinline__ f3 wrap_point(const f3 &p, const Box &b) {
                b.L[2] > 0.0f ? wrap1(p.z, b.L[2]) : p.z);
 }
 
+// ---- order-free group centre (oracle/gorder_oracle.c group_center) ------------------------------
+// groan's group_get_center folds its sums sequentially in f32, which no parallel machine reproduces.  Engine and
+// oracle share one order-free definition instead: every term (cos, sin, minimum-image displacement, coordinate) is
+// computed in f32 and added as the integer  rint(term * 2^24)  -- exact and associative, so any partition of the
+// group over threads, CTAs or devices gives the same bits -- and the circular-mean estimate, which only seeds the
+// refinement, evaluates its transcendentals with fixed polynomials in IEEE operations + fmaf (no MUFU, no libm).
+constexpr float kCenterScale = 16777216.0f;   // 2^24
+
+// sin / cos of 2 pi u (u in turns): Taylor about the nearest quarter turn, |t| <= 1/8, <= 3e-8
+__device__ __forceinline__ void sincos_turns(float u, float &sn, float &cs) {
+    const float r = __fsub_rn(u, rintf(u));          // exact, [-0.5, 0.5]
+    const float j = rintf(__fmul_rn(4.0f, r));       // -2 .. 2
+    const float t = fmaf(j, -0.25f, r);              // exact
+    const float z = __fmul_rn(t, t);
+    float sp = fmaf(z, 0x1.507834p+5f, -0x1.32d2ccp+6f);
+    sp = fmaf(z, sp, 0x1.466bc6p+6f); sp = fmaf(z, sp, -0x1.4abbcep+5f); sp = fmaf(z, sp, 0x1.921fb6p+2f);
+    sp = __fmul_rn(sp, t);
+    float cp = fmaf(z, 0x1.e1f506p+5f, -0x1.55d3c8p+6f);
+    cp = fmaf(z, cp, 0x1.03c1f0p+6f); cp = fmaf(z, cp, -0x1.3bd3ccp+4f); cp = fmaf(z, cp, 1.0f);
+    const int q = (int)j & 3;
+    sn = q == 0 ? sp : (q == 1 ? cp : (q == 2 ? -sp : -cp));
+    cs = q == 0 ? cp : (q == 1 ? -sp : (q == 2 ? -cp : sp));
+}
+
+// atan2(y, x) / 2 pi in [-0.5, 0.5] (minimax of atan(a) / (2 pi a) in a^2, <= 2e-8 turns)
+__device__ __forceinline__ float atan2_turns(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
+    const float a = mx > 0.0f ? __fdiv_rn(mn, mx) : 0.0f;
+    const float z = __fmul_rn(a, a);
+    float p = fmaf(z, -0x1.931afcp-11f, 0x1.0236b0p-8f);
+    p = fmaf(z, p, -0x1.3a0c64p-7f); p = fmaf(z, p, 0x1.03ebd4p-6f); p = fmaf(z, p, -0x1.6e1bfcp-6f);
+    p = fmaf(z, p, 0x1.046a90p-5f); p = fmaf(z, p, -0x1.b295eep-5f); p = fmaf(z, p, 0x1.45f306p-3f);
+    float r = __fmul_rn(p, a);
+    if (ay > ax) r = __fsub_rn(0.25f, r);
+    if (x < 0.0f) r = __fsub_rn(0.5f, r);
+    if (y < 0.0f) r = -r;
+    return r;
+}
+
+// term -> fixed point; `bad` is raised for NaN / Inf / out-of-range terms (the centre is then NaN)
+__device__ __forceinline__ long long center_q(float term, bool &bad) {
+    if (!(fabsf(term) < 1073741824.0f)) { bad = true; return 0; }
+    return __float2ll_rn(__fmul_rn(term, kCenterScale));
+}
+__device__ __forceinline__ float center_mean(long long sum, int n) { return (float)(((double)sum * (1.0 / 16777216.0)) / (double)n); }
+// circular-mean estimate from the fixed-point sums of cos / sin
+__device__ __forceinline__ float center_estimate(long long sc, long long ss, float L) {
+    return __fmul_rn(L, __fadd_rn(atan2_turns(-(float)ss, -(float)sc), 0.5f));
+}
+
 // nalgebra dot for 3-vectors: (x0*y0 + x1*y1) + x2*y2, no FMA.
 __device__ __forceinline__ float dot_ref(const f3 &a, const f3 &b) {
     return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));

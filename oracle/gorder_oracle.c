@@ -217,11 +217,64 @@ int gorder_oracle_predict_hydrogens(int kind, const float *t, const float *h1, c
 /* ------------------------------------------------------------------------------------------
  * Centre of geometry of a group (System::group_get_center / _naive; pbc.rs:101,270)
  * groan_rs: "refined Bai-Breen" (CHANGELOG.md v1.0.0): circular-mean estimate per axis, then the
- * mean of minimum-image displacements around the estimate, wrapped into the box.  f32, sequential
- * in ascending atom order as the reference's group iterator.
+ * mean of minimum-image displacements around the estimate, wrapped into the box.
+ *
+ * groan folds these sums sequentially in f32.  A sequential f32 fold over 1e4 - 1e6 atoms cannot be
+ * reproduced by a parallel machine, and its own rounding noise (~1e-7 L sqrt(N)) is larger than
+ * anything below, so the engine AND this oracle use one ORDER-FREE definition:
+ *   - every term (cos, sin, minimum-image displacement, coordinate) is computed in f32 and added
+ *     as the integer  llrint(term * 2^24)  (exact, associative: any order gives the same bits);
+ *   - the circular-mean estimate only seeds the refinement (the centre is independent of it up to
+ *     rounding), so its transcendental functions are evaluated by fixed polynomials in IEEE
+ *     operations and fmaf (sincos_turns / atan2_turns: <= 3e-8 / 2e-8 turns) instead of libm, whose
+ *     results no device reproduces bit for bit.
+ * variant 1 (gorder_oracle_variant_center) is the previous sequential-f32 / libm evaluation: the
+ * pins show that both agree to an ulp of the centre and give identical leaflets on every fixture.
  * ---------------------------------------------------------------------------------------- */
-static vec3 group_center(const float *xyz, const int32_t *idx, int n, const float *box, int pbc) {
-    if (n <= 0) { float q = nanf(""); return v3(q, q, q); }
+int gorder_oracle_variant_center = 0; /* 0: order-free fixed point + polynomial seed; 1: sequential f32 + libm */
+
+#define CENTER_SCALE 16777216.0f /* 2^24 */
+
+/* sin / cos of 2 pi u (u in turns), IEEE ops + fmaf only: Taylor about the nearest quarter turn, |t| <= 1/8 */
+static inline void sincos_turns(float u, float *sn, float *cs) {
+    const float r = u - rintf(u);          /* exact, [-0.5, 0.5] */
+    const float j = rintf(4.0f * r);       /* -2 .. 2 */
+    const float t = fmaf(j, -0.25f, r);    /* exact */
+    const float z = t * t;
+    float sp = fmaf(z, 0x1.507834p+5f, -0x1.32d2ccp+6f);
+    sp = fmaf(z, sp, 0x1.466bc6p+6f); sp = fmaf(z, sp, -0x1.4abbcep+5f); sp = fmaf(z, sp, 0x1.921fb6p+2f);
+    sp = sp * t;
+    float cp = fmaf(z, 0x1.e1f506p+5f, -0x1.55d3c8p+6f);
+    cp = fmaf(z, cp, 0x1.03c1f0p+6f); cp = fmaf(z, cp, -0x1.3bd3ccp+4f); cp = fmaf(z, cp, 1.0f);
+    const int q = (int)j & 3;
+    *sn = q == 0 ? sp : (q == 1 ? cp : (q == 2 ? -sp : -cp));
+    *cs = q == 0 ? cp : (q == 1 ? -sp : (q == 2 ? -cp : sp));
+}
+
+/* atan2(y, x) / 2 pi in [-0.5, 0.5], IEEE ops + fmaf only (minimax of atan(a) / (2 pi a) in a^2, <= 2e-8 turns) */
+static inline float atan2_turns(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
+    const float a = mx > 0.0f ? mn / mx : 0.0f;
+    const float z = a * a;
+    float p = fmaf(z, -0x1.931afcp-11f, 0x1.0236b0p-8f);
+    p = fmaf(z, p, -0x1.3a0c64p-7f); p = fmaf(z, p, 0x1.03ebd4p-6f); p = fmaf(z, p, -0x1.6e1bfcp-6f);
+    p = fmaf(z, p, 0x1.046a90p-5f); p = fmaf(z, p, -0x1.b295eep-5f); p = fmaf(z, p, 0x1.45f306p-3f);
+    float r = p * a;
+    if (ay > ax) r = 0.25f - r;
+    if (x < 0.0f) r = 0.5f - r;
+    if (y < 0.0f) r = -r;
+    return r;
+}
+
+/* term -> fixed point; *bad is raised for NaN / Inf / out-of-range terms (the centre is then NaN) */
+static inline int64_t center_q(float term, int *bad) {
+    if (!(fabsf(term) < 1073741824.0f)) { *bad = 1; return 0; }
+    return llrintf(term * CENTER_SCALE);
+}
+static inline float center_mean(int64_t sum, int n) { return (float)(((double)sum * (1.0 / 16777216.0)) / (double)n); }
+
+static vec3 group_center_sequential(const float *xyz, const int32_t *idx, int n, const float *box, int pbc) {
     if (!pbc) {
         vec3 s = v3(0, 0, 0);
         for (int i = 0; i < n; i++) { const float *p = xyz + 3 * (size_t)idx[i]; s = vadd(s, v3(p[0], p[1], p[2])); }
@@ -247,6 +300,34 @@ static vec3 group_center(const float *xyz, const int32_t *idx, int n, const floa
     }
     vec3 c = vadd(est, vdivs(s, (float)n));
     return wrap_point(c, box, 1);
+}
+
+static vec3 group_center(const float *xyz, const int32_t *idx, int n, const float *box, int pbc) {
+    if (n <= 0) { float q = nanf(""); return v3(q, q, q); }
+    if (gorder_oracle_variant_center == 1) return group_center_sequential(xyz, idx, n, box, pbc);
+    float c[3];
+    for (int a = 0; a < 3; a++) {
+        int bad = 0;
+        const float L = box ? box[a] : 0.0f;
+        if (!pbc) {
+            int64_t sx = 0;
+            for (int i = 0; i < n; i++) sx += center_q(xyz[3 * (size_t)idx[i] + a], &bad);
+            c[a] = bad ? nanf("") : center_mean(sx, n);
+            continue;
+        }
+        const float inv = 1.0f / L;
+        int64_t sc = 0, ss = 0, sd = 0;
+        for (int i = 0; i < n; i++) {
+            float sn, cs;
+            sincos_turns(xyz[3 * (size_t)idx[i] + a] * inv, &sn, &cs);
+            sc += center_q(cs, &bad); ss += center_q(sn, &bad);
+        }
+        const float est = L * (atan2_turns(-(float)ss, -(float)sc) + 0.5f);
+        for (int i = 0; i < n; i++) sd += center_q(min_image(xyz[3 * (size_t)idx[i] + a] - est, L), &bad);
+        if (bad || !(est == est)) { c[a] = nanf(""); continue; }
+        c[a] = wrap1(est + center_mean(sd, n), L);
+    }
+    return v3(c[0], c[1], c[2]);
 }
 
 void gorder_oracle_group_center(const float *xyz, const int32_t *idx, int n, const float *box, int pbc, float *out) {

@@ -478,7 +478,29 @@ def full_traj_golden(name: str, base: str, gro: str, bnd: str, kind: int, head: 
     print(name, q.shape, "cases:", list(cases))
 
 
+def xtc_fixtures():
+    """GROMACS-written trajectories of the reference's test tree, as they are (tests/golden/xtc/): the parity tests of the
+    XTC readers (host and device) must not only see streams of this repository's own writer.  Small files whole; of ua.xtc
+    (3.7 MB) the first five frames -- a byte prefix of an XTC file is the file of its first frames."""
+    import shutil
+    import struct
+    out = os.path.join(HERE, "xtc")
+    os.makedirs(out, exist_ok=True)
+    for rel in ("pcpepg_selected.xtc", "split/cg3.xtc", "split/pcpepg4.xtc", "multiple_resid_same_name.xtc"):
+        shutil.copyfile(os.path.join(FILES, rel), os.path.join(out, os.path.basename(rel)))
+    raw = open(os.path.join(FILES, "ua.xtc"), "rb").read()
+    pos, n = 0, 0
+    while n < 5:   # frame: 56-byte header, 32 bytes of compression parameters, length, padded stream
+        assert struct.unpack(">i", raw[pos:pos + 4])[0] == 1995
+        nbytes = struct.unpack(">i", raw[pos + 88:pos + 92])[0]
+        pos += 92 + (nbytes + 3) // 4 * 4
+        n += 1
+    open(os.path.join(out, "ua_first5.xtc"), "wb").write(raw[:pos])
+    print("xtc fixtures:", sorted(os.listdir(out)))
+
+
 if __name__ == "__main__":
+    xtc_fixtures()
     single_frame("cg_single_frame", "cg.gro", "cg.bnd", "cg.tpr", abi.KIND_CG, "cgorder.rs", 1.0, "PO4")
     single_frame("aa_single_frame", "pcpepg.gro", "pcpepg.bnd", "pcpepg.tpr", abi.KIND_AA, "aaorder.rs", -1.0, "P")
     ua_golden()

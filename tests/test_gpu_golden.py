@@ -65,22 +65,13 @@ def test_aa_trajectory_fixture():
 from test_oracle_pins import AA_FULL_CASES, CG_FULL_CASES, check_convergence, check_leaflet_export, check_maps_aa  # noqa: E402
 from parity import mean_order  # noqa: E402
 
-# geometry selections around the PBC centre of a group: a sample within an ulp of the shape's surface may fall on either side
-# depending on the summation order of the centre (oracle: f32 running sum; device: fixed-order f64 partials)
-BOUNDARY_CASES = {"cuboid_dynamic", "cylinder_dynamic", "sphere_dynamic", "sphere_dynamic_inverted"}
-
-
 def _check_full(which, name, batches):
     setup, xyz, box, fi, case = gc.full_case(which, name)
     g, r = run_both(setup, xyz, box, fi, batches=batches, oracle_threads=8)
-    if name in BOUNDARY_CASES:
-        dc = np.abs(g.count.astype(np.int64) - r.count.astype(np.int64))
-        assert dc.max() <= 2 and dc.sum() <= 8, (dc.max(), dc.sum())
-        np.testing.assert_allclose(mean_order(g.sum, g.count), mean_order(r.sum, r.count), atol=1e-3, rtol=0, equal_nan=True)
-        gc.assert_matches_yaml(g, setup, case, tol=5e-4)
-    else:
-        assert_raw_parity(g, r, setup, what=f"{which} full {name}")
-        gc.assert_matches_yaml(g, setup, case)
+    # counts bit-exact everywhere, also for geometry selections around the PBC centre of a group: engine and oracle share
+    # the order-free centre arithmetic
+    assert_raw_parity(g, r, setup, what=f"{which} full {name}")
+    gc.assert_matches_yaml(g, setup, case)
     if "maps" in case:
         check_maps_aa(g, setup, case)
     if "leaflets" in case:

@@ -370,3 +370,43 @@ def test_fast_kernel_aa_64_bond_types(leaflets, monkeypatch):
     g0, _ = run_both(s.setup, xyz, box, idx, oracle_threads=8)
     np.testing.assert_array_equal(g.sum, g0.sum)
     np.testing.assert_array_equal(g.count, g0.count)
+
+
+# ---- oracle comparisons at BASELINE.json's sizes (the oracle needs seconds for a few frames of them) ----
+def test_baseline_size_s_cg_against_oracle():
+    """configs[1] S-CG: 83 334 lipids, 1 000 008 beads, Global leaflets every frame (bond_fast_kernel + speculative centre),
+    3 frames against the oracle: counts and leaflet tables bit-exact, every sample within one unit of 1e-6."""
+    s = synthetic.s_cg(83334, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True, collect_leaflets=True)
+    xyz, box, idx = s.frames(0, 3)
+    g, r = run_both(s.setup, xyz, box, idx, batches=2, oracle_threads=8)
+    assert_raw_parity(g, r, s.setup, what="S-CG full size")
+    assert int(g.count[:, 0].sum()) == 916674 * 3
+
+
+def test_baseline_size_s_aa_large_maps_and_cylinder_against_oracle():
+    """configs[3] S-AA-large: 4 096 lipids, 64 C-H bond types, Global leaflets, XY order maps (0.1 nm bins over the box) and
+    a cylinder of 8 nm around the box centre: 2 frames against the oracle, maps included (64 x 3 maps of ~130 000 bins)."""
+    s = synthetic.s_aa(4096, n_water=0, leaflet_mode=abi.LEAFLET_GLOBAL, map_enabled=True, map_plane=abi.PLANE_XY, map_bin=(0.1, 0.1),
+                       geom_kind=abi.GEOM_CYLINDER, geom_ref_kind=abi.GEOMREF_BOX_CENTER, geom_dims=(8.0, float("-inf"), float("inf")),
+                       geom_axis=abi.AXIS_Z)
+    s.setup.map_span_x = (0.0, float(s.box[0]))
+    s.setup.map_span_y = (0.0, float(s.box[1]))
+    xyz, box, idx = s.frames(0, 2)
+    g, r = run_both(s.setup, xyz, box, idx, oracle_threads=8)
+    assert_raw_parity(g, r, s.setup, what="S-AA-large full size")
+    assert g.map_count.sum() == g.count[:, 0].sum() * 2   # with leaflets: total map = upper + lower, every sample in one bin
+    assert 0 < g.count[:, 0].sum() < 4096 * 64 * 2        # the cylinder leaves lipids out
+
+
+def test_baseline_size_s_ua_error_blocks_against_oracle():
+    """configs[2] S-UA: 256 Berger-like lipids (CH3 / CH2 / CH1), per-frame sums for the error blocks, 40 frames: per-frame
+    counts bit-exact, per-frame order within 1e-5, and the block errors of the converted results equal."""
+    from gorder_b200 import results
+    s = synthetic.s_ua(256, timewise=True, leaflet_mode=abi.LEAFLET_GLOBAL)
+    xyz, box, idx = s.frames(0, 40)
+    g, r = run_both(s.setup, xyz, box, idx, batches=3, oracle_threads=8)
+    assert_raw_parity(g, r, s.setup, what="S-UA full size")
+    cg_, cr_ = results.convert(g, s.setup, n_blocks=5, native=True), results.convert(r, s.setup, n_blocks=5)
+    for key in ("total", "upper", "lower"):
+        a, b = getattr(cg_.average, key), getattr(cr_.average, key)
+        assert abs(a.value - b.value) < 1e-5 and abs(a.error - b.error) < 1e-5, key

@@ -150,3 +150,46 @@ def test_device_decode_equals_host_decode(tmp_path, case):
         b.close()
         np.testing.assert_array_equal(wa.sum, wb.sum)
         np.testing.assert_array_equal(wa.tw_frame_index, wb.tw_frame_index)
+
+
+GROMACS_FIXTURES = ["pcpepg_selected.xtc", "cg3.xtc", "pcpepg4.xtc", "multiple_resid_same_name.xtc", "ua_first5.xtc"]
+
+
+@pytest.mark.parametrize("name", GROMACS_FIXTURES)
+def test_device_decode_of_gromacs_written_files(name):
+    """xtc_decode_kernel on streams GROMACS wrote (tests/golden/xtc: the reference's pcpepg_selected.xtc, split/cg3.xtc,
+    split/pcpepg4.xtc, multiple_resid_same_name.xtc, the first five frames of ua.xtc), checked against the ORACLE's reader
+    (oracle/xtc.c), not against this repository's host decoder or writer.  The probe engine uses EVERY atom of the file --
+    consecutive atoms form two-atom 'molecules' with one bond -- and keeps per-frame sums: the coordinates live on a
+    lattice of 1 / precision nm, so a single atom decoded one lattice step off moves S of its bond by ~1e-2 and the
+    frame's integer sum with it."""
+    import os
+    from oracle import fixtures
+    path = os.path.join(os.path.dirname(__file__), "golden", "xtc", name)
+    ref = fixtures.read_xtc(path)
+    xyz = np.ascontiguousarray(np.asarray(ref.xyz, np.float32))
+    n_frames, n_atoms = xyz.shape[0], xyz.shape[1]
+    box = np.ascontiguousarray(np.asarray(ref.box, np.float32).reshape(n_frames, 3))
+    pairs = abi.MolType(name="PAIR", mol_base=np.arange(0, n_atoms - 1, 2), bond_rel=[(0, 1)])
+    moltypes = [pairs]
+    if n_atoms % 2:   # the last atom joins the two before it
+        pairs.mol_base = pairs.mol_base[:-1]
+        moltypes.append(abi.MolType(name="TRIPLE", mol_base=np.array([n_atoms - 3]), bond_rel=[(0, 1), (1, 2)]))
+    setup = abi.EngineSetup(kind=abi.KIND_CG, n_atoms=n_atoms, moltypes=moltypes, timewise=True)
+    want = _direct(setup, xyz, box, np.arange(n_frames))
+    assert int(want.count[:, 0].sum()) == (n_atoms + 1) // 2 * n_frames   # every atom is in exactly one 'molecule'
+    with XtcFile(path) as x:
+        assert (x.n_atoms, x.n_frames) == (n_atoms, n_frames)
+        for batch in (1, 3):
+            eng = SystemTopology(setup)
+            moved = eng.run_xtc_device(x, batch_frames=batch, n_threads=2)
+            got = eng.finish()
+            eng.close()
+            assert moved > 0   # the device path took the frames (no fall-back to the host decoder)
+            np.testing.assert_array_equal(got.tw_sum, want.tw_sum)
+            np.testing.assert_array_equal(got.count, want.count)
+        host = SystemTopology(setup)
+        host.run_xtc(x, batch_frames=2, n_threads=2)
+        got = host.finish()
+        host.close()
+        np.testing.assert_array_equal(got.tw_sum, want.tw_sum)

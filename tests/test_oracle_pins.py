@@ -64,6 +64,37 @@ def test_min_image_variant_is_pinned():
         vm.value = 1
 
 
+def test_order_free_group_center_agrees_with_the_sequential_fold():
+    """group_center: engine and oracle add the terms of the refined Bai-Breen centre as fixed-point integers
+    and seed it with polynomial sin / cos / atan, so that the result does not depend on the order of the atoms.  The previous
+    evaluation (sequential f32 folds, libm: what groan most likely does) stays available as variant 1: on the reference's own
+    AA and CG trajectories both give the same centre to a few ulp -- the sequential fold itself is only good to ~1e-6 -- and
+    the leaflet fixtures are reproduced bit for bit either way (the whole module runs with variant 0)."""
+    import ctypes as C
+    L = oracle.lib()
+    vc = C.c_int.in_dll(L, "gorder_oracle_variant_center")
+    assert vc.value == 0
+    rng = np.random.default_rng(3)
+    for which in ("aa", "cg"):
+        setup, xyz, box, fi, case = gc.full_case(which, "leaflets_global")
+        mem = np.asarray(setup.membrane)
+        for f in (0, len(xyz) // 2, len(xyz) - 1):
+            a = oracle.group_center(xyz[f], mem, box[f])
+            b = oracle.group_center(xyz[f], rng.permutation(mem), box[f])
+            np.testing.assert_array_equal(a, b)               # order-free
+            vc.value = 1
+            try:
+                c = oracle.group_center(xyz[f], mem, box[f])
+            finally:
+                vc.value = 0
+            assert np.all(np.abs(a - c) <= 2e-6 * box[f]), (which, f, a, c)
+    # no PBC: the naive mean, same fixed-point sum
+    pts = rng.random((1000, 3)).astype(np.float32) * 7
+    a = oracle.group_center(pts, np.arange(1000), np.zeros(3), pbc=False)
+    np.testing.assert_allclose(a, pts.astype(np.float64).mean(axis=0), atol=1e-6)
+    assert np.all(np.isnan(oracle.group_center(np.full((4, 3), np.nan, np.float32), np.arange(4), np.ones(3))))
+
+
 @pytest.mark.parametrize("name,counts", [("cg_single_frame", ([242, 242, 24], [121, 121, 12], [121, 121, 12])),
                                          ("aa_single_frame", ([131, 128, 15], [65, 64, 8], [66, 64, 7]))])
 def test_single_frame_goldens(name, counts):

@@ -84,7 +84,6 @@ def test_truncated_and_bad_files(tmp_path):
     # a forged 64-bit length in a magic-2023 header: 0xFFFFFFFFFFFFFFF0 wraps the cursor, 2^40 points far
     # outside the mapping; both must stop the index at the frames before, not crash or loop
     import struct
-    s9 = synthetic.s_cg(100)
     for forged in (0xFFFFFFFFFFFFFFF0, 1 << 40, len(raw)):
         n_first = raw.index(struct.pack(">i", 1995), 4)          # start of the second frame
         head = bytearray(raw[n_first:n_first + 56 + 32])
@@ -117,6 +116,25 @@ def test_reference_trajectories_match_oracle_reader(name, shape):
     np.testing.assert_array_equal(time, np.asarray(ref.time, np.float32))
     if shape is not None:
         assert got.shape[:2] == shape
+
+
+GROMACS_FIXTURES = ["pcpepg_selected.xtc", "cg3.xtc", "pcpepg4.xtc", "multiple_resid_same_name.xtc", "ua_first5.xtc"]
+
+
+@pytest.mark.parametrize("name", GROMACS_FIXTURES)
+def test_gromacs_written_fixtures_match_oracle_reader(name):
+    """The committed GROMACS-written streams (tests/golden/xtc, copied from the reference's tests/files by make_golden.py):
+    product reader == the oracle's independent reader, bit for bit, and the control-bit walk of the device path accepts
+    them (the same group structure the decoder kernel will follow)."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "xtc", name)
+    ref = _oracle_read(path)
+    with XtcFile(path) as x:
+        got, box9, time, step = x.read(n_threads=2)
+        np.testing.assert_array_equal(got, np.asarray(ref.xyz, np.float32).reshape(got.shape))
+        np.testing.assert_array_equal(time, np.asarray(ref.time, np.float32))
+        groups, marks = x.scan()
+        assert np.all(groups > 0) and np.all(marks == (groups + 31) // 32)
+        assert np.all(groups <= x.n_atoms)
 
 
 _FUZZ = r'''
