@@ -12,6 +12,7 @@ SOURCES = [os.path.join(_HERE, "csrc", "gorder_capi.cu")]
 HEADERS = [
     os.path.join(_HERE, "csrc", "gorder_kernels.cuh"),
     os.path.join(_HERE, "csrc", "gorder_fast.cuh"),
+    os.path.join(_HERE, "csrc", "gorder_ua_fast.cuh"),
     os.path.join(_HERE, "csrc", "gorder_spherical.cuh"),
     os.path.join(_HERE, "csrc", "gorder_xtc.inl"),
     os.path.join(_HERE, "csrc", "gorder_results.inl"),

@@ -18,6 +18,7 @@
 
 #include "gorder_kernels.cuh"
 #include "gorder_fast.cuh"
+#include "gorder_ua_fast.cuh"
 #include "gorder_spherical.cuh"
 
 using namespace gorder;
@@ -194,6 +195,9 @@ struct GorderHandle {
     long long prof_n = 0;
 
     bool fast_ok = false;   // K1f applies (bond_fast_kernel)
+    bool ua_fast_ok = false;   // K2f applies (ua_fast_kernel)
+    size_t ua_fast_smem = 0;
+    int ua_fast_tile = 0, ua_fast_items = 0, ua_fast_orders = 0, ua_fast_nbuf = 0, n_sm = 0;
     int fast_slot = -1;     // slot of this handle's tables in constant memory (c_fast), -1: global tables
     // speculative Global leaflets (bond_order_kernel<SPEC> + spec_repair_kernel)
     bool spec_ok = false, spec_disabled = false, spec_ref_valid = false;
@@ -595,6 +599,10 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         if (h->mpt == 4) launch_bond_spec<4>(h, grid, smem, d_planes, da, o);
         else if (h->mpt == 2) launch_bond_spec<2>(h, grid, smem, d_planes, da, o);
         else launch_bond_spec<1>(h, grid, smem, d_planes, da, o);
+    } else if (h->ua_fast_ok && (reinterpret_cast<uintptr_t>(d_planes) & 15) == 0) {   // bulk copies need 16-byte aligned tiles
+        const int ctas = (int)std::min<long long>((long long)h->n_chunks * nf, h->n_sm);   // persistent: one CTA per SM
+        if (h->leaf) ua_fast_kernel<true><<<ctas, kUaThreads, h->ua_fast_smem, h->stream>>>(h->view, d_planes, da, h->d_leaf_rows, o, nf, h->ua_fast_tile, h->ua_fast_items, h->ua_fast_orders, h->ua_fast_nbuf);
+        else ua_fast_kernel<false><<<ctas, kUaThreads, h->ua_fast_smem, h->stream>>>(h->view, d_planes, da, h->d_leaf_rows, o, nf, h->ua_fast_tile, h->ua_fast_items, h->ua_fast_orders, h->ua_fast_nbuf);
     } else if (h->ua) launch_ua(h, grid, smem, d_planes, da, o);
     else if (h->mpt == 4) launch_bond3<4>(h, grid, smem, d_planes, da, o);
     else if (h->mpt == 2) launch_bond3<2>(h, grid, smem, d_planes, da, o);
@@ -1071,6 +1079,28 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
             ft.chunk0[s->n_moltypes] = c;
             for (size_t i = 0; i < bonds.size(); i++) ft.bonds[i] = bonds[i];
             CK(cudaMemcpyToSymbol(c_fast, &ft, sizeof(ft), (size_t)h->fast_slot * sizeof(FastTables)));
+        }
+    }
+    // K2f (gorder_ua_fast.cuh): UA, PBC, static normal, no geometry / maps, streaming hydrogen construction; the tile of a CTA
+    // (3 x used atoms x 256 molecules floats) must fit in shared memory next to the tables
+    if (ua && !h->nvec && !h->extra && s->handle_pbc && !h->sw.ua_exact && !h->sw.no_fast && h->frame_floats % 4 == 0) {
+        bool ok = true;
+        int max_tile = 0, max_orders = 0;
+        for (auto &t : h->types) {
+            ok = ok && t.tile == kUaTile && (t.plane_base % 4) == 0;
+            max_tile = std::max(max_tile, t.tile_stride); max_orders = std::max(max_orders, t.n_orders);
+        }
+        int max_optin = 0;
+        CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device));
+        const size_t tables = uas.size() * sizeof(UAItem) + (size_t)2 * kUaPairWarps * max_orders * 2 * sizeof(int) + 256;
+        for (int nbuf = 2; ok && nbuf >= 1 && !h->ua_fast_ok; nbuf--) {   // two tile buffers when they fit (the copy of the next tile overlaps the arithmetic), else one
+            const size_t need = (size_t)nbuf * max_tile * sizeof(float) + tables;
+            if (need + 1024 > (size_t)max_optin) continue;
+            h->ua_fast_ok = true; h->ua_fast_smem = need; h->ua_fast_nbuf = nbuf;
+            h->ua_fast_tile = max_tile; h->ua_fast_items = (int)uas.size(); h->ua_fast_orders = max_orders;
+            CK(cudaFuncSetAttribute(ua_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(ua_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         }
     }
     // speculative Global leaflets: AA/CG, static normal along the leaflet axis, PBC, assignment on every analysed frame,
