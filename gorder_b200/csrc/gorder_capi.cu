@@ -305,11 +305,11 @@ void launch_bond_spec(GorderHandle *h, dim3 grid, size_t smem, const float *plan
                                                                                              h->d_normal_npoints, o);
 }
 // K1f (gorder_fast.cuh): PBC, static normal, no geometry / maps, 2 or 4 molecules per lane
-template <int NP>
+template <int NP, int BLOCK = kBlock>
 void launch_fast(GorderHandle *h, dim3 grid, size_t smem, const float *planes, const FrameAux *aux, AccumOut o, bool spec) {
-    if (!h->leaf) bond_fast_kernel<NP, false, false><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o, h->fast_slot);
-    else if (spec) bond_fast_kernel<NP, true, true><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o, h->fast_slot);
-    else bond_fast_kernel<NP, true, false><<<grid, kBlock, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o, h->fast_slot);
+    if (!h->leaf) bond_fast_kernel<NP, false, false, BLOCK><<<grid, BLOCK, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o, h->fast_slot);
+    else if (spec) bond_fast_kernel<NP, true, true, BLOCK><<<grid, BLOCK, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o, h->fast_slot);
+    else bond_fast_kernel<NP, true, false, BLOCK><<<grid, BLOCK, smem, h->stream>>>(h->view, planes, aux, h->d_leaf_rows, o, h->fast_slot);
 }
 
 template <int MPT>
@@ -594,7 +594,8 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     }
     if (h->fast_ok && !h->sw.no_fast) {
         if (h->mpt == 4) launch_fast<2>(h, grid, smem, d_planes, da, o, spec);
-        else launch_fast<1>(h, grid, smem, d_planes, da, o, spec);
+        else if (h->mpt == 2) launch_fast<1>(h, grid, smem, d_planes, da, o, spec);
+        else launch_fast<2, 64>(h, grid, smem, d_planes, da, o, spec);   // one tile of 256 molecules: 64 lanes x 4 molecules
     } else if (spec) {
         if (h->mpt == 4) launch_bond_spec<4>(h, grid, smem, d_planes, da, o);
         else if (h->mpt == 2) launch_bond_spec<2>(h, grid, smem, d_planes, da, o);
@@ -1064,7 +1065,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         CK(cudaEventCreateWithFlags(&h->ev_post_any, cudaEventDisableTiming));
     }
 
-    h->fast_ok = !ua && !h->nvec && !h->extra && s->handle_pbc && (h->mpt == 2 || h->mpt == 4);
+    h->fast_ok = !ua && !h->nvec && !h->extra && s->handle_pbc;
     if (h->fast_ok && s->n_moltypes <= kFastTypes && (int)bonds.size() <= kFastBonds && h->device < 64 && !h->sw.no_const_tables) {
         {
             std::lock_guard<std::mutex> lock(g_fast_mu);

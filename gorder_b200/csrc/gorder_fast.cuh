@@ -182,17 +182,21 @@ __device__ __forceinline__ void fast_bond(AtomBuf<NP> &first, AtomBuf<NP> &other
     }
 }
 
-template <int NP, bool LEAF, bool SPEC>
-__global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+// BLOCK threads x 2 NP molecules = the tile of the molecule type's layout (256, 512 or 1024 molecules): small systems
+// (one tile of 256 molecules per frame, BASELINE configs[0]) run 64-thread CTAs with four molecules per lane, so that the
+// batch's frames supply the parallelism and every lane still issues 128-bit loads and packed arithmetic.
+template <int NP, bool LEAF, bool SPEC, int BLOCK = kBlock>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) bond_fast_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                               const unsigned char *__restrict__ leaf_rows, AccumOut o, int fast_slot) {
     constexpr int MPT = 2 * NP;
     constexpr int NA = LEAF ? 2 : 1;
+    constexpr int WARPS = BLOCK / 32;
     extern __shared__ int smem[];
-    __shared__ int s_nup[kWarps];
+    __shared__ int s_nup[WARPS];
     __shared__ unsigned s_done;
-    __shared__ float s_hmm[2][kWarps];
-    __shared__ double s_dsum[2][kWarps];
-    __shared__ float s_dabs[kWarps];
+    __shared__ float s_hmm[2][WARPS];
+    __shared__ double s_dsum[2][WARPS];
+    __shared__ float s_dabs[WARPS];
     Chunk ch;
     TypeDesc td;
     if (fast_slot >= 0) {   // tables in constant memory: no global load before the first plane load
@@ -200,13 +204,13 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
         int t = 0;
         while (t + 1 < ft.n_types && (int)blockIdx.x >= ft.chunk0[t + 1]) t++;
         td = ft.types[t];
-        ch.type = t; ch.first_mol = ((int)blockIdx.x - ft.chunk0[t]) * (kBlock * MPT);
+        ch.type = t; ch.first_mol = ((int)blockIdx.x - ft.chunk0[t]) * (BLOCK * MPT);
     } else {
         ch = v.chunks[blockIdx.x];
         td = v.types[ch.type];
     }
-    if (ch.first_mol + kBlock * MPT > td.n_mol) {   // the last tile of a molecule type (molecules past the end) takes the generic, masked code
-        bond_order_body<MPT, true, false, LEAF, false, SPEC>(v, planes, aux, leaf_rows, nullptr, nullptr, o);
+    if (ch.first_mol + BLOCK * MPT > td.n_mol) {   // the last tile of a molecule type (molecules past the end) takes the generic, masked code
+        bond_order_body<MPT, true, false, LEAF, false, SPEC, BLOCK>(v, planes, aux, leaf_rows, nullptr, nullptr, o);
         return;
     }
     const int f = blockIdx.y;
@@ -215,14 +219,14 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
     const int mpad = td.cstride;
     const int c0 = (v.normal_axis + 1) % 3, c1 = (v.normal_axis + 2) % 3, c2 = v.normal_axis;   // the normal axis comes last
     BondItem *s_bonds = reinterpret_cast<BondItem *>(smem);
-    int *s_acc = smem + 2 * nb;                 // [kWarps][nb][NA]
-    for (int i = threadIdx.x; i < nb; i += kBlock) s_bonds[i] = fast_slot >= 0 ? c_fast[fast_slot].bonds[td.item_off + i] : v.bonds[td.item_off + i];
+    int *s_acc = smem + 2 * nb;                 // [WARPS][nb][NA]
+    for (int i = threadIdx.x; i < nb; i += BLOCK) s_bonds[i] = fast_slot >= 0 ? c_fast[fast_slot].bonds[td.item_off + i] : v.bonds[td.item_off + i];
     if (threadIdx.x == 0) s_done = 0u;
     // The kernel is bound by memory latency (8 warps per scheduler, ~150 issue slots between a warp's loads): one
-    // lane per CTA asks L2 for the CTA's slices (kBlock * MPT floats per component: contiguous) of the planes that the
+    // lane per CTA asks L2 for the CTA's slices (BLOCK * MPT floats per component: contiguous) of the planes that the
     // bonds kPrefetchAhead iterations later will read, so that the plane loads find their lines in L2.
     constexpr int kPrefetchAhead = 2;   // measured: 1 -> 0.78, 2 -> 0.80, 3 -> 0.78, 6 -> 0.77, 11 -> 0.75 of the HBM peak
-    constexpr unsigned kSliceBytes = kBlock * MPT * sizeof(float);
+    constexpr unsigned kSliceBytes = BLOCK * MPT * sizeof(float);
     const float *tile0 = planes + (size_t)f * v.frame_floats + mol_offset(td, ch.first_mol);
     if (threadIdx.x == 0 && LEAF && (SPEC || o.inline_center)) l2_prefetch_bulk(tile0 + td.head_off + v.leaflet_axis * mpad, kSliceBytes);
     __syncthreads();
@@ -338,14 +342,14 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
     unsigned ticket = 0;
     if (lane == 0) ticket = atomicAdd(&s_done, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket != kWarps - 1) return;
+    if (ticket != WARPS - 1) return;
     __threadfence_block();
     int cta_up = 0;
-    for (int w = 0; w < kWarps; w++) cta_up += s_nup[w];
-    const int cnt_total = kBlock * MPT;
+    for (int w = 0; w < WARPS; w++) cta_up += s_nup[w];
+    const int cnt_total = BLOCK * MPT;
     for (int i = lane; i < nb; i += 32) {
         long long acc0 = 0, acc1 = 0;
-        for (int w = 0; w < kWarps; w++) {
+        for (int w = 0; w < WARPS; w++) {
             const int *p = s_acc + ((size_t)w * nb + i) * NA;
             acc0 += p[0];
             if (LEAF) acc1 += p[1];
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(kBlock, 4) bond_fast_kernel(DeviceView v, cons
         double ds = 0.0, dq = 0.0;
         float p0 = 0.0f, p1 = CUDART_INF_F, p2 = 0.0f;
         bool bad = false;
-        for (int w = 0; w < kWarps; w++) {
+        for (int w = 0; w < WARPS; w++) {
             ds += s_dsum[0][w]; dq += s_dsum[1][w];
             bad = bad || s_dabs[w] != s_dabs[w] || s_hmm[0][w] != s_hmm[0][w];
             p0 = fmaxf(p0, s_dabs[w]); p1 = fminf(p1, s_hmm[0][w]); p2 = fmaxf(p2, s_hmm[1][w]);

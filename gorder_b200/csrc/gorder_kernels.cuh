@@ -879,7 +879,7 @@ __device__ __forceinline__ void warp_commit(int *s_acc, int lane, int su, int sl
 }
 
 // CTA epilogue: add the per-warp partials of every order slot to this frame's accumulators.
-template <bool LEAF, bool EXTRA>
+template <bool LEAF, bool EXTRA, int WARPS = kWarps>
 __device__ __forceinline__ void cta_flush(const DeviceView &v, const AccumOut &o, const int *s_acc, int n_orders, int slot0, int tw_row,
                                           int cnt_total, int cnt_up) {
     constexpr int NA = AccLayout<LEAF, EXTRA>::N;
@@ -888,7 +888,7 @@ __device__ __forceinline__ void cta_flush(const DeviceView &v, const AccumOut &o
 #pragma unroll
         for (int k = 0; k < NA; k++) acc[k] = 0;
         int c_up = 0, c_lo = 0;
-        for (int w = 0; w < kWarps; w++) {
+        for (int w = 0; w < WARPS; w++) {
             const int *p = s_acc + ((size_t)w * n_orders + i) * NA;
             if (LEAF) {
                 acc[0] += p[0]; acc[1] += p[1];
@@ -1027,11 +1027,12 @@ __global__ void __launch_bounds__(256) spec_leftover_kernel(DeviceView v, const 
 //           instead of a static axis; LEAF per-leaflet accumulation; EXTRA geometry filter / maps.
 // ---------------------------------------------------------------------------------------------
 //           SPEC speculative Global leaflets: no centre pre-pass (see AccumOut::spec_*).
-template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA, bool SPEC = false>
+template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA, bool SPEC = false, int BLOCK = kBlock>
 __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                 const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
                                                 const int *__restrict__ normal_npoints, const AccumOut &o) {
     constexpr int NA = AccLayout<LEAF, EXTRA>::N;
+    constexpr int WARPS = BLOCK / 32;   // the CTA has BLOCK threads (256, or fewer when K1f hands over the partial tile of a small system)
     // Static normal without geometry / maps: S depends only on (d_axis, |d|^2), so the kernel reads the
     // components in the order (axis+1, axis+2, axis) and never selects a component at run time.
     constexpr bool PERMUTE = !NVEC && !EXTRA;
@@ -1042,9 +1043,9 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
     const FrameAux &ax = aux[f];
     const int nb = td.n_items;
     BondItem *s_bonds = reinterpret_cast<BondItem *>(smem);
-    int *s_acc = smem + 2 * nb;                 // [kWarps][nb][NA]
-    int *s_cnt = s_acc + kWarps * nb * NA;      // [2] valid, valid & upper
-    for (int i = threadIdx.x; i < nb; i += kBlock) s_bonds[i] = v.bonds[td.item_off + i];
+    int *s_acc = smem + 2 * nb;                 // [WARPS][nb][NA]
+    int *s_cnt = s_acc + WARPS * nb * NA;      // [2] valid, valid & upper
+    for (int i = threadIdx.x; i < nb; i += BLOCK) s_bonds[i] = v.bonds[td.item_off + i];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
 
@@ -1111,9 +1112,9 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
     for (int j = 0; j < MPT; j++) any_used[j] = false;
     float nan_acc = 0.0f;   // NaN coordinates poison this accumulator (checked once after the loop)
     // SPEC: head extremes of the CTA -> shared (frees the registers for the loop)
-    __shared__ float s_hmm[2][kWarps];
-    __shared__ double s_dsum[2][kWarps];
-    __shared__ float s_dabs[kWarps];
+    __shared__ float s_hmm[2][WARPS];
+    __shared__ double s_dsum[2][WARPS];
+    __shared__ float s_dabs[WARPS];
     if (SPEC) {
         float a = hnan ? CUDART_NAN_F : hmin, b = hmax;
 #pragma unroll
@@ -1240,12 +1241,12 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
         if (lane == 0) { s_dsum[0][warp] = ds; s_dsum[1][warp] = dq; s_dabs[warp] = a; }
     }
     __syncthreads();
-    cta_flush<LEAF, EXTRA>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
+    cta_flush<LEAF, EXTRA, WARPS>(v, o, s_acc, nb, td.slot0, ax.tw_row, s_cnt[0], s_cnt[1]);
     if (SPEC && threadIdx.x == 0) {
         double ds = 0.0, dq = 0.0;
         float p0 = 0.0f, p1 = CUDART_INF_F, p2 = 0.0f;
         bool bad = false;
-        for (int w = 0; w < kWarps; w++) {
+        for (int w = 0; w < WARPS; w++) {
             ds += s_dsum[0][w]; dq += s_dsum[1][w];
             bad = bad || s_dabs[w] != s_dabs[w] || s_hmm[0][w] != s_hmm[0][w];
             p0 = fmaxf(p0, s_dabs[w]); p1 = fminf(p1, s_hmm[0][w]); p2 = fmaxf(p2, s_hmm[1][w]);
