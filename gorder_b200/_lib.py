@@ -18,6 +18,7 @@ SYMBOLS = [
     "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_stream",
     "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_xtc_scan", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device",
     "gorder_results_order", "gorder_results_convergence", "gorder_results_map", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
+    "gorder_gpu_reduce", "gorder_comm_unique_id", "gorder_comm_create", "gorder_gpu_reduce_comm", "gorder_comm_broadcast_leaflets", "gorder_comm_destroy",
 ]
 
 
@@ -41,6 +42,13 @@ def lib() -> C.CDLL:
     L.gorder_gpu_reserve_frames.argtypes = [vp, i64]
     L.gorder_gpu_reserve_frames.restype = C.c_int
     L.gorder_gpu_sync.argtypes = [vp]
+    L.gorder_gpu_reduce.argtypes = [C.POINTER(vp), i32, i32]
+    L.gorder_comm_unique_id.argtypes = [vp]
+    L.gorder_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+    L.gorder_gpu_reduce_comm.argtypes = [vp, vp, i32]
+    L.gorder_comm_broadcast_leaflets.argtypes = [vp, vp, i32]
+    L.gorder_comm_destroy.argtypes = [vp]
+    L.gorder_comm_destroy.restype = None
     L.gorder_gpu_result_sizes.argtypes = [vp, C.POINTER(abi.CGorderResults)]
     L.gorder_gpu_finish.argtypes = [vp, C.POINTER(abi.CGorderResults)]
     L.gorder_gpu_accumulator_block.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]

@@ -52,6 +52,7 @@ ERR_ORDERMAP_NO_BOX = 22
 ERR_NO_DEVICE = 30
 ERR_CUDA = 31
 ERR_OUT_OF_MEMORY = 32
+ERR_NCCL = 33
 
 ERROR_NAMES = {
     ERR_UNDEFINED_BOX: "AnalysisError::UndefinedBox",
@@ -72,6 +73,7 @@ ERROR_NAMES = {
     ERR_NO_DEVICE: "no CUDA device (there is no CPU fallback)",
     ERR_CUDA: "CUDA error",
     ERR_OUT_OF_MEMORY: "out of device memory",
+    ERR_NCCL: "NCCL unavailable or a collective failed",
 }
 
 _i32p = C.POINTER(C.c_int32)

@@ -16,6 +16,7 @@ HEADERS = [
     os.path.join(_HERE, "csrc", "gorder_spherical.cuh"),
     os.path.join(_HERE, "csrc", "gorder_xtc.inl"),
     os.path.join(_HERE, "csrc", "gorder_results.inl"),
+    os.path.join(_HERE, "csrc", "gorder_multi.inl"),
     os.path.join(_HERE, "csrc", "gorder_engine.cuh"),
     os.path.join(_HERE, "csrc", "gorder_math.cuh"),
     os.path.join(_HERE, "..", "include", "gorder_b200.h"),

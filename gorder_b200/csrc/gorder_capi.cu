@@ -1494,3 +1494,4 @@ int64_t gorder_gpu_error_detail(GorderHandle *h) { return h ? h->err_detail : -1
 
 #include "gorder_xtc.inl"
 #include "gorder_results.inl"
+#include "gorder_multi.inl"

@@ -150,6 +150,14 @@ class SystemTopology:
     def write_block(self, d_src: int):
         self._check(lib().gorder_gpu_write_block(self._h, C.c_void_p(d_src)))
 
+    def reduce_comm(self, comm: "Comm", root: int = 0):
+        """``ParallelTrajData::reduce`` across ranks (one process per GPU): collective ``gorder_gpu_reduce_comm``."""
+        self._check(lib().gorder_gpu_reduce_comm(self._h, comm._c, int(root)))
+
+    def broadcast_leaflets(self, comm: "Comm", root: int = 0):
+        """``Frequency::Once``: the table of analysed frame 0 (rank ``root``) reaches every shard (collective)."""
+        self._check(lib().gorder_comm_broadcast_leaflets(self._h, comm._c, int(root)))
+
     def profile(self, enable: bool = True):
         self._check(lib().gorder_gpu_profile(self._h, int(enable)))
 
@@ -191,6 +199,49 @@ class SystemTopology:
         if self._h:
             lib().gorder_gpu_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def reduce_handles(engines, root: int = 0):
+    """``ParallelTrajData::reduce`` for one process that drives several GPUs (``gorder_gpu_reduce``): afterwards
+    ``engines[root].finish()`` returns the merged result."""
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    rc = lib().gorder_gpu_reduce(arr, len(engines), int(root))
+    if rc != abi.OK:
+        engines[root]._check(rc)
+
+
+class Comm:
+    """The library's own NCCL communicator (``gorder_comm_*``): rank 0 makes the id, the host broadcasts its 128 bytes."""
+
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(Comm.ID_BYTES)
+        rc = lib().gorder_comm_unique_id(buf)
+        if rc != abi.OK:
+            raise abi.GorderError(rc)
+        return buf.raw
+
+    def __init__(self, uid: bytes, n_ranks: int, rank: int, device: int):
+        self._c = C.c_void_p()
+        buf = C.create_string_buffer(bytes(uid), Comm.ID_BYTES)
+        rc = lib().gorder_comm_create(buf, int(n_ranks), int(rank), int(device), C.byref(self._c))
+        if rc != abi.OK:
+            self._c = C.c_void_p()
+            raise abi.GorderError(rc)
+        self.n_ranks, self.rank = n_ranks, rank
+
+    def close(self):
+        if self._c:
+            lib().gorder_comm_destroy(self._c)
+            self._c = C.c_void_p()
 
     def __del__(self):
         try:

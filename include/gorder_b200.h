@@ -108,7 +108,8 @@ enum {
     GORDER_ERR_ORDERMAP_NO_BOX = 22,           /* OrderMapConfigError::InvalidBoxAuto */
     GORDER_ERR_NO_DEVICE = 30,                 /* no usable CUDA device: there is NO CPU fallback */
     GORDER_ERR_CUDA = 31,
-    GORDER_ERR_OUT_OF_MEMORY = 32
+    GORDER_ERR_OUT_OF_MEMORY = 32,
+    GORDER_ERR_NCCL = 33                       /* NCCL missing at run time, or a collective failed */
 };
 
 /* ---- setup ------------------------------------------------------------------------------ */
@@ -294,8 +295,38 @@ int gorder_gpu_sync(GorderHandle *h);
 int gorder_gpu_result_sizes(GorderHandle *h, GorderResults *r);
 
 /* Blocks; copies accumulators into the caller's arrays (replaces ParallelTrajData::reduce for the
- * single-GPU case). May be called more than once. */
+ * single-GPU case). May be called more than once.  It does NOT reduce across GPUs: with frames sharded over several
+ * handles, merge them first (gorder_gpu_reduce / gorder_gpu_reduce_comm below), then call finish on the root. */
 int gorder_gpu_finish(GorderHandle *h, GorderResults *r);
+
+/* ---- multi-GPU merge (replaces ParallelTrajData::reduce over the per-thread clones, topology/mod.rs:256-272, and the Add
+ * chain bond.rs:449-465, order.rs:160-176, timewise.rs:34-51, ordermap.rs:116-138, normal.rs:234-256) ------
+ * The analysed frames are sharded over GPUs in CONTIGUOUS ranges (range starts on multiples of the leaflet-assignment
+ * period), one handle per GPU, all created from the same setup.  The merge leaves on the root handle
+ *   - the SUM of the accumulator blocks (integer: exact, order-free),
+ *   - the per-frame rows, collected leaflet tables and normals of all shards in frame order (shards ordered by the
+ *     frame_index of their first frame),
+ * so that gorder_gpu_finish(root) returns what a single handle fed with all frames would.  The first error of any shard (in
+ * shard order) is returned, as the first Err aborts the reference's map-reduce.  The merge ends the analysis: do not submit
+ * further frames to the root.
+ *
+ * One process drives all devices: one kernel on the root device reads the peers' blocks through NVLink peer access. */
+int gorder_gpu_reduce(GorderHandle **handles, int32_t n, int32_t root);
+
+/* One process per GPU (torchrun, MPI): NCCL, loaded at run time (libnccl.so.2; GORDER_NCCL_LIB overrides the name), on a
+ * communicator the library creates: rank 0 calls gorder_comm_unique_id, the host broadcasts the 128 bytes by any means,
+ * every rank calls gorder_comm_create.  gorder_gpu_reduce_comm is collective: ONE ncclReduce (int64 sum) of the block plus
+ * grouped send / recv of the per-frame data to the root. */
+#define GORDER_COMM_ID_BYTES 128
+typedef struct GorderComm GorderComm;
+int gorder_comm_unique_id(uint8_t *id /* [GORDER_COMM_ID_BYTES] */);
+int gorder_comm_create(const uint8_t *id, int32_t n_ranks, int32_t rank, int32_t device, GorderComm **out);
+int gorder_gpu_reduce_comm(GorderHandle *h, GorderComm *c, int32_t root);
+/* Frequency::Once (leaflets.rs:435-441, 1523-1577): the table assigned from analysed frame 0 on rank `root` reaches the
+ * other shards (collective; replaces the Arc<Mutex> shared by the reference's threads).  Single process: read the table from
+ * the owning handle's results and pass it to gorder_gpu_set_leaflets. */
+int gorder_comm_broadcast_leaflets(GorderHandle *h, GorderComm *c, int32_t root);
+void gorder_comm_destroy(GorderComm *c);
 
 /* Multi-GPU: the integer accumulators of this handle as ONE contiguous device block so that the
  * host can combine shards with a single NCCL sum-reduce. Layout: int64 words,

@@ -15,7 +15,7 @@ HEADER = os.path.join(ROOT, "include", "gorder_b200.h")
 
 
 def test_library_exports_every_declared_symbol():
-    decl = set(re.findall(r"\b(gorder_(?:gpu|xtc|results)_[a-z_]+)\s*\(", open(HEADER).read()))
+    decl = set(re.findall(r"\b(gorder_(?:gpu|xtc|results|comm)_[a-z_]+)\s*\(", open(HEADER).read()))
     assert decl == set(SYMBOLS), decl ^ set(SYMBOLS)
     L = lib()
     for s in SYMBOLS:
@@ -132,3 +132,21 @@ def test_create_rejects_classifiers_without_heads_or_methyls():
         with pytest.raises(abi.GorderError) as e:
             SystemTopology(abi.EngineSetup(moltypes=[mt], **base, **kw))
         assert e.value.code == abi.ERR_INVALID_ARGUMENT, kw
+
+
+def test_multi_gpu_entry_points_fail_cleanly_without_devices():
+    """gorder_gpu_reduce / gorder_comm_* validate their arguments before touching a device or NCCL."""
+    import ctypes as C
+    from gorder_b200 import abi
+    L = lib()
+    assert L.gorder_gpu_reduce(None, 2, 0) == abi.ERR_INVALID_ARGUMENT
+    arr = (C.c_void_p * 2)(None, None)
+    assert L.gorder_gpu_reduce(arr, 2, 0) == abi.ERR_INVALID_ARGUMENT
+    assert L.gorder_gpu_reduce(arr, 2, 5) == abi.ERR_INVALID_ARGUMENT
+    assert L.gorder_comm_unique_id(None) == abi.ERR_INVALID_ARGUMENT
+    out = C.c_void_p()
+    assert L.gorder_comm_create(None, 2, 0, 0, C.byref(out)) == abi.ERR_INVALID_ARGUMENT
+    buf = C.create_string_buffer(128)
+    assert L.gorder_comm_create(buf, 2, 3, 0, C.byref(out)) == abi.ERR_INVALID_ARGUMENT
+    assert L.gorder_gpu_reduce_comm(None, None, 0) == abi.ERR_INVALID_ARGUMENT
+    L.gorder_comm_destroy(None)
