@@ -90,22 +90,25 @@ class ClockSampler(threading.Thread):
 
 
 WORKLOADS = {
-    # name: (description, default lipids, default frames per step)
-    "cg": ("S-CG: CGOrder Martini bilayer, Global leaflets every frame (BASELINE configs[1])", N_LIPIDS, 256),
-    "aa": ("S-AA-small: AAOrder POPC-like, 64 C-H bond types, static z (BASELINE configs[0] shape)", 256, 2048),
-    "ua": ("S-UA: UAOrder Berger-like, 64 virtual C-H, error blocks (BASELINE configs[2])", 256, 2048),
-    "aa_maps": ("S-AA-large: AAOrder 4096 lipids, Global leaflets, XY order maps 0.1 nm, cylinder r=8 nm (BASELINE configs[3])", 4096, 128),
-    "cg_dyn": ("S-DYN: CGOrder flat bilayer, dynamic PCA normals r=2 nm, Global leaflets (BASELINE configs[4] kernel mix)", 100000, 8),
+    # name: (description, default lipids, frames of the resident window = frames per launch, windows per step)
+    "cg": ("S-CG: CGOrder Martini bilayer, Global leaflets every frame (BASELINE configs[1]); 20 steps of 5120 frames = the 100k-frame trajectory", N_LIPIDS, 256, 20),
+    "aa": ("S-AA-small: AAOrder POPC-like, 64 C-H bond types, static z (BASELINE configs[0] shape)", 256, 2048, 4),
+    "ua": ("S-UA: UAOrder Berger-like, 64 virtual C-H, error blocks (BASELINE configs[2])", 256, 2048, 4),
+    "aa_maps": ("S-AA-large: AAOrder 4096 lipids, Global leaflets, XY order maps 0.1 nm, cylinder r=8 nm (BASELINE configs[3])", 4096, 128, 4),
+    "cg_dyn": ("S-DYN: CGOrder flat bilayer, dynamic PCA normals r=2 nm, Global leaflets (BASELINE configs[4] kernel mix)", 100000, 8, 4),
+    "ves": ("S-VES: CGOrder Martini vesicle (100 000 lipids, outer radius 51 nm, box 114 nm), dynamic PCA normals r=2 nm, "
+            "spherical-clustering leaflets assigned once (BASELINE configs[4])", 100000, 16, 8),
 }
 
 
 def make_system(args):
     from gorder_b200 import abi, synthetic
     w, n, F = args.workload, args.lipids, args.frames
+    tw = args.scaling == "strong"   # per-frame rows (error estimation): the merge of a sharded trajectory then gathers 48 B x slots per frame
     if w == "cg":
-        return synthetic.s_cg(n, leaflet_mode=abi.LEAFLET_GLOBAL, max_batch_frames=F)
+        return synthetic.s_cg(n, leaflet_mode=abi.LEAFLET_GLOBAL, max_batch_frames=F, timewise=tw)
     if w == "aa":
-        return synthetic.s_aa(n, n_water=30000 * n // 256, max_batch_frames=F)
+        return synthetic.s_aa(n, n_water=30000 * n // 256, max_batch_frames=F, timewise=tw)
     if w == "ua":
         return synthetic.s_ua(n, timewise=True, max_batch_frames=F)
     if w == "aa_maps":
@@ -115,6 +118,8 @@ def make_system(args):
         s.setup.map_span_x = (0.0, float(s.box[0]))
         s.setup.map_span_y = (0.0, float(s.box[1]))
         return s
+    if w == "ves":
+        return synthetic.s_ves(n, max_batch_frames=F, timewise=tw)
     if w == "cg_dyn":
         return synthetic.s_cg(n, leaflet_mode=abi.LEAFLET_GLOBAL, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0, max_batch_frames=F)
     raise SystemExit(f"unknown workload {w}")
@@ -123,21 +128,21 @@ def make_system(args):
 def config(args, s, extra=None):
     st = s.setup
     c = {"workload": WORKLOADS[args.workload][0], "lipids": args.lipids, "atoms_per_frame": s.n_atoms,
-         "order_slots": st.n_slots, "samples_per_frame": st.samples_per_frame(), "frames_per_step": args.frames,
-         "leaflets": {0: "none", 1: "Global, every frame"}.get(st.leaflet_mode, str(st.leaflet_mode)),
+         "order_slots": st.n_slots, "samples_per_frame": st.samples_per_frame(), "frames_per_step": args.frames * args.windows,
+         "leaflets": {0: "none", 1: "Global, every frame", 5: "spherical clustering, once"}.get(st.leaflet_mode, str(st.leaflet_mode)),
          "normal": {0: "static z", 1: "dynamic PCA", 2: "manual"}[st.normal_mode], "pbc": bool(st.handle_pbc),
-         "l2_policy": "inputs larger than L2 (one step streams frames_per_step frames; 126 MB L2)", "parallelism": f"frame-sharded x{args.gpus}"}
+         "l2_policy": "inputs larger than L2 (a launch streams the resident window, 3.1 GB for S-CG; 126 MB L2)", "parallelism": f"frame-sharded x{args.gpus}"}
     if extra:
         c.update(extra)
     return c
 
 
-def hot_kernel_name(st, lipids):
+def hot_kernel_name(st):
     """Name of the accumulation kernel gorder_gpu_profile brackets for this configuration (gorder_capi.cu dispatch)."""
+    plain = st.handle_pbc and st.normal_mode == 0 and not st.map_enabled and st.geom_kind == 0 and not os.environ.get("GORDER_NO_FAST")
     if st.kind == 2:
-        return "ua_order_kernel"
-    plain = st.handle_pbc and st.normal_mode == 0 and not st.map_enabled and st.geom_kind == 0
-    return "bond_fast_kernel" if plain and lipids >= 1024 and not os.environ.get("GORDER_NO_FAST") else "bond_order_kernel"
+        return "ua_fast_kernel" if plain and not os.environ.get("GORDER_UA_EXACT") else "ua_order_kernel"
+    return "bond_fast_kernel" if plain else "bond_order_kernel"
 
 
 def cpu_oracle_rate(s, xyz, box, threads, min_seconds):
@@ -182,11 +187,25 @@ def run_reference(args):
     sample = f"{nf} frames of the {args.workload} workload per step, oracle port (oracle/gorder_oracle.c) with {threads} OpenMP threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config(args, s, {"frames_per_step": nf}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def my_share(args, world, rank):
+    """Frames of one step this rank analyses, as batches of <= F frames of the resident window.
+    strong scaling: a step is `windows x F` frames of ONE trajectory, split over the ranks in contiguous ranges
+    (gorder_b200.sharding.frame_ranges, the reference's thread model with contiguous instead of interleaved ownership);
+    weak scaling: every rank analyses `windows x F` frames of its own."""
+    from gorder_b200 import sharding
+    F, total = args.frames, args.frames * args.windows
+    n = total
+    if args.scaling == "strong":
+        lo, hi = sharding.frame_ranges(total, world, 1)[rank]
+        n = hi - lo
+    return [F] * (n // F) + ([n % F] if n % F else []), n, total
 
 
 def run_ours(args):
@@ -197,6 +216,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from gorder_b200 import SystemTopology
+    from gorder_b200.topology import Comm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -204,16 +224,24 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: gorder_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the library's own communicator (gorder_comm_*): rank 0 makes the id, torch.distributed only carries its 128 bytes
+        uid = torch.zeros(Comm.ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        comm = Comm(bytes(uid.cpu().numpy().tobytes()), world, rank, local)
     s = make_system(args)
     s.setup.device = local
     F, K, W = args.frames, args.steps, args.warmup
     spf = s.setup.samples_per_frame()
+    batches, n_mine, step_frames = my_share(args, world, rank)
+    job_frames_per_step = step_frames if args.scaling == "strong" else step_frames * world
 
-    # ---- inputs: every rank generates its own frames (weak scaling) ---------------------------------
-    first = rank * F
-    xyz, box, _ = s.frames(first, F)
+    # ---- inputs: a window of F frames resident in HBM, re-used with fresh frame indices ------------
+    xyz, box, _ = s.frames(rank * F if args.scaling == "weak" else 0, F)
     eng = SystemTopology(s.setup)
     planes = eng.to_native(xyz)
     d_planes = torch.from_numpy(planes).cuda()
@@ -222,43 +250,51 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
     frame_bytes = eng.frame_floats * 4
     needed_atoms = int((eng.native_layout()[1] >= 0).sum())
+    n_steps_total = W + K + 6
+    cursor = [rank * n_steps_total * max(n_mine, 1)]   # contiguous, strictly increasing frame range per rank
 
-    def step(k):
-        base = (k * world + rank) * F   # disjoint, strictly increasing frame ranges per rank
-        eng.analyze_frames_device(d_planes.data_ptr(), d_box.data_ptr(), F, frame_index=base + np.arange(F, dtype=np.int64), native=True)
+    def step():
+        for b in batches:
+            eng.analyze_frames_device(d_planes.data_ptr(), d_box.data_ptr(), b, frame_index=cursor[0] + np.arange(b, dtype=np.int64), native=True)
+            cursor[0] += b
 
-    eng.reserve_frames((W + K + 6) * F)
+    # rank 0 owns the first frames: with the whole trajectory announced to it, the merge lands the other shards' per-frame rows
+    # directly behind its own (gorder_gpu_reserve_frames; no allocation inside the timed merge)
+    eng.reserve_frames(n_steps_total * (step_frames if (rank == 0 and args.scaling == "strong") else n_mine) + 8)
     sampler = ClockSampler(local)
     sampler.start()
-    for k in range(W):
-        step(k)
+    once = s.setup.leaflet_mode != 0 and s.setup.leaflet_freq_kind == 1
+
+    def first_step(engine, fn):
+        """Frequency::Once: the table of analysed frame 0 (rank 0's first frame) reaches every shard before it accumulates."""
+        if not once:
+            return fn()
+        r = fn() if rank == 0 else None
+        if world > 1:
+            engine.broadcast_leaflets(comm, 0)
+        return r if rank == 0 else fn()
+
+    first_step(eng, step)
+    for _ in range(W - 1):
+        step()
     eng.sync()
-    block_ptr, n_words = eng.accumulator_block()
-
-    class _Block:   # zero-copy view of the engine's contiguous int64 accumulator block (sums, counts, maps)
-        __cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (block_ptr, False), "version": 2}
-
-    block = torch.as_tensor(_Block(), device=torch.device("cuda", local))
-    assert block.data_ptr() == block_ptr and block.dtype == torch.int64
     if world > 1:
-        # warm the communicator with the same collective the job ends with (channel setup is not part of a step)
-        warm = torch.zeros(n_words, dtype=torch.int64, device="cuda")
-        dist.reduce(warm, dst=0, op=dist.ReduceOp.SUM)
         dist.barrier()
     torch.cuda.synchronize()
     l0 = eng.stats()["kernel_launches"]
     eng.profile(True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0, ev1, ev_r = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_win0 = time.perf_counter()
-    with torch.cuda.stream(stream):   # the engine's main stream is torch's current stream: NCCL orders itself after it
+    with torch.cuda.stream(stream):   # the engine's main stream is torch's current stream
         if world > 1:   # align the DEVICE timelines of the ranks (the host barrier above leaves ~1 ms of launch skew)
             dist.all_reduce(torch.zeros(1, device="cuda"))
         ev0.record()
-        for k in range(W, W + K):
-            step(k)
+        for _ in range(K):
+            step()
         eng.fence()   # the tail (repair + fold) of the last batch runs on a helper stream: the main stream waits for it
-        if world > 1:   # the single collective of the job: sum the integer accumulators in place on rank 0 (no host sync)
-            dist.reduce(block, dst=0, op=dist.ReduceOp.SUM)
+        ev_r.record()
+        if world > 1:   # the single merge of the job, behind the C ABI: ncclReduce of the block + gather of the per-frame rows
+            eng.reduce_comm(comm, 0)
         ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -266,117 +302,129 @@ def run_ours(args):
     t_win1 = time.perf_counter()
     sampler.stop_flag = True
     ms = ev0.elapsed_time(ev1)
+    reduce_ms = ev_r.elapsed_time(ev1)
     hot_ms, hot_n = eng.profile_read()
     eng.profile(False)
     launches = eng.stats()["kernel_launches"] - l0
     spec_stats = eng.speculation_stats()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, reduce_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = K * F * spf * world / (ms * 1e-3)
-    res = eng.finish()
-    total_samples = int(res.count[:, 0].sum())
-    # the same kernel timed WITHOUT the overlapped centre kernels of the next batch (explains the in-step number)
-    iso_ms = iso_n = None
-    if rank == 0 and s.setup.leaflet_mode == 1:
-        os.environ["GORDER_NO_OVERLAP"] = "1"
-        eng.profile(True)
-        for k in range(W + K, W + K + 5):
-            step(k)
-        eng.sync()
-        iso_ms, iso_n = eng.profile_read()
-        eng.profile(False)
-        del os.environ["GORDER_NO_OVERLAP"]
+    ms, reduce_ms = float(t[0].item()), float(t[1].item())
+    value = K * job_frames_per_step * spf / (ms * 1e-3)
+    total_samples = rows_merged = None
+    if rank == 0:
+        res = eng.finish()
+        total_samples = int(res.count[:, 0].sum())
+        rows_merged = int(res.n_frames)
 
     # ---- end to end: pinned host AoS frames through gorder_gpu_submit, D2H of the sums every step -------
     eng2 = SystemTopology(s.setup)
-    eng2.reserve_frames((K + 4) * F)
+    Ke = max(1, min(K, args.e2e_steps))
+    eng2.reserve_frames((Ke + 2) * n_mine + 8)
     pin = torch.from_numpy(xyz).pin_memory()
     pin_box = torch.from_numpy(box).pin_memory()
     hx, hb = pin.numpy(), pin_box.numpy()
+    cur2 = [rank * (Ke + 2) * max(n_mine, 1)]
 
-    def e2e_step(k):
-        base = (k * world + rank) * F
-        eng2.analyze_frames(hx, hb, base + np.arange(F, dtype=np.int64))
-        return eng2.finish()
+    def e2e_step():
+        for b in batches:
+            eng2.analyze_frames(hx[:b], hb[:b], cur2[0] + np.arange(b, dtype=np.int64))
+            cur2[0] += b
+        return eng2.finish(totals_only=True)   # the step's result: running sums and counts (maps / per-frame rows stay on the device)
 
-    for k in range(min(W, 3)):
-        e2e_step(k)
+    r2 = first_step(eng2, e2e_step)   # warm-up: staging buffers, page locking
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for k in range(3, 3 + K):
-        r2 = e2e_step(k)
+    for _ in range(Ke):
+        r2 = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = K * F * spf * world / float(t.item())
-    h2d = int(xyz.nbytes + box.nbytes)
+    e2e_value = Ke * job_frames_per_step * spf / float(t.item())
+    h2d = int(sum(batches) * (xyz[0].nbytes + box[0].nbytes))
     d2h = int(r2.sum.nbytes + r2.count.nbytes)
     eng2.close()
 
-    # ---- end to end from a trajectory FILE: host XTC decode (all host threads) -> pinned plane batches -> engine -----
+    # ---- end to end from a trajectory FILE on EVERY rank: host XTC decode / device XTC decode -> engine ------------
     e2e_xtc = None
-    if rank == 0 and args.xtc_frames > 0:
+    if args.xtc_frames > 0:
+        xt = np.zeros(4, dtype=np.float64)   # [host-decode wall s, device-decode wall s, decode thread-seconds, ok]
+        info = {}
         try:   # an optional leg: its failure must not take the headline line with it
             import tempfile
             from gorder_b200.xtc import XtcFile, write_xtc
             nx = min(args.xtc_frames, F)
+            threads_x = max(1, (os.cpu_count() or 1) // world)
             with tempfile.TemporaryDirectory() as td:
-                path = os.path.join(td, "bench.xtc")
+                path = os.path.join(td, f"bench{rank}.xtc")
                 write_xtc(path, xyz[:nx], box[:nx])
                 fbytes = os.path.getsize(path)
                 with XtcFile(path) as xf:
-                    threads_x = os.cpu_count() or 1
                     eng4 = SystemTopology(s.setup)
                     eng4.reserve_frames(2 * nx + 8)
                     eng4.run_xtc(xf, n_threads=threads_x, batch_frames=args.xtc_batch)   # warm-up: page mappings of the file, pinned buffers
                     eng4.sync()
+                    if world > 1:
+                        dist.barrier()
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
                     dec_s = eng4.run_xtc(xf, n_threads=threads_x, batch_frames=args.xtc_batch, frame_index0=nx)
-                    rx = eng4.finish()
-                    dt_x = time.perf_counter() - t0
+                    eng4.finish(totals_only=True)
+                    xt[0], xt[2] = time.perf_counter() - t0, dec_s
                     eng4.close()
                     # the same file with the decode on the device: host threads only copy compressed bytes
                     eng5 = SystemTopology(s.setup)
-                    eng5.reserve_frames(4 * nx + 8)
-                    eng5.run_xtc_device(xf, n_threads=threads_x, batch_frames=args.xtc_dev_batch)   # warm-up: buffers, page mappings of the file
-                    eng5.sync()
-                    torch.cuda.synchronize()
                     reps = 3
+                    eng5.reserve_frames((reps + 1) * nx + 8)
+                    eng5.run_xtc_device(xf, n_threads=threads_x, batch_frames=args.xtc_dev_batch)   # warm-up
+                    eng5.sync()
+                    if world > 1:
+                        dist.barrier()
+                    torch.cuda.synchronize()
                     t0 = time.perf_counter()
                     for r_ in range(reps):
                         moved = eng5.run_xtc_device(xf, n_threads=threads_x, batch_frames=args.xtc_dev_batch, frame_index0=(r_ + 1) * nx)
-                    rd = eng5.finish()
-                    dt_d = (time.perf_counter() - t0) / reps
+                    eng5.finish(totals_only=True)
+                    xt[1] = (time.perf_counter() - t0) / reps
                     eng5.close()
-            e2e_xtc = {"value": nx * spf / dt_x, "unit": UNIT, "frames": nx, "file_bytes": fbytes, "bytes_per_atom": fbytes / nx / s.n_atoms,
-                       "decode_threads": threads_x, "decode_thread_seconds": dec_s, "wall_seconds": dt_x,
-                       "decode_atoms_per_s_per_thread": nx * s.n_atoms / max(dec_s, 1e-9),
-                       "entry": "gorder_gpu_run_xtc (host XTC decode + H2D + analysis + D2H of the sums; rank 0)",
-                       "samples_accumulated_incl_warmup": int(rx.count[:, 0].sum()),
-                       "device_decode": {"value": nx * spf / dt_d, "unit": UNIT, "wall_seconds": dt_d, "batch_frames": args.xtc_dev_batch, "h2d_bytes": moved, "h2d_bytes_per_atom": moved / nx / s.n_atoms,
-                                         "entry": "gorder_gpu_run_xtc_device (host copies + bookmarks the compressed frames; xtc_decode_kernel unpacks them on the GPU)"}}
+            xt[3] = 1.0
+            info = {"frames_per_rank": nx, "file_bytes": fbytes, "bytes_per_atom": fbytes / nx / s.n_atoms, "decode_threads_per_rank": threads_x,
+                    "h2d_bytes": moved, "h2d_bytes_per_atom": moved / nx / s.n_atoms}
         except Exception as exc:   # noqa: BLE001
-            e2e_xtc = {"error": f"{type(exc).__name__}: {exc}"}
+            info = {"error": f"{type(exc).__name__}: {exc}"}
+        tx = torch.from_numpy(xt).cuda()
+        ok = torch.tensor([xt[3]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 1.0 and rank == 0:
+            nx = info["frames_per_rank"]
+            e2e_xtc = {"value": world * nx * spf / float(tx[0]), "unit": UNIT, "ranks": world, **info, "wall_seconds": float(tx[0]),
+                       "decode_atoms_per_s_per_thread": nx * s.n_atoms / max(float(tx[2]), 1e-9),
+                       "entry": "gorder_gpu_run_xtc on every rank (host XTC decode + H2D + analysis + D2H of the sums), whole-job rate, max time over ranks",
+                       "device_decode": {"value": world * nx * spf / float(tx[1]), "unit": UNIT, "wall_seconds": float(tx[1]), "batch_frames": args.xtc_dev_batch,
+                                         "entry": "gorder_gpu_run_xtc_device on every rank (host copies + bookmarks the compressed frames; xtc_decode_kernel unpacks them on the GPU)"}}
+        elif rank == 0:
+            e2e_xtc = info if "error" in info else {"error": "the XTC leg failed on another rank"}
 
     out = None
     if rank == 0:
         peak, peak_src = peaks()
         # algorithmic bytes: every coordinate the path needs, once (12 B x used atoms; S-CG: all 1 000 008 beads)
-        launch_bytes = K * F * needed_atoms * BYTES_PER_ATOM / max(hot_n, 1)   # a step may be several launches
+        launch_bytes = K * n_mine * needed_atoms * BYTES_PER_ATOM / max(hot_n, 1)   # a step is several launches
         achieved = launch_bytes / (hot_ms / max(hot_n, 1) * 1e-3) / 1e9 if hot_n else None
-        traffic = None
+        traffic = traffic_src = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
                 tr = json.load(f)
             if args.workload == "cg" and args.lipids == N_LIPIDS:   # the capture is of this workload only
-                traffic = tr["dram_bytes_per_frame"] * K * F / max(hot_n, 1)
+                traffic = tr["dram_bytes_per_frame"] * K * n_mine / max(hot_n, 1)
+                traffic_src = "replayed, not measured in this run: dram__bytes (read + write) per frame of ONE ncu --set full capture (profiles/roofline_traffic.json) x frames per launch"
         except Exception:
             pass
         # ---- CPU baseline (oracle port) on a bounded sample + parity of the GPU sums against it ------
@@ -390,27 +438,34 @@ def run_ours(args):
         parity = {"counts_equal": bool(np.array_equal(g.count, ref.count)),
                   "max_abs_dS": float(np.abs(g.sum / np.maximum(g.count, 1).astype(np.float64) - ref.sum / np.maximum(ref.count, 1).astype(np.float64)).max() / 1e6),
                   "frames": nb}
+        tw_bytes = rows_merged * s.setup.n_slots * 3 * 16 if s.setup.timewise else 0
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config(args, s, {"resident_layout": "engine planes (gorder_gpu_native_layout)", "native_frame_bytes": frame_bytes}),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config(args, s, {"frames_per_step": job_frames_per_step, "frames_per_step_per_gpu": n_mine, "resident_window_frames": F,
+                                       "trajectory_frames_timed": K * job_frames_per_step,
+                                       "per_frame_rows": bool(s.setup.timewise),
+                                       "resident_layout": "engine planes (gorder_gpu_native_layout)", "native_frame_bytes": frame_bytes}),
             "clocks": sampler.summary(t_win0, t_win1),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "entry": "gorder_gpu_submit (pinned host [atom][xyz] frames) + gorder_gpu_finish", "timer": "host wall clock between device syncs"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "entry": "gorder_gpu_submit (pinned host [atom][xyz] frames) + gorder_gpu_finish (sums and counts)", "timer": "host wall clock between device syncs, max over ranks"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "kernel": hot_kernel_name(s.setup, args.lipids), "launches_timed": hot_n, "avg_launch_ms": hot_ms / max(hot_n, 1),
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": hot_kernel_name(s.setup), "launches_timed": hot_n, "avg_launch_ms": hot_ms / max(hot_n, 1),
                          "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
-                         "step_share": (hot_ms / ms) if ms else None,
-                         "note": ("in-step duration; speculative Global leaflets: no centre pre-pass, the kernel runs alone" if spec_stats["enabled"] else
-                                  "in-step duration; with Global leaflets the centre kernels of the NEXT batch run concurrently on a second stream"),
-                         "isolated": ({"avg_launch_ms": iso_ms / iso_n, "achieved": launch_bytes / (iso_ms / iso_n * 1e-3) / 1e9,
-                                       "frac": launch_bytes / (iso_ms / iso_n * 1e-3) / 1e9 / peak} if iso_n else None)},
+                         "step_share": (hot_ms / (ms - reduce_ms)) if ms else None,
+                         "note": ("in-step duration, CUDA events around every launch of the kernel on the engine's stream (gorder_gpu_profile); "
+                                  + ("speculative Global leaflets: no centre pre-pass" if spec_stats["enabled"] else "rank 0"))},
+            "reduce": ({"ms": reduce_ms, "entry": "gorder_gpu_reduce_comm: one ncclReduce (int64 sum) of the accumulator block + grouped send / recv of the per-frame rows to rank 0",
+                        "per_frame_row_bytes_gathered": tw_bytes, "rows_on_root": rows_merged} if world > 1 else None),
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{cpu_frames} frames of the same workload ({cpu_t:.1f} s), oracle port with {threads} OpenMP threads"},
+                             "sample": f"{cpu_frames} frames of the same workload ({cpu_t:.1f} s), oracle port (oracle/gorder_oracle.c, -O3 -march=native) with {threads} OpenMP threads; "
+                                       "the reference's published single-thread runs correspond to ~60-80 ns per sample on an i7-11700 (BASELINE.md), this port needs more (libm fmodf / acosf / cosf)"},
             "e2e_xtc": e2e_xtc, "parity": parity, "total_samples_accumulated": total_samples, "speculative_leaflets": spec_stats,
         }
     eng.close()
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -425,7 +480,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cg", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=0, help="frames per step (batch); 0 = workload default")
+    ap.add_argument("--frames", type=int, default=0, help="frames of the resident window = frames per launch; 0 = workload default")
+    ap.add_argument("--windows", type=int, default=0, help="passes over the window per step (a step = windows x frames trajectory frames); 0 = workload default")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: a step's frames belong to ONE trajectory and are split over the GPUs; weak: every GPU analyses a step's worth of its own")
+    ap.add_argument("--e2e-steps", type=int, default=2, help="timed steps of the end-to-end leg (each moves frames_per_step x 12 B x atoms over PCIe)")
     ap.add_argument("--lipids", type=int, default=0, help="0 = workload default")
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU arms; 0 = one per host thread")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -436,6 +495,7 @@ def main():
     args.warmup = max(args.warmup, 0)
     args.lipids = args.lipids or WORKLOADS[args.workload][1]
     args.frames = args.frames or WORKLOADS[args.workload][2]
+    args.windows = args.windows or WORKLOADS[args.workload][3]
     args.ref_frames = args.ref_frames or max(8, os.cpu_count() or 8)
     if args.impl == "reference":
         run_reference(args)

@@ -420,8 +420,9 @@ class RawResults:
     normals: Optional[np.ndarray] = None    # [n_frames][n_molecules_total][3]
 
 
-def fetch_results(lib, handle, prefix: str, setup: EngineSetup) -> RawResults:
-    """Allocate arrays from ``*_result_sizes`` and call ``*_finish`` (shared by engine and oracle)."""
+def fetch_results(lib, handle, prefix: str, setup: EngineSetup, totals_only: bool = False) -> RawResults:
+    """Allocate arrays from ``*_result_sizes`` and call ``*_finish`` (shared by engine and oracle).  ``totals_only``: fetch the
+    running sums / counts only (the arrays of GorderResults left NULL are skipped by the library)."""
     r = CGorderResults()
     rc = getattr(lib, prefix + "_result_sizes")(handle, C.byref(r))
     if rc != OK:
@@ -433,6 +434,11 @@ def fetch_results(lib, handle, prefix: str, setup: EngineSetup) -> RawResults:
     r.count = out.count.ctypes.data_as(_u64p)
     out.tw_frame_index = np.zeros(nf, np.int64)
     r.tw_frame_index = out.tw_frame_index.ctypes.data_as(_i64p)
+    if totals_only:
+        rc = getattr(lib, prefix + "_finish")(handle, C.byref(r))
+        if rc != OK:
+            raise GorderError(rc)
+        return out
     if setup.timewise:
         out.tw_sum = np.zeros((nf, ns, 3), np.int64)
         out.tw_count = np.zeros((nf, ns, 3), np.uint64)

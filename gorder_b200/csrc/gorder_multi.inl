@@ -18,6 +18,8 @@
 //                            (dlopen of libnccl.so.2), so the library has no link-time dependency on it.
 #include <dlfcn.h>
 
+#include <chrono>
+
 namespace {
 
 // ---- block sum over peer memory -------------------------------------------------------------------------------------
@@ -93,13 +95,20 @@ struct MergedArrays {
     unsigned long long *bcnt = nullptr;
     unsigned char *leaf = nullptr;
     float *normals = nullptr;
+    bool rows_in_place = false;   // the root's own rows already sit at the front of arrays large enough for all shards
 };
 
-int alloc_merged(GorderHandle *h, const MergePlan &p, MergedArrays *a) {
+// `root`: index of the root's shard.  When the root owns the first frames and gorder_gpu_reserve_frames announced the whole
+// trajectory to it, the peers' rows land directly behind its own: no allocation, no copy of the root's rows.
+int alloc_merged(GorderHandle *h, const MergePlan &p, int root, MergedArrays *a) {
     const size_t row = (size_t)h->n_slots * 3;
     if (h->s.timewise && p.total_frames > 0) {
-        CK(cudaMalloc((void **)&a->bsum, (size_t)p.total_frames * row * sizeof(long long)));
-        CK(cudaMalloc((void **)&a->bcnt, (size_t)p.total_frames * row * sizeof(unsigned long long)));
+        if (p.row_off[(size_t)root] == 0 && h->d_bsum && h->tw_cap >= p.total_frames) {
+            a->bsum = h->d_bsum; a->bcnt = h->d_bcnt; a->rows_in_place = true;
+        } else {
+            CK(cudaMalloc((void **)&a->bsum, (size_t)p.total_frames * row * sizeof(long long)));
+            CK(cudaMalloc((void **)&a->bcnt, (size_t)p.total_frames * row * sizeof(unsigned long long)));
+        }
     }
     if (h->s.collect_leaflets && p.total_leaf > 0) CK(cudaMalloc((void **)&a->leaf, (size_t)p.total_leaf * h->n_molpad));
     if (h->s.collect_normals && h->s.normal_mode == GORDER_NORMAL_DYNAMIC && p.total_frames > 0)
@@ -109,7 +118,7 @@ int alloc_merged(GorderHandle *h, const MergePlan &p, MergedArrays *a) {
 
 // the root handle takes the merged arrays and the merged frame lists over
 void adopt_merged(GorderHandle *h, const std::vector<ShardMeta> &m, const MergePlan &p, const MergedArrays &a) {
-    if (a.bsum) { cudaFree(h->d_bsum); cudaFree(h->d_bcnt); h->d_bsum = a.bsum; h->d_bcnt = a.bcnt; h->tw_cap = p.total_frames; }
+    if (a.bsum && !a.rows_in_place) { cudaFree(h->d_bsum); cudaFree(h->d_bcnt); h->d_bsum = a.bsum; h->d_bcnt = a.bcnt; h->tw_cap = p.total_frames; }
     if (a.leaf) { cudaFree(h->d_leaf_collect); h->d_leaf_collect = a.leaf; h->leaf_collect_cap = p.total_leaf; }
     if (a.normals) { cudaFree(h->d_normals_collect); h->d_normals_collect = a.normals; h->normals_collect_cap = p.total_frames; }
     h->frame_index_done.clear(); h->leaf_frame_index.clear();
@@ -186,7 +195,23 @@ Nccl *nccl() {
 struct GorderComm {
     void *comm = nullptr;
     int n_ranks = 0, rank = 0, device = 0;
+    long long *d_scratch = nullptr;   // headers and frame lists of a merge (grown on demand)
+    size_t scratch_words = 0;
 };
+
+namespace {
+int comm_scratch(GorderHandle *h, GorderComm *c, size_t words, long long **out) {
+    if (words > c->scratch_words) {
+        if (c->d_scratch) cudaFree(c->d_scratch);
+        c->d_scratch = nullptr; c->scratch_words = 0;
+        const size_t cap = std::max<size_t>(words, 1 << 20);
+        CK(cudaMalloc((void **)&c->d_scratch, cap * sizeof(long long)));
+        c->scratch_words = cap;
+    }
+    *out = c->d_scratch;
+    return GORDER_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -227,12 +252,12 @@ int gorder_gpu_reduce(GorderHandle **hs, int32_t n, int32_t root) {
     }
     const MergePlan plan = make_plan(meta);
     MergedArrays merged;
-    if (int rc = alloc_merged(h, plan, &merged)) return rc;
+    if (int rc = alloc_merged(h, plan, root, &merged)) return rc;
     const size_t row = (size_t)h->n_slots * 3;
     for (int i = 0; i < n; i++) {   // gathers: peer-to-peer copies into the merged arrays (the root's own rows included)
         GorderHandle *s = hs[i];
         const ShardMeta &m = meta[(size_t)i];
-        if (merged.bsum && m.n_frames > 0) {
+        if (merged.bsum && m.n_frames > 0 && !(i == root && merged.rows_in_place)) {
             CK(cudaMemcpyPeerAsync(merged.bsum + (size_t)plan.row_off[(size_t)i] * row, h->device, s->d_bsum, s->device, (size_t)m.n_frames * row * sizeof(long long), h->stream));
             CK(cudaMemcpyPeerAsync(merged.bcnt + (size_t)plan.row_off[(size_t)i] * row, h->device, s->d_bcnt, s->device, (size_t)m.n_frames * row * sizeof(long long), h->stream));
         }
@@ -273,6 +298,31 @@ int gorder_comm_create(const uint8_t *id, int32_t n_ranks, int32_t rank, int32_t
     GorderComm *c = new GorderComm();
     c->n_ranks = n_ranks; c->rank = rank; c->device = device;
     if (N->CommInitRank(&c->comm, n_ranks, uid, rank) != 0) { delete c; return GORDER_ERR_NCCL; }
+    {   // NCCL connects its channels lazily, at the first use of every collective / peer pair (hundreds of milliseconds): do
+        // it here, once, with the operations gorder_gpu_reduce_comm uses (all-gather, reduce, broadcast, send / recv between all pairs)
+        cudaStream_t st = nullptr;
+        long long *d = nullptr;
+        bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess && cudaMalloc((void **)&d, (size_t)(2 * n_ranks + 2) * sizeof(long long)) == cudaSuccess;
+        if (ok) {
+            cudaMemsetAsync(d, 0, (size_t)(2 * n_ranks + 2) * sizeof(long long), st);
+            ok = N->AllGather(d + n_ranks, d, 1, kNcclInt64, c->comm, st) == 0 && N->Reduce(d, d, 1, kNcclInt64, kNcclSum, 0, c->comm, st) == 0 &&
+                 N->Broadcast(d, d, 8, kNcclInt8, 0, c->comm, st) == 0;
+            if (ok && n_ranks > 1) {
+                ok = N->GroupStart() == 0;
+                for (int r = 0; ok && r < n_ranks; r++)
+                    if (r != rank) ok = N->Send(d + n_ranks, 1, kNcclInt64, r, c->comm, st) == 0 && N->Recv(d + n_ranks + 1 + r, 1, kNcclInt64, r, c->comm, st) == 0;
+                ok = N->GroupEnd() == 0 && ok;
+            }
+            ok = cudaStreamSynchronize(st) == cudaSuccess && ok;
+        }
+        if (d) cudaFree(d);
+        if (st) cudaStreamDestroy(st);
+        if (!ok) { N->CommDestroy(c->comm); delete c; cudaGetLastError(); return GORDER_ERR_NCCL; }
+        // headers and frame lists of a merge: allocated now -- with peer access enabled (NCCL), cudaMalloc / cudaFree have to update
+        // the peer mappings and take tens to hundreds of milliseconds, which must not happen inside the merge
+        if (cudaMalloc((void **)&c->d_scratch, ((size_t)1 << 20) * sizeof(long long)) == cudaSuccess) c->scratch_words = (size_t)1 << 20;
+        else cudaGetLastError();
+    }
     *out = c;
     return GORDER_OK;
 }
@@ -281,6 +331,7 @@ void gorder_comm_destroy(GorderComm *c) {
     if (!c) return;
     Nccl *N = nccl();
     if (N && c->comm) { cudaSetDevice(c->device); N->CommDestroy(c->comm); }
+    if (c->d_scratch) cudaFree(c->d_scratch);
     delete c;
 }
 
@@ -307,22 +358,27 @@ int gorder_gpu_reduce_comm(GorderHandle *h, GorderComm *c, int32_t root) {
     Nccl *N = nccl();
     if (!N) { h->set_error(GORDER_ERR_NCCL, "NCCL is not available"); return h->err_code; }
     cudaSetDevice(h->device);
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (h->sw.verbose) fprintf(stderr, "[gorder_gpu_reduce_comm rank %d] %-28s %8.3f ms\n", c->rank, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     const int own_rc = gorder_gpu_sync(h);   // do not return yet: the collective below must be entered by every rank
+    lap("own work finished");
     const int R = c->n_ranks, me = c->rank;
     const bool is_root = me == root;
     // ---- 1. header of every shard on every rank: frames, collected tables, error, shape ----
     constexpr int kHdr = 8;
     std::vector<long long> hdr_all((size_t)R * kHdr, 0);
     long long *d_hdr = nullptr;
-    cudaMalloc((void **)&d_hdr, (size_t)(R + 1) * kHdr * sizeof(long long));
+    if (int rc = comm_scratch(h, c, (size_t)(R + 1) * kHdr, &d_hdr)) return rc;
     const long long mine[kHdr] = {h->n_frames, h->n_leaf_collected, own_rc ? own_rc : h->err_code, h->err_detail, h->block_words, h->n_slots, h->n_molpad,
                                   (long long)h->s.timewise | ((long long)h->s.collect_leaflets << 1) | ((long long)h->s.collect_normals << 2)};
     cudaMemcpyAsync(d_hdr + (size_t)R * kHdr, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream);
     int nrc = N->AllGather(d_hdr + (size_t)R * kHdr, d_hdr, kHdr, kNcclInt64, c->comm, h->stream);
     cudaMemcpyAsync(hdr_all.data(), d_hdr, (size_t)R * kHdr * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
-    cudaFree(d_hdr);
     if (nrc != 0) { h->err_code = 0; h->set_error(GORDER_ERR_NCCL, std::string("ncclAllGather: ") + N->GetErrorString(nrc)); return h->err_code; }
+    lap("headers gathered");
     std::vector<ShardMeta> meta((size_t)R);
     for (int r = 0; r < R; r++) {
         const long long *q = hdr_all.data() + (size_t)r * kHdr;
@@ -339,7 +395,7 @@ int gorder_gpu_reduce_comm(GorderHandle *h, GorderComm *c, int32_t root) {
     for (int r = 0; r < R; r++) total_idx += meta[(size_t)r].n_frames + meta[(size_t)r].n_leaf;
     long long *d_idx = nullptr;
     const long long my_idx = h->n_frames + h->n_leaf_collected;
-    CK(cudaMalloc((void **)&d_idx, (size_t)std::max<long long>(1, is_root ? total_idx : my_idx) * sizeof(long long)));
+    if (int rc = comm_scratch(h, c, (size_t)std::max<long long>(1, is_root ? total_idx : my_idx), &d_idx)) return rc;
     std::vector<long long> own(h->frame_index_done);
     own.insert(own.end(), h->leaf_frame_index.begin(), h->leaf_frame_index.end());
     std::vector<long long> off_idx((size_t)R + 1, 0);
@@ -362,8 +418,9 @@ int gorder_gpu_reduce_comm(GorderHandle *h, GorderComm *c, int32_t root) {
             meta[(size_t)r].leaf_frame_index.assign(q + meta[(size_t)r].n_frames, q + meta[(size_t)r].n_frames + meta[(size_t)r].n_leaf);
         }
         plan = make_plan(meta);
-        if (int rc = alloc_merged(h, plan, &merged)) return rc;
+        if (int rc = alloc_merged(h, plan, me, &merged)) return rc;
     }
+    lap("frame lists on the root");
     // ---- 3. the single sum-reduce of the accumulator block + the gathers of per-frame data, one NCCL group ----
     const size_t row = (size_t)h->n_slots * 3;
     const bool tw = h->s.timewise != 0, lf = h->s.collect_leaflets != 0, nm = h->s.collect_normals && h->s.normal_mode == GORDER_NORMAL_DYNAMIC;
@@ -374,7 +431,7 @@ int gorder_gpu_reduce_comm(GorderHandle *h, GorderComm *c, int32_t root) {
             const ShardMeta &m = meta[(size_t)r];
             const size_t ro = (size_t)plan.row_off[(size_t)r], lo = (size_t)plan.leaf_off[(size_t)r];
             if (r == me) {
-                if (tw && m.n_frames) {
+                if (tw && m.n_frames && !merged.rows_in_place) {
                     CK(cudaMemcpyAsync(merged.bsum + ro * row, h->d_bsum, (size_t)m.n_frames * row * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
                     CK(cudaMemcpyAsync(merged.bcnt + ro * row, h->d_bcnt, (size_t)m.n_frames * row * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
                 }
@@ -399,8 +456,9 @@ int gorder_gpu_reduce_comm(GorderHandle *h, GorderComm *c, int32_t root) {
     }
     NK(N->GroupEnd());
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_idx);
+    lap("block reduced, rows gathered");
     if (is_root) adopt_merged(h, meta, plan, merged);
+    lap("done");
     return GORDER_OK;
 }
 

@@ -247,3 +247,109 @@ def s_ua(n_lipids: int = 256, **kw) -> SyntheticSystem:
     kw.setdefault("timewise", True)
     with_sat = kw.pop("with_ch1_sat", False)
     return make_bilayer(berger_like_popc(with_sat), n_lipids, abi.KIND_UA, area_per_lipid=0.64, box_z=8.0, **kw)
+
+
+# -- vesicle (BASELINE config 5, S-VES) ----------------------------------------------------------
+
+@dataclass
+class SyntheticVesicle:
+    """A generated vesicle: lipids of the outer / inner leaflet on two concentric spheres (Fibonacci lattice + jitter), every
+    lipid a chain of beads along its radial director (tails towards the mid-surface) with a tilt and thermal noise; the
+    vesicle is centred at a per-frame random point and every bead is wrapped into the cubic box, so the vesicle is cut by the
+    periodic boundary in most frames."""
+
+    template: LipidTemplate
+    n_lipids: int
+    box: np.ndarray
+    unit: np.ndarray           # [n_lipids][3] radial unit vector of every lipid
+    is_outer: np.ndarray       # [n_lipids] bool
+    r_outer: float
+    r_inner: float
+    setup: abi.EngineSetup
+    seed: int = SEED
+    tilt_sigma_deg: float = 20.0
+    noise: float = 0.05
+    n_water: int = 0
+
+    @property
+    def n_atoms(self) -> int:
+        return self.setup.n_atoms
+
+    def frame(self, f: int) -> Tuple[np.ndarray, np.ndarray]:
+        rng = np.random.Generator(np.random.Philox(key=self.seed + 1, counter=[0, 0, 0, f]))
+        t = self.template
+        n, ns = self.n_lipids, t.n_sites
+        box = (self.box * (1.0 + 0.004 * (2.0 * rng.random() - 1.0))).astype(np.float32)
+        v = self.unit + rng.normal(0.0, 0.01, (n, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        sign = np.where(self.is_outer, -1.0, 1.0)[:, None]        # director: from the head towards the mid-surface
+        tilt = np.abs(rng.normal(0.0, np.deg2rad(self.tilt_sigma_deg), n))
+        phi = rng.uniform(0.0, 2.0 * np.pi, n)
+        e1 = np.cross(v, np.array([0.0, 0.0, 1.0]))
+        e1n = np.linalg.norm(e1, axis=1, keepdims=True)
+        e1 = np.where(e1n > 1e-6, e1 / np.maximum(e1n, 1e-6), np.array([1.0, 0.0, 0.0]))
+        e2 = np.cross(v, e1)
+        u = sign * v * np.cos(tilt)[:, None] + (e1 * np.cos(phi)[:, None] + e2 * np.sin(phi)[:, None]) * np.sin(tilt)[:, None]
+        radius = np.where(self.is_outer, self.r_outer, self.r_inner)[:, None] + rng.normal(0.0, 0.1, (n, 1))
+        head = v * radius
+        pos = (head[:, None, :] + (t.depth * t.spacing)[None, :, None] * u[:, None, :] + t.lateral[None, :, None] * e1[:, None, :]
+               + rng.normal(0.0, self.noise, (n, ns, 3)))
+        centre = rng.uniform(0.0, 1.0, 3) * box
+        pos = pos + centre
+        pos -= np.floor(pos / box) * box                          # every bead on its own: broken molecules at the boundary
+        xyz = np.empty((self.n_atoms, 3), np.float32)
+        xyz[: n * ns] = pos.reshape(n * ns, 3)
+        if self.n_water:
+            xyz[n * ns:] = rng.random((self.n_water, 3)) * box
+        return xyz, box
+
+    def frames(self, first: int, count: int, step: int = 1) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        xyz = np.empty((count, self.n_atoms, 3), np.float32)
+        box = np.empty((count, 3), np.float32)
+        idx = np.arange(count, dtype=np.int64) * step + first
+        for i, f in enumerate(idx):
+            xyz[i], box[i] = self.frame(int(f))
+        return xyz, box, idx
+
+
+def _fibonacci_sphere(n: int) -> np.ndarray:
+    k = np.arange(n) + 0.5
+    z = 1.0 - 2.0 * k / n
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    phi = np.pi * (1.0 + 5.0 ** 0.5) * k
+    return np.stack([r * np.cos(phi), r * np.sin(phi), z], 1)
+
+
+def s_ves(n_lipids: int = 100000, *, area_per_lipid: float = 0.61, thickness: float = 4.0, margin: float = 6.0, **kw) -> SyntheticVesicle:
+    """BASELINE config 5 (S-VES): CGOrder on a Martini vesicle with dynamic local membrane normals (heads = PO4, r = 2 nm) and
+    spherical-clustering leaflets (reference: examples/coarse_grained/3_vesicles.yaml, tests_cg.rs:3391-3417 and the
+    clustering variant after it).  The radii follow from the lipid count at 0.61 nm^2 per lipid and a 4 nm bilayer (100 000
+    lipids: outer radius 54 nm, box 120 nm; SURVEY.md §8d's "R = 20 / 16 nm, ~100 k lipids" would pack 7 lipids per nm^2)."""
+    t = martini_popc()
+    # n_out / n_in = (R / (R - thickness))^2 and n_out * area = 4 pi R^2
+    r_out = 0.5 * thickness + np.sqrt(max(0.0, n_lipids * area_per_lipid / (8.0 * np.pi) - 0.25 * thickness ** 2))
+    r_out = float(max(r_out, thickness + 1.0))
+    r_in = r_out - thickness
+    n_out = int(round(n_lipids * r_out ** 2 / (r_out ** 2 + r_in ** 2)))
+    n_in = n_lipids - n_out
+    unit = np.concatenate([_fibonacci_sphere(n_out), _fibonacci_sphere(max(n_in, 1))[:n_in]], 0)
+    is_outer = np.arange(n_lipids) < n_out
+    rng = np.random.default_rng(SEED)
+    perm = rng.permutation(n_lipids)                     # leaflets interleaved in the topology, as after self-assembly
+    unit, is_outer = unit[perm], is_outer[perm]
+    side = 2.0 * r_out + 2.0 * margin
+    box = np.array([side, side, side], np.float32)
+    ns = t.n_sites
+    bases = np.arange(n_lipids, dtype=np.int64) * ns
+    heads = (bases + t.head).astype(np.int32)
+    mt = abi.MolType(name=t.name, mol_base=bases.tolist(), bond_rel=sorted(t.bonds), head_rel=t.head, methyl_rel=t.methyls, normal_head_rel=t.head,
+                     bond_names=[f"{t.site_names[i]}-{t.site_names[j]}" for i, j in sorted(t.bonds)])
+    kw.setdefault("normal_mode", abi.NORMAL_DYNAMIC)
+    kw.setdefault("dynamic_radius", 2.0)
+    kw.setdefault("normal_heads", heads)
+    kw.setdefault("leaflet_mode", abi.LEAFLET_SPHERICAL)
+    kw.setdefault("leaflet_freq_kind", abi.FREQ_ONCE)
+    if kw["leaflet_mode"] == abi.LEAFLET_SPHERICAL:
+        kw.setdefault("membrane", heads)                 # the ClusterHeads group
+    setup = abi.EngineSetup(kind=abi.KIND_CG, n_atoms=n_lipids * ns, moltypes=[mt], **kw)
+    return SyntheticVesicle(t, n_lipids, box, unit, is_outer, r_out, r_in, setup)

@@ -186,10 +186,11 @@ class SystemTopology:
     def stream(self) -> int:
         return int(lib().gorder_gpu_stream(self._h) or 0)
 
-    def finish(self) -> abi.RawResults:
-        """``ParallelTrajData::reduce`` for one GPU: fetch the raw accumulators."""
+    def finish(self, totals_only: bool = False) -> abi.RawResults:
+        """``ParallelTrajData::reduce`` for one GPU: fetch the raw accumulators (``totals_only``: without per-frame rows, maps,
+        leaflet tables and normals)."""
         try:
-            return abi.fetch_results(lib(), self._h, "gorder_gpu", self.setup)
+            return abi.fetch_results(lib(), self._h, "gorder_gpu", self.setup, totals_only)
         except abi.GorderError as e:
             buf = C.create_string_buffer(512)
             lib().gorder_gpu_last_error(self._h, buf, 512)

@@ -18,7 +18,7 @@ def test_reference_arm_prints_one_json_line():
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["scaling"] == "strong"
     assert d["value"] > 0 and d["steps"] == 2 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -59,12 +59,17 @@ def _cases():
                                 map_span_y=(0.0, 4.0), timewise=True), 7),
         "dynamic_normals": (synthetic.s_cg(300, normal_mode=abi.NORMAL_DYNAMIC, dynamic_radius=2.0, collect_normals=True, timewise=True), 6),
         "ua_error_blocks": (synthetic.s_ua(100, timewise=True, leaflet_mode=abi.LEAFLET_INDIVIDUAL), 8),
+        # BASELINE configs[4]: vesicle, dynamic normals, spherical-clustering leaflets assigned once, sharded by frame ranges
+        "vesicle_once": (synthetic.s_ves(2500, timewise=True, collect_leaflets=True, collect_normals=True), 6),
     }
 
 
 @needs2
+@pytest.mark.parametrize("root", [1, 0])
 @pytest.mark.parametrize("name", sorted(_cases()))
-def test_two_devices_one_process(name):
+def test_two_devices_one_process(name, root):
+    """root = 1: the merge happens on the shard that does NOT hold frame 0 (the rows must still come out in frame order);
+    root = 0 with the whole trajectory announced (reserve_frames): the peers' rows land behind the root's own, in place."""
     s, n = _cases()[name]
     xyz, box, idx = s.frames(0, n)
     want = _single(s.setup, xyz, box, idx)
@@ -74,15 +79,16 @@ def test_two_devices_one_process(name):
         st = dataclasses.replace(s.setup, device=dev)
         engines.append(SystemTopology(st))
     once = s.setup.leaflet_mode != abi.LEAFLET_NONE and s.setup.leaflet_freq_kind == abi.FREQ_ONCE
+    if root == 0:
+        engines[0].reserve_frames(n)
     for dev, (lo, hi) in enumerate(ranges):
         if once and dev > 0:   # the table of analysed frame 0 (shard 0) reaches the other shards before they accumulate
             engines[dev].set_leaflets(engines[0].finish().leaflets[0], 0)
         if hi > lo:
             engines[dev].analyze_frames(xyz[lo:hi], box[lo:hi], idx[lo:hi])
-    for root in (1,):   # merge on the shard that does NOT hold frame 0: the order of the rows must still be by frame
-        reduce_handles(engines, root=root)
-        got = engines[root].finish()
-        _assert_same(got, want)
+    reduce_handles(engines, root=root)
+    got = engines[root].finish()
+    _assert_same(got, want)
     for e in engines:
         e.close()
 
@@ -129,6 +135,8 @@ else:
 comm = Comm(uid, world, rank, rank)
 s.setup.device = rank
 eng = SystemTopology(s.setup)
+if rank == 0 and mode != "once":
+    eng.reserve_frames(n)   # the root of this mode: the other shard's per-frame rows land behind its own, in place
 lo, hi = sharding.frame_ranges(n, world, sharding.assignment_period(s.setup))[rank]
 if mode == "once":
     if rank == 0:
@@ -138,7 +146,7 @@ if mode == "once":
         eng.analyze_frames(xyz[lo:hi], box[lo:hi], idx[lo:hi])
 else:
     eng.analyze_frames(xyz[lo:hi], box[lo:hi], idx[lo:hi])
-root = world - 1
+root = world - 1 if mode == "once" else 0
 eng.reduce_comm(comm, root)
 if rank == root:
     r = eng.finish()
@@ -153,7 +161,8 @@ comm.close()
 @pytest.mark.parametrize("mode", ["every3", "once"])
 def test_two_processes_nccl(tmp_path, mode):
     """One process per GPU, the library's own NCCL communicator (unique id handed over through a file, as an MPI / torchrun
-    host would broadcast it): merged result on the LAST rank == single-GPU result."""
+    host would broadcast it): merged result on the last rank ("once") or on rank 0 with the rows gathered in place ("every3")
+    == single-GPU result."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
