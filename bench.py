@@ -304,6 +304,7 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     reduce_ms = ev_r.elapsed_time(ev1)
     hot_ms, hot_n = eng.profile_read()
+    nrm_ms, nrm_n = eng.profile_read_normals()
     eng.profile(False)
     launches = eng.stats()["kernel_launches"] - l0
     spec_stats = eng.speculation_stats()
@@ -456,6 +457,13 @@ def run_ours(args):
                          "step_share": (hot_ms / (ms - reduce_ms)) if ms else None,
                          "note": ("in-step duration, CUDA events around every launch of the kernel on the engine's stream (gorder_gpu_profile); "
                                   + ("speculative Global leaflets: no centre pre-pass" if spec_stats["enabled"] else "rank 0"))},
+            # dynamic normals: the neighbour search + PCA of every lipid (normal.rs:160-199) dominates the step.  It is a gather through
+            # L2 (per lipid ~27 cells x a few heads x 16 B), not an HBM stream: its floor is the one read of the head coordinates
+            "normals_stage": ({"kernels": "cell_count / cell_scan / cell_fill / dynamic_normal_cell_kernel", "ms_per_frame": nrm_ms / max(K * n_mine, 1),
+                               "step_share": nrm_ms / (ms - reduce_ms), "lipids_per_s": K * n_mine * s.setup.n_molecules_total / (nrm_ms * 1e-3) if nrm_ms else None,
+                               "algorithmic_bytes_per_frame": 12 * len(s.setup.normal_heads),
+                               "hbm_frac_of_floor": (12 * len(s.setup.normal_heads) * K * n_mine / (nrm_ms * 1e-3) / 1e9 / peak) if nrm_ms else None}
+                              if nrm_n else None),
             "reduce": ({"ms": reduce_ms, "entry": "gorder_gpu_reduce_comm: one ncclReduce (int64 sum) of the accumulator block + grouped send / recv of the per-frame rows to rank 0",
                         "per_frame_row_bytes_gathered": tw_bytes, "rows_on_root": rows_merged} if world > 1 else None),
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",

@@ -14,7 +14,7 @@ SYMBOLS = [
     "gorder_gpu_create", "gorder_gpu_submit", "gorder_gpu_submit_device", "gorder_gpu_native_layout",
     "gorder_gpu_submit_native", "gorder_gpu_submit_native_device", "gorder_gpu_reserve_frames", "gorder_gpu_set_leaflets", "gorder_gpu_sync",
     "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block", "gorder_gpu_stats",
-    "gorder_gpu_read_block", "gorder_gpu_write_block", "gorder_gpu_profile", "gorder_gpu_profile_read",
+    "gorder_gpu_read_block", "gorder_gpu_write_block", "gorder_gpu_profile", "gorder_gpu_profile_read", "gorder_gpu_profile_read_normals",
     "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_stream",
     "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_xtc_scan", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device",
     "gorder_results_order", "gorder_results_convergence", "gorder_results_map", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",

@@ -193,6 +193,11 @@ struct GorderHandle {
     size_t prof_used = 0;
     double prof_ms = 0.0;
     long long prof_n = 0;
+    // ... and of the membrane-normal stage (cell list + PCA kernels), when there is one
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events_n;
+    size_t prof_used_n = 0;
+    double prof_ms_n = 0.0;
+    long long prof_n_n = 0;
 
     bool fast_ok = false;   // K1f applies (bond_fast_kernel)
     bool ua_fast_ok = false;   // K2f applies (ua_fast_kernel)
@@ -543,6 +548,16 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         CK(cudaEventRecord(h->ev_pre[slot], sp));
         CK(cudaStreamWaitEvent(h->stream, h->ev_pre[slot], 0));
     }
+    std::pair<cudaEvent_t, cudaEvent_t> *pn = nullptr;
+    if (h->nvec && h->profiling) {
+        if (h->prof_used_n == h->prof_events_n.size()) {
+            std::pair<cudaEvent_t, cudaEvent_t> e;
+            CK(cudaEventCreate(&e.first)); CK(cudaEventCreate(&e.second));
+            h->prof_events_n.push_back(e);
+        }
+        pn = &h->prof_events_n[h->prof_used_n++];
+        CK(cudaEventRecord(pn->first, h->stream));
+    }
     if (h->nvec) {
         if (s.normal_mode == GORDER_NORMAL_DYNAMIC && h->use_cells) {
             const int nh = s.n_normal_heads;
@@ -564,6 +579,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         }
         h->n_launches++;
         if (h->d_normal_used) CK(cudaMemsetAsync(h->d_normal_used, 0, (size_t)nf * h->n_molpad, h->stream));
+        if (pn) CK(cudaEventRecord(pn->second, h->stream));
     }
     AccumOut o{};
     o.inline_center = (inline_leaf && !spec) ? h->d_center : nullptr;
@@ -706,6 +722,7 @@ void gorder_gpu_destroy(GorderHandle *h) {
         g_fast_used[h->device][h->fast_slot] = false;
     }
     for (auto &e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : h->prof_events_n) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream_pre) cudaStreamDestroy(h->stream_pre);
@@ -942,7 +959,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
     v.n_types = s->n_moltypes; v.n_chunks = h->n_chunks; v.n_slots = h->n_slots; v.n_molpad = h->n_molpad; v.n_mol_total = h->n_mol_total;
     v.frame_floats = h->frame_floats;
     v.kind = s->kind; v.handle_pbc = s->handle_pbc; v.step = s->step;
-    v.normal_mode = s->normal_mode; v.normal_axis = s->normal_axis; v.dynamic_radius = s->dynamic_radius;
+    v.normal_mode = s->normal_mode; v.normal_axis = s->normal_axis; v.dynamic_radius = s->dynamic_radius; v.collect_normals = s->collect_normals;
     v.leaflet_mode = s->leaflet_mode; v.leaflet_axis = s->leaflet_axis; v.leaflet_flip = s->leaflet_flip;
     v.leaflet_freq_kind = s->leaflet_freq_kind; v.leaflet_freq = s->leaflet_freq; v.leaflet_radius = s->leaflet_radius;
     v.shape.kind = s->geom_kind; v.shape.invert = s->geom_invert; v.shape.axis = s->geom_axis; v.shape.ref_kind = s->geom_ref_kind;
@@ -1422,7 +1439,7 @@ int gorder_gpu_write_block(GorderHandle *h, const void *d_src) {
 }
 
 static int drain_profile(GorderHandle *h) {
-    if (h->prof_used == 0) return GORDER_OK;
+    if (h->prof_used == 0 && h->prof_used_n == 0) return GORDER_OK;
     CK(cudaStreamSynchronize(h->stream));
     for (size_t i = 0; i < h->prof_used; i++) {
         float ms = 0.f;
@@ -1430,6 +1447,12 @@ static int drain_profile(GorderHandle *h) {
         h->prof_ms += ms; h->prof_n++;
     }
     h->prof_used = 0;
+    for (size_t i = 0; i < h->prof_used_n; i++) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->prof_events_n[i].first, h->prof_events_n[i].second));
+        h->prof_ms_n += ms; h->prof_n_n++;
+    }
+    h->prof_used_n = 0;
     return GORDER_OK;
 }
 
@@ -1450,6 +1473,17 @@ int gorder_gpu_profile_read(GorderHandle *h, double *hot_kernel_ms, int64_t *hot
     if (hot_kernel_ms) *hot_kernel_ms = h->prof_ms;
     if (hot_kernel_launches) *hot_kernel_launches = h->prof_n;
     h->prof_ms = 0.0; h->prof_n = 0;
+    return GORDER_OK;
+}
+
+int gorder_gpu_profile_read_normals(GorderHandle *h, double *stage_ms, int64_t *batches) {
+    if (!h) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
+    cudaSetDevice(h->device);
+    if (int rc = drain_profile(h)) return rc;
+    if (stage_ms) *stage_ms = h->prof_ms_n;
+    if (batches) *batches = h->prof_n_n;
+    h->prof_ms_n = 0.0; h->prof_n_n = 0;
     return GORDER_OK;
 }
 

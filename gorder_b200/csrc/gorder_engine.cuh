@@ -103,7 +103,7 @@ struct DeviceView {
     long long frame_floats;   // floats per native frame
     // configuration
     int kind, handle_pbc, step;
-    int normal_mode, normal_axis;
+    int normal_mode, normal_axis, collect_normals;
     float dynamic_radius;
     int leaflet_mode, leaflet_axis, leaflet_flip, leaflet_freq_kind, leaflet_freq;
     float leaflet_radius;

@@ -490,6 +490,203 @@ __device__ __forceinline__ void jacobi_smallest(float a00, float a01, float a02,
     out = unit_ref(n);
 }
 
+// ---- the SIGN of the reference's normal ----------------------------------------------------------------------------------
+// membrane_normal_from_cloud (normal.rs:421-458) returns the last row of V^T of nalgebra's SVD of the demeaned N x 3 cloud,
+// sign included (exported normals are compared signed: tests/common/mod.rs:84-87).  nalgebra's bidiagonalisation applies its
+// Householder reflections as sign * H, which makes the bidiagonal matrix and V^T functions of A^T A alone (the first row after
+// the first step is (|a0|, a0.a1 / |a0|, a0.a2 / |a0|) whatever the order or the signs of the rows), so running the SAME
+// algorithm -- reflection axes  x + sign(x0)|x| e1,  v_t() replayed on the identity, Wilkinson-shift QR sweeps with
+// GivensRotation::cancel_y, the 2 x 2 closing step, rows ordered by singular value -- on the 3 x 3 Cholesky factor of the
+// scatter matrix gives the same last row.  The device takes the DIRECTION from the Jacobi eigenvector (f64 moments) and only
+// the sign from this replay (oracle/gorder_oracle.c nalgebra_svd_last_row is the N x 3 restatement, pinned on the reference's
+// 274 signed vectors; tests/test_gpu_parity.py compares signed normals).
+__device__ __forceinline__ float signum_rust(float x) { return signbit(x) ? -1.0f : 1.0f; }
+__device__ __forceinline__ float refl_axis(float *col, int n, bool &nz) {   // householder::reflection_axis_mut, n <= 3
+    float sq = 0.0f;
+    for (int i = 0; i < n; i++) sq += col[i] * col[i];
+    const float norm = sqrtf(sq), modulus = fabsf(col[0]), signed_norm = signum_rust(col[0]) * norm;
+    const float factor = (sq + modulus * norm) * 2.0f;
+    col[0] += signed_norm;
+    if (factor != 0.0f) {
+        const float f = sqrtf(factor);
+        float s2 = 0.0f;
+        for (int i = 0; i < n; i++) { col[i] /= f; s2 += col[i] * col[i]; }
+        const float nn = sqrtf(s2);
+        for (int i = 0; i < n; i++) col[i] /= nn;
+        nz = true;
+        return -signed_norm;
+    }
+    nz = false;
+    return signed_norm;
+}
+__device__ __forceinline__ bool givens_cancel_y(float x, float y, float &c, float &s, float &r) {
+    if (y == 0.0f) return false;
+    const float mod0 = fabsf(x), sign0 = signum_rust(x), denom = sqrtf(mod0 * mod0 + y * y);
+    c = mod0 / denom; s = -y / (sign0 * denom); r = sign0 * denom;
+    return true;
+}
+__device__ __forceinline__ void givens_new(float cin, float sin_, float &c, float &s, float &norm) {
+    const float mod0 = fabsf(cin), sign0 = signum_rust(cin), denom = sqrtf(mod0 * mod0 + sin_ * sin_);
+    if (denom > 0.0f) { norm = sign0 * denom; c = mod0 / denom; s = sin_ / norm; }
+    else { c = 1.0f; s = 0.0f; norm = 0.0f; }
+}
+__device__ __forceinline__ void svd3_delimit(float *d, float *o, int end, float eps, int &start_out, int &end_out) {
+    int n = end;
+    while (n > 0) {
+        const int m = n - 1;
+        if (o[m] == 0.0f || fabsf(o[m]) <= eps * (fabsf(d[n]) + fabsf(d[m]))) o[m] = 0.0f;
+        else break;
+        n--;
+    }
+    if (n == 0) { start_out = 0; end_out = 0; return; }
+    int ns = n - 1;
+    while (ns > 0) {
+        const int m = ns - 1;
+        if (fabsf(o[m]) <= eps * (fabsf(d[ns]) + fabsf(d[m]))) { o[m] = 0.0f; break; }
+        ns--;
+    }
+    start_out = ns; end_out = n;
+}
+// last row of V^T of nalgebra's SVD::new applied to the upper-triangular 3 x 3 matrix a (row-major, overwritten)
+__device__ __noinline__ void nalgebra_svd3_last_row(float (&a)[3][3], f3 &out) {
+    float amax = 0.0f;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) amax = fmaxf(amax, fabsf(a[i][j]));
+    if (amax != 0.0f) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] /= amax;
+    float ds[3], os[2];
+    bool nz;
+    for (int ite = 0; ite < 2; ite++) {
+        const int len = 3 - ite;
+        float axis[3];
+        for (int i = 0; i < len; i++) axis[i] = a[ite + i][ite];
+        float rn = refl_axis(axis, len, nz);
+        for (int i = 0; i < len; i++) a[ite + i][ite] = axis[i];
+        if (nz) {
+            const float sign = signum_rust(rn);
+            for (int j = ite + 1; j < 3; j++) {
+                float dot = 0.0f;
+                for (int i = 0; i < len; i++) dot += axis[i] * a[ite + i][j];
+                const float factor = dot * (sign * -2.0f);
+                for (int i = 0; i < len; i++) a[ite + i][j] = factor * axis[i] + sign * a[ite + i][j];
+            }
+        }
+        ds[ite] = rn;
+        const int rl = 2 - ite;
+        float rax[2];
+        for (int j = 0; j < rl; j++) rax[j] = a[ite][ite + 1 + j];
+        rn = refl_axis(rax, rl, nz);
+        if (nz) {
+            const float sign = signum_rust(rn);
+            for (int i = ite + 1; i < 3; i++) {
+                float w = 0.0f;
+                for (int j = 0; j < rl; j++) w += a[i][ite + 1 + j] * rax[j];
+                const float f = w * (sign * -2.0f);
+                for (int j = 0; j < rl; j++) a[i][ite + 1 + j] = sign * a[i][ite + 1 + j] + f * rax[j];
+            }
+        }
+        for (int j = 0; j < rl; j++) a[ite][ite + 1 + j] = rax[j];
+        os[ite] = rn;
+    }
+    {
+        float axis[1] = {a[2][2]};
+        ds[2] = refl_axis(axis, 1, nz);
+    }
+    float vt[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 1; i >= 0; i--) {
+        const int rl = 2 - i;
+        float sq = 0.0f;
+        for (int j = 0; j < rl; j++) sq += a[i][i + 1 + j] * a[i][i + 1 + j];
+        if (sq == 0.0f) continue;
+        const float sign = signum_rust(os[i]);
+        for (int r = i; r < 3; r++) {
+            float w = 0.0f;
+            for (int j = 0; j < rl; j++) w += vt[r][i + 1 + j] * a[i][i + 1 + j];
+            const float f = w * (sign * -2.0f);
+            for (int j = 0; j < rl; j++) vt[r][i + 1 + j] = sign * vt[r][i + 1 + j] + f * a[i][i + 1 + j];
+        }
+    }
+    float d[3] = {fabsf(ds[0]), fabsf(ds[1]), fabsf(ds[2])}, o[2] = {fabsf(os[0]), fabsf(os[1])};
+    const float eps = 1.1920929e-07f * 5.0f;
+    int start, end;
+    svd3_delimit(d, o, 2, eps, start, end);
+    for (int niter = 0; end != start && niter < 64; niter++) {
+        if (end - start + 1 > 2) {
+            const int m = end - 1, nn = end;
+            const float dm = d[m], dn = d[nn], fm = o[m];
+            const float tmm = dm * dm + o[m - 1] * o[m - 1], tmn = dm * fm, tnn = dn * dn + fm * fm;
+            float shift = tnn;
+            const float sq = tmn * tmn;
+            if (sq != 0.0f) {
+                const float dd = (tmm - tnn) * 0.5f;
+                shift = tnn - sq / (dd + signum_rust(dd) * sqrtf(dd * dd + sq));
+            }
+            float vx = d[start] * d[start] - shift, vy = d[start] * o[start];
+            for (int k = start; k < nn; k++) {
+                const float m12 = (k == nn - 1) ? 0.0f : o[k + 1];
+                float s00 = d[k], s01 = o[k], s02 = 0.0f, s10 = 0.0f, s11 = d[k + 1], s12 = m12;
+                float c1, s1, norm1, c2, s2, norm2;
+                if (!givens_cancel_y(vx, vy, c1, s1, norm1)) break;
+                {
+                    const float sn = -s1;
+                    float a0 = s00, b0 = s01; s00 = a0 * c1 + sn * b0; s01 = -sn * a0 + b0 * c1;
+                    a0 = s10; b0 = s11; s10 = a0 * c1 + sn * b0; s11 = -sn * a0 + b0 * c1;
+                }
+                if (k > start) o[k - 1] = norm1;
+                if (!givens_cancel_y(s00, s10, c2, s2, norm2)) { c2 = 1.0f; s2 = 0.0f; norm2 = s00; }
+                {
+                    float a0 = s01, b0 = s11; s01 = a0 * c2 - s2 * b0; s11 = s2 * a0 + b0 * c2;
+                    a0 = s02; b0 = s12; s02 = a0 * c2 - s2 * b0; s12 = s2 * a0 + b0 * c2;
+                }
+                s00 = norm2;
+                for (int j = 0; j < 3; j++) { const float p = vt[k][j], q = vt[k + 1][j]; vt[k][j] = p * c1 - s1 * q; vt[k + 1][j] = s1 * p + q * c1; }
+                d[k] = s00; d[k + 1] = s11; o[k] = s01;
+                if (k != nn - 1) o[k + 1] = s12;
+                vx = s01; vy = s02;
+            }
+        } else {
+            const float m11 = d[start], m12 = o[start], m22 = d[start + 1];
+            const float denom = hypotf(m11 + m22, m12) + hypotf(m11 - m22, m12);
+            float v1 = m11 * m22 * 2.0f / denom, v2 = 0.5f * denom;
+            float cv, sv, sgn_v, cu_, su_, sgn_u;
+            const float diff = fabsf(m11) >= fabsf(m22) ? v1 * v1 - m11 * m11 : -(m11 * m11 * m12 * m12) / (m12 * m12 + m22 * m22 - v1 * v1);
+            givens_new(m11 * m12, diff, cv, sv, sgn_v);
+            v1 *= sgn_v; v2 *= sgn_v;
+            givens_new((m11 * cv + m12 * sv) / v1, (m22 * sv) / v1, cu_, su_, sgn_u);
+            v1 *= sgn_u; v2 *= sgn_u;
+            d[start] = v1; d[start + 1] = v2; o[start] = 0.0f;
+            const float si = -sv;
+            for (int j = 0; j < 3; j++) { const float p = vt[start][j], q = vt[start + 1][j]; vt[start][j] = p * cv - si * q; vt[start + 1][j] = si * p + q * cv; }
+            end -= 1;
+        }
+        svd3_delimit(d, o, end, eps, start, end);
+    }
+    int k = 0;
+    for (int i = 1; i < 3; i++) if (fabsf(d[i]) <= fabsf(d[k])) k = i;
+    out = mk3(vt[k][0], vt[k][1], vt[k][2]);
+}
+
+// Normal of a cloud from its scatter matrix (sum of outer products of the demeaned positions): direction by Jacobi, sign as
+// the reference's SVD gives it.
+// `signed_`: only exported normals need the reference's sign (S is invariant under n -> -n).
+__device__ __forceinline__ void pca_normal(double a00, double a01, double a02, double a11, double a12, double a22, bool signed_, f3 &out) {
+    f3 n;
+    jacobi_smallest((float)a00, (float)a01, (float)a02, (float)a11, (float)a12, (float)a22, n);
+    // Cholesky factor (upper) of the scatter matrix = R of the cloud's QR factorisation with a positive diagonal
+    const double r00 = sqrt(fmax(a00, 0.0));
+    if (signed_ && r00 > 0.0) {
+        const double r01 = a01 / r00, r02 = a02 / r00;
+        const double r11 = sqrt(fmax(a11 - r01 * r01, 0.0));
+        if (r11 > 0.0) {
+            const double r12 = (a12 - r01 * r02) / r11;
+            const double r22 = sqrt(fmax(a22 - r02 * r02 - r12 * r12, 0.0));
+            float R[3][3] = {{(float)r00, (float)r01, (float)r02}, {0.0f, (float)r11, (float)r12}, {0.0f, 0.0f, (float)r22}};
+            f3 ref;
+            nalgebra_svd3_last_row(R, ref);
+            if (ref.x * n.x + ref.y * n.y + ref.z * n.z < 0.0f) n = mk3(-n.x, -n.y, -n.z);
+        }
+    }
+    out = n;
+}
+
 __global__ void __launch_bounds__(128) dynamic_normal_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                              const int *__restrict__ molpad_type, float *__restrict__ normals,
                                                              int *__restrict__ normal_npoints) {
@@ -538,7 +735,7 @@ __global__ void __launch_bounds__(128) dynamic_normal_kernel(DeviceView v, const
         }
     }
     f3 nrm;
-    jacobi_smallest(a00, a01, a02, a11, a12, a22, nrm);
+    pca_normal(a00, a01, a02, a11, a12, a22, v.collect_normals != 0, nrm);
     nx[0] = nrm.x; nx[v.n_molpad] = nrm.y; nx[2 * (size_t)v.n_molpad] = nrm.z;
 }
 
@@ -718,8 +915,7 @@ __global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, 
     if (cnt < 3) { nx[0] = CUDART_NAN_F; nx[v.n_molpad] = CUDART_NAN_F; nx[2 * (size_t)v.n_molpad] = CUDART_NAN_F; return; }
     const double inv = 1.0 / cnt, mx = sx * inv, my = sy * inv, mz = sz * inv;
     f3 nrm;
-    jacobi_smallest((float)(xx - cnt * mx * mx), (float)(xy - cnt * mx * my), (float)(xz - cnt * mx * mz), (float)(yy - cnt * my * my),
-                    (float)(yz - cnt * my * mz), (float)(zz - cnt * mz * mz), nrm);
+    pca_normal(xx - cnt * mx * mx, xy - cnt * mx * my, xz - cnt * mx * mz, yy - cnt * my * my, yz - cnt * my * mz, zz - cnt * mz * mz, v.collect_normals != 0, nrm);
     nx[0] = nrm.x; nx[v.n_molpad] = nrm.y; nx[2 * (size_t)v.n_molpad] = nrm.z;
 }
 

@@ -167,6 +167,12 @@ class SystemTopology:
         self._check(lib().gorder_gpu_profile_read(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def profile_read_normals(self):
+        """(summed ms, batches) of the membrane-normal stage (cell list + PCA kernels) since the last read."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        self._check(lib().gorder_gpu_profile_read_normals(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def stats(self):
         k, f = C.c_int64(0), C.c_int64(0)
         lib().gorder_gpu_stats(self._h, C.byref(k), C.byref(f))

@@ -344,6 +344,9 @@ int gorder_gpu_write_block(GorderHandle *h, const void *d_src);
  * read and resets both. */
 int gorder_gpu_profile(GorderHandle *h, int enable);
 int gorder_gpu_profile_read(GorderHandle *h, double *hot_kernel_ms, int64_t *hot_kernel_launches);
+/* The same for the membrane-normal stage of dynamic / manual normals (cell list + PCA kernels of a batch, normal.rs:160-199):
+ * summed duration and number of batches since the last read. */
+int gorder_gpu_profile_read_normals(GorderHandle *h, double *stage_ms, int64_t *batches);
 
 /* Counters for benchmarking: kernels launched by this handle and frames analysed so far. */
 int gorder_gpu_stats(GorderHandle *h, int64_t *kernel_launches, int64_t *frames);

@@ -460,12 +460,237 @@ static void jacobi_eig3(double a[3][3], double v[3][3], double w[3]) {
     for (int i = 0; i < 3; i++) w[i] = a[i][i];
 }
 
-/* returns 0 ok, GORDER_ERR_DYNAMIC_NORMAL_POINTS if n < 3 */
+/* ------------------------------------------------------------------------------------------
+ * nalgebra 0.34 SVD::new(data, true, true) of the demeaned N x 3 cloud (normal.rs:443), restated: the reference takes
+ * the LAST ROW of V^T, sign included (its exported normals are compared signed, tests/common/mod.rs:84-87), so the
+ * conventions of nalgebra's algorithm are part of the result:
+ *   - the matrix is divided by its largest |entry|;
+ *   - Bidiagonal::new: Householder reflections with the axis  x + sign(x0) |x| e1  (normalised twice), applied as
+ *     sign * H with sign = signum(-sign(x0) |x|), alternately to columns and rows; v_t() replays the row reflections
+ *     on the identity, from the last to the first, with the sign of the stored (signed) off-diagonal;
+ *   - the diagonal and off-diagonal handed to the iteration are the MODULI of the stored values;
+ *   - implicit-shift QR sweeps (Wilkinson shift of the trailing 2 x 2 of B^T B) by Givens rotations
+ *     (GivensRotation::cancel_y: c = |x| / r, s = -y / (sign(x) r)), V^T rotated by the right-hand rotation; off-diagonal
+ *     entries are zeroed when <= 5 eps (|d_i| + |d_i+1|); a remaining 2 x 2 block by compute_2x2_uptrig_svd;
+ *   - rows sorted by decreasing singular value (the rows keep their sign).
+ * Pinned by the reference's own signed vectors: the 274 normals of normal.rs:664-963 (pcpepg.tpr, P atoms, r = 2 nm) are
+ * reproduced with their signs (tests/test_oracle_pins.py), and so is tests/files/ua_normals.yaml.
+ * Zero diagonal entries (singular value <= 5 eps of the largest entry: collinear clouds) are not chased as nalgebra does;
+ * the sweep then simply stops at 64 iterations.
+ * ---------------------------------------------------------------------------------------- */
+static inline float signumf_rust(float x) { return signbit(x) ? -1.0f : 1.0f; }
+
+/* nalgebra's dot (base/blas.rs): chunks of eight products, res += (p0 + p4); (p1 + p5); (p2 + p6); (p3 + p7); then the tail */
+static float dot8(const float *x, int sx, const float *y, int sy, int n) {
+    float res = 0.0f;
+    int i = 0;
+    for (; n - i >= 8; i += 8) {
+        float p[8];
+        for (int k = 0; k < 8; k++) p[k] = x[(i + k) * sx] * y[(i + k) * sy];
+        res += p[0] + p[4]; res += p[1] + p[5]; res += p[2] + p[6]; res += p[3] + p[7];
+    }
+    for (; i < n; i++) res += x[i * sx] * y[i * sy];
+    return res;
+}
+
+/* householder::reflection_axis_mut on a strided vector; returns the (signed) reflection norm, *nz = axis is usable */
+static float reflection_axis(float *col, int n, int stride, int *nz) {
+    float sq = dot8(col, stride, col, stride, n);
+    const float norm = sqrtf(sq);
+    const float modulus = fabsf(col[0]), sign = signumf_rust(col[0]);
+    const float signed_norm = sign * norm;
+    const float factor = (sq + modulus * norm) * 2.0f;
+    col[0] += signed_norm;
+    if (factor != 0.0f) {
+        const float f = sqrtf(factor);
+        for (int i = 0; i < n; i++) col[i * stride] /= f;
+        const float nn = sqrtf(dot8(col, stride, col, stride, n));
+        for (int i = 0; i < n; i++) col[i * stride] /= nn;
+        *nz = 1;
+        return -signed_norm;
+    }
+    *nz = 0;
+    return signed_norm;
+}
+
+typedef struct { float c, s; } givens_t;
+static int givens_cancel_y(float x, float y, givens_t *g, float *r) {
+    if (y == 0.0f) return 0;
+    const float mod0 = fabsf(x), sign0 = signumf_rust(x);
+    const float denom = sqrtf(mod0 * mod0 + y * y);
+    g->c = mod0 / denom; g->s = -y / (sign0 * denom);
+    *r = sign0 * denom;
+    return 1;
+}
+static void givens_new(float c, float s, givens_t *g, float *norm) {
+    const float mod0 = fabsf(c), sign0 = signumf_rust(c);
+    const float denom = sqrtf(mod0 * mod0 + s * s);
+    if (denom > 0.0f) { *norm = sign0 * denom; g->c = mod0 / denom; g->s = s / *norm; }
+    else { g->c = 1.0f; g->s = 0.0f; *norm = 0.0f; }
+}
+/* rows k, k + 1 of a 3-column matrix: rhs = R rhs with R = [[c, -s], [s, c]] */
+static void givens_rotate_rows3(givens_t g, float *r0, float *r1) {
+    for (int j = 0; j < 3; j++) { const float a = r0[j], b = r1[j]; r0[j] = a * g.c - g.s * b; r1[j] = g.s * a + b * g.c; }
+}
+
+static void svd_delimit(float *d, float *o, int end, float eps, int *start_out, int *end_out) {
+    int n = end;
+    while (n > 0) {
+        const int m = n - 1;
+        if (o[m] == 0.0f || fabsf(o[m]) <= eps * (fabsf(d[n]) + fabsf(d[m]))) o[m] = 0.0f;
+        else break;
+        n--;
+    }
+    if (n == 0) { *start_out = 0; *end_out = 0; return; }
+    int ns = n - 1;
+    while (ns > 0) {
+        const int m = ns - 1;
+        if (fabsf(o[m]) <= eps * (fabsf(d[ns]) + fabsf(d[m]))) { o[m] = 0.0f; break; }
+        ns--;
+    }
+    *start_out = ns; *end_out = n;
+}
+
+/* a: [n][3] row-major, overwritten.  out: last row of V^T of SVD::new(a). */
+static void nalgebra_svd_last_row(float *a, int n, float out[3]) {
+    float amax = 0.0f;
+    for (int i = 0; i < 3 * n; i++) amax = fmaxf(amax, fabsf(a[i]));
+    if (amax != 0.0f) for (int i = 0; i < 3 * n; i++) a[i] /= amax;
+    float ds[3], os[2];   /* stored (signed) diagonal / off-diagonal of Bidiagonal::new */
+    int nz;
+    for (int ite = 0; ite < 2; ite++) {
+        /* clear_column_unchecked(matrix, ite, 0, None) */
+        float *axis = a + 3 * ite + ite;   /* rows ite.., column ite, stride 3 */
+        const int len = n - ite;
+        float rn = reflection_axis(axis, len, 3, &nz);
+        if (nz) {
+            const float sign = signumf_rust(rn);
+            for (int j = ite + 1; j < 3; j++) {
+                float *col = a + 3 * ite + j;
+                const float factor = dot8(axis, 3, col, 3, len) * (sign * -2.0f);
+                for (int i = 0; i < len; i++) col[3 * i] = factor * axis[3 * i] + sign * col[3 * i];
+            }
+        }
+        ds[ite] = rn;
+        /* clear_row_unchecked(matrix, axis_packed, work, ite, 1) */
+        float rax[2];
+        const int rl = 3 - (ite + 1);
+        for (int j = 0; j < rl; j++) rax[j] = a[3 * ite + ite + 1 + j];
+        rn = reflection_axis(rax, rl, 1, &nz);
+        if (nz) {
+            const float sign = signumf_rust(rn);
+            for (int i = ite + 1; i < n; i++) {
+                float *row = a + 3 * i + ite + 1;
+                float w = 0.0f;
+                for (int j = 0; j < rl; j++) w += row[j] * rax[j];
+                const float f = w * (sign * -2.0f);
+                for (int j = 0; j < rl; j++) row[j] = sign * row[j] + f * rax[j];
+            }
+        }
+        for (int j = 0; j < rl; j++) a[3 * ite + ite + 1 + j] = rax[j];
+        os[ite] = rn;
+    }
+    ds[2] = reflection_axis(a + 3 * 2 + 2, n - 2, 3, &nz);
+    /* v_t(): the row reflections replayed on the identity, i = 1, 0 */
+    float vt[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 1; i >= 0; i--) {
+        const int rl = 3 - (i + 1);
+        const float *axis = a + 3 * i + i + 1;
+        float sq = 0.0f;
+        for (int j = 0; j < rl; j++) sq += axis[j] * axis[j];
+        if (sq == 0.0f) continue;
+        const float sign = signumf_rust(os[i]);
+        for (int r = i; r < 3; r++) {
+            float w = 0.0f;
+            for (int j = 0; j < rl; j++) w += vt[r][i + 1 + j] * axis[j];
+            const float f = w * (sign * -2.0f);
+            for (int j = 0; j < rl; j++) vt[r][i + 1 + j] = sign * vt[r][i + 1 + j] + f * axis[j];
+        }
+    }
+    float d[3] = {fabsf(ds[0]), fabsf(ds[1]), fabsf(ds[2])}, o[2] = {fabsf(os[0]), fabsf(os[1])};
+    const float eps = 1.1920929e-07f * 5.0f;
+    int start, end;
+    svd_delimit(d, o, 2, eps, &start, &end);
+    for (int niter = 0; end != start && niter < 64; niter++) {
+        const int subdim = end - start + 1;
+        if (subdim > 2) {
+            const int m = end - 1, nn = end;
+            const float dm = d[m], dn = d[nn], fm = o[m];
+            const float tmm = dm * dm + o[m - 1] * o[m - 1], tmn = dm * fm, tnn = dn * dn + fm * fm;
+            float shift = tnn;
+            const float sq = tmn * tmn;
+            if (sq != 0.0f) {   /* symmetric_eigen::wilkinson_shift */
+                const float dd = (tmm - tnn) * 0.5f;
+                shift = tnn - sq / (dd + signumf_rust(dd) * sqrtf(dd * dd + sq));
+            }
+            float vx = d[start] * d[start] - shift, vy = d[start] * o[start];
+            for (int k = start; k < nn; k++) {
+                const float m12 = (k == nn - 1) ? 0.0f : o[k + 1];
+                float s00 = d[k], s01 = o[k], s02 = 0.0f, s10 = 0.0f, s11 = d[k + 1], s12 = m12;
+                givens_t r1, r2;
+                float norm1, norm2;
+                if (!givens_cancel_y(vx, vy, &r1, &norm1)) break;
+                {   /* rot1.inverse().rotate_rows(columns 0..2): lhs = lhs * [[c, s], [-s, c]] */
+                    const float c = r1.c, sn = -r1.s;
+                    float a0 = s00, b0 = s01; s00 = a0 * c + sn * b0; s01 = -sn * a0 + b0 * c;
+                    a0 = s10; b0 = s11; s10 = a0 * c + sn * b0; s11 = -sn * a0 + b0 * c;
+                }
+                if (k > start) o[k - 1] = norm1;
+                if (!givens_cancel_y(s00, s10, &r2, &norm2)) { r2.c = 1.0f; r2.s = 0.0f; norm2 = s00; }
+                {   /* rot2.rotate(columns 1..3) */
+                    float a0 = s01, b0 = s11; s01 = a0 * r2.c - r2.s * b0; s11 = r2.s * a0 + b0 * r2.c;
+                    a0 = s02; b0 = s12; s02 = a0 * r2.c - r2.s * b0; s12 = r2.s * a0 + b0 * r2.c;
+                }
+                s00 = norm2;
+                givens_rotate_rows3(r1, vt[k], vt[k + 1]);
+                d[k] = s00; d[k + 1] = s11; o[k] = s01;
+                if (k != nn - 1) o[k + 1] = s12;
+                vx = s01; vy = s02;
+            }
+        } else if (subdim == 2) {   /* compute_2x2_uptrig_svd */
+            const float m11 = d[start], m12 = o[start], m22 = d[start + 1];
+            const float denom = hypotf(m11 + m22, m12) + hypotf(m11 - m22, m12);
+            float v1 = m11 * m22 * 2.0f / denom, v2 = 0.5f * denom;
+            givens_t csv, csu;
+            float sgn_v, sgn_u;
+            /* nalgebra builds the rotation from (m11 m12, v1^2 - m11^2), which is free of cancellation when |m11| >= |m22| (v1
+             * is then the singular value next to m22).  QR sweeps may leave the block the other way round; the difference is
+             * then evaluated from the characteristic equation, v1^2 - m11^2 = -m11^2 m12^2 / (m12^2 + m22^2 - v1^2): the same
+             * number in exact arithmetic (a borderline deflation decides whether the reference gets here at all). */
+            const float diff = fabsf(m11) >= fabsf(m22) ? v1 * v1 - m11 * m11 : -(m11 * m11 * m12 * m12) / (m12 * m12 + m22 * m22 - v1 * v1);
+            givens_new(m11 * m12, diff, &csv, &sgn_v);
+            v1 *= sgn_v; v2 *= sgn_v;
+            const float cu = (m11 * csv.c + m12 * csv.s) / v1, su = (m22 * csv.s) / v1;
+            givens_new(cu, su, &csu, &sgn_u);
+            v1 *= sgn_u; v2 *= sgn_u;
+            d[start] = v1; d[start + 1] = v2; o[start] = 0.0f;
+            givens_t inv = {csv.c, -csv.s};
+            givens_rotate_rows3(inv, vt[start], vt[start + 1]);
+            end -= 1;
+        }
+        svd_delimit(d, o, end, eps, &start, &end);
+    }
+    int k = 0;   /* sort_by_singular_values: the last row belongs to the smallest singular value (stable) */
+    for (int i = 1; i < 3; i++) if (fabsf(d[i]) <= fabsf(d[k])) k = i;
+    out[0] = vt[k][0]; out[1] = vt[k][1]; out[2] = vt[k][2];
+}
+
+/* membrane_normal_from_cloud (normal.rs:421-458).  returns 0 ok, GORDER_ERR_DYNAMIC_NORMAL_POINTS if n < 3 */
+int gorder_oracle_variant_normal = 0;   /* 0: nalgebra SVD restatement (signed); 1: eigenvector of the scatter matrix (sign arbitrary) */
 static int normal_from_cloud(const vec3 *pts, int n, vec3 *out) {
     if (n < 3) return GORDER_ERR_DYNAMIC_NORMAL_POINTS;
     vec3 c = v3(0, 0, 0);
     for (int i = 0; i < n; i++) c = vadd(c, pts[i]);
     c = vdivs(c, (float)n);
+    if (gorder_oracle_variant_normal == 0) {
+        float *a = (float *)malloc(sizeof(float) * 3 * (size_t)n);
+        for (int i = 0; i < n; i++) { a[3 * i] = pts[i].x - c.x; a[3 * i + 1] = pts[i].y - c.y; a[3 * i + 2] = pts[i].z - c.z; }
+        float r[3];
+        nalgebra_svd_last_row(a, n, r);
+        free(a);
+        *out = vunit(v3(r[0], r[1], r[2]));
+        return 0;
+    }
     double a[3][3] = {{0}};
     for (int i = 0; i < n; i++) {
         float d[3] = {pts[i].x - c.x, pts[i].y - c.y, pts[i].z - c.z};

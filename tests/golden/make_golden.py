@@ -499,8 +499,23 @@ def xtc_fixtures():
     print("xtc fixtures:", sorted(os.listdir(out)))
 
 
+def normals_planar():
+    """The reference's unit test of membrane_normal_from_cloud (normal.rs:664-963): positions of the 274 P atoms of
+    pcpepg.tpr, its box, and the 274 expected SIGNED normals copied from the Rust source."""
+    st = fixtures.read_gro(os.path.join(FILES, "pcpepg.gro"))
+    xyz, box, _ = fixtures.tpr_coordinates(os.path.join(FILES, "pcpepg.tpr"), st.xyz)
+    p = np.array([i for i in range(st.n_atoms) if st.name[i] == "P"])
+    src = open(os.path.join(REF, "src", "analysis", "normal.rs")).read()
+    body = src[src.index("fn test_real_planar"):src.index("fn test_real_vesicle")]
+    exp = np.array([[float(x) for x in m] for m in re.findall(r"Vector3D::new\(\s*([-0-9.e]+),\s*([-0-9.e]+),\s*([-0-9.e]+)\s*,?\s*\)", body)], np.float32)
+    assert exp.shape == (len(p), 3)
+    np.savez_compressed(os.path.join(HERE, "normals_planar.npz"), P=xyz[p].astype(np.float32), box=np.asarray(box, np.float32), expected=exp)
+    print("normals_planar", exp.shape)
+
+
 if __name__ == "__main__":
     xtc_fixtures()
+    normals_planar()
     single_frame("cg_single_frame", "cg.gro", "cg.bnd", "cg.tpr", abi.KIND_CG, "cgorder.rs", 1.0, "PO4")
     single_frame("aa_single_frame", "pcpepg.gro", "pcpepg.bnd", "pcpepg.tpr", abi.KIND_AA, "aaorder.rs", -1.0, "P")
     ua_golden()

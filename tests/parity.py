@@ -50,9 +50,13 @@ def assert_raw_parity(gpu: abi.RawResults, ref: abi.RawResults, setup: abi.Engin
         g, r = gpu.normals, ref.normals
         assert np.array_equal(np.isnan(g), np.isnan(r)), f"{what}: NaN pattern of normals differs"
         ok = ~np.isnan(r[..., 0])
-        # the sign of a PCA normal is implementation-defined (S is sign-invariant): compare up to sign
-        dots = np.abs(np.sum(g[ok] * r[ok], axis=-1))
-        assert np.all(dots > 1 - 1e-4), f"{what}: normals differ (min |cos| {dots.min()})"
+        # SIGNED: the reference exports the last row of V^T of nalgebra's SVD as it comes (normal.rs:443-457) and compares the
+        # components signed (tests/common/mod.rs:84-87); oracle and device both reproduce that sign
+        # (a sign decision of the algorithm -- e.g. the sign of the cloud's x-y covariance -- that sits within rounding of zero
+        # comes out either way, in the reference too: at most one normal in a thousand may differ in sign)
+        dots = np.sum(g[ok] * r[ok], axis=-1)
+        assert np.all(np.abs(dots) > 1 - 1e-4), f"{what}: normals differ (min |cos| {np.abs(dots).min()})"
+        assert (dots < 0).sum() <= max(1, 1e-3 * dots.size), f"{what}: {int((dots < 0).sum())} of {dots.size} normals with the opposite sign"
 
 
 def run_both(setup: abi.EngineSetup, xyz, box, frame_index=None, batches=1, oracle_threads=2, native=False):

@@ -35,8 +35,10 @@ def test_ua_trajectory_fixtures(name):
     if name == "dynamic_normals":
         for mt, (m0, n) in zip(setup.moltypes, _mol_ranges(setup)):
             exp = np.array(case["normals"][mt.name], np.float32)
-            dots = np.abs(np.sum(exp * g.normals[:, m0:m0 + n, :], axis=-1))
-            assert np.all(dots > 1 - 2e-5), dots.min()
+            # signed components against the reference's ua_normals.yaml (see tests/test_oracle_pins.py for the bars)
+            diff = np.abs(exp - g.normals[:, m0:m0 + n, :]).max(axis=-1)
+            assert np.all(np.sum(exp * g.normals[:, m0:m0 + n, :], axis=-1) > 0.99), mt.name
+            assert np.mean(diff < 1e-5) > 0.99 and float(diff.max()) < 2e-4, (mt.name, float(diff.max()))
 
 
 def test_ua_leaflets_once_export_bit_exact():

@@ -196,10 +196,45 @@ def test_ua_trajectory_fixtures(name):
             exp = np.array(case["normals"][mt.name], np.float32)
             got = raw.normals[:, m0:m0 + n, :]
             assert exp.shape == got.shape
-            dots = np.abs(np.sum(exp * got, axis=-1))
-            assert np.all(dots > 1 - 2e-5), dots.min()
-            same_sign = np.mean(np.sum(exp * got, axis=-1) > 0)
-            print(f"{mt.name}: {same_sign:.3f} of the normals have the reference's sign")
+            # SIGNED components, as the reference's comparator (tests/common/mod.rs:84-87, epsilon 1e-5): every one of the
+            # 51 x 128 normals has the reference's sign; 99.5 % agree to 1e-5, the rest -- clouds of a few heads, where one ulp
+            # of a re-imaged position (the neighbour order of groan's CellGrid is not known) is amplified -- to 2e-4, with the
+            # f32 SVD restatement and with an f64 eigen-decomposition of the same cloud alike
+            diff = np.abs(exp - got).max(axis=-1)
+            assert np.all(np.sum(exp * got, axis=-1) > 0.99), mt.name
+            assert np.mean(diff < 1e-5) > 0.99 and float(diff.max()) < 2e-4, (mt.name, float(diff.max()), float(np.mean(diff < 1e-5)))
+
+
+def test_signed_normals_of_the_reference_unit_test():
+    """membrane_normal_from_cloud (normal.rs:421-458) takes the last row of V^T of nalgebra's SVD, sign included.  The oracle
+    restates that algorithm (oracle/gorder_oracle.c nalgebra_svd_last_row); here it reproduces the 274 signed normals of the
+    reference's own unit test (normal.rs:664-963: pcpepg.tpr, the P atoms within 2 nm of every P atom, positions NOT re-imaged)
+    -- tests/golden/normals_planar.npz holds the P positions, the box and the expected vectors (make_golden.py)."""
+    d = np.load(os.path.join(gc.GOLDEN, "normals_planar.npz"))
+    pts, L, exp = d["P"], d["box"], d["expected"]
+    assert exp.shape == (274, 3)
+    worst = 0.0
+    for i in range(len(exp)):
+        dd = pts - pts[i]
+        dd -= np.round(dd / L) * L                      # groan's Sphere filter measures the distance through the box
+        got = oracle.normal_from_cloud(pts[np.linalg.norm(dd, axis=1) < 2.0])
+        worst = max(worst, float(np.abs(got - exp[i]).max()))
+    assert worst < 5e-6, worst
+    # the eigenvector route (variant 1) gives the same directions with arbitrary signs
+    import ctypes as C
+    vn = C.c_int.in_dll(oracle.lib(), "gorder_oracle_variant_normal")
+    vn.value = 1
+    try:
+        flipped = 0
+        for i in range(0, len(exp), 7):
+            dd = pts - pts[i]
+            dd -= np.round(dd / L) * L
+            got = oracle.normal_from_cloud(pts[np.linalg.norm(dd, axis=1) < 2.0])
+            assert abs(abs(float(np.dot(got, exp[i]))) - 1) < 1e-5
+            flipped += float(np.dot(got, exp[i])) < 0
+        assert flipped > 0
+    finally:
+        vn.value = 0
 
 
 def _mol_ranges(setup):
