@@ -150,3 +150,89 @@ def test_multi_gpu_entry_points_fail_cleanly_without_devices():
     assert L.gorder_comm_create(buf, 2, 3, 0, C.byref(out)) == abi.ERR_INVALID_ARGUMENT
     assert L.gorder_gpu_reduce_comm(None, None, 0) == abi.ERR_INVALID_ARGUMENT
     L.gorder_comm_destroy(None)
+
+
+def _header_struct(name):
+    """[(field, c type, is pointer, array length)] of a struct of include/gorder_b200.h, in declaration order."""
+    hdr = open(HEADER).read()
+    body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        const, typ, rest = re.match(r"(const )?(\w+) (.*)$", decl).groups()
+        for var in rest.split(","):
+            var = var.strip()
+            ptr = var.startswith("*")
+            var = var.lstrip("*").strip()
+            arr = None
+            m = re.match(r"(\w+)\[(\d+)\]", var)
+            if m:
+                var, arr = m.group(1), int(m.group(2))
+            out.append((var, typ, bool(const), ptr, arr))
+    return out
+
+
+def test_rust_shim_structs_and_functions_match_the_header():
+    """integration/gpu.rs (the module a maintainer adds to the gorder crate) cannot be compiled here (no Rust toolchain): its
+    #[repr(C)] structs must at least list the header's fields in order with the matching types, and its extern block must
+    declare functions the library exports, with the header's argument counts."""
+    rs = open(os.path.join(ROOT, "integration", "gpu.rs")).read()
+    rust_type = {"int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "uint8_t": "u8", "float": "f32", "GorderMolType": "GorderMolType"}
+    for name in ("GorderMolType", "GorderSetup", "GorderResults"):
+        body = re.search(r"#\[repr\(C\)\]\s*pub struct " + name + r" \{(.*?)\n\}", rs, re.S).group(1)
+        got = [(m.group(1), m.group(2).strip()) for m in re.finditer(r"pub (\w+): ([^,]+),", body)]
+        want = []
+        for var, typ, const, ptr, arr in _header_struct(name):
+            t = rust_type[typ]
+            if ptr:
+                t = ("*const " if const else "*mut ") + t
+            if arr:
+                t = f"[{t}; {arr}]"
+            want.append((var, t))
+        assert got == want, (name, [x for x in zip(got, want) if x[0] != x[1]][:3])
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(gorder_\w+)\s*\(([^)]*)\)\s*;", hdr)}
+    ext = re.search(r'extern "C" \{(.*?)\n\}', rs, re.S).group(1)
+    L = lib()
+    seen = 0
+    for m in re.finditer(r"pub fn (gorder_\w+)\(([^)]*)\)", ext):
+        fn, args = m.group(1), m.group(2)
+        assert fn in decl and hasattr(L, fn), fn
+        n_c = 0 if decl[fn].strip() in ("", "void") else decl[fn].count(",") + 1
+        n_rs = 0 if not args.strip() else args.count(",") + 1
+        assert n_c == n_rs, (fn, decl[fn], args)
+        seen += 1
+    assert seen >= 15
+    for name, val in re.findall(r"pub const (GORDER_[A-Z0-9_]+): i32 = (\d+);", rs):
+        m = re.search(r"\b" + name + r"\s*=\s*(\d+)", hdr) or re.search(r"#define " + name + r" (\d+)", hdr)
+        assert m and int(m.group(1)) == int(val), name
+
+
+def test_every_struct_field_offset_matches_c(tmp_path):
+    """sizeof / offsetof of EVERY field of GorderSetup / GorderMolType / GorderResults / GorderRaw as gcc lays them out ==
+    the ctypes mirror the tests and the bench drive the library with."""
+    import subprocess
+    structs = {"GorderSetup": abi.CGorderSetup, "GorderMolType": abi.CGorderMolType, "GorderResults": abi.CGorderResults, "GorderRaw": abi.CGorderRaw}
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "gorder_b200.h"\nint main(){\n'
+    order = []
+    for st in structs:
+        prog += f'printf("%zu\\n", sizeof({st}));\n'
+        order.append((st, None))
+        for var, *_ in _header_struct(st):
+            prog += f'printf("%zu\\n", offsetof({st}, {var}));\n'
+            order.append((st, var))
+    prog += "return 0;}\n"
+    src = tmp_path / "layout_all.c"
+    src.write_text(prog)
+    exe = tmp_path / "layout_all"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert len(out) == len(order)
+    for (st, var), val in zip(order, out):
+        if var is None:
+            assert C.sizeof(structs[st]) == val, st
+        else:
+            assert getattr(structs[st], var).offset == val, (st, var)
