@@ -18,6 +18,11 @@ SYMBOLS = [
     "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_stream",
     "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_xtc_scan", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device",
     "gorder_results_order", "gorder_results_convergence", "gorder_results_map", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
+    "gorder_topology_last_error", "gorder_system_from_tpr", "gorder_system_from_arrays", "gorder_system_free", "gorder_system_n_atoms", "gorder_system_n_bonds",
+    "gorder_system_tpx_version", "gorder_system_atoms", "gorder_system_bonds", "gorder_system_positions", "gorder_system_box", "gorder_system_set_bonds",
+    "gorder_system_read_bonds", "gorder_classify_bonds", "gorder_classify_ua", "gorder_classification_free", "gorder_classification_n_types",
+    "gorder_classification_moltypes", "gorder_classification_type_name", "gorder_classification_item_name", "gorder_classification_warning",
+    "gorder_classification_n_atoms_rel", "gorder_classification_atoms_rel",
     "gorder_gpu_reduce", "gorder_comm_unique_id", "gorder_comm_create", "gorder_gpu_reduce_comm", "gorder_comm_broadcast_leaflets", "gorder_comm_destroy",
 ]
 
@@ -75,6 +80,45 @@ def lib() -> C.CDLL:
     L.gorder_results_convergence.argtypes = [C.POINTER(abi.CGorderRaw), vp, i32, C.c_float, vp]
     L.gorder_results_map.argtypes = [vp, vp, i64, i32, C.c_float, vp]
     for name in ("gorder_results_order", "gorder_results_convergence", "gorder_results_map"):
+        getattr(L, name).restype = C.c_int
+    # structure / topology / classification (host only)
+    L.gorder_topology_last_error.restype = C.c_char_p
+    L.gorder_system_from_tpr.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.gorder_system_from_arrays.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), vp, vp, vp, C.POINTER(vp)]
+    L.gorder_system_free.argtypes = [vp]
+    L.gorder_system_free.restype = None
+    L.gorder_system_n_atoms.argtypes = [vp]
+    L.gorder_system_n_atoms.restype = i32
+    L.gorder_system_n_bonds.argtypes = [vp]
+    L.gorder_system_n_bonds.restype = i64
+    L.gorder_system_tpx_version.argtypes = [vp]
+    L.gorder_system_tpx_version.restype = i32
+    L.gorder_system_atoms.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.gorder_system_bonds.argtypes = [vp, vp]
+    L.gorder_system_positions.argtypes = [vp, vp, C.POINTER(i32)]
+    L.gorder_system_box.argtypes = [vp, vp, C.POINTER(i32)]
+    L.gorder_system_set_bonds.argtypes = [vp, vp, i64]
+    L.gorder_system_read_bonds.argtypes = [vp, C.c_char_p]
+    L.gorder_classify_bonds.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, C.POINTER(vp)]
+    L.gorder_classify_ua.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, C.POINTER(vp)]
+    L.gorder_classification_free.argtypes = [vp]
+    L.gorder_classification_free.restype = None
+    L.gorder_classification_n_types.argtypes = [vp]
+    L.gorder_classification_n_types.restype = i32
+    L.gorder_classification_moltypes.argtypes = [vp]
+    L.gorder_classification_moltypes.restype = vp
+    L.gorder_classification_type_name.argtypes = [vp, i32]
+    L.gorder_classification_type_name.restype = C.c_char_p
+    L.gorder_classification_item_name.argtypes = [vp, i32, i32]
+    L.gorder_classification_item_name.restype = C.c_char_p
+    L.gorder_classification_warning.argtypes = [vp]
+    L.gorder_classification_warning.restype = C.c_char_p
+    L.gorder_classification_n_atoms_rel.argtypes = [vp, i32]
+    L.gorder_classification_n_atoms_rel.restype = i32
+    L.gorder_classification_atoms_rel.argtypes = [vp, i32]
+    L.gorder_classification_atoms_rel.restype = C.POINTER(i32)
+    for name in ("gorder_system_from_tpr", "gorder_system_from_arrays", "gorder_system_atoms", "gorder_system_bonds", "gorder_system_positions",
+                 "gorder_system_box", "gorder_system_set_bonds", "gorder_system_read_bonds", "gorder_classify_bonds", "gorder_classify_ua"):
         getattr(L, name).restype = C.c_int
     L.gorder_gpu_fence.argtypes = [vp]
     L.gorder_gpu_fence.restype = C.c_int

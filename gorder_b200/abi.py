@@ -53,6 +53,16 @@ ERR_NO_DEVICE = 30
 ERR_CUDA = 31
 ERR_OUT_OF_MEMORY = 32
 ERR_NCCL = 33
+ERR_IO = 40
+ERR_TPR_FORMAT = 41
+ERR_BONDS_PARSE = 42
+ERR_BONDS_ATOM_NOT_FOUND = 43
+ERR_BONDS_SELF = 44
+ERR_TOPOLOGY_NO_HEAD = 45
+ERR_TOPOLOGY_MULTIPLE_HEADS = 46
+ERR_TOPOLOGY_NO_METHYL = 47
+ERR_TOPOLOGY_INCONSISTENT_METHYLS = 48
+ERR_TOPOLOGY_NO_UA_CARBONS = 49
 
 ERROR_NAMES = {
     ERR_UNDEFINED_BOX: "AnalysisError::UndefinedBox",
@@ -74,6 +84,16 @@ ERROR_NAMES = {
     ERR_CUDA: "CUDA error",
     ERR_OUT_OF_MEMORY: "out of device memory",
     ERR_NCCL: "NCCL unavailable or a collective failed",
+    ERR_IO: "file missing or unreadable",
+    ERR_TPR_FORMAT: "not a supported TPR file",
+    ERR_BONDS_PARSE: "BondsError::CouldNotParse",
+    ERR_BONDS_ATOM_NOT_FOUND: "BondsError::AtomNotFound",
+    ERR_BONDS_SELF: "BondsError::SelfBonding",
+    ERR_TOPOLOGY_NO_HEAD: "TopologyError::NoHead",
+    ERR_TOPOLOGY_MULTIPLE_HEADS: "TopologyError::MultipleHeads",
+    ERR_TOPOLOGY_NO_METHYL: "TopologyError::NoMethyl",
+    ERR_TOPOLOGY_INCONSISTENT_METHYLS: "TopologyError::InconsistentNumberOfMethyls",
+    ERR_TOPOLOGY_NO_UA_CARBONS: "TopologyError::NoUACarbons",
 }
 
 _i32p = C.POINTER(C.c_int32)

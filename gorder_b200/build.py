@@ -17,6 +17,7 @@ HEADERS = [
     os.path.join(_HERE, "csrc", "gorder_xtc.inl"),
     os.path.join(_HERE, "csrc", "gorder_results.inl"),
     os.path.join(_HERE, "csrc", "gorder_multi.inl"),
+    os.path.join(_HERE, "csrc", "gorder_topology.inl"),
     os.path.join(_HERE, "csrc", "gorder_engine.cuh"),
     os.path.join(_HERE, "csrc", "gorder_math.cuh"),
     os.path.join(_HERE, "..", "include", "gorder_b200.h"),
@@ -45,14 +46,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the engine if the shared library is missing or older than its sources."""
     if not force and not is_stale():
         return SO_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + SOURCES
+    tmp = f"{SO_PATH}.tmp.{os.getpid()}"   # never leave a half-written library where a loader (or a snapshot) can see it
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
     env = dict(os.environ)
     # the image exports CC=/opt/gcc/bin/gcc; nvcc must use the system host compiler
     res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout)
+    os.replace(tmp, SO_PATH)
     return SO_PATH
 
 

@@ -7,13 +7,16 @@
 // There is NO CPU fallback: every entry point fails with GORDER_ERR_NO_DEVICE / GORDER_ERR_CUDA
 // when the device is not usable.
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "gorder_kernels.cuh"
@@ -58,6 +61,7 @@ struct Switches {
     bool no_inline_leaflets = false;   // GORDER_NO_INLINE_LEAFLETS: separate leaflet_assign_kernel for Global-every-frame
     bool no_overlap = false;     // GORDER_NO_OVERLAP: one stream instead of the pre / main / post pipeline
     bool ua_exact = false;       // GORDER_UA_EXACT: bit-exact hydrogen construction everywhere
+    bool no_sorted_normals = false;   // GORDER_NO_SORTED_NORMALS: one lane per lipid in molecule order (dynamic_normal_cell_kernel)
     bool verbose = false;        // GORDER_VERBOSE
     int center_blocks = 0, center_sub = 0;   // GORDER_CENTER_BLOCKS, GORDER_CENTER_SUB
     int cell_min_heads = 2048, lcell_min_atoms = 4096;   // GORDER_CELL_MIN_HEADS, GORDER_LCELL_MIN_ATOMS
@@ -70,6 +74,7 @@ struct Switches {
         w.no_spec = flag("GORDER_NO_SPEC"); w.no_spec_leftover = flag("GORDER_NO_SPEC_LEFTOVER");
         w.no_inline_leaflets = flag("GORDER_NO_INLINE_LEAFLETS"); w.no_overlap = flag("GORDER_NO_OVERLAP");
         w.ua_exact = flag("GORDER_UA_EXACT"); w.verbose = flag("GORDER_VERBOSE");
+        w.no_sorted_normals = flag("GORDER_NO_SORTED_NORMALS");
         w.center_blocks = num("GORDER_CENTER_BLOCKS", 0); w.center_sub = num("GORDER_CENTER_SUB", 0);
         w.cell_min_heads = num("GORDER_CELL_MIN_HEADS", 2048); w.lcell_min_atoms = num("GORDER_LCELL_MIN_ATOMS", 4096);
         return w;
@@ -148,6 +153,8 @@ struct GorderHandle {
 
     // cell list of the normal heads (K4)
     bool use_cells = false;
+    bool normals_sorted = false;   // dynamic_normal_sorted_kernel: every analysed lipid's normal head is in the NormalHeads group
+    int *d_head_molpad = nullptr;  // NormalHeads member -> padded molecule whose normal head it is (-1: none)
     int cells_cap = 0;
     int *d_head_cell = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr;
     float4 *d_cell_sorted = nullptr;   // head positions (+ index) in cell order
@@ -566,9 +573,17 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
             cell_count_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, da, h->d_head_cell, h->d_cell_count, h->cells_cap);
             cell_scan_kernel<<<nf, 1024, 0, h->stream>>>(h->view, da, h->d_cell_count, h->d_cell_start, h->cells_cap);
             cell_fill_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, da, h->d_head_cell, h->d_cell_count, h->d_cell_start, h->d_cell_sorted, h->cells_cap);
-            dim3 grid((h->n_molpad + 127) / 128, nf);
-            dynamic_normal_cell_kernel<<<grid, 128, 0, h->stream>>>(h->view, d_planes, da, h->d_molpad_type, h->d_cell_start, h->d_cell_sorted,
-                                                                   h->cells_cap, h->d_normals, h->d_normal_npoints);
+            if (h->normals_sorted) {
+                // lanes walk the cell-sorted heads; molecules without a head in the list (padding) keep NaN
+                CK(cudaMemsetAsync(h->d_normals, 0xff, (size_t)nf * 3 * h->n_molpad * sizeof(float), h->stream));
+                dim3 grid((nh + 127) / 128, nf);
+                dynamic_normal_sorted_kernel<<<grid, 128, 0, h->stream>>>(h->view, da, h->d_head_molpad, h->d_cell_start, h->d_cell_sorted,
+                                                                         h->cells_cap, h->d_normals, h->d_normal_npoints);
+            } else {
+                dim3 grid((h->n_molpad + 127) / 128, nf);
+                dynamic_normal_cell_kernel<<<grid, 128, 0, h->stream>>>(h->view, d_planes, da, h->d_molpad_type, h->d_cell_start, h->d_cell_sorted,
+                                                                       h->cells_cap, h->d_normals, h->d_normal_npoints);
+            }
             h->n_launches += 3;
         } else if (s.normal_mode == GORDER_NORMAL_DYNAMIC) {
             dim3 grid((h->n_molpad + 127) / 128, nf);
@@ -1045,6 +1060,24 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
             if ((rc = dev_alloc(h, &h->d_cell_sorted, B * (size_t)s->n_normal_heads))) return rc;
             if ((rc = dev_alloc(h, &h->d_cell_count, B * (size_t)h->cells_cap))) return rc;
             if ((rc = dev_alloc(h, &h->d_cell_start, B * ((size_t)h->cells_cap + 1)))) return rc;
+            // NormalHeads member -> the padded molecule whose normal head it is
+            std::unordered_map<int, int> head_of;
+            size_t need = 0;
+            for (int t = 0; t < s->n_moltypes; t++) {
+                const int rel = s->moltypes[t].normal_head_rel;
+                if (rel < 0) continue;
+                for (int m = 0; m < h->types[t].n_mol; m++, need++) head_of[h->mol_base[t][m] + rel] = h->types[t].molpad0 + m;
+            }
+            std::vector<int> hm(s->n_normal_heads, -1);
+            std::vector<char> seen(h->n_molpad, 0);
+            size_t found = 0;
+            for (int i = 0; i < s->n_normal_heads; i++) {
+                auto it = head_of.find(s->normal_heads[i]);
+                if (it == head_of.end() || seen[it->second]) continue;   // a repeated member counts in the clouds, not as a second lipid
+                seen[it->second] = 1; hm[i] = it->second; found++;
+            }
+            h->normals_sorted = found == need && !h->sw.no_sorted_normals;
+            if ((rc = dev_upload(h, &h->d_head_molpad, hm))) return rc;
         }
     }
     if (s->leaflet_mode == GORDER_LEAFLET_LOCAL && s->handle_pbc) {
@@ -1529,3 +1562,4 @@ int64_t gorder_gpu_error_detail(GorderHandle *h) { return h ? h->err_detail : -1
 #include "gorder_xtc.inl"
 #include "gorder_results.inl"
 #include "gorder_multi.inl"
+#include "gorder_topology.inl"

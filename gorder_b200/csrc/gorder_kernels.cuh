@@ -464,9 +464,13 @@ __global__ void __launch_bounds__(256) leaflet_assign_kernel(DeviceView v, const
 __device__ __forceinline__ void jacobi_smallest(float a00, float a01, float a02, float a11, float a12, float a22, f3 &out) {
     float A[3][3] = {{a00, a01, a02}, {a01, a11, a12}, {a02, a12, a22}};
     float V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    // Cyclic Jacobi converges quadratically: once the off-diagonal part is at f32 resolution of the diagonal, one more
+    // sweep finishes the eigenvectors.  (Twelve unconditional sweeps, unrolled, were 22 % of the normals kernel.)
+#pragma unroll 1
     for (int sweep = 0; sweep < 12; sweep++) {
-        float off = fabsf(A[0][1]) + fabsf(A[0][2]) + fabsf(A[1][2]);
+        const float off = fabsf(A[0][1]) + fabsf(A[0][2]) + fabsf(A[1][2]);
         if (off < 1e-30f) break;
+        const bool last = off <= 3e-7f * (fabsf(A[0][0]) + fabsf(A[1][1]) + fabsf(A[2][2]));
 #pragma unroll
         for (int p = 0; p < 2; p++)
 #pragma unroll
@@ -482,6 +486,7 @@ __device__ __forceinline__ void jacobi_smallest(float a00, float a01, float a02,
 #pragma unroll
                 for (int k = 0; k < 3; k++) { float x = V[k][p], y = V[k][q]; V[k][p] = c * x - s * y; V[k][q] = s * x + c * y; }
             }
+        if (last) break;
     }
     int k = 0;
     if (A[1][1] < A[k][k]) k = 1;
@@ -800,10 +805,13 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(DeviceView v, const Fra
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < nc; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const int x = i < nc ? cnt[i] : 0;
-        int incl = x;
+    constexpr int kPer = 8;   // consecutive cells per thread: 8192 cells per pass of the CTA
+    for (int base = 0; base < nc; base += blockDim.x * kPer) {
+        const int i0 = base + threadIdx.x * kPer;
+        int x[kPer], tot = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) { x[j] = i0 + j < nc ? cnt[i0 + j] : 0; tot += x[j]; }
+        int incl = tot;
         for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
@@ -813,10 +821,14 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(DeviceView v, const Fra
             s_warp[lane] = w;
         }
         __syncthreads();
-        const int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - x;
-        if (i < nc) { st[i] = excl; cnt[i] = 0; }   // the counts become the fill cursors
+        int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - tot;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            if (i0 + j < nc) { st[i0 + j] = excl; cnt[i0 + j] = 0; }   // the counts become the fill cursors
+            excl += x[j];
+        }
         __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = excl + x;
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl;
         __syncthreads();
     }
     if (threadIdx.x == 0) st[nc] = s_carry;
@@ -916,6 +928,109 @@ __global__ void __launch_bounds__(128) dynamic_normal_cell_kernel(DeviceView v, 
     const double inv = 1.0 / cnt, mx = sx * inv, my = sy * inv, mz = sz * inv;
     f3 nrm;
     pca_normal(xx - cnt * mx * mx, xy - cnt * mx * my, xz - cnt * mx * mz, yy - cnt * my * my, yz - cnt * my * mz, zz - cnt * mz * mz, v.collect_normals != 0, nrm);
+    nx[0] = nrm.x; nx[v.n_molpad] = nrm.y; nx[2 * (size_t)v.n_molpad] = nrm.z;
+}
+
+// K4, sorted variant (default when every analysed lipid's head is a member of the NormalHeads group).
+// dynamic_normal_cell_kernel above gives lane j the lipid j, so the lanes of a warp sit in unrelated cells: their 27 candidate
+// loops have unrelated trip counts and the f64 accumulation runs whenever ANY lane accepts -- ncu: 17 of 32 lanes active in
+// the candidate loop, 10 of 32 in the accepting branch, 67 % of the kernel's instructions there.  Here
+//   * lane k takes the k-th head of the CELL-SORTED list (cell_fill_kernel): the lanes of a warp share a handful of home
+//     cells, hence candidate ranges, and `sorted_pos[k]` is the lipid's own head (coalesced);
+//   * the three z cells of a column are one contiguous run of the sorted list (cells are numbered z-fastest), split only at
+//     the periodic boundary: 9 - 18 ranges instead of 27 cell look-ups;
+//   * stage 1 only filters: a candidate that passes the cheap image-by-cell-offset bound (or cannot use it) has its index
+//     appended to the lane's list in shared memory; stage 2 runs the exact fold, the exact `<` and the f64 moments over the
+//     list, ~22 entries that nearly all pass, so the lanes stay together.
+// Same arithmetic per accepted head as the kernel above (the sums are f64: independent of the order to ~1e-13).
+constexpr int kNormCap = 48;   // list entries per lane (a full list is drained early)
+
+struct NormAcc {
+    int cnt;
+    double sx, sy, sz, xx, xy, xz, yy, yz, zz;
+};
+__device__ __forceinline__ void normal_drain(const int *lst, int nl, const float4 *__restrict__ srt, const f3 &ref, const FrameAux &a,
+                                             float g0, float g1, float g2, float radius, NormAcc &s) {
+    for (int j = 0; j < nl; j++) {
+        const float4 q = __ldg(srt + lst[j * 128]);
+        f3 d;   // Vector3D::vector_to(reference, head)
+        d.x = min_image_g(__fsub_rn(q.x, ref.x), a.L[0], a.half[0], g0);
+        d.y = min_image_g(__fsub_rn(q.y, ref.y), a.L[1], a.half[1], g1);
+        d.z = min_image_g(__fsub_rn(q.z, ref.z), a.L[2], a.half[2], g2);
+        if (norm_ref(d) < radius) {
+            s.cnt++;
+            s.sx += d.x; s.sy += d.y; s.sz += d.z;
+            s.xx += (double)d.x * d.x; s.xy += (double)d.x * d.y; s.xz += (double)d.x * d.z;
+            s.yy += (double)d.y * d.y; s.yz += (double)d.y * d.z; s.zz += (double)d.z * d.z;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) dynamic_normal_sorted_kernel(DeviceView v, const FrameAux *__restrict__ aux, const int *__restrict__ head_molpad,
+                                                                    const int *__restrict__ cell_start, const float4 *__restrict__ sorted_pos,
+                                                                    int cells_cap, float *__restrict__ normals, int *__restrict__ normal_npoints) {
+    __shared__ int s_list[kNormCap * 128];
+    const int f = blockIdx.y, nh = v.normal_heads.n;
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= nh) return;
+    const float4 *srt = sorted_pos + (size_t)f * nh;
+    const float4 me = __ldg(srt + k);
+    const int wi = __float_as_int(me.w);
+    const int mp = head_molpad[wi >= 0 ? wi : ~wi];
+    if (mp < 0) return;   // a head that only takes part in the clouds of others
+    const FrameAux &a = aux[f];
+    int n[3];
+    cell_dims(a, v.dynamic_radius, n);
+    const f3 ref = mk3(me.x, me.y, me.z);
+    const int c0[3] = {cell_coord(ref.x, a.L[0], n[0]), cell_coord(ref.y, a.L[1], n[1]), cell_coord(ref.z, a.L[2], n[2])};
+    const int *st = cell_start + (size_t)f * (cells_cap + 1);
+    const float g0 = 0.99f * a.half[0], g1 = 0.99f * a.half[1], g2 = 0.99f * a.half[2];
+    const float radius = v.dynamic_radius;
+    const bool quick = wi >= 0 && n[0] >= 3 && n[1] >= 3 && n[2] >= 3;   // wi >= 0: the reference lies inside [0, L)
+    const float r_hi = radius + 1e-5f * radius + 6e-7f * fmaxf(a.L[0], fmaxf(a.L[1], a.L[2]));
+    const float r2hi = r_hi * r_hi;
+    NormAcc acc{};
+    int *lst = s_list + threadIdx.x;
+    int nl = 0;
+    const int lo0 = n[0] >= 3 ? -1 : 0, hi0 = n[0] >= 3 ? 1 : n[0] - 1;
+    const int lo1 = n[1] >= 3 ? -1 : 0, hi1 = n[1] >= 3 ? 1 : n[1] - 1;
+    // z runs of a column: the cells inside [0, n2) as one run, a wrapped cell below / above as a run of its own
+    const bool z3 = n[2] >= 3;
+    const int za = z3 ? max(c0[2] - 1, 0) : 0, zb = z3 ? min(c0[2] + 1, n[2] - 1) : n[2] - 1;
+    const int zw = !z3 ? -1 : (c0[2] == 0 ? n[2] - 1 : (c0[2] == n[2] - 1 ? 0 : -1));   // the wrapped cell, if any
+    const float zshift = c0[2] == 0 ? a.L[2] : -a.L[2];
+    for (int dx = lo0; dx <= hi0; dx++) {
+        const int cx = n[0] >= 3 ? (c0[0] + dx + n[0]) % n[0] : dx;
+        const float rsx = ref.x + (c0[0] + dx < 0 ? a.L[0] : (c0[0] + dx >= n[0] ? -a.L[0] : 0.0f));
+        for (int dy = lo1; dy <= hi1; dy++) {
+            const int cy = n[1] >= 3 ? (c0[1] + dy + n[1]) % n[1] : dy;
+            const float rsy = ref.y + (c0[1] + dy < 0 ? a.L[1] : (c0[1] + dy >= n[1] ? -a.L[1] : 0.0f));
+            const int cb = (cx * n[1] + cy) * n[2];
+            for (int part = 0; part < (zw >= 0 ? 2 : 1); part++) {
+                const int kb = part == 0 ? st[cb + za] : st[cb + zw], ke = part == 0 ? st[cb + zb + 1] : st[cb + zw + 1];
+                const float rsz = part == 0 ? ref.z : ref.z + zshift;
+                for (int kk = kb; kk < ke; kk++) {
+                    const float4 q = __ldg(srt + kk);
+                    if (quick && __float_as_int(q.w) >= 0) {
+                        const float ex = q.x - rsx, ey = q.y - rsy, ez = q.z - rsz;
+                        if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > r2hi) continue;
+                    }
+                    if (nl == kNormCap) { normal_drain(lst, nl, srt, ref, a, g0, g1, g2, radius, acc); nl = 0; }
+                    lst[nl * 128] = kk;
+                    nl++;
+                }
+            }
+        }
+    }
+    normal_drain(lst, nl, srt, ref, a, g0, g1, g2, radius, acc);
+    float *nx = normals + ((size_t)f * 3) * v.n_molpad + mp;
+    const int cnt = acc.cnt;
+    normal_npoints[(size_t)f * v.n_molpad + mp] = cnt;
+    if (cnt < 3) { nx[0] = CUDART_NAN_F; nx[v.n_molpad] = CUDART_NAN_F; nx[2 * (size_t)v.n_molpad] = CUDART_NAN_F; return; }
+    const double inv = 1.0 / cnt, mx = acc.sx * inv, my = acc.sy * inv, mz = acc.sz * inv;
+    f3 nrm;
+    pca_normal(acc.xx - cnt * mx * mx, acc.xy - cnt * mx * my, acc.xz - cnt * mx * mz, acc.yy - cnt * my * my, acc.yz - cnt * my * mz,
+               acc.zz - cnt * mz * mz, v.collect_normals != 0, nrm);
     nx[0] = nrm.x; nx[v.n_molpad] = nrm.y; nx[2 * (size_t)v.n_molpad] = nrm.z;
 }
 

@@ -109,7 +109,18 @@ enum {
     GORDER_ERR_NO_DEVICE = 30,                 /* no usable CUDA device: there is NO CPU fallback */
     GORDER_ERR_CUDA = 31,
     GORDER_ERR_OUT_OF_MEMORY = 32,
-    GORDER_ERR_NCCL = 33                       /* NCCL missing at run time, or a collective failed */
+    GORDER_ERR_NCCL = 33,                      /* NCCL missing at run time, or a collective failed */
+    /* structure / topology / classification (host only; gorder_system_*, gorder_classify_*) */
+    GORDER_ERR_IO = 40,                        /* file missing or unreadable (BondsError::FileNotFound / CouldNotReadLine) */
+    GORDER_ERR_TPR_FORMAT = 41,                /* not a TPR file, unsupported tpx version, truncated or inconsistent */
+    GORDER_ERR_BONDS_PARSE = 42,               /* BondsError::CouldNotParse */
+    GORDER_ERR_BONDS_ATOM_NOT_FOUND = 43,      /* BondsError::AtomNotFound */
+    GORDER_ERR_BONDS_SELF = 44,                /* BondsError::SelfBonding */
+    GORDER_ERR_TOPOLOGY_NO_HEAD = 45,          /* TopologyError::NoHead(first atom of the molecule) */
+    GORDER_ERR_TOPOLOGY_MULTIPLE_HEADS = 46,   /* TopologyError::MultipleHeads */
+    GORDER_ERR_TOPOLOGY_NO_METHYL = 47,        /* TopologyError::NoMethyl */
+    GORDER_ERR_TOPOLOGY_INCONSISTENT_METHYLS = 48, /* TopologyError::InconsistentNumberOfMethyls */
+    GORDER_ERR_TOPOLOGY_NO_UA_CARBONS = 49     /* TopologyError::NoUACarbons */
 };
 
 /* ---- setup ------------------------------------------------------------------------------ */
@@ -423,6 +434,58 @@ int gorder_results_order(const GorderRaw *raw, const int32_t *slots, int32_t n_s
 int gorder_results_convergence(const GorderRaw *raw, const int32_t *slots, int32_t n_sel, float sign, float *out /* [n_frames][3] */);
 /* Order-map bins (ordermap.rs / converter.rs:159-308): out[i] = sign * (sum[i] / 1e6) / count[i], NaN below min_samples. */
 int gorder_results_map(const int64_t *map_sum, const uint64_t *map_count, int64_t n, int32_t min_samples, float sign, float *out);
+
+/* ---- structure, topology and molecule classification, the step before the path -----------------
+ * Host only: no GPU, no handle.  Replaces, for a host without the Rust front end, read_structure_and_topology
+ * (structure.rs:27-88: groan_rs System::from_file on a TPR -> minitpr 0.2.3; read_bonds :91-165) and
+ * MoleculesClassifier::classify (topology/classify.rs:45-315, 318-580).  Atom groups are index lists: parsing the selection
+ * language stays with the host.  gorder_topology_last_error() describes the last failure on the calling thread. */
+typedef struct GorderSystem GorderSystem;
+typedef struct GorderClassification GorderClassification;
+const char *gorder_topology_last_error(void);
+/* TPR of GROMACS 5.1 .. 2022 (tpx 103 .. 127, single or double precision): atoms (name, residue name / number, atomic number,
+ * mass, charge), bonds (BONDS .. RESTRBONDS, CONSTR, CONSTRNC, the O-H pairs of SETTLE, intermolecular lists), box and
+ * coordinates.  Anything else -> GORDER_ERR_TPR_FORMAT. */
+int gorder_system_from_tpr(const char *path, GorderSystem **out);
+/* A structure read by the host (GRO / PDB ...): names and residue numbers as arrays; xyz [n][3] and box9 may be NULL. */
+int gorder_system_from_arrays(int32_t n_atoms, const char *const *atom_names, const char *const *res_names, const int32_t *res_ids,
+                              const float *xyz, const float *box9, GorderSystem **out);
+void gorder_system_free(GorderSystem *s);
+int32_t gorder_system_n_atoms(const GorderSystem *s);
+int64_t gorder_system_n_bonds(const GorderSystem *s);
+int32_t gorder_system_tpx_version(const GorderSystem *s);   /* 0 unless read from a TPR */
+/* names: [n][8] NUL-padded; any output may be NULL */
+int gorder_system_atoms(const GorderSystem *s, char *atom_names8, char *res_names8, int32_t *res_ids, int32_t *atomic_numbers, float *masses,
+                        float *charges);
+int gorder_system_bonds(const GorderSystem *s, int32_t *pairs /* [n_bonds][2], i < j, sorted */);
+int gorder_system_positions(const GorderSystem *s, float *xyz /* [n][3] */, int32_t *has);
+int gorder_system_box(const GorderSystem *s, float *box9, int32_t *has);
+/* Replace all bonds: by pairs of atom indices (from 0), or from a bonds file (structure.rs:91-165: `i j k ...`, serial
+ * numbers from 1, '#' comments; GORDER_ERR_IO / _BONDS_PARSE / _BONDS_ATOM_NOT_FOUND / _BONDS_SELF as BondsError). */
+int gorder_system_set_bonds(GorderSystem *s, const int32_t *pairs, int64_t n_pairs);
+int gorder_system_read_bonds(GorderSystem *s, const char *bonds_file);
+/* Molecule types for AA (group1 = heavy atoms, group2 = hydrogens) and CG (group1 = group2 = beads): classify.rs:53-76.
+ * heads / methyls / normal_heads: the leaflet and dynamic-normal groups, NULL when unused (common.rs:345-375: exactly one
+ * head per molecule; leaflets.rs:743-775: the same positive number of methyls in every molecule of a type).
+ * As in the reference (classify.rs:297-315) a system without analysable molecules, or with a molecule type that has no order
+ * bond, yields ZERO types and a warning, not an error. */
+int gorder_classify_bonds(const GorderSystem *s, const int32_t *group1, int32_t n1, const int32_t *group2, int32_t n2,
+                          const int32_t *heads, int32_t n_heads, const int32_t *methyls, int32_t n_methyls,
+                          const int32_t *normal_heads, int32_t n_normal_heads, GorderClassification **out);
+/* UA (classify.rs:77-90; carbon typing uaorder.rs:580-665; `ignore` = atoms that do not count as bonded). */
+int gorder_classify_ua(const GorderSystem *s, const int32_t *saturated, int32_t n_sat, const int32_t *unsaturated, int32_t n_unsat,
+                       const int32_t *ignore, int32_t n_ignore, const int32_t *heads, int32_t n_heads, const int32_t *methyls, int32_t n_methyls,
+                       const int32_t *normal_heads, int32_t n_normal_heads, GorderClassification **out);
+void gorder_classification_free(GorderClassification *c);
+int32_t gorder_classification_n_types(const GorderClassification *c);
+/* [n_types], ready for GorderSetup.moltypes (manual tables unset); valid until gorder_classification_free */
+const GorderMolType *gorder_classification_moltypes(const GorderClassification *c);
+const char *gorder_classification_type_name(const GorderClassification *c, int32_t type);   /* "POPC", "POPE-POPG", "POPC2" */
+/* "POPC C22 (20) - POPC H2R (21)" for bond type i, "POPC C22 (20)" for united-atom carbon i */
+const char *gorder_classification_item_name(const GorderClassification *c, int32_t type, int32_t item);
+const char *gorder_classification_warning(const GorderClassification *c);   /* "" when molecule types were found */
+int32_t gorder_classification_n_atoms_rel(const GorderClassification *c, int32_t type);
+const int32_t *gorder_classification_atoms_rel(const GorderClassification *c, int32_t type);   /* relative indices of the molecule's atoms */
 
 /* The host stage of gorder_gpu_run_xtc_device without a GPU: walks the control bits of frames first .. first + count - 1
  * and reports per frame its groups (one "large" atom + its run of small ones) and the bookmarks the kernel would get.  A
