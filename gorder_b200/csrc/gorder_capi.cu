@@ -156,7 +156,7 @@ struct GorderHandle {
     bool normals_sorted = false;   // dynamic_normal_sorted_kernel: every analysed lipid's normal head is in the NormalHeads group
     int *d_head_molpad = nullptr;  // NormalHeads member -> padded molecule whose normal head it is (-1: none)
     int cells_cap = 0;
-    int *d_head_cell = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr;
+    int *d_head_cell = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_span = nullptr;
     float4 *d_cell_sorted = nullptr;   // head positions (+ index) in cell order
 
     // 2-D cell list of the membrane atoms (Local leaflets)
@@ -527,7 +527,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
             lcell_count_kernel<<<gm, 256, 0, sp>>>(h->view, d_planes, da, dl_assign, h->d_matom_cell, h->d_lcell_count, h->lcells_cap);
             lcell_scan_kernel<<<n_assign, 1024, 0, sp>>>(h->view, da, dl_assign, h->d_lcell_count, h->d_lcell_start, h->lcells_cap);
             lcell_fill_kernel<<<gm, 256, 0, sp>>>(h->view, d_planes, dl_assign, h->d_matom_cell, h->d_lcell_count, h->d_lcell_start, h->d_lcell_sorted, h->lcells_cap);
-            h->n_launches += 3;
+            h->n_launches += 4;
         }
         dim3 grid((h->n_molpad + 255) / 256, n_assign);
         if (h->spherical) {   // gorder_spherical.cuh
@@ -571,7 +571,8 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
             CK(cudaMemsetAsync(h->d_cell_count, 0, (size_t)nf * h->cells_cap * sizeof(int), h->stream));
             dim3 gh((nh + 255) / 256, nf);
             cell_count_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, da, h->d_head_cell, h->d_cell_count, h->cells_cap);
-            cell_scan_kernel<<<nf, 1024, 0, h->stream>>>(h->view, da, h->d_cell_count, h->d_cell_start, h->cells_cap);
+            cell_span_sum_kernel<<<dim3(kScanBlocks, nf), 1024, 0, h->stream>>>(h->view, da, h->d_cell_count, h->d_cell_span, h->cells_cap);
+            cell_scan_kernel<<<dim3(kScanBlocks, nf), 1024, 0, h->stream>>>(h->view, da, h->d_cell_count, h->d_cell_start, h->d_cell_span, h->cells_cap);
             cell_fill_kernel<<<gh, 256, 0, h->stream>>>(h->view, d_planes, da, h->d_head_cell, h->d_cell_count, h->d_cell_start, h->d_cell_sorted, h->cells_cap);
             if (h->normals_sorted) {
                 // lanes walk the cell-sorted heads; molecules without a head in the list (padding) keep NaN
@@ -1060,6 +1061,7 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
             if ((rc = dev_alloc(h, &h->d_cell_sorted, B * (size_t)s->n_normal_heads))) return rc;
             if ((rc = dev_alloc(h, &h->d_cell_count, B * (size_t)h->cells_cap))) return rc;
             if ((rc = dev_alloc(h, &h->d_cell_start, B * ((size_t)h->cells_cap + 1)))) return rc;
+            if ((rc = dev_alloc(h, &h->d_cell_span, B * (size_t)kScanBlocks))) return rc;
             // NormalHeads member -> the padded molecule whose normal head it is
             std::unordered_map<int, int> head_of;
             size_t need = 0;

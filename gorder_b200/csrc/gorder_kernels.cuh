@@ -793,45 +793,69 @@ __global__ void __launch_bounds__(256) cell_count_kernel(DeviceView v, const flo
     atomicAdd(&cell_count[(size_t)f * cells_cap + c], 1);
 }
 
-__global__ void __launch_bounds__(1024) cell_scan_kernel(DeviceView v, const FrameAux *__restrict__ aux, int *__restrict__ cell_count,
-                                                         int *__restrict__ cell_start, int cells_cap) {
-    const int f = blockIdx.x;
+// Exclusive scan of the cell counts, two levels: a CTA owns kScanSpan consecutive cells of one frame (a vesicle in a big box
+// has 2e5 cells, mostly empty: one CTA per frame walked them in 23 passes, 15 us per frame of pure latency).
+constexpr int kScanPer = 8;                      // consecutive cells per thread
+constexpr int kScanSpan = 1024 * kScanPer;       // cells per CTA
+constexpr int kScanBlocks = (kCellBudget + kScanSpan - 1) / kScanSpan;   // CTAs per frame (32)
+
+__global__ void __launch_bounds__(1024) cell_span_sum_kernel(DeviceView v, const FrameAux *__restrict__ aux, const int *__restrict__ cell_count,
+                                                             int *__restrict__ span_sum, int cells_cap) {
+    const int f = blockIdx.y;
     int n[3];
     cell_dims(aux[f], v.dynamic_radius, n);
     const int nc = n[0] * n[1] * n[2];
+    const int i0 = blockIdx.x * kScanSpan + threadIdx.x * kScanPer;
+    const int *cnt = cell_count + (size_t)f * cells_cap;
+    int tot = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPer; j++) tot += i0 + j < nc ? cnt[i0 + j] : 0;
+    __shared__ int s_warp[32];
+    tot = __reduce_add_sync(0xffffffffu, tot);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int w = __reduce_add_sync(0xffffffffu, s_warp[threadIdx.x]);
+        if (threadIdx.x == 0) span_sum[f * kScanBlocks + blockIdx.x] = w;
+    }
+}
+
+__global__ void __launch_bounds__(1024) cell_scan_kernel(DeviceView v, const FrameAux *__restrict__ aux, int *__restrict__ cell_count,
+                                                         int *__restrict__ cell_start, const int *__restrict__ span_sum, int cells_cap) {
+    const int f = blockIdx.y;
+    int n[3];
+    cell_dims(aux[f], v.dynamic_radius, n);
+    const int nc = n[0] * n[1] * n[2];
+    if (blockIdx.x * kScanSpan >= nc) return;
     int *cnt = cell_count + (size_t)f * cells_cap, *st = cell_start + (size_t)f * (cells_cap + 1);
     __shared__ int s_warp[32];
     __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kPer = 8;   // consecutive cells per thread: 8192 cells per pass of the CTA
-    for (int base = 0; base < nc; base += blockDim.x * kPer) {
-        const int i0 = base + threadIdx.x * kPer;
-        int x[kPer], tot = 0;
-#pragma unroll
-        for (int j = 0; j < kPer; j++) { x[j] = i0 + j < nc ? cnt[i0 + j] : 0; tot += x[j]; }
-        int incl = tot;
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = s_warp[lane];
-            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - tot;
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            if (i0 + j < nc) { st[i0 + j] = excl; cnt[i0 + j] = 0; }   // the counts become the fill cursors
-            excl += x[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = excl;
-        __syncthreads();
+    if (warp == 0) {   // cells in the spans before this one
+        const int w = __reduce_add_sync(0xffffffffu, lane < (int)blockIdx.x ? span_sum[f * kScanBlocks + lane] : 0);
+        if (lane == 0) s_carry = w;
     }
-    if (threadIdx.x == 0) st[nc] = s_carry;
+    const int i0 = blockIdx.x * kScanSpan + threadIdx.x * kScanPer;
+    int x[kScanPer], tot = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPer; j++) { x[j] = i0 + j < nc ? cnt[i0 + j] : 0; tot += x[j]; }
+    int incl = tot;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - tot;
+#pragma unroll
+    for (int j = 0; j < kScanPer; j++) {
+        if (i0 + j < nc) { st[i0 + j] = excl; cnt[i0 + j] = 0; }   // the counts become the fill cursors
+        excl += x[j];
+    }
+    if (i0 <= nc - 1 && nc - 1 < i0 + kScanPer) st[nc] = excl;      // the thread that owns the last cell closes the table
 }
 
 __global__ void __launch_bounds__(256) cell_fill_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux, const int *__restrict__ head_cell,
@@ -1000,17 +1024,26 @@ __global__ void __launch_bounds__(128) dynamic_normal_sorted_kernel(DeviceView v
     const int zw = !z3 ? -1 : (c0[2] == 0 ? n[2] - 1 : (c0[2] == n[2] - 1 ? 0 : -1));   // the wrapped cell, if any
     const float zshift = c0[2] == 0 ? a.L[2] : -a.L[2];
     for (int dx = lo0; dx <= hi0; dx++) {
-        const int cx = n[0] >= 3 ? (c0[0] + dx + n[0]) % n[0] : dx;
-        const float rsx = ref.x + (c0[0] + dx < 0 ? a.L[0] : (c0[0] + dx >= n[0] ? -a.L[0] : 0.0f));
+        int cx = dx;
+        float rsx = ref.x;
+        if (n[0] >= 3) {   // neighbour cell and the image of the reference next to it (no division: |dx| <= 1)
+            cx = c0[0] + dx;
+            if (cx < 0) { cx += n[0]; rsx += a.L[0]; } else if (cx >= n[0]) { cx -= n[0]; rsx -= a.L[0]; }
+        }
         for (int dy = lo1; dy <= hi1; dy++) {
-            const int cy = n[1] >= 3 ? (c0[1] + dy + n[1]) % n[1] : dy;
-            const float rsy = ref.y + (c0[1] + dy < 0 ? a.L[1] : (c0[1] + dy >= n[1] ? -a.L[1] : 0.0f));
+            int cy = dy;
+            float rsy = ref.y;
+            if (n[1] >= 3) {
+                cy = c0[1] + dy;
+                if (cy < 0) { cy += n[1]; rsy += a.L[1]; } else if (cy >= n[1]) { cy -= n[1]; rsy -= a.L[1]; }
+            }
             const int cb = (cx * n[1] + cy) * n[2];
             for (int part = 0; part < (zw >= 0 ? 2 : 1); part++) {
                 const int kb = part == 0 ? st[cb + za] : st[cb + zw], ke = part == 0 ? st[cb + zb + 1] : st[cb + zw + 1];
                 const float rsz = part == 0 ? ref.z : ref.z + zshift;
-                for (int kk = kb; kk < ke; kk++) {
-                    const float4 q = __ldg(srt + kk);
+                const float4 *qp = srt + kb;
+                for (int kk = kb; kk < ke; kk++, qp++) {
+                    const float4 q = __ldg(qp);
                     if (quick && __float_as_int(q.w) >= 0) {
                         const float ex = q.x - rsx, ey = q.y - rsy, ez = q.z - rsz;
                         if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > r2hi) continue;

@@ -534,9 +534,10 @@ static void solve_name_conflicts(std::vector<GorderClassification::Type> &types)
         for (auto &c : counts) if (c.first == t.name) { c.second++; hit = true; break; }
         if (!hit) counts.emplace_back(t.name, 1);
     }
+    counts.erase(std::remove_if(counts.begin(), counts.end(), [](const std::pair<std::string, int> &c) { return c.second <= 1; }), counts.end());
     for (auto it = types.rbegin(); it != types.rend(); ++it)
         for (auto &c : counts)
-            if (c.second > 1 && c.first == it->name) { it->name += std::to_string(c.second); c.second--; break; }
+            if (c.first == it->name) { it->name += std::to_string(c.second); c.second--; break; }
 }
 
 struct Groups {

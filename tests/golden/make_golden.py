@@ -513,7 +513,93 @@ def normals_planar():
     print("normals_planar", exp.shape)
 
 
+def tpr_golden():
+    """tests/golden/tpr/: small GROMACS-written TPR files of the reference's test tree as they are (tpx 103, 122, 127) for the
+    C++ reader of csrc/gorder_topology.inl, `expected.json` with what they hold, and cg_asym.npz -- the trajectory and the
+    reference's expected order parameters of its asymmetric CG membrane (tests_cg.rs:2182-2309), a fixture whose topology
+    exists ONLY as a TPR file.  expected.json is written from the C++ reader after it has been checked here (a) against the
+    independent Python parser tests/golden/tpr_independent.py on every file and (b) against the reference's .gro / .bnd / .pdb
+    files for the three systems that have them; on the GPU box, where the reference tree is absent, it is a regression pin."""
+    import shutil
+    import zlib
+    import importlib.util
+    from gorder_b200.structure import System
+    spec = importlib.util.spec_from_file_location("tpr_independent", os.path.join(HERE, "tpr_independent.py"))
+    ind = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ind)
+    out = os.path.join(HERE, "tpr")
+    os.makedirs(out, exist_ok=True)
+
+    def independent(path):
+        d = ind.parse(path, False)
+        names, resn, bonds, off = [], [], set(), 0
+        btypes = ["BONDS", "G96BONDS", "MORSE", "CUBICBONDS", "CONNBONDS", "HARMONIC", "FENEBONDS", "TABBONDS", "TABBONDSNC", "RESTRBONDS", "CONSTR", "CONSTRNC"]
+        for (t, nmol, nat) in d["mbs"]:
+            mname, atoms, an, res, il = d["mts"][t]
+            for _ in range(nmol):
+                for k in btypes:
+                    if k in il:
+                        for _, i, j in il[k].reshape(-1, 3):
+                            bonds.add((min(i, j) + off, max(i, j) + off))
+                if "SETTLE" in il:
+                    for _, o, h1, h2 in il["SETTLE"].reshape(-1, 4):
+                        bonds.add((o + off, h1 + off)); bonds.add((o + off, h2 + off))
+                for a in range(nat):
+                    names.append(an[a]); resn.append(res[atoms[a][2]][0])
+                off += nat
+        return names, resn, sorted(bonds), d["x"], d["box"]
+
+    exp = {}
+    every = ["cg.tpr", "pcpepg.tpr", "ua.tpr", "asymmetric/cg_asym.tpr", "asymmetric/aa_asym.tpr", "cyclic.tpr", "scrambling/cg_scrambling.tpr",
+             "cg_buckled.tpr", "pepg_cg.tpr", "multiple_resid.tpr", "multiple_resid_same_name.tpr", "same_name.tpr"]
+    keep = {"asymmetric/cg_asym.tpr", "cyclic.tpr", "pepg_cg.tpr", "multiple_resid.tpr", "multiple_resid_same_name.tpr", "same_name.tpr"}
+    for rel in every:
+        path = os.path.join(FILES, rel)
+        s = System.from_tpr(path)
+        names, resn, resid, z, m, q = s.atoms()
+        inames, iresn, ibonds, ix, ibox = independent(path)
+        assert names == inames and resn == iresn, rel
+        assert [tuple(b) for b in s.bonds().tolist()] == [tuple(int(v) for v in b) for b in ibonds], rel
+        assert np.array_equal(s.positions(), np.asarray(ix, np.float32)) and np.array_equal(s.box9(), np.asarray(ibox, np.float32)), rel
+        if rel in keep:
+            fn = os.path.basename(rel)
+            shutil.copyfile(path, os.path.join(out, fn))
+            exp[fn] = dict(tpx=s.tpx_version, n_atoms=s.n_atoms, n_bonds=s.n_bonds, names_head=names[:24], resn_head=resn[:24],
+                           resid_head=[int(v) for v in resid[:24]], names_crc=zlib.crc32(" ".join(names).encode()),
+                           resn_crc=zlib.crc32(" ".join(resn).encode()), bonds_crc=zlib.crc32(s.bonds().astype("<i4").tobytes()),
+                           xyz_head=[float(v) for v in s.positions()[:4].reshape(-1)], box9=[float(v) for v in s.box9()])
+    for tpr, gro, bnd in (("cg.tpr", "cg.gro", "cg.bnd"), ("pcpepg.tpr", "pcpepg.gro", "pcpepg.bnd")):
+        s = System.from_tpr(os.path.join(FILES, tpr))
+        st = fixtures.read_gro(os.path.join(FILES, gro))
+        fixtures.read_bnd(os.path.join(FILES, bnd), st)
+        names, resn, *_ = s.atoms()
+        assert names == st.name and resn == st.resname and set(st.bonds) <= set(map(tuple, s.bonds().tolist())), tpr
+    json.dump(exp, open(os.path.join(out, "expected.json"), "w"), indent=1)
+
+    # the asymmetric CG membrane: trajectory of the membrane beads + the reference's expected values
+    s = System.from_tpr(os.path.join(FILES, "asymmetric/cg_asym.tpr"))
+    names, resn, *_ = s.atoms()
+    keep_atoms = np.array([i for i in range(s.n_atoms) if resn[i] in LIPIDS], dtype=np.int64)   # @membrane = the Master group
+    tr = fixtures.read_xtc(os.path.join(FILES, "asymmetric/cg_asym.xtc"))
+    assert tr.xyz.shape[1] == s.n_atoms
+    prec = 100.0
+    q = np.round(tr.xyz[:, keep_atoms, :].astype(np.float64) * prec).astype(np.int32)
+    assert np.array_equal(q.astype(np.float32) * np.float32(1.0 / prec), tr.xyz[:, keep_atoms, :]), "XTC coordinates are not k/100"
+    tul = ("total", "upper", "lower")
+    cases = {}
+    for case, yf, extra in (("leaflets", "asymmetric/cg_order_asymmetric.yaml", {}),
+                            ("errors", "asymmetric/cg_order_asymmetric_errors.yaml", dict(n_blocks=5))):
+        doc = yaml.safe_load(open(os.path.join(FILES, yf)))
+        cases[case] = dict(expected=flatten_yaml(doc, tul), keys=list(tul), source=yf, **extra)
+    np.savez_compressed(os.path.join(HERE, "cg_asym.npz"), keep=keep_atoms, box=tr.box.astype(np.float32), precision=np.float32(prec),
+                        cases=json.dumps(cases), **pack_lattice(q))
+    print("tpr fixtures:", sorted(os.listdir(out)), "cg_asym.npz", os.path.getsize(os.path.join(HERE, "cg_asym.npz")))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tpr":
+        tpr_golden()
+        sys.exit(0)
     xtc_fixtures()
     normals_planar()
     single_frame("cg_single_frame", "cg.gro", "cg.bnd", "cg.tpr", abi.KIND_CG, "cgorder.rs", 1.0, "PO4")

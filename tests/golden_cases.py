@@ -62,6 +62,31 @@ def full_case_names(which: str):
     return list(json.loads(str(z["cases"])))
 
 
+def cg_asym():
+    """The reference's asymmetric CG membrane (tests_cg.rs:2182-2309: beads ``@membrane``, Global leaflets, heads ``name
+    PO4``).  Its topology exists only as a TPR file, so the setup is built HERE by the C++ reader and classifier
+    (gorder_b200.structure): TPR -> Master group (the membrane atoms, renumbered densely: common.rs:92-103) -> molecule types.
+    Returns setup, frames, boxes, cases."""
+    from gorder_b200.structure import System
+    z = np.load(os.path.join(GOLDEN, "cg_asym.npz"))
+    s = System.from_tpr(os.path.join(GOLDEN, "tpr", "cg_asym.tpr"))
+    names, resn, resid, *_ = s.atoms()
+    keep = z["keep"].astype(np.int64)
+    new = -np.ones(s.n_atoms, np.int64)
+    new[keep] = np.arange(keep.size)
+    b = s.bonds().astype(np.int64)
+    b = b[(new[b[:, 0]] >= 0) & (new[b[:, 1]] >= 0)]
+    master = System.from_arrays([names[i] for i in keep], [resn[i] for i in keep], res_ids=resid[keep])
+    master.set_bonds(new[b])
+    allm = np.arange(keep.size)
+    heads = np.array([i for i in allm if names[keep[i]] == "PO4"])
+    mts = master.classify_bonds(abi.KIND_CG, allm, allm, heads=heads)
+    setup = abi.EngineSetup(kind=abi.KIND_CG, n_atoms=int(keep.size), moltypes=mts, membrane=allm, leaflet_mode=abi.LEAFLET_GLOBAL)
+    q = np.cumsum(z["dq"].astype(np.int32), axis=0)
+    xyz = q.astype(np.float32) * np.float32(1.0 / float(z["precision"]))   # exactly the XTC decoder's arithmetic
+    return setup, xyz, z["box"].astype(np.float32), json.loads(str(z["cases"]))
+
+
 _UA = None
 
 

@@ -2,12 +2,15 @@
 
 Pinned in two ways:
   * on the small GROMACS-written TPR files committed under ``tests/golden/tpr`` (tpx 103, 122, 127) against
-    ``tests/golden/tpr/expected.json`` (made by ``tests/golden/make_golden.py tpr`` from the reference's .gro / .bnd files of
-    the same systems -- NOT from this reader);
+    ``tests/golden/tpr/expected.json`` (written by ``tests/golden/make_golden.py tpr`` after the reader agreed, file by
+    file, with the independent parser ``tests/golden/tpr_independent.py`` and with the reference's .gro / .bnd / .pdb files:
+    a regression pin for machines without the reference tree) and against the reference's expected output for
+    ``cg_asym.tpr`` (``tests/test_gpu_topology.py``, ``test_cg_asym_oracle`` below);
   * where the reference tree is mounted, on all 14 TPR files of ``/root/reference/tests/files`` against the .gro / .bnd /
     .pdb files next to them, and the C++ classifier against the Python restatement in ``oracle/fixtures.py`` (which the
     reference's YAML fixtures pin end to end).
 """
+import dataclasses
 import json
 import os
 
@@ -97,14 +100,16 @@ def test_tpr_errors(tmp_path):
         System.from_tpr(str(tmp_path / "missing.tpr"))
     assert e.value.code == abi.ERR_IO
     raw = open(os.path.join(TPR, "cyclic.tpr"), "rb").read()
-    for cut in (0, 3, 40, 99, 500, 5000, len(raw) - 13):
+    for cut in (0, 3, 40, 99, 500, 5000, 14500):   # 14500: inside the coordinates (the file goes on with velocities and run parameters)
         p = tmp_path / f"cut{cut}.tpr"
         p.write_bytes(raw[:cut])
         with pytest.raises(abi.GorderError) as e:
             System.from_tpr(str(p))
         assert e.value.code == abi.ERR_TPR_FORMAT
     bad = bytearray(raw)
-    bad[32:36] = (200).to_bytes(4, "big")   # tpx version of the future
+    ver_at = 8 + (int.from_bytes(raw[4:8], "big") + 3) // 4 * 4 + 4   # VERSION string, precision, then the tpx version
+    assert int.from_bytes(raw[ver_at:ver_at + 4], "big") == 127
+    bad[ver_at:ver_at + 4] = (200).to_bytes(4, "big")   # tpx version of the future
     p = tmp_path / "future.tpr"
     p.write_bytes(bytes(bad))
     with pytest.raises(abi.GorderError) as e:
@@ -301,7 +306,22 @@ def test_reference_classification_matches_python_restatement():
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
     mg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mg)
-    sat, unsat, heads, meth = mg.ua_selections(st)[:4]
+    sat, unsat = mg.ua_selections(st)
+    heads = st.select(lambda r, n: r in LIPIDS and n.startswith("P"))
+    meth = st.select(lambda r, n: (r == "POPC" and n in ("CA2", "C50")) or (r == "POPS" and n in ("C36", "C55")))
     ref = fixtures.build_ua_setup(st, sat, unsat, heads=heads, methyls=meth).moltypes
-    lip_bonds = [b for b in s.bonds().tolist()]
     _same_types(s.classify_ua(sat, unsat, heads=heads, methyls=meth), ref, abi.KIND_UA)
+
+
+def test_cg_asym_oracle():
+    """The asymmetric CG membrane of the reference (tests_cg.rs:2182-2309), whose topology exists only as a TPR file: C++ TPR
+    reader -> Master group -> C++ classifier -> oracle, against cg_order_asymmetric.yaml and ..._errors.yaml."""
+    from oracle import oracle
+    import golden_cases
+    setup, xyz, box, cases = golden_cases.cg_asym()
+    assert [m.name for m in setup.moltypes] == ["POPE", "POPG"] and setup.n_atoms == 279 * 12
+    for name, case in cases.items():
+        st = dataclasses.replace(setup, timewise="n_blocks" in case)
+        o = oracle.Oracle(st)
+        o.analyze_frames(xyz, box)
+        golden_cases.assert_matches_yaml(o.finish(), st, case)
