@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libgorder_b200.so")
+SO_PATH = os.environ.get("GORDER_B200_LIB") or os.path.join(_HERE, "libgorder_b200.so")   # the override is for A/B builds
 SOURCES = [os.path.join(_HERE, "csrc", "gorder_capi.cu")]
 HEADERS = [
     os.path.join(_HERE, "csrc", "gorder_kernels.cuh"),

@@ -1017,7 +1017,9 @@ static int create_impl(const GorderSetup *s, GorderHandle *h) {
         v.map.enabled = 1; v.map.plane = s->map_plane;
         v.map.nx = (int)roundf(sx / s->map_bin[0]) + 1; v.map.ny = (int)roundf(sy / s->map_bin[1]) + 1;
         v.map.x0 = s->map_span_x[0]; v.map.y0 = s->map_span_y[0]; v.map.binx = s->map_bin[0]; v.map.biny = s->map_bin[1];
+        v.map.inv_binx = 1.0f / v.map.binx; v.map.inv_biny = 1.0f / v.map.biny;
         v.map.n_bins = (long long)v.map.nx * v.map.ny;
+        if (v.map.n_bins >= (1LL << 31)) { h->set_error(GORDER_ERR_INVALID_ARGUMENT, "ordermap with more than 2^31 bins"); return h->err_code; }
     }
 
     // ---- accumulators ----------------------------------------------------------------------------

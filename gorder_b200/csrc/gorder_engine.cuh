@@ -82,6 +82,7 @@ struct Seg { int off, len; };
 struct MapParams {
     int enabled, plane, nx, ny;
     float x0, y0, binx, biny;
+    float inv_binx, inv_biny;   // 1 / bin: the bin look-up divides only next to a bin edge
     long long n_bins;
 };
 

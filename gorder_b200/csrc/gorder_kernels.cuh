@@ -68,6 +68,15 @@ __device__ __forceinline__ Box load_box(const FrameAux &a) {
     return b;
 }
 
+// sqrt_rn(r2) < radius, with the IEEE square root only where it decides: sqrt is monotone and radius^2 is within one rounding
+// of the square, so two parts in a million away from radius^2 the comparison of the squares gives the same answer.
+__device__ __forceinline__ bool radius_less(float r2, float radius) {
+    const float R2 = radius * radius;
+    if (r2 < R2 * 0.999998f) return true;
+    if (r2 > R2 * 1.000002f) return false;
+    return __fsqrt_rn(r2) < radius;
+}
+
 // Shape::inside / inside_naive XOR invert (geometry.rs:181-190; groan Rectangular / Cylinder / Sphere).
 template <bool PBC>
 __device__ __forceinline__ bool shape_inside(const ShapeParams &sp, const FrameAux &a, const Box &bx, const f3 &pt) {
@@ -92,32 +101,42 @@ __device__ __forceinline__ bool shape_inside(const ShapeParams &sp, const FrameA
             if (PBC && bx.L[k] > 0.0f) d = min_image(d, bx.L[k], bx.half[k]);
             r2 = __fadd_rn(r2, __fmul_rn(d, d));
         }
-        in = __fsqrt_rn(r2) < a.shape_radius;
+        in = radius_less(r2, a.shape_radius);
         float d = __fsub_rn(q[sp.axis], o[sp.axis]);
         if (PBC) {
-            if (bx.L[sp.axis] > 0.0f) d = wrap1(d, bx.L[sp.axis]);
-            in = in && (d <= a.shape_height);
+            // an infinite span: every wrapped distance lies below it (NaN coordinates are caught by the accumulator's check)
+            if (a.shape_height < CUDART_INF_F) {
+                if (bx.L[sp.axis] > 0.0f) d = wrap1(d, bx.L[sp.axis]);
+                in = in && (d <= a.shape_height);
+            }
         } else in = in && (d >= 0.0f) && (d <= a.shape_height);
     } else if (sp.kind == GORDER_GEOM_SPHERE) {
         f3 c = mk3(o[0], o[1], o[2]);
         f3 d = vector_to<PBC>(c, pt, bx);
-        in = norm_ref(d) < a.shape_radius;
+        in = radius_less(dot_ref(d, d), a.shape_radius);
     }
     return in != (sp.invert != 0);
 }
 
 // Map::add_order bin lookup (ordermap.rs:100-113): nearest node, -1 if outside.
+// groan GridMap: nearest node = round((x - min) / bin), half away from zero (pinned by the reference's AA map fixtures,
+// where bond midpoints sit exactly on bin edges; floor(v + 0.5) does not reproduce them).
+// The IEEE division and roundf are only needed next to a bin edge: t = (x - min) * (1 / bin) is within 2 ulp of the quotient,
+// so unless t lies within that distance of a half-integer its nearest integer (one FRND) IS the reference's node.
+__device__ __forceinline__ float map_node(float d, float bin, float inv_bin) {
+    const float t = __fmul_rn(d, inv_bin), r = rintf(t);
+    if (fabsf(__fsub_rn(t, r)) < 0.5f - fmaf(fabsf(t), 1e-6f, 1e-6f)) return r;
+    return roundf(__fdiv_rn(d, bin));
+}
 __device__ __forceinline__ long long map_bin(const MapParams &mp, const f3 &pos) {
     float x, y;
     if (mp.plane == GORDER_PLANE_XY) { x = pos.x; y = pos.y; }
     else if (mp.plane == GORDER_PLANE_XZ) { x = pos.x; y = pos.z; }
     else { x = pos.z; y = pos.y; }   // sic: YZ projects to (z, y), input/ordermap.rs:48
-    // groan GridMap: nearest node = round((x - min) / bin), half away from zero (pinned by the reference's AA map fixtures,
-    // where bond midpoints sit exactly on bin edges; floor(v + 0.5) does not reproduce them)
-    float fx = roundf(__fdiv_rn(__fsub_rn(x, mp.x0), mp.binx));
-    float fy = roundf(__fdiv_rn(__fsub_rn(y, mp.y0), mp.biny));
+    const float fx = map_node(__fsub_rn(x, mp.x0), mp.binx, mp.inv_binx);
+    const float fy = map_node(__fsub_rn(y, mp.y0), mp.biny, mp.inv_biny);
     if (!(fx >= 0.0f) || !(fy >= 0.0f) || fx >= (float)mp.nx || fy >= (float)mp.ny) return -1;
-    return (long long)fx * mp.ny + (long long)fy;
+    return (long long)((int)fx * mp.ny + (int)fy);   // n_bins < 2^31 (checked at create)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1599,8 +1618,17 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
     }
 }
 
+// Resident CTAs per SM the variants are compiled for (measured on B200, round 2).  Geometry / maps: 4 (64 registers, a few
+// spills) -- S-AA-large launches 512 CTAs, which 4 per SM hold in ONE wave (0.77 -> 0.55 ms per 128 frames; at 2 or 3 per SM
+// the second wave is a tail).  Per-molecule normals without geometry: 3 (0.056 -> 0.046 ms per 8 frames of S-CG).
+#ifndef GORDER_EXTRA_MINB
+#define GORDER_EXTRA_MINB 4
+#endif
+#ifndef GORDER_NVEC_MINB
+#define GORDER_NVEC_MINB 3
+#endif
 template <int MPT, bool PBC, bool NVEC, bool LEAF, bool EXTRA, bool SPEC = false>
-__global__ void __launch_bounds__(kBlock, (EXTRA || NVEC) ? 2 : 4) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
+__global__ void __launch_bounds__(kBlock, EXTRA ? GORDER_EXTRA_MINB : (NVEC ? GORDER_NVEC_MINB : 4)) bond_order_kernel(DeviceView v, const float *__restrict__ planes, const FrameAux *__restrict__ aux,
                                                             const unsigned char *__restrict__ leaf_rows, const float *__restrict__ normals,
                                                             const int *__restrict__ normal_npoints, AccumOut o) {
     bond_order_body<MPT, PBC, NVEC, LEAF, EXTRA, SPEC>(v, planes, aux, leaf_rows, normals, normal_npoints, o);
