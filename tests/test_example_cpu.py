@@ -46,3 +46,41 @@ def test_cpp_host_builds_and_needs_a_gpu(tmp_path):
         for k, key in enumerate(("total", "upper", "lower")):
             o = getattr(item.order, key)
             assert abs(got[b, k, 0] - o.value) < 5.1e-5 and abs(got[b, k, 1] - o.error) < 5.1e-5
+
+
+def test_tpr_host_builds_and_needs_a_gpu(tmp_path):
+    """examples/tpr_order.cpp: run file + trajectory -> order parameters with no Rust and no Python in the loop.  On a GPU its
+    table is the reference's cg_order_asymmetric_errors.yaml (tests_cg.rs:2246-2309)."""
+    import golden_cases as gc
+    exe = str(tmp_path / "tpr_order")
+    lib_dir = os.path.join(ROOT, "gorder_b200")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "tpr_order.cpp"),
+                    "-L", lib_dir, "-lgorder_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True, capture_output=True, text=True)
+    # the trajectory of the fixture holds the membrane beads only: put them back among the 9170 atoms of the run file
+    setup, xyz, box, cases = gc.cg_asym()
+    z = np.load(os.path.join(gc.GOLDEN, "cg_asym.npz"))
+    full = np.zeros((xyz.shape[0], 9170, 3), np.float32)
+    full[:, z["keep"], :] = xyz
+    path = str(tmp_path / "t.xtc")
+    write_xtc(path, full, box, precision=100.0)
+    tpr = os.path.join(gc.GOLDEN, "tpr", "cg_asym.tpr")
+    r = subprocess.run([exe, tpr, path, "POPE,POPG", "PO4", "5"], capture_output=True, text=True, timeout=300)
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if not have_gpu:
+        assert r.returncode == 1 and f"code {abi.ERR_NO_DEVICE}" in r.stderr, (r.returncode, r.stderr)
+        return
+    assert r.returncode == 0, r.stderr
+    rows = [ln for ln in r.stdout.splitlines() if not ln.startswith("#")]
+    assert len(rows) == 2 * 12 + 1 and "POPE NH3 (0) - POPE PO4 (1)" in rows[0]
+    val = lambda ln: [float(t) for t in ln.split()[-9:] if t != "+-"]   # total, error, upper, error, lower, error
+    got = val(rows[-1])                       # flatten_yaml order: system average, then per molecule its average and its bonds
+    for m in range(2):
+        got += val(rows[12 * m + 11])
+        for b in range(11):
+            got += val(rows[12 * m + b])
+    exp = np.array(cases["errors"]["expected"], np.float64)
+    np.testing.assert_allclose(np.array(got), exp, atol=2e-4, rtol=0, equal_nan=True)

@@ -12,3 +12,11 @@ def test_cpp_host_on_the_gpu(tmp_path):
     import torch
     assert torch.cuda.is_available()
     _run_example(tmp_path)
+
+
+def test_tpr_host_on_the_gpu(tmp_path):
+    """run file + trajectory -> the reference's cg_order_asymmetric_errors.yaml, through C++ only (examples/tpr_order.cpp)."""
+    from test_example_cpu import test_tpr_host_builds_and_needs_a_gpu as run
+    import torch
+    assert torch.cuda.is_available()
+    run(tmp_path)
