@@ -18,7 +18,7 @@ SYMBOLS = [
     "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_stream",
     "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_xtc_scan", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device",
     "gorder_results_order", "gorder_results_convergence", "gorder_results_map", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
-    "gorder_topology_last_error", "gorder_system_from_tpr", "gorder_system_from_arrays", "gorder_system_free", "gorder_system_n_atoms", "gorder_system_n_bonds",
+    "gorder_topology_last_error", "gorder_system_from_tpr", "gorder_system_from_file", "gorder_system_from_arrays", "gorder_system_free", "gorder_system_n_atoms", "gorder_system_n_bonds",
     "gorder_system_tpx_version", "gorder_system_atoms", "gorder_system_bonds", "gorder_system_positions", "gorder_system_box", "gorder_system_set_bonds",
     "gorder_system_read_bonds", "gorder_classify_bonds", "gorder_classify_ua", "gorder_classification_free", "gorder_classification_n_types",
     "gorder_classification_moltypes", "gorder_classification_type_name", "gorder_classification_item_name", "gorder_classification_warning",
@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
     # structure / topology / classification (host only)
     L.gorder_topology_last_error.restype = C.c_char_p
     L.gorder_system_from_tpr.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.gorder_system_from_file.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
+    L.gorder_system_from_file.restype = C.c_int
     L.gorder_system_from_arrays.argtypes = [i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), vp, vp, vp, C.POINTER(vp)]
     L.gorder_system_free.argtypes = [vp]
     L.gorder_system_free.restype = None
@@ -117,7 +119,7 @@ def lib() -> C.CDLL:
     L.gorder_classification_n_atoms_rel.restype = i32
     L.gorder_classification_atoms_rel.argtypes = [vp, i32]
     L.gorder_classification_atoms_rel.restype = C.POINTER(i32)
-    for name in ("gorder_system_from_tpr", "gorder_system_from_arrays", "gorder_system_atoms", "gorder_system_bonds", "gorder_system_positions",
+    for name in ("gorder_system_from_tpr", "gorder_system_from_file", "gorder_system_from_arrays", "gorder_system_atoms", "gorder_system_bonds", "gorder_system_positions",
                  "gorder_system_box", "gorder_system_set_bonds", "gorder_system_read_bonds", "gorder_classify_bonds", "gorder_classify_ua"):
         getattr(L, name).restype = C.c_int
     L.gorder_gpu_fence.argtypes = [vp]

@@ -63,6 +63,9 @@ ERR_TOPOLOGY_MULTIPLE_HEADS = 46
 ERR_TOPOLOGY_NO_METHYL = 47
 ERR_TOPOLOGY_INCONSISTENT_METHYLS = 48
 ERR_TOPOLOGY_NO_UA_CARBONS = 49
+ERR_NO_TOPOLOGY = 50
+ERR_PDB_TOPOLOGY = 51
+ERR_STRUCTURE_FORMAT = 52
 
 ERROR_NAMES = {
     ERR_UNDEFINED_BOX: "AnalysisError::UndefinedBox",
@@ -94,6 +97,9 @@ ERROR_NAMES = {
     ERR_TOPOLOGY_NO_METHYL: "TopologyError::NoMethyl",
     ERR_TOPOLOGY_INCONSISTENT_METHYLS: "TopologyError::InconsistentNumberOfMethyls",
     ERR_TOPOLOGY_NO_UA_CARBONS: "TopologyError::NoUACarbons",
+    ERR_NO_TOPOLOGY: "ConfigError::NoTopology",
+    ERR_PDB_TOPOLOGY: "ConfigError::InvalidPdbTopology",
+    ERR_STRUCTURE_FORMAT: "ConfigError::InvalidStructureFormat",
 }
 
 _i32p = C.POINTER(C.c_int32)

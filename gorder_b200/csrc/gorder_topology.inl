@@ -313,6 +313,190 @@ int gorder_system_from_tpr(const char *path, GorderSystem **out) {
     return GORDER_OK;
 }
 
+}  // extern "C"
+
+// ---- GRO and PDB (groan_rs System::from_file for the two text formats gorder's tests use) ---------------------------------
+namespace gtopo {
+
+static bool read_text(const char *path, std::vector<std::string> &lines) {
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    std::string cur;
+    char buf[4096];
+    while (fgets(buf, sizeof(buf), f)) {
+        cur += buf;
+        if (!cur.empty() && cur.back() == '\n') { cur.pop_back(); if (!cur.empty() && cur.back() == '\r') cur.pop_back(); lines.push_back(cur); cur.clear(); }
+    }
+    if (!cur.empty()) lines.push_back(cur);
+    fclose(f);
+    return true;
+}
+static std::string field(const std::string &ln, size_t a, size_t b) {   // columns [a, b), trimmed
+    if (a >= ln.size()) return "";
+    std::string t = ln.substr(a, std::min(b, ln.size()) - a);
+    const size_t i = t.find_first_not_of(' '), j = t.find_last_not_of(' ');
+    return i == std::string::npos ? "" : t.substr(i, j - i + 1);
+}
+static bool to_float(const std::string &t, float &v) { if (t.empty()) return false; char *e = nullptr; v = strtof(t.c_str(), &e); return e && *e == 0; }
+static bool to_int(const std::string &t, int &v) { if (t.empty()) return false; char *e = nullptr; long x = strtol(t.c_str(), &e, 10); v = (int)x; return e && *e == 0; }
+
+// GRO: title, atom count, `%5d%-5s%5s%5d` + three positions of width n + 5 (n decimals: GROMACS writes any precision; the width
+// is the distance between the decimal points), box line (3 or 9 numbers: xx yy zz xy xz yx yz zx zy)
+static void parse_gro(const std::vector<std::string> &ln, GorderSystem &sys) {
+    if (ln.size() < 3) throw ParseError{"GRO file with fewer than three lines"};
+    int n;
+    if (!to_int(field(ln[1], 0, ln[1].size()), n) || n < 0 || (size_t)n + 3 > ln.size()) throw ParseError{"GRO atom count does not match the file"};
+    sys.n_atoms = n;
+    sys.xyz.resize(3 * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        const std::string &l = ln[2 + i];
+        if (l.size() < 20 + 3 * 4) throw ParseError{"GRO atom line too short (line " + std::to_string(3 + i) + ")"};
+        int resid;
+        if (!to_int(field(l, 0, 5), resid)) throw ParseError{"GRO residue number (line " + std::to_string(3 + i) + ")"};
+        sys.resid.push_back(resid); sys.resname.push_back(field(l, 5, 10)); sys.name.push_back(field(l, 10, 15));
+        sys.atomic_number.push_back(0); sys.mass.push_back(0.0f); sys.charge.push_back(0.0f);
+        const size_t d1 = l.find('.', 20), d2 = d1 == std::string::npos ? d1 : l.find('.', d1 + 1);
+        if (d2 == std::string::npos) throw ParseError{"GRO positions (line " + std::to_string(3 + i) + ")"};
+        const size_t w = d2 - d1;
+        for (int k = 0; k < 3; k++)
+            if (!to_float(field(l, 20 + k * w, 20 + (k + 1) * w), sys.xyz[3 * (size_t)i + k])) throw ParseError{"GRO positions (line " + std::to_string(3 + i) + ")"};
+    }
+    float b[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int nb = 0;
+    {
+        const std::string &l = ln[2 + (size_t)n];
+        size_t i = 0;
+        while (i < l.size() && nb < 9) {
+            while (i < l.size() && isspace((unsigned char)l[i])) i++;
+            size_t j = i;
+            while (j < l.size() && !isspace((unsigned char)l[j])) j++;
+            if (j > i && !to_float(l.substr(i, j - i), b[nb++])) throw ParseError{"GRO box line"};
+            i = j;
+        }
+    }
+    if (nb == 3 || nb == 9) {   // row-major box matrix: rows = box vectors
+        sys.box9[0] = b[0]; sys.box9[4] = b[1]; sys.box9[8] = b[2];
+        if (nb == 9) { sys.box9[1] = b[3]; sys.box9[2] = b[4]; sys.box9[3] = b[5]; sys.box9[5] = b[6]; sys.box9[6] = b[7]; sys.box9[7] = b[8]; }
+        sys.has_box = true;
+    }
+    sys.bonded.resize(n);
+}
+
+// PDB: ATOM / HETATM of the first model (Angstrom -> nm), CRYST1, CONECT.  Returns false when the serial numbers repeat
+// (ParsePdbConnectivityError::DuplicateAtomNumbers: the CONECT records are ambiguous then).
+static bool parse_pdb(const std::vector<std::string> &ln, GorderSystem &sys, bool &has_conect) {
+    std::vector<std::pair<int, int>> serial_index;
+    bool model_done = false, dup = false;
+    std::vector<std::pair<int, int>> conect;
+    has_conect = false;
+    for (const std::string &l : ln) {
+        const std::string rec = l.substr(0, std::min<size_t>(6, l.size()));
+        if ((rec == "ATOM  " || rec == "HETATM") && !model_done) {
+            if (l.size() < 54) throw ParseError{"PDB atom record too short"};
+            int serial = 0, resid = 0;
+            to_int(field(l, 6, 11), serial);
+            if (!to_int(field(l, 22, 26), resid)) resid = 0;
+            float x, y, z;
+            if (!to_float(field(l, 30, 38), x) || !to_float(field(l, 38, 46), y) || !to_float(field(l, 46, 54), z)) throw ParseError{"PDB coordinates"};
+            serial_index.emplace_back(serial, sys.n_atoms);
+            sys.name.push_back(field(l, 12, 16)); sys.resname.push_back(field(l, 17, 21)); sys.resid.push_back(resid);
+            sys.atomic_number.push_back(0); sys.mass.push_back(0.0f); sys.charge.push_back(0.0f);
+            sys.xyz.push_back(x / 10.0f); sys.xyz.push_back(y / 10.0f); sys.xyz.push_back(z / 10.0f);
+            sys.n_atoms++;
+        } else if (rec == "CRYST1") {
+            float a, b, c, al = 90, be = 90, ga = 90;
+            if (to_float(field(l, 6, 15), a) && to_float(field(l, 15, 24), b) && to_float(field(l, 24, 33), c)) {
+                to_float(field(l, 33, 40), al); to_float(field(l, 40, 47), be); to_float(field(l, 47, 54), ga);
+                const double d2r = 3.14159265358979323846 / 180.0, ca = cos(al * d2r), cb = cos(be * d2r), cg = cos(ga * d2r), sg = sin(ga * d2r);
+                a /= 10.0f; b /= 10.0f; c /= 10.0f;
+                auto clean = [](double v) { return fabs(v) < 1e-6 ? 0.0f : (float)v; };
+                sys.box9[0] = a; sys.box9[3] = clean(b * cg); sys.box9[4] = clean(b * sg);
+                sys.box9[6] = clean(c * cb); sys.box9[7] = clean(c * (ca - cb * cg) / sg);
+                const double z2 = (double)c * c - (double)sys.box9[6] * sys.box9[6] - (double)sys.box9[7] * sys.box9[7];
+                sys.box9[8] = (float)sqrt(z2 > 0 ? z2 : 0.0);
+                sys.has_box = true;
+            }
+        } else if (rec == "CONECT") {
+            has_conect = true;
+            int first = 0;
+            if (!to_int(field(l, 6, 11), first)) continue;
+            for (size_t k = 11; k + 1 <= l.size() && k < 31; k += 5) {
+                int other;
+                if (to_int(field(l, k, k + 5), other)) conect.emplace_back(first, other);
+            }
+        } else if (rec.compare(0, 6, "ENDMDL") == 0) model_done = true;
+    }
+    sys.bonded.resize(sys.n_atoms);
+    std::sort(serial_index.begin(), serial_index.end());
+    for (size_t i = 1; i < serial_index.size(); i++) if (serial_index[i].first == serial_index[i - 1].first) dup = true;
+    if (dup && has_conect) return false;
+    auto find = [&](int serial) -> int {
+        auto it = std::lower_bound(serial_index.begin(), serial_index.end(), std::make_pair(serial, -1));
+        return it != serial_index.end() && it->first == serial ? it->second : -1;
+    };
+    for (const auto &c : conect) {
+        const int a = find(c.first), b = find(c.second);
+        if (a < 0 || b < 0) throw ParseError{"CONECT record names an atom that does not exist"};
+        if (a != b) sys.add_bond(a, b);
+    }
+    sys.finish_bonds();
+    return true;
+}
+
+static bool ends_with(const std::string &s, const char *suffix) {
+    const size_t n = strlen(suffix);
+    if (s.size() < n) return false;
+    for (size_t i = 0; i < n; i++) if (tolower((unsigned char)s[s.size() - n + i]) != suffix[i]) return false;
+    return true;
+}
+
+}  // namespace gtopo
+
+extern "C" int gorder_system_read_bonds(GorderSystem *s, const char *bonds_file);
+
+// read_structure_and_topology (structure.rs:27-88): a bonds file, when given, replaces whatever topology the structure holds;
+// without one a TPR brings its own bonds, a PDB its CONECT records (none: NoTopology; repeated atom numbers:
+// InvalidPdbTopology) and a GRO file has no topology (NoTopology).  Box checks (check_box) are the engine's.
+extern "C" int gorder_system_from_file(const char *structure, const char *bonds_file, GorderSystem **out) {
+    if (!structure || !out) return GORDER_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    const std::string path(structure);
+    GorderSystem *sys = nullptr;
+    int rc = GORDER_OK;
+    if (gtopo::ends_with(path, ".tpr")) {
+        if ((rc = gorder_system_from_tpr(structure, &sys))) return rc;
+    } else if (gtopo::ends_with(path, ".gro") || gtopo::ends_with(path, ".pdb")) {
+        const bool pdb = gtopo::ends_with(path, ".pdb");
+        std::vector<std::string> lines;
+        if (!gtopo::read_text(structure, lines)) { g_topology_error = "could not open '" + path + "'"; return GORDER_ERR_IO; }
+        sys = new GorderSystem();
+        bool has_conect = false, ok = true;
+        try {
+            if (pdb) ok = gtopo::parse_pdb(lines, *sys, has_conect); else gtopo::parse_gro(lines, *sys);
+        } catch (const gtopo::ParseError &e) {
+            g_topology_error = path + ": " + e.what;
+            delete sys;
+            return GORDER_ERR_STRUCTURE_FORMAT;
+        }
+        if (!bonds_file) {
+            if (pdb && !ok) { g_topology_error = "cannot parse topology from the provided PDB file '" + path + "' - non-unique atom numbers make the CONECT information ambiguous"; delete sys; return GORDER_ERR_PDB_TOPOLOGY; }
+            if (!pdb || !has_conect || sys->n_bonds() == 0) {
+                g_topology_error = "the input structure file '" + path + "' does not contain topology information (hint: provide a `bonds` file)";
+                delete sys;
+                return GORDER_ERR_NO_TOPOLOGY;
+            }
+        }
+    } else {
+        g_topology_error = "the provided structure file '" + path + "' has an unknown, invalid, or unsupported format";
+        return GORDER_ERR_STRUCTURE_FORMAT;
+    }
+    if (bonds_file && (rc = gorder_system_read_bonds(sys, bonds_file))) { delete sys; return rc; }
+    *out = sys;
+    return GORDER_OK;
+}
+
+extern "C" {
+
 int gorder_system_from_arrays(int32_t n_atoms, const char *const *atom_names, const char *const *res_names, const int32_t *res_ids,
                               const float *xyz, const float *box9, GorderSystem **out) {
     if (!out || n_atoms < 0 || (n_atoms > 0 && (!atom_names || !res_names))) return GORDER_ERR_INVALID_ARGUMENT;

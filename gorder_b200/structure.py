@@ -45,6 +45,15 @@ class System:
         return cls(h)
 
     @classmethod
+    def from_file(cls, structure: str, bonds_file: Optional[str] = None) -> "System":
+        """``read_structure_and_topology`` (structure.rs:27-88): TPR, PDB (CONECT) or GRO, bonds file optional."""
+        h = C.c_void_p()
+        rc = lib().gorder_system_from_file(structure.encode(), bonds_file.encode() if bonds_file else None, C.byref(h))
+        if rc != abi.OK:
+            _fail(rc)
+        return cls(h)
+
+    @classmethod
     def from_arrays(cls, atom_names: Sequence[str], res_names: Sequence[str], res_ids=None, xyz=None, box9=None) -> "System":
         n = len(atom_names)
         an = (C.c_char_p * n)(*[s.encode() for s in atom_names])

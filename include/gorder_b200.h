@@ -120,7 +120,10 @@ enum {
     GORDER_ERR_TOPOLOGY_MULTIPLE_HEADS = 46,   /* TopologyError::MultipleHeads */
     GORDER_ERR_TOPOLOGY_NO_METHYL = 47,        /* TopologyError::NoMethyl */
     GORDER_ERR_TOPOLOGY_INCONSISTENT_METHYLS = 48, /* TopologyError::InconsistentNumberOfMethyls */
-    GORDER_ERR_TOPOLOGY_NO_UA_CARBONS = 49     /* TopologyError::NoUACarbons */
+    GORDER_ERR_TOPOLOGY_NO_UA_CARBONS = 49,    /* TopologyError::NoUACarbons */
+    GORDER_ERR_NO_TOPOLOGY = 50,               /* ConfigError::NoTopology: structure without bonds and no bonds file */
+    GORDER_ERR_PDB_TOPOLOGY = 51,              /* ConfigError::InvalidPdbTopology: repeated atom numbers make CONECT ambiguous */
+    GORDER_ERR_STRUCTURE_FORMAT = 52           /* ConfigError::InvalidStructureFormat, or a GRO / PDB file that does not parse */
 };
 
 /* ---- setup ------------------------------------------------------------------------------ */
@@ -447,6 +450,10 @@ const char *gorder_topology_last_error(void);
  * mass, charge), bonds (BONDS .. RESTRBONDS, CONSTR, CONSTRNC, the O-H pairs of SETTLE, intermolecular lists), box and
  * coordinates.  Anything else -> GORDER_ERR_TPR_FORMAT. */
 int gorder_system_from_tpr(const char *path, GorderSystem **out);
+/* read_structure_and_topology (structure.rs:27-88) by file extension: .tpr as above; .pdb with its CONECT records; .gro; a
+ * bonds file (may be NULL) replaces the topology of any of them.  GORDER_ERR_NO_TOPOLOGY when no bonds come from anywhere,
+ * GORDER_ERR_PDB_TOPOLOGY for CONECT records over repeated atom numbers, GORDER_ERR_STRUCTURE_FORMAT otherwise. */
+int gorder_system_from_file(const char *structure, const char *bonds_file, GorderSystem **out);
 /* A structure read by the host (GRO / PDB ...): names and residue numbers as arrays; xyz [n][3] and box9 may be NULL. */
 int gorder_system_from_arrays(int32_t n_atoms, const char *const *atom_names, const char *const *res_names, const int32_t *res_ids,
                               const float *xyz, const float *box9, GorderSystem **out);

@@ -325,3 +325,90 @@ def test_cg_asym_oracle():
         o = oracle.Oracle(st)
         o.analyze_frames(xyz, box)
         golden_cases.assert_matches_yaml(o.finish(), st, case)
+
+
+# ---- GRO / PDB / read_structure_and_topology ------------------------------------------------------------------------------
+GRO = """toy
+    4
+    1LIP      P    1   1.000   2.000   3.000
+    1LIP     C1    2   1.100   2.000   3.000
+    1LIP     C2    3   1.200   2.000   3.000
+    2SOL     OW    4   0.500   0.500   0.500
+   4.00000   5.00000   6.00000
+"""
+PDB = """CRYST1   40.000   50.000   60.000  90.00  90.00  90.00 P 1           1
+ATOM      1  P   LIP     1      10.000  20.000  30.000  1.00  0.00
+ATOM      2  C1  LIP     1      11.000  20.000  30.000  1.00  0.00
+ATOM      3  C2  LIP     1      12.000  20.000  30.000  1.00  0.00
+ATOM      4  OW  SOL     2       5.000   5.000   5.000  1.00  0.00
+ENDMDL
+CONECT    1    2
+CONECT    2    1    3
+CONECT    3    2
+"""
+
+
+def test_structure_files_and_topology_rules(tmp_path):
+    """structure.rs:27-88: a GRO file has no topology (NoTopology) unless a bonds file comes with it; a PDB brings CONECT
+    records (none: NoTopology, repeated atom numbers: InvalidPdbTopology); unknown extensions are refused."""
+    gro, pdb, bnd = tmp_path / "s.gro", tmp_path / "s.pdb", tmp_path / "s.bnd"
+    gro.write_text(GRO); pdb.write_text(PDB); bnd.write_text("1 2\n2 3\n")
+    with pytest.raises(abi.GorderError) as e:
+        System.from_file(str(gro))
+    assert e.value.code == abi.ERR_NO_TOPOLOGY
+    s = System.from_file(str(gro), str(bnd))
+    names, resn, resid, *_ = s.atoms()
+    assert names == ["P", "C1", "C2", "OW"] and resn == ["LIP", "LIP", "LIP", "SOL"] and resid.tolist() == [1, 1, 1, 2]
+    assert s.bonds().tolist() == [[0, 1], [1, 2]]
+    assert np.allclose(s.positions()[1], [1.1, 2.0, 3.0]) and np.allclose(s.box9()[[0, 4, 8]], [4, 5, 6])
+    p = System.from_file(str(pdb))
+    assert p.atoms()[0] == names and p.bonds().tolist() == [[0, 1], [1, 2]]
+    assert np.allclose(p.positions(), s.positions(), atol=1e-6) and np.allclose(p.box9()[[0, 4, 8]], [4, 5, 6])
+    (tmp_path / "n.pdb").write_text("".join(ln + "\n" for ln in PDB.splitlines() if not ln.startswith("CONECT")))
+    with pytest.raises(abi.GorderError) as e:
+        System.from_file(str(tmp_path / "n.pdb"))
+    assert e.value.code == abi.ERR_NO_TOPOLOGY
+    assert System.from_file(str(tmp_path / "n.pdb"), str(bnd)).n_bonds == 2
+    (tmp_path / "d.pdb").write_text(PDB.replace("ATOM      4", "ATOM      1"))
+    with pytest.raises(abi.GorderError) as e:
+        System.from_file(str(tmp_path / "d.pdb"))
+    assert e.value.code == abi.ERR_PDB_TOPOLOGY
+    for bad in ("s.xyz", "s"):
+        (tmp_path / bad).write_text(GRO)
+        with pytest.raises(abi.GorderError) as e:
+            System.from_file(str(tmp_path / bad))
+        assert e.value.code == abi.ERR_STRUCTURE_FORMAT
+    (tmp_path / "t.gro").write_text("toy\n   9\n    1LIP      P    1   1.000\n")
+    with pytest.raises(abi.GorderError) as e:
+        System.from_file(str(tmp_path / "t.gro"), str(bnd))
+    assert e.value.code == abi.ERR_STRUCTURE_FORMAT
+    with pytest.raises(abi.GorderError) as e:
+        System.from_file(str(tmp_path / "missing.gro"))
+    assert e.value.code == abi.ERR_IO
+    t = System.from_file(os.path.join(TPR, "cyclic.tpr"))
+    assert t.n_atoms == 36 and t.tpx_version == 127
+    t2 = System.from_file(os.path.join(TPR, "cyclic.tpr"), str(bnd))   # the bonds file wins over the run file's topology
+    assert t2.n_bonds == 2
+
+
+@needs_ref
+def test_reference_gro_pdb_match_python_readers():
+    from oracle import fixtures
+    for gro, bnd in (("cg.gro", "cg.bnd"), ("pcpepg.gro", "pcpepg.bnd")):
+        s = System.from_file(os.path.join(REF, gro), os.path.join(REF, bnd))
+        st = fixtures.read_gro(os.path.join(REF, gro))
+        fixtures.read_bnd(os.path.join(REF, bnd), st)
+        names, resn, resid, *_ = s.atoms()
+        assert names == st.name and resn == st.resname and np.array_equal(resid, st.resid)
+        assert np.array_equal(s.positions(), st.xyz) and np.array_equal(s.box9()[[0, 4, 8]], st.box)
+        assert list(map(tuple, s.bonds().tolist())) == st.bonds
+    s = System.from_file(os.path.join(REF, "ua_nobox.pdb"))
+    st = fixtures.read_pdb(os.path.join(REF, "ua_nobox.pdb"))
+    names, resn, resid, *_ = s.atoms()
+    assert names == st.name and resn == st.resname and np.array_equal(resid, st.resid)
+    # Angstrom -> nm: an f32 division here, a double division rounded to f32 in the Python reader
+    assert np.abs(s.positions() - st.xyz).max() < 1e-6 and list(map(tuple, s.bonds().tolist())) == st.bonds
+    c = System.from_file(os.path.join(REF, "cg.pdb"), os.path.join(REF, "cg.bnd"))
+    g = System.from_file(os.path.join(REF, "cg.gro"), os.path.join(REF, "cg.bnd"))
+    assert c.atoms()[0] == g.atoms()[0] and np.abs(c.positions() - g.positions()).max() < 1e-3
+    assert np.allclose(c.box9(), g.box9(), atol=1e-3)
