@@ -365,23 +365,28 @@ def run_ours(args):
                 path = os.path.join(td, f"bench{rank}.xtc")
                 write_xtc(path, xyz[:nx], box[:nx])
                 fbytes = os.path.getsize(path)
+                # the device-decode leg reads a longer file (the same frames appended `xtc_repeat` times): its pipeline
+                # (host copy | H2D | walk + unpack + analysis) needs more than a handful of batches to show its steady state
+                for r_ in range(1, args.xtc_repeat):
+                    write_xtc(path, xyz[:nx], box[:nx], append=True, first_step=r_ * nx)
+                nx_dev = nx * args.xtc_repeat
                 with XtcFile(path) as xf:
                     eng4 = SystemTopology(s.setup)
                     eng4.reserve_frames(2 * nx + 8)
-                    eng4.run_xtc(xf, n_threads=threads_x, batch_frames=args.xtc_batch)   # warm-up: page mappings of the file, pinned buffers
+                    eng4.run_xtc(xf, last=nx, n_threads=threads_x, batch_frames=args.xtc_batch)   # warm-up: page mappings of the file, pinned buffers
                     eng4.sync()
                     if world > 1:
                         dist.barrier()
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    dec_s = eng4.run_xtc(xf, n_threads=threads_x, batch_frames=args.xtc_batch, frame_index0=nx)
+                    dec_s = eng4.run_xtc(xf, last=nx, n_threads=threads_x, batch_frames=args.xtc_batch, frame_index0=nx)
                     eng4.finish(totals_only=True)
                     xt[0], xt[2] = time.perf_counter() - t0, dec_s
                     eng4.close()
                     # the same file with the decode on the device: host threads only copy compressed bytes
                     eng5 = SystemTopology(s.setup)
-                    reps = 3
-                    eng5.reserve_frames((reps + 1) * nx + 8)
+                    reps = 2
+                    eng5.reserve_frames((reps + 1) * nx_dev + 8)
                     eng5.run_xtc_device(xf, n_threads=threads_x, batch_frames=args.xtc_dev_batch)   # warm-up
                     eng5.sync()
                     if world > 1:
@@ -389,13 +394,13 @@ def run_ours(args):
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
                     for r_ in range(reps):
-                        moved = eng5.run_xtc_device(xf, n_threads=threads_x, batch_frames=args.xtc_dev_batch, frame_index0=(r_ + 1) * nx)
+                        moved = eng5.run_xtc_device(xf, n_threads=threads_x, batch_frames=args.xtc_dev_batch, frame_index0=(r_ + 1) * nx_dev)
                     eng5.finish(totals_only=True)
                     xt[1] = (time.perf_counter() - t0) / reps
                     eng5.close()
             xt[3] = 1.0
             info = {"frames_per_rank": nx, "file_bytes": fbytes, "bytes_per_atom": fbytes / nx / s.n_atoms, "decode_threads_per_rank": threads_x,
-                    "h2d_bytes": moved, "h2d_bytes_per_atom": moved / nx / s.n_atoms}
+                    "h2d_bytes": moved, "h2d_bytes_per_atom": moved / nx_dev / s.n_atoms, "device_decode_frames_per_rank": nx_dev}
         except Exception as exc:   # noqa: BLE001
             info = {"error": f"{type(exc).__name__}: {exc}"}
         tx = torch.from_numpy(xt).cuda()
@@ -408,8 +413,9 @@ def run_ours(args):
             e2e_xtc = {"value": world * nx * spf / float(tx[0]), "unit": UNIT, "ranks": world, **info, "wall_seconds": float(tx[0]),
                        "decode_atoms_per_s_per_thread": nx * s.n_atoms / max(float(tx[2]), 1e-9),
                        "entry": "gorder_gpu_run_xtc on every rank (host XTC decode + H2D + analysis + D2H of the sums), whole-job rate, max time over ranks",
-                       "device_decode": {"value": world * nx * spf / float(tx[1]), "unit": UNIT, "wall_seconds": float(tx[1]), "batch_frames": args.xtc_dev_batch,
-                                         "entry": "gorder_gpu_run_xtc_device on every rank (host copies + bookmarks the compressed frames; xtc_decode_kernel unpacks them on the GPU)"}}
+                       "device_decode": {"value": world * info["device_decode_frames_per_rank"] * spf / float(tx[1]), "unit": UNIT, "wall_seconds": float(tx[1]), "batch_frames": args.xtc_dev_batch,
+                                         "frames_per_rank": info["device_decode_frames_per_rank"],
+                                         "entry": "gorder_gpu_run_xtc_device on every rank (host threads copy the compressed frames into pinned batches; xtc_walk_kernel + xtc_decode_kernel unpack them on the GPU)"}}
         elif rank == 0:
             e2e_xtc = info if "error" in info else {"error": "the XTC leg failed on another rank"}
 
@@ -497,8 +503,9 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU arms; 0 = one per host thread")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--xtc-frames", type=int, default=256, help="frames of the XTC end-to-end leg (0 = skip)")
+    ap.add_argument("--xtc-repeat", type=int, default=4, help="the device-decode leg reads the XTC frames appended this many times (one call)")
     ap.add_argument("--xtc-batch", type=int, default=16, help="frames per decoded batch of the XTC leg")
-    ap.add_argument("--xtc-dev-batch", type=int, default=64, help="frames per batch of the device-decode XTC leg (>= 4 per staging thread lets a thread walk 4 frames at once)")
+    ap.add_argument("--xtc-dev-batch", type=int, default=128, help="frames per batch of the device-decode XTC leg (the walk of a batch takes ~6 ms whatever its size: large batches hide it behind the copies)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.lipids = args.lipids or WORKLOADS[args.workload][1]

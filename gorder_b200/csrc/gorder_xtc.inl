@@ -584,6 +584,8 @@ struct DevFrame {
     unsigned sizeint[3];
     int bitsint[3];
     float inv_precision;
+    int smallidx;                 // of the frame header: where the walk starts
+    int pad_;
 };
 
 // host: bookmarks of one frame; returns the number of groups, -1 when the stream is inconsistent, -2 when it needs
@@ -691,13 +693,9 @@ __device__ __forceinline__ void dev_unpack3(unsigned long long v, unsigned s1, u
     }
 }
 
-__global__ void __launch_bounds__(256) xtc_decode_kernel(const unsigned char *__restrict__ bytes, const DevFrame *__restrict__ frames,
-                                                         const Bookmark *__restrict__ bookmarks, const int *__restrict__ slot_of_atom,
-                                                         int n_engine_atoms, float *__restrict__ xyz) {
-    const int f = blockIdx.y;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const DevFrame &fr = frames[f];
-    if (g >= __ldg(&fr.n_groups)) return;
+// one group (a "large" atom + its run of small ones): from the warp's bookmark to the group by the control bits, then unpack
+__device__ __forceinline__ void xtc_decode_group(const unsigned char *__restrict__ bytes, const DevFrame &fr, const Bookmark *__restrict__ bookmarks,
+                                                 const int *__restrict__ slot_of_atom, int n_engine_atoms, float *__restrict__ xyz, int f, int g) {
     const unsigned *w = reinterpret_cast<const unsigned *>(bytes + __ldg(&fr.payload));
     const int bitsize = __ldg(&fr.bitsize);
     const int large_bits = bitsize ? bitsize : __ldg(&fr.bitsint[0]) + __ldg(&fr.bitsint[1]) + __ldg(&fr.bitsint[2]);
@@ -754,6 +752,106 @@ __global__ void __launch_bounds__(256) xtc_decode_kernel(const unsigned char *__
         if (k == 0) { emit(i, t); emit(i + 1, cur); i += 2; }   // the first two atoms of a run are stored in swapped order
         else { emit(i, t); i++; }
         prev[0] = t[0]; prev[1] = t[1]; prev[2] = t[2];
+    }
+}
+
+// grid (x, frames); the x dimension strides over the frame's groups, whose number the device walk only knows on the device
+__global__ void __launch_bounds__(256) xtc_decode_kernel(const unsigned char *__restrict__ bytes, const DevFrame *__restrict__ frames,
+                                                         const Bookmark *__restrict__ bookmarks, const int *__restrict__ slot_of_atom,
+                                                         int n_engine_atoms, float *__restrict__ xyz) {
+    const int f = blockIdx.y;
+    const DevFrame &fr = frames[f];
+    const int ng = __ldg(&fr.n_groups);   // <= 0: nothing to do (empty, inconsistent or unsupported frame)
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += gridDim.x * blockDim.x)
+        xtc_decode_group(bytes, fr, bookmarks, slot_of_atom, n_engine_atoms, xyz, f, g);
+}
+
+// The walk over the control bits on the DEVICE: one warp per frame; lane 0 follows the chain
+//     position -> 6 bits of the stream -> run / smallidx -> next position
+// and drops a bookmark every 32 groups -- the same walk as gxtc::Walker on the host (identical bookmarks) -- while all lanes
+// stream the frame through a ring of four 4 KB chunks in shared memory with cp.async, two chunks ahead of the walker: a walk
+// straight from global memory paid a DRAM miss for every new 32-byte sector (250 ns per group, 45 ms per 1 M-atom frame);
+// from shared memory a step is ~70 cycles of dependent instructions.  That is still slow for ONE frame (~7 ms) and
+// irrelevant for a batch: its frames walk side by side on as many SMs while the copy engine brings in the next batch, so the
+// host has nothing left to do per frame but hand over the compressed bytes.  n_groups of the frame = its groups, or -1
+// (inconsistent stream) / -2 (a small triple of more than 64 bits: not covered) -- the decoder skips such a frame and the
+// engine's deferred error word takes GORDER_ERR_INVALID_ARGUMENT with the frame's number (reported by the next sync / finish).
+constexpr int kWalkChunk = 4096, kWalkSlots = 4;
+__global__ void __launch_bounds__(32) xtc_walk_kernel(const unsigned char *__restrict__ bytes, DevFrame *__restrict__ frames,
+                                                      Bookmark *__restrict__ bookmarks, unsigned marks_per_frame, unsigned frame_cap,
+                                                      int *__restrict__ err, long long *__restrict__ err_detail, long long frame0, long long frame_stride) {
+    __shared__ __align__(16) unsigned ring[kWalkSlots * kWalkChunk / 4];
+    const int f = blockIdx.x, lane = threadIdx.x;
+    DevFrame &fr = frames[f];
+    const unsigned char *src = bytes + fr.payload;   // 16-byte aligned
+    const int n = fr.natoms;
+    const int large_bits = fr.bitsize ? fr.bitsize : fr.bitsint[0] + fr.bitsint[1] + fr.bitsint[2];
+    const unsigned end = fr.nbytes * 8u;             // nbytes < 2^29 (checked on the host)
+    const unsigned limit = min(frame_cap, (fr.nbytes + 32u + 15u) & ~15u);   // bytes of the slot that hold the stream and its zeros
+    const int n_chunks = (int)((fr.nbytes + 16u + kWalkChunk - 1) / kWalkChunk);
+    Bookmark *bm = bookmarks + fr.bookmarks;
+    auto load_chunk = [&](int c) {   // all lanes: chunk c -> its slot of the ring (zeros past the stream)
+        if (c < n_chunks + 1) {
+            const unsigned base = (unsigned)c * kWalkChunk;
+            unsigned char *dst = reinterpret_cast<unsigned char *>(ring) + (size_t)(c % kWalkSlots) * kWalkChunk;
+            for (unsigned k = (unsigned)lane * 16u; k < (unsigned)kWalkChunk; k += 512u) {
+                if (base + k + 16u <= limit) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + k);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + base + k) : "memory");
+                } else *reinterpret_cast<uint4 *>(dst + k) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_chunk(0);
+    load_chunk(1);
+    unsigned pos = 0;
+    int i = 0, g = 0, smalls = 0, sidx = fr.smallidx, rc = 0;
+    bool done = n <= 0 || sidx > 64 || sidx < kFirstIdx;
+    if (n > 0 && sidx > 64) rc = -2; else if (n > 0 && sidx < kFirstIdx) rc = -1;
+    for (int c = 0; !done; c++) {
+        load_chunk(c + 2);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunks <= c + 1 have landed
+        __syncwarp();
+        if (lane == 0) {
+            // groups whose control bits START in chunk c (the look reaches 8 bytes further); in the last chunks `end` closes the window
+            const unsigned stop = min((unsigned)(c + 1) * kWalkChunk * 8u, end);
+            constexpr unsigned kRing = kWalkSlots * kWalkChunk / 4;
+            for (;;) {   // one group per turn; the chain  pos -> 6 bits -> run, smallidx -> pos  is all there is: keep it short
+                const unsigned cpos = pos + (unsigned)large_bits;
+                if (cpos >= stop) { if (stop == end) rc = -1; break; }   // next chunk; or atoms left and no stream
+                if ((g & (kBookmarkEvery - 1)) == 0) {
+                    if ((unsigned)(g / kBookmarkEvery) >= marks_per_frame) { rc = -1; break; }
+                    bm[g / kBookmarkEvery] = Bookmark{pos, (unsigned)i, (unsigned short)(3 * smalls), (unsigned short)sidx, 0u};
+                }
+                const unsigned wi = cpos >> 5;
+                const unsigned w0 = __byte_perm(ring[wi % kRing], 0, 0x0123), w1 = __byte_perm(ring[(wi + 1) % kRing], 0, 0x0123);
+                const unsigned six = __funnelshift_l(w1, w0, cpos & 31u) >> 26;
+                pos = cpos + 1u;
+                int run_bits = smalls * sidx;
+                if (six & 32u) {
+                    const int code = (int)(six & 31u);
+                    smalls = (code * 11) >> 5;            // code / 3 for code < 32
+                    run_bits = smalls * sidx;             // the run is read with the smallidx BEFORE its change
+                    sidx += code - 3 * smalls - 1;
+                    pos += 5u;
+                }
+                pos += (unsigned)run_bits;
+                i += 1 + smalls;
+                g++;
+                if (i >= n) { rc = (i != n || pos > end) ? -1 : g; break; }
+                if ((unsigned)(sidx - kFirstIdx) > (unsigned)(64 - kFirstIdx)) { rc = sidx > 64 ? -2 : -1; break; }   // as the host: before the next group
+            }
+        }
+        rc = __shfl_sync(0xffffffffu, rc, 0);
+        done = rc != 0;
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (lane == 0) {
+        if (n <= 0) rc = 0;
+        fr.n_groups = rc;
+        if (rc < 0 && atomicCAS(err, 0, (int)GORDER_ERR_INVALID_ARGUMENT) == 0) *err_detail = frame0 + (long long)f * frame_stride;
     }
 }
 
@@ -890,7 +988,13 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
     long long moved = 0;
     std::atomic<int> bad{0}, unsupported{0};
     std::vector<int> n_groups((size_t)B);
-    auto stage = [&](int64_t j0, int nf, int buf) {   // compressed frames + bookmarks -> pinned batch
+    // Who walks the control bits?  The device (xtc_walk_kernel: the host only hands over the compressed bytes) unless a frame
+    // could meet a small triple of more than 64 bits -- smallidx moves inside [first - 8, first + 8] of the frame header's
+    // value (the writer's window) -- in which case the host walks, as in round 1, and hands such frames to the host decoder.
+    bool dev_walk = !h->sw.xtc_host_walk;
+    for (int64_t j = 0; dev_walk && j < total; j++)
+        if (x->frames[(size_t)(first + j * stride)].smallidx + 8 > 64) dev_walk = false;
+    auto stage = [&](int64_t j0, int nf, int buf) {   // compressed frames (+ bookmarks, when the host walks) -> pinned batch
         std::atomic<int> next{0};
         const int nt = std::max(1, std::min<int>(n_threads, nf));
         // a thread walks the control bits of up to kWalkWays frames in one loop (gxtc::Walker): the walk is a chain of dependent
@@ -916,22 +1020,24 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
                     for (int c = 0; c < 3; c++) { d.minint[c] = f.minint[c]; sz[c] = d.sizeint[c] = (unsigned)(f.maxint[c] - f.minint[c] + 1); }
                     if ((sz[0] | sz[1] | sz[2]) > 0xffffffu) { d.bitsize = 0; for (int c = 0; c < 3; c++) d.bitsint[c] = gxtc::bits_of(sz[c]); }
                     else { d.bitsize = gxtc::bits_of_triple(sz); d.bitsint[0] = d.bitsint[1] = d.bitsint[2] = 0; }
-                    d.inv_precision = 1.0f / f.precision;
+                    d.inv_precision = 1.0f / f.precision; d.smallidx = f.smallidx; d.pad_ = 0;
                     fr[k] = &f; bits[k] = d.bitsize ? d.bitsize : d.bitsint[0] + d.bitsint[1] + d.bitsint[2];
                     marks[k].clear(); out[k] = &marks[k];
                 }
-                gxtc::bookmark_many(x->data, fr, bits, out, ngs, m);
+                if (!dev_walk) gxtc::bookmark_many(x->data, fr, bits, out, ngs, m);
                 for (int k = 0; k < m; k++) {
-                    const int j = jb + k, ng = ngs[k];
+                    const int j = jb + k, ng = dev_walk ? 0 : ngs[k];
                     const gxtc::Frame &f = *fr[k];
                     gxtc::DevFrame &d = D.h_frames[buf][j];
-                    if (ng == -2) { unsupported = 1; d.n_groups = 0; }
+                    if (dev_walk) d.n_groups = 0;   // filled in by xtc_walk_kernel
+                    else if (ng == -2) { unsupported = 1; d.n_groups = 0; }
                     else if (ng < 0 || marks[k].size() > marks_per_frame) { bad = GORDER_ERR_INVALID_ARGUMENT; d.n_groups = 0; }
                     else { d.n_groups = ng; memcpy(D.h_marks[buf] + d.bookmarks, marks[k].data(), marks[k].size() * sizeof(gxtc::Bookmark)); }
                     n_groups[(size_t)j] = d.n_groups;
                     unsigned char *dst = D.h_bytes[buf] + d.payload;
                     memcpy(dst, x->data + f.payload, f.nbytes);
-                    memset(dst + f.nbytes, 0, frame_cap - f.nbytes);
+                    // the readers look up to 8 bytes past a field: zeros behind the stream (the whole slack when it travels)
+                    memset(dst + f.nbytes, 0, dev_walk ? std::min<size_t>(32, frame_cap - f.nbytes) : frame_cap - f.nbytes);
                     D.h_box[buf][3 * j] = f.box[0]; D.h_box[buf][3 * j + 1] = f.box[4]; D.h_box[buf][3 * j + 2] = f.box[8];
                 }
             }
@@ -952,16 +1058,31 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
             rc = gorder_gpu_run_xtc(h, x, atom_of_slot, first + j0 * stride, last, stride, frame_index0 + j0 * stride, n_threads, batch_frames, nullptr);
             break;
         }
-        const size_t nbytes = (size_t)nf * frame_cap, mbytes = (size_t)nf * marks_per_frame * sizeof(gxtc::Bookmark);
-        CK(cudaMemcpyAsync(D.d_bytes[buf], D.h_bytes[buf], nbytes, cudaMemcpyHostToDevice, h->copy_stream));
-        CK(cudaMemcpyAsync(D.d_marks[buf], D.h_marks[buf], mbytes, cudaMemcpyHostToDevice, h->copy_stream));
+        size_t nbytes = (size_t)nf * frame_cap, mbytes = (size_t)nf * marks_per_frame * sizeof(gxtc::Bookmark);
+        if (dev_walk) {   // only the streams travel (+ 32 bytes of zeros each): no slack, no bookmarks
+            nbytes = 0; mbytes = 0;
+            for (int j = 0; j < nf; j++) {
+                const size_t off = (size_t)D.h_frames[buf][j].payload, len = std::min(frame_cap, (((size_t)D.h_frames[buf][j].nbytes + 32) + 15) & ~(size_t)15);
+                CK(cudaMemcpyAsync(D.d_bytes[buf] + off, D.h_bytes[buf] + off, len, cudaMemcpyHostToDevice, h->copy_stream));
+                nbytes += len;
+            }
+        } else {
+            CK(cudaMemcpyAsync(D.d_bytes[buf], D.h_bytes[buf], nbytes, cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaMemcpyAsync(D.d_marks[buf], D.h_marks[buf], mbytes, cudaMemcpyHostToDevice, h->copy_stream));
+        }
         CK(cudaMemcpyAsync(D.d_frames[buf], D.h_frames[buf], nf * sizeof(gxtc::DevFrame), cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaMemcpyAsync(D.d_box[buf], D.h_box[buf], nf * 3 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaEventRecord(D.ev_copied[buf], h->copy_stream));
         moved += (long long)(nbytes + mbytes);
         CK(cudaStreamWaitEvent(h->stream, D.ev_copied[buf], 0));
         int max_groups = 1;
-        for (int j = 0; j < nf; j++) max_groups = std::max(max_groups, n_groups[(size_t)j]);
+        if (dev_walk) {
+            gxtc::xtc_walk_kernel<<<nf, 32, 0, h->stream>>>(D.d_bytes[buf], D.d_frames[buf], D.d_marks[buf], (unsigned)marks_per_frame, (unsigned)frame_cap, h->d_err, h->d_err_detail,
+                                                          (long long)(first + j0 * stride), (long long)stride);
+            h->n_launches++;
+            max_groups = std::max(1, x->natoms / 4);   // the decoder strides: any grid is correct, this one covers ~5 atoms per group in one pass
+        } else
+            for (int j = 0; j < nf; j++) max_groups = std::max(max_groups, n_groups[(size_t)j]);
         dim3 grid((max_groups + 255) / 256, nf);
         gxtc::xtc_decode_kernel<<<grid, 256, 0, h->stream>>>(D.d_bytes[buf], D.d_frames[buf], D.d_marks[buf], D.d_slot_of_atom, na, D.d_xyz);
         h->n_launches++;

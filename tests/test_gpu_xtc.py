@@ -193,3 +193,50 @@ def test_device_decode_of_gromacs_written_files(name):
         got = host.finish()
         host.close()
         np.testing.assert_array_equal(got.tw_sum, want.tw_sum)
+
+
+def test_device_walk_equals_host_walk(tmp_path, monkeypatch):
+    """Round 2: the control bits are walked by xtc_walk_kernel (one thread per frame); GORDER_XTC_HOST_WALK=1 keeps the host
+    threads' walk.  Same bookmarks, hence the same accumulators; fewer bytes cross PCIe (no bookmarks, no slack)."""
+    s = synthetic.s_cg(2600, leaflet_mode=abi.LEAFLET_GLOBAL, timewise=True)
+    xyz, box, idx = s.frames(0, 9)
+    path = str(tmp_path / "t.xtc")
+    write_xtc(path, xyz, box)
+    out = {}
+    with XtcFile(path) as x:
+        for mode in ("device", "host"):
+            if mode == "host":
+                monkeypatch.setenv("GORDER_XTC_HOST_WALK", "1")
+            eng = SystemTopology(s.setup)
+            moved = eng.run_xtc_device(x, batch_frames=4, n_threads=3)
+            out[mode] = (eng.finish(), moved)
+            eng.close()
+    np.testing.assert_array_equal(out["device"][0].sum, out["host"][0].sum)
+    np.testing.assert_array_equal(out["device"][0].tw_sum, out["host"][0].tw_sum)
+    assert 0 < out["device"][1] < out["host"][1]
+
+
+def test_corrupt_stream_is_an_error_on_the_device_path(tmp_path):
+    """Garbage in the compressed bytes of one frame: the device walk loses the thread (atom count / stream length do not
+    come out), the decoder skips the frame and the engine reports GORDER_ERR_INVALID_ARGUMENT with the frame's number."""
+    s = synthetic.s_cg(600, leaflet_mode=abi.LEAFLET_GLOBAL)
+    xyz, box, idx = s.frames(0, 6)
+    path = str(tmp_path / "t.xtc")
+    write_xtc(path, xyz, box)
+    raw = bytearray(open(path, "rb").read())
+    with XtcFile(path) as x:
+        n_frames = x.n_frames
+    per = len(raw) // n_frames
+    rng = np.random.default_rng(3)
+    lo = 4 * per + 200   # inside the stream of frame 4 (headers are ~92 bytes)
+    raw[lo:lo + 400] = bytes(rng.integers(0, 256, 400, dtype=np.uint8))
+    open(path, "wb").write(bytes(raw))
+    with XtcFile(path) as x:
+        eng = SystemTopology(s.setup)
+        try:
+            with pytest.raises(abi.GorderError) as e:
+                eng.run_xtc_device(x, batch_frames=4)
+                eng.finish()
+            assert e.value.code == abi.ERR_INVALID_ARGUMENT
+        finally:
+            eng.close()
