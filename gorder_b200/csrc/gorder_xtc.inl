@@ -642,6 +642,20 @@ inline int bookmark_frame(const uint8_t *base, const Frame &f, int large_bits, s
     while (w.rc == 0) w.step(T);
     return w.result();
 }
+// page cache -> pinned batch with non-temporal stores (dst 16-byte aligned): the pinned lines are read next by the copy
+// engine, not by a core, so they need not be fetched for ownership nor kept in the cache (GORDER_XTC_NT_COPY, A/B switch)
+inline void stream_copy(unsigned char *dst, const unsigned char *src, size_t n) {
+    size_t i = 0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i)), b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 32)), d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a); _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c); _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
+        }
+    memcpy(dst + i, src + i, n - i);
+    _mm_sfence();
+}
 // up to kWalkWays frames at once (see Walker): ng[k] = groups of frame k or its error code
 constexpr int kWalkWays = 4;
 inline void bookmark_many(const uint8_t *base, const Frame *const *fr, const int *bits, std::vector<Bookmark> *const *out, int *ng, int count) {
@@ -1035,7 +1049,7 @@ int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom
                     else { d.n_groups = ng; memcpy(D.h_marks[buf] + d.bookmarks, marks[k].data(), marks[k].size() * sizeof(gxtc::Bookmark)); }
                     n_groups[(size_t)j] = d.n_groups;
                     unsigned char *dst = D.h_bytes[buf] + d.payload;
-                    memcpy(dst, x->data + f.payload, f.nbytes);
+                    if (h->sw.xtc_nt_copy) gxtc::stream_copy(dst, x->data + f.payload, f.nbytes); else memcpy(dst, x->data + f.payload, f.nbytes);
                     // the readers look up to 8 bytes past a field: zeros behind the stream (the whole slack when it travels)
                     memset(dst + f.nbytes, 0, dev_walk ? std::min<size_t>(32, frame_cap - f.nbytes) : frame_cap - f.nbytes);
                     D.h_box[buf][3 * j] = f.box[0]; D.h_box[buf][3 * j + 1] = f.box[4]; D.h_box[buf][3 * j + 2] = f.box[8];
