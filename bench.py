@@ -505,7 +505,7 @@ def main():
     ap.add_argument("--xtc-frames", type=int, default=256, help="frames of the XTC end-to-end leg (0 = skip)")
     ap.add_argument("--xtc-repeat", type=int, default=4, help="the device-decode leg reads the XTC frames appended this many times (one call)")
     ap.add_argument("--xtc-batch", type=int, default=16, help="frames per decoded batch of the XTC leg")
-    ap.add_argument("--xtc-dev-batch", type=int, default=128, help="frames per batch of the device-decode XTC leg (the walk of a batch takes ~6 ms whatever its size: large batches hide it behind the copies)")
+    ap.add_argument("--xtc-dev-batch", type=int, default=256, help="frames per batch of the device-decode XTC leg (the walk of a batch takes ~6 ms whatever its size: large batches hide it behind the copies)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.lipids = args.lipids or WORKLOADS[args.workload][1]

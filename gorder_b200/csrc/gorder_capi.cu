@@ -63,7 +63,7 @@ struct Switches {
     bool no_inline_leaflets = false;   // GORDER_NO_INLINE_LEAFLETS: separate leaflet_assign_kernel for Global-every-frame
     bool no_overlap = false;     // GORDER_NO_OVERLAP: one stream instead of the pre / main / post pipeline
     bool ua_exact = false;       // GORDER_UA_EXACT: bit-exact hydrogen construction everywhere
-    bool xtc_nt_copy = false;         // GORDER_XTC_NT_COPY: non-temporal stores for the copy of compressed frames into the pinned batch
+    bool xtc_nt_copy = true;          // GORDER_XTC_NO_NT_COPY: plain memcpy instead of non-temporal stores for the compressed frames -> pinned batch
     bool xtc_host_walk = false;       // GORDER_XTC_HOST_WALK: the host threads walk the XTC control bits (bookmarks) instead of xtc_walk_kernel
     bool no_sorted_normals = false;   // GORDER_NO_SORTED_NORMALS: one lane per lipid in molecule order (dynamic_normal_cell_kernel)
     bool verbose = false;        // GORDER_VERBOSE
@@ -78,7 +78,7 @@ struct Switches {
         w.no_spec = flag("GORDER_NO_SPEC"); w.no_spec_leftover = flag("GORDER_NO_SPEC_LEFTOVER");
         w.no_inline_leaflets = flag("GORDER_NO_INLINE_LEAFLETS"); w.no_overlap = flag("GORDER_NO_OVERLAP");
         w.ua_exact = flag("GORDER_UA_EXACT"); w.verbose = flag("GORDER_VERBOSE");
-        w.no_sorted_normals = flag("GORDER_NO_SORTED_NORMALS"); w.xtc_host_walk = flag("GORDER_XTC_HOST_WALK"); w.xtc_nt_copy = flag("GORDER_XTC_NT_COPY");
+        w.no_sorted_normals = flag("GORDER_NO_SORTED_NORMALS"); w.xtc_host_walk = flag("GORDER_XTC_HOST_WALK"); w.xtc_nt_copy = !flag("GORDER_XTC_NO_NT_COPY");
         w.center_blocks = num("GORDER_CENTER_BLOCKS", 0); w.center_sub = num("GORDER_CENTER_SUB", 0);
         w.cell_min_heads = num("GORDER_CELL_MIN_HEADS", 2048); w.lcell_min_atoms = num("GORDER_LCELL_MIN_ATOMS", 4096);
         return w;
