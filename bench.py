@@ -367,9 +367,10 @@ def run_ours(args):
                 fbytes = os.path.getsize(path)
                 # the device-decode leg reads a longer file (the same frames appended `xtc_repeat` times): its pipeline
                 # (host copy | H2D | walk + unpack + analysis) needs more than a handful of batches to show its steady state
-                for r_ in range(1, args.xtc_repeat):
+                repeat = max(1, args.xtc_repeat // world)   # every rank writes its own file: keep the job's temporary files below ~5 GB
+                for r_ in range(1, repeat):
                     write_xtc(path, xyz[:nx], box[:nx], append=True, first_step=r_ * nx)
-                nx_dev = nx * args.xtc_repeat
+                nx_dev = nx * repeat
                 with XtcFile(path) as xf:
                     eng4 = SystemTopology(s.setup)
                     eng4.reserve_frames(2 * nx + 8)
