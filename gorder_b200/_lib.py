@@ -23,6 +23,8 @@ SYMBOLS = [
     "gorder_system_read_bonds", "gorder_classify_bonds", "gorder_classify_ua", "gorder_classification_free", "gorder_classification_n_types",
     "gorder_classification_moltypes", "gorder_classification_type_name", "gorder_classification_item_name", "gorder_classification_warning",
     "gorder_classification_n_atoms_rel", "gorder_classification_atoms_rel",
+    "gorder_ndx_open", "gorder_ndx_close", "gorder_ndx_n_groups", "gorder_ndx_group_name", "gorder_ndx_group_size", "gorder_ndx_group_atoms", "gorder_ndx_find",
+    "gorder_leaflets_from_ndx",
     "gorder_gpu_reduce", "gorder_comm_unique_id", "gorder_comm_create", "gorder_gpu_reduce_comm", "gorder_comm_broadcast_leaflets", "gorder_comm_destroy",
 ]
 
@@ -122,6 +124,22 @@ def lib() -> C.CDLL:
     for name in ("gorder_system_from_tpr", "gorder_system_from_file", "gorder_system_from_arrays", "gorder_system_atoms", "gorder_system_bonds", "gorder_system_positions",
                  "gorder_system_box", "gorder_system_set_bonds", "gorder_system_read_bonds", "gorder_classify_bonds", "gorder_classify_ua"):
         getattr(L, name).restype = C.c_int
+    L.gorder_ndx_open.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+    L.gorder_ndx_open.restype = C.c_int
+    L.gorder_ndx_close.argtypes = [vp]
+    L.gorder_ndx_close.restype = None
+    L.gorder_ndx_n_groups.argtypes = [vp]
+    L.gorder_ndx_n_groups.restype = i32
+    L.gorder_ndx_group_name.argtypes = [vp, i32]
+    L.gorder_ndx_group_name.restype = C.c_char_p
+    L.gorder_ndx_group_size.argtypes = [vp, i32]
+    L.gorder_ndx_group_size.restype = i64
+    L.gorder_ndx_group_atoms.argtypes = [vp, i32]
+    L.gorder_ndx_group_atoms.restype = C.POINTER(i32)
+    L.gorder_ndx_find.argtypes = [vp, C.c_char_p]
+    L.gorder_ndx_find.restype = i32
+    L.gorder_leaflets_from_ndx.argtypes = [C.POINTER(C.c_char_p), i32, i32, C.c_char_p, C.c_char_p, vp, i32, vp]
+    L.gorder_leaflets_from_ndx.restype = C.c_int
     L.gorder_gpu_fence.argtypes = [vp]
     L.gorder_gpu_fence.restype = C.c_int
     L.gorder_gpu_stream.argtypes = [vp]

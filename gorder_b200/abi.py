@@ -66,6 +66,11 @@ ERR_TOPOLOGY_NO_UA_CARBONS = 49
 ERR_NO_TOPOLOGY = 50
 ERR_PDB_TOPOLOGY = 51
 ERR_STRUCTURE_FORMAT = 52
+ERR_NDX_PARSE = 53
+ERR_NDX_INVALID_NAME = 54
+ERR_NDX_DUPLICATE_NAME = 55
+ERR_NDX_GROUP_NOT_FOUND = 56
+ERR_NDX_ASSIGNMENT_NOT_FOUND = 57
 
 ERROR_NAMES = {
     ERR_UNDEFINED_BOX: "AnalysisError::UndefinedBox",
@@ -100,6 +105,11 @@ ERROR_NAMES = {
     ERR_NO_TOPOLOGY: "ConfigError::NoTopology",
     ERR_PDB_TOPOLOGY: "ConfigError::InvalidPdbTopology",
     ERR_STRUCTURE_FORMAT: "ConfigError::InvalidStructureFormat",
+    ERR_NDX_PARSE: "NdxLeafletClassificationError::CouldNotParse",
+    ERR_NDX_INVALID_NAME: "NdxLeafletClassificationError::InvalidName",
+    ERR_NDX_DUPLICATE_NAME: "NdxLeafletClassificationError::DuplicateName",
+    ERR_NDX_GROUP_NOT_FOUND: "NdxLeafletClassificationError::GroupNotFound",
+    ERR_NDX_ASSIGNMENT_NOT_FOUND: "NdxLeafletClassificationError::AssignmentNotFound",
 }
 
 _i32p = C.POINTER(C.c_int32)

@@ -627,6 +627,117 @@ int gorder_system_read_bonds(GorderSystem *s, const char *bonds_file) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// GROMACS index files (groan_rs Groups::from_ndx) and the leaflet tables read from them (leaflets.rs:1030-1215)
+// ---------------------------------------------------------------------------------------------------------------------------
+struct GorderNdx {
+    std::vector<std::string> names;                 // in file order; a repeated name replaces the earlier group (and is reported)
+    std::vector<std::vector<int32_t>> atoms;        // 0-based, as listed
+    std::vector<std::string> invalid, duplicate;    // names refused ('"&|!@()<>= are not allowed), names that occurred twice
+    int find(const std::string &n) const { for (size_t i = 0; i < names.size(); i++) if (names[i] == n) return (int)i; return -1; }
+};
+
+namespace gtopo {
+
+static int parse_ndx(const char *path, int n_atoms, GorderNdx &nd) {
+    std::vector<std::string> lines;
+    if (!read_text(path, lines)) { g_topology_error = std::string("could not open the ndx file '") + path + "'"; return GORDER_ERR_IO; }
+    int cur = -1;       // group being filled; -1: none yet, -2: a group with an invalid name (its atoms are skipped)
+    for (size_t li = 0; li < lines.size(); li++) {
+        const std::string &l = lines[li];
+        const size_t a = l.find_first_not_of(" \t");
+        if (a == std::string::npos) continue;
+        if (l[a] == '[') {
+            const size_t b = l.find(']', a);
+            if (b == std::string::npos) { g_topology_error = std::string(path) + ": line " + std::to_string(li + 1) + ": group header without ']'"; return GORDER_ERR_NDX_PARSE; }
+            const std::string name = field(l, a + 1, b);
+            if (name.empty() || name.find_first_of("'\"&|!@()<>=") != std::string::npos) { nd.invalid.push_back(name); cur = -2; continue; }
+            const int old = nd.find(name);
+            if (old >= 0) { nd.duplicate.push_back(name); nd.atoms[old].clear(); cur = old; }
+            else { nd.names.push_back(name); nd.atoms.emplace_back(); cur = (int)nd.names.size() - 1; }
+            continue;
+        }
+        size_t i = a;
+        while (i < l.size()) {
+            while (i < l.size() && isspace((unsigned char)l[i])) i++;
+            size_t j = i;
+            while (j < l.size() && !isspace((unsigned char)l[j])) j++;
+            if (j > i) {
+                int v;
+                if (!to_int(l.substr(i, j - i), v) || v < 1) { g_topology_error = std::string(path) + ": line " + std::to_string(li + 1) + ": '" + l.substr(i, j - i) + "' is not an atom number"; return GORDER_ERR_NDX_PARSE; }
+                if (n_atoms >= 0 && v > n_atoms) { g_topology_error = std::string(path) + ": atom number " + std::to_string(v) + " does not exist (the system has " + std::to_string(n_atoms) + " atoms)"; return GORDER_ERR_NDX_PARSE; }
+                if (cur == -1) { g_topology_error = std::string(path) + ": atom numbers before the first group header"; return GORDER_ERR_NDX_PARSE; }
+                if (cur >= 0) nd.atoms[cur].push_back(v - 1);
+            }
+            i = j;
+        }
+    }
+    return GORDER_OK;
+}
+
+}  // namespace gtopo
+
+extern "C" {
+
+// n_atoms < 0: atom numbers are not range-checked
+int gorder_ndx_open(const char *path, int32_t n_atoms, GorderNdx **out) {
+    if (!path || !out) return GORDER_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    auto nd = std::make_unique<GorderNdx>();
+    if (int rc = gtopo::parse_ndx(path, n_atoms, *nd)) return rc;
+    *out = nd.release();
+    return GORDER_OK;
+}
+void gorder_ndx_close(GorderNdx *n) { delete n; }
+int32_t gorder_ndx_n_groups(const GorderNdx *n) { return n ? (int32_t)n->names.size() : -1; }
+const char *gorder_ndx_group_name(const GorderNdx *n, int32_t g) { return n && g >= 0 && g < (int32_t)n->names.size() ? n->names[g].c_str() : nullptr; }
+int64_t gorder_ndx_group_size(const GorderNdx *n, int32_t g) { return n && g >= 0 && g < (int32_t)n->names.size() ? (int64_t)n->atoms[g].size() : -1; }
+const int32_t *gorder_ndx_group_atoms(const GorderNdx *n, int32_t g) { return n && g >= 0 && g < (int32_t)n->names.size() ? n->atoms[g].data() : nullptr; }
+int32_t gorder_ndx_find(const GorderNdx *n, const char *name) { return n && name ? n->find(name) : -1; }
+
+// LeafletClassification::FromNdx (leaflets.rs:1030-1215, NdxClassification): one ndx file per assignment frame; a molecule is
+// Upper if its head is in the group `upper`, else Lower if it is in `lower`, else AssignmentNotFound.  table[f][m] for the
+// n_molecules heads (absolute atom indices, in molecule order) = GORDER_UPPER / GORDER_LOWER: GorderMolType.manual_leaflets of
+// GORDER_LEAFLET_MANUAL (a run longer than n_files assignment frames then fails with GORDER_ERR_MANUAL_LEAFLET_FRAME =
+// NdxLeafletClassificationError::FrameNotFound).  Invalid / repeated group names matter only when they are one of the two.
+int gorder_leaflets_from_ndx(const char *const *ndx_files, int32_t n_files, int32_t n_atoms, const char *upper, const char *lower,
+                             const int32_t *heads, int32_t n_molecules, uint8_t *table) {
+    if (n_files < 0 || n_molecules < 0 || !upper || !lower || (n_files > 0 && !ndx_files) || (n_molecules > 0 && (!heads || !table))) return GORDER_ERR_INVALID_ARGUMENT;
+    std::vector<char> in_up, in_lo;
+    for (int f = 0; f < n_files; f++) {
+        GorderNdx nd;
+        if (int rc = gtopo::parse_ndx(ndx_files[f], n_atoms, nd)) return rc;
+        for (const auto &nm : nd.invalid)
+            if (nm == upper || nm == lower) { g_topology_error = "group name '" + nm + "' specified in an ndx file '" + ndx_files[f] + "' is invalid and cannot be used"; return GORDER_ERR_NDX_INVALID_NAME; }
+        for (const auto &nm : nd.duplicate)
+            if (nm == upper || nm == lower) { g_topology_error = "multiple groups named '" + nm + "' are specified in an ndx file '" + ndx_files[f] + "'"; return GORDER_ERR_NDX_DUPLICATE_NAME; }
+        const int gu = nd.find(upper), gl = nd.find(lower);
+        if (gu < 0 || gl < 0) {
+            g_topology_error = std::string("group '") + (gu < 0 ? upper : lower) + "' expected to specify " + (gu < 0 ? "upper" : "lower") + "-leaflet lipids not found in the ndx file '" + ndx_files[f] + "'";
+            return GORDER_ERR_NDX_GROUP_NOT_FOUND;
+        }
+        int hi = 0;
+        for (int m = 0; m < n_molecules; m++) hi = std::max(hi, heads[m]);
+        for (int a : nd.atoms[gu]) hi = std::max(hi, a);
+        for (int a : nd.atoms[gl]) hi = std::max(hi, a);
+        in_up.assign((size_t)hi + 1, 0); in_lo.assign((size_t)hi + 1, 0);
+        for (int a : nd.atoms[gu]) in_up[a] = 1;
+        for (int a : nd.atoms[gl]) in_lo[a] = 1;
+        for (int m = 0; m < n_molecules; m++) {
+            if (heads[m] < 0) return GORDER_ERR_INVALID_ARGUMENT;
+            if (in_up[heads[m]]) table[(size_t)f * n_molecules + m] = GORDER_UPPER;
+            else if (in_lo[heads[m]]) table[(size_t)f * n_molecules + m] = GORDER_LOWER;
+            else {
+                g_topology_error = "could not assign molecule " + std::to_string(m) + " (head atom index " + std::to_string(heads[m]) + ") to a leaflet: not in '" + upper + "' nor '" + lower + "' of '" + ndx_files[f] + "'";
+                return GORDER_ERR_NDX_ASSIGNMENT_NOT_FOUND;
+            }
+        }
+    }
+    return GORDER_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // classification
 // ---------------------------------------------------------------------------------------------------------------------------
 struct GorderClassification {

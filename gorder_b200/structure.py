@@ -181,3 +181,33 @@ class System:
         if rc != abi.OK:
             _fail(rc)
         return self._collect(h, abi.KIND_UA)
+
+
+def read_ndx(path: str, n_atoms: int = -1):
+    """GROMACS index file -> {group name: atom indices from 0} (groan_rs ``Groups::from_ndx``)."""
+    L = lib()
+    h = C.c_void_p()
+    rc = L.gorder_ndx_open(path.encode(), n_atoms, C.byref(h))
+    if rc != abi.OK:
+        _fail(rc)
+    try:
+        out = {}
+        for g in range(L.gorder_ndx_n_groups(h)):
+            n = L.gorder_ndx_group_size(h, g)
+            p = L.gorder_ndx_group_atoms(h, g)
+            out[L.gorder_ndx_group_name(h, g).decode()] = np.array([p[i] for i in range(n)], dtype=np.int32)
+        return out
+    finally:
+        L.gorder_ndx_close(h)
+
+
+def leaflets_from_ndx(ndx_files: Sequence[str], heads, upper: str = "Upper", lower: str = "Lower", n_atoms: int = -1) -> np.ndarray:
+    """``LeafletClassification::from_ndx`` (leaflets.rs:1030-1215) for the molecules whose head atoms are ``heads`` (absolute
+    indices, molecule order): uint8 table [len(ndx_files)][len(heads)] for ``MolType.manual_leaflets``."""
+    hd = np.ascontiguousarray(heads, dtype=np.int32).reshape(-1)
+    files = (C.c_char_p * len(ndx_files))(*[f.encode() for f in ndx_files])
+    table = np.zeros((len(ndx_files), hd.size), np.uint8)
+    rc = lib().gorder_leaflets_from_ndx(files, len(ndx_files), n_atoms, upper.encode(), lower.encode(), _p(hd), hd.size, _p(table))
+    if rc != abi.OK:
+        _fail(rc)
+    return table

@@ -123,7 +123,12 @@ enum {
     GORDER_ERR_TOPOLOGY_NO_UA_CARBONS = 49,    /* TopologyError::NoUACarbons */
     GORDER_ERR_NO_TOPOLOGY = 50,               /* ConfigError::NoTopology: structure without bonds and no bonds file */
     GORDER_ERR_PDB_TOPOLOGY = 51,              /* ConfigError::InvalidPdbTopology: repeated atom numbers make CONECT ambiguous */
-    GORDER_ERR_STRUCTURE_FORMAT = 52           /* ConfigError::InvalidStructureFormat, or a GRO / PDB file that does not parse */
+    GORDER_ERR_STRUCTURE_FORMAT = 52,          /* ConfigError::InvalidStructureFormat, or a GRO / PDB file that does not parse */
+    GORDER_ERR_NDX_PARSE = 53,                 /* NdxLeafletClassificationError::CouldNotParse (groan ParseNdxError) */
+    GORDER_ERR_NDX_INVALID_NAME = 54,          /* NdxLeafletClassificationError::InvalidName */
+    GORDER_ERR_NDX_DUPLICATE_NAME = 55,        /* NdxLeafletClassificationError::DuplicateName */
+    GORDER_ERR_NDX_GROUP_NOT_FOUND = 56,       /* NdxLeafletClassificationError::GroupNotFound */
+    GORDER_ERR_NDX_ASSIGNMENT_NOT_FOUND = 57   /* NdxLeafletClassificationError::AssignmentNotFound(molecule, head) */
 };
 
 /* ---- setup ------------------------------------------------------------------------------ */
@@ -493,6 +498,22 @@ const char *gorder_classification_item_name(const GorderClassification *c, int32
 const char *gorder_classification_warning(const GorderClassification *c);   /* "" when molecule types were found */
 int32_t gorder_classification_n_atoms_rel(const GorderClassification *c, int32_t type);
 const int32_t *gorder_classification_atoms_rel(const GorderClassification *c, int32_t type);   /* relative indices of the molecule's atoms */
+
+/* GROMACS index files (groan_rs Groups::from_ndx): `[ name ]` headers, atom numbers from 1.  A name with one of '"&|!@()<>= is
+ * refused (its atoms are skipped), a repeated name replaces the earlier group; n_atoms < 0 skips the range check of the numbers. */
+typedef struct GorderNdx GorderNdx;
+int gorder_ndx_open(const char *path, int32_t n_atoms, GorderNdx **out);
+void gorder_ndx_close(GorderNdx *n);
+int32_t gorder_ndx_n_groups(const GorderNdx *n);
+const char *gorder_ndx_group_name(const GorderNdx *n, int32_t group);
+int64_t gorder_ndx_group_size(const GorderNdx *n, int32_t group);
+const int32_t *gorder_ndx_group_atoms(const GorderNdx *n, int32_t group);   /* from 0, as listed */
+int32_t gorder_ndx_find(const GorderNdx *n, const char *name);              /* -1: no such group */
+/* LeafletClassification::FromNdx (leaflets.rs:1030-1215): one ndx file per assignment frame, groups `upper` / `lower` of head
+ * atoms -> table[n_files][n_molecules] of GORDER_UPPER / GORDER_LOWER for the heads (absolute atom indices, molecule order) of
+ * one molecule type: GorderMolType.manual_leaflets under GORDER_LEAFLET_MANUAL.  Errors as NdxLeafletClassificationError. */
+int gorder_leaflets_from_ndx(const char *const *ndx_files, int32_t n_files, int32_t n_atoms, const char *upper, const char *lower,
+                             const int32_t *heads, int32_t n_molecules, uint8_t *table);
 
 /* The host stage of gorder_gpu_run_xtc_device without a GPU: walks the control bits of frames first .. first + count - 1
  * and reports per frame its groups (one "large" atom + its run of small ones) and the bookmarks the kernel would get.  A

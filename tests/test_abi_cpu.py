@@ -15,7 +15,7 @@ HEADER = os.path.join(ROOT, "include", "gorder_b200.h")
 
 
 def test_library_exports_every_declared_symbol():
-    decl = set(re.findall(r"\b(gorder_(?:gpu|xtc|results|comm|system|classify|classification|topology)_[a-z_]+)\s*\(", open(HEADER).read()))
+    decl = set(re.findall(r"\b(gorder_(?:gpu|xtc|results|comm|system|classify|classification|topology|ndx|leaflets)_[a-z_]+)\s*\(", open(HEADER).read()))
     assert decl == set(SYMBOLS), decl ^ set(SYMBOLS)
     L = lib()
     for s in SYMBOLS:
