@@ -274,10 +274,13 @@ def run_ours(args):
             engine.broadcast_leaflets(comm, 0)
         return r if rank == 0 else fn()
 
+    eng.profile(True)   # the warm-up launches are the burst measurement: the first milliseconds of load after an idle period
     first_step(eng, step)
     for _ in range(W - 1):
         step()
     eng.sync()
+    burst_ms, burst_n = eng.profile_read()
+    eng.profile_read_normals()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -462,6 +465,10 @@ def run_ours(args):
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": hot_kernel_name(s.setup), "launches_timed": hot_n, "avg_launch_ms": hot_ms / max(hot_n, 1),
                          "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
                          "step_share": (hot_ms / (ms - reduce_ms)) if ms else None,
+                         # the same kernel in the warm-up steps, i.e. before the board reaches its power cap
+                         "burst": ({"avg_launch_ms": burst_ms / burst_n, "launches": burst_n, "achieved": launch_bytes / (burst_ms / burst_n * 1e-3) / 1e9,
+                                    "frac": launch_bytes / (burst_ms / burst_n * 1e-3) / 1e9 / peak, "what": "warm-up steps, first launches after idle"}
+                                   if burst_n and burst_ms > 0 else None),
                          "note": ("in-step duration, CUDA events around every launch of the kernel on the engine's stream (gorder_gpu_profile); "
                                   + ("speculative Global leaflets: no centre pre-pass" if spec_stats["enabled"] else "rank 0"))},
             # dynamic normals: the neighbour search + PCA of every lipid (normal.rs:160-199) dominates the step.  It is a gather through

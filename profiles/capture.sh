@@ -2,7 +2,8 @@
 # Re-captures the evidence under profiles/ on a B200 box.  Run from the repo root THROUGH gpurun, e.g.
 #   gpurun --timeout 1500 -- 'bash profiles/capture.sh r02 bench'
 # Writes into gpurun_out/ (scratch); copy what should be judged into profiles/<tag>_*.
-# Parts: tests | bench | workloads | launches | ncu | ncu_ua | ncu_aa | xtc     (ONE ncu part per gpurun call)
+# Parts: tests | bench | workloads | launches | ncu | ncu_ua | ncu_aa | ncu_dyn | ncu_maps | xtc | multi     (ONE ncu part per gpurun call)
+# multi: under `gpurun --gpus N`: the 2-GPU engine tests, the strong-scaling bench and the platform's H2D ceiling
 set -u
 TAG=${1:-rXX}; PART=${2:-bench}; OUT=gpurun_out; mkdir -p $OUT
 want() { [ "$PART" = "$1" ]; }
@@ -34,8 +35,15 @@ ncu_full() {   # $1 kernel regex, $2 name, rest: bench arguments
 if want ncu; then ncu_full bond_fast_kernel bond_fast_kernel --steps 2 --warmup 1 --windows 1 --frames 128 --cpu-seconds 0.2 --xtc-frames 0 --e2e-steps 1; fi
 if want ncu_ua; then ncu_full ua_fast_kernel ua_fast_kernel --workload ua --steps 2 --warmup 1 --windows 1 --cpu-seconds 0.2 --xtc-frames 0 --e2e-steps 1; fi
 if want ncu_aa; then ncu_full bond_fast_kernel bond_fast_kernel_aa_small --workload aa --steps 2 --warmup 1 --windows 1 --cpu-seconds 0.2 --xtc-frames 0 --e2e-steps 1; fi
-if want ncu_dyn; then ncu_full dynamic_normal_cell_kernel dynamic_normal_cell_kernel --workload ves --steps 2 --warmup 1 --windows 1 --cpu-seconds 0.2 --xtc-frames 0 --e2e-steps 1; fi
+if want ncu_dyn; then ncu_full dynamic_normal_sorted_kernel dynamic_normal_sorted_kernel --workload cg_dyn --steps 2 --warmup 1 --windows 1 --cpu-seconds 0.2 --xtc-frames 0 --e2e-steps 1; fi
 if want xtc; then         # launch list of the device-decode leg
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_xtc_device.csv \
       python bench.py --steps 1 --warmup 1 --windows 1 --frames 32 --cpu-seconds 0.2 --xtc-frames 64 > $OUT/${TAG}_ncu_xtc.log 2>&1
+fi
+if want ncu_maps; then ncu_full bond_order_kernel aa_maps_kernel --workload aa_maps --steps 2 --warmup 1 --windows 1 --cpu-seconds 0.2 --xtc-frames 0 --e2e-steps 1; fi
+if want multi; then
+  N=${3:-2}
+  python -m pytest tests/test_gpu_multi.py -m gpu -q 2>&1 | tail -4 | tee $OUT/${TAG}_pytest_multi_${N}gpu.txt
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N > $OUT/${TAG}_bench_${N}gpu.json 2> $OUT/${TAG}_bench_${N}gpu.err
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 profiles/h2d_scaling.py > $OUT/${TAG}_h2d_scaling_${N}gpu.json 2>/dev/null
 fi
