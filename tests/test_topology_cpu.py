@@ -412,3 +412,21 @@ def test_reference_gro_pdb_match_python_readers():
     g = System.from_file(os.path.join(REF, "cg.gro"), os.path.join(REF, "cg.bnd"))
     assert c.atoms()[0] == g.atoms()[0] and np.abs(c.positions() - g.positions()).max() < 1e-3
     assert np.allclose(c.box9(), g.box9(), atol=1e-3)
+
+
+def test_weird_molecules_fixture():
+    """tests_aa.rs:1961-2035 (test_aa_order_maps_basic_weird_molecules): molecules that share a name and span several residues.
+    The reference names its order-map files after the molecule types and bonds the classifier finds; those names, from
+    multiple_resid_same_name.tpr with heavy atoms `name C1A C3A C1B C3B` and hydrogens `name D2A C4A C2B C4B`."""
+    s = System.from_tpr(os.path.join(TPR, "multiple_resid_same_name.tpr"))
+    names, resn, *_ = s.atoms()
+    sel = lambda want: [i for i in range(s.n_atoms) if resn[i] in ("POPC", "POPE") and names[i] in want]
+    mts = s.classify_bonds(abi.KIND_AA, sel(("C1A", "C3A", "C1B", "C3B")), sel(("D2A", "C4A", "C2B", "C4B")))
+    got = {m.name: ["--".join(part.replace(" (", "-").replace(")", "").replace(" ", "-") for part in b.split(" - ")) for b in m.bond_names] for m in mts}
+    assert got == {
+        "POPC-POPE1": ["POPC-C1A-4--POPC-D2A-5", "POPC-D2A-5--POPE-C3A-6", "POPE-C3A-6--POPE-C4A-7", "POPE-C1B-8--POPE-C2B-9", "POPE-C2B-9--POPE-C3B-10",
+                       "POPE-C3B-10--POPE-C4B-11"],
+        "POPC-POPE2": ["POPC-C1A-4--POPC-D2A-5", "POPC-D2A-5--POPE-C3A-6", "POPE-C3A-6--POPE-C4A-7", "POPE-C3B-10--POPE-C4B-11"],
+        "POPC": ["POPC-C1A-4--POPC-D2A-5", "POPC-D2A-5--POPC-C3A-6", "POPC-C3A-6--POPC-C4A-7", "POPC-C1B-8--POPC-C2B-9", "POPC-C2B-9--POPC-C3B-10",
+                 "POPC-C3B-10--POPC-C4B-11"],
+    }, got
