@@ -113,7 +113,8 @@ namespace gtopo {
 
 struct MolTypeTpr {
     std::vector<std::string> atom_name, res_name;
-    std::vector<int32_t> res_nr, atomic_number;
+    std::vector<int32_t> res_nr, res_index, atomic_number;
+    int n_res = 0;
     std::vector<float> mass, charge;
     std::vector<std::pair<int, int>> bonds;
 };
@@ -185,8 +186,9 @@ static void parse_tpr(Reader &r, GorderSystem &sys) {
         for (size_t j = 0; j < nres; j++) { rname.push_back(symstr()); rnr.push_back(r.i32()); (void)r.uchar_(); }
         for (size_t a = 0; a < nr; a++) {
             if (resind[a] < 0 || (size_t)resind[a] >= nres) throw ParseError{"residue index out of range"};
-            mt.res_name.push_back(rname[resind[a]]); mt.res_nr.push_back(rnr[resind[a]]);
+            mt.res_name.push_back(rname[resind[a]]); mt.res_nr.push_back(rnr[resind[a]]); mt.res_index.push_back(resind[a]);
         }
+        mt.n_res = (int)nres;
         for (int ft : file_ft) {             // do_ilists
             const size_t len = r.count();
             if (len > (r.n - r.p) / 4) throw ParseError{"file ends inside a record"};
@@ -211,6 +213,10 @@ static void parse_tpr(Reader &r, GorderSystem &sys) {
     }
     const size_t nmolblock = r.count();
     sys.n_atoms = 0;
+    // Residue numbers as GROMACS shows them (mtop_util: molecule types of ONE residue are renumbered consecutively over the
+    // molecules of the system, starting behind the largest number a multi-residue type stores; the others keep theirs)
+    long long next_res = 1;
+    for (const auto &mt : mts) if (mt.n_res > 1) for (int v : mt.res_nr) next_res = std::max<long long>(next_res, (long long)v + 1);
     for (size_t bidx = 0; bidx < nmolblock; bidx++) {   // do_molblock
         const size_t type = r.count(), nmol = r.count();
         (void)r.i32();   // atoms per molecule
@@ -223,18 +229,18 @@ static void parse_tpr(Reader &r, GorderSystem &sys) {
         for (size_t mol = 0; mol < nmol; mol++) {
             const int base = sys.n_atoms;
             for (size_t a = 0; a < na; a++) {
-                sys.name.push_back(mt.atom_name[a]); sys.resname.push_back(mt.res_name[a]); sys.resid.push_back(mt.res_nr[a]);
+                sys.name.push_back(mt.atom_name[a]); sys.resname.push_back(mt.res_name[a]);
+                sys.resid.push_back(mt.n_res <= 1 ? (int32_t)(next_res + (long long)mol * mt.n_res + mt.res_index[a]) : mt.res_nr[a]);
                 sys.atomic_number.push_back(mt.atomic_number[a]); sys.mass.push_back(mt.mass[a]); sys.charge.push_back(mt.charge[a]);
             }
             sys.n_atoms += (int)na;
             sys.bonded.resize(sys.n_atoms);
             for (const auto &bd : mt.bonds) if (bd.first != bd.second) sys.add_bond(base + bd.first, base + bd.second);
         }
+        if (mt.n_res <= 1) next_res += (long long)nmol * mt.n_res;
     }
     if (r.i32() != natoms || sys.n_atoms != natoms) throw ParseError{"atom counts of header, topology and molecule blocks disagree"};
     sys.finish_bonds();
-    // residue numbers: GROMACS renumbers the residues of consecutive molecules unless the molecule type has several residues
-    // ... (mtop_util: maxres_renum); the reference reads the numbers through minitpr -> kept as stored per molecule type.
     if (ver >= 103 && r.boolean()) {      // intermolecular interactions: one more set of lists over global indices
         for (int ft : file_ft) {
             const size_t len = r.count();
