@@ -410,11 +410,13 @@ void gorder_xtc_close(GorderXtc *x);
 int gorder_gpu_run_xtc(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride,
                        int64_t frame_index0, int32_t n_threads, int32_t batch_frames, double *decode_seconds);
 
-/* The same with the decode on the DEVICE: host threads only copy the compressed frames into pinned batches
- * and bookmark every 32nd group of the bit stream (control bits only; 4-6 B per atom cross PCIe instead of 12);
+/* The same with the decode on the DEVICE: host threads only copy the compressed frames into pinned batches (4-5 B per
+ * atom cross PCIe instead of 12); xtc_walk_kernel follows the control bits of every frame and bookmarks every 32nd group,
  * xtc_decode_kernel unpacks the groups in parallel into the engine's staging frames.  Coordinates are bit-identical to the
- * host decoder's.  Frames the device path does not cover (> 64 bits per triple, <= 9 atoms) take the host decoder.
- * bytes_h2d (optional): bytes that crossed PCIe. */
+ * host decoder's.  Frames the device path does not cover (> 64 bits per triple, <= 9 atoms) take the host decoder; a stream
+ * the walk cannot follow is skipped and reported as a deferred error (GORDER_ERR_INVALID_ARGUMENT, detail = the frame's
+ * number in the file) by the next gorder_gpu_sync / gorder_gpu_finish.  batch_frames >= 128 hides the walk (a few ms per
+ * batch whatever its size) behind the copies.  bytes_h2d (optional): bytes that crossed PCIe. */
 int gorder_gpu_run_xtc_device(GorderHandle *h, GorderXtc *x, const int32_t *atom_of_slot, int64_t first, int64_t last, int64_t stride,
                               int64_t frame_index0, int32_t n_threads, int32_t batch_frames, int64_t *bytes_h2d);
 
