@@ -276,6 +276,8 @@ def run_ours(args):
 
     eng.profile(True)   # the warm-up launches are the burst measurement: the first milliseconds of load after an idle period
     first_step(eng, step)
+    eng.sync()
+    eng.profile_read()   # ... without the very first step (clock ramp-up from idle, first-touch of the accumulators)
     for _ in range(W - 1):
         step()
     eng.sync()
@@ -467,7 +469,7 @@ def run_ours(args):
                          "step_share": (hot_ms / (ms - reduce_ms)) if ms else None,
                          # the same kernel in the warm-up steps, i.e. before the board reaches its power cap
                          "burst": ({"avg_launch_ms": burst_ms / burst_n, "launches": burst_n, "achieved": launch_bytes / (burst_ms / burst_n * 1e-3) / 1e9,
-                                    "frac": launch_bytes / (burst_ms / burst_n * 1e-3) / 1e9 / peak, "what": "warm-up steps, first launches after idle"}
+                                    "frac": launch_bytes / (burst_ms / burst_n * 1e-3) / 1e9 / peak, "what": "warm-up steps after the first one: the first milliseconds of load after an idle period"}
                                    if burst_n and burst_ms > 0 else None),
                          "note": ("in-step duration, CUDA events around every launch of the kernel on the engine's stream (gorder_gpu_profile); "
                                   + ("speculative Global leaflets: no centre pre-pass" if spec_stats["enabled"] else "rank 0"))},
