@@ -487,7 +487,10 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
     const bool overlap = inline_leaf && !spec && !planes_on_main && !h->nvec && !h->sw.no_overlap;
     // speculative path on resident frames: the bond kernels of consecutive batches run back to back on the main stream,
     // the setup of the next batch and the tail (repair + fold) of the previous one run beside them
-    const bool pipelined = spec && !planes_on_main && !s.collect_leaflets && !h->sw.no_overlap;
+    // ... and so do runs without leaflets (nothing of a batch depends on the previous one but the totals, which only the
+    // post stream touches): for small systems the setup and the fold are a quarter of a batch (S-UA, S-AA-small)
+    const bool plain = !h->leaf && !h->nvec;
+    const bool pipelined = (spec || plain) && !planes_on_main && !s.collect_leaflets && !h->sw.no_overlap;
     cudaStream_t sp = (overlap || pipelined) ? h->stream_pre : h->stream;
     cudaStream_t spost = pipelined ? h->stream_post : h->stream;
     if (!pipelined && h->post_used) CK(cudaStreamWaitEvent(h->stream, h->ev_post_any, 0));   // totals are touched by one stream at a time
