@@ -484,7 +484,7 @@ int process_batch(GorderHandle *h, const float *d_planes, const float *d_box, co
         if (checked >= 16 && repaired * 8ull > checked) h->spec_disabled = true;   // thick membrane / thin water: pre-pass is cheaper
     }
     const bool spec = inline_leaf && h->spec_ok && !h->spec_disabled;
-    const bool overlap = inline_leaf && !spec && !planes_on_main && !h->nvec && !h->sw.no_overlap;
+    const bool overlap = inline_leaf && !spec && !planes_on_main && !h->sw.no_overlap;   // (with per-molecule normals too: they are computed on the main stream, in order)
     // speculative path on resident frames: the bond kernels of consecutive batches run back to back on the main stream,
     // the setup of the next batch and the tail (repair + fold) of the previous one run beside them
     // ... and so do runs without leaflets (nothing of a batch depends on the previous one but the totals, which only the
