@@ -1000,7 +1000,7 @@ __device__ __forceinline__ void normal_drain(const int *lst, int nl, const float
         d.x = min_image_g(__fsub_rn(q.x, ref.x), a.L[0], a.half[0], g0);
         d.y = min_image_g(__fsub_rn(q.y, ref.y), a.L[1], a.half[1], g1);
         d.z = min_image_g(__fsub_rn(q.z, ref.z), a.L[2], a.half[2], g2);
-        if (norm_ref(d) < radius) {
+        if (radius_less(dot_ref(d, d), radius)) {   // norm_ref(d) < radius, the IEEE square root only next to the sphere
             s.cnt++;
             s.sx += d.x; s.sy += d.y; s.sz += d.z;
             s.xx += (double)d.x * d.x; s.xy += (double)d.x * d.y; s.xz += (double)d.x * d.z;
@@ -1063,13 +1063,13 @@ __global__ void __launch_bounds__(128) dynamic_normal_sorted_kernel(DeviceView v
                 const float4 *qp = srt + kb;
                 for (int kk = kb; kk < ke; kk++, qp++) {
                     const float4 q = __ldg(qp);
-                    if (quick && __float_as_int(q.w) >= 0) {
-                        const float ex = q.x - rsx, ey = q.y - rsy, ez = q.z - rsz;
-                        if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > r2hi) continue;
-                    }
-                    if (nl == kNormCap) { normal_drain(lst, nl, srt, ref, a, g0, g1, g2, radius, acc); nl = 0; }
+                    // no branch on the outcome: the slot behind the list is always free, the index is written there and
+                    // kept by advancing the count (the accepting branch ran with a quarter of the lanes)
+                    const float ex = q.x - rsx, ey = q.y - rsy, ez = q.z - rsz;
+                    const bool far = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > r2hi;
                     lst[nl * 128] = kk;
-                    nl++;
+                    nl += (far && quick && __float_as_int(q.w) >= 0) ? 0 : 1;
+                    if (nl == kNormCap) { normal_drain(lst, nl, srt, ref, a, g0, g1, g2, radius, acc); nl = 0; }
                 }
             }
         }

@@ -31,9 +31,9 @@ __device__ __forceinline__ float fmod_near(float x, float L) {
 __device__ __noinline__ float min_image_slow(float d, float L, float half) {
     if (!(L > 0.0f)) return d;
     float t = __fadd_rn(d, half);
-    t = fmodf(t, L);
+    t = fmod_near(t, L);      // exact for |t| < 2L (one subtraction), fmodf beyond: the same bits either way
     float u = __fadd_rn(t, L);
-    u = fmodf(u, L);
+    u = fmod_near(u, L);
     return __fsub_rn(u, half);
 }
 
