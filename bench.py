@@ -94,10 +94,10 @@ WORKLOADS = {
     "cg": ("S-CG: CGOrder Martini bilayer, Global leaflets every frame (BASELINE configs[1]); 20 steps of 5120 frames = the 100k-frame trajectory", N_LIPIDS, 256, 20),
     "aa": ("S-AA-small: AAOrder POPC-like, 64 C-H bond types, static z (BASELINE configs[0] shape)", 256, 2048, 4),
     "ua": ("S-UA: UAOrder Berger-like, 64 virtual C-H, error blocks (BASELINE configs[2])", 256, 2048, 4),
-    "aa_maps": ("S-AA-large: AAOrder 4096 lipids, Global leaflets, XY order maps 0.1 nm, cylinder r=8 nm (BASELINE configs[3])", 4096, 128, 4),
-    "cg_dyn": ("S-DYN: CGOrder flat bilayer, dynamic PCA normals r=2 nm, Global leaflets (BASELINE configs[4] kernel mix)", 100000, 8, 4),
+    "aa_maps": ("S-AA-large: AAOrder 4096 lipids, Global leaflets, XY order maps 0.1 nm, cylinder r=8 nm (BASELINE configs[3])", 4096, 148, 4),   # 148 frames x 8 tiles = two whole waves of the map kernel
+    "cg_dyn": ("S-DYN: CGOrder flat bilayer, dynamic PCA normals r=2 nm, Global leaflets (BASELINE configs[4] kernel mix)", 100000, 32, 2),   # 32 = the engine's batch limit with dynamic normals
     "ves": ("S-VES: CGOrder Martini vesicle (100 000 lipids, outer radius 51 nm, box 114 nm), dynamic PCA normals r=2 nm, "
-            "spherical-clustering leaflets assigned once (BASELINE configs[4])", 100000, 16, 8),
+            "spherical-clustering leaflets assigned once (BASELINE configs[4])", 100000, 32, 4),
 }
 
 
