@@ -15,7 +15,7 @@ SYMBOLS = [
     "gorder_gpu_submit_native", "gorder_gpu_submit_native_device", "gorder_gpu_reserve_frames", "gorder_gpu_set_leaflets", "gorder_gpu_sync",
     "gorder_gpu_result_sizes", "gorder_gpu_finish", "gorder_gpu_accumulator_block", "gorder_gpu_stats",
     "gorder_gpu_read_block", "gorder_gpu_write_block", "gorder_gpu_profile", "gorder_gpu_profile_read", "gorder_gpu_profile_read_normals",
-    "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_stream",
+    "gorder_gpu_speculation_stats", "gorder_gpu_fence", "gorder_gpu_wave_frames", "gorder_gpu_stream",
     "gorder_xtc_open", "gorder_xtc_info", "gorder_xtc_read", "gorder_xtc_write", "gorder_xtc_close", "gorder_xtc_scan", "gorder_gpu_run_xtc", "gorder_gpu_run_xtc_device",
     "gorder_results_order", "gorder_results_convergence", "gorder_results_map", "gorder_gpu_last_error", "gorder_gpu_error_detail", "gorder_gpu_destroy", "gorder_gpu_version",
     "gorder_topology_last_error", "gorder_system_from_tpr", "gorder_system_from_file", "gorder_system_from_arrays", "gorder_system_free", "gorder_system_n_atoms", "gorder_system_n_bonds",
@@ -142,6 +142,8 @@ def lib() -> C.CDLL:
     L.gorder_leaflets_from_ndx.restype = C.c_int
     L.gorder_gpu_fence.argtypes = [vp]
     L.gorder_gpu_fence.restype = C.c_int
+    L.gorder_gpu_wave_frames.argtypes = [vp, C.POINTER(i32)]
+    L.gorder_gpu_wave_frames.restype = C.c_int
     L.gorder_gpu_stream.argtypes = [vp]
     L.gorder_gpu_stream.restype = vp
     L.gorder_gpu_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]

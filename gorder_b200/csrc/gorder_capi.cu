@@ -1553,6 +1553,26 @@ int gorder_gpu_speculation_stats(GorderHandle *h, int32_t *enabled, int64_t *fra
     return GORDER_OK;
 }
 
+// Frames per batch for which the grid of the accumulation kernel (tiles x frames) is a whole number of waves: the kernels
+// are compiled for a fixed number of resident CTAs per SM, and a last, partly filled wave costs as much as a full one
+// (S-AA-large: 128 -> 148 frames per batch = +15 % in the kernel).  0: no preference (persistent kernel).
+int gorder_gpu_wave_frames(GorderHandle *h, int32_t *frames) {
+    if (!h || !frames) return GORDER_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
+    *frames = 0;
+    if (h->ua && h->ua_fast_ok) return GORDER_OK;
+    int per_sm = 4;                                                   // bond_fast_kernel<.., 256>, bond_order_kernel, ua_order_kernel
+    const bool fast = h->fast_ok && !h->sw.no_fast;
+    if (fast && h->mpt == 1) per_sm = 16;                             // bond_fast_kernel<.., 64>
+    else if (!fast && !h->ua && h->extra) per_sm = GORDER_EXTRA_MINB;
+    else if (!fast && !h->ua && h->nvec) per_sm = GORDER_NVEC_MINB;
+    const long long slots = (long long)per_sm * h->n_sm;
+    long long a = slots, b = std::max(1, h->n_chunks);
+    while (b) { const long long t = a % b; a = b; b = t; }            // gcd
+    *frames = (int32_t)std::min<long long>(slots / a, 1 << 20);
+    return GORDER_OK;
+}
+
 int gorder_gpu_fence(GorderHandle *h) {
     if (!h) return GORDER_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::recursive_mutex> lock(h->mu);

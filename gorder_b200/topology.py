@@ -75,6 +75,12 @@ class SystemTopology:
         fn = lib().gorder_gpu_submit_native_device if native else lib().gorder_gpu_submit_device
         self._check(fn(self._h, C.c_void_p(d_ptr), C.c_void_p(d_box), _ptr(fi), n_frames))
 
+    def wave_frames(self) -> int:
+        """Frames per batch that make the accumulation kernel's grid a whole number of waves (0: no preference)."""
+        n = C.c_int32(0)
+        self._check(lib().gorder_gpu_wave_frames(self._h, C.byref(n)))
+        return int(n.value)
+
     def run_xtc(self, xtc, atom_of_slot=None, first: int = 0, last: int | None = None, stride: int = 1, n_threads: int = 0,
                 batch_frames: int = 0, frame_index0: int = 0) -> float:
         """``read_trajectory`` for an open :class:`gorder_b200.xtc.XtcFile`: host threads decode, the engine analyses.

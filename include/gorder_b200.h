@@ -524,6 +524,10 @@ int gorder_leaflets_from_ndx(const char *const *ndx_files, int32_t n_files, int3
  * be NULL. */
 int gorder_xtc_scan(GorderXtc *x, int64_t first, int64_t count, int32_t *n_groups /* [count] */, int32_t *n_bookmarks /* [count] */);
 
+/* Tuning hint: the smallest number of frames per batch for which the grid of the accumulation kernel (tiles x frames) is a
+ * whole number of waves on this device; multiples of it avoid a partly filled last wave.  0 = no preference. */
+int gorder_gpu_wave_frames(GorderHandle *h, int32_t *frames);
+
 /* Human-readable detail of the last error of this handle (offending atom index etc.). */
 int gorder_gpu_last_error(GorderHandle *h, char *buf, size_t len);
 

@@ -410,3 +410,21 @@ def test_baseline_size_s_ua_error_blocks_against_oracle():
     for key in ("total", "upper", "lower"):
         a, b = getattr(cg_.average, key), getattr(cr_.average, key)
         assert abs(a.value - b.value) < 1e-5 and abs(a.error - b.error) < 1e-5, key
+
+
+def test_wave_frames_hint():
+    """gorder_gpu_wave_frames: tiles x frames is a whole number of waves of the accumulation kernel for the hinted batch."""
+    from gorder_b200 import SystemTopology
+    import torch
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    for s, per_sm in ((synthetic.s_cg(4096, leaflet_mode=abi.LEAFLET_GLOBAL), 4),                      # K1f, 256-thread CTAs, 4 tiles of 1024
+                      (synthetic.s_aa(256, n_water=0), 16),                                            # K1f, 64-thread CTAs, one tile
+                      (synthetic.s_cg(4096, leaflet_mode=abi.LEAFLET_GLOBAL, geom_kind=abi.GEOM_SPHERE, geom_ref_kind=abi.GEOMREF_BOX_CENTER,
+                                      geom_dims=(3.0,)), 4)):                                           # geometry: two molecules per lane, 8 tiles
+        eng = SystemTopology(s.setup)
+        f = eng.wave_frames()
+        eng.close()
+        assert f > 0 and (per_sm * n_sm) % f == 0 or f == per_sm * n_sm, (f, per_sm)
+    eng = SystemTopology(synthetic.s_ua(256).setup)
+    assert eng.wave_frames() == 0     # persistent kernel: no preference
+    eng.close()
