@@ -1566,7 +1566,9 @@ int gorder_gpu_wave_frames(GorderHandle *h, int32_t *frames) {
     if (fast && h->mpt == 1) per_sm = 16;                             // bond_fast_kernel<.., 64>
     else if (!fast && !h->ua && h->extra) per_sm = GORDER_EXTRA_MINB;
     else if (!fast && !h->ua && h->nvec) per_sm = GORDER_NVEC_MINB;
-    const long long slots = (long long)per_sm * h->n_sm;
+    int n_sm = h->n_sm;
+    if (n_sm <= 0) { cudaSetDevice(h->device); CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device)); }
+    const long long slots = (long long)per_sm * n_sm;
     long long a = slots, b = std::max(1, h->n_chunks);
     while (b) { const long long t = a % b; a = b; b = t; }            // gcd
     *frames = (int32_t)std::min<long long>(slots / a, 1 << 20);
