@@ -431,3 +431,40 @@ def test_weird_molecules_fixture():
         "POPC": ["POPC-C1A-4--POPC-D2A-5", "POPC-D2A-5--POPC-C3A-6", "POPC-C3A-6--POPC-C4A-7", "POPC-C1B-8--POPC-C2B-9", "POPC-C2B-9--POPC-C3B-10",
                  "POPC-C3B-10--POPC-C4B-11"],
     }, got
+
+
+def test_text_readers_fuzz(tmp_path):
+    """GRO / PDB / bonds / ndx readers on damaged files: an error code or a result, never a crash."""
+    from gorder_b200.structure import read_ndx
+    rng = np.random.default_rng(11)
+    texts = {"s.gro": GRO, "s.pdb": PDB, "s.ndx": "[ Upper ]\n1 2 3\n[ Lower ]\n4\n", "s.bnd": "1 2 3\n2 3\n# c\n4 1\n"}
+    base = System.from_arrays(["A"] * 4, ["R"] * 4)
+    for it in range(400):
+        fn = list(texts)[it % 4]
+        b = bytearray(texts[fn].encode())
+        for _ in range(int(rng.integers(1, 6))):
+            k = int(rng.integers(0, 3))
+            if not b:
+                break
+            pos = int(rng.integers(0, len(b)))
+            if k == 0:
+                b[pos] = int(rng.integers(0, 256))
+            elif k == 1:
+                del b[pos:pos + int(rng.integers(1, 20))]
+            else:
+                b[pos:pos] = bytes(rng.integers(32, 127, int(rng.integers(1, 12)), dtype=np.uint8))
+        p = tmp_path / fn
+        p.write_bytes(bytes(b))
+        try:
+            if fn == "s.ndx":
+                read_ndx(str(p), 4)
+            elif fn == "s.bnd":
+                base.read_bonds(str(p))
+            else:
+                s = System.from_file(str(p), None if fn == "s.pdb" else str(tmp_path / "ok.bnd") if (tmp_path / "ok.bnd").exists() else None)
+                s.atoms(); s.bonds(); s.close()
+        except abi.GorderError as e:
+            assert e.code in (abi.ERR_STRUCTURE_FORMAT, abi.ERR_NO_TOPOLOGY, abi.ERR_PDB_TOPOLOGY, abi.ERR_NDX_PARSE, abi.ERR_BONDS_PARSE,
+                              abi.ERR_BONDS_ATOM_NOT_FOUND, abi.ERR_BONDS_SELF, abi.ERR_IO), e
+        except UnicodeDecodeError:
+            pass   # a name that is no longer UTF-8 (the C side handed it over byte for byte)
