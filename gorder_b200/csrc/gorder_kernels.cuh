@@ -26,6 +26,11 @@ __device__ __forceinline__ void raise_error(const DeviceView &v, int code, long 
     if (atomicCAS(v.err, 0, code) == 0) *v.err_detail = detail;
 }
 
+// DRAM -> L2 prefetch of a contiguous run (one instruction, one thread); 16-byte aligned address, size a multiple of 16
+__device__ __forceinline__ void l2_prefetch_run(const float *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // L2 eviction-priority hint (createpolicy + ld.global.L2::cache_hint): the centre passes want the axis planes to
 // survive from pass 0 to pass 1 (evict_last).
 __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
@@ -1503,7 +1508,24 @@ __device__ __forceinline__ void bond_order_body(const DeviceView &v, const float
     Vec<MPT> x1, y1, z1, x2, y2, z2;
 #pragma unroll
     for (int j = 0; j < MPT; j++) x1.v[j] = y1.v[j] = z1.v[j] = x2.v[j] = y2.v[j] = z2.v[j] = 0.0f;
+    // As in K1f: one lane per CTA asks L2 for the CTA's slices of the planes the bonds two iterations ahead will read (the
+    // variants with geometry / maps / per-molecule normals stall on these loads: long scoreboard led their ncu profiles)
+    constexpr int kAhead = 2;
+    const float *tile0 = planes + (size_t)f * v.frame_floats + mol_offset(td, ch.first_mol);
+    const unsigned slice_bytes = (unsigned)(BLOCK * MPT * sizeof(float));
+    auto prefetch_bond = [&](int bb) {
+        if (threadIdx.x != 0 || bb >= nb) return;
+        const BondItem it = s_bonds[bb];
+        if ((it.a_off & 3) == 0) {
+            const float *pa = tile0 + (it.a_off & ~15);
+            l2_prefetch_run(pa, slice_bytes); l2_prefetch_run(pa + mpad, slice_bytes); l2_prefetch_run(pa + 2 * mpad, slice_bytes);
+        }
+        const float *pb = tile0 + it.b_off;
+        l2_prefetch_run(pb, slice_bytes); l2_prefetch_run(pb + mpad, slice_bytes); l2_prefetch_run(pb + 2 * mpad, slice_bytes);
+    };
+    if (EXTRA || NVEC) for (int bb = 0; bb < kAhead; bb++) prefetch_bond(bb);
     for (int b = 0; b < nb; b++) {
+        if (EXTRA || NVEC) prefetch_bond(b + kAhead);
         {
             const BondItem bi = s_bonds[b];
             // low bits of a_off: 1 = first atom is the previous bond's first atom, 2 = ... second atom;
